@@ -1,0 +1,156 @@
+/* lkb200.h - C ABI of the B200-native periodogram-and-detrending engine.
+ *
+ * The reference (lightkurve, pure Python) has no FFI: its de-facto boundary is
+ * five Python call sites into astropy/scipy/numpy.  Each entry
+ * point below replaces one of those call sites; the ctypes stub a lightkurve
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns an int status: 0 = LKB_OK, < 0 = error; a
+ *    thread-local message is available from lkb_last_error().
+ *  - all buffers are caller-allocated and caller-owned.  `mem` says where they
+ *    live: LKB_MEM_HOST (plain host pointers; the call stages through the
+ *    library's device workspace and is synchronous) or LKB_MEM_DEVICE (device
+ *    pointers on the current device; the call is asynchronous on `stream`).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *    stream).  No torch types anywhere.
+ *  - ragged batches are CSR: int64 offsets[B+1] into the concatenated arrays.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns LKB_E_CUDA.
+ */
+#ifndef LKB200_H
+#define LKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LKB_OK             0
+#define LKB_E_ARG         -1   /* bad argument */
+#define LKB_E_CUDA        -2   /* CUDA runtime error / no device */
+#define LKB_E_OOM         -3   /* device allocation failed */
+#define LKB_E_SINGULAR    -4   /* normal equations singular (numpy LinAlgError analogue) */
+#define LKB_E_UNSUPPORTED -5   /* shape outside what the kernels support */
+
+#define LKB_MEM_HOST   0
+#define LKB_MEM_DEVICE 1
+
+#define LKB_DTYPE_F32 0
+#define LKB_DTYPE_F64 1
+
+/* Lomb-Scargle output normalisation (periodogram.py:969-975) */
+#define LKB_LS_NORM_PSD_RAW   0  /* astropy normalization="psd": 0.5*N*(YC^2/CC+YS^2/SS)   */
+#define LKB_LS_NORM_PSD_SCALE 1  /* raw * norm_scale[b]   (lightkurve "psd": 2/(N*oversample*fs)) */
+#define LKB_LS_NORM_AMPLITUDE 2  /* sqrt(raw)*sqrt(4/N)   (lightkurve "amplitude")          */
+
+/* shared-grid Lomb-Scargle contraction algorithm */
+#define LKB_LS_ALGO_AUTO     0   /* tcgen05 when shapes allow, else SIMT */
+#define LKB_LS_ALGO_SIMT     1   /* fp32 CUDA-core tiled contraction */
+#define LKB_LS_ALGO_TCGEN05  2   /* split-fp16 tcgen05.mma, fp32 TMEM accumulators */
+
+/* BLS objective (astropy BoxLeastSquares.power objective=) */
+#define LKB_BLS_LIKELIHOOD 0
+#define LKB_BLS_SNR        1
+
+/* ---- library management ------------------------------------------------ */
+const char* lkb_last_error(void);
+int lkb_version(void);                 /* 1000*major + minor */
+int lkb_device_count(void);            /* number of visible CUDA devices (0 if none) */
+int lkb_init(int device);              /* bind the calling process to `device`, create the workspace pool */
+int lkb_shutdown(void);                /* free the workspace pool */
+int lkb_sm_count(void);                /* multiprocessor count of the bound device */
+/* counters: number of kernels this library launched since init (bench gpu_launches) */
+int64_t lkb_launch_count(void);
+
+/* ---- Lomb-Scargle ------------------------------------------------------- */
+/* K1: ragged batch, one (time, flux) pair per light curve; replaces
+ *   LombScargle(time, flux, normalization="psd").power(frequency, method)
+ * at /root/reference/src/lightkurve/periodogram.py:961-964 plus the rescale at
+ * :969-975.  Computes the exact floating-mean sums (astropy "slow" math).
+ *   t            [offsets[B]] fp64 days (any origin; shifted internally)
+ *   y            [offsets[B]] flux, y_dtype F32 or F64; no NaNs (caller drops
+ *                them as periodogram.py:785-790 does)
+ *   freq         fp64 cycles/day.  freq_offsets == NULL: one grid of F bins
+ *                shared by all light curves; else CSR [B+1] per-LC grids.
+ *   norm_scale   [B] or NULL (required for LKB_LS_NORM_PSD_SCALE)
+ *   power        fp32, [B,F] (shared grid) or CSR like freq.
+ */
+int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B,
+                 const double* freq, const int64_t* freq_offsets, int64_t F,
+                 int normalization, const double* norm_scale,
+                 float* power, int mem, void* stream);
+
+/* K2: batch sharing ONE cadence grid (BASELINE config 2); same math, but the
+ * sin/cos design matrix is synthesised once per (frequency, cadence) tile and
+ * contracted against all B light curves.
+ *   t [N] fp64, y [B,N] row-major (y_dtype), freq [F] fp64, power [B,F] fp32.
+ *   norm_scale: scalar pointer (one value, all LCs share N) or NULL.
+ */
+int lkb_ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N,
+                        const double* freq, int64_t F,
+                        int normalization, const double* norm_scale,
+                        float* power, int mem, void* stream, int algo);
+
+/* ---- Box Least Squares --------------------------------------------------- */
+/* K3: replaces BoxLeastSquares(t, y, dy).power(period, duration, objective,
+ * method="fast", oversample) at periodogram.py:1161-1169.  Inputs are the RAW
+ * time/flux (the call subtracts min(t) and median(y) itself like astropy's
+ * core.py); dy == NULL means unit weights.  period [P] ascending or not,
+ * duration [D]; outputs fp64 [B,P] each; transit_time is absolute (t_ref added).
+ * best_bins (nullable) int32 [B,P,2] = (start bin n, duration in bins) of the
+ * winning box - the quantity the parity tests require bit-exact.
+ */
+int lkb_bls_power(const double* t, const double* y, const double* dy, const int64_t* offsets, int B,
+                  const double* period, int64_t P, const double* duration, int D,
+                  int oversample, int objective,
+                  double* power, double* depth, double* depth_err, double* duration_out,
+                  double* transit_time, double* depth_snr, double* log_likelihood,
+                  int32_t* best_bins, int mem, void* stream);
+
+/* Debug/parity entry: the per-sample bin index of bls.c for ONE period,
+ * ind[n] = (int)(fabs(fmod(t[n]-min_t, period))/bin_duration)+1, evaluated by the
+ * same device function the search kernel uses. */
+int lkb_bls_bin_index(const double* t_rel, int64_t N, double min_t, double period,
+                      double bin_duration, int32_t* ind, int mem, void* stream);
+
+/* ---- flatten (Savitzky-Golay detrend) ------------------------------------ */
+/* K4: replaces the body of LightCurve.flatten, lightcurve.py:996-1070
+ * (scipy savgol_filter :1040 + interp1d :1053 + the sigma-clip loop).
+ *   time, flux, flux_err  [offsets[B]] fp64 (flux_err may be NULL)
+ *   exclude_mask          uint8 [offsets[B]] or NULL; 1 = do not use (mask=True in lightkurve)
+ *   break_tolerance       NaN disables gap splitting (break_tolerance=None)
+ *   outputs flat, flat_err, trend  fp64 [offsets[B]]  (flat_err may be NULL)
+ */
+int lkb_flatten(const double* time, const double* flux, const double* flux_err,
+                const uint8_t* exclude_mask, const int64_t* offsets, int B,
+                int window_length, int polyorder, double break_tolerance, int niters, double sigma,
+                double* flat, double* flat_err, double* trend, int mem, void* stream);
+
+/* ---- RegressionCorrector -------------------------------------------------- */
+/* K5: replaces _fit_coefficients + the correct() loop,
+ * correctors/regressioncorrector.py:127-189,244-279 (dense branch).
+ *   X            [N,K] row-major fp64, shared by the batch (x_batched=0) or [B,N,K] (x_batched=1)
+ *   y            [B,N] fp64;  flux_err [B,N] or NULL (NULL = ones, :157-160)
+ *   cadence_mask uint8 [B,N] or NULL (1 = use)
+ *   prior_mu, prior_sigma [K] fp64 (sigma may be +inf) or both NULL
+ *   outputs: coeff [B,K], model [B,N] (median-subtracted, :278-279),
+ *            outlier_mask uint8 [B,N]; status_out int32 [B] (0 or LKB_E_SINGULAR per LC, nullable)
+ */
+int lkb_regress(const double* X, int x_batched, const double* y, const double* flux_err,
+                const uint8_t* cadence_mask, const double* prior_mu, const double* prior_sigma,
+                int B, int64_t N, int K, double clip_sigma, int niters,
+                double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out,
+                int mem, void* stream);
+
+/* ---- batched order statistics (K6) ---------------------------------------- */
+/* nanmedian and nanstd (ddof=0) per light curve: np.nanmedian / np.nanstd as used by
+ * normalize (lightcurve.py:1253-1254) and flatten (:1003-1005). out_median/out_std [B]. */
+int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B,
+                      double* out_median, double* out_std, int mem, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKB200_H */

@@ -1,0 +1,195 @@
+// extern "C" surface of liblkb200.so (declared in include/lkb200.h) + context/workspace.
+#include <stdarg.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace lkb {
+
+static thread_local char t_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+struct Ctx {
+  bool inited = false;
+  int device = -1;
+  int sms = 0;
+  void* ptr[WS_NSLOTS] = {nullptr};
+  size_t cap[WS_NSLOTS] = {0};
+};
+static Ctx g_ctx;
+static std::mutex g_mu;
+
+int ensure_device() {
+  if (g_ctx.inited) {
+    cudaError_t e = cudaSetDevice(g_ctx.device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", g_ctx.device, cudaGetErrorString(e)); return LKB_E_CUDA; }
+    return LKB_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); liblkb200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    cudaGetLastError();
+    return LKB_E_CUDA;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return LKB_E_CUDA; }
+  if (prop.major != 10) {
+    set_error("liblkb200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return LKB_E_CUDA;
+  }
+  g_ctx.device = dev;
+  g_ctx.sms = prop.multiProcessorCount;
+  g_ctx.inited = true;
+  return LKB_OK;
+}
+
+int sm_count() { return g_ctx.sms; }
+
+int ws_get(int slot, size_t bytes, void** out) {
+  if (slot < 0 || slot >= WS_NSLOTS) { set_error("bad workspace slot"); return LKB_E_ARG; }
+  if (bytes == 0) bytes = 16;
+  if (g_ctx.cap[slot] < bytes) {
+    if (g_ctx.ptr[slot]) {
+      cudaDeviceSynchronize();   // buffer may still be in use by an earlier async call
+      cudaFree(g_ctx.ptr[slot]);
+      g_ctx.ptr[slot] = nullptr;
+      g_ctx.cap[slot] = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&g_ctx.ptr[slot], want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+      return LKB_E_OOM;
+    }
+    g_ctx.cap[slot] = want;
+  }
+  *out = g_ctx.ptr[slot];
+  return LKB_OK;
+}
+
+// implemented in the kernel translation units
+int ls_power_ragged(const double*, const void*, int, const int64_t*, int, const double*, const int64_t*, int64_t,
+                    int, const double*, float*, int, cudaStream_t);
+int ls_power_shared(const double*, const void*, int, int, int64_t, const double*, int64_t, int, const double*,
+                    float*, int, cudaStream_t, int);
+int bls_power(const double*, const double*, const double*, const int64_t*, int, const double*, int64_t,
+              const double*, int, int, int, double*, double*, double*, double*, double*, double*, double*, int32_t*,
+              int, cudaStream_t);
+int bls_bin_index(const double*, int64_t, double, double, double, int32_t*, int, cudaStream_t);
+int flatten(const double*, const double*, const double*, const uint8_t*, const int64_t*, int, int, int, double, int,
+            double, double*, double*, double*, int, cudaStream_t);
+int regress(const double*, int, const double*, const double*, const uint8_t*, const double*, const double*, int,
+            int64_t, int, double, int, double*, double*, uint8_t*, int32_t*, int, cudaStream_t);
+int nanmedian_std(const double*, const int64_t*, int, double*, double*, int, cudaStream_t);
+
+}  // namespace lkb
+
+using namespace lkb;
+
+extern "C" {
+
+const char* lkb_last_error(void) { return t_err; }
+int lkb_version(void) { return 1000 * 0 + 1; }
+
+int lkb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lkb_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int n = lkb_device_count();
+  if (n <= 0) { set_error("lkb_init: no CUDA device; liblkb200 has no CPU fallback"); return LKB_E_CUDA; }
+  if (device < 0 || device >= n) { set_error("lkb_init: device %d out of range [0,%d)", device, n); return LKB_E_ARG; }
+  if (g_ctx.inited && g_ctx.device != device) {
+    set_error("lkb_init: already bound to device %d (one device per process)", g_ctx.device);
+    return LKB_E_ARG;
+  }
+  LKB_CUDA_CHECK(cudaSetDevice(device));
+  return ensure_device();
+}
+
+int lkb_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_ctx.inited) return LKB_OK;
+  cudaSetDevice(g_ctx.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < WS_NSLOTS; ++i) {
+    if (g_ctx.ptr[i]) cudaFree(g_ctx.ptr[i]);
+    g_ctx.ptr[i] = nullptr;
+    g_ctx.cap[i] = 0;
+  }
+  g_ctx.inited = false;
+  return LKB_OK;
+}
+
+int lkb_sm_count(void) { return g_ctx.inited ? g_ctx.sms : 0; }
+int64_t lkb_launch_count(void) { return g_launches; }
+
+int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B, const double* freq,
+                 const int64_t* freq_offsets, int64_t F, int normalization, const double* norm_scale, float* power,
+                 int mem, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return ls_power_ragged(t, y, y_dtype, offsets, B, freq, freq_offsets, F, normalization, norm_scale, power, mem,
+                         (cudaStream_t)stream);
+}
+
+int lkb_ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
+                        int normalization, const double* norm_scale, float* power, int mem, void* stream, int algo) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return ls_power_shared(t, y, y_dtype, B, N, freq, F, normalization, norm_scale, power, mem, (cudaStream_t)stream,
+                         algo);
+}
+
+int lkb_bls_power(const double* t, const double* y, const double* dy, const int64_t* offsets, int B,
+                  const double* period, int64_t P, const double* duration, int D, int oversample, int objective,
+                  double* power, double* depth, double* depth_err, double* duration_out, double* transit_time,
+                  double* depth_snr, double* log_likelihood, int32_t* best_bins, int mem, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return bls_power(t, y, dy, offsets, B, period, P, duration, D, oversample, objective, power, depth, depth_err,
+                   duration_out, transit_time, depth_snr, log_likelihood, best_bins, mem, (cudaStream_t)stream);
+}
+
+int lkb_bls_bin_index(const double* t_rel, int64_t N, double min_t, double period, double bin_duration,
+                      int32_t* ind, int mem, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return bls_bin_index(t_rel, N, min_t, period, bin_duration, ind, mem, (cudaStream_t)stream);
+}
+
+int lkb_flatten(const double* time, const double* flux, const double* flux_err, const uint8_t* exclude_mask,
+                const int64_t* offsets, int B, int window_length, int polyorder, double break_tolerance, int niters,
+                double sigma, double* flat, double* flat_err, double* trend, int mem, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return flatten(time, flux, flux_err, exclude_mask, offsets, B, window_length, polyorder, break_tolerance, niters,
+                 sigma, flat, flat_err, trend, mem, (cudaStream_t)stream);
+}
+
+int lkb_regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
+                const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma,
+                int niters, double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, int mem,
+                void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return regress(X, x_batched, y, flux_err, cadence_mask, prior_mu, prior_sigma, B, N, K, clip_sigma, niters, coeff,
+                 model, outlier_mask, status_out, mem, (cudaStream_t)stream);
+}
+
+int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B, double* out_median, double* out_std, int mem,
+                      void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return nanmedian_std(x, offsets, B, out_median, out_std, mem, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// K3: Box Least Squares, the search lightkurve obtains from astropy at
+//   /root/reference/src/lightkurve/periodogram.py:1161-1169
+//   (BoxLeastSquares(t, y, dy).power(period, duration, objective, method="fast", oversample)).
+// Algorithm = astropy bls.c (restated in oracle/bls_c.c): per trial period, fold the samples
+// into bins of width min(duration)/oversample, wrap-pad, inclusive prefix sum, then scan every
+// (duration, start bin) box and keep the FIRST strict maximum of the objective with y_out >= y_in.
+//
+// B200 mapping: one WARP per (light curve, period).  A CTA = BLS_WARPS warps working on
+// consecutive periods of the SAME light curve, so the (t, w*y, w) sample tiles are staged into
+// shared memory once per CTA and re-used by every warp.  Each warp owns a private
+// shared-memory histogram (plain `+=`, no atomics): 32 consecutive samples have non-decreasing
+// bin indices except at a period wrap, so a warp-segmented reduction leaves exactly one
+// writer per bin (wrap blocks are split into monotone pieces).
+//
+// Bit-exactness: the bin index (int)(fabs(fmod(t - min_t, P)) / bin_duration) + 1 is evaluated
+// with an exact fmod (fma remainder + fix-up) and an IEEE fp64 division, so it equals the C
+// result bit for bit.  This file is compiled with -fmad=false so that no a*b+c is contracted
+// where the C code (built with -ffp-contract=off) has two roundings.  The binned sums are
+// accumulated in a different order than the sequential C loop => equal to ~1e-13 relative,
+// not bitwise; exact ties between boxes that cover the same samples are preserved by the
+// scan construction (see bls_cumsum).
+#include "common.cuh"
+#include "select.cuh"
+#include <float.h>
+#include <vector>
+
+namespace lkb {
+
+constexpr int BLS_WARPS = 8;
+constexpr int BLS_TILE = 1024;
+
+// exact fmod for finite x, p != 0, |x/p| < 2^50 (true for any real light curve)
+__device__ __forceinline__ double bls_fmod(double x, double p, double inv_p) {
+  const double a = fabs(x), b = fabs(p);
+  if (a < b) return x;
+  double q = trunc(a * inv_p);
+  double r = fma(-q, b, a);
+  if (r < 0.0) { q -= 1.0; r = fma(-q, b, a); }
+  else if (r >= b) { q += 1.0; r = fma(-q, b, a); }
+  return copysign(r, x);
+}
+
+__device__ __forceinline__ int bls_bin(double t, double min_t, double period, double inv_period, double bin_duration) {
+  const double r = fabs(bls_fmod(t - min_t, period, inv_period));
+  return (int)(r / bin_duration) + 1;
+}
+
+__global__ void bls_bin_index_kernel(const double* __restrict__ t, int64_t N, double min_t, double period,
+                                     double bin_duration, int32_t* __restrict__ ind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) ind[i] = bls_bin(t[i], min_t, period, 1.0 / fabs(period), bin_duration);
+}
+
+// ---- prologue: astropy core.py power(): t - min(t), y - median(y), ivar = 1/dy^2 ----------
+struct BlsLcInfo {
+  double t_ref, sum_y, sum_ivar, min_t;
+};
+
+__global__ void __launch_bounds__(256)
+bls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, const double* __restrict__ dy,
+                const int64_t* __restrict__ offsets, double* __restrict__ trel, double* __restrict__ wy,
+                double* __restrict__ iv, BlsLcInfo* __restrict__ info) {
+  __shared__ SelSmem sm;
+  const int b = blockIdx.x;
+  const int64_t o = offsets[b], n = offsets[b + 1] - o;
+  if (n <= 0) return;
+  // t_ref = min(t)
+  double mn = __longlong_as_double(0x7ff0000000000000ll);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mn = fmin(mn, t[o + i]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = sm.red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) x = fmin(x, sm.red[w]);
+    sm.red[32] = x;
+  }
+  __syncthreads();
+  const double t_ref = sm.red[32];
+  __syncthreads();
+  const double* yy = y + o;
+  const double med = block_nanmedian([&](int64_t i) { return yy[i]; }, n, sm);
+  double sy = 0.0, si = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double w = dy ? 1.0 / (dy[o + i] * dy[o + i]) : 1.0;
+    const double v = (yy[i] - med) * w;
+    trel[o + i] = t[o + i] - t_ref;
+    wy[o + i] = v;
+    iv[o + i] = w;
+    sy += v;
+    si += w;
+  }
+  const double sum_y = block_sum(sy, sm.red);
+  const double sum_i = block_sum(si, sm.red);
+  if (threadIdx.x == 0) {
+    info[b].t_ref = t_ref;
+    info[b].sum_y = sum_y;
+    info[b].sum_ivar = sum_i;
+    info[b].min_t = 0.0;   // min(t - t_ref)
+  }
+}
+
+// ---- per-warp pieces ------------------------------------------------------------------------
+// Add the 32 samples held one per lane into the warp's histogram. key < 0 => lane inactive.
+__device__ __forceinline__ void bls_warp_bin(int key, double vy, double vi, double* hy, double* hi, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int prev = __shfl_up_sync(full, key, 1);
+  const bool head = (lane == 0) || (key != prev);
+  const bool wrap = (lane != 0) && (key < prev) && (key >= 0);
+  const unsigned headmask = __ballot_sync(full, head);
+  const unsigned wrapmask = __ballot_sync(full, wrap);
+  const unsigned le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+  const int start = 31 - __clz(headmask & le);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double uy = __shfl_up_sync(full, vy, o);
+    const double ui = __shfl_up_sync(full, vi, o);
+    if (lane - o >= start) { vy += uy; vi += ui; }
+  }
+  const bool tail = ((headmask >> 1) | 0x80000000u) >> lane & 1u;
+  if (wrapmask == 0) {
+    if (tail && key >= 0) { hy[key] += vy; hi[key] += vi; }
+  } else {
+    // split into monotone pieces so that equal keys are contiguous within a piece
+    const int piece = __popc(wrapmask & le);
+    const int npieces = __popc(wrapmask) + 1;
+    for (int q = 0; q < npieces; ++q) {
+      if (tail && key >= 0 && piece == q) { hy[key] += vy; hi[key] += vi; }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+}
+
+// Inclusive prefix sum over h[0..n] (n+1 entries), in place.  Each lane scans a contiguous chunk
+// sequentially; chunk offsets are a SEQUENTIAL prefix (lane 0) so that an empty bin leaves the
+// running sum bitwise unchanged also across chunk boundaries (tie preservation).
+__device__ __forceinline__ void bls_cumsum(double* h, int n_entries, double* scratch, int lane) {
+  const int L = (n_entries + 31) / 32;
+  const int lo = min(lane * L, n_entries), hi = min(lo + L, n_entries);
+  double run = 0.0;
+  for (int i = lo; i < hi; ++i) { run += h[i]; h[i] = run; }
+  scratch[lane] = run;
+  __syncwarp();
+  if (lane == 0) {
+    double off = 0.0;
+    for (int l = 0; l < 32; ++l) { const double tot = scratch[l]; scratch[l] = off; off += tot; }
+  }
+  __syncwarp();
+  const double off = scratch[lane];
+  if (lane > 0)
+    for (int i = lo; i < hi; ++i) h[i] = off + h[i];
+  __syncwarp();
+}
+
+struct BlsBest {
+  double obj, depth, depth_err, snr, ll;
+  int k, n, dur;
+};
+
+__global__ void __launch_bounds__(BLS_WARPS * 32)
+bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy, const double* __restrict__ iv,
+                  const int64_t* __restrict__ offsets, const BlsLcInfo* __restrict__ info,
+                  const double* __restrict__ period, int64_t p_begin, int64_t p_end, int64_t P,
+                  const double* __restrict__ duration, const int* __restrict__ dur_bins, int D, double bin_duration,
+                  int oversample, int objective, int hist_stride, double* __restrict__ g_hist,
+                  double* __restrict__ o_power, double* __restrict__ o_depth, double* __restrict__ o_depth_err,
+                  double* __restrict__ o_duration, double* __restrict__ o_ttime, double* __restrict__ o_snr,
+                  double* __restrict__ o_ll, int32_t* __restrict__ o_bins) {
+  extern __shared__ __align__(16) unsigned char bls_smem[];
+  double* s_t = reinterpret_cast<double*>(bls_smem);
+  double* s_wy = s_t + BLS_TILE;
+  double* s_iv = s_wy + BLS_TILE;
+  double* s_scr = s_iv + BLS_TILE;                 // BLS_WARPS * 32
+  double* s_hist = s_scr + BLS_WARPS * 32;         // BLS_WARPS * 2 * hist_stride (unless g_hist)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int64_t o = offsets[b], n = offsets[b + 1] - o;
+  if (n <= 0) return;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t p = p_begin + (int64_t)blockIdx.x * nwarps + warp;
+  const bool active = p < p_end;
+  const double per = active ? period[p] : 1.0;
+  const double inv_per = 1.0 / fabs(per);
+  const int n_bins = (int)ceil(per / bin_duration) + oversample;
+  const BlsLcInfo li = info[b];
+
+  double *hy, *hi;
+  if (g_hist) {
+    const size_t slot = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nwarps + warp;
+    hy = g_hist + slot * 2 * (size_t)hist_stride;
+  } else {
+    hy = s_hist + (size_t)warp * 2 * hist_stride;
+  }
+  hi = hy + hist_stride;
+  if (active)
+    for (int i = lane; i <= n_bins; i += 32) { hy[i] = 0.0; hi[i] = 0.0; }
+
+  for (int64_t c0 = 0; c0 < n; c0 += BLS_TILE) {
+    const int cnt = (int)min((int64_t)BLS_TILE, n - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      s_t[i] = trel[o + c0 + i];
+      s_wy[i] = wy[o + c0 + i];
+      s_iv[i] = iv[o + c0 + i];
+    }
+    __syncthreads();
+    if (active) {
+      for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int i = i0 + lane;
+        int key = -1;
+        double vy = 0.0, vi = 0.0;
+        if (i < cnt) {
+          key = bls_bin(s_t[i], li.min_t, per, inv_per, bin_duration);
+          vy = s_wy[i];
+          vi = s_iv[i];
+        }
+        bls_warp_bin(key, vy, vi, hy, hi, lane);
+      }
+    }
+  }
+  if (!active) return;
+  __syncwarp();
+
+  // wrap-pad: mean[n_bins - oversample + (n-1)] = mean[n], n = 1..oversample (no overlap)
+  for (int i = lane + 1; i <= oversample; i += 32) {
+    const int ind = n_bins - oversample + (i - 1);
+    hy[ind] = hy[i];
+    hi[ind] = hi[i];
+  }
+  __syncwarp();
+  double* scr = s_scr + warp * 32;
+  bls_cumsum(hy, n_bins + 1, scr, lane);
+  bls_cumsum(hi, n_bins + 1, scr, lane);
+
+  BlsBest best;
+  best.obj = -INFINITY; best.depth = 0.0; best.depth_err = 0.0; best.snr = 0.0; best.ll = 0.0;
+  best.k = 0x7fffffff; best.n = 0x7fffffff; best.dur = -1;
+  for (int k = 0; k < D; ++k) {
+    const int dur = dur_bins[k];
+    const int n_max = n_bins - dur;
+    for (int nn = lane; nn <= n_max; nn += 32) {
+      double y_in = hy[nn + dur] - hy[nn];
+      const double ivar_in = hi[nn + dur] - hi[nn];
+      double y_out = li.sum_y - y_in;
+      const double ivar_out = li.sum_ivar - ivar_in;
+      if ((ivar_in < DBL_EPSILON) || (ivar_out < DBL_EPSILON)) continue;
+      y_in /= ivar_in;
+      y_out /= ivar_out;
+      const double depth = y_out - y_in;
+      const double depth_err = sqrt(1.0 / ivar_in + 1.0 / ivar_out);
+      const double snr = depth / depth_err;
+      const double ll = 0.5 * ivar_in * (y_out - y_in) * (y_out - y_in);
+      const double obj = objective ? snr : ll;
+      if (y_out >= y_in && obj > best.obj) {
+        best.obj = obj; best.depth = depth; best.depth_err = depth_err; best.snr = snr; best.ll = ll;
+        best.k = k; best.n = nn; best.dur = dur;
+      }
+    }
+  }
+  // first maximum in (duration-major, start-bin-minor) order across lanes
+  double wobj = best.obj;
+  int wk = best.k, wn = best.n, wl = lane;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const double oo = __shfl_xor_sync(0xffffffffu, wobj, s);
+    const int ok = __shfl_xor_sync(0xffffffffu, wk, s);
+    const int on = __shfl_xor_sync(0xffffffffu, wn, s);
+    const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
+    const bool take = (oo > wobj) || (oo == wobj && (ok < wk || (ok == wk && on < wn)));
+    if (take) { wobj = oo; wk = ok; wn = on; wl = ol; }
+  }
+  if (lane == wl) {
+    const int64_t oi = (int64_t)b * P + p;
+    o_power[oi] = best.obj;
+    o_depth[oi] = best.depth;
+    o_depth_err[oi] = best.depth_err;
+    o_snr[oi] = best.snr;
+    o_ll[oi] = best.ll;
+    double bd = 0.0, ph = 0.0;
+    if (best.dur >= 0) {
+      bd = best.dur * bin_duration;
+      ph = bls_fmod(best.n * bin_duration + 0.5 * bd + li.min_t, per, inv_per);
+    }
+    o_duration[oi] = bd;
+    o_ttime[oi] = ph + li.t_ref;
+    if (o_bins) {
+      o_bins[2 * oi] = best.dur >= 0 ? best.n : -1;
+      o_bins[2 * oi + 1] = best.dur;
+    }
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------
+int bls_bin_index(const double* t_rel, int64_t N, double min_t, double period, double bin_duration, int32_t* ind,
+                  int mem, cudaStream_t st) {
+  LKB_REQUIRE(t_rel && ind && N > 0, "lkb_bls_bin_index: null/empty argument");
+  LKB_REQUIRE(period > 0 && bin_duration > 0, "lkb_bls_bin_index: period and bin_duration must be positive");
+  LKB_TRY(ensure_device());
+  const double* d_t = nullptr;
+  int32_t* d_i = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, t_rel, N, &d_t, st));
+  LKB_TRY(stage_out_alloc<int32_t>(mem, WS_OUT0, ind, N, &d_i));
+  bls_bin_index_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_t, N, min_t, period, bin_duration, d_i);
+  LKB_LAUNCH_CHECK();
+  LKB_TRY(stage_out_copy<int32_t>(mem, ind, d_i, N, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+int bls_power(const double* t, const double* y, const double* dy, const int64_t* h_offsets, int B,
+              const double* period, int64_t P, const double* duration, int D, int oversample, int objective,
+              double* power, double* depth, double* depth_err, double* duration_out, double* transit_time,
+              double* depth_snr, double* log_like, int32_t* best_bins, int mem, cudaStream_t st) {
+  LKB_REQUIRE(t && y && h_offsets && period && duration, "lkb_bls_power: null input");
+  LKB_REQUIRE(power && depth && depth_err && duration_out && transit_time && depth_snr && log_like,
+              "lkb_bls_power: null output");
+  LKB_REQUIRE(B > 0 && B <= 65535 && P > 0 && D > 0 && oversample > 0, "lkb_bls_power: bad sizes");
+  LKB_REQUIRE(objective == 0 || objective == 1, "lkb_bls_power: bad objective");
+  LKB_TRY(ensure_device());
+  const int64_t total = h_offsets[B];
+
+  // the period / duration grids are needed on the host for validation and launch shaping
+  std::vector<double> h_per(P), h_dur(D);
+  if (mem == LKB_MEM_HOST) {
+    memcpy(h_per.data(), period, sizeof(double) * P);
+    memcpy(h_dur.data(), duration, sizeof(double) * D);
+  } else {
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_per.data(), period, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_dur.data(), duration, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  double min_period = h_per[0], max_period = h_per[0], min_dur = h_dur[0], max_dur = h_dur[0];
+  for (int64_t i = 0; i < P; ++i) {
+    if (!(h_per[i] == h_per[i]) || isinf(h_per[i])) { set_error("lkb_bls_power: period contains nan/inf"); return LKB_E_ARG; }
+    min_period = fmin(min_period, h_per[i]);
+    max_period = fmax(max_period, h_per[i]);
+  }
+  for (int i = 0; i < D; ++i) {
+    if (!(h_dur[i] == h_dur[i]) || isinf(h_dur[i])) { set_error("lkb_bls_power: duration contains nan/inf"); return LKB_E_ARG; }
+    min_dur = fmin(min_dur, h_dur[i]);
+    max_dur = fmax(max_dur, h_dur[i]);
+  }
+  if (min_period < DBL_EPSILON) { set_error("lkb_bls_power: periods must be positive"); return LKB_E_ARG; }
+  if (max_dur >= min_period || min_dur < DBL_EPSILON) {
+    set_error("The maximum transit duration must be shorter than the minimum period");
+    return LKB_E_ARG;
+  }
+  const double bin_duration = min_dur / (double)oversample;
+  std::vector<int> h_durbins(D);
+  for (int i = 0; i < D; ++i) h_durbins[i] = (int)round(h_dur[i] / bin_duration);
+
+  const double *d_t = nullptr, *d_y = nullptr, *d_dy = nullptr, *d_per = nullptr, *d_dur = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, t, total, &d_t, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN1, y, total, &d_y, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN2, dy, total, &d_dy, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN3, period, P, &d_per, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN4, duration, D, &d_dur, st));
+  int64_t* d_off = nullptr;
+  int* d_durbins = nullptr;
+  LKB_TRY(ws_get_t<int64_t>(WS_A, B + 1, &d_off));
+  LKB_TRY(ws_get_t<int>(WS_B, D, &d_durbins));
+  LKB_CUDA_CHECK(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  LKB_CUDA_CHECK(cudaMemcpyAsync(d_durbins, h_durbins.data(), sizeof(int) * D, cudaMemcpyHostToDevice, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));   // h_durbins is a local
+
+  double *d_trel = nullptr, *d_wy = nullptr, *d_iv = nullptr;
+  BlsLcInfo* d_info = nullptr;
+  LKB_TRY(ws_get_t<double>(WS_C, total, &d_trel));
+  LKB_TRY(ws_get_t<double>(WS_D, total, &d_wy));
+  LKB_TRY(ws_get_t<double>(WS_E, total, &d_iv));
+  LKB_TRY(ws_get_t<BlsLcInfo>(WS_F, B, &d_info));
+
+  const size_t outn = (size_t)B * P;
+  double *o0, *o1, *o2, *o3, *o4, *o5, *o6;
+  int32_t* ob = nullptr;
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT0, power, outn, &o0));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, depth, outn, &o1));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT2, depth_err, outn, &o2));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT3, duration_out, outn, &o3));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT4, transit_time, outn, &o4));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT5, depth_snr, outn, &o5));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT6, log_like, outn, &o6));
+  LKB_TRY(stage_out_alloc<int32_t>(mem, WS_OUT7, best_bins, 2 * outn, &ob));
+
+  bls_prep_kernel<<<B, 256, 0, st>>>(d_t, d_y, d_dy, d_off, d_trel, d_wy, d_iv, d_info);
+  LKB_LAUNCH_CHECK();
+
+  // chunk the period list so that one launch's per-warp histograms have a common size
+  const size_t fixed_smem = (size_t)(3 * BLS_TILE + BLS_WARPS * 32) * sizeof(double);
+  const size_t smem_cap = 200 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(bls_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int64_t p0 = 0;
+  while (p0 < P) {
+    int nb_min = (int)ceil(h_per[p0] / bin_duration) + oversample, nb_max = nb_min;
+    int64_t p1 = p0 + 1;
+    while (p1 < P) {
+      const int nb = (int)ceil(h_per[p1] / bin_duration) + oversample;
+      const int lo = nb < nb_min ? nb : nb_min, hi = nb > nb_max ? nb : nb_max;
+      if (hi > lo + lo / 4 + 64) break;
+      nb_min = lo; nb_max = hi;
+      ++p1;
+    }
+    const int stride = ((nb_max + 1 + 3) / 4) * 4;
+    // warps (= periods) per CTA: as many as fit with their private histograms in shared memory
+    int W = BLS_WARPS;
+    while (W > 1 && fixed_smem + (size_t)W * 2 * stride * sizeof(double) > smem_cap) W >>= 1;
+    size_t hist_bytes = (size_t)W * 2 * stride * sizeof(double);
+    double* g_hist = nullptr;
+    size_t smem = fixed_smem + hist_bytes;
+    if (smem > smem_cap) { W = BLS_WARPS; hist_bytes = (size_t)W * 2 * stride * sizeof(double); }
+    const unsigned gx = (unsigned)((p1 - p0 + W - 1) / W);
+    if (smem > smem_cap) {
+      // histograms do not fit in shared memory: keep them in (L2-resident) global workspace
+      smem = fixed_smem;
+      const size_t need = (size_t)gx * B * hist_bytes;
+      if (need > ((size_t)8 << 30)) {
+        set_error("lkb_bls_power: %d bins per period needs %zu bytes of histogram workspace; "
+                  "use fewer light curves per call", nb_max, need);
+        return LKB_E_UNSUPPORTED;
+      }
+      LKB_TRY(ws_get_t<double>(WS_G, need / sizeof(double), &g_hist));
+    }
+    dim3 grid(gx, (unsigned)B);
+    bls_search_kernel<<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P, d_dur,
+                                                        d_durbins, D, bin_duration, oversample, objective, stride,
+                                                        g_hist, o0, o1, o2, o3, o4, o5, o6, ob);
+    LKB_LAUNCH_CHECK();
+    p0 = p1;
+  }
+
+  LKB_TRY(stage_out_copy<double>(mem, power, o0, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, depth, o1, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, depth_err, o2, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, duration_out, o3, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, transit_time, o4, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, depth_snr, o5, outn, st));
+  LKB_TRY(stage_out_copy<double>(mem, log_like, o6, outn, st));
+  LKB_TRY(stage_out_copy<int32_t>(mem, best_bins, ob, 2 * outn, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+}  // namespace lkb

@@ -1,0 +1,144 @@
+// Shared host/device helpers for liblkb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/lkb200.h"
+
+namespace lkb {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define LKB_CUDA_CHECK(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      lkb::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,           \
+                     cudaGetErrorString(_e));                                       \
+      return (_e == cudaErrorMemoryAllocation) ? LKB_E_OOM : LKB_E_CUDA;            \
+    }                                                                               \
+  } while (0)
+
+#define LKB_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    lkb::g_launches++;                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      lkb::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                     cudaGetErrorString(_e));                                       \
+      return LKB_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define LKB_REQUIRE(cond, msg)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      lkb::set_error("%s (%s:%d)", msg, __FILE__, __LINE__);                        \
+      return LKB_E_ARG;                                                             \
+    }                                                                               \
+  } while (0)
+
+#define LKB_TRY(expr)                                                               \
+  do {                                                                              \
+    int _s = (expr);                                                                \
+    if (_s != LKB_OK) return _s;                                                    \
+  } while (0)
+
+// ---- workspace pool -----------------------------------------------------------
+// Grow-only device buffers keyed by slot; freed by lkb_shutdown().  Not
+// re-entrant across host threads (one engine context per process/device).
+enum Slot {
+  WS_A = 0, WS_B, WS_C, WS_D, WS_E, WS_F, WS_G, WS_H, WS_I, WS_J, WS_K, WS_L, WS_M, WS_N, WS_O, WS_P,
+  WS_IN0, WS_IN1, WS_IN2, WS_IN3, WS_IN4, WS_IN5, WS_IN6, WS_IN7,
+  WS_OUT0, WS_OUT1, WS_OUT2, WS_OUT3, WS_OUT4, WS_OUT5, WS_OUT6, WS_OUT7,
+  WS_NSLOTS
+};
+int ws_get(int slot, size_t bytes, void** out);
+template <typename T>
+inline int ws_get_t(int slot, size_t count, T** out) {
+  void* p = nullptr;
+  int s = ws_get(slot, count * sizeof(T), &p);
+  *out = reinterpret_cast<T*>(p);
+  return s;
+}
+int ensure_device();
+int sm_count();
+
+// Stage a host buffer into the pool (or pass a device pointer through).
+template <typename T>
+inline int stage_in(int mem, int slot, const T* src, size_t count, const T** out, cudaStream_t st) {
+  if (src == nullptr) { *out = nullptr; return LKB_OK; }
+  if (mem == LKB_MEM_DEVICE) { *out = src; return LKB_OK; }
+  T* d = nullptr;
+  LKB_TRY(ws_get_t<T>(slot, count ? count : 1, &d));
+  if (count) LKB_CUDA_CHECK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  *out = d;
+  return LKB_OK;
+}
+template <typename T>
+inline int stage_out_alloc(int mem, int slot, T* dst, size_t count, T** out) {
+  if (dst == nullptr) { *out = nullptr; return LKB_OK; }
+  if (mem == LKB_MEM_DEVICE) { *out = dst; return LKB_OK; }
+  return ws_get_t<T>(slot, count ? count : 1, out);
+}
+template <typename T>
+inline int stage_out_copy(int mem, T* dst, const T* dev, size_t count, cudaStream_t st) {
+  if (dst == nullptr || mem == LKB_MEM_DEVICE || count == 0) return LKB_OK;
+  LKB_CUDA_CHECK(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return LKB_OK;
+}
+
+// ---- device helpers --------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of doubles; result valid in all threads.  `red` needs 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double x = (lane < nw) ? red[lane] : 0.0;
+    x = warp_sum(x);
+    if (lane == 0) red[32] = x;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    long long x = (lane < nw) ? red[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[32] = x;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+}  // namespace lkb

@@ -1,0 +1,512 @@
+// Lomb-Scargle kernels (generalised floating-mean periodogram, Zechmeister & Kuerster 2009),
+// the arithmetic lightkurve obtains from astropy at
+//   /root/reference/src/lightkurve/periodogram.py:961-964  (LombScargle(...).power)
+// followed by lightkurve's own rescale at :969-975 (fused here as the epilogue).
+//
+//   K1  ls_direct_kernel      ragged batch: one warp per group of LS_FPW frequency bins, the
+//                             light curve's (time, flux) tiles staged into shared memory by the
+//                             TMA engine (cp.async.bulk + mbarrier), fp64 phase reduction,
+//                             MUFU sin/cos, fp32 lane partials flushed to fp64 per tile,
+//                             warp-shuffle reduction, fp64 epilogue.
+//   K2a ls_window_kernel      shared cadence grid: the y-independent sums (S, C, CC, SC) -> the
+//                             rotation tau and 1/CC', 1/SS' once per frequency.
+//   K2b ls_shared_simt_kernel shared cadence grid, CUDA-core contraction: sin/cos design-matrix
+//                             tiles synthesised on the fly in shared memory and contracted with
+//                             a [cadence x light-curve] flux tile (register-tiled fp32 FMA).
+//   (K2c, the tcgen05 contraction, lives in ls_tc.cu.)
+#include "common.cuh"
+#include "ptx.cuh"
+#include "ls_common.cuh"
+
+namespace lkb {
+
+// =====================================================================================
+// Prologue: centre the flux the way astropy does (y - dot(w, y), w = 1/N), shift time to
+// the light curve's first cadence (power is shift-invariant; the shift keeps f*t small),
+// convert flux to fp32, and lay each light curve out at a 16-byte aligned offset so that
+// the TMA bulk copies in K1 are legal.
+// =====================================================================================
+template <typename TY>
+__global__ void __launch_bounds__(256)
+ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
+                      const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
+                      double* __restrict__ t_out, float* __restrict__ y_out) {
+  __shared__ double red[33];
+  __shared__ int s_const;
+  const int b = blockIdx.x;
+  const int64_t o = offsets[b], n = offsets[b + 1] - o, po = poffsets[b], np_ = poffsets[b + 1] - po;
+  if (n <= 0) return;
+  double acc = 0.0;
+  if (threadIdx.x == 0) s_const = 1;
+  __syncthreads();
+  const double y0 = (double)y[o];
+  int is_const = 1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = (double)y[o + i];
+    acc += v;
+    if (v != y0) is_const = 0;
+  }
+  if (!is_const) s_const = 0;
+  const double mean = block_sum(acc, red) / (double)n;
+  const bool cst = s_const != 0;
+  const double t0 = t[o];
+  for (int64_t i = threadIdx.x; i < np_; i += blockDim.x) {
+    if (i < n) {
+      t_out[po + i] = t[o + i] - t0;
+      y_out[po + i] = cst ? 0.0f : (float)((double)y[o + i] - mean);
+    } else {
+      t_out[po + i] = 0.0;
+      y_out[po + i] = 0.0f;
+    }
+  }
+}
+
+// Same for a [B, N] matrix sharing one time grid: writes Yc [B, Npad] fp32, zero padded.
+template <typename TY>
+__global__ void __launch_bounds__(256)
+ls_prep_shared_kernel(const TY* __restrict__ y, int64_t N, int64_t Npad, float* __restrict__ y_out,
+                      float* __restrict__ y_absmax) {
+  __shared__ double red[33];
+  __shared__ int s_const;
+  __shared__ float s_max[8];
+  const int b = blockIdx.x;
+  const TY* yr = y + (int64_t)b * N;
+  float* yo = y_out + (int64_t)b * Npad;
+  if (threadIdx.x == 0) s_const = 1;
+  __syncthreads();
+  const double y0 = (double)yr[0];
+  double acc = 0.0;
+  int is_const = 1;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    double v = (double)yr[i];
+    acc += v;
+    if (v != y0) is_const = 0;
+  }
+  if (!is_const) s_const = 0;
+  const double mean = block_sum(acc, red) / (double)N;
+  const bool cst = s_const != 0;
+  float mx = 0.f;
+  for (int64_t i = threadIdx.x; i < Npad; i += blockDim.x) {
+    float v = (i < N && !cst) ? (float)((double)yr[i] - mean) : 0.0f;
+    yo[i] = v;
+    mx = fmaxf(mx, fabsf(v));
+  }
+  if (y_absmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
+      y_absmax[b] = m;
+    }
+  }
+}
+
+// t_out[i] = t[i] - t[0] for i < N, 0 for the padding cadences [N, Npad)
+__global__ void ls_shift_time_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double* __restrict__ t_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Npad) t_out[i] = (i < N) ? (t[i] - t[0]) : 0.0;
+}
+
+// =====================================================================================
+// K1: direct sums, ragged batch.
+// grid = (ceil(Fmax / LS_FPB), B), block = LS_WARPS*32.
+// =====================================================================================
+constexpr int LS_WARPS = 8;
+constexpr int LS_FPW = 4;                       // frequency bins per warp
+constexpr int LS_FPB = LS_WARPS * LS_FPW;       // frequency bins per block
+constexpr int LS_TN = 1536;                     // cadences per shared-memory tile
+
+__global__ void __launch_bounds__(LS_WARPS * 32)
+ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
+                 const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
+                 const double* __restrict__ freq, const int64_t* __restrict__ freq_offsets, int64_t F_shared,
+                 int normalization, const double* __restrict__ norm_scale, float* __restrict__ power) {
+  __shared__ __align__(16) double s_t[2][LS_TN];
+  __shared__ __align__(16) float s_y[2][LS_TN];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int b = blockIdx.y;
+  const int64_t n = offsets[b + 1] - offsets[b];
+  const int64_t po = poffsets[b], np_ = poffsets[b + 1] - po;
+  const int64_t fo = freq_offsets ? freq_offsets[b] : 0;
+  const int64_t F = freq_offsets ? (freq_offsets[b + 1] - fo) : F_shared;
+  const int64_t po_out = freq_offsets ? fo : (int64_t)b * F_shared;
+  const int64_t f_blk = (int64_t)blockIdx.x * LS_FPB;
+  if (f_blk >= F || n <= 0) return;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f_base = f_blk + warp * LS_FPW;
+
+  double fr[LS_FPW];
+#pragma unroll
+  for (int j = 0; j < LS_FPW; ++j) fr[j] = (f_base + j < F) ? freq[fo + f_base + j] : 0.0;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&s_bar[0], 1);
+    ptx::mbar_init(&s_bar[1], 1);
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int ntiles = (int)((np_ + LS_TN - 1) / LS_TN);
+  auto issue = [&](int tile) {
+    const int buf = tile & 1;
+    const int64_t c0 = (int64_t)tile * LS_TN;
+    const uint32_t cnt = (uint32_t)min((int64_t)LS_TN, np_ - c0);   // multiple of 4
+    ptx::mbar_arrive_expect_tx(&s_bar[buf], cnt * 12u);
+    ptx::bulk_g2s(&s_t[buf][0], tws + po + c0, cnt * 8u, &s_bar[buf]);
+    ptx::bulk_g2s(&s_y[buf][0], yws + po + c0, cnt * 4u, &s_bar[buf]);
+  };
+  if (threadIdx.x == 0) issue(0);
+
+  LsSums<double> dsum[LS_FPW];
+#pragma unroll
+  for (int j = 0; j < LS_FPW; ++j) dsum[j].zero();
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (threadIdx.x == 0 && tile + 1 < ntiles) {
+      ptx::fence_proxy_async_smem();
+      issue(tile + 1);
+    }
+    ptx::mbar_wait(&s_bar[buf], (tile >> 1) & 1);
+
+    const int64_t c0 = (int64_t)tile * LS_TN;
+    const int cnt = (int)min((int64_t)LS_TN, n - c0);   // true (unpadded) cadences in this tile
+    LsSums<float> fs[LS_FPW];
+#pragma unroll
+    for (int j = 0; j < LS_FPW; ++j) fs[j].zero();
+    for (int i = lane; i < cnt; i += 32) {
+      const double tt = s_t[buf][i];
+      const float yy = s_y[buf][i];
+#pragma unroll
+      for (int j = 0; j < LS_FPW; ++j) {
+        float s, c;
+        ls_sincos_cycles(fr[j] * tt, s, c);
+        fs[j].add(yy, s, c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LS_FPW; ++j) dsum[j].accumulate(fs[j]);
+    __syncthreads();   // everyone done with `buf` before it is refilled
+  }
+
+#pragma unroll
+  for (int j = 0; j < LS_FPW; ++j) {
+    dsum[j].warp_reduce();
+    if (lane == 0 && f_base + j < F) {
+      const double p = ls_power_from_sums(dsum[j], (double)n);
+      power[po_out + f_base + j] = ls_normalize(p, (double)n, normalization, norm_scale ? norm_scale[b] : 1.0);
+    }
+  }
+}
+
+// =====================================================================================
+// K2a: per-frequency window terms on the shared grid.
+// One warp per frequency; rot[f] = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+ls_window_kernel(const double* __restrict__ t, int64_t N, const double* __restrict__ freq, int64_t F,
+                 float4* __restrict__ rot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (f >= F) return;
+  const double fr = freq[f];
+  LsSums<double> d;
+  d.zero();
+  for (int64_t c0 = 0; c0 < N; c0 += 32 * 64) {
+    LsSums<float> fs;
+    fs.zero();
+    const int64_t c1 = min(N, c0 + 32 * 64);
+    for (int64_t i = c0 + lane; i < c1; i += 32) {
+      float s, c;
+      ls_sincos_cycles(fr * t[i], s, c);
+      fs.add(0.f, s, c);
+    }
+    d.accumulate(fs);
+  }
+  d.warp_reduce();
+  if (lane == 0) {
+    double ct, st, cc, ss;
+    ls_rotation(d, (double)N, ct, st, cc, ss);
+    const double k = 1.0 / (2.0 * (double)N);
+    rot[f] = make_float4((float)ct, (float)st, (float)(k / cc), (float)(k / ss));
+  }
+}
+
+// =====================================================================================
+// K2b: CUDA-core contraction on the shared grid.
+//   Sh[f,b] = sum_n sin(2 pi f t_n) y_b[n],  Ch likewise;  epilogue -> power[b, f].
+// Block tile 128 frequencies x 128 light curves, k-tile 16 cadences, 256 threads,
+// 8x8x{cos,sin} register tile per thread, double-buffered shared memory.
+// =====================================================================================
+constexpr int SG_BM = 128, SG_BN = 128, SG_BK = 16, SG_LDY = SG_BN + 4;
+struct SgStage {
+  float ac[SG_BK][SG_BM];
+  float as[SG_BK][SG_BM];
+  float y[SG_BK][SG_LDY];
+};
+
+__global__ void __launch_bounds__(256)
+ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, const float* __restrict__ yc, int B,
+                      const double* __restrict__ freq, int64_t F, const float4* __restrict__ rot,
+                      int normalization, double norm_scale, float* __restrict__ power) {
+  extern __shared__ __align__(16) unsigned char sg_smem[];
+  SgStage* st = reinterpret_cast<SgStage*>(sg_smem);
+
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * SG_BM;
+  const int b0 = blockIdx.y * SG_BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // design-matrix role: one frequency per thread, 8 cadences of each k-tile
+  const int gf = tid & (SG_BM - 1), gk0 = (tid >> 7) * 8;
+  const double my_f = (f0 + gf < F) ? freq[f0 + gf] : 0.0;
+  // flux-tile role: two float4 per thread
+  const int yr0 = tid >> 2, yq = tid & 3;            // rows yr0 and yr0+64, k-quad yq
+
+  float acc_c[8][8], acc_s[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_c[i][j] = 0.f; acc_s[i][j] = 0.f; }
+
+  float gc[8], gs[8];
+  float4 yv[2];
+  const int nkt = (int)(Npad / SG_BK);
+
+  auto gen = [&](int kt) {
+    const int64_t n0 = (int64_t)kt * SG_BK + gk0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t nn = n0 + i;
+      const double tt = (nn < N) ? t[nn] : 0.0;
+      ls_sincos_cycles(my_f * tt, gs[i], gc[i]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int bb = b0 + yr0 + 64 * r;
+      yv[r] = (bb < B) ? *reinterpret_cast<const float4*>(yc + (int64_t)bb * Npad + (int64_t)kt * SG_BK + yq * 4)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto put = [&](int s) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      st[s].ac[gk0 + i][gf] = gc[i];
+      st[s].as[gk0 + i][gf] = gs[i];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = yr0 + 64 * r;
+      st[s].y[yq * 4 + 0][row] = yv[r].x;
+      st[s].y[yq * 4 + 1][row] = yv[r].y;
+      st[s].y[yq * 4 + 2][row] = yv[r].z;
+      st[s].y[yq * 4 + 3][row] = yv[r].w;
+    }
+  };
+
+  gen(0);
+  put(0);
+  __syncthreads();
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nkt) gen(kt + 1);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float a_c[8], a_s[8], yy[8];
+      *reinterpret_cast<float4*>(&a_c[0]) = *reinterpret_cast<const float4*>(&st[cur].ac[k][tx * 4]);
+      *reinterpret_cast<float4*>(&a_c[4]) = *reinterpret_cast<const float4*>(&st[cur].ac[k][64 + tx * 4]);
+      *reinterpret_cast<float4*>(&a_s[0]) = *reinterpret_cast<const float4*>(&st[cur].as[k][tx * 4]);
+      *reinterpret_cast<float4*>(&a_s[4]) = *reinterpret_cast<const float4*>(&st[cur].as[k][64 + tx * 4]);
+      *reinterpret_cast<float4*>(&yy[0]) = *reinterpret_cast<const float4*>(&st[cur].y[k][ty * 4]);
+      *reinterpret_cast<float4*>(&yy[4]) = *reinterpret_cast<const float4*>(&st[cur].y[k][64 + ty * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc_c[i][j] = fmaf(a_c[i], yy[j], acc_c[i][j]);
+          acc_s[i][j] = fmaf(a_s[i], yy[j], acc_s[i][j]);
+        }
+    }
+    if (kt + 1 < nkt) put(cur ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue: rotate by tau, divide by CC'/SS', lightkurve normalisation
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t f = f0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+    if (f >= F) continue;
+    const float4 r = rot[f];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int bb = b0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
+      if (bb >= B) continue;
+      power[(int64_t)bb * F + f] =
+          ls_epilogue_shared(acc_c[i][j], acc_s[i][j], r, (float)N, normalization, (float)norm_scale);
+    }
+  }
+}
+
+// =====================================================================================
+// Host launchers
+// =====================================================================================
+int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* h_offsets, int B,
+                    const double* freq, const int64_t* h_freq_offsets, int64_t F, int normalization,
+                    const double* norm_scale, float* power, int mem, cudaStream_t st) {
+  LKB_REQUIRE(B > 0 && t && y && h_offsets && freq && power, "lkb_ls_power: null argument");
+  LKB_REQUIRE(y_dtype == LKB_DTYPE_F32 || y_dtype == LKB_DTYPE_F64, "lkb_ls_power: bad y_dtype");
+  LKB_REQUIRE(normalization >= 0 && normalization <= 2, "lkb_ls_power: bad normalization");
+  LKB_REQUIRE(normalization != LKB_LS_NORM_PSD_SCALE || norm_scale, "lkb_ls_power: norm_scale required");
+  LKB_TRY(ensure_device());
+  const int64_t total = h_offsets[B];
+  // padded offsets (16-byte alignment of every light curve for the TMA bulk copies)
+  int64_t* h_po = (int64_t*)malloc(sizeof(int64_t) * (B + 1));
+  if (!h_po) { set_error("host malloc failed"); return LKB_E_OOM; }
+  h_po[0] = 0;
+  int64_t Fmax = F, Ftot = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = h_offsets[b + 1] - h_offsets[b];
+    if (n < 0) { free(h_po); set_error("lkb_ls_power: offsets not monotone"); return LKB_E_ARG; }
+    h_po[b + 1] = h_po[b] + ((n + 3) / 4) * 4;
+  }
+  if (h_freq_offsets) {
+    Fmax = 0;
+    for (int b = 0; b < B; ++b) Fmax = max(Fmax, h_freq_offsets[b + 1] - h_freq_offsets[b]);
+    Ftot = h_freq_offsets[B];
+  } else {
+    Ftot = F;
+  }
+  const int64_t ptotal = h_po[B];
+  const size_t ysz = (y_dtype == LKB_DTYPE_F32) ? 4 : 8;
+
+  int64_t *d_off = nullptr, *d_po = nullptr, *d_fo = nullptr;
+  int s = ws_get_t<int64_t>(WS_A, B + 1, &d_off);
+  if (s == LKB_OK) s = ws_get_t<int64_t>(WS_B, B + 1, &d_po);
+  if (s == LKB_OK && h_freq_offsets) s = ws_get_t<int64_t>(WS_C, B + 1, &d_fo);
+  double* d_t = nullptr;
+  float* d_y = nullptr;
+  if (s == LKB_OK) s = ws_get_t<double>(WS_D, ptotal + 4, &d_t);
+  if (s == LKB_OK) s = ws_get_t<float>(WS_E, ptotal + 4, &d_y);
+  if (s != LKB_OK) { free(h_po); return s; }
+  cudaError_t e = cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_po, h_po, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && h_freq_offsets)
+    e = cudaMemcpyAsync(d_fo, h_freq_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // h_po is freed below
+  free(h_po);
+  if (e != cudaSuccess) { set_error("offset upload failed: %s", cudaGetErrorString(e)); return LKB_E_CUDA; }
+
+  const double* dt_in = nullptr;
+  const void* dy_in = nullptr;
+  const double *d_freq = nullptr, *d_ns = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, t, total, &dt_in, st));
+  {
+    const unsigned char* tmp = nullptr;
+    LKB_TRY(stage_in<unsigned char>(mem, WS_IN1, (const unsigned char*)y, total * ysz, &tmp, st));
+    dy_in = tmp;
+  }
+  LKB_TRY(stage_in<double>(mem, WS_IN2, freq, Ftot, &d_freq, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN3, norm_scale, B, &d_ns, st));
+  const int64_t out_count = h_freq_offsets ? Ftot : (int64_t)B * F;
+  float* d_pow = nullptr;
+  LKB_TRY(stage_out_alloc<float>(mem, WS_OUT0, power, out_count, &d_pow));
+
+  if (y_dtype == LKB_DTYPE_F32)
+    ls_prep_ragged_kernel<float><<<B, 256, 0, st>>>(dt_in, (const float*)dy_in, d_off, d_po, d_t, d_y);
+  else
+    ls_prep_ragged_kernel<double><<<B, 256, 0, st>>>(dt_in, (const double*)dy_in, d_off, d_po, d_t, d_y);
+  LKB_LAUNCH_CHECK();
+
+  dim3 grid((unsigned)((Fmax + LS_FPB - 1) / LS_FPB), (unsigned)B);
+  LKB_REQUIRE(B <= 65535, "lkb_ls_power: B > 65535 per call (split the batch)");
+  ls_direct_kernel<<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, normalization, d_ns,
+                                                   d_pow);
+  LKB_LAUNCH_CHECK();
+  LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, const float* d_absmax, int B,
+                 const double* d_freq, int64_t F, const float4* d_rot, int normalization, double norm_scale,
+                 float* d_pow, cudaStream_t st);   // ls_tc.cu
+bool ls_tc_supported(int B, int64_t N, int64_t F);
+
+int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
+                    int normalization, const double* norm_scale, float* power, int mem, cudaStream_t st,
+                    int algo) {
+  LKB_REQUIRE(B > 0 && N > 0 && F > 0 && t && y && freq && power, "lkb_ls_power_shared: null/empty argument");
+  LKB_REQUIRE(y_dtype == LKB_DTYPE_F32 || y_dtype == LKB_DTYPE_F64, "lkb_ls_power_shared: bad y_dtype");
+  LKB_REQUIRE(normalization >= 0 && normalization <= 2, "lkb_ls_power_shared: bad normalization");
+  LKB_REQUIRE(normalization != LKB_LS_NORM_PSD_SCALE || norm_scale, "lkb_ls_power_shared: norm_scale required");
+  LKB_REQUIRE(algo >= 0 && algo <= 2, "lkb_ls_power_shared: bad algo");
+  LKB_TRY(ensure_device());
+  const int64_t Npad = ((N + 63) / 64) * 64;
+  const size_t ysz = (y_dtype == LKB_DTYPE_F32) ? 4 : 8;
+
+  const double *dt_in = nullptr, *d_freq = nullptr;
+  const void* dy_in = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, t, N, &dt_in, st));
+  {
+    const unsigned char* tmp = nullptr;
+    LKB_TRY(stage_in<unsigned char>(mem, WS_IN1, (const unsigned char*)y, (size_t)B * N * ysz, &tmp, st));
+    dy_in = tmp;
+  }
+  LKB_TRY(stage_in<double>(mem, WS_IN2, freq, F, &d_freq, st));
+  double ns = 1.0;
+  if (norm_scale) {
+    if (mem == LKB_MEM_HOST) ns = *norm_scale;
+    else LKB_CUDA_CHECK(cudaMemcpyAsync(&ns, norm_scale, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mem == LKB_MEM_DEVICE) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  float* d_pow = nullptr;
+  LKB_TRY(stage_out_alloc<float>(mem, WS_OUT0, power, (size_t)B * F, &d_pow));
+
+  double* d_t = nullptr;
+  float *d_yc = nullptr, *d_absmax = nullptr;
+  float4* d_rot = nullptr;
+  LKB_TRY(ws_get_t<double>(WS_D, Npad, &d_t));
+  LKB_TRY(ws_get_t<float>(WS_E, (size_t)B * Npad, &d_yc));
+  LKB_TRY(ws_get_t<float4>(WS_F, F, &d_rot));
+  LKB_TRY(ws_get_t<float>(WS_G, B, &d_absmax));
+
+  ls_shift_time_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(dt_in, N, Npad, d_t);
+  LKB_LAUNCH_CHECK();
+  if (y_dtype == LKB_DTYPE_F32)
+    ls_prep_shared_kernel<float><<<B, 256, 0, st>>>((const float*)dy_in, N, Npad, d_yc, d_absmax);
+  else
+    ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax);
+  LKB_LAUNCH_CHECK();
+  ls_window_kernel<<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, N, d_freq, F, d_rot);
+  LKB_LAUNCH_CHECK();
+
+  bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
+  if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
+    set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
+    return LKB_E_UNSUPPORTED;
+  }
+  if (use_tc) {
+    LKB_TRY(ls_tc_launch(d_t, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, normalization, ns, d_pow, st));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_shared_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(2 * sizeof(SgStage))));
+      attr_set = true;
+    }
+    dim3 grid((unsigned)((F + SG_BM - 1) / SG_BM), (unsigned)((B + SG_BN - 1) / SG_BN));
+    ls_shared_simt_kernel<<<grid, 256, 2 * sizeof(SgStage), st>>>(d_t, N, Npad, d_yc, B, d_freq, F, d_rot,
+                                                                 normalization, ns, d_pow);
+    LKB_LAUNCH_CHECK();
+  }
+  LKB_TRY(stage_out_copy<float>(mem, power, d_pow, (size_t)B * F, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+}  // namespace lkb

@@ -1,0 +1,80 @@
+// Device math shared by the Lomb-Scargle kernels.
+// Math: astropy lombscargle_slow (fit_mean=True, center_data=True, dy=1 => w = 1/N,
+// normalization="psd"), restated in oracle/ls.py:ls_slow_psd.
+#pragma once
+#include "common.cuh"
+
+namespace lkb {
+
+// sin/cos of 2*pi*phase where `phase` is in CYCLES and may be large: reduce in fp64
+// (H1 of SURVEY.md: fp32 omega*t loses the phase at Kepler baselines), evaluate in fp32
+// on the MUFU pipe.
+__device__ __forceinline__ void ls_sincos_cycles(double phase, float& s, float& c) {
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer trick
+  const double r = __dadd_rn(phase, magic);
+  const double frac = __dsub_rn(phase, __dsub_rn(r, magic));   // in [-0.5, 0.5]
+  const float x = (float)frac * 6.283185307179586f;
+  s = __sinf(x);
+  c = __cosf(x);
+}
+
+template <typename T>
+struct LsSums {
+  T sh, ch, s, c, cc, sc;
+  __device__ __forceinline__ void zero() { sh = ch = s = c = cc = sc = (T)0; }
+  __device__ __forceinline__ void add(T y, T sn, T cs) {
+    sh += y * sn;
+    ch += y * cs;
+    s += sn;
+    c += cs;
+    cc += cs * cs;
+    sc += sn * cs;
+  }
+  template <typename U>
+  __device__ __forceinline__ void accumulate(const LsSums<U>& o) {
+    sh += (T)o.sh; ch += (T)o.ch; s += (T)o.s; c += (T)o.c; cc += (T)o.cc; sc += (T)o.sc;
+  }
+  __device__ __forceinline__ void warp_reduce() {
+    sh = warp_sum(sh); ch = warp_sum(ch); s = warp_sum(s); c = warp_sum(c); cc = warp_sum(cc); sc = warp_sum(sc);
+  }
+};
+
+// tau rotation and the floating-mean corrected CC', SS' (weights w = 1/N).
+__device__ __forceinline__ void ls_rotation(const LsSums<double>& d, double N, double& ct, double& st,
+                                            double& ccp, double& ssp) {
+  const double Sb = d.s / N, Cb = d.c / N, CCb = d.cc / N, SCb = d.sc / N, SSb = 1.0 - CCb;
+  const double S2 = 2.0 * SCb - 2.0 * Sb * Cb;
+  const double C2 = (2.0 * CCb - 1.0) - (Cb * Cb - Sb * Sb);
+  const double ta = 0.5 * atan2(S2, C2);
+  sincos(ta, &st, &ct);
+  const double Ctau = Cb * ct + Sb * st, Stau = Sb * ct - Cb * st;
+  ccp = CCb * ct * ct + 2.0 * SCb * ct * st + SSb * st * st - Ctau * Ctau;
+  ssp = SSb * ct * ct - 2.0 * SCb * ct * st + CCb * st * st - Stau * Stau;
+}
+
+// astropy normalization="psd": 0.5 * N * (YC^2/CC + YS^2/SS)
+__device__ __forceinline__ double ls_power_from_sums(const LsSums<double>& d, double N) {
+  double ct, st, ccp, ssp;
+  ls_rotation(d, N, ct, st, ccp, ssp);
+  const double YC = (d.ch * ct + d.sh * st) / N, YS = (d.sh * ct - d.ch * st) / N;
+  return 0.5 * N * (YC * YC / ccp + YS * YS / ssp);
+}
+
+// lightkurve rescale, periodogram.py:969-975
+__device__ __forceinline__ float ls_normalize(double p_raw, double N, int normalization, double scale) {
+  if (normalization == LKB_LS_NORM_PSD_SCALE) return (float)(p_raw * scale);
+  if (normalization == LKB_LS_NORM_AMPLITUDE) return (float)(sqrt(p_raw) * sqrt(4.0 / N));
+  return (float)p_raw;
+}
+
+// shared-grid epilogue: rot = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}
+__device__ __forceinline__ float ls_epilogue_shared(float ch, float sh, const float4 rot, float N, int normalization,
+                                                    float scale) {
+  const float yc = ch * rot.x + sh * rot.y, ys = sh * rot.x - ch * rot.y;
+  const float p = yc * yc * rot.z + ys * ys * rot.w;
+  if (normalization == LKB_LS_NORM_PSD_SCALE) return p * scale;
+  if (normalization == LKB_LS_NORM_AMPLITUDE) return sqrtf(p * (4.0f / N));
+  return p;
+}
+
+}  // namespace lkb

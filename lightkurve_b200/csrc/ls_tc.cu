@@ -1,0 +1,305 @@
+// K2c: shared-cadence-grid Lomb-Scargle contraction on the 5th-generation tensor cores.
+//
+//   Ch[f, b] = sum_n cos(2 pi f t_n) y_b[n],   Sh[f, b] = sum_n sin(2 pi f t_n) y_b[n]
+// is a GEMM  D[M = frequencies, N = light curves] = A[M, K = cadences] * Y[N, K]^T  whose A operand
+// (the sin/cos design matrix, F x N_cad - 1.3e10 elements at BASELINE config 2) is never
+// materialised in HBM: producer warps synthesise each 128 x 32 tile directly into shared
+// memory in the UMMA canonical K-major SWIZZLE_64B layout, while the TMA engine streams the
+// matching 256 x 32 flux tile.  One elected thread issues tcgen05.mma (kind::f16, M128 N256
+// K16, cta_group::1); the cos and sin accumulators (128 lanes x 256 fp32 columns each) fill the
+// SM's 512 TMEM columns, and the epilogue reads them back with tcgen05.ld, applies the
+// per-frequency tau rotation / CC' SS' terms (ls_window_kernel) and lightkurve's normalisation.
+//
+// Precision: fp16 operands alone would leave ~1e-3 relative error in weak bins.
+// Both operands are split hi + lo (fp16 + fp16 residual, power-of-two pre-scaling so that the
+// residuals stay normal numbers) and three products are accumulated per k-step
+// (Ah*Yh + Ah*Yl + Al*Yh; Al*Yl ~ 2^-22 is dropped), fp32 accumulation in TMEM.
+// Roofline: algorithmic flops = 4 F N B; issued tensor flops = 3x that.
+//
+// Warp roles (320 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM
+// owner, warps 2..9 = design-matrix generators; warps 2..5 double as the epilogue (their
+// warp_id % 4 covers the four TMEM lane quadrants).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "ls_common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace lkb {
+
+constexpr int TC_BM = 128;            // frequencies per CTA (TMEM lanes)
+constexpr int TC_BN = 256;            // light curves per CTA (columns per accumulator)
+constexpr int TC_BK = 32;             // cadences per pipeline stage (64-byte fp16 rows, SWIZZLE_64B)
+constexpr int TC_STAGES = 3;
+constexpr int TC_GEN_WARPS = 8;
+constexpr int TC_THREADS = (2 + TC_GEN_WARPS) * 32;
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;          // 8 KB
+constexpr int TC_Y_TILE = TC_BN * TC_BK * 2;          // 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE + 2 * TC_Y_TILE;   // 64 KB
+constexpr float TC_A_SCALE = 256.0f;                  // 2^8: keeps fp16 residuals of cos/sin normal
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row atoms of 512 B (SBO), version 1.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                              // layout type: SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=256
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+// flux -> power-of-two scaled fp16 hi/lo planes: yhl[0][b][n] = hi, yhl[1][b][n] = lo
+__global__ void __launch_bounds__(256)
+tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ absmax, int B, int64_t Npad,
+                     __half* __restrict__ yhl, float* __restrict__ inv_scale) {
+  const int b = blockIdx.y;
+  const float am = absmax[b];
+  // scale = 2^k with scale*absmax in [2^13, 2^14); all-zero light curves keep scale 1
+  int e = 0;
+  float sc = 1.0f;
+  if (am > 0.f && isfinite(am)) {
+    frexpf(am, &e);                       // am = m * 2^e, m in [0.5, 1)
+    sc = ldexpf(1.0f, 14 - e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[b] = 1.0f / (sc * TC_A_SCALE);
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= Npad) return;
+  const float2 v = *reinterpret_cast<const float2*>(yc + (int64_t)b * Npad + i);
+  const float a0 = v.x * sc, a1 = v.y * sc;
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+  *reinterpret_cast<__half2*>(yhl + (int64_t)b * Npad + i) = h;
+  *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
+}
+
+struct TcParams {
+  const double* t;        // [Npad] shifted times (padding cadences hold 0)
+  const double* freq;     // [F]
+  const float4* rot;      // [F]
+  const float* inv_scale; // [B]
+  float* power;           // [B, F]
+  int64_t N, Npad, F;
+  int B;
+  int normalization;
+  float norm_scale;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  // 1024-byte aligned carve-up (swizzle atoms need their natural alignment)
+  const uint32_t raw = ptx::smem_u32(tc_smem_raw);
+  unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_y = bars;                    // [STAGES] TMA bytes landed
+  uint64_t* full_a = bars + TC_STAGES;        // [STAGES] generator warps done
+  uint64_t* empty = bars + 2 * TC_STAGES;     // [STAGES] MMAs of the stage retired
+  uint64_t* acc_full = bars + 3 * TC_STAGES;  // accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
+  const int b0 = blockIdx.y * TC_BN;
+  const int nst = (int)(p.Npad / TC_BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      ptx::mbar_init(&full_y[s], 1);
+      ptx::mbar_init(&full_a[s], TC_GEN_WARPS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&ymap);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: flux hi/lo tiles =================
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % TC_STAGES;
+        if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+        unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_y[s], 2 * TC_Y_TILE);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, it * TC_BK, p.B + b0, &full_y[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        ptx::mbar_wait(&full_y[s], ph);
+        ptx::mbar_wait(&full_a[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+        const uint32_t a_ch = sa, a_cl = sa + TC_A_TILE, a_sh = sa + 2 * TC_A_TILE, a_sl = sa + 3 * TC_A_TILE;
+        const uint32_t y_h = sa + 4 * TC_A_TILE, y_l = y_h + TC_Y_TILE;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t ko = k * 32;                      // 16 fp16 = 32 bytes along K inside the 64 B row
+          const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
+          const uint64_t dyh = tc_smem_desc(y_h + ko), dyl = tc_smem_desc(y_l + ko);
+          // cos accumulator: columns [0, 256)
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyh, TC_IDESC, first);
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyl, TC_IDESC, 1u);
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_cl + ko), dyh, TC_IDESC, 1u);
+          // sin accumulator: columns [256, 512)
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyh, TC_IDESC, first);
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyl, TC_IDESC, 1u);
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, TC_IDESC, 1u);
+        }
+        ptx::umma_commit(&empty[s]);          // smem stage reusable once these MMAs retire
+      }
+      ptx::umma_commit(acc_full);
+    }
+  } else {
+    // ================= design-matrix generators =================
+    const int g = threadIdx.x - 64;                       // 0..255
+    const int row = g & (TC_BM - 1);                      // frequency row inside the tile
+    const int kh = g >> 7;                                // which 16-cadence half of the stage
+    const double fr = (f0 + row < p.F) ? p.freq[f0 + row] : 0.0;
+    const uint32_t row_off = (uint32_t)row * 64u;
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % TC_STAGES;
+      if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+      unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+      const double* tp = p.t + (int64_t)it * TC_BK + kh * 16;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {                       // two 16-byte chunks (8 cadences each)
+        uint32_t ch[4], cl[4], sh[4], sl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float s0, c0, s1, c1;
+          ls_sincos_cycles(fr * tp[c * 8 + 2 * q], s0, c0);
+          ls_sincos_cycles(fr * tp[c * 8 + 2 * q + 1], s1, c1);
+          s0 *= TC_A_SCALE; c0 *= TC_A_SCALE; s1 *= TC_A_SCALE; c1 *= TC_A_SCALE;
+          const __half2 hc = __floats2half2_rn(c0, c1), hs = __floats2half2_rn(s0, s1);
+          const float2 fc = __half22float2(hc), fs = __half22float2(hs);
+          const __half2 lc = __floats2half2_rn(c0 - fc.x, c1 - fc.y), ls = __floats2half2_rn(s0 - fs.x, s1 - fs.y);
+          ch[q] = *reinterpret_cast<const uint32_t*>(&hc);
+          cl[q] = *reinterpret_cast<const uint32_t*>(&lc);
+          sh[q] = *reinterpret_cast<const uint32_t*>(&hs);
+          sl[q] = *reinterpret_cast<const uint32_t*>(&ls);
+        }
+        const uint32_t chunk = (uint32_t)(kh * 2 + c);    // logical 16-byte chunk inside the 64 B row
+        const uint32_t off = row_off + ((chunk ^ sw) << 4);
+        *reinterpret_cast<uint4*>(st + off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<uint4*>(st + TC_A_TILE + off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+        *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+        *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+      }
+      ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_a[s]);
+    }
+
+    // ================= epilogue (warps 2..5: TMEM lane quadrant = warp % 4) =================
+    if (warp < 6) {
+      ptx::mbar_wait(acc_full, 0);
+      ptx::tc_fence_after();
+      const int quad = warp & 3;
+      const int64_t f = f0 + quad * 32 + lane;
+      const bool f_ok = f < p.F;
+      const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
+      const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+      const float Nf = (float)p.N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t vc[32], vs[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + c0, vc);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TC_BN + c0, vs);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int b = b0 + c0 + j;
+          if (f_ok && b < p.B) {
+            const float h = p.inv_scale[b];
+            const float chv = __uint_as_float(vc[j]) * h, shv = __uint_as_float(vs[j]) * h;
+            p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(chv, shv, r, Nf, p.normalization, p.norm_scale);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ---- host -------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+bool ls_tc_supported(int B, int64_t N, int64_t F) {
+  // worthwhile only when a flux tile is reasonably full; any shape is functionally fine
+  return B >= 64 && N >= 256 && F >= 128;
+}
+
+int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, const float* d_absmax, int B,
+                 const double* d_freq, int64_t F, const float4* d_rot, int normalization, double norm_scale,
+                 float* d_pow, cudaStream_t st) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
+  __half* d_yhl = nullptr;
+  float* d_inv = nullptr;
+  LKB_TRY(ws_get_t<__half>(WS_H, (size_t)2 * B * Npad, &d_yhl));
+  LKB_TRY(ws_get_t<float>(WS_I, B, &d_inv));
+  tc_split_flux_kernel<<<dim3((unsigned)((Npad / 2 + 255) / 256), (unsigned)B), 256, 0, st>>>(d_yc, d_absmax, B, Npad,
+                                                                                           d_yhl, d_inv);
+  LKB_LAUNCH_CHECK();
+
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {(cuuint64_t)Npad, (cuuint64_t)(2 * (int64_t)B)};
+  const cuuint64_t strides[1] = {(cuuint64_t)Npad * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BN};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_yhl, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)cr); return LKB_E_CUDA; }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_set = true;
+  }
+  TcParams p;
+  p.t = d_t; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow;
+  p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
+  dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
+  ls_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
+}
+
+}  // namespace lkb

@@ -1,0 +1,389 @@
+// K5: RegressionCorrector numerics, /root/reference/src/lightkurve/correctors/regressioncorrector.py
+//   _fit_coefficients :127-189 (dense branch): A = X^T diag(1/s^2) X + diag(1/prior_sigma^2),
+//                                            rhs = X^T (y/s^2) + prior_mu/prior_sigma^2, np.linalg.solve
+//   correct() loop     :244-279: niters x { fit on cadence_mask & ~outlier_mask; residuals with the
+//                                masked cadences set to NaN; outlier_mask |= sigma_clip(residuals).mask }
+//                                then model = X w - median(X w).
+// fp64 throughout (the reference is fp64; 7-decimal known answers in
+// tests/correctors/test_regressioncorrector.py:13-83).
+//
+// Kernels:  rg_rows     build the list of cadences entering (iteration 0) or LEAVING (later
+//                       iterations: the outlier mask only grows, so A and rhs are DOWNDATED by the
+//                       newly clipped rows instead of being rebuilt - N*K^2 work once, not niters times)
+//           rg_accum    weighted Gram blocks (64x64 tiles of [X | y]^T W [X | y], upper triangle)
+//           rg_solve    add the Gaussian priors, LU with partial pivoting in shared memory (gesv-like)
+//           rg_clip     model = X w, residuals, astropy sigma_clip (median / std, <= 5 rounds)
+//           rg_final    model - median(model)
+#include "common.cuh"
+#include "select.cuh"
+
+namespace lkb {
+
+constexpr int RG_BLK = 64;      // Gram tile edge
+constexpr int RG_RC = 32;       // cadences per shared-memory chunk
+constexpr int RG_KMAX = 165;    // (K+1)^2 doubles must fit in shared memory for the LU
+
+struct RgWs {
+  int32_t* rows;      // [B, N] cadence list for the current accumulate pass
+  int32_t* cnt;       // [B]
+  uint8_t* used;      // [B, N] cadences currently inside A/rhs
+  double* gram;       // [B, Ka, Ka], Ka = K + 1 (column K is y)
+  double* resid;      // [B, N]
+};
+
+__device__ __forceinline__ const double* rg_xrow(const double* X, int x_batched, int b, int64_t N, int K, int64_t r) {
+  return X + ((x_batched ? (int64_t)b * N : 0) + r) * K;
+}
+
+// ---- row lists -------------------------------------------------------------------------------
+// first = 1: rows = cadence_mask (& ~outlier, which is empty), used := that.
+// first = 0: rows = used & outlier (newly clipped), used := used & ~outlier.
+__global__ void __launch_bounds__(256)
+rg_rows_kernel(const uint8_t* __restrict__ cadence_mask, const uint8_t* __restrict__ outlier, int64_t N, int first,
+               RgWs ws) {
+  __shared__ int s_wc[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint8_t* cm = cadence_mask ? cadence_mask + (int64_t)b * N : nullptr;
+  const uint8_t* om = outlier + (int64_t)b * N;
+  uint8_t* used = ws.used + (int64_t)b * N;
+  int32_t* rows = ws.rows + (int64_t)b * N;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < N; c0 += blockDim.x) {
+    const int64_t i = c0 + threadIdx.x;
+    bool p = false;
+    if (i < N) {
+      if (first) {
+        p = (cm ? cm[i] != 0 : true) && om[i] == 0;
+        used[i] = p ? 1 : 0;
+      } else {
+        p = used[i] != 0 && om[i] != 0;
+        if (p) used[i] = 0;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) s_wc[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_wc[w];
+    if (p) rows[off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_wc[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ws.cnt[b] = s_base;
+}
+
+// ---- weighted Gram accumulation -----------------------------------------------------------------
+// grid = (n_upper_blocks, B); 128 threads = 8 (i) x 16 (j); thread tile 8 x 4.
+__global__ void __launch_bounds__(128)
+rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y,
+                const double* __restrict__ flux_err, int64_t N, int K, int nblk, double sign, RgWs ws) {
+  __shared__ double s_a[RG_RC][RG_BLK];   // w * [X|y][:, bi block]
+  __shared__ double s_b[RG_RC][RG_BLK];   //     [X|y][:, bj block]
+  const int b = blockIdx.y;
+  // decode upper-triangular block index
+  int bi = 0, rem = blockIdx.x;
+  while (rem >= nblk - bi) { rem -= nblk - bi; ++bi; }
+  const int bj = bi + rem;
+  const int Ka = K + 1;
+  const int cnt = ws.cnt[b];
+  if (cnt == 0) return;
+  const int32_t* rows = ws.rows + (int64_t)b * N;
+  const double* yb = y + (int64_t)b * N;
+  const double* fe = flux_err ? flux_err + (int64_t)b * N : nullptr;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int c0 = 0; c0 < cnt; c0 += RG_RC) {
+    const int nr = min(RG_RC, cnt - c0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < RG_RC * RG_BLK; e += blockDim.x) {
+      const int r = e / RG_BLK, c = e % RG_BLK;
+      double va = 0.0, vb = 0.0;
+      if (r < nr) {
+        const int64_t row = rows[c0 + r];
+        const double s = fe ? fe[row] : 1.0;
+        const double w = 1.0 / (s * s);
+        const double* xr = rg_xrow(X, x_batched, b, N, K, row);
+        const int ca = bi * RG_BLK + c, cb = bj * RG_BLK + c;
+        if (ca < Ka) va = (ca < K ? xr[ca] : yb[row]) * w;
+        if (cb < Ka) vb = (cb < K ? xr[cb] : yb[row]);
+      }
+      s_a[r][c] = va;
+      s_b[r][c] = vb;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < RG_RC; ++k) {
+      double a[8], bb[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = s_a[k][ty + 8 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = s_b[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+  }
+  double* G = ws.gram + (int64_t)b * Ka * Ka;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gi = bi * RG_BLK + ty + 8 * i;
+    if (gi >= Ka) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = bj * RG_BLK + tx + 16 * j;
+      if (gj >= Ka) continue;
+      G[(int64_t)gi * Ka + gj] += sign * acc[i][j];     // this CTA owns the block: no atomics
+    }
+  }
+}
+
+// ---- solve ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __restrict__ prior_sigma, RgWs ws,
+                double* __restrict__ coeff, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) double s_m[];        // [K][K+1] augmented
+  __shared__ double s_red[8];
+  __shared__ int s_redi[8];
+  __shared__ int s_piv;
+  const int b = blockIdx.x;
+  const int Ka = K + 1;
+  const double* G = ws.gram + (int64_t)b * Ka * Ka;
+  // symmetric fill from the upper triangle (only blocks bi <= bj were accumulated, but inside a
+  // diagonal block both triangles are present; use i <= j entries everywhere for exact symmetry)
+  for (int e = threadIdx.x; e < K * Ka; e += blockDim.x) {
+    const int i = e / Ka, j = e % Ka;
+    double v = (j >= i) ? G[(int64_t)i * Ka + j] : G[(int64_t)j * Ka + i];
+    if (prior_sigma) {
+      const double ps = prior_sigma[i];
+      if (j == i) v += 1.0 / (ps * ps);
+      if (j == K) v += prior_mu[i] / (ps * ps);
+    }
+    s_m[e] = v;
+  }
+  __syncthreads();
+  bool singular = false;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = 0; c < K; ++c) {
+    // partial pivoting: first row with the largest |value| in column c
+    double best = -1.0;
+    int bi = c;
+    for (int r = c + threadIdx.x; r < K; r += blockDim.x) {
+      const double v = fabs(s_m[r * Ka + c]);
+      if (v > best) { best = v; bi = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_red[warp] = best; s_redi[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bb = s_red[0];
+      int ii = s_redi[0];
+      for (int w = 1; w < nw; ++w)
+        if (s_red[w] > bb || (s_red[w] == bb && s_redi[w] < ii)) { bb = s_red[w]; ii = s_redi[w]; }
+      s_piv = (bb > 0.0) ? ii : -1;      // exact zero (or NaN) pivot => singular, like LAPACK gesv info > 0
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv < 0) { singular = true; break; }
+    if (piv != c) {
+      for (int k = threadIdx.x; k < Ka; k += blockDim.x) {
+        const double tmp = s_m[c * Ka + k];
+        s_m[c * Ka + k] = s_m[piv * Ka + k];
+        s_m[piv * Ka + k] = tmp;
+      }
+    }
+    __syncthreads();
+    const double pv = s_m[c * Ka + c];
+    for (int r = c + 1 + warp; r < K; r += nw) {
+      const double fct = s_m[r * Ka + c] / pv;
+      __syncwarp();
+      for (int k = c + 1 + lane; k < Ka; k += 32) s_m[r * Ka + k] = fma(-fct, s_m[c * Ka + k], s_m[r * Ka + k]);
+      __syncwarp();
+      if (lane == 0) s_m[r * Ka + c] = 0.0;
+    }
+    __syncthreads();
+  }
+  if (singular) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) coeff[(int64_t)b * K + k] = __longlong_as_double(0x7ff8000000000000ll);
+    if (threadIdx.x == 0 && status) status[b] = LKB_E_SINGULAR;
+    return;
+  }
+  // back substitution (warp 0)
+  if (warp == 0) {
+    for (int c = K - 1; c >= 0; --c) {
+      double part = 0.0;
+      for (int k = c + 1 + lane; k < K; k += 32) part = fma(s_m[c * Ka + k], s_m[k * Ka + K], part);
+      part = warp_sum(part);
+      if (lane == 0) s_m[c * Ka + K] = (s_m[c * Ka + K] - part) / s_m[c * Ka + c];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) coeff[(int64_t)b * K + k] = s_m[k * Ka + K];
+  if (threadIdx.x == 0 && status) status[b] = LKB_OK;
+}
+
+// ---- model + sigma clip ---------------------------------------------------------------------------
+__device__ __forceinline__ void rg_model_rows(const double* X, int x_batched, int b, int64_t N, int K,
+                                              const double* s_w, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t r = warp; r < N; r += nw) {
+    const double* xr = rg_xrow(X, x_batched, b, N, K, r);
+    double acc = 0.0;
+    for (int k = lane; k < K; k += 32) acc = fma(xr[k], s_w[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[r] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(512)
+rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y, int64_t N, int K,
+               const double* __restrict__ coeff, double clip_sigma, RgWs ws, uint8_t* __restrict__ outlier) {
+  extern __shared__ __align__(16) double s_w[];
+  __shared__ SelSmem sm;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_w[k] = coeff[(int64_t)b * K + k];
+  __syncthreads();
+  double* res = ws.resid + (int64_t)b * N;
+  const uint8_t* used = ws.used + (int64_t)b * N;
+  uint8_t* om = outlier + (int64_t)b * N;
+  const double* yb = y + (int64_t)b * N;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  rg_model_rows(X, x_batched, b, N, K, s_w, res);
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) res[i] = used[i] ? (yb[i] - res[i]) : qnan;
+  __syncthreads();
+  // astropy.stats.sigma_clip(residuals, sigma): maxiters=5, cenfunc=median, stdfunc=std
+  for (int it = 0; it < 5; ++it) {
+    long long cntv = 0;
+    const double med = block_nanmedian([&](int64_t i) { return res[i]; }, N, sm, &cntv);
+    if (cntv == 0) break;
+    const double sd = block_nanstd([&](int64_t i) { return res[i]; }, N, sm);
+    const double lo = med - sd * clip_sigma, hi = med + sd * clip_sigma;
+    long long changed = 0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+      const double v = res[i];
+      if (v == v && (v < lo || v > hi)) { res[i] = qnan; changed++; }
+    }
+    const long long tot = block_sum_ll(changed, sm.redll);
+    if (tot == 0) break;
+  }
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const double v = res[i];
+    if (!(v == v)) om[i] = 1;          // .mask includes the cadences that were NaN on entry
+  }
+}
+
+__global__ void __launch_bounds__(512)
+rg_final_kernel(const double* __restrict__ X, int x_batched, int64_t N, int K, const double* __restrict__ coeff,
+                double* __restrict__ model) {
+  extern __shared__ __align__(16) double s_w[];
+  __shared__ SelSmem sm;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_w[k] = coeff[(int64_t)b * K + k];
+  __syncthreads();
+  double* mo = model + (int64_t)b * N;
+  rg_model_rows(X, x_batched, b, N, K, s_w, mo);
+  __syncthreads();
+  // np.median (NaN-propagating): a NaN model (singular fit) stays NaN
+  long long cntv = 0;
+  const double med = block_nanmedian([&](int64_t i) { return mo[i]; }, N, sm, &cntv);
+  const double m = (cntv == N) ? med : __longlong_as_double(0x7ff8000000000000ll);
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) mo[i] -= m;
+}
+
+__global__ void rg_zero_kernel(double* p, int64_t n, uint8_t* q, int64_t nq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+  if (q && i < nq) q[i] = 0;
+}
+
+int regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
+            const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma, int niters,
+            double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, int mem, cudaStream_t st) {
+  LKB_REQUIRE(X && y && coeff && model && outlier_mask, "lkb_regress: null argument");
+  LKB_REQUIRE(B > 0 && B <= 65535 && N > 0 && K > 0 && niters >= 1, "lkb_regress: bad sizes");
+  LKB_REQUIRE((prior_mu == nullptr) == (prior_sigma == nullptr), "Please specify both `prior_mu` and `prior_sigma`");
+  LKB_REQUIRE(N < ((int64_t)1 << 31), "lkb_regress: N too large");
+  if (K > RG_KMAX) { set_error("lkb_regress: K=%d > %d unsupported", K, RG_KMAX); return LKB_E_UNSUPPORTED; }
+  LKB_TRY(ensure_device());
+  const int Ka = K + 1;
+  const size_t BN = (size_t)B * N;
+
+  const double *d_X = nullptr, *d_y = nullptr, *d_fe = nullptr, *d_pm = nullptr, *d_ps = nullptr;
+  const uint8_t* d_cm = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, X, (x_batched ? BN : (size_t)N) * K, &d_X, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN1, y, BN, &d_y, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN2, flux_err, BN, &d_fe, st));
+  LKB_TRY(stage_in<uint8_t>(mem, WS_IN3, cadence_mask, BN, &d_cm, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN4, prior_mu, K, &d_pm, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN5, prior_sigma, K, &d_ps, st));
+
+  RgWs ws;
+  LKB_TRY(ws_get_t<int32_t>(WS_A, BN, &ws.rows));
+  LKB_TRY(ws_get_t<int32_t>(WS_B, B, &ws.cnt));
+  LKB_TRY(ws_get_t<uint8_t>(WS_C, BN, &ws.used));
+  LKB_TRY(ws_get_t<double>(WS_D, (size_t)B * Ka * Ka, &ws.gram));
+  LKB_TRY(ws_get_t<double>(WS_E, BN, &ws.resid));
+
+  double *o_c = nullptr, *o_m = nullptr;
+  uint8_t* o_om = nullptr;
+  int32_t* o_st = nullptr;
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT0, coeff, (size_t)B * K, &o_c));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, model, BN, &o_m));
+  LKB_TRY(stage_out_alloc<uint8_t>(mem, WS_OUT2, outlier_mask, BN, &o_om));
+  LKB_TRY(stage_out_alloc<int32_t>(mem, WS_OUT3, status_out, B, &o_st));
+
+  {
+    const int64_t ng = (int64_t)B * Ka * Ka, nz = ng > (int64_t)BN ? ng : (int64_t)BN;
+    rg_zero_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(ws.gram, ng, o_om, (int64_t)BN);
+    LKB_LAUNCH_CHECK();
+  }
+  const int nblk = (Ka + RG_BLK - 1) / RG_BLK;
+  const int nupper = nblk * (nblk + 1) / 2;
+  const size_t solve_smem = (size_t)K * Ka * sizeof(double);
+  static size_t solve_attr = 0;
+  if (solve_smem > solve_attr) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    solve_attr = solve_smem;
+  }
+  for (int it = 0; it < niters; ++it) {
+    rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, N, it == 0 ? 1 : 0, ws);
+    LKB_LAUNCH_CHECK();
+    rg_accum_kernel<<<dim3(nupper, B), 128, 0, st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk, it == 0 ? 1.0 : -1.0, ws);
+    LKB_LAUNCH_CHECK();
+    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, o_st);
+    LKB_LAUNCH_CHECK();
+    rg_clip_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om);
+    LKB_LAUNCH_CHECK();
+  }
+  rg_final_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, N, K, o_c, o_m);
+  LKB_LAUNCH_CHECK();
+
+  LKB_TRY(stage_out_copy<double>(mem, coeff, o_c, (size_t)B * K, st));
+  LKB_TRY(stage_out_copy<double>(mem, model, o_m, BN, st));
+  LKB_TRY(stage_out_copy<uint8_t>(mem, outlier_mask, o_om, BN, st));
+  LKB_TRY(stage_out_copy<int32_t>(mem, status_out, o_st, B, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+}  // namespace lkb

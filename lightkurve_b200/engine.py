@@ -1,0 +1,248 @@
+"""Batched host-side entry points over the C ABI (``include/lkb200.h``).
+
+Every function takes either host ``numpy`` arrays (the library stages them through
+its device workspace; the call is synchronous) or CUDA ``torch`` tensors (raw device
+pointers are handed over; the call is asynchronous on the current torch stream).
+PyTorch is only the allocator / stream provider here - no torch op is on the
+compute path.  No CPU fallback exists: without the built library or without a GPU
+these functions raise.
+"""
+import numpy as np
+
+from . import _lib as L
+
+_NORMS = {"psd_raw": L.LS_NORM_PSD_RAW, "psd": L.LS_NORM_PSD_SCALE, "amplitude": L.LS_NORM_AMPLITUDE}
+_ALGOS = {"auto": L.LS_ALGO_AUTO, "simt": L.LS_ALGO_SIMT, "tcgen05": L.LS_ALGO_TCGEN05}
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_count():
+    return L.load().lkb_device_count()
+
+
+def init(device=0):
+    """Bind this process to one GPU (one process per GPU, like torch.distributed ranks)."""
+    L.check(L.load().lkb_init(int(device)))
+
+
+def shutdown():
+    L.check(L.load().lkb_shutdown())
+
+
+def launch_count():
+    return int(L.load().lkb_launch_count())
+
+
+def sm_count():
+    return int(L.load().lkb_sm_count())
+
+
+def _csr(arrays, dtype=np.float64):
+    lens = [len(a) for a in arrays]
+    offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    cat = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=dtype) for a in arrays])) if arrays else \
+        np.zeros(0, dtype)
+    return cat, offsets
+
+
+def _y_dtype_code(dt):
+    if dt == np.float32:
+        return L.DTYPE_F32
+    if dt == np.float64:
+        return L.DTYPE_F64
+    raise TypeError("flux must be float32 or float64")
+
+
+# --------------------------------------------------------------------------------------
+# Lomb-Scargle
+# --------------------------------------------------------------------------------------
+def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_scale=None):
+    """K1.  `times`/`fluxes`: lists of 1-D arrays (one per light curve, no NaNs).
+    `frequency`: one 1-D grid shared by all light curves, or a list of per-LC grids.
+    Returns a [B, F] float32 array (shared grid) or a list of float32 arrays."""
+    lib = L.load()
+    B = len(times)
+    if B == 0:
+        return []
+    t, offsets = _csr(times)
+    ydt = np.float32 if all(np.asarray(f).dtype == np.float32 for f in fluxes) else np.float64
+    y, yoff = _csr(fluxes, ydt)
+    if not np.array_equal(offsets, yoff):
+        raise ValueError("time and flux lengths differ")
+    per_lc = isinstance(frequency, (list, tuple))
+    if per_lc:
+        freq, foff = _csr(frequency)
+        F = 0
+        out = np.empty(int(foff[-1]), dtype=np.float32)
+    else:
+        freq = np.ascontiguousarray(frequency, dtype=np.float64)
+        foff = None
+        F = len(freq)
+        out = np.empty((B, F), dtype=np.float32)
+    ns = None if norm_scale is None else np.ascontiguousarray(np.broadcast_to(norm_scale, (B,)), dtype=np.float64)
+    L.check(lib.lkb_ls_power(L.ptr(t), L.ptr(y), _y_dtype_code(ydt), L.ptr(offsets), B, L.ptr(freq), L.ptr(foff), F,
+                             _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_HOST, None))
+    if per_lc:
+        return [out[foff[b]:foff[b + 1]] for b in range(B)]
+    return out
+
+
+def ls_power_shared(t, Y, frequency, normalization="amplitude", norm_scale=None, algo="auto", out=None):
+    """K2.  One cadence grid `t` [N] shared by the batch `Y` [B, N]; `frequency` [F].
+    numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode)."""
+    lib = L.load()
+    if _is_torch(Y):
+        import torch
+        if not (Y.is_cuda and t.is_cuda and frequency.is_cuda):
+            raise ValueError("device mode needs CUDA tensors for t, Y and frequency")
+        B, N = Y.shape
+        F = frequency.numel()
+        if t.dtype != torch.float64 or frequency.dtype != torch.float64:
+            raise TypeError("t and frequency must be float64")
+        ycode = L.DTYPE_F32 if Y.dtype == torch.float32 else L.DTYPE_F64
+        if out is None:
+            out = torch.empty((B, F), dtype=torch.float32, device=Y.device)
+        ns = None
+        if norm_scale is not None:
+            ns = torch.tensor([float(norm_scale)], dtype=torch.float64, device=Y.device)
+        L.check(lib.lkb_ls_power_shared(L.ptr(t), L.ptr(Y), ycode, int(B), int(N), L.ptr(frequency), int(F),
+                                        _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_DEVICE, _stream_ptr(),
+                                        _ALGOS[algo]))
+        return out
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    Y = np.ascontiguousarray(Y)
+    if Y.dtype not in (np.float32, np.float64):
+        Y = Y.astype(np.float64)
+    B, N = Y.shape
+    freq = np.ascontiguousarray(frequency, dtype=np.float64)
+    if out is None:
+        out = np.empty((B, len(freq)), dtype=np.float32)
+    ns = None if norm_scale is None else np.array([float(norm_scale)], dtype=np.float64)
+    L.check(lib.lkb_ls_power_shared(L.ptr(t), L.ptr(Y), _y_dtype_code(Y.dtype), B, N, L.ptr(freq), len(freq),
+                                    _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_HOST, None, _ALGOS[algo]))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Box Least Squares
+# --------------------------------------------------------------------------------------
+BLS_FIELDS = ("power", "depth", "depth_err", "duration", "transit_time", "depth_snr", "log_likelihood")
+
+
+def bls_power(times, fluxes, flux_errs, period, duration, oversample=10, objective="likelihood",
+              return_bins=False):
+    """K3.  Lists of per-LC arrays (flux_errs: list or None => unit weights), one shared
+    period grid [P] and duration grid [D].  Returns dict of [B, P] float64 arrays."""
+    lib = L.load()
+    B = len(times)
+    t, offsets = _csr(times)
+    y, yoff = _csr(fluxes)
+    if not np.array_equal(offsets, yoff):
+        raise ValueError("time and flux lengths differ")
+    dy = None
+    if flux_errs is not None:
+        dy, doff = _csr(flux_errs)
+        if not np.array_equal(offsets, doff):
+            raise ValueError("time and flux_err lengths differ")
+    period = np.ascontiguousarray(np.atleast_1d(period), dtype=np.float64)
+    duration = np.ascontiguousarray(np.atleast_1d(duration), dtype=np.float64)
+    P, D = len(period), len(duration)
+    outs = [np.empty((B, P), dtype=np.float64) for _ in range(7)]
+    bins = np.empty((B, P, 2), dtype=np.int32) if return_bins else None
+    L.check(lib.lkb_bls_power(L.ptr(t), L.ptr(y), L.ptr(dy), L.ptr(offsets), B, L.ptr(period), P, L.ptr(duration), D,
+                              int(oversample), L.BLS_SNR if objective == "snr" else L.BLS_LIKELIHOOD,
+                              *[L.ptr(o) for o in outs], L.ptr(bins), L.MEM_HOST, None))
+    res = dict(zip(BLS_FIELDS, outs))
+    res["period"] = period
+    if return_bins:
+        res["bins"] = bins
+    return res
+
+
+def bls_bin_index(t_rel, min_t, period, bin_duration):
+    lib = L.load()
+    t_rel = np.ascontiguousarray(t_rel, dtype=np.float64)
+    out = np.empty(len(t_rel), dtype=np.int32)
+    L.check(lib.lkb_bls_bin_index(L.ptr(t_rel), len(t_rel), float(min_t), float(period), float(bin_duration),
+                                  L.ptr(out), L.MEM_HOST, None))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# flatten
+# --------------------------------------------------------------------------------------
+def flatten(times, fluxes, flux_errs=None, masks=None, window_length=101, polyorder=2, break_tolerance=5,
+            niters=3, sigma=3):
+    """K4.  Lists of per-LC arrays.  `masks`: list of bool arrays, True = exclude (lightkurve
+    semantics) or None.  Returns (flat, flat_err, trend) as lists of float64 arrays."""
+    lib = L.load()
+    B = len(times)
+    t, offsets = _csr(times)
+    f, foff = _csr(fluxes)
+    if not np.array_equal(offsets, foff):
+        raise ValueError("time and flux lengths differ")
+    fe = None
+    if flux_errs is not None:
+        fe, _ = _csr(flux_errs)
+    ex = None
+    if masks is not None:
+        ex = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=bool) for m in masks]).astype(np.uint8))
+    flat = np.empty_like(f)
+    flat_err = np.empty_like(f)
+    trend = np.empty_like(f)
+    bt = np.nan if break_tolerance is None else float(break_tolerance)
+    L.check(lib.lkb_flatten(L.ptr(t), L.ptr(f), L.ptr(fe), L.ptr(ex), L.ptr(offsets), B, int(window_length),
+                            int(polyorder), bt, int(niters), float(sigma), L.ptr(flat), L.ptr(flat_err),
+                            L.ptr(trend), L.MEM_HOST, None))
+    sp = lambda a: [a[offsets[b]:offsets[b + 1]] for b in range(B)]
+    return sp(flat), sp(flat_err), sp(trend)
+
+
+# --------------------------------------------------------------------------------------
+# regression
+# --------------------------------------------------------------------------------------
+def regress(X, Y, flux_err=None, cadence_mask=None, prior_mu=None, prior_sigma=None, sigma=5, niters=5):
+    """K5.  X [N, K] (shared) or [B, N, K]; Y [B, N]; flux_err [B, N] or None (ones);
+    cadence_mask bool [B, N] or None.  Returns dict(coefficients [B,K], model [B,N]
+    (median-subtracted), outlier_mask bool [B,N], status int32 [B])."""
+    lib = L.load()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+    B, N = Y.shape
+    batched = X.ndim == 3
+    K = X.shape[-1]
+    if X.shape[-2] != N or (batched and X.shape[0] != B):
+        raise ValueError("X shape %s does not match Y shape %s" % (X.shape, Y.shape))
+    fe = None if flux_err is None else np.ascontiguousarray(np.broadcast_to(flux_err, Y.shape), dtype=np.float64)
+    cm = None if cadence_mask is None else \
+        np.ascontiguousarray(np.broadcast_to(np.asarray(cadence_mask, dtype=bool), Y.shape).astype(np.uint8))
+    pm = None if prior_mu is None else np.ascontiguousarray(prior_mu, dtype=np.float64)
+    ps = None if prior_sigma is None else np.ascontiguousarray(prior_sigma, dtype=np.float64)
+    coeff = np.empty((B, K), dtype=np.float64)
+    model = np.empty((B, N), dtype=np.float64)
+    om = np.empty((B, N), dtype=np.uint8)
+    status = np.empty(B, dtype=np.int32)
+    L.check(lib.lkb_regress(L.ptr(X), 1 if batched else 0, L.ptr(Y), L.ptr(fe), L.ptr(cm), L.ptr(pm), L.ptr(ps),
+                            B, N, K, float(sigma), int(niters), L.ptr(coeff), L.ptr(model), L.ptr(om),
+                            L.ptr(status), L.MEM_HOST, None))
+    return dict(coefficients=coeff, model=model, outlier_mask=om.astype(bool), status=status)
+
+
+def nanmedian_std(arrays):
+    """K6.  np.nanmedian and np.nanstd of each array."""
+    lib = L.load()
+    x, offsets = _csr(arrays)
+    B = len(arrays)
+    med = np.empty(B, dtype=np.float64)
+    sd = np.empty(B, dtype=np.float64)
+    L.check(lib.lkb_nanmedian_std(L.ptr(x), L.ptr(offsets), B, L.ptr(med), L.ptr(sd), L.MEM_HOST, None))
+    return med, sd

@@ -1,0 +1,331 @@
+"""`LightCurve`: the slice of /root/reference/src/lightkurve/lightcurve.py that sits on the hot path.
+
+Mirrors the reference's names, defaults, warnings and error behaviour for: the constructor
+(:355-488), ``normalize`` (:1216-1298), ``remove_nans`` (:1300-1327), ``flatten`` (:943-1078),
+``to_periodogram`` (:2490-2535), ``remove_outliers`` (:1429-1549, sigma_clip on the GPU select
+kernel), ``estimate_cdpp`` (:1764-1833), ``fold``-free arithmetic used by the correctors, and
+``to_corrector``.  The container is numpy-backed (the reference subclasses astropy TimeSeries,
+which cannot be imported here); plotting, FITS export, binning and archive access are out of
+scope.  The arithmetic of flatten / periodograms / sigma-clip statistics is
+NOT done here: it is routed through ``engine`` into the CUDA kernels.
+"""
+import copy as _copy
+import logging
+import warnings
+
+import numpy as np
+
+from . import units as u
+from .units import Quantity, Time
+from .utils import LightkurveWarning, validate_method, running_mean
+
+log = logging.getLogger(__name__)
+
+__all__ = ["LightCurve"]
+
+
+def _as_flux_quantity(x, unit=None):
+    if isinstance(x, Quantity):
+        return x if unit is None else x.to(unit)
+    if hasattr(x, "unmasked") and hasattr(x, "mask"):            # astropy Masked -> NaN where masked
+        data = np.array(getattr(x.unmasked, "value", x.unmasked), dtype=float)
+        data[np.asarray(x.mask, dtype=bool)] = np.nan
+        return Quantity(data, u._as_unit(getattr(x.unmasked, "unit", unit)))
+    if isinstance(x, np.ma.MaskedArray):
+        data = np.array(x.filled(np.nan), dtype=float)
+        return Quantity(data, unit)
+    if u.is_quantity(x):
+        return Quantity(x)
+    arr = np.asarray(x)
+    if arr.dtype.kind not in "f":
+        arr = arr.astype(float)
+    return Quantity(arr, unit, dtype=arr.dtype)
+
+
+class LightCurve:
+    """Time series of flux values (subset of lightkurve.LightCurve).
+
+    Parameters mirror the reference: ``LightCurve(data=None, *, time=None, flux=None,
+    flux_err=None, **kwargs)``; deprecated keywords ``flux_unit``, ``time_format``,
+    ``time_scale``, ``targetid``, ``label`` are accepted (lightcurve.py:327-333).
+    """
+
+    _default_time_format = "jd"
+    _default_time_scale = "tdb"
+
+    def __init__(self, data=None, *args, time=None, flux=None, flux_err=None, meta=None, **kwargs):
+        if len(args) in (1, 2):                       # deprecated positional form (time, flux[, flux_err])
+            time, flux, data = data, args[0], None
+            if len(args) == 2:
+                flux_err = args[1]
+        if isinstance(data, dict):
+            time = data.get("time", time)
+            flux = data.get("flux", flux)
+            flux_err = data.get("flux_err", flux_err)
+        elif data is not None:
+            raise TypeError("`data` must be a dict with 'time'/'flux'[/'flux_err'] in this build")
+        flux_unit = kwargs.pop("flux_unit", None)
+        time_format = kwargs.pop("time_format", self._default_time_format)
+        time_scale = kwargs.pop("time_scale", self._default_time_scale)
+        self.meta = dict(meta) if meta else {}
+        for kw in ("targetid", "label"):
+            if kw in kwargs:
+                self.meta[kw.upper()] = kwargs.pop(kw)
+        self.meta.update({k.upper(): v for k, v in kwargs.items() if k.isupper() or k in ("mission", "sector")})
+
+        if time is None and flux is not None:
+            time = np.arange(len(flux))                              # :388-389
+        if time is None:
+            time = np.zeros(0)
+        if not isinstance(time, Time):
+            time = Time(time, format=time_format, scale=time_scale)
+        if flux is None:
+            flux = np.full(len(time), np.nan)
+        flux = _as_flux_quantity(flux, flux_unit)
+        if flux_err is None:
+            flux_err = np.full(len(flux), np.nan)                     # :458-460
+        flux_err = _as_flux_quantity(flux_err, None if u.is_quantity(flux_err) else flux.unit)
+        if not (len(time) == len(flux) == len(flux_err)):
+            raise ValueError("time, flux and flux_err must have the same length")
+        self.time = time
+        self.flux = flux
+        self.flux_err = flux_err
+
+    # ------------------------------------------------------------------ container protocol
+    def __len__(self):
+        return len(self.time)
+
+    def __repr__(self):
+        return "<LightCurve length={} label={!r}>".format(len(self), self.label)
+
+    @property
+    def targetid(self):
+        return self.meta.get("TARGETID")
+
+    @property
+    def label(self):
+        return self.meta.get("LABEL")
+
+    def copy(self, copy_data=True):
+        new = self.__class__.__new__(self.__class__)
+        new.meta = _copy.deepcopy(self.meta)
+        new.time = self.time.copy() if copy_data else self.time
+        new.flux = self.flux.copy() if copy_data else self.flux
+        new.flux_err = self.flux_err.copy() if copy_data else self.flux_err
+        return new
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return getattr(self, key)
+        if isinstance(key, (int, np.integer)):
+            key = slice(key, key + 1 if key != -1 else None)
+        new = self.copy(copy_data=False)
+        new.time = Time(self.time.value[key], self.time.format, self.time.scale)
+        new.flux = Quantity(self.flux.value[key], self.flux.unit, dtype=self.flux.dtype)
+        new.flux_err = Quantity(self.flux_err.value[key], self.flux_err.unit, dtype=self.flux_err.dtype)
+        return new
+
+    def __setitem__(self, key, value):
+        if isinstance(key, str):
+            setattr(self, key, value)
+            return
+        # row assignment, e.g. lc[400:500] = np.nan (tests/test_periodogram.py:39)
+        self.flux.view(np.ndarray)[key] = value
+        self.flux_err.view(np.ndarray)[key] = value
+
+    def _binop(self, other, op):
+        new = self.copy()
+        if isinstance(other, LightCurve):
+            if len(other) != len(self):
+                raise ValueError("Cannot combine LightCurve objects of different length.")
+            a, b = self.flux, other.flux
+            if op in ("add", "sub"):
+                new.flux = a + b if op == "add" else a - b
+                new.flux_err = np.hypot(self.flux_err, other.flux_err)
+            elif op == "mul":
+                new.flux = a * b
+                new.flux_err = abs(new.flux) * np.hypot((self.flux_err / a).value, (other.flux_err / b).value)
+            else:
+                new.flux = a / b
+                new.flux_err = abs(new.flux) * np.hypot((self.flux_err / a).value, (other.flux_err / b).value)
+            return new
+        if op == "add":
+            new.flux = self.flux + other
+        elif op == "sub":
+            new.flux = self.flux - other
+        elif op == "mul":
+            new.flux = self.flux * other
+            new.flux_err = self.flux_err * abs(other)
+        else:
+            new.flux = self.flux / other
+            new.flux_err = self.flux_err / abs(other)
+        return new
+
+    def __add__(self, other):
+        return self._binop(other, "add")
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._binop(other, "sub")
+
+    def __rsub__(self, other):
+        return (-1 * self).__add__(other)
+
+    def __mul__(self, other):
+        return self._binop(other, "mul")
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        return self._binop(other, "div")
+
+    # ------------------------------------------------------------------ cleaning
+    def remove_nans(self, column="flux"):
+        """Removes cadences where ``column`` is a NaN (lightcurve.py:1300-1327)."""
+        return self[~np.isnan(np.asarray(getattr(self, column).value))]
+
+    def normalize(self, unit="unscaled"):
+        """Divide flux and flux_err by the median flux (lightcurve.py:1216-1298).
+        The median/std are batched-select kernel results (K6)."""
+        validate_method(unit, ["unscaled", "percent", "ppt", "ppm"])
+        from . import engine
+        med, sd = engine.nanmedian_std([np.asarray(self.flux.value, dtype=np.float64)])
+        median_flux, std_flux = float(med[0]), float(sd[0])
+        if (median_flux == 0) or (np.isfinite(std_flux) and (np.abs(median_flux) < 0.5 * std_flux)):
+            warnings.warn(
+                "The light curve appears to be zero-centered "
+                "(median={:.2e} +/- {:.2e}); `normalize()` will divide "
+                "the light curve by a value close to zero, which is "
+                "probably not what you want."
+                "".format(median_flux, std_flux),
+                LightkurveWarning,
+            )
+        if median_flux < 0:
+            warnings.warn(
+                "The light curve has a negative median flux ({:.2e});"
+                " `normalize()` will therefore divide by a negative "
+                "number and invert the light curve, which is probably"
+                "not what you want".format(median_flux),
+                LightkurveWarning,
+            )
+        lc = self.copy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lc.flux = Quantity(self.flux.value / median_flux, u.dimensionless_unscaled)
+            lc.flux_err = Quantity(self.flux_err.value / median_flux, u.dimensionless_unscaled)
+        if unit == "percent":
+            lc.flux, lc.flux_err = lc.flux.to(u.percent), lc.flux_err.to(u.percent)
+        elif unit in ("ppt", "ppm"):
+            lc.flux, lc.flux_err = lc.flux.to(unit), lc.flux_err.to(unit)
+        lc.meta["NORMALIZED"] = True
+        return lc
+
+    def remove_outliers(self, sigma=5.0, sigma_lower=None, sigma_upper=None, return_mask=False, **kwargs):
+        """Sigma-clip outliers (lightcurve.py:1429-1549; astropy sigma_clip defaults:
+        maxiters=5, median centre, std).  Centre/spread come from the GPU select kernel."""
+        from . import engine
+        maxiters = kwargs.pop("maxiters", 5)
+        lo_s = sigma if sigma_lower is None else sigma_lower
+        hi_s = sigma if sigma_upper is None else sigma_upper
+        data = np.array(self.flux.value, dtype=np.float64)
+        mask = ~np.isfinite(data)
+        it = 0
+        while maxiters is None or it < maxiters:
+            it += 1
+            work = np.where(mask, np.nan, data)
+            if np.isnan(work).all():
+                break
+            med, sd = engine.nanmedian_std([work])
+            with np.errstate(invalid="ignore"):
+                new = mask | (data < med[0] - sd[0] * lo_s) | (data > med[0] + sd[0] * hi_s)
+            if new.sum() == mask.sum():
+                break
+            mask = new
+        if return_mask:
+            return self[~mask], mask
+        return self[~mask]
+
+    # ------------------------------------------------------------------ hot path: flatten
+    def flatten(self, window_length=101, polyorder=2, return_trend=False, break_tolerance=5, niters=3, sigma=3,
+                mask=None, **kwargs):
+        """Removes the low frequency trend with a Savitzky-Golay filter (lightcurve.py:943-1078).
+
+        Same parameters as the reference.  ``mask`` True = cadence NOT used for the fit.  The
+        whole loop (sigma-clip pre-mask, gap segmentation, savgol, residual clip, interp1d) runs
+        in the CUDA kernel ``lkb_flatten``; extra ``**kwargs`` for scipy's savgol_filter are not
+        supported (the kernel implements the reference's own call: mode="interp", deriv=0).
+        """
+        if kwargs:
+            raise TypeError("flatten(): unsupported savgol_filter keyword(s) %s" % sorted(kwargs))
+        from . import engine
+        if polyorder >= window_length:
+            polyorder = window_length - 1
+            log.warning("polyorder must be smaller than window_length, "
+                        "using polyorder={}.".format(polyorder))
+        t = np.asarray(self.time.value, dtype=np.float64)
+        f = np.asarray(self.flux.value)
+        out_dtype = f.dtype if f.dtype == np.float32 else np.float64
+        m = None if mask is None else [np.asarray(mask, dtype=bool)]
+        flat, flat_err, trend = engine.flatten([t], [f.astype(np.float64)],
+                                               [np.asarray(self.flux_err.value, dtype=np.float64)], m,
+                                               window_length=window_length, polyorder=polyorder,
+                                               break_tolerance=break_tolerance, niters=niters, sigma=sigma)
+        return self._wrap_flatten(flat[0].astype(out_dtype), flat_err[0].astype(out_dtype),
+                                  trend[0].astype(out_dtype), return_trend)
+
+    def _wrap_flatten(self, flat, flat_err, trend, return_trend):
+        flatten_lc = self.copy()
+        flatten_lc.flux = Quantity(flat, u.dimensionless_unscaled)
+        flatten_lc.flux_err = Quantity(flat_err, u.dimensionless_unscaled)
+        flatten_lc.meta["NORMALIZED"] = True
+        if return_trend:
+            trend_lc = self.copy()
+            trend_lc.flux = Quantity(trend, self.flux.unit)
+            return flatten_lc, trend_lc
+        return flatten_lc
+
+    def estimate_cdpp(self, transit_duration=13, savgol_window=101, savgol_polyorder=2, sigma=5.0):
+        """Savitzky-Golay CDPP noise metric in ppm (lightcurve.py:1764-1833)."""
+        if not isinstance(transit_duration, int):
+            raise ValueError(
+                "transit_duration must be an integer in units "
+                "number of cadences, got {}.".format(transit_duration)
+            )
+        detrended_lc = self.flatten(window_length=savgol_window, polyorder=savgol_polyorder)
+        cleaned_lc = detrended_lc.remove_outliers(sigma=sigma)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", LightkurveWarning)
+            normalized_lc = cleaned_lc.normalize("ppm")
+        mean = running_mean(data=np.asarray(normalized_lc.flux.value), window_size=transit_duration)
+        return Quantity(np.std(mean), u.ppm)
+
+    # ------------------------------------------------------------------ hot path: periodograms
+    def to_periodogram(self, method="lombscargle", **kwargs):
+        """Converts the light curve to a Periodogram (lightcurve.py:2490-2535).
+        method : {'lombscargle', 'boxleastsquares', 'ls', 'bls'}"""
+        supported_methods = ["ls", "bls", "lombscargle", "boxleastsquares"]
+        method = validate_method(method.replace(" ", ""), supported_methods)
+        if method in ["bls", "boxleastsquares"]:
+            from .periodogram import BoxLeastSquaresPeriodogram
+            return BoxLeastSquaresPeriodogram.from_lightcurve(lc=self, **kwargs)
+        from .periodogram import LombScarglePeriodogram
+        return LombScarglePeriodogram.from_lightcurve(lc=self, **kwargs)
+
+    def to_corrector(self, method="regression", **kwargs):
+        """Returns a corrector object (lightcurve.py:2732); only 'regression' is in scope."""
+        method = validate_method(method, ["regression"])
+        from .correctors import RegressionCorrector
+        return RegressionCorrector(self, **kwargs)
+
+    # ------------------------------------------------------------------ BLS follow-ups (host-side, cheap)
+    def create_transit_mask(self, period, transit_time, duration):
+        """True for in-transit cadences (lightcurve.py:2967-3037)."""
+        period = np.atleast_1d(getattr(period, "value", period)).astype(float)
+        duration = np.atleast_1d(getattr(duration, "value", duration)).astype(float)
+        transit_time = np.atleast_1d(getattr(transit_time, "value", transit_time)).astype(float)
+        t = np.asarray(self.time.value, dtype=float)
+        in_transit = np.zeros(len(t), dtype=bool)
+        for per, dur, t0 in zip(period, duration, transit_time):
+            hp = per * 0.5
+            in_transit |= np.abs((t - t0 + hp) % per - hp) < 0.5 * dur
+        return in_transit
