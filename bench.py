@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py - the headline benchmark of the hot path (BASELINE.json: Lomb-Scargle throughput in
+frequency-bins x cadences / s; config[1] at N=1: 1024 Kepler long-cadence light curves (65 000
+cadences, shared time grid) x 1e5 frequencies).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels via the C ABI)
+  python bench.py --impl reference ...                     # the reference's CPU algorithm (oracle port
+                                                           #   of astropy LombScargle method="fast")
+For N > 1 launch with torchrun (one rank per GPU): the batch is sharded BY TARGET, every rank
+processes its own 1024 light curves (weak scaling) and one NCCL all-gather reassembles the power
+array (the only collective of the path).
+
+One JSON line on stdout (rank 0).  A "step" = one pass of lkb_ls_power_shared over the batch.
+  value   : whole-job F*N*B_total / time, inputs resident in HBM (CUDA events, max over ranks)
+  e2e     : same metric through the same C-ABI call with HOST buffers: pinned H2D of the flux
+            matrix and D2H of the power array inside the timed region
+  roofline: tensor roofline of the dominant kernel (ls_tc_kernel): algorithmic flops 4*F*N*B per
+            launch / CUDA-event duration of that kernel, vs MEASURED_PEAKS.json bf16 sustained
+  cpu_baseline: the oracle port of the reference default (astropy "fast" extirpolation+FFT),
+            timed on a bounded sample of the same workload on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lombscargle_freqbins_x_cadences_per_s"
+UNIT = "bin*cadence/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "c2": dict(B=1024, N=65000, F=100000, desc="1024 Kepler LC (65000 cadences, shared grid) x 1e5 frequencies"),
+    # reduced shapes for debugging only (never the reported number)
+    "c2_small": dict(B=256, N=8192, F=4096, desc="DEBUG 256 x 8192 x 4096"),
+}
+
+
+def make_workload(name, seed):
+    """Kepler grid t = 131.5 + c*0.0204336 d, c = 71 500 consecutive cadence
+    numbers with ~9 % deleted in 18 contiguous gaps -> N cadences shared by the batch; flux = 1 + up to
+    3 sinusoids (A~LogU(1e-4,1e-2), f~U(0.05,20)/d) + N(0, sigma_b), fp32; F regular frequencies,
+    f0 = df = 1/(5*baseline); amplitude normalisation."""
+    w = WORKLOADS[name]
+    B, N, F = w["B"], w["N"], w["F"]
+    rng = np.random.default_rng(seed)
+    ntot = int(round(N * 1.1))
+    keep = np.ones(ntot, bool)
+    ndel = ntot - N
+    cuts = np.sort(rng.choice(ntot - ndel // 18 - 2, 18, replace=False))
+    for i, c in enumerate(cuts):
+        keep[c:c + ndel // 18 + (1 if i < ndel % 18 else 0)] = False
+    idx = np.flatnonzero(keep)
+    if len(idx) > N:
+        idx = idx[:N]
+    elif len(idx) < N:                          # overlapping gaps: top up with the first deleted cadences
+        extra = np.flatnonzero(~keep)[:N - len(idx)]
+        idx = np.sort(np.concatenate([idx, extra]))
+    t = 131.5 + idx * 0.0204336
+    Y = np.ones((B, N), dtype=np.float32)
+    chunk = 64
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        acc = np.zeros((nb, N))
+        for _ in range(3):
+            A = 10 ** rng.uniform(-4, -2, (nb, 1))
+            f = rng.uniform(0.05, 20, (nb, 1))
+            ph = rng.uniform(0, 2 * np.pi, (nb, 1))
+            acc += A * np.sin(2 * np.pi * f * t[None, :] + ph)
+        sig = 10 ** rng.uniform(np.log10(5e-5), -3, (nb, 1))
+        acc += sig * rng.standard_normal((nb, N))
+        Y[b0:b0 + nb] = (1.0 + acc).astype(np.float32)
+    df = 1.0 / (5.0 * (t[-1] - t[0]))
+    freq = df * (1 + np.arange(F))
+    return t, Y, freq
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # under load = samples above half of the max seen
+        load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _cpu_ls_worker(args):
+    from oracle import ls as ols
+    t, y, f0, df, nf = args
+    p = ols.ls_fast_psd(t, y.astype(np.float64), f0, df, nf)
+    return float(np.sqrt(p[-1]))
+
+
+def cpu_reference_rate(t, Y, freq, n_lc, procs):
+    """Reference CPU path (oracle port of astropy LombScargle(...).power(method='fast'), the
+    lightkurve default) on `n_lc` light curves of the workload, `procs` worker processes.
+    Returns (bin*cadence/s equivalent, seconds)."""
+    from multiprocessing import get_context
+    f0, df, nf = float(freq[0]), float(freq[1] - freq[0]), len(freq)
+    jobs = [(t, Y[i % len(Y)], f0, df, nf) for i in range(n_lc)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        for j in jobs:
+            _cpu_ls_worker(j)
+    else:
+        with get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_ls_worker, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return len(freq) * len(t) * n_lc / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU algorithm on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    name = args.workload
+    w = WORKLOADS[name]
+    t, Y, freq = make_workload_sample(name, args.seed)
+    cores = os.cpu_count() or 1
+    n_lc = max(cores, 8)
+    for _ in range(args.warmup):
+        cpu_reference_rate(t, Y, freq, min(n_lc, cores), cores)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, _ = cpu_reference_rate(t, Y, freq, n_lc, cores)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s; CPU sample = %d light curves per step" % (name, w["desc"], n_lc)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of %d light curves per step, astropy 'fast' (extirpolation+FFT) restated in "
+                                   "oracle/ls.py, %d processes" % (n_lc, w["B"], cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_workload_sample(name, seed, n_lc=16):
+    """Same generator, but only the first `n_lc` light curves (the CPU legs never need the full batch)."""
+    w = dict(WORKLOADS[name])
+    full_B = w["B"]
+    WORKLOADS["_sample"] = dict(w, B=min(n_lc, full_B))
+    try:
+        return make_workload("_sample", seed)
+    finally:
+        del WORKLOADS["_sample"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--seed", type=int, default=1002)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from lightkurve_b200 import engine
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    engine.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = WORKLOADS[args.workload]
+    B, N, F = w["B"], w["N"], w["F"]
+    t, Y, freq = make_workload(args.workload, args.seed + rank)      # every rank: its own 1024 targets
+    dev = torch.device("cuda", local_rank)
+    d_t = torch.tensor(t, device=dev)
+    d_f = torch.tensor(freq, device=dev)
+    d_Y = torch.tensor(Y, device=dev)
+    d_P = torch.empty((B, F), dtype=torch.float32, device=dev)
+    d_all = torch.empty((world * B, F), dtype=torch.float32, device=dev) if world > 1 else None
+    h_Y = torch.from_numpy(Y).pin_memory()
+    h_P = torch.empty((B, F), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo=args.algo, out=d_P)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_P)
+
+    def step_e2e():
+        d_Y.copy_(h_Y, non_blocking=True)                     # H2D of this step's inputs (pinned)
+        engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo=args.algo, out=d_P)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_P)
+        h_P.copy_(d_P, non_blocking=True)                     # D2H of this step's result (pinned)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    engine.profile_enable(True)
+    l0 = engine.launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = engine.launch_count() - l0
+    kms = engine.profile_read()
+    engine.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    units_per_step = float(F) * N * B * world
+    value = units_per_step * args.steps / (ms_res * 1e-3)
+    e2e = units_per_step * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        k_ms = float(np.mean(kms)) if len(kms) else float("nan")
+        flops = 4.0 * F * N * B                                # algorithmic: 2 (cos,sin) x 2 flop per MAC
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None, "kernel": "ls_tc_kernel" if args.algo != "simt"
+                    else "ls_shared_simt_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                    "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
+        cpu = None
+        if not args.no_cpu_baseline:
+            ts, Ys, fs = t, Y[:8], freq
+            rate, secs = cpu_reference_rate(ts, Ys, fs, 8, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "8 of %d light curves (%.1f s), astropy method='fast' (lightkurve default) restated "
+                             "in oracle/ls.py, 1 process; equivalent bin*cadence/s = F*N*n/time" % (B, secs)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x2-split in / f32 accumulate (tcgen05), f64 phase",
+            "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_per_gpu": B, "cadences": N,
+                       "frequencies": F, "normalization": "amplitude", "algo": args.algo,
+                       "sharding": "by target, %d rank(s), NCCL all-gather of power" % world,
+                       "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((Y.nbytes + B * F * 4) / 1e6)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(Y.nbytes) * world,
+                    "d2h_bytes_per_step": int(B * F * 4) * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

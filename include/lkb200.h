@@ -63,6 +63,12 @@ int lkb_shutdown(void);                /* free the workspace pool */
 int lkb_sm_count(void);                /* multiprocessor count of the bound device */
 /* counters: number of kernels this library launched since init (bench gpu_launches) */
 int64_t lkb_launch_count(void);
+/* Measurement hooks (bench.py roofline): when enabled, every compute call records CUDA events on
+ * its stream around its DOMINANT kernel (LS contraction / BLS search / flatten / Gram accumulation).
+ * lkb_profile_read synchronises, writes up to max_n durations [ms] in call order, resets the ring
+ * and returns how many were written (< 0 on error). */
+int lkb_profile_enable(int on);
+int lkb_profile_read(double* ms_out, int max_n);
 
 /* ---- Lomb-Scargle ------------------------------------------------------- */
 /* K1: ragged batch, one (time, flux) pair per light curve; replaces
@@ -127,6 +133,12 @@ int lkb_flatten(const double* time, const double* flux, const double* flux_err,
                 const uint8_t* exclude_mask, const int64_t* offsets, int B,
                 int window_length, int polyorder, double break_tolerance, int niters, double sigma,
                 double* flat, double* flat_err, double* trend, int mem, void* stream);
+
+/* Host-only helper (no GPU needed): the Savitzky-Golay tables lkb_flatten uploads -
+ * coeffs[w] = scipy.signal.savgol_coeffs(w, p) (symmetric FIR) and edge[w*(w/2)] with
+ * edge[j*(w/2)+i] = weight of x[j] in the degree-p polynomial fit of the first w samples
+ * evaluated at position i (scipy _fit_edges_polyfit).  Exposed so CPU tests can pin them. */
+int lkb_savgol_tables(int window_length, int polyorder, double* coeffs, double* edge);
 
 /* ---- RegressionCorrector -------------------------------------------------- */
 /* K5: replaces _fit_coefficients + the correct() loop,

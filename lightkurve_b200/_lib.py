@@ -31,6 +31,8 @@ SIGNATURES = {
     "lkb_shutdown": (c_int, []),
     "lkb_sm_count": (c_int, []),
     "lkb_launch_count": (c_i64, []),
+    "lkb_profile_enable": (c_int, [c_int]),
+    "lkb_profile_read": (c_int, [c_vp, c_int]),
     "lkb_ls_power": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
     "lkb_ls_power_shared": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_int,
                                     c_vp, c_int]),
@@ -41,6 +43,7 @@ SIGNATURES = {
                             c_vp, c_vp, c_vp, c_int, c_vp]),
     "lkb_regress": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_dbl, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "lkb_savgol_tables": (c_int, [c_int, c_int, c_vp, c_vp]),
     "lkb_nanmedian_std": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
 }
 

@@ -56,6 +56,26 @@ int ensure_device() {
 
 int sm_count() { return g_ctx.sms; }
 
+// ---- dominant-kernel profiling ring ----
+constexpr int PROF_MAX = 512;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[PROF_MAX][2];
+static bool g_prof_created = false;
+void prof_begin(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  if (!g_prof_created) {
+    for (int i = 0; i < PROF_MAX; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
+    g_prof_created = true;
+  }
+  cudaEventRecord(g_prof_ev[g_prof_n][0], st);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[g_prof_n][1], st);
+  g_prof_n++;
+}
+
 int ws_get(int slot, size_t bytes, void** out) {
   if (slot < 0 || slot >= WS_NSLOTS) { set_error("bad workspace slot"); return LKB_E_ARG; }
   if (bytes == 0) bytes = 16;
@@ -93,6 +113,7 @@ int flatten(const double*, const double*, const double*, const uint8_t*, const i
 int regress(const double*, int, const double*, const double*, const uint8_t*, const double*, const double*, int,
             int64_t, int, double, int, double*, double*, uint8_t*, int32_t*, int, cudaStream_t);
 int nanmedian_std(const double*, const int64_t*, int, double*, double*, int, cudaStream_t);
+int savgol_tables_host(int, int, double*, double*);
 
 }  // namespace lkb
 
@@ -137,6 +158,26 @@ int lkb_shutdown(void) {
 }
 
 int lkb_sm_count(void) { return g_ctx.inited ? g_ctx.sms : 0; }
+
+int lkb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+  return LKB_OK;
+}
+
+int lkb_profile_read(double* ms_out, int max_n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int n = g_prof_n < max_n ? g_prof_n : max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof_ev[i][1]) != cudaSuccess) { set_error("profile event sync failed"); return LKB_E_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof_ev[i][0], g_prof_ev[i][1]);
+    ms_out[i] = (double)ms;
+  }
+  g_prof_n = 0;
+  return n;
+}
 int64_t lkb_launch_count(void) { return g_launches; }
 
 int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B, const double* freq,
@@ -184,6 +225,10 @@ int lkb_regress(const double* X, int x_batched, const double* y, const double* f
   std::lock_guard<std::mutex> lk(g_mu);
   return regress(X, x_batched, y, flux_err, cadence_mask, prior_mu, prior_sigma, B, N, K, clip_sigma, niters, coeff,
                  model, outlier_mask, status_out, mem, (cudaStream_t)stream);
+}
+
+int lkb_savgol_tables(int window_length, int polyorder, double* coeffs, double* edge) {
+  return savgol_tables_host(window_length, polyorder, coeffs, edge);
 }
 
 int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B, double* out_median, double* out_std, int mem,

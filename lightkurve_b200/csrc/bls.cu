@@ -397,6 +397,7 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
     attr_set = true;
   }
   int64_t p0 = 0;
+  prof_begin(st);
   while (p0 < P) {
     int nb_min = (int)ceil(h_per[p0] / bin_duration) + oversample, nb_max = nb_min;
     int64_t p1 = p0 + 1;
@@ -434,6 +435,7 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
     LKB_LAUNCH_CHECK();
     p0 = p1;
   }
+  prof_end(st);
 
   LKB_TRY(stage_out_copy<double>(mem, power, o0, outn, st));
   LKB_TRY(stage_out_copy<double>(mem, depth, o1, outn, st));

@@ -67,6 +67,10 @@ inline int ws_get_t(int slot, size_t count, T** out) {
 }
 int ensure_device();
 int sm_count();
+// optional per-launch timing of the dominant kernel of a call (bench.py roofline):
+// CUDA events recorded on the launching stream around that kernel when profiling is enabled.
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 // Stage a host buffer into the pool (or pass a device pointer through).
 template <typename T>

@@ -339,6 +339,16 @@ static bool savgol_tables(int w, int p, std::vector<double>& coeffs, std::vector
   return true;
 }
 
+int savgol_tables_host(int w, int p, double* coeffs, double* edge) {
+  LKB_REQUIRE(w >= 1 && (w & 1), "window_length must be a positive odd integer");
+  LKB_REQUIRE(p >= 0 && p < w && p <= 12, "polyorder must be in [0, min(window_length-1, 12)]");
+  std::vector<double> c, e;
+  if (!savgol_tables(w, p, c, e)) { set_error("singular Savitzky-Golay system"); return LKB_E_SINGULAR; }
+  if (coeffs) memcpy(coeffs, c.data(), sizeof(double) * w);
+  if (edge && w / 2 > 0) memcpy(edge, e.data(), sizeof(double) * (size_t)w * (w / 2));
+  return LKB_OK;
+}
+
 int flatten(const double* time, const double* flux, const double* flux_err, const uint8_t* exclude_mask,
             const int64_t* h_offsets, int B, int window_length, int polyorder, double break_tolerance, int niters,
             double sigma, double* flat, double* flat_err, double* trend, int mem, cudaStream_t st) {
@@ -398,8 +408,10 @@ int flatten(const double* time, const double* flux, const double* flux_err, cons
     LKB_CUDA_CHECK(cudaFuncSetAttribute(flatten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
+  prof_begin(st);
   flatten_kernel<<<B, FL_THREADS, smem, st>>>(d_t, d_f, d_fe, d_ex, d_off, ws, window_length, polyorder,
                                             break_tolerance, niters, sigma, d_c, d_e, o_flat, o_fe, o_tr);
+  prof_end(st);
   LKB_LAUNCH_CHECK();
   LKB_TRY(stage_out_copy<double>(mem, flat, o_flat, total, st));
   LKB_TRY(stage_out_copy<double>(mem, flat_err, o_fe, total, st));

@@ -424,8 +424,10 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 
   dim3 grid((unsigned)((Fmax + LS_FPB - 1) / LS_FPB), (unsigned)B);
   LKB_REQUIRE(B <= 65535, "lkb_ls_power: B > 65535 per call (split the batch)");
+  prof_begin(st);
   ls_direct_kernel<<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, normalization, d_ns,
                                                    d_pow);
+  prof_end(st);
   LKB_LAUNCH_CHECK();
   LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
   if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -500,8 +502,10 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
       attr_set = true;
     }
     dim3 grid((unsigned)((F + SG_BM - 1) / SG_BM), (unsigned)((B + SG_BN - 1) / SG_BN));
+    prof_begin(st);
     ls_shared_simt_kernel<<<grid, 256, 2 * sizeof(SgStage), st>>>(d_t, N, Npad, d_yc, B, d_freq, F, d_rot,
                                                                  normalization, ns, d_pow);
+    prof_end(st);
     LKB_LAUNCH_CHECK();
   }
   LKB_TRY(stage_out_copy<float>(mem, power, d_pow, (size_t)B * F, st));

@@ -16,6 +16,13 @@
 // (Ah*Yh + Ah*Yl + Al*Yh; Al*Yl ~ 2^-22 is dropped), fp32 accumulation in TMEM.
 // Roofline: algorithmic flops = 4 F N B; issued tensor flops = 3x that.
 //
+// Accumulation (measured on B200, profiles/): tcgen05 adds into the fp32 accumulator with
+// TRUNCATION, so a chain of k MMAs shrinks the sum by ~0.35 k 2^-24 (2.5e-4 at 65 000 cadences,
+// 12 k chained MMAs - outside the LS tolerance).  The cadence axis is therefore split into
+// segments of <= TC_SEG_STAGES pipeline stages (split-K): blockIdx.z owns one segment, writes
+// its fp32 partial (Ch, Sh) tile, and ls_tc_finish_kernel sums the segments with
+// round-to-nearest CUDA-core adds before the epilogue.
+//
 // Warp roles (320 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM
 // owner, warps 2..9 = design-matrix generators; warps 2..5 double as the epilogue (their
 // warp_id % 4 covers the four TMEM lane quadrants).
@@ -24,6 +31,7 @@
 #include "ls_common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace lkb {
 
@@ -38,6 +46,7 @@ constexpr int TC_Y_TILE = TC_BN * TC_BK * 2;          // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE + 2 * TC_Y_TILE;   // 64 KB
 constexpr float TC_A_SCALE = 256.0f;                  // 2^8: keeps fp16 residuals of cos/sin normal
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SEG_STAGES = 128;    // <= 4096 cadences (768 chained MMAs) per accumulator chain
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row atoms of 512 B (SBO), version 1.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
@@ -83,10 +92,12 @@ struct TcParams {
   const float4* rot;      // [F]
   const float* inv_scale; // [B]
   float* power;           // [B, F]
+  float* part;            // [nseg, 2, B, F] partial (Ch, Sh) when nseg > 1
   int64_t N, Npad, F;
   int B;
   int normalization;
   float norm_scale;
+  int seg_stages, nseg;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -105,7 +116,9 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
   const int b0 = blockIdx.y * TC_BN;
-  const int nst = (int)(p.Npad / TC_BK);
+  const int nst_total = (int)(p.Npad / TC_BK);
+  const int st0 = blockIdx.z * p.seg_stages;
+  const int nst = min(p.seg_stages, nst_total - st0);      // stages of this segment (local index `it`)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -134,8 +147,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
         unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(&full_y[s], 2 * TC_Y_TILE);
-        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b0, &full_y[s]);
-        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, it * TC_BK, p.B + b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, (st0 + it) * TC_BK, b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, (st0 + it) * TC_BK, p.B + b0, &full_y[s]);
       }
     }
   } else if (warp == 1) {
@@ -180,7 +193,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       const int s = it % TC_STAGES;
       if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-      const double* tp = p.t + (int64_t)it * TC_BK + kh * 16;
+      const double* tp = p.t + (int64_t)(st0 + it) * TC_BK + kh * 16;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {                       // two 16-byte chunks (8 cadences each)
         uint32_t ch[4], cl[4], sh[4], sl[4];
@@ -232,7 +245,13 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
           if (f_ok && b < p.B) {
             const float h = p.inv_scale[b];
             const float chv = __uint_as_float(vc[j]) * h, shv = __uint_as_float(vs[j]) * h;
-            p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(chv, shv, r, Nf, p.normalization, p.norm_scale);
+            if (p.nseg == 1) {
+              p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(chv, shv, r, Nf, p.normalization, p.norm_scale);
+            } else {
+              float* pc = p.part + ((int64_t)(blockIdx.z * 2) * p.B + b) * p.F + f;
+              pc[0] = chv;
+              pc[(int64_t)p.B * p.F] = shv;
+            }
           }
         }
       }
@@ -241,6 +260,23 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   }
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// sum the split-K partials (round-to-nearest fp32 adds) and apply the epilogue
+__global__ void __launch_bounds__(256)
+ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, const float4* __restrict__ rot,
+                    float N, int normalization, float norm_scale, float* __restrict__ power) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (f >= F) return;
+  const int64_t plane = (int64_t)B * F;
+  const float* pc = part + (int64_t)b * F + f;
+  float ch = 0.f, sh = 0.f;
+  for (int s = 0; s < nseg; ++s) {
+    ch += pc[(int64_t)(2 * s) * plane];
+    sh += pc[(int64_t)(2 * s + 1) * plane];
+  }
+  power[(int64_t)b * F + f] = ls_epilogue_shared(ch, sh, rot[f], N, normalization, norm_scale);
 }
 
 // ---- host -------------------------------------------------------------------------------------
@@ -293,12 +329,29 @@ int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, 
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     attr_set = true;
   }
+  const int nst_total = (int)(Npad / TC_BK);
+  int seg_cap = TC_SEG_STAGES;
+  if (const char* e = getenv("LKB_TC_SEG_STAGES")) { const int v = atoi(e); if (v > 0) seg_cap = v; }
+  const int nseg0 = (nst_total + seg_cap - 1) / seg_cap;
+  const int seg_stages = (nst_total + nseg0 - 1) / nseg0;     // balanced segments
+  const int nseg = (nst_total + seg_stages - 1) / seg_stages; // every segment non-empty
+  float* d_part = nullptr;
+  if (nseg > 1) LKB_TRY(ws_get_t<float>(WS_J, (size_t)nseg * 2 * B * F, &d_part));
+
   TcParams p;
-  p.t = d_t; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow;
+  p.t = d_t; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
-  dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
+  p.seg_stages = seg_stages; p.nseg = nseg;
+  dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN), (unsigned)nseg);
+  prof_begin(st);
   ls_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  prof_end(st);
   LKB_LAUNCH_CHECK();
+  if (nseg > 1) {
+    ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(
+        d_part, nseg, B, F, d_rot, (float)N, normalization, (float)norm_scale, d_pow);
+    LKB_LAUNCH_CHECK();
+  }
   return LKB_OK;
 }
 

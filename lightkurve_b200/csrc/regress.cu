@@ -368,7 +368,9 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
   for (int it = 0; it < niters; ++it) {
     rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, N, it == 0 ? 1 : 0, ws);
     LKB_LAUNCH_CHECK();
+    if (it == 0) prof_begin(st);
     rg_accum_kernel<<<dim3(nupper, B), 128, 0, st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk, it == 0 ? 1.0 : -1.0, ws);
+    if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
     rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, o_st);
     LKB_LAUNCH_CHECK();

@@ -41,6 +41,20 @@ def launch_count():
     return int(L.load().lkb_launch_count())
 
 
+def profile_enable(on=True):
+    """Record CUDA events around the dominant kernel of each subsequent call (see lkb200.h)."""
+    L.check(L.load().lkb_profile_enable(1 if on else 0))
+
+
+def profile_read(max_n=512):
+    """Durations [ms] of the dominant kernels launched since profile_enable / the last read."""
+    buf = np.zeros(max_n, dtype=np.float64)
+    n = L.load().lkb_profile_read(L.ptr(buf), max_n)
+    if n < 0:
+        L.check(n)
+    return buf[:n].copy()
+
+
 def sm_count():
     return int(L.load().lkb_sm_count())
 
