@@ -22,7 +22,6 @@ One JSON line on stdout (rank 0).  A "step" = one pass of lkb_ls_power_shared ov
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -83,57 +82,59 @@ def make_workload(name, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device_index):
+    def __init__(self, device_index, period_s=0.05):
         self.dev = device_index
-        self.rows = []
-        self.proc = None
+        self.period = period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.th = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.dev)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                    # pragma: no cover
+            self.err = "nvml unavailable: %r" % (e,)
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, v in bits.items():
+                    if r & v:
+                        self.reasons.add(k)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception as e:                                # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            p = [x.strip() for x in r.split(",")]
-            if len(p) < 8:
-                continue
-            try:
-                sm.append(float(p[1]))
-                smax.append(float(p[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        # under load = samples above half of the max seen
-        load = [x for x in sm if x > 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None,
-                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.th is not None:
+            self.th.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+               "reasons": sorted(self.reasons), "samples": len(self.sm),
+               "power_w_max": max(self.power) if self.power else None}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def _cpu_ls_worker(args):

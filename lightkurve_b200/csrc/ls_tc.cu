@@ -19,13 +19,15 @@
 // Accumulation (measured on B200, profiles/): tcgen05 adds into the fp32 accumulator with
 // TRUNCATION, so a chain of k MMAs shrinks the sum by ~0.35 k 2^-24 (2.5e-4 at 65 000 cadences,
 // 12 k chained MMAs - outside the LS tolerance).  The cadence axis is therefore split into
-// segments of <= TC_SEG_STAGES pipeline stages (split-K): blockIdx.z owns one segment, writes
-// its fp32 partial (Ch, Sh) tile, and ls_tc_finish_kernel sums the segments with
-// round-to-nearest CUDA-core adds before the epilogue.
+// segments of <= TC_SEG_STAGES pipeline stages: the CTA walks the segments of its tile back to
+// back (the smem pipeline never drains), four dedicated epilogue warps copy each finished
+// segment's accumulators out of TMEM as an fp32 partial (Ch, Sh) plane while the producers
+// already fill the next stages, and ls_tc_finish_kernel sums the planes with round-to-nearest
+// CUDA-core adds before the epilogue math.
 //
-// Warp roles (320 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM
-// owner, warps 2..9 = design-matrix generators; warps 2..5 double as the epilogue (their
-// warp_id % 4 covers the four TMEM lane quadrants).
+// Warp roles (448 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM
+// owner, warps 2..9 = design-matrix generators, warps 10..13 = epilogue (warp_id % 4 covers the
+// four TMEM lane quadrants).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "ls_common.cuh"
@@ -40,13 +42,14 @@ constexpr int TC_BN = 256;            // light curves per CTA (columns per accum
 constexpr int TC_BK = 32;             // cadences per pipeline stage (64-byte fp16 rows, SWIZZLE_64B)
 constexpr int TC_STAGES = 3;
 constexpr int TC_GEN_WARPS = 8;
-constexpr int TC_THREADS = (2 + TC_GEN_WARPS) * 32;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_THREADS = (2 + TC_GEN_WARPS + TC_EPI_WARPS) * 32;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;          // 8 KB
 constexpr int TC_Y_TILE = TC_BN * TC_BK * 2;          // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE + 2 * TC_Y_TILE;   // 64 KB
 constexpr float TC_A_SCALE = 256.0f;                  // 2^8: keeps fp16 residuals of cos/sin normal
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int TC_SEG_STAGES = 128;    // <= 4096 cadences (768 chained MMAs) per accumulator chain
+constexpr int TC_SEG_STAGES = 64;     // <= 2048 cadences (384 chained MMAs) per accumulator chain
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row atoms of 512 B (SBO), version 1.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
@@ -110,15 +113,14 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   uint64_t* full_y = bars;                    // [STAGES] TMA bytes landed
   uint64_t* full_a = bars + TC_STAGES;        // [STAGES] generator warps done
   uint64_t* empty = bars + 2 * TC_STAGES;     // [STAGES] MMAs of the stage retired
-  uint64_t* acc_full = bars + 3 * TC_STAGES;  // accumulators complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+  uint64_t* acc_full = bars + 3 * TC_STAGES;       // a segment's accumulators are complete
+  uint64_t* acc_empty = bars + 3 * TC_STAGES + 1;  // the epilogue warps have drained TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
   const int b0 = blockIdx.y * TC_BN;
-  const int nst_total = (int)(p.Npad / TC_BK);
-  const int st0 = blockIdx.z * p.seg_stages;
-  const int nst = min(p.seg_stages, nst_total - st0);      // stages of this segment (local index `it`)
+  const int nst = (int)(p.Npad / TC_BK);                    // all stages; segments are p.seg_stages long
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -127,6 +129,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       ptx::mbar_init(&empty[s], 1);
     }
     ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, TC_EPI_WARPS);
     ptx::mbar_fence_init();
     ptx::prefetch_tensormap(&ymap);
   }
@@ -147,8 +150,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
         unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(&full_y[s], 2 * TC_Y_TILE);
-        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, (st0 + it) * TC_BK, b0, &full_y[s]);
-        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, (st0 + it) * TC_BK, p.B + b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, it * TC_BK, p.B + b0, &full_y[s]);
       }
     }
   } else if (warp == 1) {
@@ -157,8 +160,12 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       for (int it = 0; it < nst; ++it) {
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
+        const int seg = it / p.seg_stages;
+        const bool seg_first = (it - seg * p.seg_stages) == 0;
+        const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
         ptx::mbar_wait(&full_y[s], ph);
         ptx::mbar_wait(&full_a[s], ph);
+        if (seg_first && seg > 0) ptx::mbar_wait(acc_empty, (seg - 1) & 1);   // TMEM drained by the epilogue
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
         const uint32_t a_ch = sa, a_cl = sa + TC_A_TILE, a_sh = sa + 2 * TC_A_TILE, a_sl = sa + 3 * TC_A_TILE;
@@ -166,7 +173,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           const uint32_t ko = k * 32;                      // 16 fp16 = 32 bytes along K inside the 64 B row
-          const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
+          const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
           const uint64_t dyh = tc_smem_desc(y_h + ko), dyl = tc_smem_desc(y_l + ko);
           // cos accumulator: columns [0, 256)
           ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyh, TC_IDESC, first);
@@ -178,10 +185,10 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
           ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, TC_IDESC, 1u);
         }
         ptx::umma_commit(&empty[s]);          // smem stage reusable once these MMAs retire
+        if (seg_last) ptx::umma_commit(acc_full);
       }
-      ptx::umma_commit(acc_full);
     }
-  } else {
+  } else if (warp < 2 + TC_GEN_WARPS) {
     // ================= design-matrix generators =================
     const int g = threadIdx.x - 64;                       // 0..255
     const int row = g & (TC_BM - 1);                      // frequency row inside the tile
@@ -193,7 +200,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       const int s = it % TC_STAGES;
       if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-      const double* tp = p.t + (int64_t)(st0 + it) * TC_BK + kh * 16;
+      const double* tp = p.t + (int64_t)it * TC_BK + kh * 16;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {                       // two 16-byte chunks (8 cadences each)
         uint32_t ch[4], cl[4], sh[4], sl[4];
@@ -223,16 +230,17 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
     }
 
-    // ================= epilogue (warps 2..5: TMEM lane quadrant = warp % 4) =================
-    if (warp < 6) {
-      ptx::mbar_wait(acc_full, 0);
+  } else {
+    // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
+    const int quad = warp & 3;
+    const int64_t f = f0 + quad * 32 + lane;
+    const bool f_ok = f < p.F;
+    const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const float Nf = (float)p.N;
+    for (int seg = 0; seg < p.nseg; ++seg) {
+      ptx::mbar_wait(acc_full, seg & 1);
       ptx::tc_fence_after();
-      const int quad = warp & 3;
-      const int64_t f = f0 + quad * 32 + lane;
-      const bool f_ok = f < p.F;
-      const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
-      const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-      const float Nf = (float)p.N;
 #pragma unroll 1
       for (int c0 = 0; c0 < TC_BN; c0 += 32) {
         uint32_t vc[32], vs[32];
@@ -248,7 +256,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
             if (p.nseg == 1) {
               p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(chv, shv, r, Nf, p.normalization, p.norm_scale);
             } else {
-              float* pc = p.part + ((int64_t)(blockIdx.z * 2) * p.B + b) * p.F + f;
+              float* pc = p.part + ((int64_t)(seg * 2) * p.B + b) * p.F + f;
               pc[0] = chv;
               pc[(int64_t)p.B * p.F] = shv;
             }
@@ -256,6 +264,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         }
       }
       ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
     }
   }
   __syncthreads();
@@ -342,7 +352,7 @@ int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, 
   p.t = d_t; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
-  dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN), (unsigned)nseg);
+  dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   prof_begin(st);
   ls_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
   prof_end(st);

@@ -21,6 +21,8 @@ class Unit:
     """scale * prod(base ** power).  `bases` carries the physics ('s', 'electron', 'K');
     `parts` carries the named factors used for display only (e.g. {'uHz': -1, 'electron': 2})."""
 
+    __array_ufunc__ = None          # ndarray <op> Unit defers to Unit.__r<op>__ (-> one Quantity)
+
     def __init__(self, bases=None, scale=1.0, name=None, parts=None):
         self.bases = {k: v for k, v in (bases or {}).items() if v != 0}
         self.scale = float(scale)
@@ -270,8 +272,11 @@ class Quantity(np.ndarray):
     def __getitem__(self, item):
         out = super().__getitem__(item)
         if not isinstance(out, Quantity):
-            out = np.asarray(out).view(Quantity)
+            out = np.asarray(out).view(type(self))
             out._unit = self._unit
+            for attr in ("format", "scale"):
+                if hasattr(self, attr):
+                    setattr(out, attr, getattr(self, attr))
         return out
 
     def __repr__(self):

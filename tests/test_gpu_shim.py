@@ -1,0 +1,372 @@
+"""GPU tests of the drop-in Python surface: the reference's own tests for the hot path
+(/root/reference/tests/test_periodogram.py, test_lightcurve.py, correctors/test_regressioncorrector.py)
+ported to `lightkurve_b200` - they read like the originals; matplotlib/plot calls are dropped."""
+import logging
+
+import numpy as np
+import pytest
+from numpy.testing import assert_almost_equal, assert_array_equal, assert_equal
+
+import lightkurve_b200 as lk
+from lightkurve_b200 import LightCurve, LightCurveCollection, units as u
+from lightkurve_b200.correctors import DesignMatrix, DesignMatrixCollection, RegressionCorrector
+from lightkurve_b200.units import Time
+from oracle import detrend as odet
+from oracle import ls as ols
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _bind(engine):
+    yield
+
+
+# ------------------------------------------------------------------ test_periodogram.py
+def test_periodogram_basics():
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1)
+    lc = lc.normalize()
+    pg = lc.to_periodogram()
+    str(pg)
+    assert len(pg.power) == 2497
+    lc[400:500] = np.nan
+    pg = lc.to_periodogram()
+    assert np.isfinite(pg.power.value).all()
+
+
+def test_periodogram_normalization_and_units():
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1,
+                    flux_unit="electron/second")
+    pg = lc.to_periodogram(normalization="amplitude")
+    assert pg.power.unit == u.electron / u.second
+    pg = lc.normalize(unit="ppm").to_periodogram(normalization="amplitude")
+    assert pg.power.unit == u.ppm
+    pg = lc.to_periodogram(freq_unit=u.microhertz, normalization="psd")
+    assert pg.power.unit == (u.electron / u.second) ** 2 / u.microhertz
+    pg = lc.normalize(unit="ppm").to_periodogram(freq_unit=u.microhertz, normalization="psd")
+    assert pg.power.unit == u.ppm ** 2 / u.microhertz
+    p = lc.to_periodogram(normalization="amplitude")
+    assert p.frequency.unit == 1.0 / u.day
+    assert p.period.unit == u.day
+    assert p.frequency_at_max_power.unit == 1.0 / u.day
+    assert p.max_power.unit == u.electron / u.second
+
+
+def test_periodogram_can_find_periods():
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1)
+    lc.flux += np.sin((lc.time.value / float(lc.time.value.max())) * 20 * np.pi)
+    lc = lc.normalize()
+    p = lc.to_periodogram(normalization="amplitude")
+    assert np.isclose(p.period_at_max_power.value, 100, rtol=1e-3)
+
+
+def test_psd_normalisation_matches_oracle():
+    rng = np.random.default_rng(7)
+    t = np.arange(1000.0)
+    f = rng.normal(1, 0.1, 1000)
+    lc = LightCurve(time=t, flux=f)
+    pg = lc.to_periodogram(normalization="psd", freq_unit=1 / u.day)
+    fr, p, _ = ols.lombscargle(t, f, normalization="psd", ls_method="slow")
+    np.testing.assert_allclose(pg.frequency.value, fr, rtol=1e-14)
+    np.testing.assert_allclose(pg.power.value, p, rtol=2e-4, atol=1e-5 * p.max())
+
+
+def test_assign_periods_and_frequencies():
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1)
+    periods = np.arange(1, 100) * u.day
+    p = lc.to_periodogram(period=periods)
+    assert np.isclose(np.sum(periods - p.period).value, 0, rtol=1e-14)
+    frequency = np.arange(1, 100) * u.Hz
+    p = lc.to_periodogram(frequency=frequency)
+    np.testing.assert_allclose(p.frequency.to(u.Hz).value, frequency.value, rtol=1e-14)
+    p = lc.to_periodogram(frequency=frequency, freq_unit=u.microhertz)
+    assert p.frequency.unit == u.microhertz
+    np.testing.assert_allclose(p.frequency.to(u.Hz).value, frequency.value, rtol=1e-14)
+
+
+def test_periodogram_slicing_bin_smooth_flatten():
+    np.random.seed(42)
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1)
+    p = lc.to_periodogram()
+    assert len(p[0:200].frequency) == 200
+    assert len(p.bin(binsize=10).frequency) == len(p.frequency) // 10
+    assert ((p + 100).power == (p.power + 100)).all() and ((p * 100).power == (p.power * 100)).all()
+    psd = lc.to_periodogram(normalization="psd")
+    s = psd.flatten()
+    assert s.power.unit == u.dimensionless_unscaled
+    assert np.isclose(s.power.value.mean(), 1, atol=0.2)
+    sm = psd.smooth(method="boxkernel", filter_width=Quantity_like(20, psd))
+    assert sm.power.shape == psd.power.shape
+
+
+def Quantity_like(v, pg):
+    return u.Quantity(v, pg.frequency.unit)
+
+
+def test_bls(caplog):
+    lc = LightCurve(time=np.linspace(0, 10, 200), flux=np.random.normal(100, 0.1, 200), flux_err=np.zeros(200) + 0.1)
+    p = lc.to_periodogram(method="bls")
+    keys = ["period", "power", "duration", "transit_time", "depth", "snr"]
+    assert np.all([key in dir(p) for key in keys])
+    lc.to_periodogram(method="bls", minimum_period=0.2, duration=0.1, maximum_period=0.5)
+    with pytest.raises(ValueError):
+        lc.to_periodogram(method="bls", frequency_factor=0.00001)
+    with caplog.at_level(logging.WARNING):
+        p.compute_stats()
+    for record in caplog.records:
+        assert record.levelname == "WARNING"
+    assert len(caplog.records) == 3
+    assert "No period specified." in caplog.text
+    stats = p.compute_stats(1, 0.1, 0)
+    assert len(caplog.records) == 3
+    assert isinstance(stats, dict)
+    p.get_transit_model()
+    assert len(caplog.records) == 6
+    model = p.get_transit_model(1, 0.1, 0)
+    assert len(caplog.records) == 6
+    assert isinstance(model, LightCurve)
+    assert np.isin(model.time.value, lc.time.value).all()
+    mask = p.get_transit_mask(1, 0.1, 0)
+    assert isinstance(mask, np.ndarray) and isinstance(mask[0], np.bool_)
+    assert mask.sum() < (~mask).sum()
+    assert isinstance(p.period_at_max_power, u.Quantity)
+    assert isinstance(p.duration_at_max_power, u.Quantity)
+    assert isinstance(p.transit_time_at_max_power, Time)
+    assert isinstance(p.depth_at_max_power, u.Quantity)
+
+
+def test_bls_period_recovery():
+    period, transit_time, duration, depth, flux_err = 2.0, 0.5, 0.1, 0.2, 0.01
+    time = np.arange(0, 20, 0.02)
+    flux = np.ones_like(time)
+    transit_mask = np.abs((time - transit_time + 0.5 * period) % period - 0.5 * period) < 0.5 * duration
+    flux[transit_mask] = 1.0 - depth
+    flux += flux_err * np.random.randn(len(time))
+    synthetic_lc = LightCurve(time=time, flux=flux)
+    bls_period = synthetic_lc.to_periodogram("bls").period_at_max_power
+    assert_almost_equal(bls_period.value, period, decimal=2)
+    synthetic_lc.flux.view(np.ndarray)[10] = np.nan
+    bls_period = synthetic_lc.to_periodogram("bls").period_at_max_power
+    assert_almost_equal(bls_period.value, period, decimal=2)
+    synthetic_lc.flux_err = u.Quantity(np.array([np.nan] * len(time)))
+    bls_period = synthetic_lc.to_periodogram("bls").period_at_max_power
+    assert_almost_equal(bls_period.value, period, decimal=2)
+
+
+def test_bls_period():
+    lc = LightCurve(time=[1, 2, 3], flux=[4, 5, 6])
+    period = [1, 2, 3, 4, 5]
+    pg = lc.to_periodogram(method="bls", period=period)
+    assert_array_equal(pg.period.value, period)
+    with pytest.raises(ValueError) as err:
+        lc.to_periodogram(method="bls", period=[1, 2, 3, np.nan, 4])
+    assert "period" in err.value.args[0]
+
+
+def test_masked_flux_nans():
+    time = [1, 2, 3, 4]
+    flux = np.ma.masked_array([1.0, np.nan, 1.0, 1.0], mask=[False, True, False, False])
+    lc = LightCurve(time=time, flux=flux)
+    pg = lc.to_periodogram()
+    assert not np.isnan(pg.power.value).all()
+    assert (pg.power.value == 0).all()
+
+
+def create_beta_lyr_like_lc(dtype=np.float64):
+    t = np.arange(0, 30, 0.1)
+    f = np.array(np.sin(t * 2 + np.pi / 2) + np.sin(t) + 1, dtype=dtype)
+    return LightCurve(time=Time(t + 2457000, format="jd"), flux=f).normalize()
+
+
+@pytest.mark.parametrize("flux_dtype", [np.float64, np.float32])
+def test_ls_method_basics(flux_dtype):
+    lc = create_beta_lyr_like_lc(dtype=flux_dtype)
+    pg = lc.to_periodogram(method="ls", ls_method="fast", nterms=1)
+    assert_almost_equal(pg.period_at_max_power.to(u.d).value, np.pi, decimal=1)
+    assert_equal(pg.nterms, 1)
+
+
+def test_ls_method_uneven_freq_grid(caplog):
+    lc = create_beta_lyr_like_lc()
+    freq_grid = 1 / (np.arange(1, 10, 0.01) * u.d)
+    with caplog.at_level(logging.WARNING):
+        pg = lc.to_periodogram(method="ls", ls_method="fast", nterms=1, frequency=freq_grid)
+    assert_almost_equal(pg.period_at_max_power.to(u.d).value, np.pi, decimal=1)
+    assert_equal(pg.ls_method, "slow")
+    assert "Method has been changed from 'fast' to 'slow'" in caplog.text
+
+
+# ------------------------------------------------------------------ test_lightcurve.py (flatten, cdpp)
+def test_flatten_with_nans():
+    lc = LightCurve(time=[1, 2, 3, 4, 5], flux=[np.nan, 1.1, 1.2, np.nan, 1.4], flux_err=[1.0, np.nan, 1.2, 1.3, np.nan])
+    flat_lc = lc.flatten(window_length=3)
+    assert len(flat_lc.time) == 5
+    assert np.isfinite(flat_lc.flux.value).sum() == 3
+    assert np.isfinite(flat_lc.flux_err.value).sum() == 3
+
+
+def test_flatten_robustness():
+    lc = LightCurve(time=[1, 2, 3, 4, 5, 6], flux=[10, 20, 30, 40, 50, 60])
+    expected_result = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    flat_lc = lc.flatten(window_length=3, polyorder=1)
+    assert_almost_equal(flat_lc.flux.value, expected_result)
+    flat_lc = lc.flatten(window_length=7, polyorder=1)       # window_length > len -> median
+    assert_almost_equal(flat_lc.flux.value, lc.flux.value / np.median(lc.flux.value))
+    flat_lc = lc.flatten(window_length=3, polyorder=5)       # polyorder clamp
+    assert_almost_equal(flat_lc.flux.value, expected_result)
+    flat_lc = lc.flatten(window_length=3, break_tolerance=None)
+    flat_lc, trend_lc = lc.flatten(return_trend=True)
+    assert_almost_equal(lc.flux.value, flat_lc.flux.value * trend_lc.flux.value)
+
+
+def test_flatten_returns_normalized():
+    lc = LightCurve(time=[1, 2, 3, 4, 5, 6], flux=[10.1, 20.2, 30.3, 40.4, 50.5, 60.6], flux_unit="electron/s")
+    flat_lc, trend_lc = lc.flatten(return_trend=True)
+    assert flat_lc.flux.unit == u.dimensionless_unscaled and flat_lc.flux_err.unit == u.dimensionless_unscaled
+    assert trend_lc.flux.unit == lc.flux.unit
+    assert flat_lc.meta["NORMALIZED"]
+
+
+def test_iterative_flatten():
+    x = np.arange(2000)
+    y = np.sin(x / 200) / 100 + 1
+    y[250] -= 0.01
+    lc = LightCurve(time=x, flux=y)
+    c, f = lc.flatten(window_length=25, niters=2, sigma=3, return_trend=True)
+    assert np.isclose(c.flux.value, 1, rtol=0.00001).sum() == 1999
+    mask = np.zeros(2000, dtype=bool)
+    mask[250] = True
+    c, f = lc.flatten(window_length=25, niters=1, sigma=3, mask=mask, return_trend=True)
+    assert np.isclose(c.flux.value, 1, rtol=0.00001).sum() == 1999
+
+
+def test_cdpp():
+    lc = LightCurve(time=np.arange(10000), flux=np.ones(10000))
+    assert_almost_equal(lc.estimate_cdpp().value, 0)
+    np.random.seed(1)
+    lc = LightCurve(time=np.arange(10000), flux=np.random.normal(loc=1, scale=100e-6, size=10000),
+                    flux_err=np.zeros(10000) + 100e-6)
+    assert_almost_equal(lc.estimate_cdpp(transit_duration=1).value, 100, decimal=-0.5)
+    with pytest.raises(ValueError):
+        lc.estimate_cdpp(1.5)
+
+
+def test_normalize_and_remove_outliers():
+    np.random.seed(3)
+    f = np.random.normal(20000, 5, 500)
+    f[[10, 200]] = [21000, 19000]
+    lc = LightCurve(time=np.arange(500), flux=f, flux_err=np.full(500, 5.0))
+    n = lc.normalize()
+    assert_almost_equal(np.median(n.flux.value), 1.0)
+    assert_almost_equal(n.flux_err.value, 5.0 / np.median(f))
+    clean, mask = lc.remove_outliers(sigma=5, return_mask=True)
+    assert mask.sum() == 2 and mask[10] and mask[200] and len(clean) == 498
+    assert np.array_equal(mask, odet.sigma_clip_mask(f, 5))
+
+
+# ------------------------------------------------------------------ test_regressioncorrector.py
+def test_regressioncorrector_priors():
+    lc1 = LightCurve(flux=[5, 10])
+    lc2 = LightCurve(flux=[5, 10], flux_err=[1, 1])
+    design_matrix = DesignMatrix(np.array([[1, 1], [1, 2]]).astype(float))
+    for dm in [design_matrix]:
+        for lc in [lc1, lc2]:
+            rc = RegressionCorrector(lc)
+            rc.correct(dm)
+            assert_almost_equal(rc.coefficients, [0, 5])
+            dm.prior_mu = np.array([99.0, 99.0])
+            dm.prior_sigma = np.array([1e-9, 1e-9])
+            rc.correct(dm)
+            assert_almost_equal(rc.coefficients, [99, 99])
+            dm.prior_sigma = np.array([1e9, 1e9])
+            rc.correct(dm)
+            assert_almost_equal(rc.coefficients, [0, 5])
+            dm.prior_mu = np.zeros(2)
+            dm.prior_sigma = np.ones(2) * np.inf
+
+
+def test_sinusoid_noise():
+    size = 100
+    time = np.linspace(1, 100, size)
+    true_flux = np.ones(size)
+    noise = np.sin(time / 5)
+    true_lc = LightCurve(time=time, flux=true_flux, flux_err=0.1 * np.ones(size))
+    noisy_lc = LightCurve(time=time, flux=true_flux + noise, flux_err=true_lc.flux_err)
+    dm = DesignMatrix({"noise": noise, "offset": np.ones(len(time))}, name="noise_model")
+    rc = RegressionCorrector(noisy_lc)
+    corrected_lc = rc.correct(dm)
+    assert_almost_equal(corrected_lc.normalize().flux.value, true_lc.flux.value)
+    assert set(rc.diagnostic_lightcurves) == {"noise_model"}
+    dm.prior_mu = [0.1, 0.1]
+    dm.prior_sigma = [1e6, 1e6]
+    corrected_lc = RegressionCorrector(noisy_lc).correct(dm)
+    assert_almost_equal(corrected_lc.normalize().flux.value, true_lc.flux.value)
+    noisy_lc = LightCurve(time=time, flux=true_flux + noise)
+    corrected_lc = RegressionCorrector(noisy_lc).correct(dm)
+    assert_almost_equal(corrected_lc.normalize().flux.value, true_lc.flux.value)
+
+
+def test_singular_matrix_raises_linalgerror():
+    lc = LightCurve(flux=np.arange(50.0) + 1)
+    with pytest.raises(np.linalg.LinAlgError):
+        with pytest.warns(lk.LightkurveWarning):
+            RegressionCorrector(lc).correct(DesignMatrix(np.ones((50, 4))))
+
+
+# ------------------------------------------------------------------ collection-level == per-LC loop
+def _collection(rng, shared_grid, n_lc=6):
+    lcs = []
+    t0 = np.arange(1500) * 0.0204336 + 131.5
+    for i in range(n_lc):
+        t = t0 if shared_grid else np.sort(rng.uniform(0, 30, int(rng.integers(300, 1500))))
+        f = 1 + 0.01 * np.sin(2 * np.pi * t / (1.5 + i)) + 1e-3 * rng.normal(size=len(t))
+        lcs.append(LightCurve(time=t, flux=f, flux_err=np.full(len(t), 1e-3), label="lc%d" % i))
+    return LightCurveCollection(lcs)
+
+
+@pytest.mark.parametrize("shared_grid", [True, False])
+@pytest.mark.parametrize("normalization", ["amplitude", "psd"])
+def test_collection_ls_equals_loop(shared_grid, normalization):
+    coll = _collection(np.random.default_rng(5), shared_grid)
+    batch = coll.to_periodogram(normalization=normalization)
+    for lc, pg in zip(coll, batch):
+        one = lc.to_periodogram(normalization=normalization)
+        assert pg.label == lc.label and pg.power.unit == one.power.unit
+        np.testing.assert_allclose(pg.frequency.value, one.frequency.value, rtol=1e-15)
+        np.testing.assert_allclose(pg.power.value, one.power.value, rtol=2e-4, atol=2e-5 * one.power.value.max())
+
+
+def test_collection_bls_and_flatten_equal_loop():
+    coll = _collection(np.random.default_rng(6), shared_grid=True, n_lc=4)
+    per = np.linspace(0.5, 3.0, 200)
+    for lc, pg in zip(coll, coll.to_periodogram("bls", period=per, duration=[0.05, 0.1])):
+        one = lc.to_periodogram("bls", period=per, duration=[0.05, 0.1])
+        np.testing.assert_allclose(pg.power.value, one.power.value, rtol=1e-12)
+        np.testing.assert_allclose(pg.depth.value, one.depth.value, rtol=1e-12)
+    flat, trend = coll.flatten(window_length=101, return_trend=True)
+    for lc, fl, tr in zip(coll, flat, trend):
+        one, one_tr = lc.flatten(window_length=101, return_trend=True)
+        np.testing.assert_array_equal(fl.flux.value, one.flux.value)
+        np.testing.assert_array_equal(tr.flux.value, one_tr.flux.value)
+
+
+def test_correct_batch_equals_loop():
+    rng = np.random.default_rng(8)
+    N, K, B = 800, 12, 5
+    X = np.hstack([np.cumsum(rng.normal(size=(N, K - 1)), axis=0) / 30, np.ones((N, 1))])
+    dmc = DesignMatrixCollection([DesignMatrix(X[:, :-1], name="cbv"), DesignMatrix(X[:, -1:], name="const",
+                                                                                 columns=["offset"])])
+    lcs = []
+    for b in range(B):
+        y = 1 + X @ (rng.normal(size=K) * 1e-3) + 3e-4 * rng.normal(size=N)
+        y[rng.choice(N, 4, replace=False)] += 5e-3
+        lcs.append(LightCurve(time=np.arange(N) * 0.02, flux=y, flux_err=np.full(N, 3e-4)))
+    batch = RegressionCorrector.correct_batch(lcs, dmc)
+    for lc, rc_b in zip(lcs, batch):
+        rc = RegressionCorrector(lc)
+        rc.correct(dmc)
+        np.testing.assert_array_equal(rc.outlier_mask, rc_b.outlier_mask)
+        np.testing.assert_allclose(rc.coefficients, rc_b.coefficients, rtol=1e-10)
+        np.testing.assert_allclose(rc.corrected_lc.flux.value, rc_b.corrected_lc.flux.value, rtol=1e-12)
+        ref = odet.regress(X, lc.flux.value, lc.flux_err.value)
+        np.testing.assert_allclose(rc.coefficients, ref["coefficients"], rtol=1e-7, atol=1e-10)
