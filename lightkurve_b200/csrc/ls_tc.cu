@@ -41,14 +41,15 @@ constexpr int TC_BM = 128;            // frequencies per CTA (TMEM lanes)
 constexpr int TC_BN = 256;            // light curves per CTA (columns per accumulator)
 constexpr int TC_BK = 32;             // cadences per pipeline stage (64-byte fp16 rows, SWIZZLE_64B)
 constexpr int TC_STAGES = 3;
-constexpr int TC_GEN_WARPS = 8;
+constexpr int TC_GEN_WARPS = 16;      // 512 generator threads: one 8-cadence chunk of one row per stage each
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_THREADS = (2 + TC_GEN_WARPS + TC_EPI_WARPS) * 32;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;          // 8 KB
 constexpr int TC_Y_TILE = TC_BN * TC_BK * 2;          // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_A_TILE + 2 * TC_Y_TILE;   // 64 KB
 constexpr float TC_A_SCALE = 256.0f;                  // 2^8: keeps fp16 residuals of cos/sin normal
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SCRATCH = TC_GEN_WARPS * 8 * 16;     // per-warp broadcast slots for the phase table
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_SCRATCH;
 constexpr int TC_SEG_STAGES = 64;     // <= 2048 cadences (384 chained MMAs) per accumulator chain
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row atoms of 512 B (SBO), version 1.
@@ -89,13 +90,46 @@ tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ abs
   *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
 }
 
+// Regular frequency grids f_k = f0 + k df (the lightkurve default, and what astropy's "fast"
+// method requires): phase(k, n) = frac(f0 t_n) + k frac(df t_n) is evaluated in 64-bit FIXED POINT
+// (cycles * 2^64, wrap-around = mod 1 for free) - exact integer arithmetic instead of an fp64
+// multiply / round / subtract / convert chain per design-matrix element.  This kernel builds the
+// per-cadence table {a_n, b_n}; padding cadences get 0.
+__global__ void tc_phase_table_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double f0, double df,
+                                      ulonglong2* __restrict__ tab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  ulonglong2 v = make_ulonglong2(0ull, 0ull);
+  if (i < N) {
+    const double x = f0 * t[i], y = df * t[i];
+    const double fx = x - floor(x), fy = y - floor(y);
+    v.x = __double2ull_rd(fx * 18446744073709551616.0);
+    v.y = __double2ull_rd(fy * 18446744073709551616.0);
+  }
+  tab[i] = v;
+}
+
+// max_k |freq[k] - (f0 + k df)| / |df| (0 for a perfectly regular grid)
+__global__ void tc_grid_regularity_kernel(const double* __restrict__ freq, int64_t F, float* __restrict__ out) {
+  const double f0 = freq[0], df = freq[1] - freq[0];
+  float worst = 0.f;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < F; k += (int64_t)gridDim.x * blockDim.x) {
+    const double dev = fabs(freq[k] - (f0 + (double)k * df)) / fabs(df);
+    worst = fmaxf(worst, (float)dev);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(worst));   // worst >= 0
+}
+
 struct TcParams {
-  const double* t;        // [Npad] shifted times (padding cadences hold 0)
-  const double* freq;     // [F]
-  const float4* rot;      // [F]
-  const float* inv_scale; // [B]
-  float* power;           // [B, F]
-  float* part;            // [nseg, 2, B, F] partial (Ch, Sh) when nseg > 1
+  const double* t;          // [Npad] shifted times (padding cadences hold 0)       (irregular grids)
+  const ulonglong2* tab;    // [Npad] fixed-point phase table {a_n, b_n}            (regular grids)
+  const double* freq;       // [F]
+  const float4* rot;        // [F]
+  const float* inv_scale;   // [B]
+  float* power;             // [B, F]
+  float* part;              // [nseg, 2, B, F] raw partial (Ch, Sh) accumulators when nseg > 1
   int64_t N, Npad, F;
   int B;
   int normalization;
@@ -103,6 +137,29 @@ struct TcParams {
   int seg_stages, nseg;
 };
 
+// split fp32 (c0, c1) and (s0, s1) into fp16 hi / residual words
+__device__ __forceinline__ void tc_split2(float c0, float c1, float s0, float s1, uint32_t& ch, uint32_t& cl,
+                                          uint32_t& sh, uint32_t& sl) {
+  c0 *= TC_A_SCALE; c1 *= TC_A_SCALE; s0 *= TC_A_SCALE; s1 *= TC_A_SCALE;
+  const __half2 hc = __floats2half2_rn(c0, c1), hs = __floats2half2_rn(s0, s1);
+  const float2 fc = __half22float2(hc), fs = __half22float2(hs);
+  const __half2 lc = __floats2half2_rn(c0 - fc.x, c1 - fc.y), ls = __floats2half2_rn(s0 - fs.x, s1 - fs.y);
+  ch = *reinterpret_cast<const uint32_t*>(&hc);
+  cl = *reinterpret_cast<const uint32_t*>(&lc);
+  sh = *reinterpret_cast<const uint32_t*>(&hs);
+  sl = *reinterpret_cast<const uint32_t*>(&ls);
+}
+
+// sin/cos of a 64-bit fixed-point phase (cycles * 2^64): top 23 bits -> float in [-0.5, 0.5)
+__device__ __forceinline__ void tc_sincos_fixed(unsigned long long ph, float& s, float& c) {
+  const uint32_t u = (uint32_t)(ph >> 32) ^ 0x80000000u;
+  const float x = __uint_as_float((u >> 9) | 0x3f800000u) - 1.5f;
+  const float r = x * 6.283185307179586f;
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
+template <bool REGULAR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -110,17 +167,18 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   const uint32_t raw = ptx::smem_u32(tc_smem_raw);
   unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full_y = bars;                    // [STAGES] TMA bytes landed
-  uint64_t* full_a = bars + TC_STAGES;        // [STAGES] generator warps done
-  uint64_t* empty = bars + 2 * TC_STAGES;     // [STAGES] MMAs of the stage retired
+  uint64_t* full_y = bars;                         // [STAGES] TMA bytes landed
+  uint64_t* full_a = bars + TC_STAGES;             // [STAGES] generator warps done
+  uint64_t* empty = bars + 2 * TC_STAGES;          // [STAGES] MMAs of the stage retired
   uint64_t* acc_full = bars + 3 * TC_STAGES;       // a segment's accumulators are complete
   uint64_t* acc_empty = bars + 3 * TC_STAGES + 1;  // the epilogue warps have drained TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(bars) + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
   const int b0 = blockIdx.y * TC_BN;
-  const int nst = (int)(p.Npad / TC_BK);                    // all stages; segments are p.seg_stages long
+  const int nst = (int)(p.Npad / TC_BK);           // all stages; segments are p.seg_stages long
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -147,7 +205,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     if (lane == 0) {
       for (int it = 0; it < nst; ++it) {
         const int s = it % TC_STAGES;
-        if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+        if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, 200);
         unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(&full_y[s], 2 * TC_Y_TILE);
         ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b0, &full_y[s]);
@@ -163,9 +221,9 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         const int seg = it / p.seg_stages;
         const bool seg_first = (it - seg * p.seg_stages) == 0;
         const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
-        ptx::mbar_wait(&full_y[s], ph);
-        ptx::mbar_wait(&full_a[s], ph);
-        if (seg_first && seg > 0) ptx::mbar_wait(acc_empty, (seg - 1) & 1);   // TMEM drained by the epilogue
+        ptx::mbar_wait_sleep(&full_y[s], ph, 40);
+        ptx::mbar_wait_sleep(&full_a[s], ph, 40);
+        if (seg_first && seg > 0) ptx::mbar_wait_sleep(acc_empty, (seg - 1) & 1, 40);   // TMEM drained
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
         const uint32_t a_ch = sa, a_cl = sa + TC_A_TILE, a_sh = sa + 2 * TC_A_TILE, a_sl = sa + 3 * TC_A_TILE;
@@ -190,46 +248,54 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     }
   } else if (warp < 2 + TC_GEN_WARPS) {
     // ================= design-matrix generators =================
-    const int g = threadIdx.x - 64;                       // 0..255
-    const int row = g & (TC_BM - 1);                      // frequency row inside the tile
-    const int kh = g >> 7;                                // which 16-cadence half of the stage
-    const double fr = (f0 + row < p.F) ? p.freq[f0 + row] : 0.0;
-    const uint32_t row_off = (uint32_t)row * 64u;
-    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    // thread -> (frequency row, one 16-byte chunk = 8 cadences of the stage); a warp covers 32 rows of
+    // ONE chunk, so its 8 cadences' table entries are prefetched by lanes 0..7 one stage ahead and
+    // broadcast through a private shared-memory scratch (no L2 latency on the critical path).
+    const int gw = warp - 2;                              // 0..15
+    const int row = (gw & 3) * 32 + lane;                 // frequency row inside the tile
+    const int chunk = gw >> 2;                            // which 8-cadence chunk of the stage
+    const uint32_t row_off = (uint32_t)row * 64u + ((((uint32_t)chunk) ^ (uint32_t)((row >> 1) & 3)) << 4);
+    ulonglong2* my_scr = reinterpret_cast<ulonglong2*>(scratch + gw * 128);
+    const unsigned long long kfreq = (unsigned long long)(f0 + row);          // global frequency index
+    const double fr = (!REGULAR && f0 + row < p.F) ? p.freq[f0 + row] : 0.0;
+    ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
+    auto prefetch = [&](int it) {
+      if (lane < 8) {
+        const int64_t n = (int64_t)it * TC_BK + chunk * 8 + lane;
+        if (REGULAR) nxt = p.tab[n];
+        else nxt.x = (unsigned long long)__double_as_longlong(p.t[n]);
+      }
+    };
+    prefetch(0);
     for (int it = 0; it < nst; ++it) {
       const int s = it % TC_STAGES;
+      if (lane < 8) my_scr[lane] = nxt;
+      __syncwarp();
+      if (it + 1 < nst) prefetch(it + 1);
       if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-      const double* tp = p.t + (int64_t)it * TC_BK + kh * 16;
+      uint32_t ch[4], cl[4], sh[4], sl[4];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {                       // two 16-byte chunks (8 cadences each)
-        uint32_t ch[4], cl[4], sh[4], sl[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float s0, c0, s1, c1;
-          ls_sincos_cycles(fr * tp[c * 8 + 2 * q], s0, c0);
-          ls_sincos_cycles(fr * tp[c * 8 + 2 * q + 1], s1, c1);
-          s0 *= TC_A_SCALE; c0 *= TC_A_SCALE; s1 *= TC_A_SCALE; c1 *= TC_A_SCALE;
-          const __half2 hc = __floats2half2_rn(c0, c1), hs = __floats2half2_rn(s0, s1);
-          const float2 fc = __half22float2(hc), fs = __half22float2(hs);
-          const __half2 lc = __floats2half2_rn(c0 - fc.x, c1 - fc.y), ls = __floats2half2_rn(s0 - fs.x, s1 - fs.y);
-          ch[q] = *reinterpret_cast<const uint32_t*>(&hc);
-          cl[q] = *reinterpret_cast<const uint32_t*>(&lc);
-          sh[q] = *reinterpret_cast<const uint32_t*>(&hs);
-          sl[q] = *reinterpret_cast<const uint32_t*>(&ls);
+      for (int q = 0; q < 4; ++q) {
+        float s0, c0, s1, c1;
+        const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
+        if (REGULAR) {
+          tc_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
+          tc_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+        } else {
+          ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
+          ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
         }
-        const uint32_t chunk = (uint32_t)(kh * 2 + c);    // logical 16-byte chunk inside the 64 B row
-        const uint32_t off = row_off + ((chunk ^ sw) << 4);
-        *reinterpret_cast<uint4*>(st + off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-        *reinterpret_cast<uint4*>(st + TC_A_TILE + off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
-        *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-        *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+        tc_split2(c0, c1, s0, s1, ch[q], cl[q], sh[q], sl[q]);
       }
+      *reinterpret_cast<uint4*>(st + row_off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+      *reinterpret_cast<uint4*>(st + TC_A_TILE + row_off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+      *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + row_off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+      *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + row_off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
       ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
     }
-
   } else {
     // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
     const int quad = warp & 3;
@@ -238,27 +304,35 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float Nf = (float)p.N;
+    const int64_t plane = (int64_t)p.B * p.F;
     for (int seg = 0; seg < p.nseg; ++seg) {
-      ptx::mbar_wait(acc_full, seg & 1);
+      ptx::mbar_wait_sleep(acc_full, seg & 1, 500);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-        uint32_t vc[32], vs[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + c0, vc);
-        ptx::tmem_ld_32x32b_x32(lane_addr + TC_BN + c0, vs);
+      for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+        uint32_t vc[16], vs[16];
+        ptx::tmem_ld_32x32b_x16(lane_addr + c0, vc);
+        ptx::tmem_ld_32x32b_x16(lane_addr + TC_BN + c0, vs);
         ptx::tmem_ld_wait();
+        if (f_ok) {
+          if (p.nseg == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int b = b0 + c0 + j;
-          if (f_ok && b < p.B) {
-            const float h = p.inv_scale[b];
-            const float chv = __uint_as_float(vc[j]) * h, shv = __uint_as_float(vs[j]) * h;
-            if (p.nseg == 1) {
-              p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(chv, shv, r, Nf, p.normalization, p.norm_scale);
-            } else {
-              float* pc = p.part + ((int64_t)(seg * 2) * p.B + b) * p.F + f;
-              pc[0] = chv;
-              pc[(int64_t)p.B * p.F] = shv;
+            for (int j = 0; j < 16; ++j) {
+              const int b = b0 + c0 + j;
+              if (b < p.B) {
+                const float h = p.inv_scale[b];
+                p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
+                                                                  r, Nf, p.normalization, p.norm_scale);
+              }
+            }
+          } else {
+            float* pc = p.part + (int64_t)(seg * 2) * plane + (int64_t)(b0 + c0) * p.F + f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (b0 + c0 + j < p.B) {
+                pc[(int64_t)j * p.F] = __uint_as_float(vc[j]);
+                pc[plane + (int64_t)j * p.F] = __uint_as_float(vs[j]);
+              }
             }
           }
         }
@@ -272,10 +346,11 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
-// sum the split-K partials (round-to-nearest fp32 adds) and apply the epilogue
+// sum the split-K partials (round-to-nearest fp32 adds), undo the operand scaling, apply the epilogue
 __global__ void __launch_bounds__(256)
 ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, const float4* __restrict__ rot,
-                    float N, int normalization, float norm_scale, float* __restrict__ power) {
+                    const float* __restrict__ inv_scale, float N, int normalization, float norm_scale,
+                    float* __restrict__ power) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (f >= F) return;
@@ -286,7 +361,8 @@ ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, 
     ch += pc[(int64_t)(2 * s) * plane];
     sh += pc[(int64_t)(2 * s + 1) * plane];
   }
-  power[(int64_t)b * F + f] = ls_epilogue_shared(ch, sh, rot[f], N, normalization, norm_scale);
+  const float h = inv_scale[b];
+  power[(int64_t)b * F + f] = ls_epilogue_shared(ch * h, sh * h, rot[f], N, normalization, norm_scale);
 }
 
 // ---- host -------------------------------------------------------------------------------------
@@ -336,8 +412,31 @@ int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, 
 
   static bool attr_set = false;
   if (!attr_set) {
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     attr_set = true;
+  }
+  // regular frequency grid?  (decides fixed-point vs fp64 phase generation)
+  bool regular = false;
+  double h_f01[2] = {0.0, 0.0};
+  ulonglong2* d_tab = nullptr;
+  if (F >= 2 && !getenv("LKB_TC_FORCE_FP64_PHASE")) {
+    float* d_dev = nullptr;
+    LKB_TRY(ws_get_t<float>(WS_K, 4, &d_dev));
+    LKB_CUDA_CHECK(cudaMemsetAsync(d_dev, 0, sizeof(float), st));
+    tc_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, d_dev);
+    LKB_LAUNCH_CHECK();
+    float h_dev = 1.f;
+    LKB_CUDA_CHECK(cudaMemcpyAsync(&h_dev, d_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    regular = (h_dev <= 1e-6f) && h_f01[0] >= 0.0 && h_f01[1] > h_f01[0] && F < ((int64_t)1 << 31);
+  }
+  if (regular) {
+    LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
+    tc_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, h_f01[0], h_f01[1] - h_f01[0],
+                                                                        d_tab);
+    LKB_LAUNCH_CHECK();
   }
   const int nst_total = (int)(Npad / TC_BK);
   int seg_cap = TC_SEG_STAGES;
@@ -349,17 +448,18 @@ int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, 
   if (nseg > 1) LKB_TRY(ws_get_t<float>(WS_J, (size_t)nseg * 2 * B * F, &d_part));
 
   TcParams p;
-  p.t = d_t; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
+  p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   prof_begin(st);
-  ls_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  if (regular) ls_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  else ls_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
   prof_end(st);
   LKB_LAUNCH_CHECK();
   if (nseg > 1) {
     ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(
-        d_part, nseg, B, F, d_rot, (float)N, normalization, (float)norm_scale, d_pow);
+        d_part, nseg, B, F, d_rot, d_inv, (float)N, normalization, (float)norm_scale, d_pow);
     LKB_LAUNCH_CHECK();
   }
   return LKB_OK;
