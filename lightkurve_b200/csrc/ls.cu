@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "ls_common.cuh"
+#include <stdlib.h>
 
 namespace lkb {
 
@@ -208,13 +209,15 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
 // K2a: per-frequency window terms on the shared grid.
 // One warp per frequency; rot[f] = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}.
 // =====================================================================================
+template <bool REGULAR>
 __global__ void __launch_bounds__(256)
-ls_window_kernel(const double* __restrict__ t, int64_t N, const double* __restrict__ freq, int64_t F,
-                 float4* __restrict__ rot) {
+ls_window_kernel(const double* __restrict__ t, const ulonglong2* __restrict__ tab, int64_t N,
+                 const double* __restrict__ freq, int64_t F, float4* __restrict__ rot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (f >= F) return;
   const double fr = freq[f];
+  const unsigned long long kf = (unsigned long long)f;
   LsSums<double> d;
   d.zero();
   for (int64_t c0 = 0; c0 < N; c0 += 32 * 64) {
@@ -223,7 +226,12 @@ ls_window_kernel(const double* __restrict__ t, int64_t N, const double* __restri
     const int64_t c1 = min(N, c0 + 32 * 64);
     for (int64_t i = c0 + lane; i < c1; i += 32) {
       float s, c;
-      ls_sincos_cycles(fr * t[i], s, c);
+      if (REGULAR) {
+        const ulonglong2 e = tab[i];
+        ls_sincos_fixed(e.x + kf * e.y, s, c);
+      } else {
+        ls_sincos_cycles(fr * t[i], s, c);
+      }
       fs.add(0.f, s, c);
     }
     d.accumulate(fs);
@@ -434,9 +442,9 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
   return LKB_OK;
 }
 
-int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, const float* d_absmax, int B,
-                 const double* d_freq, int64_t F, const float4* d_rot, int normalization, double norm_scale,
-                 float* d_pow, cudaStream_t st);   // ls_tc.cu
+int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot, int normalization,
+                 double norm_scale, float* d_pow, cudaStream_t st);   // ls_tc.cu
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
@@ -484,7 +492,29 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   else
     ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax);
   LKB_LAUNCH_CHECK();
-  ls_window_kernel<<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, N, d_freq, F, d_rot);
+  // Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
+  // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain.
+  ulonglong2* d_tab = nullptr;
+  if (F >= 2 && F < ((int64_t)1 << 31) && !getenv("LKB_LS_FORCE_FP64_PHASE")) {
+    float* d_dev = nullptr;
+    LKB_TRY(ws_get_t<float>(WS_K, 4, &d_dev));
+    LKB_CUDA_CHECK(cudaMemsetAsync(d_dev, 0, sizeof(float), st));
+    ls_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, d_dev);
+    LKB_LAUNCH_CHECK();
+    float h_dev = 1.f;
+    double h_f01[2] = {0.0, 0.0};
+    LKB_CUDA_CHECK(cudaMemcpyAsync(&h_dev, d_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_dev <= 1e-6f && h_f01[0] >= 0.0 && h_f01[1] > h_f01[0]) {
+      LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
+      ls_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, h_f01[0],
+                                                                          h_f01[1] - h_f01[0], d_tab);
+      LKB_LAUNCH_CHECK();
+    }
+  }
+  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot);
+  else ls_window_kernel<false><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot);
   LKB_LAUNCH_CHECK();
 
   bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
@@ -493,7 +523,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     return LKB_E_UNSUPPORTED;
   }
   if (use_tc) {
-    LKB_TRY(ls_tc_launch(d_t, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, normalization, ns, d_pow, st));
+    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, normalization, ns, d_pow, st));
   } else {
     static bool attr_set = false;
     if (!attr_set) {

@@ -18,6 +18,48 @@ __device__ __forceinline__ void ls_sincos_cycles(double phase, float& s, float& 
   c = __cosf(x);
 }
 
+// sin/cos of a 64-bit fixed-point phase (cycles * 2^64): top 23 bits -> float in [-0.5, 0.5)
+__device__ __forceinline__ void ls_sincos_fixed(unsigned long long ph, float& s, float& c) {
+  const uint32_t u = (uint32_t)(ph >> 32) ^ 0x80000000u;
+  const float x = __uint_as_float((u >> 9) | 0x3f800000u) - 1.5f;
+  const float r = x * 6.283185307179586f;
+  s = __sinf(r);
+  c = __cosf(r);
+}
+
+
+// Regular frequency grids f_k = f0 + k df (the lightkurve default, and what astropy's "fast"
+// method requires): phase(k, n) = frac(f0 t_n) + k frac(df t_n) is evaluated in 64-bit FIXED POINT
+// (cycles * 2^64, wrap-around = mod 1 for free) - exact integer arithmetic instead of an fp64
+// multiply / round / subtract / convert chain per design-matrix element.  This kernel builds the
+// per-cadence table {a_n, b_n}; padding cadences get 0.
+static __global__ void ls_phase_table_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double f0, double df,
+                                      ulonglong2* __restrict__ tab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  ulonglong2 v = make_ulonglong2(0ull, 0ull);
+  if (i < N) {
+    const double x = f0 * t[i], y = df * t[i];
+    const double fx = x - floor(x), fy = y - floor(y);
+    v.x = __double2ull_rd(fx * 18446744073709551616.0);
+    v.y = __double2ull_rd(fy * 18446744073709551616.0);
+  }
+  tab[i] = v;
+}
+
+// max_k |freq[k] - (f0 + k df)| / |df| (0 for a perfectly regular grid)
+static __global__ void ls_grid_regularity_kernel(const double* __restrict__ freq, int64_t F, float* __restrict__ out) {
+  const double f0 = freq[0], df = freq[1] - freq[0];
+  float worst = 0.f;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < F; k += (int64_t)gridDim.x * blockDim.x) {
+    const double dev = fabs(freq[k] - (f0 + (double)k * df)) / fabs(df);
+    worst = fmaxf(worst, (float)dev);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(worst));   // worst >= 0
+}
+
 template <typename T>
 struct LsSums {
   T sh, ch, s, c, cc, sc;

@@ -90,38 +90,6 @@ tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ abs
   *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
 }
 
-// Regular frequency grids f_k = f0 + k df (the lightkurve default, and what astropy's "fast"
-// method requires): phase(k, n) = frac(f0 t_n) + k frac(df t_n) is evaluated in 64-bit FIXED POINT
-// (cycles * 2^64, wrap-around = mod 1 for free) - exact integer arithmetic instead of an fp64
-// multiply / round / subtract / convert chain per design-matrix element.  This kernel builds the
-// per-cadence table {a_n, b_n}; padding cadences get 0.
-__global__ void tc_phase_table_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double f0, double df,
-                                      ulonglong2* __restrict__ tab) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Npad) return;
-  ulonglong2 v = make_ulonglong2(0ull, 0ull);
-  if (i < N) {
-    const double x = f0 * t[i], y = df * t[i];
-    const double fx = x - floor(x), fy = y - floor(y);
-    v.x = __double2ull_rd(fx * 18446744073709551616.0);
-    v.y = __double2ull_rd(fy * 18446744073709551616.0);
-  }
-  tab[i] = v;
-}
-
-// max_k |freq[k] - (f0 + k df)| / |df| (0 for a perfectly regular grid)
-__global__ void tc_grid_regularity_kernel(const double* __restrict__ freq, int64_t F, float* __restrict__ out) {
-  const double f0 = freq[0], df = freq[1] - freq[0];
-  float worst = 0.f;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < F; k += (int64_t)gridDim.x * blockDim.x) {
-    const double dev = fabs(freq[k] - (f0 + (double)k * df)) / fabs(df);
-    worst = fmaxf(worst, (float)dev);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(worst));   // worst >= 0
-}
-
 struct TcParams {
   const double* t;          // [Npad] shifted times (padding cadences hold 0)       (irregular grids)
   const ulonglong2* tab;    // [Npad] fixed-point phase table {a_n, b_n}            (regular grids)
@@ -148,15 +116,6 @@ __device__ __forceinline__ void tc_split2(float c0, float c1, float s0, float s1
   cl = *reinterpret_cast<const uint32_t*>(&lc);
   sh = *reinterpret_cast<const uint32_t*>(&hs);
   sl = *reinterpret_cast<const uint32_t*>(&ls);
-}
-
-// sin/cos of a 64-bit fixed-point phase (cycles * 2^64): top 23 bits -> float in [-0.5, 0.5)
-__device__ __forceinline__ void tc_sincos_fixed(unsigned long long ph, float& s, float& c) {
-  const uint32_t u = (uint32_t)(ph >> 32) ^ 0x80000000u;
-  const float x = __uint_as_float((u >> 9) | 0x3f800000u) - 1.5f;
-  const float r = x * 6.283185307179586f;
-  s = __sinf(r);
-  c = __cosf(r);
 }
 
 template <bool REGULAR>
@@ -272,7 +231,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       if (lane < 8) my_scr[lane] = nxt;
       __syncwarp();
       if (it + 1 < nst) prefetch(it + 1);
-      if (it >= TC_STAGES) ptx::mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+      if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, 100);
       unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
       uint32_t ch[4], cl[4], sh[4], sl[4];
 #pragma unroll
@@ -280,8 +239,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         float s0, c0, s1, c1;
         const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
         if (REGULAR) {
-          tc_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
-          tc_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+          ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
+          ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
         } else {
           ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
           ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
@@ -387,9 +346,9 @@ bool ls_tc_supported(int B, int64_t N, int64_t F) {
   return B >= 64 && N >= 256 && F >= 128;
 }
 
-int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, const float* d_absmax, int B,
-                 const double* d_freq, int64_t F, const float4* d_rot, int normalization, double norm_scale,
-                 float* d_pow, cudaStream_t st) {
+int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot, int normalization,
+                 double norm_scale, float* d_pow, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
@@ -416,28 +375,7 @@ int ls_tc_launch(const double* d_t, int64_t N, int64_t Npad, const float* d_yc, 
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     attr_set = true;
   }
-  // regular frequency grid?  (decides fixed-point vs fp64 phase generation)
-  bool regular = false;
-  double h_f01[2] = {0.0, 0.0};
-  ulonglong2* d_tab = nullptr;
-  if (F >= 2 && !getenv("LKB_TC_FORCE_FP64_PHASE")) {
-    float* d_dev = nullptr;
-    LKB_TRY(ws_get_t<float>(WS_K, 4, &d_dev));
-    LKB_CUDA_CHECK(cudaMemsetAsync(d_dev, 0, sizeof(float), st));
-    tc_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, d_dev);
-    LKB_LAUNCH_CHECK();
-    float h_dev = 1.f;
-    LKB_CUDA_CHECK(cudaMemcpyAsync(&h_dev, d_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
-    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-    regular = (h_dev <= 1e-6f) && h_f01[0] >= 0.0 && h_f01[1] > h_f01[0] && F < ((int64_t)1 << 31);
-  }
-  if (regular) {
-    LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
-    tc_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, h_f01[0], h_f01[1] - h_f01[0],
-                                                                        d_tab);
-    LKB_LAUNCH_CHECK();
-  }
+  const bool regular = d_tab != nullptr;
   const int nst_total = (int)(Npad / TC_BK);
   int seg_cap = TC_SEG_STAGES;
   if (const char* e = getenv("LKB_TC_SEG_STAGES")) { const int v = atoi(e); if (v > 0) seg_cap = v; }

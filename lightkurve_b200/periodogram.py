@@ -164,7 +164,9 @@ class Periodogram(object):
             if width % 2 == 0:
                 kernel[0] = kernel[-1] = 0.5
             kernel /= kernel.sum()
-            smooth_power = np.convolve(self.power.value, kernel, mode="same")
+            full = np.convolve(self.power.value, kernel, mode="full")      # zero-filled boundaries
+            start = (ntaps - 1) // 2
+            smooth_power = full[start:start + len(self.power)]
             smooth_pg = self.copy()
             smooth_pg.power = Quantity(smooth_power, self.power.unit)
             return smooth_pg

@@ -33,8 +33,8 @@ if "k1" in which:      # config 5 shape: ragged, irregular sampling, common grid
     F = 20000
     times, fluxes = [], []
     for _ in range(B):
-        n = int(round(10 ** rng.uniform(np.log10(2000), np.log10(20000))))
-        grid = 1325 + np.arange(int(27.4 * 720)) / 720.0
+        grid = 1325 + np.arange(int(27.8 * 720)) / 720.0
+        n = min(len(grid), int(round(10 ** rng.uniform(np.log10(2000), np.log10(20000)))))
         keep = np.sort(rng.choice(len(grid), n, replace=False))
         t = grid[keep] + rng.uniform(-20, 20, n) / 86400.0
         times.append(t)
