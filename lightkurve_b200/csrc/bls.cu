@@ -40,15 +40,29 @@ __device__ __forceinline__ double bls_fmod(double x, double p, double inv_p) {
   return copysign(r, x);
 }
 
-__device__ __forceinline__ int bls_bin(double t, double min_t, double period, double inv_period, double bin_duration) {
+// (int)(r / bd) with the IEEE division replaced, on the fast path, by a reciprocal multiply whose
+// result is PROVEN equal: k = trunc(r * (1/bd)); rem = fma(-k, bd, r) is the exact remainder (one
+// rounding of an exactly representable-or-nearly value); if 0 <= rem < bd * (1 - (k + 2) 2^-51) the
+// real quotient lies in [k, k + 1 - margin) and RN(r / bd) cannot reach k + 1, so trunc(RN(r/bd)) = k.
+// Anything else (a sample within ~1e-13 of a bin edge) takes the true division.  Bit-exact with bls.c.
+__device__ __forceinline__ int bls_div_trunc(double r, double bd, double inv_bd) {
+  const double k = trunc(r * inv_bd);
+  const double rem = fma(-k, bd, r);
+  const double margin = bd * ((k + 2.0) * 4.440892098500626e-16);
+  if (rem >= 0.0 && rem < bd - margin && k < 1073741824.0) return (int)k;
+  return (int)(r / bd);
+}
+
+__device__ __forceinline__ int bls_bin(double t, double min_t, double period, double inv_period, double bin_duration,
+                                       double inv_bin) {
   const double r = fabs(bls_fmod(t - min_t, period, inv_period));
-  return (int)(r / bin_duration) + 1;
+  return bls_div_trunc(r, bin_duration, inv_bin) + 1;
 }
 
 __global__ void bls_bin_index_kernel(const double* __restrict__ t, int64_t N, double min_t, double period,
                                      double bin_duration, int32_t* __restrict__ ind) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) ind[i] = bls_bin(t[i], min_t, period, 1.0 / fabs(period), bin_duration);
+  if (i < N) ind[i] = bls_bin(t[i], min_t, period, 1.0 / fabs(period), bin_duration, 1.0 / bin_duration);
 }
 
 // ---- prologue: astropy core.py power(): t - min(t), y - median(y), ivar = 1/dy^2 ----------
@@ -184,6 +198,7 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   const bool active = p < p_end;
   const double per = active ? period[p] : 1.0;
   const double inv_per = 1.0 / fabs(per);
+  const double inv_bin = 1.0 / bin_duration;
   const int n_bins = (int)ceil(per / bin_duration) + oversample;
   const BlsLcInfo li = info[b];
 
@@ -213,7 +228,7 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
         int key = -1;
         double vy = 0.0, vi = 0.0;
         if (i < cnt) {
-          key = bls_bin(s_t[i], li.min_t, per, inv_per, bin_duration);
+          key = bls_bin(s_t[i], li.min_t, per, inv_per, bin_duration, inv_bin);
           vy = s_wy[i];
           vi = s_iv[i];
         }

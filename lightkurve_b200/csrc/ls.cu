@@ -18,6 +18,8 @@
 #include "ptx.cuh"
 #include "ls_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
+#include <vector>
 
 namespace lkb {
 
@@ -31,9 +33,12 @@ template <typename TY>
 __global__ void __launch_bounds__(256)
 ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
                       const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
-                      double* __restrict__ t_out, float* __restrict__ y_out) {
+                      double* __restrict__ t_out, float* __restrict__ y_out, double* __restrict__ tspan,
+                      const double* __restrict__ grid_f0, const double* __restrict__ grid_df,
+                      ulonglong2* __restrict__ tab_out, double* __restrict__ ysum) {
   __shared__ double red[33];
   __shared__ int s_const;
+  __shared__ double s_span[8];
   const int b = blockIdx.x;
   const int64_t o = offsets[b], n = offsets[b + 1] - o, po = poffsets[b], np_ = poffsets[b + 1] - po;
   if (n <= 0) return;
@@ -51,22 +56,45 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
   const double mean = block_sum(acc, red) / (double)n;
   const bool cst = s_const != 0;
   const double t0 = t[o];
+  double span = 0.0, resid = 0.0;
   for (int64_t i = threadIdx.x; i < np_; i += blockDim.x) {
+    ulonglong2 e = make_ulonglong2(0ull, 0ull);
     if (i < n) {
-      t_out[po + i] = t[o + i] - t0;
-      y_out[po + i] = cst ? 0.0f : (float)((double)y[o + i] - mean);
+      const double tr = t[o + i] - t0;
+      span = fmax(span, fabs(tr));
+      t_out[po + i] = tr;
+      const float yv = cst ? 0.0f : (float)((double)y[o + i] - mean);
+      y_out[po + i] = yv;
+      resid += (double)yv;
+      if (tab_out) {      // fixed-point phase table of this light curve's regular grid (ls_common.cuh)
+        const double x = grid_f0[b] * tr, z = grid_df[b] * tr;
+        e.x = __double2ull_rd((x - floor(x)) * 18446744073709551616.0);
+        e.y = __double2ull_rd((z - floor(z)) * 18446744073709551616.0);
+      }
     } else {
       t_out[po + i] = 0.0;
       y_out[po + i] = 0.0f;
     }
+    if (tab_out) tab_out[po + i] = e;
   }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) span = fmax(span, __shfl_xor_sync(0xffffffffu, span, s));
+  if ((threadIdx.x & 31) == 0) s_span[threadIdx.x >> 5] = span;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, s_span[w]);
+    tspan[b] = m;
+  }
+  const double rs = block_sum(resid, red);
+  if (threadIdx.x == 0) ysum[b] = rs;
 }
 
 // Same for a [B, N] matrix sharing one time grid: writes Yc [B, Npad] fp32, zero padded.
 template <typename TY>
 __global__ void __launch_bounds__(256)
 ls_prep_shared_kernel(const TY* __restrict__ y, int64_t N, int64_t Npad, float* __restrict__ y_out,
-                      float* __restrict__ y_absmax) {
+                      float* __restrict__ y_absmax, float* __restrict__ ysum) {
   __shared__ double red[33];
   __shared__ int s_const;
   __shared__ float s_max[8];
@@ -87,11 +115,15 @@ ls_prep_shared_kernel(const TY* __restrict__ y, int64_t N, int64_t Npad, float* 
   const double mean = block_sum(acc, red) / (double)N;
   const bool cst = s_const != 0;
   float mx = 0.f;
+  double resid = 0.0;
   for (int64_t i = threadIdx.x; i < Npad; i += blockDim.x) {
     float v = (i < N && !cst) ? (float)((double)yr[i] - mean) : 0.0f;
     yo[i] = v;
+    resid += (double)v;
     mx = fmaxf(mx, fabsf(v));
   }
+  const double rs = block_sum(resid, red);
+  if (threadIdx.x == 0 && ysum) ysum[b] = (float)rs;
   if (y_absmax) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -118,15 +150,20 @@ __global__ void ls_shift_time_kernel(const double* __restrict__ t, int64_t N, in
 constexpr int LS_WARPS = 8;
 constexpr int LS_FPW = 4;                       // frequency bins per warp
 constexpr int LS_FPB = LS_WARPS * LS_FPW;       // frequency bins per block
-constexpr int LS_TN = 1536;                     // cadences per shared-memory tile
 
+// REGULAR = every frequency grid is f0 + k df: phases come from the fixed-point table (16 B per
+// cadence, no fp64 on the hot loop); otherwise fp64 phase = f * t (8 B per cadence).
+template <bool REGULAR>
 __global__ void __launch_bounds__(LS_WARPS * 32)
-ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
+ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ tabws, const float* __restrict__ yws,
                  const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
                  const double* __restrict__ freq, const int64_t* __restrict__ freq_offsets, int64_t F_shared,
-                 int normalization, const double* __restrict__ norm_scale, float* __restrict__ power) {
-  __shared__ __align__(16) double s_t[2][LS_TN];
-  __shared__ __align__(16) float s_y[2][LS_TN];
+                 const double* __restrict__ tspan, const double* __restrict__ ysum, int normalization,
+                 const double* __restrict__ norm_scale, float* __restrict__ power) {
+  constexpr int TN = REGULAR ? 1024 : 1536;     // cadences per shared-memory tile (<= 40 KB static smem)
+  using Elem = typename std::conditional<REGULAR, ulonglong2, double>::type;
+  __shared__ __align__(16) Elem s_t[2][TN];
+  __shared__ __align__(16) float s_y[2][TN];
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int b = blockIdx.y;
@@ -142,8 +179,14 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
   const int64_t f_base = f_blk + warp * LS_FPW;
 
   double fr[LS_FPW];
+  double fmin_abs = 1e300;
 #pragma unroll
-  for (int j = 0; j < LS_FPW; ++j) fr[j] = (f_base + j < F) ? freq[fo + f_base + j] : 0.0;
+  for (int j = 0; j < LS_FPW; ++j) {
+    fr[j] = (f_base + j < F) ? freq[fo + f_base + j] : 0.0;
+    if (f_base + j < F) fmin_abs = fmin(fmin_abs, fabs(fr[j]));
+  }
+  // low-frequency group (see ls_common.cuh): full fp64 evaluation, warp-uniform choice
+  const bool lowf = fmin_abs * tspan[b] <= LS_LOWF_CYCLES;
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(&s_bar[0], 1);
@@ -152,13 +195,14 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
   }
   __syncthreads();
 
-  const int ntiles = (int)((np_ + LS_TN - 1) / LS_TN);
+  const Elem* src = REGULAR ? reinterpret_cast<const Elem*>(tabws) : reinterpret_cast<const Elem*>(tws);
+  const int ntiles = (int)((np_ + TN - 1) / TN);
   auto issue = [&](int tile) {
     const int buf = tile & 1;
-    const int64_t c0 = (int64_t)tile * LS_TN;
-    const uint32_t cnt = (uint32_t)min((int64_t)LS_TN, np_ - c0);   // multiple of 4
-    ptx::mbar_arrive_expect_tx(&s_bar[buf], cnt * 12u);
-    ptx::bulk_g2s(&s_t[buf][0], tws + po + c0, cnt * 8u, &s_bar[buf]);
+    const int64_t c0 = (int64_t)tile * TN;
+    const uint32_t cnt = (uint32_t)min((int64_t)TN, np_ - c0);   // multiple of 4
+    ptx::mbar_arrive_expect_tx(&s_bar[buf], cnt * (uint32_t)(sizeof(Elem) + 4));
+    ptx::bulk_g2s(&s_t[buf][0], src + po + c0, cnt * (uint32_t)sizeof(Elem), &s_bar[buf]);
     ptx::bulk_g2s(&s_y[buf][0], yws + po + c0, cnt * 4u, &s_bar[buf]);
   };
   if (threadIdx.x == 0) issue(0);
@@ -175,23 +219,48 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
     }
     ptx::mbar_wait(&s_bar[buf], (tile >> 1) & 1);
 
-    const int64_t c0 = (int64_t)tile * LS_TN;
-    const int cnt = (int)min((int64_t)LS_TN, n - c0);   // true (unpadded) cadences in this tile
-    LsSums<float> fs[LS_FPW];
+    const int64_t c0 = (int64_t)tile * TN;
+    const int cnt = (int)min((int64_t)TN, n - c0);   // true (unpadded) cadences in this tile
+    if (lowf) {
+      for (int i = lane; i < cnt; i += 32) {
+        const double tt = tws[po + c0 + i];          // rare path: read the times straight from L2
+        const double yy = (double)s_y[buf][i];
 #pragma unroll
-    for (int j = 0; j < LS_FPW; ++j) fs[j].zero();
-    for (int i = lane; i < cnt; i += 32) {
-      const double tt = s_t[buf][i];
-      const float yy = s_y[buf][i];
-#pragma unroll
-      for (int j = 0; j < LS_FPW; ++j) {
-        float s, c;
-        ls_sincos_cycles(fr[j] * tt, s, c);
-        fs[j].add(yy, s, c);
+        for (int j = 0; j < LS_FPW; ++j) {
+          double s, c;
+          ls_sincos_cycles_f64(fr[j] * tt, s, c);
+          dsum[j].add(yy, s, c);
+        }
       }
-    }
+    } else {
+      LsSums<float> fs[LS_FPW];
 #pragma unroll
-    for (int j = 0; j < LS_FPW; ++j) dsum[j].accumulate(fs[j]);
+      for (int j = 0; j < LS_FPW; ++j) fs[j].zero();
+      for (int i = lane; i < cnt; i += 32) {
+        const float yy = s_y[buf][i];
+        if constexpr (REGULAR) {
+          const ulonglong2 e = s_t[buf][i];
+          unsigned long long ph = e.x + (unsigned long long)f_base * e.y;
+#pragma unroll
+          for (int j = 0; j < LS_FPW; ++j) {
+            float s, c;
+            ls_sincos_fixed(ph, s, c);
+            fs[j].add(yy, s, c);
+            ph += e.y;
+          }
+        } else {
+          const double tt = s_t[buf][i];
+#pragma unroll
+          for (int j = 0; j < LS_FPW; ++j) {
+            float s, c;
+            ls_sincos_cycles(fr[j] * tt, s, c);
+            fs[j].add(yy, s, c);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < LS_FPW; ++j) dsum[j].accumulate(fs[j]);
+    }
     __syncthreads();   // everyone done with `buf` before it is refilled
   }
 
@@ -199,7 +268,7 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
   for (int j = 0; j < LS_FPW; ++j) {
     dsum[j].warp_reduce();
     if (lane == 0 && f_base + j < F) {
-      const double p = ls_power_from_sums(dsum[j], (double)n);
+      const double p = ls_power_from_sums(dsum[j], (double)n, ysum[b]);
       power[po_out + f_base + j] = ls_normalize(p, (double)n, normalization, norm_scale ? norm_scale[b] : 1.0);
     }
   }
@@ -212,7 +281,7 @@ ls_direct_kernel(const double* __restrict__ tws, const float* __restrict__ yws,
 template <bool REGULAR>
 __global__ void __launch_bounds__(256)
 ls_window_kernel(const double* __restrict__ t, const ulonglong2* __restrict__ tab, int64_t N,
-                 const double* __restrict__ freq, int64_t F, float4* __restrict__ rot) {
+                 const double* __restrict__ freq, int64_t F, float4* __restrict__ rot, float2* __restrict__ rot2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (f >= F) return;
@@ -220,6 +289,14 @@ ls_window_kernel(const double* __restrict__ t, const ulonglong2* __restrict__ ta
   const unsigned long long kf = (unsigned long long)f;
   LsSums<double> d;
   d.zero();
+  const bool lowf = fabs(fr) * fabs(t[N - 1]) <= LS_LOWF_CYCLES;     // t is shifted to t[0] = 0 and sorted
+  if (lowf) {
+    for (int64_t i = lane; i < N; i += 32) {
+      double s, c;
+      ls_sincos_cycles_f64(fr * t[i], s, c);
+      d.add(0.0, s, c);
+    }
+  } else
   for (int64_t c0 = 0; c0 < N; c0 += 32 * 64) {
     LsSums<float> fs;
     fs.zero();
@@ -242,6 +319,7 @@ ls_window_kernel(const double* __restrict__ t, const ulonglong2* __restrict__ ta
     ls_rotation(d, (double)N, ct, st, cc, ss);
     const double k = 1.0 / (2.0 * (double)N);
     rot[f] = make_float4((float)ct, (float)st, (float)(k / cc), (float)(k / ss));
+    rot2[f] = make_float2((float)((d.c * ct + d.s * st) / (double)N), (float)((d.s * ct - d.c * st) / (double)N));
   }
 }
 
@@ -261,6 +339,7 @@ struct SgStage {
 __global__ void __launch_bounds__(256)
 ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, const float* __restrict__ yc, int B,
                       const double* __restrict__ freq, int64_t F, const float4* __restrict__ rot,
+                      const float2* __restrict__ rot2, const float* __restrict__ ysum,
                       int normalization, double norm_scale, float* __restrict__ power) {
   extern __shared__ __align__(16) unsigned char sg_smem[];
   SgStage* st = reinterpret_cast<SgStage*>(sg_smem);
@@ -350,12 +429,13 @@ ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, con
     const int64_t f = f0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
     if (f >= F) continue;
     const float4 r = rot[f];
+    const float2 r2 = rot2[f];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int bb = b0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
       if (bb >= B) continue;
       power[(int64_t)bb * F + f] =
-          ls_epilogue_shared(acc_c[i][j], acc_s[i][j], r, (float)N, normalization, (float)norm_scale);
+          ls_epilogue_shared(acc_c[i][j], acc_s[i][j], r, r2, ysum[bb], (float)N, normalization, (float)norm_scale);
     }
   }
 }
@@ -400,11 +480,45 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
   float* d_y = nullptr;
   if (s == LKB_OK) s = ws_get_t<double>(WS_D, ptotal + 4, &d_t);
   if (s == LKB_OK) s = ws_get_t<float>(WS_E, ptotal + 4, &d_y);
+  double *d_span = nullptr, *d_ysum = nullptr;
+  if (s == LKB_OK) s = ws_get_t<double>(WS_F, B, &d_span);
+  if (s == LKB_OK) s = ws_get_t<double>(WS_J, B, &d_ysum);
+  // Regular frequency grids?  Host-mode calls can tell from the host copy of `freq`
+  // (device-mode callers of the ragged entry keep the fp64 phase path).
+  bool regular = (mem == LKB_MEM_HOST) && !getenv("LKB_LS_FORCE_FP64_PHASE");
+  std::vector<double> h_f0(B, 0.0), h_df(B, 0.0);
+  if (regular) {
+    for (int b = 0; b < B && regular; ++b) {
+      const int64_t fo = h_freq_offsets ? h_freq_offsets[b] : 0;
+      const int64_t Fb = h_freq_offsets ? h_freq_offsets[b + 1] - fo : F;
+      const double* fq = freq + fo;
+      if (Fb < 2 || Fb >= ((int64_t)1 << 31)) { regular = false; break; }
+      const double f0 = fq[0], df = fq[1] - fq[0];
+      if (!(f0 >= 0.0) || !(df > 0.0)) { regular = false; break; }
+      for (int64_t k = 0; k < Fb; ++k)
+        if (fabs(fq[k] - (f0 + (double)k * df)) > 1e-6 * df) { regular = false; break; }
+      h_f0[b] = f0;
+      h_df[b] = df;
+      if (!h_freq_offsets) {          // one shared grid: same (f0, df) for every light curve
+        for (int bb = 1; bb < B; ++bb) { h_f0[bb] = f0; h_df[bb] = df; }
+        break;
+      }
+    }
+  }
+  double *d_gf0 = nullptr, *d_gdf = nullptr;
+  ulonglong2* d_tab = nullptr;
+  if (s == LKB_OK && regular) {
+    s = ws_get_t<double>(WS_G, B, &d_gf0);
+    if (s == LKB_OK) s = ws_get_t<double>(WS_H, B, &d_gdf);
+    if (s == LKB_OK) s = ws_get_t<ulonglong2>(WS_I, ptotal + 4, &d_tab);
+  }
   if (s != LKB_OK) { free(h_po); return s; }
   cudaError_t e = cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_po, h_po, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && h_freq_offsets)
     e = cudaMemcpyAsync(d_fo, h_freq_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && regular) e = cudaMemcpyAsync(d_gf0, h_f0.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && regular) e = cudaMemcpyAsync(d_gdf, h_df.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // h_po is freed below
   free(h_po);
   if (e != cudaSuccess) { set_error("offset upload failed: %s", cudaGetErrorString(e)); return LKB_E_CUDA; }
@@ -425,16 +539,22 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
   LKB_TRY(stage_out_alloc<float>(mem, WS_OUT0, power, out_count, &d_pow));
 
   if (y_dtype == LKB_DTYPE_F32)
-    ls_prep_ragged_kernel<float><<<B, 256, 0, st>>>(dt_in, (const float*)dy_in, d_off, d_po, d_t, d_y);
+    ls_prep_ragged_kernel<float><<<B, 256, 0, st>>>(dt_in, (const float*)dy_in, d_off, d_po, d_t, d_y, d_span, d_gf0,
+                                                    d_gdf, d_tab, d_ysum);
   else
-    ls_prep_ragged_kernel<double><<<B, 256, 0, st>>>(dt_in, (const double*)dy_in, d_off, d_po, d_t, d_y);
+    ls_prep_ragged_kernel<double><<<B, 256, 0, st>>>(dt_in, (const double*)dy_in, d_off, d_po, d_t, d_y, d_span, d_gf0,
+                                                     d_gdf, d_tab, d_ysum);
   LKB_LAUNCH_CHECK();
 
   dim3 grid((unsigned)((Fmax + LS_FPB - 1) / LS_FPB), (unsigned)B);
   LKB_REQUIRE(B <= 65535, "lkb_ls_power: B > 65535 per call (split the batch)");
   prof_begin(st);
-  ls_direct_kernel<<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, normalization, d_ns,
-                                                   d_pow);
+  if (regular)
+    ls_direct_kernel<true><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_tab, d_y, d_off, d_po, d_freq, d_fo, F, d_span,
+                                                           d_ysum, normalization, d_ns, d_pow);
+  else
+    ls_direct_kernel<false><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_tab, d_y, d_off, d_po, d_freq, d_fo, F, d_span,
+                                                            d_ysum, normalization, d_ns, d_pow);
   prof_end(st);
   LKB_LAUNCH_CHECK();
   LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
@@ -443,8 +563,8 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 }
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
-                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot, int normalization,
-                 double norm_scale, float* d_pow, cudaStream_t st);   // ls_tc.cu
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
+                 const float2* d_rot2, int normalization, double norm_scale, float* d_pow, cudaStream_t st);   // ls_tc.cu
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
@@ -484,13 +604,17 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   LKB_TRY(ws_get_t<float>(WS_E, (size_t)B * Npad, &d_yc));
   LKB_TRY(ws_get_t<float4>(WS_F, F, &d_rot));
   LKB_TRY(ws_get_t<float>(WS_G, B, &d_absmax));
+  float2* d_rot2 = nullptr;
+  float* d_ysumf = nullptr;
+  LKB_TRY(ws_get_t<float2>(WS_M, F, &d_rot2));
+  LKB_TRY(ws_get_t<float>(WS_N, B, &d_ysumf));
 
   ls_shift_time_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(dt_in, N, Npad, d_t);
   LKB_LAUNCH_CHECK();
   if (y_dtype == LKB_DTYPE_F32)
-    ls_prep_shared_kernel<float><<<B, 256, 0, st>>>((const float*)dy_in, N, Npad, d_yc, d_absmax);
+    ls_prep_shared_kernel<float><<<B, 256, 0, st>>>((const float*)dy_in, N, Npad, d_yc, d_absmax, d_ysumf);
   else
-    ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax);
+    ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax, d_ysumf);
   LKB_LAUNCH_CHECK();
   // Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
   // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain.
@@ -513,8 +637,8 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
       LKB_LAUNCH_CHECK();
     }
   }
-  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot);
-  else ls_window_kernel<false><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot);
+  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
+  else ls_window_kernel<false><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
   LKB_LAUNCH_CHECK();
 
   bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
@@ -523,7 +647,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     return LKB_E_UNSUPPORTED;
   }
   if (use_tc) {
-    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, normalization, ns, d_pow, st));
+    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, normalization, ns, d_pow, st));
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -534,7 +658,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     dim3 grid((unsigned)((F + SG_BM - 1) / SG_BM), (unsigned)((B + SG_BN - 1) / SG_BN));
     prof_begin(st);
     ls_shared_simt_kernel<<<grid, 256, 2 * sizeof(SgStage), st>>>(d_t, N, Npad, d_yc, B, d_freq, F, d_rot,
-                                                                 normalization, ns, d_pow);
+                                                                 d_rot2, d_ysumf, normalization, ns, d_pow);
     prof_end(st);
     LKB_LAUNCH_CHECK();
   }

@@ -18,6 +18,15 @@ __device__ __forceinline__ void ls_sincos_cycles(double phase, float& s, float& 
   c = __cosf(x);
 }
 
+// Full-fp64 unit for the LOW-FREQUENCY bins (f * baseline <~ 2 cycles): there cos(wt) barely
+// varies, CC' = E[c'^2] - E[c']^2 cancels to ~1e-3..1e-7 of its terms and fp32 sums (or MUFU
+// sin/cos) would leave a 1e-4..1e-2 relative error in the power.  Only a handful of bins per
+// light curve take this path (the lightkurve default grid starts at f * baseline = 0.2).
+constexpr double LS_LOWF_CYCLES = 2.0;
+__device__ __forceinline__ void ls_sincos_cycles_f64(double phase, double& s, double& c) {
+  sincospi(2.0 * (phase - rint(phase)), &s, &c);
+}
+
 // sin/cos of a 64-bit fixed-point phase (cycles * 2^64): top 23 bits -> float in [-0.5, 0.5)
 __device__ __forceinline__ void ls_sincos_fixed(unsigned long long ph, float& s, float& c) {
   const uint32_t u = (uint32_t)(ph >> 32) ^ 0x80000000u;
@@ -94,11 +103,15 @@ __device__ __forceinline__ void ls_rotation(const LsSums<double>& d, double N, d
   ssp = SSb * ct * ct - 2.0 * SCb * ct * st + CCb * st * st - Stau * Stau;
 }
 
-// astropy normalization="psd": 0.5 * N * (YC^2/CC + YS^2/SS)
-__device__ __forceinline__ double ls_power_from_sums(const LsSums<double>& d, double N) {
+// astropy normalization="psd": 0.5 * N * (YC^2/CC + YS^2/SS).  `ysum` = sum of the (centred, then
+// fp32-rounded) flux actually fed to the sums: YC = sum(w y c') - Y sum(w c') with Y = ysum / N
+// (astropy keeps this term; it only matters when c' is nearly constant, i.e. f * baseline << 1).
+__device__ __forceinline__ double ls_power_from_sums(const LsSums<double>& d, double N, double ysum) {
   double ct, st, ccp, ssp;
   ls_rotation(d, N, ct, st, ccp, ssp);
-  const double YC = (d.ch * ct + d.sh * st) / N, YS = (d.sh * ct - d.ch * st) / N;
+  const double Y = ysum / N;
+  const double Ctau = (d.c * ct + d.s * st) / N, Stau = (d.s * ct - d.c * st) / N;
+  const double YC = (d.ch * ct + d.sh * st) / N - Y * Ctau, YS = (d.sh * ct - d.ch * st) / N - Y * Stau;
   return 0.5 * N * (YC * YC / ccp + YS * YS / ssp);
 }
 
@@ -109,10 +122,11 @@ __device__ __forceinline__ float ls_normalize(double p_raw, double N, int normal
   return (float)p_raw;
 }
 
-// shared-grid epilogue: rot = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}
-__device__ __forceinline__ float ls_epilogue_shared(float ch, float sh, const float4 rot, float N, int normalization,
-                                                    float scale) {
-  const float yc = ch * rot.x + sh * rot.y, ys = sh * rot.x - ch * rot.y;
+// shared-grid epilogue: rot = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}, rot2 = {Ctau, Stau}
+// (= sum(w c'), sum(w s')), ysum = sum of the light curve's effective centred flux.
+__device__ __forceinline__ float ls_epilogue_shared(float ch, float sh, const float4 rot, const float2 rot2,
+                                                    float ysum, float N, int normalization, float scale) {
+  const float yc = ch * rot.x + sh * rot.y - ysum * rot2.x, ys = sh * rot.x - ch * rot.y - ysum * rot2.y;
   const float p = yc * yc * rot.z + ys * ys * rot.w;
   if (normalization == LKB_LS_NORM_PSD_SCALE) return p * scale;
   if (normalization == LKB_LS_NORM_AMPLITUDE) return sqrtf(p * (4.0f / N));

@@ -65,11 +65,13 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=256
 constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
-// flux -> power-of-two scaled fp16 hi/lo planes: yhl[0][b][n] = hi, yhl[1][b][n] = lo
+// flux -> power-of-two scaled fp16 hi/lo planes: yhl[0][b][n] = hi, yhl[1][b][n] = lo.  One block
+// per light curve; also returns the sum of the EFFECTIVE values (hi + lo) / scale for the mean term.
 __global__ void __launch_bounds__(256)
 tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ absmax, int B, int64_t Npad,
-                     __half* __restrict__ yhl, float* __restrict__ inv_scale) {
-  const int b = blockIdx.y;
+                     __half* __restrict__ yhl, float* __restrict__ inv_scale, float* __restrict__ ysum_eff) {
+  __shared__ double red[33];
+  const int b = blockIdx.x;
   const float am = absmax[b];
   // scale = 2^k with scale*absmax in [2^13, 2^14); all-zero light curves keep scale 1
   int e = 0;
@@ -78,16 +80,23 @@ tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ abs
     frexpf(am, &e);                       // am = m * 2^e, m in [0.5, 1)
     sc = ldexpf(1.0f, 14 - e);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[b] = 1.0f / (sc * TC_A_SCALE);
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (i >= Npad) return;
-  const float2 v = *reinterpret_cast<const float2*>(yc + (int64_t)b * Npad + i);
-  const float a0 = v.x * sc, a1 = v.y * sc;
-  const __half2 h = __floats2half2_rn(a0, a1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-  *reinterpret_cast<__half2*>(yhl + (int64_t)b * Npad + i) = h;
-  *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)threadIdx.x * 2; i < Npad; i += (int64_t)blockDim.x * 2) {
+    const float2 v = *reinterpret_cast<const float2*>(yc + (int64_t)b * Npad + i);
+    const float a0 = v.x * sc, a1 = v.y * sc;
+    const __half2 h = __floats2half2_rn(a0, a1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+    const float2 lf = __half22float2(l);
+    acc += (double)hf.x + (double)lf.x + (double)hf.y + (double)lf.y;
+    *reinterpret_cast<__half2*>(yhl + (int64_t)b * Npad + i) = h;
+    *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    inv_scale[b] = 1.0f / (sc * TC_A_SCALE);
+    ysum_eff[b] = (float)(tot / (double)sc);
+  }
 }
 
 struct TcParams {
@@ -95,6 +104,8 @@ struct TcParams {
   const ulonglong2* tab;    // [Npad] fixed-point phase table {a_n, b_n}            (regular grids)
   const double* freq;       // [F]
   const float4* rot;        // [F]
+  const float2* rot2;       // [F]
+  const float* ysum;        // [B] sum of the effective (hi + lo) / scale flux
   const float* inv_scale;   // [B]
   float* power;             // [B, F]
   float* part;              // [nseg, 2, B, F] raw partial (Ch, Sh) accumulators when nseg > 1
@@ -261,6 +272,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const int64_t f = f0 + quad * 32 + lane;
     const bool f_ok = f < p.F;
     const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
+    const float2 r2 = f_ok ? p.rot2[f] : make_float2(0.f, 0.f);
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float Nf = (float)p.N;
     const int64_t plane = (int64_t)p.B * p.F;
@@ -281,7 +293,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
               if (b < p.B) {
                 const float h = p.inv_scale[b];
                 p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
-                                                                  r, Nf, p.normalization, p.norm_scale);
+                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale);
               }
             }
           } else {
@@ -308,6 +320,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
 // sum the split-K partials (round-to-nearest fp32 adds), undo the operand scaling, apply the epilogue
 __global__ void __launch_bounds__(256)
 ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, const float4* __restrict__ rot,
+                    const float2* __restrict__ rot2, const float* __restrict__ ysum,
                     const float* __restrict__ inv_scale, float N, int normalization, float norm_scale,
                     float* __restrict__ power) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,12 +329,23 @@ ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, 
   const int64_t plane = (int64_t)B * F;
   const float* pc = part + (int64_t)b * F + f;
   float ch = 0.f, sh = 0.f;
-  for (int s = 0; s < nseg; ++s) {
+  int s = 0;
+  for (; s + 8 <= nseg; s += 8) {        // 16 independent loads in flight per thread
+    float c[8], d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c[j] = __ldcs(pc + (int64_t)(2 * (s + j)) * plane);
+      d[j] = __ldcs(pc + (int64_t)(2 * (s + j) + 1) * plane);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ch += c[j]; sh += d[j]; }
+  }
+  for (; s < nseg; ++s) {
     ch += pc[(int64_t)(2 * s) * plane];
     sh += pc[(int64_t)(2 * s + 1) * plane];
   }
   const float h = inv_scale[b];
-  power[(int64_t)b * F + f] = ls_epilogue_shared(ch * h, sh * h, rot[f], N, normalization, norm_scale);
+  power[(int64_t)b * F + f] = ls_epilogue_shared(ch * h, sh * h, rot[f], rot2[f], ysum[b], N, normalization, norm_scale);
 }
 
 // ---- host -------------------------------------------------------------------------------------
@@ -347,16 +371,16 @@ bool ls_tc_supported(int B, int64_t N, int64_t F) {
 }
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
-                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot, int normalization,
-                 double norm_scale, float* d_pow, cudaStream_t st) {
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
+                 const float2* d_rot2, int normalization, double norm_scale, float* d_pow, cudaStream_t st) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
-  float* d_inv = nullptr;
+  float *d_inv = nullptr, *d_ysum = nullptr;
   LKB_TRY(ws_get_t<__half>(WS_H, (size_t)2 * B * Npad, &d_yhl));
   LKB_TRY(ws_get_t<float>(WS_I, B, &d_inv));
-  tc_split_flux_kernel<<<dim3((unsigned)((Npad / 2 + 255) / 256), (unsigned)B), 256, 0, st>>>(d_yc, d_absmax, B, Npad,
-                                                                                           d_yhl, d_inv);
+  LKB_TRY(ws_get_t<float>(WS_O, B, &d_ysum));
+  tc_split_flux_kernel<<<B, 256, 0, st>>>(d_yc, d_absmax, B, Npad, d_yhl, d_inv, d_ysum);
   LKB_LAUNCH_CHECK();
 
   CUtensorMap map;
@@ -386,7 +410,7 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   if (nseg > 1) LKB_TRY(ws_get_t<float>(WS_J, (size_t)nseg * 2 * B * F, &d_part));
 
   TcParams p;
-  p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
+  p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.rot2 = d_rot2; p.ysum = d_ysum; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
@@ -397,7 +421,7 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   LKB_LAUNCH_CHECK();
   if (nseg > 1) {
     ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(
-        d_part, nseg, B, F, d_rot, d_inv, (float)N, normalization, (float)norm_scale, d_pow);
+        d_part, nseg, B, F, d_rot, d_rot2, d_ysum, d_inv, (float)N, normalization, (float)norm_scale, d_pow);
     LKB_LAUNCH_CHECK();
   }
   return LKB_OK;

@@ -62,6 +62,32 @@ def test_ls_ragged_per_lc_grids_and_f32(engine):
         assert_ls_close(o, p)
 
 
+def test_ls_very_low_frequencies(engine):
+    """f * baseline << 1: CC'/SS' cancel to ~1e-6 of their terms; the kernels take a full-fp64 path
+    for those bins (ragged, shared-SIMT and shared-tcgen05 window terms)."""
+    rng = np.random.default_rng(13)
+    N = 6000
+    t = np.sort(rng.uniform(0, 27.4, N)) + 1325
+    y = 1 + 1e-3 * np.sin(2 * np.pi * 3.1 * t) + 3e-4 * rng.normal(size=N)
+    T = t[-1] - t[0]
+    # (below f * baseline ~ 0.01 the fp64 reference formula itself is ill-conditioned: CC' ~ 1e-11)
+    freq = np.concatenate([np.array([0.01, 0.02, 0.03, 0.05, 0.1, 0.3, 1.0, 1.9, 2.1, 3.0]) / T,
+                           np.linspace(5 / T, 8.0, 390)])
+    ref = np.sqrt(ols.ls_slow_psd(t, y, freq)) * np.sqrt(4.0 / N)
+    out = engine.ls_power_ragged([t], [y], freq, "amplitude")[0]
+    np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-5 * ref.max())
+    reg = (1 + np.arange(400)) * (0.05 / T)                       # regular grid starting at 0.05 cycles/baseline
+    ref = np.sqrt(ols.ls_slow_psd(t, y, reg)) * np.sqrt(4.0 / N)
+    out = engine.ls_power_ragged([t], [y], reg, "amplitude")[0]
+    np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-5 * ref.max())
+    Y = np.stack([y + 1e-4 * rng.normal(size=N) for _ in range(70)])
+    for algo in ("simt", "tcgen05"):
+        out = engine.ls_power_shared(t, Y, reg, "amplitude", algo=algo)
+        for b in (0, 69):
+            ref = np.sqrt(ols.ls_slow_psd(t, Y[b], reg)) * np.sqrt(4.0 / N)
+            np.testing.assert_allclose(out[b], ref, rtol=2e-4, atol=1e-5 * ref.max(), err_msg=algo)
+
+
 def test_ls_constant_flux_is_exactly_zero(engine):
     """reference tests/test_periodogram.py:445-457 (masked NaN -> [1,1,1] must give power == 0)."""
     t = np.array([1.0, 3.0, 4.0])
