@@ -27,6 +27,8 @@ struct FlWs {
   uint8_t* mask1;    // [total]
   int32_t* sidx;     // [total] survivors (positions in the compacted list)
   int32_t* cuts;     // [total + B] segment start positions
+  double* xs;        // [total] survivors' times (contiguous)
+  double* ys;        // [total] survivors' trend values
 };
 
 __device__ __forceinline__ int fl_skew(int e) { return e + (e >> 4); }
@@ -204,17 +206,22 @@ flatten_kernel(const double* __restrict__ time, const double* __restrict__ flux,
     const int ms = block_compact([&](int i) { return mask1[i] != 0; }, m, sidx, s_wc, &s_base);
     if (ms < 2) { ok = false; break; }
     // ---- interp1d(kind="linear", fill_value="extrapolate") onto every cadence (:1053-1058) ----
+    // survivors' (time, trend) made contiguous first (re-using fc / the tail of tc is not possible:
+    // both are still needed), so the binary search does one dependent load per step
+    double* xs = ws.xs + o;
+    double* ys = ws.ys + o;
+    for (int k = threadIdx.x; k < ms; k += blockDim.x) { const int j = sidx[k]; xs[k] = tc[j]; ys[k] = trc[j]; }
+    __syncthreads();
     for (int g = threadIdx.x; g < n; g += blockDim.x) {
       const double xq = t[g];
       // np.searchsorted(xp, xq, side="left")
       int lo = 0, hi = ms;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (tc[sidx[mid]] < xq) lo = mid + 1; else hi = mid;
+        if (xs[mid] < xq) lo = mid + 1; else hi = mid;
       }
-      int idx = lo < 1 ? 1 : (lo > ms - 1 ? ms - 1 : lo);
-      const int il = sidx[idx - 1], ih = sidx[idx];
-      const double xl = tc[il], xh = tc[ih], yl = trc[il], yh = trc[ih];
+      const int idx = lo < 1 ? 1 : (lo > ms - 1 ? ms - 1 : lo);
+      const double xl = xs[idx - 1], xh = xs[idx], yl = ys[idx - 1], yh = ys[idx];
       const double slope = (yh - yl) / (xh - xl);
       tr[g] = slope * (xq - xl) + yl;
     }
@@ -396,6 +403,8 @@ int flatten(const double* time, const double* flux, const double* flux_err, cons
   LKB_TRY(ws_get_t<uint8_t>(WS_I, total, &ws.mask1));
   LKB_TRY(ws_get_t<int32_t>(WS_J, total, &ws.sidx));
   LKB_TRY(ws_get_t<int32_t>(WS_K, total + B, &ws.cuts));
+  LKB_TRY(ws_get_t<double>(WS_L, total, &ws.xs));
+  LKB_TRY(ws_get_t<double>(WS_M, total, &ws.ys));
 
   double *o_flat = nullptr, *o_fe = nullptr, *o_tr = nullptr;
   LKB_TRY(stage_out_alloc<double>(mem, WS_OUT0, flat, total, &o_flat));

@@ -240,13 +240,14 @@ ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ 
         const float yy = s_y[buf][i];
         if constexpr (REGULAR) {
           const ulonglong2 e = s_t[buf][i];
-          unsigned long long ph = e.x + (unsigned long long)f_base * e.y;
+          uint32_t ph = (uint32_t)((e.x + (unsigned long long)f_base * e.y) >> 32);   // exact for bin f_base
+          const uint32_t db = (uint32_t)(e.y >> 32);        // next bins: 32-bit steps (error < 3 * 2^-32 cycle)
 #pragma unroll
           for (int j = 0; j < LS_FPW; ++j) {
             float s, c;
-            ls_sincos_fixed(ph, s, c);
+            ls_sincos_fixed32(ph, s, c);
             fs[j].add(yy, s, c);
-            ph += e.y;
+            ph += db;
           }
         } else {
           const double tt = s_t[buf][i];
@@ -339,7 +340,7 @@ struct SgStage {
 __global__ void __launch_bounds__(256)
 ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, const float* __restrict__ yc, int B,
                       const double* __restrict__ freq, int64_t F, const float4* __restrict__ rot,
-                      const float2* __restrict__ rot2, const float* __restrict__ ysum,
+                      const float2* __restrict__ rot2, const float* __restrict__ ysum, double lowf_max,
                       int normalization, double norm_scale, float* __restrict__ power) {
   extern __shared__ __align__(16) unsigned char sg_smem[];
   SgStage* st = reinterpret_cast<SgStage*>(sg_smem);
@@ -352,6 +353,7 @@ ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, con
   // design-matrix role: one frequency per thread, 8 cadences of each k-tile
   const int gf = tid & (SG_BM - 1), gk0 = (tid >> 7) * 8;
   const double my_f = (f0 + gf < F) ? freq[f0 + gf] : 0.0;
+  const bool my_low = fabs(my_f) <= lowf_max;
   // flux-tile role: two float4 per thread
   const int yr0 = tid >> 2, yq = tid & 3;            // rows yr0 and yr0+64, k-quad yq
 
@@ -371,7 +373,8 @@ ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, con
     for (int i = 0; i < 8; ++i) {
       const int64_t nn = n0 + i;
       const double tt = (nn < N) ? t[nn] : 0.0;
-      ls_sincos_cycles(my_f * tt, gs[i], gc[i]);
+      if (my_low) ls_sincos_cycles_low(my_f * tt, gs[i], gc[i]);
+      else ls_sincos_cycles(my_f * tt, gs[i], gc[i]);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -430,12 +433,14 @@ ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, con
     if (f >= F) continue;
     const float4 r = rot[f];
     const float2 r2 = rot2[f];
+    const bool low = fabs(freq[f]) <= lowf_max;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int bb = b0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
       if (bb >= B) continue;
       power[(int64_t)bb * F + f] =
-          ls_epilogue_shared(acc_c[i][j], acc_s[i][j], r, r2, ysum[bb], (float)N, normalization, (float)norm_scale);
+          ls_epilogue_shared(acc_c[i][j], acc_s[i][j], r, r2, ysum[bb], (float)N, normalization, (float)norm_scale,
+                             low);
     }
   }
 }
@@ -564,7 +569,8 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, int normalization, double norm_scale, float* d_pow, cudaStream_t st);   // ls_tc.cu
+                 const float2* d_rot2, double lowf_max, int normalization, double norm_scale, float* d_pow,
+                 cudaStream_t st);   // ls_tc.cu
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
@@ -641,13 +647,19 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   else ls_window_kernel<false><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
   LKB_LAUNCH_CHECK();
 
+  // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
+  double h_tlast = 0.0;
+  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_tlast, d_t + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  const double lowf_max = (h_tlast > 0.0) ? LS_LOWF_CYCLES / h_tlast : 0.0;
+
   bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
   if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
     set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
     return LKB_E_UNSUPPORTED;
   }
   if (use_tc) {
-    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, normalization, ns, d_pow, st));
+    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, lowf_max, normalization, ns, d_pow, st));
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -658,7 +670,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     dim3 grid((unsigned)((F + SG_BM - 1) / SG_BM), (unsigned)((B + SG_BN - 1) / SG_BN));
     prof_begin(st);
     ls_shared_simt_kernel<<<grid, 256, 2 * sizeof(SgStage), st>>>(d_t, N, Npad, d_yc, B, d_freq, F, d_rot,
-                                                                 d_rot2, d_ysumf, normalization, ns, d_pow);
+                                                                 d_rot2, d_ysumf, lowf_max, normalization, ns, d_pow);
     prof_end(st);
     LKB_LAUNCH_CHECK();
   }

@@ -17,6 +17,21 @@ __device__ __forceinline__ void ls_sincos_cycles(double phase, float& s, float& 
   s = __sinf(x);
   c = __cosf(x);
 }
+// Low-frequency rows of the shared-grid contractions (f * baseline <= LS_LOWF_CYCLES): the design
+// matrix carries cos - 1 = -2 sin^2(phase / 2) instead of cos.  sum y (cos - 1) is a sum of SMALL
+// well-conditioned terms (sum y cos would be ~sum y + a tiny signal, amplifying fp32 / tensor-core
+// accumulation error by 1 / (f T)^2); the epilogue adds sum y back.  `x` = phase in cycles, [-0.5, 0.5].
+__device__ __forceinline__ float ls_cos_minus1(float x) {
+  const float h = __sinf(3.14159265358979f * x);
+  return -2.0f * h * h;
+}
+__device__ __forceinline__ void ls_sincos_cycles_low(double phase, float& s, float& cm1) {
+  const double magic = 6755399441055744.0;
+  const double r = __dadd_rn(phase, magic);
+  const float x = (float)__dsub_rn(phase, __dsub_rn(r, magic));
+  s = __sinf(x * 6.283185307179586f);
+  cm1 = ls_cos_minus1(x);
+}
 
 // Full-fp64 unit for the LOW-FREQUENCY bins (f * baseline <~ 2 cycles): there cos(wt) barely
 // varies, CC' = E[c'^2] - E[c']^2 cancels to ~1e-3..1e-7 of its terms and fp32 sums (or MUFU
@@ -27,15 +42,24 @@ __device__ __forceinline__ void ls_sincos_cycles_f64(double phase, double& s, do
   sincospi(2.0 * (phase - rint(phase)), &s, &c);
 }
 
-// sin/cos of a 64-bit fixed-point phase (cycles * 2^64): top 23 bits -> float in [-0.5, 0.5)
-__device__ __forceinline__ void ls_sincos_fixed(unsigned long long ph, float& s, float& c) {
-  const uint32_t u = (uint32_t)(ph >> 32) ^ 0x80000000u;
-  const float x = __uint_as_float((u >> 9) | 0x3f800000u) - 1.5f;
-  const float r = x * 6.283185307179586f;
+// sin/cos of a fixed-point phase given by its top 32 bits (cycles * 2^32): the top 23 bits become
+// the mantissa of a float in [1, 2), one FFMA maps it to radians in [0, 2 pi)  (3 integer/FMA ops,
+// no fp64, no conversion instruction; quantisation 2^-23 cycle = 7.5e-7 rad, below the MUFU error).
+__device__ __forceinline__ void ls_sincos_fixed32(uint32_t ph, float& s, float& c) {
+  const float m = __uint_as_float((ph >> 9) | 0x3f800000u);
+  const float r = fmaf(m, 6.283185307179586f, -6.283185307179586f);
   s = __sinf(r);
   c = __cosf(r);
 }
-
+__device__ __forceinline__ void ls_sincos_fixed(unsigned long long ph, float& s, float& c) {
+  ls_sincos_fixed32((uint32_t)(ph >> 32), s, c);
+}
+__device__ __forceinline__ void ls_sincos_fixed_low(unsigned long long ph, float& s, float& cm1) {
+  const float x = __uint_as_float(((uint32_t)(ph >> 32) >> 9) | 0x3f800000u) - 1.0f;   // [0, 1) cycles
+  const float xc = x - (x >= 0.5f ? 1.0f : 0.0f);                                     // [-0.5, 0.5)
+  s = __sinf(xc * 6.283185307179586f);
+  cm1 = ls_cos_minus1(xc);
+}
 
 // Regular frequency grids f_k = f0 + k df (the lightkurve default, and what astropy's "fast"
 // method requires): phase(k, n) = frac(f0 t_n) + k frac(df t_n) is evaluated in 64-bit FIXED POINT
@@ -125,7 +149,9 @@ __device__ __forceinline__ float ls_normalize(double p_raw, double N, int normal
 // shared-grid epilogue: rot = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}, rot2 = {Ctau, Stau}
 // (= sum(w c'), sum(w s')), ysum = sum of the light curve's effective centred flux.
 __device__ __forceinline__ float ls_epilogue_shared(float ch, float sh, const float4 rot, const float2 rot2,
-                                                    float ysum, float N, int normalization, float scale) {
+                                                    float ysum, float N, int normalization, float scale,
+                                                    bool low_row = false) {
+  if (low_row) ch += ysum;      // the design matrix held cos - 1 for this frequency (see ls_cos_minus1)
   const float yc = ch * rot.x + sh * rot.y - ysum * rot2.x, ys = sh * rot.x - ch * rot.y - ysum * rot2.y;
   const float p = yc * yc * rot.z + ys * ys * rot.w;
   if (normalization == LKB_LS_NORM_PSD_SCALE) return p * scale;

@@ -114,6 +114,8 @@ struct TcParams {
   int normalization;
   float norm_scale;
   int seg_stages, nseg;
+  double lowf_max;          // frequencies <= this are "low rows": design matrix carries cos - 1
+  double f0, df;            // regular grid (REGULAR kernels)
 };
 
 // split fp32 (c0, c1) and (s0, s1) into fp16 hi / residual words
@@ -227,7 +229,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const uint32_t row_off = (uint32_t)row * 64u + ((((uint32_t)chunk) ^ (uint32_t)((row >> 1) & 3)) << 4);
     ulonglong2* my_scr = reinterpret_cast<ulonglong2*>(scratch + gw * 128);
     const unsigned long long kfreq = (unsigned long long)(f0 + row);          // global frequency index
-    const double fr = (!REGULAR && f0 + row < p.F) ? p.freq[f0 + row] : 0.0;
+    const double fr = REGULAR ? (p.f0 + (double)(f0 + row) * p.df) : ((f0 + row < p.F) ? p.freq[f0 + row] : 0.0);
+    const bool low_row = fabs(fr) <= p.lowf_max;
     ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
     auto prefetch = [&](int it) {
       if (lane < 8) {
@@ -250,11 +253,21 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         float s0, c0, s1, c1;
         const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
         if (REGULAR) {
-          ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
-          ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+          if (low_row) {
+            ls_sincos_fixed_low(e0.x + kfreq * e0.y, s0, c0);
+            ls_sincos_fixed_low(e1.x + kfreq * e1.y, s1, c1);
+          } else {
+            ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
+            ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+          }
         } else {
-          ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
-          ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
+          if (low_row) {
+            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e0.x), s0, c0);
+            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e1.x), s1, c1);
+          } else {
+            ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
+            ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
+          }
         }
         tc_split2(c0, c1, s0, s1, ch[q], cl[q], sh[q], sl[q]);
       }
@@ -273,6 +286,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const bool f_ok = f < p.F;
     const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
     const float2 r2 = f_ok ? p.rot2[f] : make_float2(0.f, 0.f);
+    const bool low_out = f_ok && fabs(p.freq[f]) <= p.lowf_max;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const float Nf = (float)p.N;
     const int64_t plane = (int64_t)p.B * p.F;
@@ -293,7 +307,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
               if (b < p.B) {
                 const float h = p.inv_scale[b];
                 p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
-                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale);
+                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale, low_out);
               }
             }
           } else {
@@ -321,8 +335,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
 __global__ void __launch_bounds__(256)
 ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, const float4* __restrict__ rot,
                     const float2* __restrict__ rot2, const float* __restrict__ ysum,
-                    const float* __restrict__ inv_scale, float N, int normalization, float norm_scale,
-                    float* __restrict__ power) {
+                    const float* __restrict__ inv_scale, const double* __restrict__ freq, double lowf_max, float N,
+                    int normalization, float norm_scale, float* __restrict__ power) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (f >= F) return;
@@ -345,7 +359,8 @@ ls_tc_finish_kernel(const float* __restrict__ part, int nseg, int B, int64_t F, 
     sh += pc[(int64_t)(2 * s + 1) * plane];
   }
   const float h = inv_scale[b];
-  power[(int64_t)b * F + f] = ls_epilogue_shared(ch * h, sh * h, rot[f], rot2[f], ysum[b], N, normalization, norm_scale);
+  power[(int64_t)b * F + f] = ls_epilogue_shared(ch * h, sh * h, rot[f], rot2[f], ysum[b], N, normalization, norm_scale,
+                                                 fabs(freq[f]) <= lowf_max);
 }
 
 // ---- host -------------------------------------------------------------------------------------
@@ -372,7 +387,8 @@ bool ls_tc_supported(int B, int64_t N, int64_t F) {
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, int normalization, double norm_scale, float* d_pow, cudaStream_t st) {
+                 const float2* d_rot2, double lowf_max, int normalization, double norm_scale, float* d_pow,
+                 cudaStream_t st) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
@@ -413,6 +429,14 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.rot2 = d_rot2; p.ysum = d_ysum; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
+  p.lowf_max = lowf_max; p.f0 = 0.0; p.df = 0.0;
+  if (regular) {
+    double h_f01[2];
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    p.f0 = h_f01[0];
+    p.df = h_f01[1] - h_f01[0];
+  }
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   prof_begin(st);
   if (regular) ls_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
@@ -421,7 +445,8 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   LKB_LAUNCH_CHECK();
   if (nseg > 1) {
     ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(
-        d_part, nseg, B, F, d_rot, d_rot2, d_ysum, d_inv, (float)N, normalization, (float)norm_scale, d_pow);
+        d_part, nseg, B, F, d_rot, d_rot2, d_ysum, d_inv, d_freq, lowf_max, (float)N, normalization, (float)norm_scale,
+        d_pow);
     LKB_LAUNCH_CHECK();
   }
   return LKB_OK;

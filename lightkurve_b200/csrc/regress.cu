@@ -87,6 +87,8 @@ rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __res
                 const double* __restrict__ flux_err, int64_t N, int K, int nblk, double sign, RgWs ws) {
   __shared__ double s_a[RG_RC][RG_BLK];   // w * [X|y][:, bi block]
   __shared__ double s_b[RG_RC][RG_BLK];   //     [X|y][:, bj block]
+  __shared__ double s_w[RG_RC];           // 1 / flux_err^2 of the chunk's cadences
+  __shared__ int s_row[RG_RC];
   const int b = blockIdx.y;
   // decode upper-triangular block index
   int bi = 0, rem = blockIdx.x;
@@ -108,13 +110,24 @@ rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __res
   for (int c0 = 0; c0 < cnt; c0 += RG_RC) {
     const int nr = min(RG_RC, cnt - c0);
     __syncthreads();
+    if (threadIdx.x < RG_RC) {
+      int row = 0;
+      double w = 0.0;
+      if (threadIdx.x < nr) {
+        row = rows[c0 + threadIdx.x];
+        const double s = fe ? fe[row] : 1.0;
+        w = 1.0 / (s * s);
+      }
+      s_row[threadIdx.x] = row;
+      s_w[threadIdx.x] = w;
+    }
+    __syncthreads();
     for (int e = threadIdx.x; e < RG_RC * RG_BLK; e += blockDim.x) {
       const int r = e / RG_BLK, c = e % RG_BLK;
       double va = 0.0, vb = 0.0;
       if (r < nr) {
-        const int64_t row = rows[c0 + r];
-        const double s = fe ? fe[row] : 1.0;
-        const double w = 1.0 / (s * s);
+        const int64_t row = s_row[r];
+        const double w = s_w[r];
         const double* xr = rg_xrow(X, x_batched, b, N, K, row);
         const int ca = bi * RG_BLK + c, cb = bj * RG_BLK + c;
         if (ca < Ka) va = (ca < K ? xr[ca] : yb[row]) * w;

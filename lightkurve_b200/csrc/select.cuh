@@ -34,12 +34,20 @@ __device__ unsigned long long block_select_key(Get get, int64_t n, long long k, 
   for (int shift = 56; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.hist[i] = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const double v = get(i);
-      if (v == v) {
-        const unsigned long long key = f64_key(v);
-        if ((key & mask) == prefix) atomicAdd(&sm.hist[(int)((key >> shift) & 255ull)], 1);
+    for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {         // warp-uniform trip count
+      const int64_t i = i0 + threadIdx.x;
+      int digit = -1;
+      if (i < n) {
+        const double v = get(i);
+        if (v == v) {
+          const unsigned long long key = f64_key(v);
+          if ((key & mask) == prefix) digit = (int)((key >> shift) & 255ull);
+        }
       }
+      // warp-aggregated update: one atomic per distinct digit per warp (a regular cadence makes every
+      // dt identical - a naive per-lane atomicAdd would serialise 32-way on one counter)
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (digit >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&sm.hist[digit], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < 32) {
