@@ -312,8 +312,15 @@ def main():
         k_ms = float(np.mean(kms)) if len(kms) else float("nan")
         flops = 4.0 * F * N * B                                # algorithmic: 2 (cos,sin) x 2 flop per MAC
         achieved = flops / (k_ms * 1e-3) / 1e12
+        traffic = None
+        try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "bench_kernel_traffic.json")))
+            if args.workload == "c2" and args.algo != "simt":
+                traffic = tj["ls_tc_kernel"]["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "kernel": "ls_tc_kernel" if args.algo != "simt"
+                    "frac": achieved / peak_tf, "traffic": traffic, "kernel": "ls_tc_kernel" if args.algo != "simt"
                     else "ls_shared_simt_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
                     "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
         cpu = None

@@ -56,6 +56,18 @@ int ensure_device() {
 
 int sm_count() { return g_ctx.sms; }
 
+static cudaStream_t g_aux = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+int aux_stream_get(cudaStream_t* aux, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+  if (!g_aux) {
+    LKB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking));
+    LKB_CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+    LKB_CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  }
+  *aux = g_aux; *ev_fork = g_ev_fork; *ev_join = g_ev_join;
+  return LKB_OK;
+}
+
 // ---- dominant-kernel profiling ring ----
 constexpr int PROF_MAX = 512;
 static bool g_prof_on = false;
@@ -153,6 +165,7 @@ int lkb_shutdown(void) {
     g_ctx.ptr[i] = nullptr;
     g_ctx.cap[i] = 0;
   }
+  if (g_aux) { cudaStreamDestroy(g_aux); cudaEventDestroy(g_ev_fork); cudaEventDestroy(g_ev_join); g_aux = nullptr; }
   g_ctx.inited = false;
   return LKB_OK;
 }

@@ -126,8 +126,16 @@ __device__ __forceinline__ void bls_warp_bin(int key, double vy, double vi, doub
   const unsigned wrapmask = __ballot_sync(full, wrap);
   const unsigned le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
   const int start = 31 - __clz(headmask & le);
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
+  // scan only as many steps as the longest run needs (runs are ~bin_duration/cadence ~ 3-4 samples):
+  // after smearing the head mask by 2^s - 1 lanes, "all ones" means every lane has its run head within
+  // 2^s - 1 lanes, i.e. all runs are <= 2^s long and s steps suffice.  headmask is warp-uniform.
+  unsigned m = headmask | (headmask << 1);
+  int span = 2;
+  if (m != full) { m |= m << 2; span = 4; }
+  if (m != full) { m |= m << 4; span = 8; }
+  if (m != full) { m |= m << 8; span = 16; }
+  if (m != full) span = 32;
+  for (int o = 1; o < span; o <<= 1) {
     const double uy = __shfl_up_sync(full, vy, o);
     const double ui = __shfl_up_sync(full, vi, o);
     if (lane - o >= start) { vy += uy; vi += ui; }

@@ -71,6 +71,9 @@ int sm_count();
 // CUDA events recorded on the launching stream around that kernel when profiling is enabled.
 void prof_begin(cudaStream_t st);
 void prof_end(cudaStream_t st);
+// Library-owned side stream + fork/join events: lets a small independent kernel (the LS window
+// terms) run concurrently with the long contraction kernel on the caller's stream.
+int aux_stream_get(cudaStream_t* aux, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
 
 // Stage a host buffer into the pool (or pass a device pointer through).
 template <typename T>

@@ -59,7 +59,7 @@ __device__ int block_compact(Pred pred, int n, int32_t* out, int* s_warp_counts,
   return *s_base;
 }
 
-__global__ void __launch_bounds__(FL_THREADS)
+__global__ void __launch_bounds__(FL_THREADS, 2)
 flatten_kernel(const double* __restrict__ time, const double* __restrict__ flux, const double* __restrict__ flux_err,
                const uint8_t* __restrict__ exclude, const int64_t* __restrict__ offsets, FlWs ws,
                int window_length, int polyorder, double break_tolerance, int niters, double sigma,

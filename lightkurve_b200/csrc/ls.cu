@@ -280,7 +280,7 @@ ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ 
 // One warp per frequency; rot[f] = {cos tau, sin tau, 1/(2 N CC'), 1/(2 N SS')}.
 // =====================================================================================
 template <bool REGULAR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 ls_window_kernel(const double* __restrict__ t, const ulonglong2* __restrict__ tab, int64_t N,
                  const double* __restrict__ freq, int64_t F, float4* __restrict__ rot, float2* __restrict__ rot2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -569,8 +569,8 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, double lowf_max, int normalization, double norm_scale, float* d_pow,
-                 cudaStream_t st);   // ls_tc.cu
+                 const float2* d_rot2, double lowf_max, double grid_f0, double grid_df, int normalization,
+                 double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready);   // ls_tc.cu
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
@@ -622,36 +622,46 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   else
     ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax, d_ysumf);
   LKB_LAUNCH_CHECK();
+  // One small device->host read-back per call: grid regularity, f0, f1 and the baseline t[N-1].
   // Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
   // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain.
   ulonglong2* d_tab = nullptr;
-  if (F >= 2 && F < ((int64_t)1 << 31) && !getenv("LKB_LS_FORCE_FP64_PHASE")) {
-    float* d_dev = nullptr;
-    LKB_TRY(ws_get_t<float>(WS_K, 4, &d_dev));
-    LKB_CUDA_CHECK(cudaMemsetAsync(d_dev, 0, sizeof(float), st));
-    ls_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, d_dev);
+  double h_meta[4] = {1.0, 0.0, 0.0, 0.0};      // {regularity deviation, f0, f1, t_last}
+  {
+    double* d_meta = nullptr;
+    LKB_TRY(ws_get_t<double>(WS_K, 4, &d_meta));
+    LKB_CUDA_CHECK(cudaMemsetAsync(d_meta, 0, 4 * sizeof(double), st));
+    ls_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, reinterpret_cast<float*>(d_meta));
     LKB_LAUNCH_CHECK();
-    float h_dev = 1.f;
-    double h_f01[2] = {0.0, 0.0};
-    LKB_CUDA_CHECK(cudaMemcpyAsync(&h_dev, d_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
-    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ls_meta_kernel<<<1, 1, 0, st>>>(d_freq, F, d_t, N, d_meta);
+    LKB_LAUNCH_CHECK();
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_meta, d_meta, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (h_dev <= 1e-6f && h_f01[0] >= 0.0 && h_f01[1] > h_f01[0]) {
-      LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
-      ls_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, h_f01[0],
-                                                                          h_f01[1] - h_f01[0], d_tab);
-      LKB_LAUNCH_CHECK();
-    }
   }
-  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
-  else ls_window_kernel<false><<<(unsigned)((F + 7) / 8), 256, 0, st>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
-  LKB_LAUNCH_CHECK();
-
+  const double grid_f0 = h_meta[1], grid_df = h_meta[2] - h_meta[1];
+  const bool regular = F >= 2 && F < ((int64_t)1 << 31) && !getenv("LKB_LS_FORCE_FP64_PHASE") &&
+                       h_meta[0] <= 1e-6 && grid_f0 >= 0.0 && grid_df > 0.0;
+  if (regular) {
+    LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
+    ls_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, grid_f0, grid_df, d_tab);
+    LKB_LAUNCH_CHECK();
+  }
   // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
-  double h_tlast = 0.0;
-  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_tlast, d_t + (N - 1), sizeof(double), cudaMemcpyDeviceToHost, st));
-  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-  const double lowf_max = (h_tlast > 0.0) ? LS_LOWF_CYCLES / h_tlast : 0.0;
+  const double lowf_max = (h_meta[3] > 0.0) ? LS_LOWF_CYCLES / h_meta[3] : 0.0;
+  // The window terms depend only on (t, freq).  They CAN run on the library's side stream, co-resident
+  // with the contraction kernel (LKB_LS_OVERLAP_WINDOW=1), but measured on B200 that costs more than it
+  // hides (tc kernel 65 -> 73.6 ms: the co-resident MUFU work competes for issue slots and for the power
+  // budget), so by default they run in order on the caller's stream.
+  cudaStream_t aux;
+  cudaEvent_t ev_fork, ev_join;
+  LKB_TRY(aux_stream_get(&aux, &ev_fork, &ev_join));
+  if (!getenv("LKB_LS_OVERLAP_WINDOW")) aux = st;
+  LKB_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+  LKB_CUDA_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
+  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
+  else ls_window_kernel<false><<<(unsigned)((F + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
+  LKB_LAUNCH_CHECK();
+  LKB_CUDA_CHECK(cudaEventRecord(ev_join, aux));
 
   bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
   if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
@@ -659,7 +669,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     return LKB_E_UNSUPPORTED;
   }
   if (use_tc) {
-    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, lowf_max, normalization, ns, d_pow, st));
+    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, lowf_max, grid_f0, grid_df, normalization, ns, d_pow, st, ev_join));
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -668,6 +678,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
       attr_set = true;
     }
     dim3 grid((unsigned)((F + SG_BM - 1) / SG_BM), (unsigned)((B + SG_BN - 1) / SG_BN));
+    LKB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
     prof_begin(st);
     ls_shared_simt_kernel<<<grid, 256, 2 * sizeof(SgStage), st>>>(d_t, N, Npad, d_yc, B, d_freq, F, d_rot,
                                                                  d_rot2, d_ysumf, lowf_max, normalization, ns, d_pow);

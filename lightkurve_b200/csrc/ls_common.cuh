@@ -82,6 +82,7 @@ static __global__ void ls_phase_table_kernel(const double* __restrict__ t, int64
 
 // max_k |freq[k] - (f0 + k df)| / |df| (0 for a perfectly regular grid)
 static __global__ void ls_grid_regularity_kernel(const double* __restrict__ freq, int64_t F, float* __restrict__ out) {
+  if (F < 2) return;
   const double f0 = freq[0], df = freq[1] - freq[0];
   float worst = 0.f;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < F; k += (int64_t)gridDim.x * blockDim.x) {
@@ -91,6 +92,16 @@ static __global__ void ls_grid_regularity_kernel(const double* __restrict__ freq
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(worst));   // worst >= 0
+}
+
+// meta[0] (written as float bits by the regularity kernel, 0 when F < 2) -> double; meta[1..3] = f0, f1, t_last
+static __global__ void ls_meta_kernel(const double* __restrict__ freq, int64_t F, const double* __restrict__ t,
+                                      int64_t N, double* __restrict__ meta) {
+  const float dev = *reinterpret_cast<const float*>(meta);
+  meta[0] = (F >= 2) ? (double)dev : 1.0;
+  meta[1] = freq[0];
+  meta[2] = (F >= 2) ? freq[1] : freq[0];
+  meta[3] = fabs(t[N - 1]);
 }
 
 template <typename T>

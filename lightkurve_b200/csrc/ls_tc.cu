@@ -387,8 +387,8 @@ bool ls_tc_supported(int B, int64_t N, int64_t F) {
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, double lowf_max, int normalization, double norm_scale, float* d_pow,
-                 cudaStream_t st) {
+                 const float2* d_rot2, double lowf_max, double grid_f0, double grid_df, int normalization,
+                 double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
@@ -429,21 +429,16 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.rot2 = d_rot2; p.ysum = d_ysum; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
-  p.lowf_max = lowf_max; p.f0 = 0.0; p.df = 0.0;
-  if (regular) {
-    double h_f01[2];
-    LKB_CUDA_CHECK(cudaMemcpyAsync(h_f01, d_freq, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-    p.f0 = h_f01[0];
-    p.df = h_f01[1] - h_f01[0];
-  }
+  p.lowf_max = lowf_max; p.f0 = grid_f0; p.df = grid_df;
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
+  if (nseg == 1) LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));   // direct epilogue needs rot
   prof_begin(st);
   if (regular) ls_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
   else ls_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
   prof_end(st);
   LKB_LAUNCH_CHECK();
   if (nseg > 1) {
+    LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));
     ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(
         d_part, nseg, B, F, d_rot, d_rot2, d_ysum, d_inv, d_freq, lowf_max, (float)N, normalization, (float)norm_scale,
         d_pow);

@@ -82,18 +82,30 @@ rg_rows_kernel(const uint8_t* __restrict__ cadence_mask, const uint8_t* __restri
 
 // ---- weighted Gram accumulation -----------------------------------------------------------------
 // grid = (n_upper_blocks, B); 128 threads = 8 (i) x 16 (j); thread tile 8 x 4.
+// Gathered cadence rows are streamed with cp.async into a double-buffered shared-memory stage
+// (chunk c+1 lands while chunk c is multiplied), then weighted in place.
+__device__ __forceinline__ void rg_cp8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+struct RgStage {
+  double a[RG_RC][RG_BLK];   // [X|y][:, bi block]  (scaled by w after landing)
+  double b[RG_RC][RG_BLK];   // [X|y][:, bj block]
+  double fe[RG_RC];          // flux_err of the chunk's cadences
+  double yv[RG_RC];          // flux of the chunk's cadences (column K)
+};
+
 __global__ void __launch_bounds__(128)
 rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y,
                 const double* __restrict__ flux_err, int64_t N, int K, int nblk, double sign, RgWs ws) {
-  __shared__ double s_a[RG_RC][RG_BLK];   // w * [X|y][:, bi block]
-  __shared__ double s_b[RG_RC][RG_BLK];   //     [X|y][:, bj block]
-  __shared__ double s_w[RG_RC];           // 1 / flux_err^2 of the chunk's cadences
-  __shared__ int s_row[RG_RC];
+  extern __shared__ __align__(16) unsigned char rg_smem[];
+  RgStage* st = reinterpret_cast<RgStage*>(rg_smem);
   const int b = blockIdx.y;
   // decode upper-triangular block index
   int bi = 0, rem = blockIdx.x;
   while (rem >= nblk - bi) { rem -= nblk - bi; ++bi; }
   const int bj = bi + rem;
+  const bool diag = (bi == bj);
   const int Ka = K + 1;
   const int cnt = ws.cnt[b];
   if (cnt == 0) return;
@@ -107,43 +119,61 @@ rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __res
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-  for (int c0 = 0; c0 < cnt; c0 += RG_RC) {
+  auto issue = [&](int c0, int buf) {
     const int nr = min(RG_RC, cnt - c0);
-    __syncthreads();
-    if (threadIdx.x < RG_RC) {
-      int row = 0;
-      double w = 0.0;
-      if (threadIdx.x < nr) {
-        row = rows[c0 + threadIdx.x];
-        const double s = fe ? fe[row] : 1.0;
-        w = 1.0 / (s * s);
-      }
-      s_row[threadIdx.x] = row;
-      s_w[threadIdx.x] = w;
-    }
-    __syncthreads();
+    RgStage& s = st[buf];
     for (int e = threadIdx.x; e < RG_RC * RG_BLK; e += blockDim.x) {
       const int r = e / RG_BLK, c = e % RG_BLK;
-      double va = 0.0, vb = 0.0;
       if (r < nr) {
-        const int64_t row = s_row[r];
-        const double w = s_w[r];
+        const int64_t row = rows[c0 + r];
         const double* xr = rg_xrow(X, x_batched, b, N, K, row);
-        const int ca = bi * RG_BLK + c, cb = bj * RG_BLK + c;
-        if (ca < Ka) va = (ca < K ? xr[ca] : yb[row]) * w;
-        if (cb < Ka) vb = (cb < K ? xr[cb] : yb[row]);
+        const int cb = bj * RG_BLK + c;
+        if (cb < K) rg_cp8(&s.b[r][c], xr + cb);
+        if (!diag) {
+          const int ca = bi * RG_BLK + c;
+          if (ca < K) rg_cp8(&s.a[r][c], xr + ca);
+        }
       }
-      s_a[r][c] = va;
-      s_b[r][c] = vb;
+    }
+    if (threadIdx.x < nr) {
+      const int64_t row = rows[c0 + threadIdx.x];
+      rg_cp8(&s.yv[threadIdx.x], yb + row);
+      if (fe) rg_cp8(&s.fe[threadIdx.x], fe + row);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(0, 0);
+  int buf = 0;
+  for (int c0 = 0; c0 < cnt; c0 += RG_RC, buf ^= 1) {
+    const int nr = min(RG_RC, cnt - c0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                     // chunk c0 landed; everybody is done computing on buf^1
+    if (c0 + RG_RC < cnt) issue(c0 + RG_RC, buf ^ 1);
+    RgStage& s = st[buf];
+    // fix-ups (column K = y, zero padding) and the 1/flux_err^2 weighting of the bi tile
+    for (int e = threadIdx.x; e < RG_RC * RG_BLK; e += blockDim.x) {
+      const int r = e / RG_BLK, c = e % RG_BLK;
+      const int cb = bj * RG_BLK + c, ca = bi * RG_BLK + c;
+      double vb = 0.0, va = 0.0;
+      if (r < nr) {
+        const double yy = s.yv[r];
+        vb = (cb < K) ? s.b[r][c] : (cb == K ? yy : 0.0);
+        va = diag ? vb : ((ca < K) ? s.a[r][c] : (ca == K ? yy : 0.0));
+        const double f = fe ? s.fe[r] : 1.0;
+        va *= 1.0 / (f * f);
+      }
+      s.b[r][c] = vb;
+      s.a[r][c] = va;
     }
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < RG_RC; ++k) {
       double a[8], bb[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = s_a[k][ty + 8 * i];
+      for (int i = 0; i < 8; ++i) a[i] = s.a[k][ty + 8 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = s_b[k][tx + 16 * j];
+      for (int j = 0; j < 4; ++j) bb[j] = s.b[k][tx + 16 * j];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -378,11 +408,18 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     solve_attr = solve_smem;
   }
+  static bool accum_attr = false;
+  if (!accum_attr) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(2 * sizeof(RgStage))));
+    accum_attr = true;
+  }
   for (int it = 0; it < niters; ++it) {
     rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, N, it == 0 ? 1 : 0, ws);
     LKB_LAUNCH_CHECK();
     if (it == 0) prof_begin(st);
-    rg_accum_kernel<<<dim3(nupper, B), 128, 0, st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk, it == 0 ? 1.0 : -1.0, ws);
+    rg_accum_kernel<<<dim3(nupper, B), 128, 2 * sizeof(RgStage), st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk,
+                                                                         it == 0 ? 1.0 : -1.0, ws);
     if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
     rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, o_st);
