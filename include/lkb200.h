@@ -148,12 +148,14 @@ int lkb_savgol_tables(int window_length, int polyorder, double* coeffs, double* 
  *   cadence_mask uint8 [B,N] or NULL (1 = use)
  *   prior_mu, prior_sigma [K] fp64 (sigma may be +inf) or both NULL
  *   outputs: coeff [B,K], model [B,N] (median-subtracted, :278-279),
- *            outlier_mask uint8 [B,N]; status_out int32 [B] (0 or LKB_E_SINGULAR per LC, nullable)
+ *            outlier_mask uint8 [B,N]; status_out int32 [B] (0 or LKB_E_SINGULAR per LC, nullable);
+ *            coeff_cov [B,K,K] (nullable) = (X^T W X + diag(1/prior_sigma^2))^-1 of the last fit, the
+ *            np.linalg.inv(sigma_w_inv) of propagate_errors=True (:185)
  */
 int lkb_regress(const double* X, int x_batched, const double* y, const double* flux_err,
                 const uint8_t* cadence_mask, const double* prior_mu, const double* prior_sigma,
                 int B, int64_t N, int K, double clip_sigma, int niters,
-                double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out,
+                double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, double* coeff_cov,
                 int mem, void* stream);
 
 /* ---- batched order statistics (K6) ---------------------------------------- */

@@ -42,7 +42,7 @@ SIGNATURES = {
     "lkb_flatten": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_dbl,
                             c_vp, c_vp, c_vp, c_int, c_vp]),
     "lkb_regress": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_dbl, c_int,
-                            c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+                            c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "lkb_savgol_tables": (c_int, [c_int, c_int, c_vp, c_vp]),
     "lkb_nanmedian_std": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
 }

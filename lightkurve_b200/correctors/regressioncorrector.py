@@ -7,6 +7,7 @@ kernels.  ``RegressionCorrector.correct_batch`` is the new collection-level entr
 curves sharing one design matrix, BASELINE config 4) with the same per-light-curve semantics.
 """
 import logging
+import warnings
 
 import numpy as np
 
@@ -73,9 +74,6 @@ class RegressionCorrector:
 
     def correct(self, design_matrix_collection, cadence_mask=None, sigma=5, niters=5, propagate_errors=False):
         """Find the best fit correction for the light curve (regressioncorrector.py:191-309)."""
-        if propagate_errors:
-            raise NotImplementedError("propagate_errors=True (np.linalg.inv + 100 MVN draws, "
-                                      "regressioncorrector.py:185,280-297) is not on the GPU path yet")
         from .. import engine
         dmc = self._as_collection(design_matrix_collection)
         dmc.validate()
@@ -92,18 +90,33 @@ class RegressionCorrector:
         fe_arg = None if np.all(~np.isfinite(fe)) else fe[None, :]          # :157-160
         res = engine.regress(X, np.asarray(self.lc.flux.value, dtype=np.float64)[None, :], fe_arg,
                              self.cadence_mask[None, :], np.asarray(dmc.prior_mu, dtype=np.float64),
-                             np.asarray(dmc.prior_sigma, dtype=np.float64), sigma=sigma, niters=niters)
+                             np.asarray(dmc.prior_sigma, dtype=np.float64), sigma=sigma, niters=niters,
+                             return_cov=bool(propagate_errors))
         if res["status"][0] != 0:
             raise np.linalg.LinAlgError("Singular matrix")
         self.outlier_mask = res["outlier_mask"][0]
         self.coefficients = res["coefficients"][0]
-        self.coefficients_err = np.zeros(len(self.coefficients)) * np.nan
-        self._finish(res["model"][0])
+        model_err = None
+        if propagate_errors:
+            # (X^T W X + prior)^-1 comes from the GPU (np.linalg.inv at :185); the 100 multivariate-normal
+            # draws use numpy's global RNG exactly like the reference (:280-297) so that a seeded run draws
+            # the same stream - RNG bookkeeping, not hot-path arithmetic.
+            self.coefficients_err = res["covariance"][0]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                samples = np.asarray([X.dot(np.random.multivariate_normal(self.coefficients, self.coefficients_err))
+                                      for idx in range(100)]).T
+            model_err = np.abs(np.percentile(samples, [16, 84], axis=1)
+                               - np.median(samples, axis=1)[:, None].T).mean(axis=0)
+        else:
+            self.coefficients_err = np.zeros(len(self.coefficients)) * np.nan
+        self._finish(res["model"][0], model_err)
         return self.corrected_lc
 
-    def _finish(self, model_flux):
+    def _finish(self, model_flux, model_err=None):
         unit = self.lc.flux.unit
-        model_err = np.zeros(len(model_flux))
+        if model_err is None:
+            model_err = np.zeros(len(model_flux))
         self.model_lc = LightCurve(time=self.lc.time, flux=Quantity(model_flux, unit),
                                    flux_err=Quantity(model_err, unit))
         self.corrected_lc = self.lc.copy()

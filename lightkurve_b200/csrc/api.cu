@@ -123,7 +123,7 @@ int bls_bin_index(const double*, int64_t, double, double, double, int32_t*, int,
 int flatten(const double*, const double*, const double*, const uint8_t*, const int64_t*, int, int, int, double, int,
             double, double*, double*, double*, int, cudaStream_t);
 int regress(const double*, int, const double*, const double*, const uint8_t*, const double*, const double*, int,
-            int64_t, int, double, int, double*, double*, uint8_t*, int32_t*, int, cudaStream_t);
+            int64_t, int, double, int, double*, double*, uint8_t*, int32_t*, double*, int, cudaStream_t);
 int nanmedian_std(const double*, const int64_t*, int, double*, double*, int, cudaStream_t);
 int savgol_tables_host(int, int, double*, double*);
 
@@ -233,11 +233,11 @@ int lkb_flatten(const double* time, const double* flux, const double* flux_err, 
 
 int lkb_regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
                 const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma,
-                int niters, double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, int mem,
-                void* stream) {
+                int niters, double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out,
+                double* coeff_cov, int mem, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   return regress(X, x_batched, y, flux_err, cadence_mask, prior_mu, prior_sigma, B, N, K, clip_sigma, niters, coeff,
-                 model, outlier_mask, status_out, mem, (cudaStream_t)stream);
+                 model, outlier_mask, status_out, coeff_cov, mem, (cudaStream_t)stream);
 }
 
 int lkb_savgol_tables(int window_length, int polyorder, double* coeffs, double* edge) {

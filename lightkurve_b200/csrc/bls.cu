@@ -200,9 +200,18 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int64_t o = offsets[b], n = offsets[b + 1] - o;
-  if (n <= 0) return;
   const int nwarps = blockDim.x >> 5;
   const int64_t p = p_begin + (int64_t)blockIdx.x * nwarps + warp;
+  if (n <= 0) {      // empty light curve: every output NaN
+    if (p < p_end && lane == 0) {
+      const double qn = __longlong_as_double(0x7ff8000000000000ll);
+      const int64_t oi = (int64_t)b * P + p;
+      o_power[oi] = qn; o_depth[oi] = qn; o_depth_err[oi] = qn; o_duration[oi] = qn; o_ttime[oi] = qn;
+      o_snr[oi] = qn; o_ll[oi] = qn;
+      if (o_bins) { o_bins[2 * oi] = -1; o_bins[2 * oi + 1] = -1; }
+    }
+    return;
+  }
   const bool active = p < p_end;
   const double per = active ? period[p] : 1.0;
   const double inv_per = 1.0 / fabs(per);

@@ -173,7 +173,12 @@ ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ 
   const int64_t F = freq_offsets ? (freq_offsets[b + 1] - fo) : F_shared;
   const int64_t po_out = freq_offsets ? fo : (int64_t)b * F_shared;
   const int64_t f_blk = (int64_t)blockIdx.x * LS_FPB;
-  if (f_blk >= F || n <= 0) return;
+  if (f_blk >= F) return;
+  if (n <= 0) {      // empty light curve: numpy semantics of an empty mean -> NaN everywhere
+    for (int64_t f = f_blk + threadIdx.x; f < min(F, f_blk + (int64_t)LS_FPB); f += blockDim.x)
+      power[po_out + f] = __int_as_float(0x7fc00000);
+    return;
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t f_base = f_blk + warp * LS_FPW;
@@ -568,9 +573,10 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 }
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
-                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, double lowf_max, double grid_f0, double grid_df, int normalization,
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, float4* d_rot, float2* d_rot2,
+                 bool window_in_kernel, double lowf_max, double grid_f0, double grid_df, int normalization,
                  double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready);   // ls_tc.cu
+bool ls_tc_window_in_kernel(int64_t Npad, bool regular);
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
@@ -648,6 +654,11 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   }
   // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
   const double lowf_max = (h_meta[3] > 0.0) ? LS_LOWF_CYCLES / h_meta[3] : 0.0;
+  bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
+  if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
+    set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
+    return LKB_E_UNSUPPORTED;
+  }
   // The window terms depend only on (t, freq).  They CAN run on the library's side stream, co-resident
   // with the contraction kernel (LKB_LS_OVERLAP_WINDOW=1), but measured on B200 that costs more than it
   // hides (tc kernel 65 -> 73.6 ms: the co-resident MUFU work competes for issue slots and for the power
@@ -658,18 +669,24 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   if (!getenv("LKB_LS_OVERLAP_WINDOW")) aux = st;
   LKB_CUDA_CHECK(cudaEventRecord(ev_fork, st));
   LKB_CUDA_CHECK(cudaStreamWaitEvent(aux, ev_fork, 0));
-  if (d_tab) ls_window_kernel<true><<<(unsigned)((F + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
-  else ls_window_kernel<false><<<(unsigned)((F + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F, d_rot, d_rot2);
+  // With the tcgen05 path on a regular grid the generator warps accumulate the window sums
+  // themselves; only the low-frequency rows (the first few of an ascending regular grid) still need
+  // this kernel's full-fp64 path.
+  const bool win_in_kernel = use_tc && ls_tc_window_in_kernel(Npad, regular);
+  int64_t F_win = F;
+  if (win_in_kernel) {
+    const double nlow = floor((lowf_max - grid_f0) / grid_df) + 2.0;
+    F_win = (nlow < 0.0) ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
+  }
+  if (F_win > 0) {
+    if (d_tab) ls_window_kernel<true><<<(unsigned)((F_win + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F_win, d_rot, d_rot2);
+    else ls_window_kernel<false><<<(unsigned)((F_win + 3) / 4), 128, 0, aux>>>(d_t, d_tab, N, d_freq, F_win, d_rot, d_rot2);
+  }
   LKB_LAUNCH_CHECK();
   LKB_CUDA_CHECK(cudaEventRecord(ev_join, aux));
 
-  bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
-  if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
-    set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
-    return LKB_E_UNSUPPORTED;
-  }
   if (use_tc) {
-    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, lowf_max, grid_f0, grid_df, normalization, ns, d_pow, st, ev_join));
+    LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, win_in_kernel, lowf_max, grid_f0, grid_df, normalization, ns, d_pow, st, ev_join));
   } else {
     static bool attr_set = false;
     if (!attr_set) {

@@ -114,6 +114,8 @@ struct TcParams {
   int normalization;
   float norm_scale;
   int seg_stages, nseg;
+  double* wsum;             // [F, 4 chunks, 4] window sums (S, C, CC, SC) accumulated by the generators of
+                            // the blockIdx.y == 0 CTAs (nullptr: the separate window kernel is used)
   double lowf_max;          // frequencies <= this are "low rows": design matrix carries cos - 1
   double f0, df;            // regular grid (REGULAR kernels)
 };
@@ -231,6 +233,10 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const unsigned long long kfreq = (unsigned long long)(f0 + row);          // global frequency index
     const double fr = REGULAR ? (p.f0 + (double)(f0 + row) * p.df) : ((f0 + row < p.F) ? p.freq[f0 + row] : 0.0);
     const bool low_row = fabs(fr) <= p.lowf_max;
+    // window sums of this (row, chunk): fp32 within a segment, flushed to fp64 at segment ends
+    const bool do_win = (p.wsum != nullptr) && (blockIdx.y == 0);
+    float w_s = 0.f, w_c = 0.f, w_cc = 0.f, w_sc = 0.f;
+    double W_s = 0.0, W_c = 0.0, W_cc = 0.0, W_sc = 0.0;
     ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
     auto prefetch = [&](int it) {
       if (lane < 8) {
@@ -269,7 +275,18 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
             ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
           }
         }
+        if (do_win) {
+          const float rc0 = low_row ? 1.0f + c0 : c0, rc1 = low_row ? 1.0f + c1 : c1;   // low rows carry cos - 1
+          w_s += s0 + s1;
+          w_c += rc0 + rc1;
+          w_cc = fmaf(rc0, rc0, fmaf(rc1, rc1, w_cc));
+          w_sc = fmaf(s0, rc0, fmaf(s1, rc1, w_sc));
+        }
         tc_split2(c0, c1, s0, s1, ch[q], cl[q], sh[q], sl[q]);
+      }
+      if (do_win && (((it + 1) % p.seg_stages) == 0 || it + 1 == nst)) {
+        W_s += (double)w_s; W_c += (double)w_c; W_cc += (double)w_cc; W_sc += (double)w_sc;
+        w_s = w_c = w_cc = w_sc = 0.f;
       }
       *reinterpret_cast<uint4*>(st + row_off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
       *reinterpret_cast<uint4*>(st + TC_A_TILE + row_off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
@@ -278,6 +295,10 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
+    }
+    if (do_win && f0 + row < p.F) {
+      double* o = p.wsum + ((f0 + row) * 4 + chunk) * 4;
+      o[0] = W_s; o[1] = W_c; o[2] = W_cc; o[3] = W_sc;
     }
   } else {
     // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
@@ -329,6 +350,30 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   }
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// rot / rot2 from the window sums accumulated inside ls_tc_kernel (regular grids).  The padding
+// cadences (phase 0: cos = 1, sin = 0) are removed analytically.  Low-frequency rows are NOT
+// written here: ls_window_kernel's full-fp64 path owns them.
+__global__ void ls_tc_rot_kernel(const double* __restrict__ wsum, int64_t F, int64_t N, int64_t Npad,
+                                 const double* __restrict__ freq, double lowf_max, float4* __restrict__ rot,
+                                 float2* __restrict__ rot2) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F || fabs(freq[f]) <= lowf_max) return;
+  LsSums<double> d;
+  d.zero();
+  for (int c = 0; c < 4; ++c) {
+    const double* o = wsum + (f * 4 + c) * 4;
+    d.s += o[0]; d.c += o[1]; d.cc += o[2]; d.sc += o[3];
+  }
+  const double pad = (double)(Npad - N);
+  d.c -= pad;
+  d.cc -= pad;
+  double ct, st, cc, ss;
+  ls_rotation(d, (double)N, ct, st, cc, ss);
+  const double k = 1.0 / (2.0 * (double)N);
+  rot[f] = make_float4((float)ct, (float)st, (float)(k / cc), (float)(k / ss));
+  rot2[f] = make_float2((float)((d.c * ct + d.s * st) / (double)N), (float)((d.s * ct - d.c * st) / (double)N));
 }
 
 // sum the split-K partials (round-to-nearest fp32 adds), undo the operand scaling, apply the epilogue
@@ -385,10 +430,21 @@ bool ls_tc_supported(int B, int64_t N, int64_t F) {
   return B >= 64 && N >= 256 && F >= 128;
 }
 
+bool ls_tc_window_in_kernel(int64_t Npad, bool regular) {
+  // the generators can accumulate the window sums themselves when the epilogue is deferred to the
+  // finish kernel (more than one segment) and the phases come from the fixed-point table
+  int seg_cap = TC_SEG_STAGES;
+  if (const char* e = getenv("LKB_TC_SEG_STAGES")) { const int v = atoi(e); if (v > 0) seg_cap = v; }
+  // Measured on B200 (bench c2): folding the sums in costs the tc kernel more (65 -> 71 ms: the
+  // generator warps are already the co-bottleneck) than the separate 4.4 ms window kernel, so this
+  // is opt-in.
+  return regular && (Npad / TC_BK) > seg_cap && getenv("LKB_TC_WINDOW_IN_KERNEL") != nullptr;
+}
+
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
-                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
-                 const float2* d_rot2, double lowf_max, double grid_f0, double grid_df, int normalization,
-                 double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready) {
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, float4* d_rot,
+                 float2* d_rot2, bool window_in_kernel, double lowf_max, double grid_f0, double grid_df,
+                 int normalization, double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
@@ -430,6 +486,8 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
   p.lowf_max = lowf_max; p.f0 = grid_f0; p.df = grid_df;
+  p.wsum = nullptr;
+  if (window_in_kernel && nseg > 1 && regular) LKB_TRY(ws_get_t<double>(WS_P, (size_t)F * 16, &p.wsum));
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   if (nseg == 1) LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));   // direct epilogue needs rot
   prof_begin(st);
@@ -437,6 +495,10 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   else ls_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
   prof_end(st);
   LKB_LAUNCH_CHECK();
+  if (p.wsum) {
+    ls_tc_rot_kernel<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(p.wsum, F, N, Npad, d_freq, lowf_max, d_rot, d_rot2);
+    LKB_LAUNCH_CHECK();
+  }
   if (nseg > 1) {
     LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));
     ls_tc_finish_kernel<<<dim3((unsigned)((F + 255) / 256), (unsigned)B), 256, 0, st>>>(

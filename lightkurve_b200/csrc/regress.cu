@@ -284,6 +284,90 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
   if (threadIdx.x == 0 && status) status[b] = LKB_OK;
 }
 
+// ---- (A + prior)^-1 for propagate_errors (np.linalg.inv at regressioncorrector.py:185) -----------
+// Gauss-Jordan with partial pivoting on [M | I] held in an L2-resident global workspace [K][2K].
+__global__ void __launch_bounds__(256)
+rg_inverse_kernel(int K, const double* __restrict__ prior_sigma, RgWs ws, double* __restrict__ work,
+                  double* __restrict__ cov, const int32_t* __restrict__ status) {
+  __shared__ double s_red[8];
+  __shared__ int s_redi[8];
+  __shared__ int s_piv;
+  const int b = blockIdx.x;
+  const int Ka = K + 1, W = 2 * K;
+  double* out = cov + (int64_t)b * K * K;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (status && status[b] != LKB_OK) {
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) out[e] = qnan;
+    return;
+  }
+  const double* G = ws.gram + (int64_t)b * Ka * Ka;
+  double* M = work + (int64_t)b * K * W;
+  for (int e = threadIdx.x; e < K * W; e += blockDim.x) {
+    const int i = e / W, j = e % W;
+    double v;
+    if (j < K) {
+      v = (j >= i) ? G[(int64_t)i * Ka + j] : G[(int64_t)j * Ka + i];
+      if (prior_sigma && j == i) { const double ps = prior_sigma[i]; v += 1.0 / (ps * ps); }
+    } else {
+      v = (j - K == i) ? 1.0 : 0.0;
+    }
+    M[e] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  bool singular = false;
+  for (int c = 0; c < K; ++c) {
+    double best = -1.0;
+    int bi = c;
+    for (int r = c + threadIdx.x; r < K; r += blockDim.x) {
+      const double v = fabs(M[(int64_t)r * W + c]);
+      if (v > best) { best = v; bi = r; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_red[warp] = best; s_redi[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bb = s_red[0];
+      int ii = s_redi[0];
+      for (int w = 1; w < nw; ++w)
+        if (s_red[w] > bb || (s_red[w] == bb && s_redi[w] < ii)) { bb = s_red[w]; ii = s_redi[w]; }
+      s_piv = (bb > 0.0) ? ii : -1;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv < 0) { singular = true; break; }
+    if (piv != c)
+      for (int k = threadIdx.x; k < W; k += blockDim.x) {
+        const double tmp = M[(int64_t)c * W + k];
+        M[(int64_t)c * W + k] = M[(int64_t)piv * W + k];
+        M[(int64_t)piv * W + k] = tmp;
+      }
+    __syncthreads();
+    const double inv = 1.0 / M[(int64_t)c * W + c];
+    __syncthreads();
+    for (int k = threadIdx.x; k < W; k += blockDim.x) M[(int64_t)c * W + k] *= inv;
+    __syncthreads();
+    for (int r = warp; r < K; r += nw) {
+      if (r == c) continue;
+      const double fct = M[(int64_t)r * W + c];
+      __syncwarp();
+      if (fct != 0.0)
+        for (int k = lane; k < W; k += 32) M[(int64_t)r * W + k] = fma(-fct, M[(int64_t)c * W + k], M[(int64_t)r * W + k]);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+    const int i = e / K, j = e % K;
+    out[e] = singular ? qnan : M[(int64_t)i * W + K + j];
+  }
+}
+
 // ---- model + sigma clip ---------------------------------------------------------------------------
 __device__ __forceinline__ void rg_model_rows(const double* X, int x_batched, int b, int64_t N, int K,
                                               const double* s_w, double* out) {
@@ -361,7 +445,8 @@ __global__ void rg_zero_kernel(double* p, int64_t n, uint8_t* q, int64_t nq) {
 
 int regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
             const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma, int niters,
-            double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, int mem, cudaStream_t st) {
+            double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, double* coeff_cov, int mem,
+            cudaStream_t st) {
   LKB_REQUIRE(X && y && coeff && model && outlier_mask, "lkb_regress: null argument");
   LKB_REQUIRE(B > 0 && B <= 65535 && N > 0 && K > 0 && niters >= 1, "lkb_regress: bad sizes");
   LKB_REQUIRE((prior_mu == nullptr) == (prior_sigma == nullptr), "Please specify both `prior_mu` and `prior_sigma`");
@@ -394,6 +479,10 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
   LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, model, BN, &o_m));
   LKB_TRY(stage_out_alloc<uint8_t>(mem, WS_OUT2, outlier_mask, BN, &o_om));
   LKB_TRY(stage_out_alloc<int32_t>(mem, WS_OUT3, status_out, B, &o_st));
+  double* o_cov = nullptr;
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT4, coeff_cov, (size_t)B * K * K, &o_cov));
+  int32_t* d_status = o_st;
+  if (coeff_cov && !d_status) LKB_TRY(ws_get_t<int32_t>(WS_G, B, &d_status));
 
   {
     const int64_t ng = (int64_t)B * Ka * Ka, nz = ng > (int64_t)BN ? ng : (int64_t)BN;
@@ -422,18 +511,27 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
                                                                          it == 0 ? 1.0 : -1.0, ws);
     if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
-    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, o_st);
+    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status);
     LKB_LAUNCH_CHECK();
     rg_clip_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om);
     LKB_LAUNCH_CHECK();
   }
   rg_final_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, N, K, o_c, o_m);
   LKB_LAUNCH_CHECK();
+  if (coeff_cov) {
+    // covariance of the LAST fit (the Gram matrix in the workspace already excludes every clipped row
+    // but the ones found by the final clip, exactly like the reference's last _fit_coefficients call)
+    double* d_work = nullptr;
+    LKB_TRY(ws_get_t<double>(WS_F, (size_t)B * K * 2 * K, &d_work));
+    rg_inverse_kernel<<<B, 256, 0, st>>>(K, d_ps, ws, d_work, o_cov, d_status);
+    LKB_LAUNCH_CHECK();
+  }
 
   LKB_TRY(stage_out_copy<double>(mem, coeff, o_c, (size_t)B * K, st));
   LKB_TRY(stage_out_copy<double>(mem, model, o_m, BN, st));
   LKB_TRY(stage_out_copy<uint8_t>(mem, outlier_mask, o_om, BN, st));
   LKB_TRY(stage_out_copy<int32_t>(mem, status_out, o_st, B, st));
+  LKB_TRY(stage_out_copy<double>(mem, coeff_cov, o_cov, (size_t)B * K * K, st));
   if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
   return LKB_OK;
 }

@@ -224,7 +224,8 @@ def flatten(times, fluxes, flux_errs=None, masks=None, window_length=101, polyor
 # --------------------------------------------------------------------------------------
 # regression
 # --------------------------------------------------------------------------------------
-def regress(X, Y, flux_err=None, cadence_mask=None, prior_mu=None, prior_sigma=None, sigma=5, niters=5):
+def regress(X, Y, flux_err=None, cadence_mask=None, prior_mu=None, prior_sigma=None, sigma=5, niters=5,
+            return_cov=False):
     """K5.  X [N, K] (shared) or [B, N, K]; Y [B, N]; flux_err [B, N] or None (ones);
     cadence_mask bool [B, N] or None.  Returns dict(coefficients [B,K], model [B,N]
     (median-subtracted), outlier_mask bool [B,N], status int32 [B])."""
@@ -245,10 +246,14 @@ def regress(X, Y, flux_err=None, cadence_mask=None, prior_mu=None, prior_sigma=N
     model = np.empty((B, N), dtype=np.float64)
     om = np.empty((B, N), dtype=np.uint8)
     status = np.empty(B, dtype=np.int32)
+    cov = np.empty((B, K, K), dtype=np.float64) if return_cov else None
     L.check(lib.lkb_regress(L.ptr(X), 1 if batched else 0, L.ptr(Y), L.ptr(fe), L.ptr(cm), L.ptr(pm), L.ptr(ps),
                             B, N, K, float(sigma), int(niters), L.ptr(coeff), L.ptr(model), L.ptr(om),
-                            L.ptr(status), L.MEM_HOST, None))
-    return dict(coefficients=coeff, model=model, outlier_mask=om.astype(bool), status=status)
+                            L.ptr(status), L.ptr(cov), L.MEM_HOST, None))
+    out = dict(coefficients=coeff, model=model, outlier_mask=om.astype(bool), status=status)
+    if return_cov:
+        out["covariance"] = cov
+    return out
 
 
 def nanmedian_std(arrays):

@@ -88,6 +88,22 @@ def test_ls_very_low_frequencies(engine):
             np.testing.assert_allclose(out[b], ref, rtol=2e-4, atol=1e-5 * ref.max(), err_msg=algo)
 
 
+def test_edge_cases_empty_and_tiny_light_curves(engine):
+    freq = np.linspace(0.1, 1.0, 40)
+    t2, y2 = np.array([0.0, 1.0]), np.array([1.0, 2.0])
+    out = engine.ls_power_ragged([np.zeros(0), t2, np.arange(7.0)], [np.zeros(0), y2, np.arange(7.0) ** 2], freq, "psd_raw")
+    assert np.isnan(out[0]).all()                                   # empty light curve
+    ref = ols.ls_slow_psd(np.arange(7.0), np.arange(7.0) ** 2, freq)
+    np.testing.assert_allclose(out[2], ref, rtol=2e-4, atol=1e-5 * ref.max())
+    assert out[1].shape == freq.shape                               # 2 points: degenerate (0/0 bins), must not crash
+    one = engine.ls_power_ragged([np.arange(50.0)], [np.sin(np.arange(50.0))], np.array([0.05]), "amplitude")
+    assert one.shape == (1, 1) and np.isfinite(one).all()           # a single frequency bin
+    res = engine.bls_power([np.zeros(0), np.arange(0, 30, 0.1)], [np.zeros(0), np.ones(300)], None, [1.0, 2.0], [0.2])
+    assert np.isnan(res["power"][0]).all() and np.isfinite(res["power"][1]).all()
+    med, sd = engine.nanmedian_std([np.array([np.nan, np.nan]), np.array([3.0])])
+    assert np.isnan(med[0]) and np.isnan(sd[0]) and med[1] == 3.0 and sd[1] == 0.0
+
+
 def test_ls_constant_flux_is_exactly_zero(engine):
     """reference tests/test_periodogram.py:445-457 (masked NaN -> [1,1,1] must give power == 0)."""
     t = np.array([1.0, 3.0, 4.0])

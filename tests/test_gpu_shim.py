@@ -306,6 +306,31 @@ def test_sinusoid_noise():
     assert_almost_equal(corrected_lc.normalize().flux.value, true_lc.flux.value)
 
 
+def test_propagate_errors_covariance_and_band():
+    """regressioncorrector.py:185,280-297: coefficients_err = inv(X^T W X + prior), model error band."""
+    rng = np.random.default_rng(12)
+    N, K = 600, 5
+    X = np.hstack([rng.normal(size=(N, K - 1)), np.ones((N, 1))])
+    fe = np.full(N, 2e-3)
+    y = 1 + X @ np.array([1e-2, -2e-2, 5e-3, 0.0, 0.0]) + fe * rng.normal(size=N)
+    lc = LightCurve(time=np.arange(N) * 0.02, flux=y, flux_err=fe)
+    dm = DesignMatrix(X, prior_mu=np.zeros(K), prior_sigma=np.array([1.0, 1.0, np.inf, np.inf, np.inf]))
+    rc = RegressionCorrector(lc)
+    np.random.seed(5)
+    corrected = rc.correct(dm, propagate_errors=True)
+    used = ~rc.outlier_mask
+    A = X[used].T @ (X[used] / fe[used, None] ** 2) + np.diag(1.0 / dm.prior_sigma ** 2)
+    np.testing.assert_allclose(rc.coefficients_err, np.linalg.inv(A), rtol=1e-8, atol=1e-14)
+    assert rc.model_lc.flux_err.value.shape == (N,) and (rc.model_lc.flux_err.value > 0).all()
+    # same RNG stream as the reference's host code
+    np.random.seed(5)
+    samples = np.asarray([X.dot(np.random.multivariate_normal(rc.coefficients, rc.coefficients_err))
+                          for _ in range(100)]).T
+    band = np.abs(np.percentile(samples, [16, 84], axis=1) - np.median(samples, axis=1)[:, None].T).mean(axis=0)
+    np.testing.assert_allclose(rc.model_lc.flux_err.value, band, rtol=1e-12)
+    np.testing.assert_allclose(corrected.flux_err.value, np.hypot(fe, band), rtol=1e-12)
+
+
 def test_singular_matrix_raises_linalgerror():
     lc = LightCurve(flux=np.arange(50.0) + 1)
     with pytest.raises(np.linalg.LinAlgError):
