@@ -88,6 +88,18 @@ int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* off
                  int normalization, const double* norm_scale,
                  float* power, int mem, void* stream);
 
+/* K1n: multi-term ("chi2") periodogram = LombScargle(time, flux, nterms=n, normalization="psd")
+ * .power(frequency, method="chi2"|"fastchi2"), the call lightkurve makes for nterms > 1
+ * (periodogram.py:948-964): P = 0.5 XTy^T (XTX)^-1 XTy with X = [1, sin(k w t), cos(k w t)], k <= n.
+ * Same ragged layout as lkb_ls_power; nterms in [1, 4].  theta (nullable) receives the
+ * 2n+1 fitted parameters per (light curve, frequency) [same order as power, (2n+1) doubles each]:
+ * the maximum-likelihood model LombScargle.model evaluates (periodogram.py:1010), for times
+ * measured from the light curve's first cadence and flux centred on its mean. */
+int lkb_ls_power_chi2(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B,
+                      const double* freq, const int64_t* freq_offsets, int64_t F, int nterms,
+                      int normalization, const double* norm_scale, float* power, double* theta,
+                      int mem, void* stream);
+
 /* K2: batch sharing ONE cadence grid (BASELINE config 2); same math, but the
  * sin/cos design matrix is synthesised once per (frequency, cadence) tile and
  * contracted against all B light curves.

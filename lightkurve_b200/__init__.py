@@ -8,7 +8,7 @@ CUDA kernels behind a C ABI (``include/lkb200.h``), with a thin mirror of the re
 from . import engine  # noqa: F401
 from .utils import LightkurveWarning, validate_method  # noqa: F401
 from . import units  # noqa: F401
-from .lightcurve import LightCurve  # noqa: F401
+from .lightcurve import LightCurve, FoldedLightCurve  # noqa: F401
 from .collections import LightCurveCollection  # noqa: F401
 from .periodogram import Periodogram, LombScarglePeriodogram, BoxLeastSquaresPeriodogram  # noqa: F401
 from . import correctors  # noqa: F401

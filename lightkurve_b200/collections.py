@@ -88,7 +88,12 @@ class LightCurveCollection(Collection):
         scales = [LombScarglePeriodogram._norm_args(p)[1] for p in preps]
         shared_t = all(len(p["time"]) == len(p0["time"]) and np.array_equal(p["time"], p0["time"]) for p in preps)
         shared_f = all(len(f) == len(freqs[0]) and np.array_equal(f, freqs[0]) for f in freqs)
-        if shared_t and shared_f and len(preps) > 1:
+        if p0["ls_method"] in ("chi2", "fastchi2"):
+            fl = [np.asarray(p["lc"].flux.value) for p in preps]
+            fl = [f if f.dtype == np.float32 else f.astype(np.float64) for f in fl]
+            powers = engine.ls_power_chi2([p["time"] for p in preps], fl, freqs[0] if shared_f else freqs,
+                                          p0["nterms"], norm, None if norm != "psd" else scales)
+        elif shared_t and shared_f and len(preps) > 1:
             Y = np.stack([np.asarray(p["lc"].flux.value) for p in preps])
             if Y.dtype != np.float32:
                 Y = Y.astype(np.float64)

@@ -35,7 +35,8 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
                       const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
                       double* __restrict__ t_out, float* __restrict__ y_out, double* __restrict__ tspan,
                       const double* __restrict__ grid_f0, const double* __restrict__ grid_df,
-                      ulonglong2* __restrict__ tab_out, double* __restrict__ ysum) {
+                      ulonglong2* __restrict__ tab_out, double* __restrict__ ysum,
+                      double* __restrict__ y_out64 = nullptr) {
   __shared__ double red[33];
   __shared__ int s_const;
   __shared__ double s_span[8];
@@ -63,9 +64,15 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
       const double tr = t[o + i] - t0;
       span = fmax(span, fabs(tr));
       t_out[po + i] = tr;
-      const float yv = cst ? 0.0f : (float)((double)y[o + i] - mean);
-      y_out[po + i] = yv;
-      resid += (double)yv;
+      const double yd = cst ? 0.0 : ((double)y[o + i] - mean);
+      const float yv = (float)yd;
+      if (y_out64) {              // chi2 / model path keeps the centred flux in fp64
+        y_out64[po + i] = yd;
+        resid += yd;
+      } else {
+        y_out[po + i] = yv;
+        resid += (double)yv;
+      }
       if (tab_out) {      // fixed-point phase table of this light curve's regular grid (ls_common.cuh)
         const double x = grid_f0[b] * tr, z = grid_df[b] * tr;
         e.x = __double2ull_rd((x - floor(x)) * 18446744073709551616.0);
@@ -73,7 +80,8 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
       }
     } else {
       t_out[po + i] = 0.0;
-      y_out[po + i] = 0.0f;
+      if (y_out64) y_out64[po + i] = 0.0;
+      else y_out[po + i] = 0.0f;
     }
     if (tab_out) tab_out[po + i] = e;
   }
@@ -451,6 +459,170 @@ ls_shared_simt_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, con
 }
 
 // =====================================================================================
+// K1n: multi-term ("chi2") periodogram - astropy lombscargle_chi2 / fastchi2 as lightkurve calls it for
+// nterms > 1 (/root/reference/src/lightkurve/periodogram.py:948-964):
+//   P = 0.5 * XTy^T (XTX)^-1 XTy,  X = [1, sin(w t), cos(w t), ..., sin(n w t), cos(n w t)].
+// Same staging as K1; per frequency the warp accumulates the harmonic trig sums S_j, C_j (j <= 2n,
+// they give XTX through product-to-sum identities) and YS_j, YC_j (j <= n); the harmonics come
+// from the angle-addition recurrence, the (2n+1)x(2n+1) solve runs in fp64 on lane 0.
+// Optionally returns the fitted parameters theta (LombScargle.model, periodogram.py:1010).
+// =====================================================================================
+template <int NT>
+struct Chi2Sums {
+  double S[2 * NT], C[2 * NT], YS[NT], YC[NT];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int j = 0; j < 2 * NT; ++j) { S[j] = 0.0; C[j] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { YS[j] = 0.0; YC[j] = 0.0; }
+  }
+};
+
+template <int NT>
+__device__ void chi2_solve(const Chi2Sums<NT>& d, double N, double ysum, double& power, double* theta) {
+  constexpr int M = 2 * NT + 1;
+  double A[M][M + 1];
+  auto Cd = [&](int m) { return m == 0 ? N : d.C[m - 1]; };
+  auto Sd = [&](int m) { return m == 0 ? 0.0 : (m > 0 ? d.S[m - 1] : -d.S[-m - 1]); };
+  A[0][0] = N;
+  A[0][M] = ysum;
+  for (int i = 1; i <= NT; ++i) {
+    const int si = 2 * i - 1, ci = 2 * i;
+    A[0][si] = A[si][0] = d.S[i - 1];
+    A[0][ci] = A[ci][0] = d.C[i - 1];
+    A[si][M] = d.YS[i - 1];
+    A[ci][M] = d.YC[i - 1];
+    for (int j = 1; j <= NT; ++j) {
+      const int sj = 2 * j - 1, cj = 2 * j;
+      const int dm = i > j ? i - j : j - i;
+      A[si][sj] = 0.5 * (Cd(dm) - Cd(i + j));
+      A[ci][cj] = 0.5 * (Cd(dm) + Cd(i + j));
+      A[si][cj] = 0.5 * (Sd(i + j) + Sd(i - j));
+      A[cj][si] = A[si][cj];
+    }
+  }
+  double rhs[M];
+  for (int i = 0; i < M; ++i) rhs[i] = A[i][M];
+  bool ok = true;
+  for (int c = 0; c < M && ok; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < M; ++r)
+      if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    if (!(fabs(A[piv][c]) > 0.0)) { ok = false; break; }
+    if (piv != c)
+      for (int k = 0; k <= M; ++k) { const double tmp = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = tmp; }
+    for (int r = c + 1; r < M; ++r) {
+      const double fct = A[r][c] / A[c][c];
+      for (int k = c; k <= M; ++k) A[r][k] -= fct * A[c][k];
+    }
+  }
+  double th[M];
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (ok) {
+    for (int c = M - 1; c >= 0; --c) {
+      double v = A[c][M];
+      for (int k = c + 1; k < M; ++k) v -= A[c][k] * th[k];
+      th[c] = v / A[c][c];
+    }
+    double acc = 0.0;
+    for (int i = 0; i < M; ++i) acc += rhs[i] * th[i];
+    power = 0.5 * acc;
+  } else {
+    power = qnan;
+    for (int i = 0; i < M; ++i) th[i] = qnan;
+  }
+  if (theta)
+    for (int i = 0; i < M; ++i) theta[i] = th[i];
+}
+
+template <int NT>
+__global__ void __launch_bounds__(LS_WARPS * 32)
+ls_chi2_kernel(const double* __restrict__ tws, const double* __restrict__ yws, const int64_t* __restrict__ offsets,
+               const int64_t* __restrict__ poffsets, const double* __restrict__ freq,
+               const int64_t* __restrict__ freq_offsets, int64_t F_shared, const double* __restrict__ ysum,
+               int normalization, const double* __restrict__ norm_scale, float* __restrict__ power,
+               double* __restrict__ theta_out) {
+  constexpr int TN = 1024;
+  __shared__ __align__(16) double s_t[2][TN];
+  __shared__ __align__(16) double s_y[2][TN];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int b = blockIdx.y;
+  const int64_t n = offsets[b + 1] - offsets[b];
+  const int64_t po = poffsets[b], np_ = poffsets[b + 1] - po;
+  const int64_t fo = freq_offsets ? freq_offsets[b] : 0;
+  const int64_t F = freq_offsets ? (freq_offsets[b + 1] - fo) : F_shared;
+  const int64_t po_out = freq_offsets ? fo : (int64_t)b * F_shared;
+  const int64_t f_blk = (int64_t)blockIdx.x * LS_WARPS;           // one frequency per warp
+  if (f_blk >= F) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t fi = f_blk + warp;
+  const bool f_ok = fi < F;
+  if (n <= 0) {
+    if (f_ok && lane == 0) power[po_out + fi] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const double fr = f_ok ? freq[fo + fi] : 0.0;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&s_bar[0], 1);
+    ptx::mbar_init(&s_bar[1], 1);
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+  const int ntiles = (int)((np_ + TN - 1) / TN);
+  auto issue = [&](int tile) {
+    const int buf = tile & 1;
+    const int64_t c0 = (int64_t)tile * TN;
+    const uint32_t cnt = (uint32_t)min((int64_t)TN, np_ - c0);
+    ptx::mbar_arrive_expect_tx(&s_bar[buf], cnt * 16u);
+    ptx::bulk_g2s(&s_t[buf][0], tws + po + c0, cnt * 8u, &s_bar[buf]);
+    ptx::bulk_g2s(&s_y[buf][0], yws + po + c0, cnt * 8u, &s_bar[buf]);
+  };
+  if (threadIdx.x == 0) issue(0);
+
+  Chi2Sums<NT> d;
+  d.zero();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (threadIdx.x == 0 && tile + 1 < ntiles) {
+      ptx::fence_proxy_async_smem();
+      issue(tile + 1);
+    }
+    ptx::mbar_wait(&s_bar[buf], (tile >> 1) & 1);
+    const int64_t c0 = (int64_t)tile * TN;
+    const int cnt = (int)min((int64_t)TN, n - c0);
+    // fp64 throughout: this path is not the throughput path, and the normal equations of a
+    // multi-harmonic fit are far less forgiving than the single-term closed form
+    for (int i = lane; i < cnt; i += 32) {
+      const double yy = s_y[buf][i];
+      double s1, c1;
+      ls_sincos_cycles_f64(fr * s_t[buf][i], s1, c1);
+      double sj = s1, cj = c1;
+#pragma unroll
+      for (int j = 0; j < 2 * NT; ++j) {
+        d.S[j] += sj;
+        d.C[j] += cj;
+        if (j < NT) { d.YS[j] = fma(yy, sj, d.YS[j]); d.YC[j] = fma(yy, cj, d.YC[j]); }
+        const double sn = fma(sj, c1, cj * s1), cn = fma(cj, c1, -sj * s1);
+        sj = sn;
+        cj = cn;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * NT; ++j) { d.S[j] = warp_sum(d.S[j]); d.C[j] = warp_sum(d.C[j]); }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { d.YS[j] = warp_sum(d.YS[j]); d.YC[j] = warp_sum(d.YC[j]); }
+  if (lane == 0 && f_ok) {
+    double p;
+    chi2_solve<NT>(d, (double)n, ysum[b], p, theta_out ? theta_out + (po_out + fi) * (2 * NT + 1) : nullptr);
+    power[po_out + fi] = ls_normalize(p, (double)n, normalization, norm_scale ? norm_scale[b] : 1.0);
+  }
+}
+
+// =====================================================================================
 // Host launchers
 // =====================================================================================
 int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* h_offsets, int B,
@@ -568,6 +740,84 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
   prof_end(st);
   LKB_LAUNCH_CHECK();
   LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
+  if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return LKB_OK;
+}
+
+int ls_power_chi2(const double* t, const void* y, int y_dtype, const int64_t* h_offsets, int B, const double* freq,
+                  const int64_t* h_freq_offsets, int64_t F, int nterms, int normalization, const double* norm_scale,
+                  float* power, double* theta, int mem, cudaStream_t st) {
+  LKB_REQUIRE(B > 0 && B <= 65535 && t && y && h_offsets && freq && power, "lkb_ls_power_chi2: null/bad argument");
+  LKB_REQUIRE(y_dtype == LKB_DTYPE_F32 || y_dtype == LKB_DTYPE_F64, "lkb_ls_power_chi2: bad y_dtype");
+  LKB_REQUIRE(nterms >= 1 && nterms <= 4, "lkb_ls_power_chi2: nterms must be in [1, 4]");
+  LKB_REQUIRE(normalization >= 0 && normalization <= 2, "lkb_ls_power_chi2: bad normalization");
+  LKB_REQUIRE(normalization != LKB_LS_NORM_PSD_SCALE || norm_scale, "lkb_ls_power_chi2: norm_scale required");
+  LKB_TRY(ensure_device());
+  const int64_t total = h_offsets[B];
+  std::vector<int64_t> h_po(B + 1, 0);
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = h_offsets[b + 1] - h_offsets[b];
+    LKB_REQUIRE(n >= 0, "lkb_ls_power_chi2: offsets not monotone");
+    h_po[b + 1] = h_po[b] + ((n + 3) / 4) * 4;
+  }
+  int64_t Fmax = F, Ftot = F;
+  if (h_freq_offsets) {
+    Fmax = 0;
+    for (int b = 0; b < B; ++b) Fmax = max(Fmax, h_freq_offsets[b + 1] - h_freq_offsets[b]);
+    Ftot = h_freq_offsets[B];
+  }
+  const int64_t ptotal = h_po[B];
+  const size_t ysz = (y_dtype == LKB_DTYPE_F32) ? 4 : 8;
+  const int M = 2 * nterms + 1;
+  int64_t *d_off = nullptr, *d_po = nullptr, *d_fo = nullptr;
+  double *d_t = nullptr, *d_span = nullptr, *d_ysum = nullptr;
+  double* d_y = nullptr;
+  LKB_TRY(ws_get_t<int64_t>(WS_A, B + 1, &d_off));
+  LKB_TRY(ws_get_t<int64_t>(WS_B, B + 1, &d_po));
+  if (h_freq_offsets) LKB_TRY(ws_get_t<int64_t>(WS_C, B + 1, &d_fo));
+  LKB_TRY(ws_get_t<double>(WS_D, ptotal + 4, &d_t));
+  LKB_TRY(ws_get_t<double>(WS_E, ptotal + 4, &d_y));
+  LKB_TRY(ws_get_t<double>(WS_F, B, &d_span));
+  LKB_TRY(ws_get_t<double>(WS_J, B, &d_ysum));
+  LKB_CUDA_CHECK(cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  LKB_CUDA_CHECK(cudaMemcpyAsync(d_po, h_po.data(), sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  if (h_freq_offsets)
+    LKB_CUDA_CHECK(cudaMemcpyAsync(d_fo, h_freq_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  const double *dt_in = nullptr, *d_freq = nullptr, *d_ns = nullptr;
+  const void* dy_in = nullptr;
+  LKB_TRY(stage_in<double>(mem, WS_IN0, t, total, &dt_in, st));
+  {
+    const unsigned char* tmp = nullptr;
+    LKB_TRY(stage_in<unsigned char>(mem, WS_IN1, (const unsigned char*)y, total * ysz, &tmp, st));
+    dy_in = tmp;
+  }
+  LKB_TRY(stage_in<double>(mem, WS_IN2, freq, Ftot, &d_freq, st));
+  LKB_TRY(stage_in<double>(mem, WS_IN3, norm_scale, B, &d_ns, st));
+  const int64_t out_count = h_freq_offsets ? Ftot : (int64_t)B * F;
+  float* d_pow = nullptr;
+  double* d_theta = nullptr;
+  LKB_TRY(stage_out_alloc<float>(mem, WS_OUT0, power, out_count, &d_pow));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, theta, out_count * M, &d_theta));
+  if (y_dtype == LKB_DTYPE_F32)
+    ls_prep_ragged_kernel<float><<<B, 256, 0, st>>>(dt_in, (const float*)dy_in, d_off, d_po, d_t, nullptr, d_span,
+                                                    nullptr, nullptr, nullptr, d_ysum, d_y);
+  else
+    ls_prep_ragged_kernel<double><<<B, 256, 0, st>>>(dt_in, (const double*)dy_in, d_off, d_po, d_t, nullptr, d_span,
+                                                     nullptr, nullptr, nullptr, d_ysum, d_y);
+  LKB_LAUNCH_CHECK();
+  dim3 grid((unsigned)((Fmax + LS_WARPS - 1) / LS_WARPS), (unsigned)B);
+  prof_begin(st);
+  switch (nterms) {
+    case 1: ls_chi2_kernel<1><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, d_ysum, normalization, d_ns, d_pow, d_theta); break;
+    case 2: ls_chi2_kernel<2><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, d_ysum, normalization, d_ns, d_pow, d_theta); break;
+    case 3: ls_chi2_kernel<3><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, d_ysum, normalization, d_ns, d_pow, d_theta); break;
+    default: ls_chi2_kernel<4><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_y, d_off, d_po, d_freq, d_fo, F, d_ysum, normalization, d_ns, d_pow, d_theta); break;
+  }
+  prof_end(st);
+  LKB_LAUNCH_CHECK();
+  LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
+  LKB_TRY(stage_out_copy<double>(mem, theta, d_theta, out_count * M, st));
   if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
   return LKB_OK;
 }

@@ -110,6 +110,44 @@ def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_sc
     return out
 
 
+def ls_power_chi2(times, fluxes, frequency, nterms=1, normalization="amplitude", norm_scale=None,
+                  return_theta=False):
+    """K1n.  Multi-term periodogram (astropy method="chi2"/"fastchi2", nterms in [1, 4]); same
+    arguments as ls_power_ragged.  With return_theta also returns the 2*nterms+1 fitted parameters
+    per (light curve, frequency): [offset, sin 1, cos 1, sin 2, cos 2, ...]."""
+    lib = L.load()
+    B = len(times)
+    if B == 0:
+        return []
+    t, offsets = _csr(times)
+    ydt = np.float32 if all(np.asarray(f).dtype == np.float32 for f in fluxes) else np.float64
+    y, yoff = _csr(fluxes, ydt)
+    if not np.array_equal(offsets, yoff):
+        raise ValueError("time and flux lengths differ")
+    M = 2 * int(nterms) + 1
+    per_lc = isinstance(frequency, (list, tuple))
+    if per_lc:
+        freq, foff = _csr(frequency)
+        F = 0
+        out = np.empty(int(foff[-1]), dtype=np.float32)
+        theta = np.empty((int(foff[-1]), M), dtype=np.float64) if return_theta else None
+    else:
+        freq = np.ascontiguousarray(frequency, dtype=np.float64)
+        foff = None
+        F = len(freq)
+        out = np.empty((B, F), dtype=np.float32)
+        theta = np.empty((B, F, M), dtype=np.float64) if return_theta else None
+    ns = None if norm_scale is None else np.ascontiguousarray(np.broadcast_to(norm_scale, (B,)), dtype=np.float64)
+    L.check(lib.lkb_ls_power_chi2(L.ptr(t), L.ptr(y), _y_dtype_code(ydt), L.ptr(offsets), B, L.ptr(freq), L.ptr(foff),
+                                  F, int(nterms), _NORMS[normalization], L.ptr(ns), L.ptr(out), L.ptr(theta),
+                                  L.MEM_HOST, None))
+    if per_lc:
+        out = [out[foff[b]:foff[b + 1]] for b in range(B)]
+        if return_theta:
+            theta = [theta[foff[b]:foff[b + 1]] for b in range(B)]
+    return (out, theta) if return_theta else out
+
+
 def ls_power_shared(t, Y, frequency, normalization="amplitude", norm_scale=None, algo="auto", out=None):
     """K2.  One cadence grid `t` [N] shared by the batch `Y` [B, N]; `frequency` [F].
     numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode)."""

@@ -21,7 +21,7 @@ from .utils import LightkurveWarning, validate_method, running_mean
 
 log = logging.getLogger(__name__)
 
-__all__ = ["LightCurve"]
+__all__ = ["LightCurve", "FoldedLightCurve"]
 
 
 def _as_flux_quantity(x, unit=None):
@@ -317,6 +317,56 @@ class LightCurve:
         from .correctors import RegressionCorrector
         return RegressionCorrector(self, **kwargs)
 
+    # ------------------------------------------------------------------ fold (the step after a period search)
+    def fold(self, period=None, epoch_time=None, epoch_phase=0, wrap_phase=None, normalize_phase=False):
+        """Returns a `FoldedLightCurve` folded on a period and epoch (lightcurve.py:1089-1214, which wraps
+        astropy TimeSeries.fold): phase = ((t - epoch_time) + epoch_phase + (P - wrap)) % P - (P - wrap),
+        sorted by phase; a bare float period / epoch_phase is in days."""
+        if period is None:
+            raise ValueError("`period` must be given")
+        per = float(np.asarray(Quantity(period, u.day).value)) if u.is_quantity(period) else float(period)
+        t = np.asarray(self.time.value, dtype=np.float64)
+        t0 = t[0] if epoch_time is None else float(np.asarray(getattr(epoch_time, "value", epoch_time)))
+        if epoch_time is not None and t0 > 2450000:
+            if self.time.format == "bkjd":
+                warnings.warn("`epoch_time` appears to be given in JD, "
+                              "however the light curve time uses BKJD "
+                              "(i.e. JD - 2454833).", LightkurveWarning)
+            elif self.time.format == "btjd":
+                warnings.warn("`epoch_time` appears to be given in JD, "
+                              "however the light curve time uses BTJD "
+                              "(i.e. JD - 2457000).", LightkurveWarning)
+        ep = float(np.asarray(getattr(epoch_phase, "value", epoch_phase)))
+        ep_days = ep * per if normalize_phase else (float(np.asarray(Quantity(epoch_phase, u.day).value))
+                                                    if u.is_quantity(epoch_phase) else ep)
+        if wrap_phase is None:
+            wrap = per / 2.0
+        else:
+            wv = float(np.asarray(getattr(wrap_phase, "value", wrap_phase)))
+            if normalize_phase:
+                if wv < 0 or wv > 1:
+                    raise ValueError("wrap_phase should be between 0 and 1")
+                wrap = wv * per
+            else:
+                wrap = float(np.asarray(Quantity(wrap_phase, u.day).value)) if u.is_quantity(wrap_phase) else wv
+                if wrap < 0 or wrap > per:
+                    raise ValueError("wrap_phase should be between 0 and the period")
+        rel = ((t - t0) + ep_days + (per - wrap)) % per - (per - wrap)
+        order = np.argsort(rel, kind="stable")
+        folded = FoldedLightCurve.__new__(FoldedLightCurve)
+        folded.meta = _copy.deepcopy(self.meta)
+        phase = rel[order] / per if normalize_phase else rel[order]
+        folded.time = Quantity(phase, u.dimensionless_unscaled if normalize_phase else u.day)
+        folded.flux = Quantity(np.asarray(self.flux.value)[order], self.flux.unit, dtype=self.flux.dtype)
+        folded.flux_err = Quantity(np.asarray(self.flux_err.value)[order], self.flux_err.unit, dtype=self.flux_err.dtype)
+        folded.time_original = Time(t[order], self.time.format, self.time.scale)
+        folded.meta["PERIOD"] = Quantity(per, u.day)
+        folded.meta["EPOCH_TIME"] = None if epoch_time is None else Time(t0, self.time.format, self.time.scale)
+        folded.meta["EPOCH_PHASE"] = epoch_phase
+        folded.meta["WRAP_PHASE"] = wrap_phase
+        folded.meta["NORMALIZE_PHASE"] = normalize_phase
+        return folded
+
     # ------------------------------------------------------------------ BLS follow-ups (host-side, cheap)
     def create_transit_mask(self, period, transit_time, duration):
         """True for in-transit cadences (lightcurve.py:2967-3037)."""
@@ -329,3 +379,32 @@ class LightCurve:
             hp = per * 0.5
             in_transit |= np.abs((t - t0 + hp) % per - hp) < 0.5 * dur
         return in_transit
+
+
+class FoldedLightCurve(LightCurve):
+    """A light curve folded on a period (lightcurve.py:3166-3300): ``time`` holds the phase."""
+
+    @property
+    def phase(self):
+        return self.time
+
+    @property
+    def period(self):
+        return self.meta.get("PERIOD")
+
+    @property
+    def epoch_time(self):
+        return self.meta.get("EPOCH_TIME")
+
+    @property
+    def cycle(self):
+        """The cycle number of each cadence (lightcurve.py: FoldedLightCurve.cycle)."""
+        per = float(np.asarray(self.period.value))
+        t = np.asarray(self.time_original.value, dtype=np.float64)
+        ep = self.epoch_time
+        t0 = t.min() if ep is None else float(np.asarray(ep.value))
+        return np.asarray(np.floor(((t - t0) + per / 2.0) / per), dtype=int) if ep is not None else \
+            np.asarray(np.round((t - t0) / per), dtype=int)
+
+    def __repr__(self):
+        return "<FoldedLightCurve length={} period={}>".format(len(self), self.period)

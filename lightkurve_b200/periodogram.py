@@ -219,6 +219,7 @@ class LombScarglePeriodogram(Periodogram):
         self._LS_object = kwargs.pop("ls_obj", None)
         self.nterms = kwargs.pop("nterms", 1)
         self.ls_method = kwargs.pop("ls_method", "fastchi2")
+        self._fit_data = kwargs.pop("fit_data", None)      # (time, flux) the model() fit needs
         super(LombScarglePeriodogram, self).__init__(*args, **kwargs)
 
     def __repr__(self):
@@ -336,9 +337,8 @@ class LombScarglePeriodogram(Periodogram):
                 LightkurveWarning,
             )
             nterms = 1
-        if nterms > 1:
-            raise NotImplementedError("nterms > 1 (multi-harmonic chi2 periodograms) is not built yet "
-                                      "(SURVEY.md 8f rank 1); no CPU fallback is provided")
+        if nterms > 4:
+            raise NotImplementedError("nterms > 4 is not supported by the CUDA chi2 kernel")
         if ls_method not in ("fast", "slow", "auto", "cython", "scipy", "chi2", "fastchi2"):
             raise ValueError("unknown ls_method '{}'".format(ls_method))
         return dict(lc=lc, time=tval, frequency=frequency, freq_unit=freq_unit, fs=fs, nyquist=nyquist,
@@ -356,7 +356,9 @@ class LombScarglePeriodogram(Periodogram):
         return LombScarglePeriodogram(frequency=prep["frequency"], power=power, nyquist=prep["nyquist"],
                                       targetid=lc.meta.get("TARGETID"), label=lc.meta.get("LABEL"),
                                       default_view=prep["default_view"], ls_obj=None, nterms=prep["nterms"],
-                                      ls_method=prep["ls_method"], meta=lc.meta)
+                                      ls_method=prep["ls_method"], meta=lc.meta,
+                                      fit_data=(prep["time"], np.asarray(lc.flux.value, dtype=np.float64),
+                                                lc.flux.unit, lc.time.format, lc.time.scale))
 
     @staticmethod
     def _norm_args(prep):
@@ -383,12 +385,38 @@ class LombScarglePeriodogram(Periodogram):
         flux = np.asarray(prep["lc"].flux.value)
         if flux.dtype != np.float32:
             flux = flux.astype(np.float64)
-        out = engine.ls_power_ragged([prep["time"]], [flux], freq_day, norm,
-                                     None if scale is None else [scale])
+        if prep["ls_method"] in ("chi2", "fastchi2"):
+            # multi-term fit (periodogram.py:948-964): dedicated kernel, any nterms in [1, 4]
+            out = engine.ls_power_chi2([prep["time"]], [flux], freq_day, prep["nterms"], norm,
+                                       None if scale is None else [scale])
+        else:
+            out = engine.ls_power_ragged([prep["time"]], [flux], freq_day, norm,
+                                         None if scale is None else [scale])
         return LombScarglePeriodogram._finish(prep, out[0])
 
     def model(self, time, frequency=None):
-        raise NotImplementedError("LombScarglePeriodogram.model is a 'next' item (SURVEY.md 8f rank 1)")
+        """Obtain the flux model for a given frequency and time (periodogram.py:991-1018): the
+        maximum-likelihood offset + nterms-harmonic fit at `frequency` (default: frequency at max
+        power), evaluated at `time`, returned as a normalized LightCurve like the reference does.
+        The normal equations are accumulated and solved on the GPU (lkb_ls_power_chi2)."""
+        from . import engine
+        from .lightcurve import LightCurve
+        if self._fit_data is None:
+            raise ValueError("No `astropy` Lomb Scargle object exists.")
+        if frequency is None:
+            frequency = self.frequency_at_max_power
+        t_lc, y_lc, flux_unit, tfmt, tscale = self._fit_data
+        f_day = float(np.asarray(Quantity(frequency, self.frequency.unit).to(1 / u.day).value))
+        _, theta = engine.ls_power_chi2([t_lc], [y_lc], np.array([f_day]), self.nterms, "psd_raw", return_theta=True)
+        th = theta[0, 0]
+        tv = np.asarray(getattr(time, "value", time), dtype=np.float64)
+        trel = tv - t_lc[0]
+        f = np.full(len(tv), th[0] + y_lc.mean())
+        for i in range(1, self.nterms + 1):
+            f += th[2 * i - 1] * np.sin(2 * np.pi * i * f_day * trel) + th[2 * i] * np.cos(2 * np.pi * i * f_day * trel)
+        lc = LightCurve(time=Time(tv, tfmt, tscale), flux=Quantity(f, flux_unit),
+                        meta={"FREQUENCY": frequency, "LABEL": "LS Model"})
+        return lc.normalize()
 
 
 class BoxLeastSquaresPeriodogram(Periodogram):
@@ -554,15 +582,20 @@ class BoxLeastSquaresPeriodogram(Periodogram):
         return f(period), f(duration), f(transit_time)
 
     def compute_stats(self, period=None, duration=None, transit_time=None):
-        """Vetting statistics (periodogram.py:1194-1229): a subset of astropy's compute_stats
-        (depth, odd/even depths, transit times, per-transit counts), evaluated on the host."""
+        """Computes commonly used vetting statistics for a transit model (periodogram.py:1194-1229):
+        astropy ``BoxLeastSquares.compute_stats`` restated (depth, odd/even/half/phased depths,
+        per-transit counts and log-likelihoods, harmonic amplitude / delta log-likelihood).
+        A one-off O(N) vetting step for ONE candidate - evaluated on the host."""
         period, duration, transit_time = self._defaults(period, duration, transit_time)
-        t = np.asarray(self.time.value, dtype=np.float64)
+        t_abs = np.asarray(self.time.value, dtype=np.float64)
+        tstart = t_abs[0]
+        t = t_abs - tstart
+        transit_time = transit_time - tstart
         y = np.asarray(self.flux.value, dtype=np.float64)
         dy = getattr(self, "_dy", None)
-        ivar = np.ones_like(y) if dy is None else 1.0 / np.asarray(dy) ** 2
+        ivar = np.ones_like(y) if dy is None else 1.0 / np.asarray(dy, dtype=np.float64) ** 2
 
-        def _depth(m, y_out=None, var_out=None):
+        def _compute_depth(m, y_out=None, var_out=None):
             if np.any(m) and (var_out is None or np.isfinite(var_out)):
                 var_m = 1.0 / np.sum(ivar[m])
                 y_m = np.sum(y[m] * ivar[m]) * var_m
@@ -572,18 +605,54 @@ class BoxLeastSquaresPeriodogram(Periodogram):
             return 0.0, np.inf
 
         hp = 0.5 * period
-        transit_id = np.round((t - transit_time) / period).astype(int)
-        transit_times = period * np.arange(transit_id.min(), transit_id.max() + 1) + transit_time
         m_in = np.abs((t - transit_time + hp) % period - hp) < 0.5 * duration
         m_out = ~m_in
-        m_odd = (transit_id % 2 == 1) & m_in
-        m_even = (transit_id % 2 == 0) & m_in
-        y_out, var_out = _depth(m_out)
-        depth = _depth(m_in, y_out, var_out)
-        counts = np.bincount(transit_id[m_in] - transit_id.min(), minlength=len(transit_times))
-        return dict(transit_times=Time(transit_times, self.time.format, self.time.scale),
-                    per_transit_count=counts, depth=depth, depth_odd=_depth(m_odd, y_out, var_out),
-                    depth_even=_depth(m_even, y_out, var_out))
+        m_odd = np.abs((t - transit_time) % (2 * period) - period) < 0.5 * duration
+        m_even = np.abs((t - transit_time + period) % (2 * period) - period) < 0.5 * duration
+        y_out, var_out = _compute_depth(m_out)
+        depth = _compute_depth(m_in, y_out, var_out)
+        depth_odd = _compute_depth(m_odd, y_out, var_out)
+        depth_even = _compute_depth(m_even, y_out, var_out)
+        y_in = y_out - depth[0]
+        m_phase = np.abs((t - transit_time) % period - hp) < 0.5 * duration
+        depth_phase = _compute_depth(m_phase, *_compute_depth((~m_phase) & m_out))
+        m_half = np.abs((t - transit_time + 0.25 * period) % (0.5 * period) - 0.25 * period) < 0.5 * duration
+        depth_half = _compute_depth(m_half, *_compute_depth(~m_half))
+
+        if m_in.any():
+            transit_id = np.round((t[m_in] - transit_time) / period).astype(int)
+            transit_times = period * np.arange(transit_id.min(), transit_id.max() + 1) + transit_time
+            unique_ids, unique_counts = np.unique(transit_id, return_counts=True)
+            unique_ids = unique_ids - np.min(transit_id)
+            transit_id = transit_id - np.min(transit_id)
+            counts = np.zeros(np.max(transit_id) + 1, dtype=int)
+            counts[unique_ids] = unique_counts
+            ll = -0.5 * ivar[m_in] * ((y[m_in] - y_in) ** 2 - (y[m_in] - y_out) ** 2)
+            lls = np.zeros(len(counts))
+            for i in unique_ids:
+                lls[i] = np.sum(ll[transit_id == i])
+        else:
+            transit_times, counts, lls = np.zeros(0), np.zeros(0, dtype=int), np.zeros(0)
+        full_ll = -0.5 * np.sum(ivar[m_in] * (y[m_in] - y_in) ** 2)
+        full_ll -= 0.5 * np.sum(ivar[m_out] * (y[m_out] - y_out) ** 2)
+        A = np.vstack((np.sin(2 * np.pi * t / period), np.cos(2 * np.pi * t / period), np.ones_like(t))).T
+        w = np.linalg.solve(np.dot(A.T, A * ivar[:, None]), np.dot(A.T, y * ivar))
+        mod = np.dot(A, w)
+        sin_ll = -0.5 * np.sum((y - mod) ** 2 * ivar)
+        yu = self.flux.unit
+        q = lambda pair: (Quantity(pair[0], yu), Quantity(pair[1], yu))
+        return dict(
+            transit_times=Time(tstart + transit_times, self.time.format, self.time.scale),
+            per_transit_count=counts,
+            per_transit_log_likelihood=lls,
+            depth=q(depth),
+            depth_phased=q(depth_phase),
+            depth_half=q(depth_half),
+            depth_odd=q(depth_odd),
+            depth_even=q(depth_even),
+            harmonic_amplitude=Quantity(np.sqrt(np.sum(w[:2] ** 2)), yu),
+            harmonic_delta_log_likelihood=sin_ll - full_ll,
+        )
 
     def get_transit_model(self, period=None, duration=None, transit_time=None):
         """Box transit model (periodogram.py:1231-1274; astropy BoxLeastSquares.model)."""

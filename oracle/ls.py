@@ -142,6 +142,46 @@ def ls_fast_psd(t, y, f0, df, Nf, use_fft=True):
     return power * (0.5 * N)
 
 
+def design_matrix(t, frequency, bias=True, nterms=1):
+    """astropy implementations.mle.design_matrix with dy = 1: [1, sin(w t), cos(w t), sin(2 w t), ...]."""
+    t = np.asarray(t, dtype=np.float64)
+    cols = [np.ones(len(t))] if bias else []
+    for i in range(1, nterms + 1):
+        cols.append(np.sin(2 * np.pi * i * frequency * t))
+        cols.append(np.cos(2 * np.pi * i * frequency * t))
+    return np.transpose(np.vstack(cols))
+
+
+def ls_chi2_psd(t, y, freq, nterms=1):
+    """astropy ``lombscargle_chi2`` (fit_mean=center_data=True, dy=1, normalization="psd"):
+    P = 0.5 * XTy^T (XTX)^-1 XTy per frequency - what lightkurve gets for ls_method in
+    {"chi2", "fastchi2"} with nterms >= 1 (periodogram.py:948-964)."""
+    t = np.asarray(t, dtype=np.float64)
+    yw, _ = center(y)
+    out = np.empty(len(freq))
+    for k, f in enumerate(np.asarray(freq, dtype=np.float64)):
+        X = design_matrix(t, f, True, nterms)
+        XTX = X.T @ X
+        XTy = X.T @ yw
+        try:
+            out[k] = 0.5 * (XTy @ np.linalg.solve(XTX, XTy))
+        except np.linalg.LinAlgError:
+            out[k] = np.nan
+    return out
+
+
+def ls_model(t, y, frequency, t_fit, nterms=1):
+    """astropy ``LombScargle.model`` / mle.periodic_fit (fit_mean=center_data=True, dy=1) as called at
+    periodogram.py:1010.  Times are taken relative to t[0] like astropy does for Time inputs."""
+    t = np.asarray(t, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    t0 = t[0]
+    y_mean = y.mean()
+    X = design_matrix(t - t0, frequency, True, nterms)
+    theta = np.linalg.solve(X.T @ X, X.T @ (y - y_mean))
+    return y_mean + design_matrix(np.asarray(t_fit, dtype=np.float64) - t0, frequency, True, nterms) @ theta
+
+
 def is_regular(frequency):
     """astropy implementations.main._is_regular (periodogram.py:933)."""
     frequency = np.asarray(frequency)
@@ -172,7 +212,7 @@ def lk_normalize(power_psd, n_time, normalization="amplitude", oversample_factor
 
 
 def lombscargle(t, y, frequency=None, normalization="amplitude", ls_method="fast",
-                oversample_factor=None, **grid_kw):
+                oversample_factor=None, nterms=1, **grid_kw):
     """End-to-end restatement of LombScarglePeriodogram.from_lightcurve numerics
     for finite inputs (NaNs must be dropped by the caller, periodogram.py:785-790).
     Returns (frequency, power, ls_method_used)."""
@@ -183,9 +223,11 @@ def lombscargle(t, y, frequency=None, normalization="amplitude", ls_method="fast
     if frequency is None:
         frequency = grid
     frequency = np.asarray(frequency, dtype=np.float64)
-    if not is_regular(frequency) and ls_method == "fast":
-        ls_method = "slow"
-    if ls_method == "fast":
+    if not is_regular(frequency) and ls_method in ("fast", "fastchi2"):
+        ls_method = {"fast": "slow", "fastchi2": "chi2"}[ls_method]
+    if ls_method in ("chi2", "fastchi2"):
+        p = ls_chi2_psd(t - t[0], y, frequency, nterms)      # (fastchi2 = FFT approximation of the same sums)
+    elif ls_method == "fast":
         f0 = frequency[0]
         df = frequency[1] - frequency[0]
         p = ls_fast_psd(t, y, f0, df, len(frequency))

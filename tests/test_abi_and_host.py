@@ -223,3 +223,26 @@ def test_shard_by_length_balances_and_partitions():
     assert np.array_equal(allidx, np.arange(1000))
     work = np.array([lens[s].sum() for s in shards], dtype=float)
     assert work.max() / work.min() < 1.05
+
+
+def test_fold_matches_astropy_timeseries_fold_semantics():
+    """reference tests/test_lightcurve.py:1589-1606 (fold v2 API) + the phase formula of astropy TimeSeries.fold."""
+    import lightkurve_b200 as lk
+    from lightkurve_b200 import units as u
+    lc = lk.LightCurve(time=np.linspace(0, 10, 100), flux=np.zeros(100) + 1)
+    fld = lc.fold(period=1)
+    fld2 = lc.fold(period=1 * u.day)
+    np.testing.assert_array_equal(fld.phase.value, fld2.phase.value)
+    assert isinstance(fld, lk.FoldedLightCurve) and (np.diff(fld.phase.value) >= 0).all()
+    assert fld.phase.value.min() >= -0.5 and fld.phase.value.max() < 0.5
+    fn = lc.fold(period=2.5, epoch_time=1.0, normalize_phase=True)
+    assert fn.phase.unit == u.dimensionless_unscaled and fn.phase.value.min() >= -0.5 and fn.phase.value.max() < 0.5
+    t = np.asarray(lc.time.value)
+    want = np.sort(((t - 1.0) + 1.25) % 2.5 - 1.25) / 2.5
+    np.testing.assert_allclose(fn.phase.value, want, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(np.sort(fn.time_original.value), t)
+    fw = lc.fold(period=2.0, epoch_time=0.0, wrap_phase=2.0)           # phases in [0, P)
+    assert fw.phase.value.min() >= 0 and fw.phase.value.max() < 2.0
+    with pytest.raises(ValueError):
+        lc.fold(period=2.0, wrap_phase=3.0)
+    assert fw.meta["PERIOD"].value == 2.0 and fw.cycle.max() == 5

@@ -62,6 +62,27 @@ def test_ls_ragged_per_lc_grids_and_f32(engine):
         assert_ls_close(o, p)
 
 
+@pytest.mark.parametrize("nterms", [1, 2, 3, 4])
+def test_ls_chi2_vs_oracle(engine, nterms):
+    rng = np.random.default_rng(14)
+    lcs = [make_lc(rng, n) for n in (900, 257, 3000)]
+    for t, y in lcs:
+        y += 2e-3 * np.sin(2 * np.pi * 2 * (t - t[0]) / 3.7)        # a second harmonic
+    freq = np.linspace(0.02, 3.0, 150)
+    out, theta = engine.ls_power_chi2([l[0] for l in lcs], [l[1] for l in lcs], freq, nterms, "psd_raw",
+                                      return_theta=True)
+    for b, (t, y) in enumerate(lcs):
+        ref = ols.ls_chi2_psd(t - t[0], y, freq, nterms)
+        np.testing.assert_allclose(out[b], ref, rtol=2e-4, atol=1e-5 * ref.max())
+        k = int(np.argmax(ref))
+        X = ols.design_matrix(t - t[0], freq[k], True, nterms)
+        th_ref = np.linalg.solve(X.T @ X, X.T @ (y - y.mean()))
+        np.testing.assert_allclose(theta[b, k], th_ref, rtol=1e-5, atol=1e-9)
+    if nterms == 1:      # chi2 with one term == the closed-form kernel
+        np.testing.assert_allclose(out, engine.ls_power_ragged([l[0] for l in lcs], [l[1] for l in lcs], freq, "psd_raw"),
+                                   rtol=5e-4, atol=1e-5 * out.max())
+
+
 def test_ls_very_low_frequencies(engine):
     """f * baseline << 1: CC'/SS' cancel to ~1e-6 of their terms; the kernels take a full-fp64 path
     for those bins (ragged, shared-SIMT and shared-tcgen05 window terms)."""
@@ -91,9 +112,10 @@ def test_ls_very_low_frequencies(engine):
 def test_edge_cases_empty_and_tiny_light_curves(engine):
     freq = np.linspace(0.1, 1.0, 40)
     t2, y2 = np.array([0.0, 1.0]), np.array([1.0, 2.0])
-    out = engine.ls_power_ragged([np.zeros(0), t2, np.arange(7.0)], [np.zeros(0), y2, np.arange(7.0) ** 2], freq, "psd_raw")
+    t7 = np.arange(7.0) * 1.37                                      # (integer times x f=1.0 would be 0/0 in the reference too)
+    out = engine.ls_power_ragged([np.zeros(0), t2, t7], [np.zeros(0), y2, np.arange(7.0) ** 2], freq, "psd_raw")
     assert np.isnan(out[0]).all()                                   # empty light curve
-    ref = ols.ls_slow_psd(np.arange(7.0), np.arange(7.0) ** 2, freq)
+    ref = ols.ls_slow_psd(t7, np.arange(7.0) ** 2, freq)
     np.testing.assert_allclose(out[2], ref, rtol=2e-4, atol=1e-5 * ref.max())
     assert out[1].shape == freq.shape                               # 2 points: degenerate (0/0 bins), must not crash
     one = engine.ls_power_ragged([np.arange(50.0)], [np.sin(np.arange(50.0))], np.array([0.05]), "amplitude")

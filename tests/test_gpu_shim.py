@@ -143,8 +143,21 @@ def test_bls_period_recovery():
     flux[transit_mask] = 1.0 - depth
     flux += flux_err * np.random.randn(len(time))
     synthetic_lc = LightCurve(time=time, flux=flux)
-    bls_period = synthetic_lc.to_periodogram("bls").period_at_max_power
+    pg = synthetic_lc.to_periodogram("bls")
+    bls_period = pg.period_at_max_power
     assert_almost_equal(bls_period.value, period, decimal=2)
+    # vetting statistics of the recovered candidate (astropy compute_stats semantics) and the fold that follows
+    stats = pg.compute_stats(period, duration, transit_time)
+    n_in = transit_mask.sum()                                       # dy = None -> unit weights, like astropy
+    assert abs(stats["depth"][0].value - depth) < 3e-3
+    assert_almost_equal(stats["depth"][1].value, np.sqrt(1.0 / n_in + 1.0 / (len(time) - n_in)), decimal=12)
+    assert abs(stats["depth_odd"][0].value - depth) < 5e-3 and abs(stats["depth_even"][0].value - depth) < 5e-3
+    assert abs(stats["depth_half"][0].value) < 0.11 and abs(stats["depth_phased"][0].value) < 5e-3
+    assert len(stats["transit_times"]) == 10 and stats["per_transit_count"].sum() == transit_mask.sum()
+    assert (stats["per_transit_log_likelihood"] > 0).all() and stats["harmonic_delta_log_likelihood"] < 0
+    folded = synthetic_lc.fold(pg.period_at_max_power, epoch_time=pg.transit_time_at_max_power)
+    in_tr = np.abs(folded.phase.value) < 0.4 * duration
+    assert abs(folded.flux.value[in_tr].mean() - (1 - depth)) < 0.02
     synthetic_lc.flux.view(np.ndarray)[10] = np.nan
     bls_period = synthetic_lc.to_periodogram("bls").period_at_max_power
     assert_almost_equal(bls_period.value, period, decimal=2)
@@ -178,12 +191,40 @@ def create_beta_lyr_like_lc(dtype=np.float64):
     return LightCurve(time=Time(t + 2457000, format="jd"), flux=f).normalize()
 
 
-@pytest.mark.parametrize("flux_dtype", [np.float64, np.float32])
-def test_ls_method_basics(flux_dtype):
+@pytest.mark.parametrize("flux_dtype, ls_method, nterms, expected_period", [
+    (np.float64, "fast", 1, np.pi), (np.float64, "fastchi2", 2, np.pi * 2),
+    (np.float32, "fast", 1, np.pi), (np.float32, "fastchi2", 2, np.pi * 2)])
+def test_ls_method_basics(flux_dtype, ls_method, nterms, expected_period):
+    """/root/reference/tests/test_periodogram.py:468-488"""
     lc = create_beta_lyr_like_lc(dtype=flux_dtype)
-    pg = lc.to_periodogram(method="ls", ls_method="fast", nterms=1)
-    assert_almost_equal(pg.period_at_max_power.to(u.d).value, np.pi, decimal=1)
-    assert_equal(pg.nterms, 1)
+    pg = lc.to_periodogram(method="ls", ls_method=ls_method, nterms=nterms)
+    assert_almost_equal(pg.period_at_max_power.to(u.d).value, expected_period, decimal=1)
+    assert_equal(pg.nterms, nterms)
+
+
+def test_ls_nterms_uneven_grid_and_model():
+    """/root/reference/tests/test_periodogram.py:491-515 (fastchi2 -> chi2 on an uneven grid) and
+    LombScarglePeriodogram.model (periodogram.py:991-1018) against the oracle."""
+    lc = create_beta_lyr_like_lc()
+    freq_grid = 1 / (np.arange(1, 10, 0.01) * u.d)
+    pg = lc.to_periodogram(method="ls", ls_method="fastchi2", nterms=2, frequency=freq_grid)
+    assert_almost_equal(pg.period_at_max_power.to(u.d).value, 2 * np.pi, decimal=1)
+    assert_equal(pg.nterms, 2)
+    assert_equal(pg.ls_method, "chi2")
+    t = np.asarray(lc.time.value)
+    y = np.asarray(lc.flux.value)
+    fr = np.asarray(pg.frequency.value)
+    ref = np.sqrt(ols.ls_chi2_psd(t - t[0], y, fr, 2)) * np.sqrt(4.0 / len(t))
+    np.testing.assert_allclose(pg.power.value, ref, rtol=2e-4, atol=1e-5 * ref.max())
+    model = pg.model(lc.time)
+    fbest = float(pg.frequency_at_max_power.value)
+    mref = ols.ls_model(t, y, fbest, t, 2)
+    np.testing.assert_allclose(model.flux.value, mref / np.median(mref), rtol=1e-8)
+    # nterms = 1 model too
+    pg1 = lc.to_periodogram(ls_method="slow", frequency=freq_grid)
+    m1 = pg1.model(lc.time, pg1.frequency_at_max_power)
+    r1 = ols.ls_model(t, y, float(pg1.frequency_at_max_power.value), t, 1)
+    np.testing.assert_allclose(m1.flux.value, r1 / np.median(r1), rtol=1e-8)
 
 
 def test_ls_method_uneven_freq_grid(caplog):
