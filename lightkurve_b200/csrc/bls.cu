@@ -41,22 +41,41 @@ __device__ __forceinline__ double bls_fmod(double x, double p, double inv_p) {
 }
 
 // (int)(r / bd) with the IEEE division replaced, on the fast path, by a reciprocal multiply whose
-// result is PROVEN equal: k = trunc(r * (1/bd)); rem = fma(-k, bd, r) is the exact remainder (one
-// rounding of an exactly representable-or-nearly value); if 0 <= rem < bd * (1 - (k + 2) 2^-51) the
-// real quotient lies in [k, k + 1 - margin) and RN(r / bd) cannot reach k + 1, so trunc(RN(r/bd)) = k.
-// Anything else (a sample within ~1e-13 of a bin edge) takes the true division.  Bit-exact with bls.c.
-__device__ __forceinline__ int bls_div_trunc(double r, double bd, double inv_bd) {
-  const double k = trunc(r * inv_bd);
+// result is PROVEN equal: k = trunc(r * (1/bd)); rem = fma(-k, bd, r) is the (once rounded) remainder;
+// if 0 <= rem < bd_safe = bd * (1 - (kmax + 2) 2^-51) with kmax >= k, the real quotient lies in
+// [k, k + 1 - margin) and RN(r / bd) cannot reach k + 1, so trunc(RN(r/bd)) = k.  Anything else (a
+// sample within ~1e-13 of a bin edge) takes the true division - a warp-uniform, out-of-line branch so
+// that the ~25-instruction IEEE division is not if-converted into every iteration.
+__device__ __noinline__ double bls_div_slow(double r, double bd) { return r / bd; }
+
+__device__ __forceinline__ double bls_safe_width(double bd, int kmax) {
+  return bd - bd * (((double)kmax + 2.0) * 4.440892098500626e-16);
+}
+
+// bin index of a sample at x >= 0 (time since the first cadence); `valid` lanes only.  Warp-collective.
+__device__ __forceinline__ int bls_bin_warp(double x, bool valid, double period, double inv_period, double bd,
+                                            double inv_bd, double bd_safe) {
+  double q = trunc(x * inv_period);
+  double r = fma(-q, period, x);
+  if (r < 0.0) { q -= 1.0; r = fma(-q, period, x); }
+  else if (r >= period) { q += 1.0; r = fma(-q, period, x); }
+  double k = trunc(r * inv_bd);
   const double rem = fma(-k, bd, r);
-  const double margin = bd * ((k + 2.0) * 4.440892098500626e-16);
-  if (rem >= 0.0 && rem < bd - margin && k < 1073741824.0) return (int)k;
-  return (int)(r / bd);
+  const bool slow = valid && !(rem >= 0.0 && rem < bd_safe);
+  if (__any_sync(0xffffffffu, slow)) {
+    if (slow) k = trunc(bls_div_slow(r, bd));
+  }
+  return valid ? (int)k + 1 : -1;
 }
 
 __device__ __forceinline__ int bls_bin(double t, double min_t, double period, double inv_period, double bin_duration,
                                        double inv_bin) {
   const double r = fabs(bls_fmod(t - min_t, period, inv_period));
-  return bls_div_trunc(r, bin_duration, inv_bin) + 1;
+  const double k = trunc(r * inv_bin);
+  const double rem = fma(-k, bin_duration, r);
+  const double margin = bin_duration * ((k + 2.0) * 4.440892098500626e-16);
+  if (rem >= 0.0 && rem < bin_duration - margin && k < 1073741824.0) return (int)k + 1;
+  return (int)(r / bin_duration) + 1;
 }
 
 __global__ void bls_bin_index_kernel(const double* __restrict__ t, int64_t N, double min_t, double period,
@@ -116,8 +135,9 @@ bls_prep_kernel(const double* __restrict__ t, const double* __restrict__ y, cons
 }
 
 // ---- per-warp pieces ------------------------------------------------------------------------
-// Add the 32 samples held one per lane into the warp's histogram. key < 0 => lane inactive.
-__device__ __forceinline__ void bls_warp_bin(int key, double vy, double vi, double* hy, double* hi, int lane) {
+// Add the 32 samples held one per lane into the warp's histogram h[bin] = {sum w*y, sum w}.
+// key < 0 => lane inactive.
+__device__ __forceinline__ void bls_warp_bin(int key, double vy, double vi, double2* h, int lane) {
   const unsigned full = 0xffffffffu;
   const int prev = __shfl_up_sync(full, key, 1);
   const bool head = (lane == 0) || (key != prev);
@@ -129,64 +149,80 @@ __device__ __forceinline__ void bls_warp_bin(int key, double vy, double vi, doub
   // scan only as many steps as the longest run needs (runs are ~bin_duration/cadence ~ 3-4 samples):
   // after smearing the head mask by 2^s - 1 lanes, "all ones" means every lane has its run head within
   // 2^s - 1 lanes, i.e. all runs are <= 2^s long and s steps suffice.  headmask is warp-uniform.
+  const int dist = lane - start;                      // lanes since this run's head
   unsigned m = headmask | (headmask << 1);
-  int span = 2;
-  if (m != full) { m |= m << 2; span = 4; }
-  if (m != full) { m |= m << 4; span = 8; }
-  if (m != full) { m |= m << 8; span = 16; }
-  if (m != full) span = 32;
-  for (int o = 1; o < span; o <<= 1) {
-    const double uy = __shfl_up_sync(full, vy, o);
-    const double ui = __shfl_up_sync(full, vi, o);
-    if (lane - o >= start) { vy += uy; vi += ui; }
+  {
+    const double uy = __shfl_up_sync(full, vy, 1), ui = __shfl_up_sync(full, vi, 1);
+    if (dist >= 1) { vy += uy; vi += ui; }
   }
-  const bool tail = ((headmask >> 1) | 0x80000000u) >> lane & 1u;
+  if (m != full) {
+    m |= m << 2;
+    {
+      const double uy = __shfl_up_sync(full, vy, 2), ui = __shfl_up_sync(full, vi, 2);
+      if (dist >= 2) { vy += uy; vi += ui; }
+    }
+    if (m != full) {
+      for (int o = 4; o < 32; o <<= 1) {
+        const double uy = __shfl_up_sync(full, vy, o), ui = __shfl_up_sync(full, vi, o);
+        if (dist >= o) { vy += uy; vi += ui; }
+      }
+    }
+  }
+  const bool tail = (((headmask >> 1) | 0x80000000u) >> lane & 1u) && key >= 0;
   if (wrapmask == 0) {
-    if (tail && key >= 0) { hy[key] += vy; hi[key] += vi; }
+    if (tail) { double2 c = h[key]; c.x += vy; c.y += vi; h[key] = c; }
   } else {
     // split into monotone pieces so that equal keys are contiguous within a piece
     const int piece = __popc(wrapmask & le);
     const int npieces = __popc(wrapmask) + 1;
     for (int q = 0; q < npieces; ++q) {
-      if (tail && key >= 0 && piece == q) { hy[key] += vy; hi[key] += vi; }
+      if (tail && piece == q) { double2 c = h[key]; c.x += vy; c.y += vi; h[key] = c; }
       __syncwarp();
     }
   }
   __syncwarp();
 }
 
-// Inclusive prefix sum over h[0..n] (n+1 entries), in place.  Each lane scans a contiguous chunk
-// sequentially; chunk offsets are a SEQUENTIAL prefix (lane 0) so that an empty bin leaves the
-// running sum bitwise unchanged also across chunk boundaries (tie preservation).
-__device__ __forceinline__ void bls_cumsum(double* h, int n_entries, double* scratch, int lane) {
+// Inclusive prefix sum over h[0..n] (n+1 entries, both components), in place.  Each lane scans a
+// contiguous chunk sequentially; chunk offsets are a SEQUENTIAL prefix (lane 0) so that an empty bin
+// leaves the running sum bitwise unchanged also across chunk boundaries (tie preservation).
+__device__ __forceinline__ void bls_cumsum(double2* h, int n_entries, double2* scratch, int lane) {
   const int L = (n_entries + 31) / 32;
   const int lo = min(lane * L, n_entries), hi = min(lo + L, n_entries);
-  double run = 0.0;
-  for (int i = lo; i < hi; ++i) { run += h[i]; h[i] = run; }
-  scratch[lane] = run;
+  double rx = 0.0, ry = 0.0;
+  for (int i = lo; i < hi; ++i) {
+    double2 c = h[i];
+    rx += c.x; ry += c.y;
+    h[i] = make_double2(rx, ry);
+  }
+  scratch[lane] = make_double2(rx, ry);
   __syncwarp();
   if (lane == 0) {
-    double off = 0.0;
-    for (int l = 0; l < 32; ++l) { const double tot = scratch[l]; scratch[l] = off; off += tot; }
+    double ox = 0.0, oy = 0.0;
+    for (int l = 0; l < 32; ++l) {
+      const double2 tot = scratch[l];
+      scratch[l] = make_double2(ox, oy);
+      ox += tot.x; oy += tot.y;
+    }
   }
   __syncwarp();
-  const double off = scratch[lane];
+  const double2 off = scratch[lane];
   if (lane > 0)
-    for (int i = lo; i < hi; ++i) h[i] = off + h[i];
+    for (int i = lo; i < hi; ++i) {
+      double2 c = h[i];
+      h[i] = make_double2(off.x + c.x, off.y + c.y);
+    }
   __syncwarp();
 }
 
-struct BlsBest {
-  double obj, depth, depth_err, snr, ll;
-  int k, n, dur;
-};
-
+// GHIST = false: per-warp histograms in shared memory; true: in an (L2-resident) global workspace.
+template <bool GHIST>
 __global__ void __launch_bounds__(BLS_WARPS * 32)
 bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy, const double* __restrict__ iv,
                   const int64_t* __restrict__ offsets, const BlsLcInfo* __restrict__ info,
                   const double* __restrict__ period, int64_t p_begin, int64_t p_end, int64_t P,
-                  const double* __restrict__ duration, const int* __restrict__ dur_bins, int D, double bin_duration,
-                  int oversample, int objective, int hist_stride, double* __restrict__ g_hist,
+                  const int* __restrict__ dur_bins, int D, double bin_duration,
+                  int oversample, int objective, int hist_stride, double2* __restrict__ g_hist,
                   double* __restrict__ o_power, double* __restrict__ o_depth, double* __restrict__ o_depth_err,
                   double* __restrict__ o_duration, double* __restrict__ o_ttime, double* __restrict__ o_snr,
                   double* __restrict__ o_ll, int32_t* __restrict__ o_bins) {
@@ -194,8 +230,8 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   double* s_t = reinterpret_cast<double*>(bls_smem);
   double* s_wy = s_t + BLS_TILE;
   double* s_iv = s_wy + BLS_TILE;
-  double* s_scr = s_iv + BLS_TILE;                 // BLS_WARPS * 32
-  double* s_hist = s_scr + BLS_WARPS * 32;         // BLS_WARPS * 2 * hist_stride (unless g_hist)
+  double2* s_scr = reinterpret_cast<double2*>(s_iv + BLS_TILE);   // BLS_WARPS * 32
+  double2* s_hist = s_scr + BLS_WARPS * 32;                       // BLS_WARPS * hist_stride (unless GHIST)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -214,21 +250,21 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   }
   const bool active = p < p_end;
   const double per = active ? period[p] : 1.0;
-  const double inv_per = 1.0 / fabs(per);
+  const double inv_per = 1.0 / per;
   const double inv_bin = 1.0 / bin_duration;
   const int n_bins = (int)ceil(per / bin_duration) + oversample;
-  const BlsLcInfo li = info[b];
+  const double bd_safe = bls_safe_width(bin_duration, n_bins);
+  const BlsLcInfo li = info[b];      // min(t - t_ref) = 0: the samples below are times since the first cadence
 
-  double *hy, *hi;
-  if (g_hist) {
+  double2* h;
+  if constexpr (GHIST) {
     const size_t slot = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nwarps + warp;
-    hy = g_hist + slot * 2 * (size_t)hist_stride;
+    h = g_hist + slot * (size_t)hist_stride;
   } else {
-    hy = s_hist + (size_t)warp * 2 * hist_stride;
+    h = s_hist + (size_t)warp * hist_stride;
   }
-  hi = hy + hist_stride;
   if (active)
-    for (int i = lane; i <= n_bins; i += 32) { hy[i] = 0.0; hi[i] = 0.0; }
+    for (int i = lane; i <= n_bins; i += 32) h[i] = make_double2(0.0, 0.0);
 
   for (int64_t c0 = 0; c0 < n; c0 += BLS_TILE) {
     const int cnt = (int)min((int64_t)BLS_TILE, n - c0);
@@ -242,14 +278,12 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
     if (active) {
       for (int i0 = 0; i0 < cnt; i0 += 32) {
         const int i = i0 + lane;
-        int key = -1;
-        double vy = 0.0, vi = 0.0;
-        if (i < cnt) {
-          key = bls_bin(s_t[i], li.min_t, per, inv_per, bin_duration, inv_bin);
-          vy = s_wy[i];
-          vi = s_iv[i];
-        }
-        bls_warp_bin(key, vy, vi, hy, hi, lane);
+        const bool valid = i < cnt;
+        const int ic = valid ? i : cnt - 1;
+        const int key = bls_bin_warp(s_t[ic], valid, per, inv_per, bin_duration, inv_bin, bd_safe);
+        const double vy = valid ? s_wy[ic] : 0.0;
+        const double vi = valid ? s_iv[ic] : 0.0;
+        bls_warp_bin(key, vy, vi, h, lane);
       }
     }
   }
@@ -257,70 +291,73 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   __syncwarp();
 
   // wrap-pad: mean[n_bins - oversample + (n-1)] = mean[n], n = 1..oversample (no overlap)
-  for (int i = lane + 1; i <= oversample; i += 32) {
-    const int ind = n_bins - oversample + (i - 1);
-    hy[ind] = hy[i];
-    hi[ind] = hi[i];
-  }
+  for (int i = lane + 1; i <= oversample; i += 32) h[n_bins - oversample + (i - 1)] = h[i];
   __syncwarp();
-  double* scr = s_scr + warp * 32;
-  bls_cumsum(hy, n_bins + 1, scr, lane);
-  bls_cumsum(hi, n_bins + 1, scr, lane);
+  bls_cumsum(h, n_bins + 1, s_scr + warp * 32, lane);
 
-  BlsBest best;
-  best.obj = -INFINITY; best.depth = 0.0; best.depth_err = 0.0; best.snr = 0.0; best.ll = 0.0;
-  best.k = 0x7fffffff; best.n = 0x7fffffff; best.dur = -1;
+  // search: only the objective is evaluated per box; the statistics of the winner are recomputed below
+  double best_obj = -INFINITY;
+  int best_k = 0x7fffffff, best_n = 0x7fffffff;
   for (int k = 0; k < D; ++k) {
     const int dur = dur_bins[k];
     const int n_max = n_bins - dur;
     for (int nn = lane; nn <= n_max; nn += 32) {
-      double y_in = hy[nn + dur] - hy[nn];
-      const double ivar_in = hi[nn + dur] - hi[nn];
+      const double2 hb = h[nn + dur], ha = h[nn];
+      double y_in = hb.x - ha.x;
+      const double ivar_in = hb.y - ha.y;
       double y_out = li.sum_y - y_in;
       const double ivar_out = li.sum_ivar - ivar_in;
       if ((ivar_in < DBL_EPSILON) || (ivar_out < DBL_EPSILON)) continue;
       y_in /= ivar_in;
       y_out /= ivar_out;
-      const double depth = y_out - y_in;
-      const double depth_err = sqrt(1.0 / ivar_in + 1.0 / ivar_out);
-      const double snr = depth / depth_err;
-      const double ll = 0.5 * ivar_in * (y_out - y_in) * (y_out - y_in);
-      const double obj = objective ? snr : ll;
-      if (y_out >= y_in && obj > best.obj) {
-        best.obj = obj; best.depth = depth; best.depth_err = depth_err; best.snr = snr; best.ll = ll;
-        best.k = k; best.n = nn; best.dur = dur;
-      }
+      if (!(y_out >= y_in)) continue;
+      double obj;
+      if (objective) obj = (y_out - y_in) / sqrt(1.0 / ivar_in + 1.0 / ivar_out);
+      else obj = 0.5 * ivar_in * (y_out - y_in) * (y_out - y_in);
+      if (obj > best_obj) { best_obj = obj; best_k = k; best_n = nn; }
     }
   }
   // first maximum in (duration-major, start-bin-minor) order across lanes
-  double wobj = best.obj;
-  int wk = best.k, wn = best.n, wl = lane;
+  double wobj = best_obj;
+  int wk = best_k, wn = best_n;
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     const double oo = __shfl_xor_sync(0xffffffffu, wobj, s);
     const int ok = __shfl_xor_sync(0xffffffffu, wk, s);
     const int on = __shfl_xor_sync(0xffffffffu, wn, s);
-    const int ol = __shfl_xor_sync(0xffffffffu, wl, s);
     const bool take = (oo > wobj) || (oo == wobj && (ok < wk || (ok == wk && on < wn)));
-    if (take) { wobj = oo; wk = ok; wn = on; wl = ol; }
+    if (take) { wobj = oo; wk = ok; wn = on; }
   }
-  if (lane == wl) {
+  if (lane == 0) {
     const int64_t oi = (int64_t)b * P + p;
-    o_power[oi] = best.obj;
-    o_depth[oi] = best.depth;
-    o_depth_err[oi] = best.depth_err;
-    o_snr[oi] = best.snr;
-    o_ll[oi] = best.ll;
-    double bd = 0.0, ph = 0.0;
-    if (best.dur >= 0) {
-      bd = best.dur * bin_duration;
-      ph = bls_fmod(best.n * bin_duration + 0.5 * bd + li.min_t, per, inv_per);
+    double depth = 0.0, depth_err = 0.0, snr = 0.0, ll = 0.0, bd = 0.0, ph = 0.0;
+    int dur = -1;
+    if (wk != 0x7fffffff) {
+      dur = dur_bins[wk];
+      const double2 hb = h[wn + dur], ha = h[wn];
+      double y_in = hb.x - ha.x;
+      const double ivar_in = hb.y - ha.y;
+      double y_out = li.sum_y - y_in;
+      const double ivar_out = li.sum_ivar - ivar_in;
+      y_in /= ivar_in;
+      y_out /= ivar_out;
+      depth = y_out - y_in;
+      depth_err = sqrt(1.0 / ivar_in + 1.0 / ivar_out);
+      snr = depth / depth_err;
+      ll = 0.5 * ivar_in * (y_out - y_in) * (y_out - y_in);
+      bd = dur * bin_duration;
+      ph = bls_fmod(wn * bin_duration + 0.5 * bd + li.min_t, per, inv_per);
     }
+    o_power[oi] = wobj;
+    o_depth[oi] = depth;
+    o_depth_err[oi] = depth_err;
+    o_snr[oi] = snr;
+    o_ll[oi] = ll;
     o_duration[oi] = bd;
     o_ttime[oi] = ph + li.t_ref;
     if (o_bins) {
-      o_bins[2 * oi] = best.dur >= 0 ? best.n : -1;
-      o_bins[2 * oi + 1] = best.dur;
+      o_bins[2 * oi] = dur >= 0 ? wn : -1;
+      o_bins[2 * oi + 1] = dur;
     }
   }
 }
@@ -421,11 +458,12 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
   LKB_LAUNCH_CHECK();
 
   // chunk the period list so that one launch's per-warp histograms have a common size
-  const size_t fixed_smem = (size_t)(3 * BLS_TILE + BLS_WARPS * 32) * sizeof(double);
+  const size_t fixed_smem = (size_t)(3 * BLS_TILE + 2 * BLS_WARPS * 32) * sizeof(double);
   const size_t smem_cap = 200 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(bls_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(bls_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(bls_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int64_t p0 = 0;
@@ -445,7 +483,7 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
     int W = BLS_WARPS;
     while (W > 1 && fixed_smem + (size_t)W * 2 * stride * sizeof(double) > smem_cap) W >>= 1;
     size_t hist_bytes = (size_t)W * 2 * stride * sizeof(double);
-    double* g_hist = nullptr;
+    double2* g_hist = nullptr;
     size_t smem = fixed_smem + hist_bytes;
     if (smem > smem_cap) { W = BLS_WARPS; hist_bytes = (size_t)W * 2 * stride * sizeof(double); }
     const unsigned gx = (unsigned)((p1 - p0 + W - 1) / W);
@@ -458,12 +496,17 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
                   "use fewer light curves per call", nb_max, need);
         return LKB_E_UNSUPPORTED;
       }
-      LKB_TRY(ws_get_t<double>(WS_G, need / sizeof(double), &g_hist));
+      LKB_TRY(ws_get_t<double2>(WS_G, need / sizeof(double2), &g_hist));
     }
     dim3 grid(gx, (unsigned)B);
-    bls_search_kernel<<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P, d_dur,
-                                                        d_durbins, D, bin_duration, oversample, objective, stride,
-                                                        g_hist, o0, o1, o2, o3, o4, o5, o6, ob);
+    if (g_hist)
+      bls_search_kernel<true><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P, d_durbins,
+                                                          D, bin_duration, oversample, objective, stride, g_hist, o0,
+                                                          o1, o2, o3, o4, o5, o6, ob);
+    else
+      bls_search_kernel<false><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P,
+                                                           d_durbins, D, bin_duration, oversample, objective, stride,
+                                                           nullptr, o0, o1, o2, o3, o4, o5, o6, ob);
     LKB_LAUNCH_CHECK();
     p0 = p1;
   }
