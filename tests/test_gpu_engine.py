@@ -279,6 +279,51 @@ def test_bls_lightkurve_defaults_recovery(engine):
     np.testing.assert_almost_equal(period[np.argmax(res["power"][0])], 2.0, decimal=2)
 
 
+@pytest.mark.parametrize("density", ["0", "1e31", None])
+def test_bls_dense_sampling_boundary_path(engine, density, monkeypatch):
+    """TESS-like 2-min sampling (3.6 cadences per bin): the bin-boundary path (prefix-sum differences between
+    exactly located run starts) must give the oracle's boxes and values; forced on ("0"), off ("1e31"), auto."""
+    if density is not None:
+        monkeypatch.setenv("LKB_BLS_MIN_DENSITY", density)
+    rng = np.random.default_rng(35)
+    lcs, dys = [], []
+    for n_keep, p_true in ((9000, 2.17), (7000, 0.9), (3000, 4.4)):
+        grid = 1325.0 + np.arange(10000) / 720.0
+        grid = np.concatenate([grid[:4200], grid[4900:]])                    # a data gap
+        keep = np.sort(rng.choice(len(grid), n_keep, replace=False))
+        t = grid[keep] + rng.uniform(-2e-4, 2e-4, n_keep)
+        t.sort()
+        y = 1 + 5e-4 * rng.normal(size=n_keep)
+        y[np.abs((t - 1326.0 + 0.5 * p_true) % p_true - 0.5 * p_true) < 0.06] -= 3e-3
+        lcs.append((t, y))
+        dys.append(5e-4 * rng.uniform(0.8, 1.2, n_keep))
+    # adversarial: cadences that sit (to an ulp) ON the bin edges - decided by the exact fmod/division walk
+    t_adv = 1325.0 + np.arange(9000) * (0.005 / 4)
+    lcs.append((t_adv, 1 + 5e-4 * rng.normal(size=len(t_adv))))
+    dys.append(np.full(len(t_adv), 5e-4))
+    duration = np.linspace(0.05, 0.33, 10)
+    period = np.concatenate([obls.autoperiod(lcs[0][0], duration, 0.3314, 9.26, frequency_factor=10),
+                             [0.3314, 0.335 + 1e-13, 0.5, 1.0, 0.4 + 0.005 / 3, 2.5, 13.0]])
+    res = engine.bls_power([l[0] for l in lcs], [l[1] for l in lcs], dys, period, duration, return_bins=True)
+    for b, (t, y) in enumerate(lcs):
+        ref = obls.bls_power_c(t, y, dys[b], period, duration, return_bins=True)
+        assert_bls_close({k: v[b] for k, v in res.items() if k != "period"}, ref, t, y, dys[b], period, duration,
+                         max_tied_frac=0.02 if b < 3 else 0.5)
+    assert abs(period[np.argmax(res["power"][0])] - 2.17) < 0.01
+
+
+def test_bls_unsorted_times_fall_back_to_cadence_path(engine):
+    rng = np.random.default_rng(36)
+    t = 1325.0 + np.arange(8000) / 720.0
+    y = 1 + 5e-4 * rng.normal(size=len(t))
+    perm = rng.permutation(len(t))
+    duration = np.linspace(0.05, 0.2, 4)
+    period = obls.autoperiod(t, duration, 0.5, 5.0, frequency_factor=20)
+    res = engine.bls_power([t[perm]], [y[perm]], None, period, duration, return_bins=True)
+    ref = obls.bls_power_c(t[perm], y[perm], None, period, duration, return_bins=True)
+    assert_bls_close({k: v[0] for k, v in res.items() if k != "period"}, ref, t[perm], y[perm], None, period, duration)
+
+
 def test_bls_long_period_global_histograms(engine):
     """n_bins too large for shared memory -> global-memory histogram path."""
     rng = np.random.default_rng(34)
