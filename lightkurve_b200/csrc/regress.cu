@@ -29,6 +29,7 @@ struct RgWs {
   uint8_t* used;      // [B, N] cadences currently inside A/rhs
   double* gram;       // [B, Ka, Ka], Ka = K + 1 (column K is y)
   double* resid;      // [B, N]
+  double* wl;         // [B, N] 1/flux_err^2 of the listed cadences, in list order (ones without flux_err)
 };
 
 __device__ __forceinline__ const double* rg_xrow(const double* X, int x_batched, int b, int64_t N, int K, int64_t r) {
@@ -39,8 +40,8 @@ __device__ __forceinline__ const double* rg_xrow(const double* X, int x_batched,
 // first = 1: rows = cadence_mask (& ~outlier, which is empty), used := that.
 // first = 0: rows = used & outlier (newly clipped), used := used & ~outlier.
 __global__ void __launch_bounds__(256)
-rg_rows_kernel(const uint8_t* __restrict__ cadence_mask, const uint8_t* __restrict__ outlier, int64_t N, int first,
-               RgWs ws) {
+rg_rows_kernel(const uint8_t* __restrict__ cadence_mask, const uint8_t* __restrict__ outlier,
+               const double* __restrict__ flux_err, int64_t N, int first, RgWs ws) {
   __shared__ int s_wc[8];
   __shared__ int s_base;
   const int b = blockIdx.x;
@@ -68,7 +69,13 @@ rg_rows_kernel(const uint8_t* __restrict__ cadence_mask, const uint8_t* __restri
     __syncthreads();
     int off = s_base;
     for (int w = 0; w < warp; ++w) off += s_wc[w];
-    if (p) rows[off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+    if (p) {
+      const int pos = off + __popc(bal & ((1u << lane) - 1u));
+      rows[pos] = (int32_t)i;
+      double f = 1.0;
+      if (flux_err) f = flux_err[(int64_t)b * N + i];
+      ws.wl[(int64_t)b * N + pos] = 1.0 / (f * f);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       int tot = 0;
@@ -190,6 +197,119 @@ rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __res
       const int gj = bj * RG_BLK + tx + 16 * j;
       if (gj >= Ka) continue;
       G[(int64_t)gi * Ka + gj] += sign * acc[i][j];     // this CTA owns the block: no atomics
+    }
+  }
+}
+
+// ---- weighted Gram accumulation on the FP64 tensor cores -------------------------------------------
+// One CTA per light curve; warp w owns the 40x40 block (bi, bj >= bi) of [X | y]^T W [X | y], i.e. a 5x5
+// grid of m8n8k4 DMMA tiles whose 10 operand fragments per k-step are re-used across the 25 tiles.
+// Gathered cadence rows land by cp.async in a double-buffered [32 x 164] stage (row stride = 4 mod 16
+// doubles: the 16 lanes of a half-warp fragment load hit 16 different bank pairs).
+constexpr int RGM_RC = 32;              // cadences per stage (8 k-steps)
+constexpr int RGM_LD = 164;             // stage row stride in doubles
+struct RgmStage {
+  double x[RGM_RC][RGM_LD];
+  double w[RGM_RC];
+};
+
+__device__ __forceinline__ void rg_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NB5>
+__global__ void __launch_bounds__(32 * NB5 * (NB5 + 1) / 2)
+rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y,
+                   int64_t N, int K, double sign, RgWs ws) {
+  constexpr int nb5 = NB5;
+  extern __shared__ __align__(16) unsigned char rg_smem[];
+  RgmStage* st = reinterpret_cast<RgmStage*>(rg_smem);
+  const int b = blockIdx.x;
+  const int Ka = K + 1;
+  // gridDim.y CTAs share a light curve's cadence list (whole stages each); with 2 of them and a zeroed
+  // Gram matrix the two atomic adds commute exactly, so the result does not depend on their order
+  const int cnt_all = ws.cnt[b];
+  const int stages = (cnt_all + RGM_RC - 1) / RGM_RC;
+  const int s_lo = (int)((int64_t)stages * blockIdx.y / gridDim.y), s_hi = (int)((int64_t)stages * (blockIdx.y + 1) / gridDim.y);
+  const int r_lo = s_lo * RGM_RC;
+  const int cnt = min(cnt_all, s_hi * RGM_RC) - r_lo;
+  if (cnt <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // decode this warp's upper-triangular block
+  int bi = 0, rem = warp;
+  while (rem >= nb5 - bi) { rem -= nb5 - bi; ++bi; }
+  const int bj = bi + rem;
+  const int32_t* rows = ws.rows + (int64_t)b * N + r_lo;
+  const double* wl = ws.wl + (int64_t)b * N + r_lo;
+  const double* yb = y + (int64_t)b * N;
+
+  // zero the padding columns once (cp.async only ever writes columns < Ka)
+  for (int e = threadIdx.x; e < 2 * RGM_RC * (RGM_LD - Ka); e += blockDim.x) {
+    const int s = e / (RGM_RC * (RGM_LD - Ka)), r2 = e % (RGM_RC * (RGM_LD - Ka));
+    st[s].x[r2 / (RGM_LD - Ka)][Ka + r2 % (RGM_LD - Ka)] = 0.0;
+  }
+  auto issue = [&](int c0, int buf) {
+    RgmStage& s = st[buf];
+    const int nr = min(RGM_RC, cnt - c0);
+    for (int e = threadIdx.x; e < RGM_RC * Ka; e += blockDim.x) {
+      const int r = e / Ka, c = e - r * Ka;
+      const int64_t row = rows[c0 + min(r, nr - 1)];           // tail rows repeat a valid row with weight 0
+      const double* src = (c < K) ? rg_xrow(X, x_batched, b, N, K, row) + c : yb + row;
+      rg_cp8(&s.x[r][c], src);
+    }
+    if (threadIdx.x < RGM_RC) {
+      const int r = threadIdx.x;
+      if (r < nr) rg_cp8(&s.w[r], wl + c0 + r);
+      else s.w[r] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  double acc[5][5][2];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  issue(0, 0);
+  int buf = 0;
+  const int kr = lane & 3, kc = lane >> 2;
+  for (int c0 = 0; c0 < cnt; c0 += RGM_RC, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                     // chunk c0 landed; everybody is done computing on buf^1
+    if (c0 + RGM_RC < cnt) issue(c0 + RGM_RC, buf ^ 1);
+    RgmStage& s = st[buf];
+#pragma unroll 2
+    for (int ks = 0; ks < RGM_RC / 4; ++ks) {
+      const double* xr = &s.x[ks * 4 + kr][kc];
+      const double w = s.w[ks * 4 + kr];
+      double a[5], bb[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) a[i] = w * xr[(bi * 5 + i) * 8];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) bb[j] = xr[(bj * 5 + j) * 8];
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) rg_dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+  }
+  double* G = ws.gram + (int64_t)b * Ka * Ka;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int gi = (bi * 5 + i) * 8 + (lane >> 2);
+    if (gi >= Ka) continue;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int gj = (bj * 5 + j) * 8 + 2 * (lane & 3);
+      if (gridDim.y == 1) {                   // this warp owns the block
+        if (gj < Ka) G[(int64_t)gi * Ka + gj] += sign * acc[i][j][0];
+        if (gj + 1 < Ka) G[(int64_t)gi * Ka + gj + 1] += sign * acc[i][j][1];
+      } else {
+        if (gj < Ka) atomicAdd(&G[(int64_t)gi * Ka + gj], sign * acc[i][j][0]);
+        if (gj + 1 < Ka) atomicAdd(&G[(int64_t)gi * Ka + gj + 1], sign * acc[i][j][1]);
+      }
     }
   }
 }
@@ -471,6 +591,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
   LKB_TRY(ws_get_t<uint8_t>(WS_C, BN, &ws.used));
   LKB_TRY(ws_get_t<double>(WS_D, (size_t)B * Ka * Ka, &ws.gram));
   LKB_TRY(ws_get_t<double>(WS_E, BN, &ws.resid));
+  LKB_TRY(ws_get_t<double>(WS_H, BN, &ws.wl));
 
   double *o_c = nullptr, *o_m = nullptr;
   uint8_t* o_om = nullptr;
@@ -503,12 +624,39 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
                                         (int)(2 * sizeof(RgStage))));
     accum_attr = true;
   }
+  // FP64 tensor-core Gram kernel (default) / SIMT kernel (LKB_REGRESS_SIMT=1, kept for A/B measurements)
+  const int nb5 = (((Ka + 7) / 8) + 4) / 5;
+  static const bool force_simt = getenv("LKB_REGRESS_SIMT") != nullptr;
+  const bool use_mma = !force_simt && Ka <= RGM_LD && nb5 <= 5;
+  static bool mma_attr = false;
+  if (!mma_attr) {
+    const int sm2 = (int)(2 * sizeof(RgmStage));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    mma_attr = true;
+  }
   for (int it = 0; it < niters; ++it) {
-    rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, N, it == 0 ? 1 : 0, ws);
+    rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, d_fe, N, it == 0 ? 1 : 0, ws);
     LKB_LAUNCH_CHECK();
     if (it == 0) prof_begin(st);
-    rg_accum_kernel<<<dim3(nupper, B), 128, 2 * sizeof(RgStage), st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk,
-                                                                         it == 0 ? 1.0 : -1.0, ws);
+    if (use_mma) {
+      const double sgn = it == 0 ? 1.0 : -1.0;
+      const size_t sm2 = 2 * sizeof(RgmStage);
+      // first pass of a small batch: two CTAs per light curve to fill the SMs (wave quantisation)
+      const dim3 g((unsigned)B, (it == 0 && B < 4 * sm_count() && N >= 4096) ? 2u : 1u);
+      switch (nb5) {
+        case 1: rg_gram_mma_kernel<1><<<g, 32, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 2: rg_gram_mma_kernel<2><<<g, 96, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 3: rg_gram_mma_kernel<3><<<g, 192, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 4: rg_gram_mma_kernel<4><<<g, 320, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        default: rg_gram_mma_kernel<5><<<g, 480, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+      }
+    } else
+      rg_accum_kernel<<<dim3(nupper, B), 128, 2 * sizeof(RgStage), st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk,
+                                                                           it == 0 ? 1.0 : -1.0, ws);
     if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
     rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status);
