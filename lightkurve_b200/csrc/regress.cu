@@ -202,12 +202,13 @@ rg_accum_kernel(const double* __restrict__ X, int x_batched, const double* __res
 }
 
 // ---- weighted Gram accumulation on the FP64 tensor cores -------------------------------------------
-// One CTA per light curve; warp w owns the 40x40 block (bi, bj >= bi) of [X | y]^T W [X | y], i.e. a 5x5
-// grid of m8n8k4 DMMA tiles whose 10 operand fragments per k-step are re-used across the 25 tiles.
+// One CTA per light curve; warp w owns the (8 TB)^2 block (bi, bj >= bi) of [X | y]^T W [X | y], i.e. a TB x TB
+// grid of m8n8k4 DMMA tiles whose 2 TB operand fragments per k-step are re-used across the TB^2 tiles
+// (TB = 4: 15 warps for K = 151, an even 4/4/4/3 split over the four SM sub-partitions).
 // Gathered cadence rows land by cp.async in a double-buffered [32 x 164] stage (row stride = 4 mod 16
 // doubles: the 16 lanes of a half-warp fragment load hit 16 different bank pairs).
 constexpr int RGM_RC = 32;              // cadences per stage (8 k-steps)
-constexpr int RGM_LD = 164;             // stage row stride in doubles
+constexpr int RGM_LD = 180;             // stage row stride in doubles (>= 8 * 21 tiles, = 4 mod 16)
 struct RgmStage {
   double x[RGM_RC][RGM_LD];
   double w[RGM_RC];
@@ -218,7 +219,7 @@ __device__ __forceinline__ void rg_dmma(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int NB5>
+template <int NB5, int TB>
 __global__ void __launch_bounds__(32 * NB5 * (NB5 + 1) / 2)
 rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y,
                    int64_t N, int K, double sign, RgWs ws) {
@@ -266,11 +267,11 @@ rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  double acc[5][5][2];
+  double acc[TB][TB][2];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < TB; ++i)
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int j = 0; j < TB; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   issue(0, 0);
   int buf = 0;
@@ -284,25 +285,25 @@ rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __
     for (int ks = 0; ks < RGM_RC / 4; ++ks) {
       const double* xr = &s.x[ks * 4 + kr][kc];
       const double w = s.w[ks * 4 + kr];
-      double a[5], bb[5];
+      double a[TB], bb[TB];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) a[i] = w * xr[(bi * 5 + i) * 8];
+      for (int i = 0; i < TB; ++i) a[i] = w * xr[min((bi * TB + i) * 8, RGM_LD - 8)];   // (tiles past Ka: discarded)
 #pragma unroll
-      for (int j = 0; j < 5; ++j) bb[j] = xr[(bj * 5 + j) * 8];
+      for (int j = 0; j < TB; ++j) bb[j] = xr[min((bj * TB + j) * 8, RGM_LD - 8)];
 #pragma unroll
-      for (int i = 0; i < 5; ++i)
+      for (int i = 0; i < TB; ++i)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) rg_dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        for (int j = 0; j < TB; ++j) rg_dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
     }
   }
   double* G = ws.gram + (int64_t)b * Ka * Ka;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int gi = (bi * 5 + i) * 8 + (lane >> 2);
+  for (int i = 0; i < TB; ++i) {
+    const int gi = (bi * TB + i) * 8 + (lane >> 2);
     if (gi >= Ka) continue;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int gj = (bj * 5 + j) * 8 + 2 * (lane & 3);
+    for (int j = 0; j < TB; ++j) {
+      const int gj = (bj * TB + j) * 8 + 2 * (lane & 3);
       if (gridDim.y == 1) {                   // this warp owns the block
         if (gj < Ka) G[(int64_t)gi * Ka + gj] += sign * acc[i][j][0];
         if (gj + 1 < Ka) G[(int64_t)gi * Ka + gj + 1] += sign * acc[i][j][1];
@@ -488,6 +489,73 @@ rg_inverse_kernel(int K, const double* __restrict__ prior_sigma, RgWs ws, double
   }
 }
 
+// ---- model = X w for a whole batch on the FP64 tensor cores (shared design matrix) ------------------
+// out[b, n] = sum_k X[n, k] coeff[b, k].  CTA = 64 light curves (their coefficient rows stay in shared
+// memory) x a strided set of 32-cadence stages of X (cp.async double buffer); warp w owns the 8-cadence
+// row tile (w & 3) and four 8-light-curve column tiles: 1 + 4 fragments per 4 DMMAs.
+constexpr int RGE_LC = 64;
+struct RgeSmem {
+  double w[RGE_LC][RGM_LD];
+  double x[2][RGM_RC][RGM_LD];
+};
+
+__global__ void __launch_bounds__(256)
+rg_model_mma_kernel(const double* __restrict__ X, int64_t N, int K, int B, const double* __restrict__ coeff,
+                    double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rg_smem[];
+  RgeSmem& sm = *reinterpret_cast<RgeSmem*>(rg_smem);
+  const int lc0 = blockIdx.y * RGE_LC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = (int)((N + RGM_RC - 1) / RGM_RC);
+  for (int e = threadIdx.x; e < RGE_LC * RGM_LD; e += blockDim.x) {
+    const int r = e / RGM_LD, c = e - r * RGM_LD;
+    sm.w[r][c] = (c < K && lc0 + r < B) ? coeff[(int64_t)(lc0 + r) * K + c] : 0.0;
+  }
+  for (int e = threadIdx.x; e < 2 * RGM_RC * (RGM_LD - K); e += blockDim.x) {
+    const int sgl = e / (RGM_RC * (RGM_LD - K)), r2 = e % (RGM_RC * (RGM_LD - K));
+    sm.x[sgl][r2 / (RGM_LD - K)][K + r2 % (RGM_LD - K)] = 0.0;
+  }
+  auto issue = [&](int stage, int buf) {
+    const int64_t n0 = (int64_t)stage * RGM_RC;
+    for (int e = threadIdx.x; e < RGM_RC * K; e += blockDim.x) {
+      const int r = e / K, c = e - r * K;
+      const int64_t row = min(n0 + r, N - 1);                 // tail rows repeat the last cadence (never stored)
+      rg_cp8(&sm.x[buf][r][c], X + row * K + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int mt = warp & 3, ng = warp >> 2;
+  const int kr = lane & 3, kq = lane >> 2;
+  const int ksteps = (K + 3) / 4;
+  int stage = blockIdx.x, buf = 0;
+  if (stage < nstage) issue(stage, 0);
+  for (; stage < nstage; stage += gridDim.x, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (stage + (int)gridDim.x < nstage) issue(stage + gridDim.x, buf ^ 1);
+    double acc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    const double* xa = &sm.x[buf][mt * 8 + kq][kr];
+    const double* wb = &sm.w[ng * 32 + kq][kr];
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const double a = xa[ks * 4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rg_dmma(acc[j][0], acc[j][1], a, wb[j * 8 * RGM_LD + ks * 4]);
+    }
+    const int64_t n = (int64_t)stage * RGM_RC + mt * 8 + kq;
+    if (n < N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lc = lc0 + ng * 32 + j * 8 + 2 * kr;
+        if (lc < B) out[(int64_t)lc * N + n] = acc[j][0];
+        if (lc + 1 < B) out[(int64_t)(lc + 1) * N + n] = acc[j][1];
+      }
+    }
+  }
+}
+
 // ---- model + sigma clip ---------------------------------------------------------------------------
 __device__ __forceinline__ void rg_model_rows(const double* X, int x_batched, int b, int64_t N, int K,
                                               const double* s_w, double* out) {
@@ -503,7 +571,8 @@ __device__ __forceinline__ void rg_model_rows(const double* X, int x_batched, in
 
 __global__ void __launch_bounds__(512)
 rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y, int64_t N, int K,
-               const double* __restrict__ coeff, double clip_sigma, RgWs ws, uint8_t* __restrict__ outlier) {
+               const double* __restrict__ coeff, double clip_sigma, RgWs ws, uint8_t* __restrict__ outlier,
+               int model_ready) {
   extern __shared__ __align__(16) double s_w[];
   __shared__ SelSmem sm;
   const int b = blockIdx.x;
@@ -514,7 +583,7 @@ rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __rest
   uint8_t* om = outlier + (int64_t)b * N;
   const double* yb = y + (int64_t)b * N;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-  rg_model_rows(X, x_batched, b, N, K, s_w, res);
+  if (!model_ready) rg_model_rows(X, x_batched, b, N, K, s_w, res);      // else ws.resid already holds X w
   __syncthreads();
   for (int64_t i = threadIdx.x; i < N; i += blockDim.x) res[i] = used[i] ? (yb[i] - res[i]) : qnan;
   __syncthreads();
@@ -541,14 +610,14 @@ rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __rest
 
 __global__ void __launch_bounds__(512)
 rg_final_kernel(const double* __restrict__ X, int x_batched, int64_t N, int K, const double* __restrict__ coeff,
-                double* __restrict__ model) {
+                double* __restrict__ model, int model_ready) {
   extern __shared__ __align__(16) double s_w[];
   __shared__ SelSmem sm;
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_w[k] = coeff[(int64_t)b * K + k];
   __syncthreads();
   double* mo = model + (int64_t)b * N;
-  rg_model_rows(X, x_batched, b, N, K, s_w, mo);
+  if (!model_ready) rg_model_rows(X, x_batched, b, N, K, s_w, mo);
   __syncthreads();
   // np.median (NaN-propagating): a NaN model (singular fit) stays NaN
   long long cntv = 0;
@@ -625,18 +694,35 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     accum_attr = true;
   }
   // FP64 tensor-core Gram kernel (default) / SIMT kernel (LKB_REGRESS_SIMT=1, kept for A/B measurements)
-  const int nb5 = (((Ka + 7) / 8) + 4) / 5;
+  const int ntile = (Ka + 7) / 8;
+  const int tb = ntile <= 20 ? 4 : 5;
+  const int nb5 = (ntile + tb - 1) / tb;
   static const bool force_simt = getenv("LKB_REGRESS_SIMT") != nullptr;
   const bool use_mma = !force_simt && Ka <= RGM_LD && nb5 <= 5;
   static bool mma_attr = false;
   if (!mma_attr) {
     const int sm2 = (int)(2 * sizeof(RgmStage));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_gram_mma_kernel<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2));
     mma_attr = true;
+  }
+  // batched model X w as one FP64 tensor-core GEMM when the design matrix is shared by the batch
+  const bool gemm_model = !force_simt && !x_batched && K <= RGM_LD - 1 && B >= 8;
+  dim3 gemm_grid(1, (unsigned)((B + RGE_LC - 1) / RGE_LC));
+  if (gemm_model) {
+    static bool attr = false;
+    if (!attr) {
+      LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_model_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(RgeSmem)));
+      attr = true;
+    }
+    const int nstage = (int)((N + RGM_RC - 1) / RGM_RC);
+    int gx = (4 * sm_count() + (int)gemm_grid.y - 1) / (int)gemm_grid.y;
+    gemm_grid.x = (unsigned)(gx < 1 ? 1 : (gx > nstage ? nstage : gx));
   }
   for (int it = 0; it < niters; ++it) {
     rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, d_fe, N, it == 0 ? 1 : 0, ws);
@@ -647,12 +733,14 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
       const size_t sm2 = 2 * sizeof(RgmStage);
       // first pass of a small batch: two CTAs per light curve to fill the SMs (wave quantisation)
       const dim3 g((unsigned)B, (it == 0 && B < 4 * sm_count() && N >= 4096) ? 2u : 1u);
-      switch (nb5) {
-        case 1: rg_gram_mma_kernel<1><<<g, 32, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
-        case 2: rg_gram_mma_kernel<2><<<g, 96, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
-        case 3: rg_gram_mma_kernel<3><<<g, 192, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
-        case 4: rg_gram_mma_kernel<4><<<g, 320, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
-        default: rg_gram_mma_kernel<5><<<g, 480, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+      const unsigned nt = 32u * nb5 * (nb5 + 1) / 2;
+      if (tb == 5) rg_gram_mma_kernel<5, 5><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws);
+      else switch (nb5) {
+        case 1: rg_gram_mma_kernel<1, 4><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 2: rg_gram_mma_kernel<2, 4><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 3: rg_gram_mma_kernel<3, 4><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        case 4: rg_gram_mma_kernel<4, 4><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
+        default: rg_gram_mma_kernel<5, 4><<<g, nt, sm2, st>>>(d_X, x_batched, d_y, N, K, sgn, ws); break;
       }
     } else
       rg_accum_kernel<<<dim3(nupper, B), 128, 2 * sizeof(RgStage), st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk,
@@ -661,10 +749,19 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     LKB_LAUNCH_CHECK();
     rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status);
     LKB_LAUNCH_CHECK();
-    rg_clip_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om);
+    if (gemm_model) {
+      rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
+      LKB_LAUNCH_CHECK();
+    }
+    rg_clip_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om,
+                                                       gemm_model ? 1 : 0);
     LKB_LAUNCH_CHECK();
   }
-  rg_final_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, N, K, o_c, o_m);
+  if (gemm_model) {
+    rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, o_m);
+    LKB_LAUNCH_CHECK();
+  }
+  rg_final_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, N, K, o_c, o_m, gemm_model ? 1 : 0);
   LKB_LAUNCH_CHECK();
   if (coeff_cov) {
     // covariance of the LAST fit (the Gram matrix in the workspace already excludes every clipped row

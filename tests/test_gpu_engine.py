@@ -419,7 +419,8 @@ def test_regress_reference_known_answers(engine):
     np.testing.assert_almost_equal(r["coefficients"][0], [0, 5])
 
 
-@pytest.mark.parametrize("K,N,B", [(7, 500, 3), (151, 3000, 4), (64, 1000, 2)])
+@pytest.mark.parametrize("K,N,B", [(7, 500, 3), (151, 3000, 4), (64, 1000, 2), (151, 2011, 9), (13, 777, 70),
+                                   (163, 900, 8)])
 def test_regress_vs_oracle(engine, K, N, B):
     rng = np.random.default_rng(51)
     X = np.cumsum(rng.normal(size=(N, K - 1)), axis=0)
