@@ -176,6 +176,16 @@ int lkb_regress(const double* X, int x_batched, const double* y, const double* f
 int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B,
                       double* out_median, double* out_std, int mem, void* stream);
 
+/* ---- periodogram background (the step after Lomb-Scargle) -------------------- */
+/* Periodogram.smooth(method="logmedian") (periodogram.py:260-284), the background that
+ * Periodogram.flatten (:381-429) divides by, for B periodograms on one frequency grid:
+ *   background[b, i] = mean over the windows w covering bin i of nanmedian(power[b, lo_w:hi_w]) / corr_factor.
+ * win_lo/win_hi [W] (HOST, int32, ordered) are the half-open bin ranges of the reference's moving window
+ * (|log10 f - x0| < filter_width, x0 advancing by filter_width / 2), built by the caller from the grid.
+ * power/background [B, F] fp64 (host or device per `mem`).  Bins covered by no window get NaN (0/0). */
+int lkb_pg_logmedian(const double* power, int B, int64_t F, const int32_t* win_lo, const int32_t* win_hi, int W,
+                     double corr_factor, double* background, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

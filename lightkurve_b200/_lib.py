@@ -47,6 +47,7 @@ SIGNATURES = {
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "lkb_savgol_tables": (c_int, [c_int, c_int, c_vp, c_vp]),
     "lkb_nanmedian_std": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
+    "lkb_pg_logmedian": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_dbl, c_vp, c_int, c_vp]),
 }
 
 _lib = None

@@ -127,6 +127,7 @@ int flatten(const double*, const double*, const double*, const uint8_t*, const i
 int regress(const double*, int, const double*, const double*, const uint8_t*, const double*, const double*, int,
             int64_t, int, double, int, double*, double*, uint8_t*, int32_t*, double*, int, cudaStream_t);
 int nanmedian_std(const double*, const int64_t*, int, double*, double*, int, cudaStream_t);
+int pg_logmedian(const double*, int, int64_t, const int32_t*, const int32_t*, int, double, double*, int, cudaStream_t);
 int savgol_tables_host(int, int, double*, double*);
 
 }  // namespace lkb
@@ -258,6 +259,12 @@ int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B, double* ou
                       void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   return nanmedian_std(x, offsets, B, out_median, out_std, mem, (cudaStream_t)stream);
+}
+
+int lkb_pg_logmedian(const double* power, int B, int64_t F, const int32_t* win_lo, const int32_t* win_hi, int W,
+                     double corr_factor, double* background, int mem, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return pg_logmedian(power, B, F, win_lo, win_hi, W, corr_factor, background, mem, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -303,3 +303,61 @@ def nanmedian_std(arrays):
     sd = np.empty(B, dtype=np.float64)
     L.check(lib.lkb_nanmedian_std(L.ptr(x), L.ptr(offsets), B, L.ptr(med), L.ptr(sd), L.MEM_HOST, None))
     return med, sd
+
+
+def logmedian_windows(frequency, filter_width):
+    """Half-open bin ranges of the reference's moving log10-frequency window (periodogram.py:267-277) for an
+    ASCENDING frequency grid: window w = { i : |log10 f_i - x0_w| < filter_width }, x0 advancing by
+    filter_width / 2 from log10 f_0 (the same fp64 accumulation).  Empty windows are kept (they add nothing)."""
+    logf = np.log10(np.asarray(frequency, dtype=np.float64))
+    F = len(logf)
+    x0s = []
+    x0 = logf[0]
+    while x0 < logf[-1]:
+        x0s.append(x0)
+        x0 += 0.5 * filter_width
+    x0s = np.asarray(x0s, dtype=np.float64)
+    lo = np.searchsorted(logf, x0s - filter_width, side="right")
+    hi = np.searchsorted(logf, x0s + filter_width, side="left")
+    # the reference's expression is |logf - x0| < w in fp64: settle the edge bins with exactly that
+    inside = lambda i, c: np.abs(logf[np.clip(i, 0, F - 1)] - c) < filter_width
+    for _ in range(3):
+        grow = (lo > 0) & inside(lo - 1, x0s)
+        lo = np.where(grow, lo - 1, lo)
+        shrink = (lo < hi) & ~inside(lo, x0s)
+        lo = np.where(shrink, lo + 1, lo)
+        grow = (hi < F) & inside(hi, x0s)
+        hi = np.where(grow, hi + 1, hi)
+        shrink = (hi > lo) & ~inside(hi - 1, x0s)
+        hi = np.where(shrink, hi - 1, hi)
+    return lo.astype(np.int32), np.maximum(hi, lo).astype(np.int32)
+
+
+def pg_logmedian(frequency, power, filter_width):
+    """Background of B periodograms on one frequency grid (Periodogram.smooth(method="logmedian")).
+    power [B, F] (or [F]); returns the same shape, fp64."""
+    lib = L.load()
+    freq = np.asarray(frequency, dtype=np.float64)
+    p = np.asarray(power, dtype=np.float64)
+    one = p.ndim == 1
+    p = np.ascontiguousarray(np.atleast_2d(p))
+    B, F = p.shape
+    if len(freq) != F:
+        raise ValueError("frequency and power must have the same length")
+    order = None
+    if F > 1 and not np.all(np.diff(freq) >= 0):
+        order = np.argsort(freq, kind="stable")
+        freq, p = freq[order], np.ascontiguousarray(p[:, order])
+    lo, hi = logmedian_windows(freq, filter_width)
+    out = np.empty((B, F), dtype=np.float64)
+    if len(lo) == 0:
+        out[:] = np.nan
+    else:
+        lo, hi = np.ascontiguousarray(lo), np.ascontiguousarray(hi)
+        L.check(lib.lkb_pg_logmedian(L.ptr(p), B, F, L.ptr(lo), L.ptr(hi), len(lo), (8.0 / 9.0) ** 3, L.ptr(out),
+                                     L.MEM_HOST, None))
+    if order is not None:
+        inv = np.empty_like(order)
+        inv[order] = np.arange(F)
+        out = out[:, inv]
+    return out[0] if one else out

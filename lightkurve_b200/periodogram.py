@@ -173,20 +173,9 @@ class Periodogram(object):
         if isinstance(filter_width, Quantity) or u.is_quantity(filter_width):
             raise ValueError("the 'logmedian' method requires a dimensionless "
                              "value for `filter_width` in log10(frequency) space.")
-        fval = self.frequency.value
-        count = np.zeros(len(fval), dtype=int)
-        bkg = np.zeros_like(fval)
-        x0 = np.log10(fval[0])
-        corr_factor = (8.0 / 9.0) ** 3
-        logf = np.log10(fval)
-        while x0 < logf[-1]:
-            m = np.abs(logf - x0) < filter_width
-            if m.any():
-                bkg[m] += np.nanmedian(self.power.value[m]) / corr_factor
-                count[m] += 1
-            x0 += 0.5 * filter_width
-        with np.errstate(divide="ignore", invalid="ignore"):
-            bkg /= count
+        # moving log-median on the GPU (exact medians per window; lkb_pg_logmedian)
+        from . import engine
+        bkg = engine.pg_logmedian(self.frequency.value, self.power.value, float(filter_width))
         smooth_pg = self.copy()
         smooth_pg.power = Quantity(bkg, self.power.unit)
         return smooth_pg

@@ -464,3 +464,23 @@ def test_nanmedian_std(engine):
     for a, m, s in zip(arrs, med, sd):
         assert m == np.nanmedian(a)
         np.testing.assert_allclose(s, np.nanstd(a), rtol=1e-12, equal_nan=True)
+
+
+# ---------------------------------------------------------------- periodogram background (K6 reuse)
+@pytest.mark.parametrize("F,B,fw", [(2497, 3, 0.1), (20000, 5, 0.01), (777, 2, 0.033)])
+def test_pg_logmedian_vs_oracle(engine, F, B, fw):
+    """Periodogram.smooth(method="logmedian") (periodogram.py:260-284): exact window medians, reference summation order."""
+    from oracle import pg as opg
+    rng = np.random.default_rng(61)
+    freq = (np.arange(F) + 1) * 0.0137 if F != 777 else np.sort(rng.uniform(0.01, 300, F))
+    power = rng.chisquare(2, size=(B, F)) * (1 + 5.0 / (1 + freq))
+    power[0, 5] = np.nan                                            # nanmedian semantics
+    got = engine.pg_logmedian(freq, power, fw)
+    for b in range(B):
+        ref = opg.smooth_logmedian(freq, power[b], fw)
+        np.testing.assert_allclose(got[b], ref, rtol=1e-13, atol=0, equal_nan=True)
+    # an unsorted grid is handled by sorting (the window sets are order independent)
+    perm = rng.permutation(F)
+    got_p = engine.pg_logmedian(freq[perm], power[1][perm], fw)
+    if freq[perm][0] == freq.min() and freq[perm][-1] == freq.max():
+        np.testing.assert_allclose(got_p, got[1][perm], rtol=1e-13)

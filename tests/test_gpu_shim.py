@@ -436,3 +436,37 @@ def test_correct_batch_equals_loop():
         np.testing.assert_allclose(rc.corrected_lc.flux.value, rc_b.corrected_lc.flux.value, rtol=1e-12)
         ref = odet.regress(X, lc.flux.value, lc.flux_err.value)
         np.testing.assert_allclose(rc.coefficients, ref["coefficients"], rtol=1e-7, atol=1e-10)
+
+
+def test_smooth_and_flatten_periodogram():
+    """/root/reference/tests/test_periodogram.py:177-248 (logmedian on the GPU select kernel)."""
+    np.random.seed(42)
+    lc = LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1).normalize()
+    p = lc.to_periodogram(normalization="psd", freq_unit=u.microhertz)
+    assert all(p.smooth(method="boxkernel").frequency.value == p.frequency.value)
+    assert all(p.smooth(method="logmedian").frequency.value == p.frequency.value)
+    assert p.smooth().power.unit == p.power.unit
+    assert np.isclose(np.mean(p.smooth(method="logmedian").power.value), np.mean(p.power.value),
+                      atol=0.05 * np.mean(p.power.value))
+    with pytest.raises(ValueError):
+        p.smooth(method="boxkernel", filter_width=-5.0)
+    with pytest.raises(ValueError) as err:
+        p.smooth(method="boxkernel", filter_width=5.0 * u.day)
+    assert err.value.args[0] == "the `filter_width` parameter must have frequency units."
+    with pytest.raises(ValueError):
+        lc.to_periodogram(period=np.arange(1, 100)).smooth()
+    with pytest.raises(ValueError):
+        p.smooth(method="logmedian", filter_width=5.0 * u.day)
+    npts = 10000
+    np.random.seed(12069424)
+    lc = LightCurve(time=np.arange(npts), flux=np.random.normal(1, 0.1, npts), flux_err=np.zeros(npts) + 0.1).normalize()
+    p = lc.to_periodogram(normalization="psd", freq_unit=1 / u.day)
+    assert all(p.flatten(method="logmedian").frequency.value == p.frequency.value)
+    assert all(p.flatten(method="boxkernel").frequency.value == p.frequency.value)
+    assert np.isclose(np.mean(p.flatten(method="logmedian").power.value), 1.0, atol=0.05)
+    s_, b_ = p.flatten(return_trend=True)
+    assert all(b_.power.value == p.smooth(method="logmedian", filter_width=0.01).power.value)
+    assert all(s_.power.value == p.flatten().power.value)
+    str(s_)
+    assert len(p.bin(binsize=10, method="mean").frequency) == len(p.frequency) // 10
+    assert len(p.bin(binsize=10, method="median").frequency) == len(p.frequency) // 10

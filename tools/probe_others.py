@@ -11,7 +11,7 @@ from lightkurve_b200 import engine  # noqa: E402
 from oracle import bls as obls, detrend as odet, ls as ols  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0      # fraction of the full config batch
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["k1", "bls", "flatten", "regress"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["k1", "bls", "flatten", "regress", "pg"]
 engine.init(0)
 rng = np.random.default_rng(1003)
 
@@ -103,3 +103,17 @@ if "flatten" in which or "regress" in which:      # config 4
         print("K5 regress   : B=%d N=%d K=%d niters=5  Gram kernel %.1f ms (%.1f TFLOP/s fp64 of N*K^2 flop)  "
               "total wall %.1f ms  %.1f LC/s  cpu numpy %.1f LC/s  parity %s" % (
                   B, N, K, ker * 1e3, B * 2.0 * N * K * K / 2 / ker / 1e12, wall * 1e3, B / wall, 1 / cpu, ok))
+
+
+if "pg" in which:      # the step after config 2: log-median background of B periodograms of F = 1e5 bins
+    from oracle import pg as opg
+    B = max(4, int(1024 * scale))
+    F = 100000
+    freq = (np.arange(F) + 1) * (13.6 / F)
+    power = rng.chisquare(2, size=(B, F)) * (1 + 3.0 / (1 + freq))
+    out, wall, ker = timed(lambda: engine.pg_logmedian(freq, power, 0.01), reps=1)
+    t0 = time.perf_counter(); ref = opg.smooth_logmedian(freq, power[0], 0.01); cpu = time.perf_counter() - t0
+    ok = np.allclose(out[0], ref, rtol=1e-13, equal_nan=True)
+    nwin = len(engine.logmedian_windows(freq, 0.01)[0])
+    print("K6 logmedian : B=%d F=%d windows=%d  median kernel %.2f ms  %.1f periodograms/s (wall %.1f ms incl. H2D/D2H)  "
+          "cpu numpy %.2f s/periodogram  parity %s" % (B, F, nwin, ker * 1e3, B / ker, wall * 1e3, cpu, ok))
