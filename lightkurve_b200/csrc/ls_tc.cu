@@ -352,6 +352,243 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================
+// CTA-pair variant (cta_group::2).  Measured motivation: with one CTA per tile the M128 N256 K16 SS MMAs read
+// 12 KB of operands per 128 clk (96 B/clk) while the generators + TMA write another 64 KB per 1536-clk stage
+// (42 B/clk) - more than the 128 B/clk of one SM's shared memory, so the tensor pipe idles ~30 %.  A pair of
+// CTAs (two SMs of a TPC) computes a 256-frequency x 256-light-curve tile with M = 256 MMAs issued by the
+// leader: each SM supplies its own 128 design-matrix rows and only HALF of the flux tile, i.e. 8 KB per MMA
+// per SM and a 48 KB stage (4 stages fit).  Barriers: flux bytes of both CTAs and the "rows ready" arrivals of
+// both CTAs' generator warps are counted on the leader's mbarriers (remote arrives / cta_group::2 TMA);
+// tcgen05.commit multicasts "stage free" and "accumulators complete" to both CTAs.
+// =====================================================================================
+constexpr int T2_STAGES = 4;
+constexpr int T2_BNH = TC_BN / 2;                                  // light curves staged per CTA
+constexpr int T2_Y_TILE = T2_BNH * TC_BK * 2;                      // 8 KB
+constexpr int T2_STAGE_BYTES = 4 * TC_A_TILE + 2 * T2_Y_TILE;      // 48 KB
+constexpr size_t T2_SMEM = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + TC_SCRATCH;
+constexpr uint32_t T2_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+
+template <bool REGULAR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+ls_tc2_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const uint32_t raw = ptx::smem_u32(tc_smem_raw);
+  unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)T2_STAGES * T2_STAGE_BYTES);
+  uint64_t* full_y = bars;                         // [STAGES] (leader) flux bytes of BOTH CTAs landed
+  uint64_t* full_a = bars + T2_STAGES;             // [STAGES] (leader) generator warps of BOTH CTAs done
+  uint64_t* empty = bars + 2 * T2_STAGES;          // [STAGES] (each CTA) MMAs of the stage retired
+  uint64_t* acc_full = bars + 3 * T2_STAGES;       // (each CTA) a segment's accumulators are complete
+  uint64_t* acc_empty = bars + 3 * T2_STAGES + 1;  // (leader) the epilogue warps of BOTH CTAs drained TMEM
+  uint64_t* loc_a = bars + 3 * T2_STAGES + 2;      // [STAGES] (peer) its own generator warps done -> forwarded
+  uint64_t* loc_acc = bars + 4 * T2_STAGES + 2;    // (peer) its own epilogue warps done -> forwarded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * T2_STAGES + 3);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(bars) + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t f0 = (int64_t)blockIdx.x * TC_BM;           // this CTA's 128 frequency rows
+  const int b_tile = blockIdx.y * TC_BN;                    // the pair's 256 light curves
+  const int b_half = b_tile + (int)rank * T2_BNH;           // the half this CTA stages
+  const int nst = (int)(p.Npad / TC_BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      ptx::mbar_init(&full_y[s], 1);
+      ptx::mbar_init(&full_a[s], TC_GEN_WARPS + 1);      // own generator warps + the peer's forwarder
+      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&loc_a[s], TC_GEN_WARPS);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, TC_EPI_WARPS + 1);
+    ptx::mbar_init(loc_acc, TC_EPI_WARPS);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&ymap);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2cta(tmem_slot, 512);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                     // both CTAs' barriers are initialised before any remote arrive
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: this CTA's half of the flux hi/lo tiles =================
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % T2_STAGES;
+        if (it >= T2_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / T2_STAGES) - 1) & 1, 200);
+        unsigned char* st = smem + (size_t)s * T2_STAGE_BYTES;
+        if (leader) ptx::mbar_arrive_expect_tx(&full_y[s], 4 * T2_Y_TILE);        // 2 planes x 2 CTAs
+        const uint32_t bar = ptx::leader_addr(&full_y[s]);
+        ptx::tma_load_2d_2sm(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b_half, bar);
+        ptx::tma_load_2d_2sm(st + 4 * TC_A_TILE + T2_Y_TILE, &ymap, it * TC_BK, p.B + b_half, bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % T2_STAGES;
+        const uint32_t ph = (it / T2_STAGES) & 1;
+        const int seg = it / p.seg_stages;
+        const bool seg_first = (it - seg * p.seg_stages) == 0;
+        const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
+        ptx::mbar_wait_sleep(&full_y[s], ph, 40);
+        ptx::mbar_wait_cluster_sleep(&full_a[s], ph, 40);
+        if (seg_first && seg > 0) ptx::mbar_wait_cluster_sleep(acc_empty, (seg - 1) & 1, 40);   // TMEM drained
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * T2_STAGE_BYTES);
+        const uint32_t a_ch = sa, a_cl = sa + TC_A_TILE, a_sh = sa + 2 * TC_A_TILE, a_sl = sa + 3 * TC_A_TILE;
+        const uint32_t y_h = sa + 4 * TC_A_TILE, y_l = y_h + T2_Y_TILE;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t ko = k * 32;
+          const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
+          const uint64_t dyh = tc_smem_desc(y_h + ko), dyl = tc_smem_desc(y_l + ko);
+          ptx::umma_f16_ss_2cta(tmem, tc_smem_desc(a_ch + ko), dyh, T2_IDESC, first);
+          ptx::umma_f16_ss_2cta(tmem, tc_smem_desc(a_ch + ko), dyl, T2_IDESC, 1u);
+          ptx::umma_f16_ss_2cta(tmem, tc_smem_desc(a_cl + ko), dyh, T2_IDESC, 1u);
+          ptx::umma_f16_ss_2cta(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyh, T2_IDESC, first);
+          ptx::umma_f16_ss_2cta(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyl, T2_IDESC, 1u);
+          ptx::umma_f16_ss_2cta(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, T2_IDESC, 1u);
+        }
+        ptx::umma_commit_2cta(&empty[s]);          // both CTAs' stage s reusable once these MMAs retire
+        if (seg_last) ptx::umma_commit_2cta(acc_full);
+      }
+    } else if (!leader && lane == 0) {
+      // ---- peer CTA: forward "my rows are ready" / "my TMEM is drained" to the leader's barriers.  A remote
+      // release-arrive costs a MEMBAR.ALL.GPU (measured: 12 % of all stall samples when every generator warp
+      // did it); here it is paid once per stage by an otherwise idle thread with no memory traffic of its own.
+      const uint32_t full_a_leader = ptx::leader_addr(&full_a[0]);
+      const uint32_t acc_empty_leader = ptx::leader_addr(acc_empty);
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % T2_STAGES;
+        ptx::mbar_wait_sleep(&loc_a[s], (it / T2_STAGES) & 1, 40);
+        ptx::mbar_arrive_cluster(full_a_leader + 8u * (uint32_t)s);
+        const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
+        if (seg_last) {
+          ptx::mbar_wait_sleep(loc_acc, (it / p.seg_stages) & 1, 200);
+          ptx::mbar_arrive_cluster(acc_empty_leader);
+        }
+      }
+    }
+  } else if (warp < 2 + TC_GEN_WARPS) {
+    // ================= design-matrix generators (as in ls_tc_kernel; "rows ready" goes to the leader) =========
+    const int gw = warp - 2;
+    const int row = (gw & 3) * 32 + lane;
+    const int chunk = gw >> 2;
+    const uint32_t row_off = (uint32_t)row * 64u + ((((uint32_t)chunk) ^ (uint32_t)((row >> 1) & 3)) << 4);
+    ulonglong2* my_scr = reinterpret_cast<ulonglong2*>(scratch + gw * 128);
+    const unsigned long long kfreq = (unsigned long long)(f0 + row);
+    const double fr = REGULAR ? (p.f0 + (double)(f0 + row) * p.df) : ((f0 + row < p.F) ? p.freq[f0 + row] : 0.0);
+    const bool low_row = fabs(fr) <= p.lowf_max;
+    ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
+    auto prefetch = [&](int it) {
+      if (lane < 8) {
+        const int64_t n = (int64_t)it * TC_BK + chunk * 8 + lane;
+        if (REGULAR) nxt = p.tab[n];
+        else nxt.x = (unsigned long long)__double_as_longlong(p.t[n]);
+      }
+    };
+    prefetch(0);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % T2_STAGES;
+      if (lane < 8) my_scr[lane] = nxt;
+      __syncwarp();
+      if (it + 1 < nst) prefetch(it + 1);
+      if (it >= T2_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / T2_STAGES) - 1) & 1, 100);
+      unsigned char* st = smem + (size_t)s * T2_STAGE_BYTES;
+      uint32_t ch[4], cl[4], sh[4], sl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float s0, c0, s1, c1;
+        const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
+        if (REGULAR) {
+          if (low_row) {
+            ls_sincos_fixed_low(e0.x + kfreq * e0.y, s0, c0);
+            ls_sincos_fixed_low(e1.x + kfreq * e1.y, s1, c1);
+          } else {
+            ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
+            ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+          }
+        } else {
+          if (low_row) {
+            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e0.x), s0, c0);
+            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e1.x), s1, c1);
+          } else {
+            ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
+            ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
+          }
+        }
+        tc_split2(c0, c1, s0, s1, ch[q], cl[q], sh[q], sl[q]);
+      }
+      *reinterpret_cast<uint4*>(st + row_off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+      *reinterpret_cast<uint4*>(st + TC_A_TILE + row_off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+      *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + row_off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+      *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + row_off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(leader ? &full_a[s] : &loc_a[s]);
+    }
+  } else {
+    // ================= epilogue warps (own TMEM: this CTA's 128 frequency rows x the pair's 256 light curves) ====
+    const int quad = warp & 3;
+    const int64_t f = f0 + quad * 32 + lane;
+    const bool f_ok = f < p.F;
+    const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
+    const float2 r2 = f_ok ? p.rot2[f] : make_float2(0.f, 0.f);
+    const bool low_out = f_ok && fabs(p.freq[f]) <= p.lowf_max;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const float Nf = (float)p.N;
+    const int64_t plane = (int64_t)p.B * p.F;
+    for (int seg = 0; seg < p.nseg; ++seg) {
+      ptx::mbar_wait_sleep(acc_full, seg & 1, 500);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+        uint32_t vc[16], vs[16];
+        ptx::tmem_ld_32x32b_x16(lane_addr + c0, vc);
+        ptx::tmem_ld_32x32b_x16(lane_addr + TC_BN + c0, vs);
+        ptx::tmem_ld_wait();
+        if (f_ok) {
+          if (p.nseg == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int b = b_tile + c0 + j;
+              if (b < p.B) {
+                const float h = p.inv_scale[b];
+                p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
+                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale, low_out);
+              }
+            }
+          } else {
+            float* pc = p.part + (int64_t)(seg * 2) * plane + (int64_t)(b_tile + c0) * p.F + f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (b_tile + c0 + j < p.B) {
+                pc[(int64_t)j * p.F] = __uint_as_float(vc[j]);
+                pc[plane + (int64_t)j * p.F] = __uint_as_float(vs[j]);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(leader ? acc_empty : loc_acc);
+    }
+  }
+  __syncthreads();
+  ptx::cluster_sync();                     // nobody exits (or frees TMEM) while the peer may still touch this CTA
+  if (warp == 1) ptx::tmem_dealloc_2cta(tmem, 512);
+}
+
 // rot / rot2 from the window sums accumulated inside ls_tc_kernel (regular grids).  The padding
 // cadences (phase 0: cos = 1, sin = 0) are removed analytically.  Low-frequency rows are NOT
 // written here: ls_window_kernel's full-fp64 path owns them.
@@ -438,7 +675,8 @@ bool ls_tc_window_in_kernel(int64_t Npad, bool regular) {
   // Measured on B200 (bench c2): folding the sums in costs the tc kernel more (65 -> 71 ms: the
   // generator warps are already the co-bottleneck) than the separate 4.4 ms window kernel, so this
   // is opt-in.
-  return regular && (Npad / TC_BK) > seg_cap && getenv("LKB_TC_WINDOW_IN_KERNEL") != nullptr;
+  const bool pair_off = !(getenv("LKB_TC_2CTA") != nullptr && atoi(getenv("LKB_TC_2CTA")) != 0);  // 1-CTA kernel only
+  return pair_off && regular && (Npad / TC_BK) > seg_cap && getenv("LKB_TC_WINDOW_IN_KERNEL") != nullptr;
 }
 
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
@@ -465,10 +703,25 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)cr); return LKB_E_CUDA; }
 
+  // CTA-pair kernel (LKB_TC_2CTA=1): half-height flux boxes, one per CTA of the pair.  Measured on the bench
+  // (config 2, same box, back to back): 72.6 ms at 1702 MHz vs 71.2 ms at 1590 MHz for the one-CTA kernel - both
+  // sit on the board's power cap (the pair variant relieves shared-memory bandwidth, the clocks drop until the
+  // energy per step is the same), so the simpler one-CTA kernel stays the default.
+  const bool use_pair = getenv("LKB_TC_2CTA") != nullptr && atoi(getenv("LKB_TC_2CTA")) != 0;
+  CUtensorMap map2;
+  if (use_pair) {
+    const cuuint32_t box2[2] = {(cuuint32_t)TC_BK, (cuuint32_t)T2_BNH};
+    cr = enc(&map2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d_yhl, dims, strides, box2, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)cr); return LKB_E_CUDA; }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
     attr_set = true;
   }
   const bool regular = d_tab != nullptr;
@@ -491,8 +744,14 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   if (nseg == 1) LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));   // direct epilogue needs rot
   prof_begin(st);
-  if (regular) ls_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
-  else ls_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  if (use_pair) {
+    dim3 grid2(2u * (unsigned)((F + 2 * TC_BM - 1) / (2 * TC_BM)), grid.y);      // pairs of 128-row CTAs
+    if (regular) ls_tc2_kernel<true><<<grid2, TC_THREADS, T2_SMEM, st>>>(map2, p);
+    else ls_tc2_kernel<false><<<grid2, TC_THREADS, T2_SMEM, st>>>(map2, p);
+  } else {
+    if (regular) ls_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+    else ls_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, p);
+  }
   prof_end(st);
   LKB_LAUNCH_CHECK();
   if (p.wsum) {

@@ -188,6 +188,19 @@ def test_ls_tcgen05_long_accumulation(engine):
         assert_ls_close(sim[b], p)
 
 
+def test_ls_tcgen05_cta_pair_variant(engine, monkeypatch):
+    """The cta_group::2 kernel (two SMs per 256-frequency tile, opt-in) must meet the same tolerance."""
+    monkeypatch.setenv("LKB_TC_2CTA", "1")
+    rng = np.random.default_rng(23)
+    B, N, F = 300, 4100, 700                     # ragged tiles in every dimension, 2 flux tiles, 3 frequency pairs
+    t = np.sort(rng.uniform(0, 80, N))
+    Y = (1 + 1e-3 * np.sin(2 * np.pi * 1.7 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
+    freq = 0.01 + np.arange(F) * 0.01
+    out = engine.ls_power_shared(t, Y, freq, "psd_raw", algo="tcgen05")
+    for b in (0, 127, 128, 255, 256, 299):
+        assert_ls_close(out[b], ols.ls_slow_psd(t, Y[b].astype(np.float64), freq))
+
+
 def test_ls_shared_equals_ragged(engine):
     rng = np.random.default_rng(22)
     N, B, F = 1500, 9, 200
