@@ -214,8 +214,22 @@ flatten_kernel(const double* __restrict__ time, const double* __restrict__ flux,
     __syncthreads();
     for (int g = threadIdx.x; g < n; g += blockDim.x) {
       const double xq = t[g];
-      // np.searchsorted(xp, xq, side="left")
-      int lo = 0, hi = ms;
+      // np.searchsorted(xp, xq, side="left"): the survivors are a thinned copy of the cadences, so the answer
+      // sits next to g * ms / n - gallop out from there (2-4 dependent loads instead of log2(ms) = 16)
+      int lo, hi;
+      {
+        const int g0 = min(ms - 1, (int)(((long long)g * ms) / n));
+        int step = 1;
+        if (xs[g0] < xq) {
+          lo = g0 + 1;
+          hi = min(ms, lo + step);
+          while (hi < ms && xs[hi] < xq) { lo = hi + 1; step <<= 1; hi = min(ms, lo + step); }
+        } else {
+          hi = g0;
+          lo = max(0, hi - step);
+          while (lo > 0 && xs[lo] >= xq) { hi = lo; step <<= 1; lo = max(0, hi - step); }
+        }
+      }
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (xs[mid] < xq) lo = mid + 1; else hi = mid;

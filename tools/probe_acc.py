@@ -15,15 +15,19 @@ Y = (1 + 10 ** rng.uniform(-4, -2, (B, 1)) * np.sin(2 * np.pi * rng.uniform(0.05
 freq = np.sort(rng.uniform(0.01, 13.6, F))
 refs = {b: np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq)) * np.sqrt(4.0 / N) for b in (0, 33, 69)}
 sim = engine.ls_power_shared(t, Y, freq, "amplitude", algo="simt")
-for seg in (100000, 512, 256, 128, 64, 32):
+modes = [(int(a), 0) for a in os.environ.get("PROBE_SEGS", "100000,512,256,128,64,32").split(",")]
+modes += [(64, 1), (128, 1)]                      # FP8-residual variant (LKB_TC_FP8LO=1)
+for seg, fp8 in modes:
     os.environ["LKB_TC_SEG_STAGES"] = str(seg)
+    os.environ["LKB_TC_FP8LO"] = str(fp8)
     out = engine.ls_power_shared(t, Y, freq, "amplitude", algo="tcgen05")
     row = []
     for b, ref in refs.items():
         e = out[b] - ref
         row.append("lc%d mean rel %.2e max|rel| %.2e excess %.2f" % (b, np.mean(e / ref), np.max(np.abs(e / ref)),
                    np.max(np.abs(e) / (1e-5 * ref.max() + 1e-4 * ref))))
-    print("seg_stages %6d: %s" % (seg, " | ".join(row)))
+    print("seg_stages %6d%s: %s" % (seg, " fp8lo" if fp8 else "      ", " | ".join(row)))
+os.environ["LKB_TC_FP8LO"] = "0"
 row = []
 for b, ref in refs.items():
     e = sim[b] - ref
