@@ -126,6 +126,7 @@ struct TcParams {
   double* wsum;             // [F, 4 chunks, 4] window sums (S, C, CC, SC) accumulated by the generators of
                             // the blockIdx.y == 0 CTAs (nullptr: the separate window kernel is used)
   double lowf_max;          // frequencies <= this are "low rows": design matrix carries cos - 1
+  int debug;                // LKB_TC_DEBUG bit mask: timing experiments only (results are wrong when set)
   float low_mul;            // low rows are generated with TC_A_SCALE / low_mul (1, or 2 in the FP8 variant)
   double f0, df;            // regular grid (REGULAR kernels)
 };
@@ -163,6 +164,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
   const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
   const int b0 = blockIdx.y * TC_BN;
   const int nst = (int)(p.Npad / TC_BK);           // all stages; segments are p.seg_stages long
+  const uint32_t gen_ns = (p.debug & 8) ? 0u : ((p.debug & 32) ? 20u : 100u), mma_ns = (p.debug & 16) ? 0u : 40u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -205,8 +207,8 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
         const int seg = it / p.seg_stages;
         const bool seg_first = (it - seg * p.seg_stages) == 0;
         const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
-        ptx::mbar_wait_sleep(&full_y[s], ph, 40);
-        ptx::mbar_wait_sleep(&full_a[s], ph, 40);
+        ptx::mbar_wait_sleep(&full_y[s], ph, mma_ns);
+        ptx::mbar_wait_sleep(&full_a[s], ph, mma_ns);
         if (seg_first && seg > 0) ptx::mbar_wait_sleep(acc_empty, (seg - 1) & 1, 40);   // TMEM drained
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
@@ -219,12 +221,16 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
           const uint64_t dyh = tc_smem_desc(y_h + ko), dyl = tc_smem_desc(y_l + ko);
           // cos accumulator: columns [0, 256)
           ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyh, TC_IDESC, first);
-          ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyl, TC_IDESC, 1u);
-          ptx::umma_f16_ss(tmem, tc_smem_desc(a_cl + ko), dyh, TC_IDESC, 1u);
+          if (!(p.debug & 1)) {
+            ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyl, TC_IDESC, 1u);
+            ptx::umma_f16_ss(tmem, tc_smem_desc(a_cl + ko), dyh, TC_IDESC, 1u);
+          }
           // sin accumulator: columns [256, 512)
           ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyh, TC_IDESC, first);
-          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyl, TC_IDESC, 1u);
-          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, TC_IDESC, 1u);
+          if (!(p.debug & 1)) {
+            ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyl, TC_IDESC, 1u);
+            ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, TC_IDESC, 1u);
+          }
         }
         ptx::umma_commit(&empty[s]);          // smem stage reusable once these MMAs retire
         if (seg_last) ptx::umma_commit(acc_full);
@@ -261,11 +267,12 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       if (lane < 8) my_scr[lane] = nxt;
       __syncwarp();
       if (it + 1 < nst) prefetch(it + 1);
-      if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, 100);
+      if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, gen_ns);
       unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-      uint32_t ch[4], cl[4], sh[4], sl[4];
+      uint32_t ch[4] = {0, 0, 0, 0}, cl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, sl[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        if (p.debug & 2) break;
         float s0, c0, s1, c1;
         const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
         if (REGULAR) {
@@ -302,7 +309,7 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
       *reinterpret_cast<uint4*>(st + TC_A_TILE + row_off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
       *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + row_off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
       *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + row_off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
-      ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      if (!(p.debug & 4)) ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full_a[s]);
     }
@@ -323,6 +330,225 @@ ls_tc_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
     const int64_t plane = (int64_t)p.B * p.F;
     for (int seg = 0; seg < p.nseg; ++seg) {
       ptx::mbar_wait_sleep(acc_full, seg & 1, 500);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+        uint32_t vc[16], vs[16];
+        ptx::tmem_ld_32x32b_x16(lane_addr + c0, vc);
+        ptx::tmem_ld_32x32b_x16(lane_addr + TC_BN + c0, vs);
+        ptx::tmem_ld_wait();
+        if (f_ok) {
+          if (p.nseg == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int b = b0 + c0 + j;
+              if (b < p.B) {
+                const float h = p.inv_scale[b];
+                p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
+                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale, low_out);
+              }
+            }
+          } else {
+            float* pc = p.part + (int64_t)(seg * 2) * plane + (int64_t)(b0 + c0) * p.F + f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (b0 + c0 + j < p.B) {
+                pc[(int64_t)j * p.F] = __uint_as_float(vc[j]);
+                pc[plane + (int64_t)j * p.F] = __uint_as_float(vs[j]);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================
+// Grouped-generator variant.  Timing experiments on the kernel above (LKB_TC_DEBUG, bench config 2) showed its
+// step time is the SUM of three parts - 32.6 ms with neither design-matrix math nor the correction MMAs,
+// +22.9 ms for the math, +20.2 ms for the 8 extra MMAs per stage - i.e. the generator warps are the serial
+// bottleneck: all 16 of them fill the SAME stage in lock step, so the fixed per-stage costs (barrier wake-up,
+// table hand-off, async-proxy fence, arrive) are paid once per stage on the critical path.  Here the generator
+// warps form TG_GROUPS groups that fill alternate stages (each thread: one row x TG_GROUPS chunks), so one group's
+// fixed costs overlap the other group's math.
+// =====================================================================================
+constexpr int TG_GROUPS = 2;
+constexpr size_t TG_SMEM = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256 + 2 * TC_SCRATCH;
+
+template <bool REGULAR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ls_tcg_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  // 1024-byte aligned carve-up (swizzle atoms need their natural alignment)
+  const uint32_t raw = ptx::smem_u32(tc_smem_raw);
+  unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full_y = bars;                         // [STAGES] TMA bytes landed
+  uint64_t* full_a = bars + TC_STAGES;             // [STAGES] generator warps done
+  uint64_t* empty = bars + 2 * TC_STAGES;          // [STAGES] MMAs of the stage retired
+  uint64_t* acc_full = bars + 3 * TC_STAGES;       // a segment's accumulators are complete
+  uint64_t* acc_empty = bars + 3 * TC_STAGES + 1;  // the epilogue warps have drained TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2);
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(bars) + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
+  const int b0 = blockIdx.y * TC_BN;
+  const int nst = (int)(p.Npad / TC_BK);           // all stages; segments are p.seg_stages long
+  const uint32_t park_ns = (p.debug & 64) ? 0u : 20000u;     // suspend-time hint of the barrier waits
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      ptx::mbar_init(&full_y[s], 1);
+      ptx::mbar_init(&full_a[s], TC_GEN_WARPS / TG_GROUPS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, TC_EPI_WARPS);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&ymap);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: flux hi/lo tiles =================
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % TC_STAGES;
+        if (it >= TC_STAGES) ptx::mbar_wait_park(&empty[s], ((it / TC_STAGES) - 1) & 1, park_ns);
+        unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_y[s], 2 * TC_Y_TILE);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE, &ymap, it * TC_BK, b0, &full_y[s]);
+        ptx::tma_load_2d(st + 4 * TC_A_TILE + TC_Y_TILE, &ymap, it * TC_BK, p.B + b0, &full_y[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        const int seg = it / p.seg_stages;
+        const bool seg_first = (it - seg * p.seg_stages) == 0;
+        const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
+        ptx::mbar_wait_park(&full_y[s], ph, park_ns);
+        ptx::mbar_wait_park(&full_a[s], ph, park_ns);
+        if (seg_first && seg > 0) ptx::mbar_wait_park(acc_empty, (seg - 1) & 1, park_ns);   // TMEM drained
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+        const uint32_t a_ch = sa, a_cl = sa + TC_A_TILE, a_sh = sa + 2 * TC_A_TILE, a_sl = sa + 3 * TC_A_TILE;
+        const uint32_t y_h = sa + 4 * TC_A_TILE, y_l = y_h + TC_Y_TILE;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t ko = k * 32;                      // 16 fp16 = 32 bytes along K inside the 64 B row
+          const uint32_t first = (seg_first && k == 0) ? 0u : 1u;
+          const uint64_t dyh = tc_smem_desc(y_h + ko), dyl = tc_smem_desc(y_l + ko);
+          // cos accumulator: columns [0, 256)
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyh, TC_IDESC, first);
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_ch + ko), dyl, TC_IDESC, 1u);
+          ptx::umma_f16_ss(tmem, tc_smem_desc(a_cl + ko), dyh, TC_IDESC, 1u);
+          // sin accumulator: columns [256, 512)
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyh, TC_IDESC, first);
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sh + ko), dyl, TC_IDESC, 1u);
+          ptx::umma_f16_ss(tmem + TC_BN, tc_smem_desc(a_sl + ko), dyh, TC_IDESC, 1u);
+        }
+        ptx::umma_commit(&empty[s]);          // smem stage reusable once these MMAs retire
+        if (seg_last) ptx::umma_commit(acc_full);
+      }
+    }
+  } else if (warp < 2 + TC_GEN_WARPS) {
+    // ================= design-matrix generators =================
+    // thread -> (frequency row, one 16-byte chunk = 8 cadences of the stage); a warp covers 32 rows of
+    // ONE chunk, so its 8 cadences' table entries are prefetched by lanes 0..7 one stage ahead and
+    // broadcast through a private shared-memory scratch (no L2 latency on the critical path).
+    const int gw = warp - 2;                              // 0..15
+    const int group = gw / (TC_GEN_WARPS / TG_GROUPS);    // which stages this warp fills: it = group (mod TG_GROUPS)
+    const int gw8 = gw % (TC_GEN_WARPS / TG_GROUPS);
+    const int row = (gw8 & 3) * 32 + lane;                // frequency row inside the tile
+    const int cb = (gw8 >> 2) * TG_GROUPS;                // first of this thread's TG_GROUPS 8-cadence chunks
+    ulonglong2* my_scr = reinterpret_cast<ulonglong2*>(scratch + gw * 256);
+    const unsigned long long kfreq = (unsigned long long)(f0 + row);          // global frequency index
+    const double fr = REGULAR ? (p.f0 + (double)(f0 + row) * p.df) : ((f0 + row < p.F) ? p.freq[f0 + row] : 0.0);
+    const bool low_row = fabs(fr) <= p.lowf_max;
+    ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
+    auto prefetch = [&](int it) {
+      if (lane < 8 * TG_GROUPS) {
+        const int64_t n = (int64_t)it * TC_BK + cb * 8 + lane;
+        if (REGULAR) nxt = p.tab[n];
+        else nxt.x = (unsigned long long)__double_as_longlong(p.t[n]);
+      }
+    };
+    if (group < nst) prefetch(group);
+    for (int it = group; it < nst; it += TG_GROUPS) {
+      const int s = it % TC_STAGES;
+      if (lane < 8 * TG_GROUPS) my_scr[lane] = nxt;
+      __syncwarp();
+      if (it + TG_GROUPS < nst) prefetch(it + TG_GROUPS);
+      if (it >= TC_STAGES) ptx::mbar_wait_park(&empty[s], ((it / TC_STAGES) - 1) & 1, park_ns);
+      unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+#pragma unroll
+      for (int cc = 0; cc < TG_GROUPS; ++cc) {
+        const int chunk = cb + cc;
+        const uint32_t row_off = (uint32_t)row * 64u + ((((uint32_t)chunk) ^ (uint32_t)((row >> 1) & 3)) << 4);
+        uint32_t ch[4], cl[4], sh[4], sl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float s0, c0, s1, c1;
+          const ulonglong2 e0 = my_scr[cc * 8 + 2 * q], e1 = my_scr[cc * 8 + 2 * q + 1];
+          if (REGULAR) {
+            if (low_row) {
+              ls_sincos_fixed_low(e0.x + kfreq * e0.y, s0, c0);
+              ls_sincos_fixed_low(e1.x + kfreq * e1.y, s1, c1);
+            } else {
+              ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
+              ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
+            }
+          } else {
+            if (low_row) {
+              ls_sincos_cycles_low(fr * __longlong_as_double((long long)e0.x), s0, c0);
+              ls_sincos_cycles_low(fr * __longlong_as_double((long long)e1.x), s1, c1);
+            } else {
+              ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
+              ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
+            }
+          }
+          tc_split2(c0, c1, s0, s1, ch[q], cl[q], sh[q], sl[q]);
+        }
+        *reinterpret_cast<uint4*>(st + row_off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+        *reinterpret_cast<uint4*>(st + TC_A_TILE + row_off) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+        *reinterpret_cast<uint4*>(st + 2 * TC_A_TILE + row_off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+        *reinterpret_cast<uint4*>(st + 3 * TC_A_TILE + row_off) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+      }
+      ptx::fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_a[s]);
+    }
+  } else {
+    // ================= epilogue warps (TMEM lane quadrant = warp % 4) =================
+    const int quad = warp & 3;
+    const int64_t f = f0 + quad * 32 + lane;
+    const bool f_ok = f < p.F;
+    const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
+    const float2 r2 = f_ok ? p.rot2[f] : make_float2(0.f, 0.f);
+    const bool low_out = f_ok && fabs(p.freq[f]) <= p.lowf_max;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const float Nf = (float)p.N;
+    const int64_t plane = (int64_t)p.B * p.F;
+    for (int seg = 0; seg < p.nseg; ++seg) {
+      ptx::mbar_wait_park(acc_full, seg & 1, park_ns);
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < TC_BN; c0 += 16) {
@@ -979,6 +1205,8 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   }
   static bool attr_set = false;
   if (!attr_set) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -1003,6 +1231,7 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   p.seg_stages = seg_stages; p.nseg = nseg;
   p.lowf_max = lowf_max; p.f0 = grid_f0; p.df = grid_df;
   p.low_mul = use_fp8 ? 2.0f : 1.0f;
+  p.debug = getenv("LKB_TC_DEBUG") ? atoi(getenv("LKB_TC_DEBUG")) : 0;
   p.wsum = nullptr;
   if (window_in_kernel && nseg > 1 && regular) LKB_TRY(ws_get_t<double>(WS_P, (size_t)F * 16, &p.wsum));
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
@@ -1011,6 +1240,11 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   if (use_fp8) {
     if (regular) ls_tc8_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, map8, p);
     else ls_tc8_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, map8, p);
+  } else if (!use_pair && !(getenv("LKB_TC_GEN_GROUPS") != nullptr && atoi(getenv("LKB_TC_GEN_GROUPS")) == 1) &&
+             !window_in_kernel && p.debug == 0) {
+    // default: generator warps in two groups that fill alternate stages (LKB_TC_GEN_GROUPS=1: lock-step kernel)
+    if (regular) ls_tcg_kernel<true><<<grid, TC_THREADS, TG_SMEM, st>>>(map, p);
+    else ls_tcg_kernel<false><<<grid, TC_THREADS, TG_SMEM, st>>>(map, p);
   } else if (use_pair) {
     dim3 grid2(2u * (unsigned)((F + 2 * TC_BM - 1) / (2 * TC_BM)), grid.y);      // pairs of 128-row CTAs
     if (regular) ls_tc2_kernel<true><<<grid2, TC_THREADS, T2_SMEM, st>>>(map2, p);
