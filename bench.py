@@ -14,7 +14,7 @@ One JSON line on stdout (rank 0).  A "step" = one pass of lkb_ls_power_shared ov
   value   : whole-job F*N*B_total / time, inputs resident in HBM (CUDA events, max over ranks)
   e2e     : same metric through the same C-ABI call with HOST buffers: pinned H2D of the flux
             matrix and D2H of the power array inside the timed region
-  roofline: tensor roofline of the dominant kernel (ls_tc_kernel): algorithmic flops 4*F*N*B per
+  roofline: tensor roofline of the dominant kernel (ls_tcg_kernel): algorithmic flops 4*F*N*B per
             launch / CUDA-event duration of that kernel, vs MEASURED_PEAKS.json bf16 sustained
   cpu_baseline: the oracle port of the reference default (astropy "fast" extirpolation+FFT),
             timed on a bounded sample of the same workload on this box's host cores.
@@ -332,11 +332,11 @@ def main():
         try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "bench_kernel_traffic.json")))
             if args.workload == "c2" and args.algo != "simt":
-                traffic = tj["ls_tc_kernel"]["traffic_bytes_per_launch"]
+                traffic = tj["ls_tcg_kernel"]["traffic_bytes_per_launch"]
         except Exception:
             pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": traffic, "kernel": "ls_tc_kernel" if args.algo != "simt"
+                    "frac": achieved / peak_tf, "traffic": traffic, "kernel": "ls_tcg_kernel" if args.algo != "simt"
                     else "ls_shared_simt_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
                     "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
         cpu = None
