@@ -68,6 +68,19 @@ int aux_stream_get(cudaStream_t* aux, cudaEvent_t* ev_fork, cudaEvent_t* ev_join
   return LKB_OK;
 }
 
+// two copy streams + a few events for the chunk-pipelined host-mode paths
+static cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
+static cudaEvent_t g_pipe_ev[16];
+int pipe_streams_get(cudaStream_t* h2d, cudaStream_t* d2h, cudaEvent_t** events, int* n_events) {
+  if (!g_h2d) {
+    LKB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+    LKB_CUDA_CHECK(cudaStreamCreateWithFlags(&g_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) LKB_CUDA_CHECK(cudaEventCreateWithFlags(&g_pipe_ev[i], cudaEventDisableTiming));
+  }
+  *h2d = g_h2d; *d2h = g_d2h; *events = g_pipe_ev; *n_events = 16;
+  return LKB_OK;
+}
+
 // ---- dominant-kernel profiling ring ----
 constexpr int PROF_MAX = 512;
 static bool g_prof_on = false;

@@ -74,6 +74,7 @@ void prof_end(cudaStream_t st);
 // Library-owned side stream + fork/join events: lets a small independent kernel (the LS window
 // terms) run concurrently with the long contraction kernel on the caller's stream.
 int aux_stream_get(cudaStream_t* aux, cudaEvent_t* ev_fork, cudaEvent_t* ev_join);
+int pipe_streams_get(cudaStream_t* h2d, cudaStream_t* d2h, cudaEvent_t** events, int* n_events);
 
 // Stage a host buffer into the pool (or pass a device pointer through).
 template <typename T>

@@ -825,7 +825,7 @@ int ls_power_chi2(const double* t, const void* y, int y_dtype, const int64_t* h_
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, float4* d_rot, float2* d_rot2,
                  bool window_in_kernel, double lowf_max, double grid_f0, double grid_df, int normalization,
-                 double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready);   // ls_tc.cu
+                 double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready, int ws_alt = 0);   // ls_tc.cu
 bool ls_tc_window_in_kernel(int64_t Npad, bool regular);
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 
@@ -844,7 +844,18 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   const double *dt_in = nullptr, *d_freq = nullptr;
   const void* dy_in = nullptr;
   LKB_TRY(stage_in<double>(mem, WS_IN0, t, N, &dt_in, st));
-  {
+  // Host-mode calls on the tensor path are pipelined over chunks of light curves: the flux rows of chunk c + 1
+  // go up and the power rows of chunk c - 1 come down (two copy streams) while chunk c is computed.  Fully
+  // asynchronous when the caller's buffers are page-locked; with pageable numpy memory the copies still work,
+  // they just overlap less.
+  constexpr int PIPE_CHUNK = 256;                    // one light-curve tile of the tensor kernel
+  const bool pipelined = mem == LKB_MEM_HOST && B > PIPE_CHUNK && !getenv("LKB_LS_NO_PIPELINE") &&
+                         (algo == LKB_LS_ALGO_TCGEN05 || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
+  unsigned char* d_ystage = nullptr;
+  if (pipelined) {
+    LKB_TRY(ws_get_t<unsigned char>(WS_IN1, (size_t)B * N * ysz, &d_ystage));
+    dy_in = d_ystage;
+  } else {
     const unsigned char* tmp = nullptr;
     LKB_TRY(stage_in<unsigned char>(mem, WS_IN1, (const unsigned char*)y, (size_t)B * N * ysz, &tmp, st));
     dy_in = tmp;
@@ -873,11 +884,18 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
 
   ls_shift_time_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(dt_in, N, Npad, d_t);
   LKB_LAUNCH_CHECK();
-  if (y_dtype == LKB_DTYPE_F32)
-    ls_prep_shared_kernel<float><<<B, 256, 0, st>>>((const float*)dy_in, N, Npad, d_yc, d_absmax, d_ysumf);
-  else
-    ls_prep_shared_kernel<double><<<B, 256, 0, st>>>((const double*)dy_in, N, Npad, d_yc, d_absmax, d_ysumf);
-  LKB_LAUNCH_CHECK();
+  auto prep_rows = [&](int b_lo, int nb) {
+    if (y_dtype == LKB_DTYPE_F32)
+      ls_prep_shared_kernel<float><<<nb, 256, 0, st>>>((const float*)dy_in + (size_t)b_lo * N, N, Npad,
+                                                       d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, d_ysumf + b_lo);
+    else
+      ls_prep_shared_kernel<double><<<nb, 256, 0, st>>>((const double*)dy_in + (size_t)b_lo * N, N, Npad,
+                                                        d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, d_ysumf + b_lo);
+  };
+  if (!pipelined) {
+    prep_rows(0, B);
+    LKB_LAUNCH_CHECK();
+  }
   // One small device->host read-back per call: grid regularity, f0, f1 and the baseline t[N-1].
   // Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
   // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain.
@@ -935,6 +953,53 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   LKB_LAUNCH_CHECK();
   LKB_CUDA_CHECK(cudaEventRecord(ev_join, aux));
 
+  if (use_tc && pipelined) {
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t* ev;
+    int nev;
+    LKB_TRY(pipe_streams_get(&s_h2d, &s_d2h, &ev, &nev));
+    const int nchunk = (B + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    // chunks alternate between two compute streams (and two workspace sets): the last, partly filled wave of one
+    // chunk's tensor kernel (782 CTAs on 148 SMs) overlaps the first wave of the next chunk
+    cudaStream_t cs[2] = {st, st};
+    {
+      cudaStream_t a2; cudaEvent_t f2, j2;
+      LKB_TRY(aux_stream_get(&a2, &f2, &j2));
+      if (!getenv("LKB_LS_ONE_COMPUTE_STREAM")) cs[1] = a2;
+    }
+    // nothing may start before the earlier work on `st` (prologue kernels, window terms) is done
+    LKB_CUDA_CHECK(cudaEventRecord(ev[0], st));
+    LKB_CUDA_CHECK(cudaStreamWaitEvent(s_h2d, ev[0], 0));
+    LKB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, ev[0], 0));
+    if (cs[1] != st) LKB_CUDA_CHECK(cudaStreamWaitEvent(cs[1], ev[0], 0));
+    for (int c = 0; c < nchunk; ++c) {
+      const int b_lo = c * PIPE_CHUNK, nb = min(PIPE_CHUNK, B - b_lo);
+      cudaStream_t sc = cs[c & 1];
+      cudaEvent_t e_in = ev[1 + (2 * c) % (nev - 1)], e_out = ev[1 + (2 * c + 1) % (nev - 1)];
+      LKB_CUDA_CHECK(cudaMemcpyAsync(d_ystage + (size_t)b_lo * N * ysz, (const unsigned char*)y + (size_t)b_lo * N * ysz,
+                                     (size_t)nb * N * ysz, cudaMemcpyHostToDevice, s_h2d));
+      LKB_CUDA_CHECK(cudaEventRecord(e_in, s_h2d));
+      LKB_CUDA_CHECK(cudaStreamWaitEvent(sc, e_in, 0));
+      if (y_dtype == LKB_DTYPE_F32)
+        ls_prep_shared_kernel<float><<<nb, 256, 0, sc>>>((const float*)dy_in + (size_t)b_lo * N, N, Npad,
+                                                         d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, d_ysumf + b_lo);
+      else
+        ls_prep_shared_kernel<double><<<nb, 256, 0, sc>>>((const double*)dy_in + (size_t)b_lo * N, N, Npad,
+                                                          d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, d_ysumf + b_lo);
+      LKB_LAUNCH_CHECK();
+      LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, nb, d_freq, F, d_rot, d_rot2,
+                           false, lowf_max, grid_f0, grid_df, normalization, ns, d_pow + (size_t)b_lo * F, sc, ev_join,
+                           (sc != st) ? 1 : 0));
+      LKB_CUDA_CHECK(cudaEventRecord(e_out, sc));
+      LKB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, e_out, 0));
+      LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)b_lo * F, d_pow + (size_t)b_lo * F, (size_t)nb * F * sizeof(float),
+                                     cudaMemcpyDeviceToHost, s_d2h));
+    }
+    if (cs[1] != st) LKB_CUDA_CHECK(cudaStreamSynchronize(cs[1]));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(s_d2h));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return LKB_OK;
+  }
   if (use_tc) {
     LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, win_in_kernel, lowf_max, grid_f0, grid_df, normalization, ns, d_pow, st, ev_join));
   } else {

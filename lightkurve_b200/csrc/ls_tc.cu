@@ -1159,14 +1159,17 @@ bool ls_tc_window_in_kernel(int64_t Npad, bool regular) {
 int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t Npad, const float* d_yc,
                  const float* d_absmax, int B, const double* d_freq, int64_t F, float4* d_rot,
                  float2* d_rot2, bool window_in_kernel, double lowf_max, double grid_f0, double grid_df,
-                 int normalization, double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready) {
+                 int normalization, double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready, int ws_alt) {
+  // ws_alt = 1: second set of workspace slots, so that two calls may be in flight on two streams
+  const int S_YHL = ws_alt ? WS_OUT4 : WS_H, S_INV = ws_alt ? WS_OUT5 : WS_I, S_YSUM = ws_alt ? WS_OUT6 : WS_O,
+            S_PART = ws_alt ? WS_OUT7 : WS_J;
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return LKB_E_CUDA; }
   __half* d_yhl = nullptr;
   float *d_inv = nullptr, *d_ysum = nullptr;
-  LKB_TRY(ws_get_t<__half>(WS_H, (size_t)2 * B * Npad, &d_yhl));
-  LKB_TRY(ws_get_t<float>(WS_I, B, &d_inv));
-  LKB_TRY(ws_get_t<float>(WS_O, B, &d_ysum));
+  LKB_TRY(ws_get_t<__half>(S_YHL, (size_t)2 * B * Npad, &d_yhl));
+  LKB_TRY(ws_get_t<float>(S_INV, B, &d_inv));
+  LKB_TRY(ws_get_t<float>(S_YSUM, B, &d_ysum));
   const bool use_fp8 = getenv("LKB_TC_FP8LO") != nullptr && atoi(getenv("LKB_TC_FP8LO")) != 0;
   uint8_t* d_y8 = nullptr;
   if (use_fp8) LKB_TRY(ws_get_t<uint8_t>(WS_C, (size_t)2 * B * Npad, &d_y8));
@@ -1223,7 +1226,7 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   const int seg_stages = (nst_total + nseg0 - 1) / nseg0;     // balanced segments
   const int nseg = (nst_total + seg_stages - 1) / seg_stages; // every segment non-empty
   float* d_part = nullptr;
-  if (nseg > 1) LKB_TRY(ws_get_t<float>(WS_J, (size_t)nseg * 2 * B * F, &d_part));
+  if (nseg > 1) LKB_TRY(ws_get_t<float>(S_PART, (size_t)nseg * 2 * B * F, &d_part));
 
   TcParams p;
   p.t = d_t; p.tab = d_tab; p.freq = d_freq; p.rot = d_rot; p.rot2 = d_rot2; p.ysum = d_ysum; p.inv_scale = d_inv; p.power = d_pow; p.part = d_part;

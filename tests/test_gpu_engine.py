@@ -201,6 +201,21 @@ def test_ls_tcgen05_cta_pair_variant(engine, monkeypatch):
         assert_ls_close(out[b], ols.ls_slow_psd(t, Y[b].astype(np.float64), freq))
 
 
+def test_ls_shared_host_pipeline_matches_single_shot(engine, monkeypatch):
+    """Host-mode calls with B > 256 are chunk-pipelined (copies overlap compute): same numbers as one shot."""
+    rng = np.random.default_rng(24)
+    B, N, F = 600, 1500, 300
+    t = np.sort(rng.uniform(0, 90, N))
+    Y = (1 + 1e-3 * np.sin(2 * np.pi * 0.9 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
+    freq = 0.02 + np.arange(F) * 0.02
+    piped = engine.ls_power_shared(t, Y, freq, "amplitude")
+    monkeypatch.setenv("LKB_LS_NO_PIPELINE", "1")
+    single = engine.ls_power_shared(t, Y, freq, "amplitude")
+    np.testing.assert_array_equal(piped, single)
+    for b in (0, 255, 256, 511, 512, 599):
+        assert_ls_close(piped[b], np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq)) * np.sqrt(4.0 / N))
+
+
 def test_ls_shared_equals_ragged(engine):
     rng = np.random.default_rng(22)
     N, B, F = 1500, 9, 200
