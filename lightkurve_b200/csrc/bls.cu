@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "select.cuh"
 #include <float.h>
+#include <algorithm>
 #include <vector>
 
 namespace lkb {
@@ -370,7 +371,7 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
                   const int64_t* __restrict__ offsets, const BlsLcInfo* __restrict__ info,
                   const double* __restrict__ period, int64_t p_begin, int64_t p_end, int64_t P,
                   const int* __restrict__ dur_bins, int D, double bin_duration,
-                  int oversample, int objective, int hist_stride, double2* __restrict__ g_hist, BlsFast fast,
+                  int oversample, int objective, int hist_stride, double2* __restrict__ g_hist, BlsFast fast, int b_base,
                   double* __restrict__ o_power, double* __restrict__ o_depth, double* __restrict__ o_depth_err,
                   double* __restrict__ o_duration, double* __restrict__ o_ttime, double* __restrict__ o_snr,
                   double* __restrict__ o_ll, int32_t* __restrict__ o_bins) {
@@ -381,7 +382,7 @@ bls_search_kernel(const double* __restrict__ trel, const double* __restrict__ wy
   double2* s_hist = s_scr + BLS_WARPS * 32;                       // BLS_WARPS * hist_stride (unless GHIST)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
+  const int b = b_base + blockIdx.y;            // the launch covers light curves [b_base, b_base + gridDim.y)
   const int64_t o = offsets[b], n = offsets[b + 1] - o;
   const int nwarps = blockDim.x >> 5;
   const int64_t p = p_begin + (int64_t)blockIdx.x * nwarps + warp;
@@ -696,26 +697,32 @@ int bls_power(const double* t, const double* y, const double* dy, const int64_t*
     if (ghist_bins >= 0 ? stride > ghist_bins : 4 * (smem + 1024) > 227 * 1024) smem = smem_cap + 1;
     if (smem > smem_cap) { W = BLS_WARPS; hist_bytes = (size_t)W * 2 * stride * sizeof(double); }
     const unsigned gx = (unsigned)((p1 - p0 + W - 1) / W);
+    int b_group = B;
     if (smem > smem_cap) {
       // histograms do not fit in shared memory: keep them in (L2-resident) global workspace
       smem = fixed_smem;
-      const size_t need = (size_t)gx * B * hist_bytes;
-      if (need > ((size_t)8 << 30)) {
-        set_error("lkb_bls_power: %d bins per period needs %zu bytes of histogram workspace; "
-                  "use fewer light curves per call", nb_max, need);
+      // one histogram slot per warp of the launch: bound the workspace by launching the light curves in groups
+      const size_t per_lc = (size_t)gx * hist_bytes;
+      const size_t cap = getenv("LKB_BLS_HIST_CAP_MB") ? (size_t)atoll(getenv("LKB_BLS_HIST_CAP_MB")) << 20 : (size_t)12 << 30;
+      if (per_lc > cap) {
+        set_error("lkb_bls_power: %d bins per period needs %zu bytes of histogram workspace per light curve", nb_max,
+                  per_lc);
         return LKB_E_UNSUPPORTED;
       }
-      LKB_TRY(ws_get_t<double2>(WS_G, need / sizeof(double2), &g_hist));
+      b_group = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, cap / per_lc));
+      LKB_TRY(ws_get_t<double2>(WS_G, per_lc * b_group / sizeof(double2), &g_hist));
     }
-    dim3 grid(gx, (unsigned)B);
-    if (g_hist)
-      bls_search_kernel<true><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P, d_durbins,
-                                                          D, bin_duration, oversample, objective, stride, g_hist, fast,
-                                                          o0, o1, o2, o3, o4, o5, o6, ob);
-    else
-      bls_search_kernel<false><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P,
-                                                           d_durbins, D, bin_duration, oversample, objective, stride,
-                                                           nullptr, fast, o0, o1, o2, o3, o4, o5, o6, ob);
+    for (int bb = 0; bb < B; bb += b_group) {
+      dim3 grid(gx, (unsigned)std::min(b_group, B - bb));
+      if (g_hist)
+        bls_search_kernel<true><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P,
+                                                            d_durbins, D, bin_duration, oversample, objective, stride,
+                                                            g_hist, fast, bb, o0, o1, o2, o3, o4, o5, o6, ob);
+      else
+        bls_search_kernel<false><<<grid, W * 32, smem, st>>>(d_trel, d_wy, d_iv, d_off, d_info, d_per, p0, p1, P,
+                                                             d_durbins, D, bin_duration, oversample, objective, stride,
+                                                             nullptr, fast, bb, o0, o1, o2, o3, o4, o5, o6, ob);
+    }
     LKB_LAUNCH_CHECK();
     p0 = p1;
   }

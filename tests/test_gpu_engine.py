@@ -340,6 +340,20 @@ def test_bls_dense_sampling_boundary_path(engine, density, monkeypatch):
     assert abs(period[np.argmax(res["power"][0])] - 2.17) < 0.01
 
 
+def test_bls_global_histograms_in_light_curve_groups(engine, monkeypatch):
+    """Global-memory histograms with a tiny workspace cap: the light curves are launched in groups; same results."""
+    rng = np.random.default_rng(37)
+    lcs = [make_transit_lc(rng, n=1200, period=2.0 + 0.3 * k) for k in range(5)]
+    duration = np.linspace(0.05, 0.2, 4)
+    period = obls.autoperiod(lcs[0][0], duration, 0.5, 6.0, frequency_factor=40)
+    ref = engine.bls_power([l[0] for l in lcs], [l[1] for l in lcs], None, period, duration, return_bins=True)
+    monkeypatch.setenv("LKB_BLS_GHIST_BINS", "0")
+    monkeypatch.setenv("LKB_BLS_HIST_CAP_MB", "1")
+    got = engine.bls_power([l[0] for l in lcs], [l[1] for l in lcs], None, period, duration, return_bins=True)
+    for k in ("power", "depth", "bins", "transit_time"):
+        np.testing.assert_array_equal(got[k], ref[k])
+
+
 def test_bls_unsorted_times_fall_back_to_cadence_path(engine):
     rng = np.random.default_rng(36)
     t = 1325.0 + np.arange(8000) / 720.0
