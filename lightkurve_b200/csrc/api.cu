@@ -1,6 +1,9 @@
 // extern "C" surface of liblkb200.so (declared in include/lkb200.h) + context/workspace.
 #include <stdarg.h>
 #include <mutex>
+#include <thread>
+#include <algorithm>
+#include <cstring>
 #include "common.cuh"
 
 namespace lkb {
@@ -78,6 +81,79 @@ int pipe_streams_get(cudaStream_t* h2d, cudaStream_t* d2h, cudaEvent_t** events,
     for (int i = 0; i < 16; ++i) LKB_CUDA_CHECK(cudaEventCreateWithFlags(&g_pipe_ev[i], cudaEventDisableTiming));
   }
   *h2d = g_h2d; *d2h = g_d2h; *events = g_pipe_ev; *n_events = 16;
+  return LKB_OK;
+}
+
+// ---- bounce-buffered copies of pageable host memory ----
+constexpr size_t BOUNCE_BYTES = (size_t)32 << 20;
+constexpr size_t BOUNCE_MIN = (size_t)16 << 20;           // smaller copies: plain cudaMemcpyAsync
+static void* g_bounce[2] = {nullptr, nullptr};
+static cudaEvent_t g_bounce_ev[2];
+static int bounce_init() {
+  if (g_bounce[0]) return LKB_OK;
+  for (int i = 0; i < 2; ++i) {
+    LKB_CUDA_CHECK(cudaHostAlloc(&g_bounce[i], BOUNCE_BYTES, cudaHostAllocDefault));
+    LKB_CUDA_CHECK(cudaEventCreateWithFlags(&g_bounce_ev[i], cudaEventDisableTiming));
+  }
+  return LKB_OK;
+}
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static void par_memcpy(void* dst, const void* src, size_t n) {
+  constexpr int NT = 4;
+  std::thread th[NT - 1];
+  const size_t part = ((n / NT) + 63) & ~(size_t)63;
+  for (int i = 1; i < NT; ++i) {
+    const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
+    th[i - 1] = std::thread([=] { if (hi > lo) memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+  }
+  memcpy(dst, src, std::min(n, part));
+  for (int i = 1; i < NT; ++i) th[i - 1].join();
+}
+int big_copy_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+  if (bytes < BOUNCE_MIN || host_is_pinned(src_host) || getenv("LKB_NO_BOUNCE")) {
+    LKB_CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+    return LKB_OK;
+  }
+  LKB_TRY(bounce_init());
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += BOUNCE_BYTES, k ^= 1) {
+    const size_t n = std::min(BOUNCE_BYTES, bytes - off);
+    LKB_CUDA_CHECK(cudaEventSynchronize(g_bounce_ev[k]));          // the DMA that last read this buffer is done
+    par_memcpy(g_bounce[k], (const char*)src_host + off, n);
+    LKB_CUDA_CHECK(cudaMemcpyAsync((char*)dst_dev + off, g_bounce[k], n, cudaMemcpyHostToDevice, st));
+    LKB_CUDA_CHECK(cudaEventRecord(g_bounce_ev[k], st));
+  }
+  return LKB_OK;
+}
+int big_copy_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st) {
+  if (bytes < BOUNCE_MIN || host_is_pinned(dst_host) || getenv("LKB_NO_BOUNCE")) {
+    LKB_CUDA_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+    return LKB_OK;
+  }
+  LKB_TRY(bounce_init());
+  // both buffers may still be the source of an earlier host->device DMA
+  LKB_CUDA_CHECK(cudaEventSynchronize(g_bounce_ev[0]));
+  LKB_CUDA_CHECK(cudaEventSynchronize(g_bounce_ev[1]));
+  size_t prev_off = 0, prev_n = 0;
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += BOUNCE_BYTES, k ^= 1) {
+    const size_t n = std::min(BOUNCE_BYTES, bytes - off);
+    LKB_CUDA_CHECK(cudaMemcpyAsync(g_bounce[k], (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaEventRecord(g_bounce_ev[k], st));
+    if (prev_n) {                                                   // drain the previous chunk while this one flies
+      LKB_CUDA_CHECK(cudaEventSynchronize(g_bounce_ev[k ^ 1]));
+      par_memcpy((char*)dst_host + prev_off, g_bounce[k ^ 1], prev_n);
+    }
+    prev_off = off; prev_n = n;
+  }
+  if (prev_n) {
+    LKB_CUDA_CHECK(cudaEventSynchronize(g_bounce_ev[k ^ 1]));
+    par_memcpy((char*)dst_host + prev_off, g_bounce[k ^ 1], prev_n);
+  }
   return LKB_OK;
 }
 
@@ -182,6 +258,13 @@ int lkb_shutdown(void) {
     g_ctx.cap[i] = 0;
   }
   if (g_aux) { cudaStreamDestroy(g_aux); cudaEventDestroy(g_ev_fork); cudaEventDestroy(g_ev_join); g_aux = nullptr; }
+  if (g_h2d) {
+    cudaStreamDestroy(g_h2d); cudaStreamDestroy(g_d2h);
+    for (int i = 0; i < 16; ++i) cudaEventDestroy(g_pipe_ev[i]);
+    g_h2d = g_d2h = nullptr;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (g_bounce[i]) { cudaFreeHost(g_bounce[i]); cudaEventDestroy(g_bounce_ev[i]); g_bounce[i] = nullptr; }
   g_ctx.inited = false;
   return LKB_OK;
 }
