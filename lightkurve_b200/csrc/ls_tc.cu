@@ -33,7 +33,6 @@
 #include "ls_common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
-#include <cuda_fp8.h>
 #include <stdlib.h>
 
 namespace lkb {
@@ -70,8 +69,7 @@ constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uin
 // per light curve; also returns the sum of the EFFECTIVE values (hi + lo) / scale for the mean term.
 __global__ void __launch_bounds__(256)
 tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ absmax, int B, int64_t Npad,
-                     __half* __restrict__ yhl, float* __restrict__ inv_scale, float* __restrict__ ysum_eff,
-                     uint8_t* __restrict__ y8 = nullptr) {
+                     __half* __restrict__ yhl, float* __restrict__ inv_scale, float* __restrict__ ysum_eff) {
   __shared__ double red[33];
   const int b = blockIdx.x;
   const float am = absmax[b];
@@ -89,16 +87,9 @@ tc_split_flux_kernel(const float* __restrict__ yc, const float* __restrict__ abs
     const __half2 h = __floats2half2_rn(a0, a1);
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-    float2 lf = __half22float2(l);
+    const float2 lf = __half22float2(l);
     *reinterpret_cast<__half2*>(yhl + (int64_t)b * Npad + i) = h;
     *reinterpret_cast<__half2*>(yhl + ((int64_t)B + b) * Npad + i) = l;
-    if (y8) {       // FP8 variant: plane 0 = e4m3(Y / 64) (pairs with the design-matrix residual), plane 1 = e4m3(Y - Yh)
-      const __nv_fp8x2_storage_t q = __nv_cvt_float2_to_fp8x2(make_float2(a0 * 0.015625f, a1 * 0.015625f), __NV_SATFINITE, __NV_E4M3);
-      const __nv_fp8x2_storage_t ql = __nv_cvt_float2_to_fp8x2(make_float2(a0 - hf.x, a1 - hf.y), __NV_SATFINITE, __NV_E4M3);
-      *reinterpret_cast<__nv_fp8x2_storage_t*>(y8 + (int64_t)b * Npad + i) = q;
-      *reinterpret_cast<__nv_fp8x2_storage_t*>(y8 + ((int64_t)B + b) * Npad + i) = ql;
-      lf = __half22float2(__half2(__nv_cvt_fp8x2_to_halfraw2(ql, __NV_E4M3)));     // the residual the MMAs will see
-    }
     acc += (double)hf.x + (double)lf.x + (double)hf.y + (double)lf.y;
   }
   const double tot = block_sum(acc, red);
@@ -127,7 +118,7 @@ struct TcParams {
                             // the blockIdx.y == 0 CTAs (nullptr: the separate window kernel is used)
   double lowf_max;          // frequencies <= this are "low rows": design matrix carries cos - 1
   int debug;                // LKB_TC_DEBUG bit mask: timing experiments only (results are wrong when set)
-  float low_mul;            // low rows are generated with TC_A_SCALE / low_mul (1, or 2 in the FP8 variant)
+  float low_mul;            // extra output scale of the low rows (1; a variant may generate them at half scale)
   double f0, df;            // regular grid (REGULAR kernels)
 };
 
@@ -589,247 +580,6 @@ ls_tcg_kernel(const __grid_constant__ CUtensorMap ymap, const TcParams p) {
 }
 
 // =====================================================================================
-// FP8-residual variant (opt-in, LKB_TC_FP8LO=1).  The chip is power-capped in this kernel, so the way to go
-// faster is fewer tensor-core joules per product: the two small correction products run as E4M3 x E4M3 MMAs
-// (kind::f8f6f4, K = 32 per instruction, twice the fp16 rate):
-//     A*Y ~= Ah*Yh (fp16 x fp16)  +  e4m3(A) * e4m3(Y - Yh)  +  e4m3(64 (A - Ah)) * e4m3(Y / 64)
-// 8 MMAs per 32-cadence stage instead of 12 (1024 instead of 1536 tensor-pipe clocks).  The fp8 factors only
-// multiply terms that are already 2^-11 of the product: simulated excess over the LS tolerance +0.1..0.2
-// (tools: /tmp-free numpy model in DESIGN.md), measured below.  Stage layout (64 KB as before):
-//   cos: Ah 8 KB (SW64) | A8 4 KB | Al8 4 KB (SW32)   sin: the same   flux: Yh 16 KB (SW64) | Y8 8 KB | Yl8 8 KB (SW32)
-// Low-frequency rows carry (cos - 1) in [-2, 0]: they are generated with half the scale (e4m3 tops out at 448)
-// and the epilogue multiplies them back (TcParams::low_mul = 2).
-// =====================================================================================
-constexpr int T8_A8_TILE = TC_BM * TC_BK;             // 4 KB
-constexpr int T8_Y8_TILE = TC_BN * TC_BK;             // 8 KB
-constexpr int T8_TRIG = TC_A_TILE + 2 * T8_A8_TILE;   // 16 KB per trig function
-constexpr int T8_YOFF = 2 * T8_TRIG;                  // 32 KB
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_32B: 32-byte rows, 8-row atoms of 256 B (SBO).
-__device__ __forceinline__ uint64_t tc_smem_desc32(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;                              // layout type: SWIZZLE_32B
-  return d;
-}
-
-// two (cos, sin) pairs -> packed fp16 hi halves + e4m3 of the value and of 64 x the fp16 residual
-__device__ __forceinline__ void tc_split2_fp8(float c0, float c1, float s0, float s1, float scale, uint32_t& ch,
-                                              uint32_t& sh, uint16_t& c8, uint16_t& cl8, uint16_t& s8, uint16_t& sl8) {
-  c0 *= scale; c1 *= scale; s0 *= scale; s1 *= scale;
-  const __half2 hc = __floats2half2_rn(c0, c1), hs = __floats2half2_rn(s0, s1);
-  const float2 fc = __half22float2(hc), fs = __half22float2(hs);
-  ch = *reinterpret_cast<const uint32_t*>(&hc);
-  sh = *reinterpret_cast<const uint32_t*>(&hs);
-  c8 = __nv_cvt_float2_to_fp8x2(make_float2(c0, c1), __NV_SATFINITE, __NV_E4M3);
-  s8 = __nv_cvt_float2_to_fp8x2(make_float2(s0, s1), __NV_SATFINITE, __NV_E4M3);
-  cl8 = __nv_cvt_float2_to_fp8x2(make_float2((c0 - fc.x) * 64.f, (c1 - fc.y) * 64.f), __NV_SATFINITE, __NV_E4M3);
-  sl8 = __nv_cvt_float2_to_fp8x2(make_float2((s0 - fs.x) * 64.f, (s1 - fs.y) * 64.f), __NV_SATFINITE, __NV_E4M3);
-}
-
-template <bool REGULAR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-ls_tc8_kernel(const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap ymap8, const TcParams p) {
-  extern __shared__ unsigned char tc_smem_raw[];
-  const uint32_t raw = ptx::smem_u32(tc_smem_raw);
-  unsigned char* smem = tc_smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full_y = bars;
-  uint64_t* full_a = bars + TC_STAGES;
-  uint64_t* empty = bars + 2 * TC_STAGES;
-  uint64_t* acc_full = bars + 3 * TC_STAGES;
-  uint64_t* acc_empty = bars + 3 * TC_STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 2);
-  unsigned char* scratch = reinterpret_cast<unsigned char*>(bars) + 256;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t f0 = (int64_t)blockIdx.x * TC_BM;
-  const int b0 = blockIdx.y * TC_BN;
-  const int nst = (int)(p.Npad / TC_BK);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      ptx::mbar_init(&full_y[s], 1);
-      ptx::mbar_init(&full_a[s], TC_GEN_WARPS);
-      ptx::mbar_init(&empty[s], 1);
-    }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(acc_empty, TC_EPI_WARPS);
-    ptx::mbar_fence_init();
-    ptx::prefetch_tensormap(&ymap);
-    ptx::prefetch_tensormap(&ymap8);
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < nst; ++it) {
-        const int s = it % TC_STAGES;
-        if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, 200);
-        unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_y[s], TC_Y_TILE + 2 * T8_Y8_TILE);
-        ptx::tma_load_2d(st + T8_YOFF, &ymap, it * TC_BK, b0, &full_y[s]);                          // Yh (fp16)
-        ptx::tma_load_2d(st + T8_YOFF + TC_Y_TILE, &ymap8, it * TC_BK, b0, &full_y[s]);             // e4m3(Y / 64)
-        ptx::tma_load_2d(st + T8_YOFF + TC_Y_TILE + T8_Y8_TILE, &ymap8, it * TC_BK, p.B + b0, &full_y[s]);   // e4m3(Y - Yh)
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      for (int it = 0; it < nst; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        const int seg = it / p.seg_stages;
-        const bool seg_first = (it - seg * p.seg_stages) == 0;
-        const bool seg_last = (it + 1 == nst) || ((it + 1) % p.seg_stages == 0);
-        ptx::mbar_wait_sleep(&full_y[s], ph, 40);
-        ptx::mbar_wait_sleep(&full_a[s], ph, 40);
-        if (seg_first && seg > 0) ptx::mbar_wait_sleep(acc_empty, (seg - 1) & 1, 40);
-        ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
-        const uint32_t y_h = sa + T8_YOFF, y_8 = y_h + TC_Y_TILE, y_l8 = y_8 + T8_Y8_TILE;
-        const uint64_t d_y8 = tc_smem_desc32(y_8), d_yl8 = tc_smem_desc32(y_l8);
-#pragma unroll
-        for (int trig = 0; trig < 2; ++trig) {
-          const uint32_t a_h = sa + trig * T8_TRIG, a_8 = a_h + TC_A_TILE, a_l8 = a_8 + T8_A8_TILE;
-          const uint32_t d_t = tmem + trig * TC_BN;
-          ptx::umma_f16_ss(d_t, tc_smem_desc(a_h), tc_smem_desc(y_h), TC_IDESC, seg_first ? 0u : 1u);
-          ptx::umma_f16_ss(d_t, tc_smem_desc(a_h + 32), tc_smem_desc(y_h + 32), TC_IDESC, 1u);
-          ptx::umma_f8_ss(d_t, tc_smem_desc32(a_8), d_yl8, TC_IDESC, 1u);        // A * (Y - Yh)
-          ptx::umma_f8_ss(d_t, tc_smem_desc32(a_l8), d_y8, TC_IDESC, 1u);        // 64 (A - Ah) * Y / 64
-        }
-        ptx::umma_commit(&empty[s]);
-        if (seg_last) ptx::umma_commit(acc_full);
-      }
-    }
-  } else if (warp < 2 + TC_GEN_WARPS) {
-    const int gw = warp - 2;
-    const int row = (gw & 3) * 32 + lane;
-    const int chunk = gw >> 2;
-    const uint32_t row_off = (uint32_t)row * 64u + ((((uint32_t)chunk) ^ (uint32_t)((row >> 1) & 3)) << 4);
-    // 8-bit tiles: 32-byte rows, 16-byte unit index XOR row bit 2 (SWIZZLE_32B), 8 bytes per chunk
-    const uint32_t row_off8 = (uint32_t)row * 32u + ((((uint32_t)chunk >> 1) ^ (uint32_t)((row >> 2) & 1)) << 4) +
-                              ((uint32_t)chunk & 1u) * 8u;
-    ulonglong2* my_scr = reinterpret_cast<ulonglong2*>(scratch + gw * 128);
-    const unsigned long long kfreq = (unsigned long long)(f0 + row);
-    const double fr = REGULAR ? (p.f0 + (double)(f0 + row) * p.df) : ((f0 + row < p.F) ? p.freq[f0 + row] : 0.0);
-    const bool low_row = fabs(fr) <= p.lowf_max;
-    const float scale = low_row ? TC_A_SCALE / p.low_mul : TC_A_SCALE;
-    ulonglong2 nxt = make_ulonglong2(0ull, 0ull);
-    auto prefetch = [&](int it) {
-      if (lane < 8) {
-        const int64_t n = (int64_t)it * TC_BK + chunk * 8 + lane;
-        if (REGULAR) nxt = p.tab[n];
-        else nxt.x = (unsigned long long)__double_as_longlong(p.t[n]);
-      }
-    };
-    prefetch(0);
-    for (int it = 0; it < nst; ++it) {
-      const int s = it % TC_STAGES;
-      if (lane < 8) my_scr[lane] = nxt;
-      __syncwarp();
-      if (it + 1 < nst) prefetch(it + 1);
-      if (it >= TC_STAGES) ptx::mbar_wait_sleep(&empty[s], ((it / TC_STAGES) - 1) & 1, 100);
-      unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-      uint32_t ch[4], sh[4];
-      uint16_t c8[4], cl8[4], s8[4], sl8[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float s0, c0, s1, c1;
-        const ulonglong2 e0 = my_scr[2 * q], e1 = my_scr[2 * q + 1];
-        if (REGULAR) {
-          if (low_row) {
-            ls_sincos_fixed_low(e0.x + kfreq * e0.y, s0, c0);
-            ls_sincos_fixed_low(e1.x + kfreq * e1.y, s1, c1);
-          } else {
-            ls_sincos_fixed(e0.x + kfreq * e0.y, s0, c0);
-            ls_sincos_fixed(e1.x + kfreq * e1.y, s1, c1);
-          }
-        } else {
-          if (low_row) {
-            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e0.x), s0, c0);
-            ls_sincos_cycles_low(fr * __longlong_as_double((long long)e1.x), s1, c1);
-          } else {
-            ls_sincos_cycles(fr * __longlong_as_double((long long)e0.x), s0, c0);
-            ls_sincos_cycles(fr * __longlong_as_double((long long)e1.x), s1, c1);
-          }
-        }
-        tc_split2_fp8(c0, c1, s0, s1, scale, ch[q], sh[q], c8[q], cl8[q], s8[q], sl8[q]);
-      }
-      auto pack = [](const uint16_t* v) {
-        return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
-      };
-      *reinterpret_cast<uint4*>(st + row_off) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-      *reinterpret_cast<uint2*>(st + TC_A_TILE + row_off8) = pack(c8);
-      *reinterpret_cast<uint2*>(st + TC_A_TILE + T8_A8_TILE + row_off8) = pack(cl8);
-      *reinterpret_cast<uint4*>(st + T8_TRIG + row_off) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-      *reinterpret_cast<uint2*>(st + T8_TRIG + TC_A_TILE + row_off8) = pack(s8);
-      *reinterpret_cast<uint2*>(st + T8_TRIG + TC_A_TILE + T8_A8_TILE + row_off8) = pack(sl8);
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&full_a[s]);
-    }
-  } else {
-    const int quad = warp & 3;
-    const int64_t f = f0 + quad * 32 + lane;
-    const bool f_ok = f < p.F;
-    const float4 r = f_ok ? p.rot[f] : make_float4(1.f, 0.f, 0.f, 0.f);
-    const float2 r2 = f_ok ? p.rot2[f] : make_float2(0.f, 0.f);
-    const bool low_out = f_ok && fabs(p.freq[f]) <= p.lowf_max;
-    const float rowmul = low_out ? p.low_mul : 1.0f;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const float Nf = (float)p.N;
-    const int64_t plane = (int64_t)p.B * p.F;
-    for (int seg = 0; seg < p.nseg; ++seg) {
-      ptx::mbar_wait_sleep(acc_full, seg & 1, 500);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 16) {
-        uint32_t vc[16], vs[16];
-        ptx::tmem_ld_32x32b_x16(lane_addr + c0, vc);
-        ptx::tmem_ld_32x32b_x16(lane_addr + TC_BN + c0, vs);
-        ptx::tmem_ld_wait();
-        if (f_ok) {
-          if (p.nseg == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int b = b0 + c0 + j;
-              if (b < p.B) {
-                const float h = p.inv_scale[b] * rowmul;
-                p.power[(int64_t)b * p.F + f] = ls_epilogue_shared(__uint_as_float(vc[j]) * h, __uint_as_float(vs[j]) * h,
-                                                                  r, r2, p.ysum[b], Nf, p.normalization, p.norm_scale, low_out);
-              }
-            }
-          } else {
-            float* pc = p.part + (int64_t)(seg * 2) * plane + (int64_t)(b0 + c0) * p.F + f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (b0 + c0 + j < p.B) {
-                pc[(int64_t)j * p.F] = __uint_as_float(vc[j]);
-                pc[plane + (int64_t)j * p.F] = __uint_as_float(vs[j]);
-              }
-            }
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_empty);
-    }
-  }
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
-}
-
-// =====================================================================================
 // CTA-pair variant (cta_group::2).  Measured motivation: with one CTA per tile the M128 N256 K16 SS MMAs read
 // 12 KB of operands per 128 clk (96 B/clk) while the generators + TMA write another 64 KB per 1536-clk stage
 // (42 B/clk) - more than the 128 B/clk of one SM's shared memory, so the tensor pipe idles ~30 %.  A pair of
@@ -1170,10 +920,7 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   LKB_TRY(ws_get_t<__half>(S_YHL, (size_t)2 * B * Npad, &d_yhl));
   LKB_TRY(ws_get_t<float>(S_INV, B, &d_inv));
   LKB_TRY(ws_get_t<float>(S_YSUM, B, &d_ysum));
-  const bool use_fp8 = getenv("LKB_TC_FP8LO") != nullptr && atoi(getenv("LKB_TC_FP8LO")) != 0;
-  uint8_t* d_y8 = nullptr;
-  if (use_fp8) LKB_TRY(ws_get_t<uint8_t>(WS_C, (size_t)2 * B * Npad, &d_y8));
-  tc_split_flux_kernel<<<B, 256, 0, st>>>(d_yc, d_absmax, B, Npad, d_yhl, d_inv, d_ysum, d_y8);
+  tc_split_flux_kernel<<<B, 256, 0, st>>>(d_yc, d_absmax, B, Npad, d_yhl, d_inv, d_ysum);
   LKB_LAUNCH_CHECK();
 
   CUtensorMap map;
@@ -1199,19 +946,10 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)cr); return LKB_E_CUDA; }
   }
-  CUtensorMap map8;
-  if (use_fp8) {
-    const cuuint64_t strides8[1] = {(cuuint64_t)Npad};
-    cr = enc(&map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_y8, dims, strides8, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp8) failed: %d", (int)cr); return LKB_E_CUDA; }
-  }
   static bool attr_set = false;
   if (!attr_set) {
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TG_SMEM));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     LKB_CUDA_CHECK(cudaFuncSetAttribute(ls_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM));
@@ -1233,17 +971,14 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
   p.N = N; p.Npad = Npad; p.F = F; p.B = B; p.normalization = normalization; p.norm_scale = (float)norm_scale;
   p.seg_stages = seg_stages; p.nseg = nseg;
   p.lowf_max = lowf_max; p.f0 = grid_f0; p.df = grid_df;
-  p.low_mul = use_fp8 ? 2.0f : 1.0f;
+  p.low_mul = 1.0f;
   p.debug = getenv("LKB_TC_DEBUG") ? atoi(getenv("LKB_TC_DEBUG")) : 0;
   p.wsum = nullptr;
   if (window_in_kernel && nseg > 1 && regular) LKB_TRY(ws_get_t<double>(WS_P, (size_t)F * 16, &p.wsum));
   dim3 grid((unsigned)((F + TC_BM - 1) / TC_BM), (unsigned)((B + TC_BN - 1) / TC_BN));
   if (nseg == 1) LKB_CUDA_CHECK(cudaStreamWaitEvent(st, rot_ready, 0));   // direct epilogue needs rot
   prof_begin(st);
-  if (use_fp8) {
-    if (regular) ls_tc8_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(map, map8, p);
-    else ls_tc8_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(map, map8, p);
-  } else if (!use_pair && !(getenv("LKB_TC_GEN_GROUPS") != nullptr && atoi(getenv("LKB_TC_GEN_GROUPS")) == 1) &&
+  if (!use_pair && !(getenv("LKB_TC_GEN_GROUPS") != nullptr && atoi(getenv("LKB_TC_GEN_GROUPS")) == 1) &&
              !window_in_kernel && p.debug == 0) {
     // default: generator warps in two groups that fill alternate stages (LKB_TC_GEN_GROUPS=1: lock-step kernel)
     if (regular) ls_tcg_kernel<true><<<grid, TC_THREADS, TG_SMEM, st>>>(map, p);

@@ -16,7 +16,6 @@ freq = np.sort(rng.uniform(0.01, 13.6, F))
 refs = {b: np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq)) * np.sqrt(4.0 / N) for b in (0, 33, 69)}
 sim = engine.ls_power_shared(t, Y, freq, "amplitude", algo="simt")
 modes = [(int(a), 0) for a in os.environ.get("PROBE_SEGS", "100000,512,256,128,64,32").split(",")]
-modes += [(64, 1), (128, 1)]                      # FP8-residual variant (LKB_TC_FP8LO=1)
 for seg, fp8 in modes:
     os.environ["LKB_TC_SEG_STAGES"] = str(seg)
     os.environ["LKB_TC_FP8LO"] = str(fp8)
