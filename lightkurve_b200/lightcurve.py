@@ -81,6 +81,11 @@ class LightCurve:
             time = Time(time, format=time_format, scale=time_scale)
         if flux is None:
             flux = np.full(len(time), np.nan)
+        if np.ndim(getattr(flux, "value", flux)) == 0:               # scalars broadcast (astropy TimeSeries column semantics)
+            flux = np.full(len(time), float(getattr(flux, "value", flux))) * (flux.unit if u.is_quantity(flux) else 1)
+        if flux_err is not None and np.ndim(getattr(flux_err, "value", flux_err)) == 0:
+            flux_err = np.full(len(time), float(getattr(flux_err, "value", flux_err))) * \
+                (flux_err.unit if u.is_quantity(flux_err) else 1)
         flux = _as_flux_quantity(flux, flux_unit)
         if flux_err is None:
             flux_err = np.full(len(flux), np.nan)                     # :458-460

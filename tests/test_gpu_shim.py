@@ -470,3 +470,18 @@ def test_smooth_and_flatten_periodogram():
     str(s_)
     assert len(p.bin(binsize=10, method="mean").frequency) == len(p.frequency) // 10
     assert len(p.bin(binsize=10, method="median").frequency) == len(p.frequency) // 10
+
+
+def test_overfit_metric_lombscargle():
+    """/root/reference/tests/correctors/test_metrics.py:14-34 (exact 1.0 / 0.0 known answers)."""
+    from lightkurve_b200.correctors.metrics import overfit_metric_lombscargle
+    time = np.arange(1, 100, 0.1)
+    lc_flat = LightCurve(time=time, flux=1, flux_err=0.0)
+    lc_sine = LightCurve(time=time, flux=np.sin(time) + 1, flux_err=0.0)
+    assert overfit_metric_lombscargle(lc_flat, lc_flat) == 1.0
+    assert overfit_metric_lombscargle(lc_sine, lc_sine) == 1.0
+    assert overfit_metric_lombscargle(lc_sine, lc_flat) == 1.0
+    assert overfit_metric_lombscargle(lc_flat, lc_sine) == 0.0
+    lc_flat.flux_err += 0.5
+    lc_sine.flux_err += 0.5
+    assert overfit_metric_lombscargle(lc_flat, lc_sine) > 0.5
