@@ -11,7 +11,7 @@ from lightkurve_b200 import engine  # noqa: E402
 from oracle import bls as obls, detrend as odet, ls as ols  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0      # fraction of the full config batch
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["k1", "bls", "flatten", "regress", "pg"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["c1", "k1", "bls", "flatten", "regress", "pg"]
 engine.init(0)
 rng = np.random.default_rng(1003)
 
@@ -117,3 +117,27 @@ if "pg" in which:      # the step after config 2: log-median background of B per
     nwin = len(engine.logmedian_windows(freq, 0.01)[0])
     print("K6 logmedian : B=%d F=%d windows=%d  median kernel %.2f ms  %.1f periodograms/s (wall %.1f ms incl. H2D/D2H)  "
           "cpu numpy %.2f s/periodogram  parity %s" % (B, F, nwin, ker * 1e3, B / ker, wall * 1e3, cpu, ok))
+
+
+if "c1" in which:      # config 1: one synthetic sinusoid light curve, 1000 cadences, default to_periodogram()
+    import lightkurve_b200 as lk
+    rng1 = np.random.default_rng(1001)
+    t = np.arange(1000.0)
+    y = rng1.normal(1, 0.1, 1000) + np.sin(t / t.max() * 20 * np.pi)
+    lc = lk.LightCurve(time=t, flux=y / np.median(y))
+    pg = lc.to_periodogram()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        pg = lc.to_periodogram()
+    dt_api = (time.perf_counter() - t0) / 200
+    fr = np.asarray(pg.frequency.value)
+    yy = np.asarray(lc.flux.value)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        out = engine.ls_power_ragged([t], [yy], fr, "amplitude")
+    dt_eng = (time.perf_counter() - t0) / 200
+    t0 = time.perf_counter(); _, pref, _ = ols.lombscargle(t, yy); cpu = time.perf_counter() - t0
+    ok = np.nanargmax(pref) == np.nanargmax(pg.power.value)
+    print("C1 plumbing  : N=1000 F=%d  LightCurve.to_periodogram() %.0f us per call (engine call alone %.0f us)  "
+          "cpu oracle fast %.0f us  period %.2f d  argmax parity %s" % (len(fr), dt_api * 1e6, dt_eng * 1e6, cpu * 1e6,
+                                                                   float(pg.period_at_max_power.value), ok))
