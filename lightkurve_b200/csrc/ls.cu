@@ -23,6 +23,17 @@
 
 namespace lkb {
 
+// Per-cadence entry of a regular-grid light curve (ragged path): fixed-point phases of the grid origin and of one
+// grid step, plus the fp32 rotation by one step - the bins after a warp's first are obtained by rotating (cos, sin)
+// (4 FMA-pipe ops) instead of two more MUFU evaluations.
+struct __align__(8) LsTabEntry {
+  unsigned long long a, b;      // frac(f0 t) 2^64, frac(df t) 2^64
+  float cb, sb;                 // cos / sin of 2 pi frac(df t)
+};
+static_assert(sizeof(LsTabEntry) == 24, "LsTabEntry must be 24 bytes");
+
+
+
 // =====================================================================================
 // Prologue: centre the flux the way astropy does (y - dot(w, y), w = 1/N), shift time to
 // the light curve's first cadence (power is shift-invariant; the shift keeps f*t small),
@@ -35,7 +46,7 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
                       const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
                       double* __restrict__ t_out, float* __restrict__ y_out, double* __restrict__ tspan,
                       const double* __restrict__ grid_f0, const double* __restrict__ grid_df,
-                      ulonglong2* __restrict__ tab_out, double* __restrict__ ysum,
+                      LsTabEntry* __restrict__ tab_out, double* __restrict__ ysum,
                       double* __restrict__ y_out64 = nullptr) {
   __shared__ double red[33];
   __shared__ int s_const;
@@ -59,7 +70,8 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
   const double t0 = t[o];
   double span = 0.0, resid = 0.0;
   for (int64_t i = threadIdx.x; i < np_; i += blockDim.x) {
-    ulonglong2 e = make_ulonglong2(0ull, 0ull);
+    LsTabEntry e;
+    e.a = 0ull; e.b = 0ull; e.cb = 1.0f; e.sb = 0.0f;
     if (i < n) {
       const double tr = t[o + i] - t0;
       span = fmax(span, fabs(tr));
@@ -75,8 +87,12 @@ ls_prep_ragged_kernel(const double* __restrict__ t, const TY* __restrict__ y,
       }
       if (tab_out) {      // fixed-point phase table of this light curve's regular grid (ls_common.cuh)
         const double x = grid_f0[b] * tr, z = grid_df[b] * tr;
-        e.x = __double2ull_rd((x - floor(x)) * 18446744073709551616.0);
-        e.y = __double2ull_rd((z - floor(z)) * 18446744073709551616.0);
+        e.a = __double2ull_rd((x - floor(x)) * 18446744073709551616.0);
+        e.b = __double2ull_rd((z - floor(z)) * 18446744073709551616.0);
+        double sb, cb;
+        sincospi(2.0 * (z - rint(z)), &sb, &cb);
+        e.cb = (float)cb;
+        e.sb = (float)sb;
       }
     } else {
       t_out[po + i] = 0.0;
@@ -163,13 +179,13 @@ constexpr int LS_FPB = LS_WARPS * LS_FPW;       // frequency bins per block
 // cadence, no fp64 on the hot loop); otherwise fp64 phase = f * t (8 B per cadence).
 template <bool REGULAR>
 __global__ void __launch_bounds__(LS_WARPS * 32)
-ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ tabws, const float* __restrict__ yws,
+ls_direct_kernel(const double* __restrict__ tws, const LsTabEntry* __restrict__ tabws, const float* __restrict__ yws,
                  const int64_t* __restrict__ offsets, const int64_t* __restrict__ poffsets,
                  const double* __restrict__ freq, const int64_t* __restrict__ freq_offsets, int64_t F_shared,
                  const double* __restrict__ tspan, const double* __restrict__ ysum, int normalization,
                  const double* __restrict__ norm_scale, float* __restrict__ power) {
-  constexpr int TN = REGULAR ? 1024 : 1536;     // cadences per shared-memory tile (<= 40 KB static smem)
-  using Elem = typename std::conditional<REGULAR, ulonglong2, double>::type;
+  constexpr int TN = REGULAR ? 768 : 1536;      // cadences per shared-memory tile (<= 42 KB static smem)
+  using Elem = typename std::conditional<REGULAR, LsTabEntry, double>::type;
   __shared__ __align__(16) Elem s_t[2][TN];
   __shared__ __align__(16) float s_y[2][TN];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -252,15 +268,17 @@ ls_direct_kernel(const double* __restrict__ tws, const ulonglong2* __restrict__ 
       for (int i = lane; i < cnt; i += 32) {
         const float yy = s_y[buf][i];
         if constexpr (REGULAR) {
-          const ulonglong2 e = s_t[buf][i];
-          uint32_t ph = (uint32_t)((e.x + (unsigned long long)f_base * e.y) >> 32);   // exact for bin f_base
-          const uint32_t db = (uint32_t)(e.y >> 32);        // next bins: 32-bit steps (error < 3 * 2^-32 cycle)
+          const LsTabEntry e = s_t[buf][i];
+          const uint32_t ph = (uint32_t)((e.a + (unsigned long long)f_base * e.b) >> 32);   // exact for bin f_base
+          float s, c;
+          ls_sincos_fixed32(ph, s, c);
+          fs[0].add(yy, s, c);
 #pragma unroll
-          for (int j = 0; j < LS_FPW; ++j) {
-            float s, c;
-            ls_sincos_fixed32(ph, s, c);
+          for (int j = 1; j < LS_FPW; ++j) {              // next bins: rotate by one grid step
+            const float s2 = fmaf(s, e.cb, c * e.sb), c2 = fmaf(c, e.cb, -s * e.sb);
+            s = s2;
+            c = c2;
             fs[j].add(yy, s, c);
-            ph += db;
           }
         } else {
           const double tt = s_t[buf][i];
@@ -688,11 +706,11 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
     }
   }
   double *d_gf0 = nullptr, *d_gdf = nullptr;
-  ulonglong2* d_tab = nullptr;
+  LsTabEntry* d_tab = nullptr;
   if (s == LKB_OK && regular) {
     s = ws_get_t<double>(WS_G, B, &d_gf0);
     if (s == LKB_OK) s = ws_get_t<double>(WS_H, B, &d_gdf);
-    if (s == LKB_OK) s = ws_get_t<ulonglong2>(WS_I, ptotal + 4, &d_tab);
+    if (s == LKB_OK) s = ws_get_t<LsTabEntry>(WS_I, ptotal + 4, &d_tab);
   }
   if (s != LKB_OK) { free(h_po); return s; }
   cudaError_t e = cudaMemcpyAsync(d_off, h_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st);
