@@ -25,9 +25,11 @@
 // already fill the next stages, and ls_tc_finish_kernel sums the planes with round-to-nearest
 // CUDA-core adds before the epilogue math.
 //
-// Warp roles (448 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM
-// owner, warps 2..9 = design-matrix generators, warps 10..13 = epilogue (warp_id % 4 covers the
-// four TMEM lane quadrants).
+// Warp roles (704 threads): warp 0 = TMA producer (flux tiles), warp 1 = MMA issuer + TMEM owner, warps 2..17 =
+// design-matrix generators, warps 18..21 = epilogue (warp_id % 4 covers the four TMEM lane quadrants).
+// Kernels in this file: ls_tcg_kernel (shipped: generator warps in two groups that fill alternate stages),
+// ls_tc_kernel (its lock-step predecessor, kept for A/B timing and the LKB_TC_DEBUG experiments) and ls_tc2_kernel
+// (CTA-pair / cta_group::2 variant, opt-in) - DESIGN.md section 4 K2 has the measurements behind that choice.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "ls_common.cuh"

@@ -246,3 +246,23 @@ def test_fold_matches_astropy_timeseries_fold_semantics():
     with pytest.raises(ValueError):
         lc.fold(period=2.0, wrap_phase=3.0)
     assert fw.meta["PERIOD"].value == 2.0 and fw.cycle.max() == 5
+
+
+def test_logmedian_windows_match_reference_loop():
+    """Host-side window builder of Periodogram.smooth(method="logmedian") (periodogram.py:267-277): identical bin sets."""
+    from lightkurve_b200.engine import logmedian_windows
+    rng = np.random.default_rng(0)
+    for f in ((np.arange(5000) + 1) * 0.0137, np.sort(rng.uniform(0.01, 300, 3000)), np.logspace(-2, 2, 777)):
+        for fw in (0.01, 0.1, 0.033):
+            lo, hi = logmedian_windows(f, fw)
+            logf = np.log10(f)
+            x0, w = logf[0], 0
+            while x0 < logf[-1]:
+                idx = np.flatnonzero(np.abs(logf - x0) < fw)
+                if len(idx):
+                    assert (idx[0], idx[-1] + 1, len(idx)) == (lo[w], hi[w], hi[w] - lo[w])
+                else:
+                    assert lo[w] == hi[w]
+                x0 += 0.5 * fw
+                w += 1
+            assert w == len(lo)
