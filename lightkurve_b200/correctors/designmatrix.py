@@ -1,7 +1,7 @@
 """`DesignMatrix` / `DesignMatrixCollection`: the parts of
 /root/reference/src/lightkurve/correctors/designmatrix.py that RegressionCorrector.correct uses
-(X, prior_mu, prior_sigma, validate, append_constant, split, standardize, collection hstack);
-``pca``, plotting, sparse matrices and the spline builders are out of scope.
+(X, prior_mu, prior_sigma, validate, append_constant, split, standardize, pca, collect, collection hstack);
+plotting, sparse matrices and the spline builders are out of scope.
 """
 import warnings
 from copy import deepcopy
@@ -77,19 +77,30 @@ class DesignMatrix:
         return dm
 
     def standardize(self, inplace=False):
-        """Subtract the mean and divide by the std of each non-constant column (designmatrix.py:217-243)."""
+        """Median-subtract and sigma-divide every non-constant column (designmatrix.py:216-250); zeros are
+        treated as missing and stay zero."""
         ar = np.asarray(np.copy(self.df), dtype=float)
         ar[ar == 0] = np.nan
-        is_const = np.nanstd(ar, axis=0) == 0
-        mean = np.atleast_2d(np.nanmean(ar, axis=0))
-        std = np.atleast_2d(np.nanstd(ar, axis=0))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            ar[:, ~is_const] = ((ar - mean) / std)[:, ~is_const]
-        ar[np.isnan(ar)] = 0
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            is_const = np.nanstd(ar, axis=0) == 0
+            median = np.atleast_2d(np.nanmedian(ar, axis=0)[~is_const])
+            std = np.atleast_2d(np.nanstd(ar, axis=0)[~is_const])
+            ar[:, ~is_const] = (ar[:, ~is_const] - median) / std
         new_df = pd.DataFrame(ar, columns=self.columns).fillna(0)
         dm = self if inplace else self.copy()
         dm.df = new_df
         return dm
+
+    def pca(self, nterms=6, n_iter=10):
+        """Principal components of the (column-centred) matrix as a new DesignMatrix (designmatrix.py:252-282).
+        The reference uses the randomised `fbpca.pca`; this is the exact thin SVD (`n_iter` is accepted and ignored),
+        so the components agree up to sign and the randomised solver's error."""
+        if nterms > self.shape[1]:
+            nterms = self.shape[1]
+        a = np.asarray(self.values, dtype=float)
+        u_, _, _ = np.linalg.svd(a - a.mean(axis=0), full_matrices=False)
+        return DesignMatrix(u_[:, :nterms], name=self.name)
 
     def append_constant(self, prior_mu=0, prior_sigma=np.inf, inplace=False):
         """Append a column of ones named "offset" (designmatrix.py:284-304)."""
@@ -125,6 +136,13 @@ class DesignMatrix:
     def validate(self, rank=True):
         """Emits LightkurveWarning if the matrix has low rank; checks prior shapes (designmatrix.py:306-349)."""
         self._validate()
+
+    def __getitem__(self, key):
+        return self.df[key].values
+
+    def collect(self, matrix):
+        """Join two design matrices into a collection (designmatrix.py:382-384)."""
+        return DesignMatrixCollection([self, matrix])
 
     def __repr__(self):
         return "{} DesignMatrix {}".format(self.name, self.shape)

@@ -1,0 +1,145 @@
+"""Host-side (no GPU) behaviour the reference's own tests pin on the hot path's containers:
+/root/reference/tests/test_periodogram.py:364-431 (error messages),
+/root/reference/tests/correctors/test_designmatrix.py:12-141 (DesignMatrix / DesignMatrixCollection),
+/root/reference/tests/correctors/test_regressioncorrector.py:86-118 (input validation of RegressionCorrector)."""
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+from numpy.testing import assert_array_equal
+
+import lightkurve_b200 as lk
+from lightkurve_b200 import units as u
+from lightkurve_b200.correctors import DesignMatrix, DesignMatrixCollection, RegressionCorrector
+from lightkurve_b200.periodogram import Periodogram
+from lightkurve_b200.utils import LightkurveWarning
+
+
+def test_periodogram_error_messages():
+    lc = lk.LightCurve(time=np.arange(1000), flux=np.random.normal(1, 0.1, 1000), flux_err=np.zeros(1000) + 0.1)
+    with pytest.raises(ValueError):
+        lc.to_periodogram(maximum_frequency=0.1, minimum_period=10)
+    with pytest.raises(ValueError) as err:
+        lc.to_periodogram(maximum_frequency=0.1, minimum_frequency=10)
+    assert err.value.args[0] == "minimum_frequency cannot be larger than maximum_frequency"
+    with pytest.raises(ValueError) as err:
+        lc.to_periodogram(maximum_period=0.1, minimum_period=10)
+    assert err.value.args[0] == "minimum_period cannot be larger than maximum_period"
+    with pytest.raises(ValueError):
+        lc.to_periodogram(frequency=np.arange(10), period=np.arange(10))
+    cases = [
+        (lambda: Periodogram([0], [1]), "frequency must be an `astropy.units.Quantity` object."),
+        (lambda: Periodogram([0] * u.Hz, [1]), "power must be an `astropy.units.Quantity` object."),
+        (lambda: Periodogram([0] * u.Hz, [1] * u.K), "frequency and power must have a length greater than 1."),
+        (lambda: Periodogram([0, 1, 2, 3] * u.Hz, [1, 1] * u.K), "frequency and power must have the same length."),
+        (lambda: Periodogram([0, 1, 2] * u.K, [1, 1, 1] * u.K), "Frequency must be in units of 1/time."),
+        (lambda: Periodogram([0, 1, 2] * u.Hz, [1, 1, 1] * u.K).bin(binsize=-2),
+         "binsize must be larger than or equal to 1"),
+    ]
+    for fn, msg in cases:
+        with pytest.raises(ValueError) as err:
+            fn()
+        assert err.value.args[0] == msg
+    for fn in (lambda: Periodogram([0, 1, 2] * u.Hz, [1, 1, 1] * u.K).bin(method="not-implemented"),
+               lambda: Periodogram([0, 1, 2] * u.Hz, [1, 1, 1] * u.K).smooth(method="not-implemented")):
+        with pytest.raises(ValueError) as err:
+            fn()
+        assert "method 'not-implemented' is not supported" in err.value.args[0]
+
+
+def test_designmatrix_basics():
+    size, name = 10, "testmatrix"
+    df = pd.DataFrame({"vector1": np.ones(size), "vector2": np.zeros(size), "vector3": np.ones(size)})
+    dm = DesignMatrix(df, name=name)
+    assert dm.columns == ["vector1", "vector2", "vector3"]
+    assert dm.name == name
+    assert dm.shape == (size, 3)
+    assert (dm["vector1"] == df["vector1"]).all()
+    assert dm.append_constant().shape == (size, 4)
+    assert dm.pca(nterms=2).shape == (size, 2)
+    assert dm.split([10]).shape == (size, 6)
+    dm.__repr__()
+    dm = DesignMatrix(df, name=name)
+    dm.append_constant(inplace=True)
+    assert dm.shape == (size, 4)
+    dm = DesignMatrix(df, name=name)
+    dm.split([10], inplace=True)
+    assert dm.shape == (size, 6)
+
+
+def test_designmatrix_from_numpy_and_dict():
+    dm = DesignMatrix(np.ones((10, 2)))
+    assert dm.columns == [0, 1]
+    assert dm.name == "unnamed_matrix"
+    assert (dm[0] == np.ones(10)).all()
+    dm = DesignMatrix({"centroid_col": np.ones(10), "centroid_row": np.ones(10)}, name="motion_systematics")
+    assert dm.shape == (10, 2)
+    assert (dm["centroid_col"] == np.ones(10)).all()
+
+
+def test_split():
+    dm = DesignMatrix({"a": np.linspace(0, 9, 10), "b": np.linspace(100, 109, 10)})
+    assert dm.shape == (10, 2)
+    assert dm.split(2).shape == (10, 4)
+    assert dm.split([2, 8]).shape == (10, 6)
+    assert (dm.split([2, 8]).values[2:, 0:2] == 0).all()
+    assert (dm.split([2, 8]).values[:8, 4:] == 0).all()
+    assert len(set(dm.split(2).columns)) == 4
+
+
+def test_standardize_and_pca():
+    dm = DesignMatrix({"const": np.ones(10)})
+    assert (dm.standardize()["const"] == dm["const"]).all()
+    np.random.seed(3)
+    dm = DesignMatrix({"normal": np.random.normal(loc=5, scale=3, size=100)})
+    assert np.round(np.median(dm.standardize()["normal"]), 3) == 0
+    assert np.round(np.std(dm.standardize()["normal"]), 1) == 1
+    dm.standardize(inplace=True)
+    dm = DesignMatrix({"a": np.random.normal(10, 20, 10), "b": np.random.normal(40, 10, 10),
+                       "c": np.random.normal(60, 5, 10)})
+    for nterms in [1, 2, 3]:
+        pc = dm.pca(nterms=nterms)
+        assert pc.shape == (10, nterms)
+        np.testing.assert_allclose(pc.values.T @ pc.values, np.eye(nterms), atol=1e-12)    # orthonormal components
+
+
+def test_collection_basics():
+    dm1 = DesignMatrix(np.ones((5, 1)), columns=["col1"], name="matrix1")
+    dm2 = DesignMatrix(np.zeros((5, 2)), columns=["col2", "col3"], name="matrix2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", LightkurveWarning)              # (an all-zero matrix has rank 0)
+        dmc = DesignMatrixCollection([dm1, dm2])
+        assert_array_equal(dmc["matrix1"].values, dm1.values)
+        assert_array_equal(dmc["matrix2"].values, dm2.values)
+        assert_array_equal(dmc.values, np.hstack((dm1.values, dm2.values)))
+        dmc.__repr__()
+        dmc = dm1.collect(dm2)
+        assert_array_equal(dmc["matrix1"].values, dm1.values)
+        assert_array_equal(dmc.values, np.hstack((dm1.values, dm2.values)))
+        assert isinstance(dmc.to_designmatrix(), DesignMatrix)
+
+
+def test_designmatrix_rank_warning():
+    dm = DesignMatrix({"a": [1, 2, 3]})
+    assert dm.rank == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        dm.validate(rank=True)                                          # good rank: no warning
+    with pytest.warns(LightkurveWarning, match="rank"):
+        dm = DesignMatrix({"a": [1, 2, 3], "b": [1, 1, 1], "c": [1, 1, 1], "d": [1, 1, 1], "e": [3, 4, 5]})
+        assert dm.rank == 2
+        dm.validate(rank=True)
+
+
+def test_regressioncorrector_input_validation():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", LightkurveWarning)
+        bad = [lk.LightCurve(flux=[5, 10], flux_err=[np.nan, 1]), lk.LightCurve(flux=[np.nan, 10], flux_err=[1, 1])]
+    for lc in bad:
+        with pytest.raises(ValueError):
+            RegressionCorrector(lc)
+    RegressionCorrector(lk.LightCurve(flux=[5, 10], flux_err=[np.nan, np.nan]))     # all-NaN errors are allowed
+    for fe in ([1, 0], [1, -10]):                                                   # regression test for #668
+        with pytest.raises(ValueError):
+            RegressionCorrector(lk.LightCurve(flux=[5, 10], flux_err=fe))
