@@ -403,13 +403,29 @@ class FoldedLightCurve(LightCurve):
 
     @property
     def cycle(self):
-        """The cycle number of each cadence (lightcurve.py: FoldedLightCurve.cycle)."""
+        """The cycle of each data point; the first one is cycle 0 whether it is complete or not
+        (lightcurve.py:3213-3229).  Cycle boundaries sit half a period before `epoch_time`; without an explicit
+        epoch the reference takes the smallest folded phase as the epoch - reproduced as is."""
         per = float(np.asarray(self.period.value))
         t = np.asarray(self.time_original.value, dtype=np.float64)
         ep = self.epoch_time
-        t0 = t.min() if ep is None else float(np.asarray(ep.value))
-        return np.asarray(np.floor(((t - t0) + per / 2.0) / per), dtype=int) if ep is not None else \
-            np.asarray(np.round((t - t0) / per), dtype=int)
+        if ep is None:
+            ph_min = float(np.min(np.asarray(self.time.value)))
+            t0 = ph_min * per if self.meta.get("NORMALIZE_PHASE") else ph_min
+        else:
+            t0 = float(np.asarray(ep.value))
+        result = np.asarray(np.floor((t - (t0 - per / 2.0)) / per), dtype=int)
+        return result - result.min()
+
+    @property
+    def odd_mask(self):
+        """Boolean mask of the odd-numbered cycles (1, 3, 5, ...) (lightcurve.py:3231-3250)."""
+        return self.cycle % 2 == 1
+
+    @property
+    def even_mask(self):
+        """Boolean mask of the even-numbered cycles (0, 2, 4, ...)."""
+        return ~self.odd_mask
 
     def __repr__(self):
         return "<FoldedLightCurve length={} period={}>".format(len(self), self.period)

@@ -1,7 +1,8 @@
 """Host-side (no GPU) behaviour the reference's own tests pin on the hot path's containers:
 /root/reference/tests/test_periodogram.py:364-431 (error messages),
 /root/reference/tests/correctors/test_designmatrix.py:12-141 (DesignMatrix / DesignMatrixCollection),
-/root/reference/tests/correctors/test_regressioncorrector.py:86-118 (input validation of RegressionCorrector)."""
+/root/reference/tests/correctors/test_regressioncorrector.py:86-118 (input validation of RegressionCorrector),
+/root/reference/tests/test_lightcurve.py:242-392 (fold, cycle numbering, odd/even masks)."""
 import warnings
 
 import numpy as np
@@ -143,3 +144,52 @@ def test_regressioncorrector_input_validation():
     for fe in ([1, 0], [1, -10]):                                                   # regression test for #668
         with pytest.raises(ValueError):
             RegressionCorrector(lk.LightCurve(flux=[5, 10], flux_err=fe))
+
+
+def test_lightcurve_fold():
+    lc = lk.LightCurve(time=np.linspace(0, 10, 100), flux=np.zeros(100) + 1, targetid=999, label="mystar",
+                       meta={"CCD": 2})
+    fold = lc.fold(period=1)
+    np.testing.assert_almost_equal(fold.phase.value[0], -0.5, 2)
+    np.testing.assert_almost_equal(np.min(fold.phase.value), -0.5, 2)
+    np.testing.assert_almost_equal(np.max(fold.phase.value), 0.5, 2)
+    assert np.min(fold.cycle) == 0                       # reference issue #1397: fold() without epoch_time
+    assert np.max(fold.cycle) == 10
+    assert fold.targetid == lc.targetid and fold.label == lc.label
+    assert set(lc.meta).issubset(set(fold.meta)) and lc.meta["CCD"] == fold.meta["CCD"]
+    assert_array_equal(np.sort(fold.time_original.value), lc.time.value)
+    fold = lc.fold(period=1, epoch_time=-0.1)
+    np.testing.assert_almost_equal(fold.phase.value[0], -0.5, 2)
+    np.testing.assert_almost_equal(np.max(fold.phase.value), 0.5, 2)
+    assert np.min(fold.cycle) == 0 and np.max(fold.cycle) == 10
+    kep = lk.LightCurve(time=lk.units.Time(np.linspace(0, 10, 100), format="bkjd"), flux=np.ones(100))
+    with pytest.warns(LightkurveWarning, match="appears to be given in JD"):
+        kep.fold(10, 2456600)
+    fold = lc.fold(period=1.5, normalize_phase=False)
+    np.testing.assert_almost_equal(np.max(fold.phase.value) - np.min(fold.phase.value), 1.5, 1)
+    fold = lc.fold(period=1.5, normalize_phase=True)
+    assert fold.time.unit == u.dimensionless_unscaled
+    np.testing.assert_almost_equal(np.max(fold.phase.value) - np.min(fold.phase.value), 1, 1)
+    assert len(fold) == 100
+    fold_copy = fold.copy()
+    assert_array_equal(fold.time.value, fold_copy.time.value)
+    assert fold is not fold_copy and fold.flux is not fold_copy.flux
+    lc.fold(period=1 * u.day, epoch_time=5 * u.day)      # reference issue #520: quantities accepted
+
+
+@pytest.mark.parametrize("normalize_phase", [False, True])
+def test_lightcurve_fold_odd_even_masks(normalize_phase):
+    epoch_time, period = 3, 4
+    lc = lk.LightCurve(time=np.linspace(0, 10, 100), flux=np.zeros(100), targetid=999, label="mystar", meta={"CCD": 2})
+    lc.flux = u.Quantity(np.sin((period * 0.75 + lc.time.value - epoch_time) * 2 * np.pi / period))
+    fold = lc.fold(period=period, epoch_time=epoch_time, epoch_phase=0.5, normalize_phase=normalize_phase)
+    odd, even = fold.odd_mask, fold.even_mask
+    assert len(odd) == len(fold.time) and np.all(odd == ~even)
+    wrapped = lc.fold(period=period, epoch_time=epoch_time, epoch_phase=0.5, normalize_phase=normalize_phase,
+                      wrap_phase=0.25)
+    np.testing.assert_almost_equal(wrapped.phase.value[-1], 0.25 if normalize_phase else 0.25, decimal=1)
+    t = fold.time_original.value
+    # cycle 0: [0, 1), 1: [1, 5), 2: [5, 9), 3: [9, 10]
+    expected_cycle = np.where(t < 1, 0, np.where(t < 5, 1, np.where(t < 9, 2, 3)))
+    assert_array_equal(fold.cycle, expected_cycle)
+    assert_array_equal(even, (t < 1) | ((t >= 5) & (t < 9)))
