@@ -18,6 +18,9 @@ One JSON line on stdout (rank 0).  A "step" = one pass of lkb_ls_power_shared ov
             launch / CUDA-event duration of that kernel, vs MEASURED_PEAKS.json bf16 sustained
   cpu_baseline: the oracle port of the reference default (astropy "fast" extirpolation+FFT),
             timed on a bounded sample of the same workload on this box's host cores.
+  secondary.bls: the other half of BASELINE.json's metric ("BLS periods/s"): configs[2] (256 TESS light
+            curves x 20 000 cadences x 50 000 periods x 10 durations per GPU) with its own value / e2e /
+            roofline / cpu_baseline objects (``secondary_bls``); ``--no-secondary`` skips it.
 """
 import argparse
 import json
@@ -221,6 +224,99 @@ def make_workload_sample(name, seed, n_lc=16):
         del WORKLOADS["_sample"]
 
 
+def make_bls_workload(seed, B=256, N=20000, P=50000):
+    """SURVEY.md 8(d) config C3 (BASELINE.json configs[2]): TESS 2-min sector t = 1325 + n/720 d with a 1-d
+    mid-sector gap, N cadences; flux = 1 + N(0, 5e-4) with a box transit (P~U(1,8) d, depth~LogU(5e-4,1e-2),
+    duration~U(0.05,0.3) d) in 75 % of the light curves; flux_err = 5e-4; 10 durations linspace(0.05, 0.33);
+    P periods uniform in frequency between 1/9.26 and 1/0.3314 per day."""
+    rng = np.random.default_rng(seed)
+    t = 1325 + np.arange(N + 720) / 720.0
+    t = np.concatenate([t[: N // 2], t[N // 2 + 720:]])[:N]
+    fluxes, errs = [], []
+    for b in range(B):
+        y = 1 + 5e-4 * rng.normal(size=N)
+        per0, dep, dur0 = rng.uniform(1, 8), 10 ** rng.uniform(np.log10(5e-4), -2), rng.uniform(0.05, 0.3)
+        if b % 4 != 3:
+            y[np.abs((t - t[0] - 0.7 + 0.5 * per0) % per0 - 0.5 * per0) < 0.5 * dur0] -= dep
+        fluxes.append(y)
+        errs.append(np.full(N, 5e-4))
+    duration = np.linspace(0.05, 0.33, 10)
+    period = 1.0 / np.linspace(1 / 0.3314, 1 / 9.26, P)
+    return t, fluxes, errs, period, duration
+
+
+def secondary_bls(engine, torch, dist, rank, world, dev, steps=2, cpu_baseline=True):
+    """Second half of BASELINE.json's metric ("BLS periods/s"): configs[2] (256 TESS light curves x 20 000
+    cadences x 50 000 trial periods x 10 durations per GPU; weak scaling by target, no collective - every
+    (light curve, period) is independent and the 7 result arrays stay with the rank that owns the target).
+    value = (light curve, period) pairs / s from the library's CUDA events around the search kernels (inputs
+    resident), e2e = the same through the host-buffer C-ABI call (H2D of t/y/dy, D2H of the 7 [B, P] arrays)."""
+    B, N, P = 256, 20000, 50000
+    t, fluxes, errs, period, duration = make_bls_workload(1003 + rank, B, N, P)
+    times = [t] * B
+    engine.bls_power(times, fluxes, errs, period, duration)                     # warm-up (workspace growth)
+    engine.profile_enable(True)
+    l0 = engine.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = engine.bls_power(times, fluxes, errs, period, duration)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = engine.launch_count() - l0
+    kms = engine.profile_read()
+    engine.profile_enable(False)
+    tm = torch.tensor([float(np.mean(kms)), 1e3 * wall / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    k_ms, e2e_ms = (float(x) for x in tm.tolist())
+    pairs = float(B) * P * world
+    out = {"metric": "bls_lc_period_pairs_per_s", "unit": "(LC,period)/s", "value": pairs / (k_ms * 1e-3),
+           "ms_per_step": k_ms, "steps": steps, "n_gpus": world, "scaling": "weak", "dtype": "f64 sums, int32 bins",
+           "config": {"workload": "c3: %d TESS LC (%d cadences) x %d periods x %d durations per GPU, oversample 10, "
+                                  "objective likelihood" % (B, N, P, len(duration))},
+           "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "(LC,period)/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(3 * 8 * B * N) * world, "d2h_bytes_per_step": int(7 * 8 * B * P) * world},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": B * P * (24.0 * N + 56) / (k_ms * 1e-3) / 1e9,
+                        "note": "SURVEY 8(d) algorithmic bytes (24*N+56) per (LC, period); the kernel keeps the light "
+                                "curve in L1/L2, so this effective figure may exceed the HBM peak"}}
+    if rank == 0:
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            pk = float(peaks.get("hbm_gbs", 6589.3))
+        except Exception:
+            pk = 6589.3
+        out["roofline"]["peak"] = pk
+        out["roofline"]["frac"] = out["roofline"]["achieved"] / pk
+        if cpu_baseline:
+            out.update(_bls_cpu_leg(t, fluxes, errs, period, duration, res, P))
+    return out
+
+
+def _bls_cpu_leg(t, fluxes, errs, period, duration, res, P):
+    """CPU leg of the BLS line: astropy's bls.c restated in oracle/bls_c.c (OpenMP over periods, all host
+    cores) on one light curve x every 20th period, plus a parity check of the GPU result on that sample."""
+    try:
+        from oracle import bls as obls
+        sub = period[::20]                                                      # 2 500 of the 50 000 periods
+        t0 = time.perf_counter()
+        ref = obls.bls_power_c(t, fluxes[0], errs[0], sub, duration)
+        secs = time.perf_counter() - t0
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        return {"cpu_baseline": {"value": len(sub) / secs, "unit": "(LC,period)/s", "cores": cores, "kind": "port",
+                                 "sample": "1 light curve x %d of the %d periods (%.2f s), astropy bls.c restated "
+                                           "in oracle/bls_c.c, OpenMP over periods" % (len(sub), P, secs)},
+                "parity_on_sample": bool(np.allclose(res["power"][0][::20], ref["power"], rtol=1e-9, atol=0))}
+    except Exception as e:                                                      # pragma: no cover
+        return {"cpu_baseline": {"error": repr(e)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,6 +327,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the BLS (configs[2]) leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -319,6 +416,14 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    secondary = None
+    if not args.no_secondary and args.workload == "c2":
+        try:
+            secondary = {"bls": secondary_bls(engine, torch, dist, rank, world, dev,
+                                              cpu_baseline=not args.no_cpu_baseline)}
+        except Exception as e:                                    # the headline line must survive this leg
+            secondary = {"bls": {"error": repr(e)}}
+
     units_per_step = float(F) * N * B * world
     value = units_per_step * args.steps / (ms_res * 1e-3)
     e2e = units_per_step * args.steps / (ms_e2e * 1e-3)
@@ -364,6 +469,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(Y.nbytes) * world,
                     "d2h_bytes_per_step": int(B * F * 4) * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
