@@ -14,7 +14,8 @@ import numpy as np
 from .. import units as u
 from ..lightcurve import LightCurve
 from ..units import Quantity
-from .designmatrix import DesignMatrix, DesignMatrixCollection
+from .designmatrix import (DesignMatrix, DesignMatrixCollection, SparseDesignMatrix,
+                           SparseDesignMatrixCollection)
 
 log = logging.getLogger(__name__)
 
@@ -64,9 +65,20 @@ class RegressionCorrector:
         return self.lc
 
     @staticmethod
+    def _dense_X(dmc):
+        """The collection's matrix as the C-contiguous float64 array ``lkb_regress`` takes.  The GPU Gram
+        kernel is dense, so a sparse collection is densified here, once per call."""
+        X = dmc.X
+        if hasattr(X, "toarray"):
+            X = X.toarray()
+        return np.ascontiguousarray(X, dtype=np.float64)
+
+    @staticmethod
     def _as_collection(design_matrix_collection):
         if not isinstance(design_matrix_collection, DesignMatrixCollection):
-            if isinstance(design_matrix_collection, DesignMatrix):
+            if isinstance(design_matrix_collection, SparseDesignMatrix):        # regressioncorrector.py:225-232
+                design_matrix_collection = SparseDesignMatrixCollection([design_matrix_collection])
+            elif isinstance(design_matrix_collection, DesignMatrix):
                 design_matrix_collection = DesignMatrixCollection([design_matrix_collection])
             else:
                 raise TypeError("design_matrix_collection must be a DesignMatrix or DesignMatrixCollection")
@@ -83,7 +95,7 @@ class RegressionCorrector:
             self.cadence_mask = np.ones(n, bool)
         else:
             self.cadence_mask = np.asarray(cadence_mask, dtype=bool)
-        X = np.ascontiguousarray(dmc.X, dtype=np.float64)
+        X = self._dense_X(dmc)
         if X.shape[0] != n:
             raise ValueError("design matrix has {} rows but the light curve has {} cadences".format(X.shape[0], n))
         fe = np.asarray(self.lc.flux_err.value, dtype=np.float64)
@@ -134,7 +146,7 @@ class RegressionCorrector:
             k = submatrix.shape[1]
             firstcol, lastcol = idx, idx + k
             idx = lastcol
-            model_flux = np.asarray(submatrix.X, dtype=np.float64).dot(self.coefficients[firstcol:lastcol])
+            model_flux = np.asarray(submatrix.X.dot(self.coefficients[firstcol:lastcol]), dtype=np.float64)
             lcs[submatrix.name] = LightCurve(time=self.lc.time, flux=Quantity(model_flux, self.lc.flux.unit),
                                              flux_err=Quantity(np.zeros(len(model_flux)), self.lc.flux.unit),
                                              label=submatrix.name)
@@ -150,7 +162,7 @@ class RegressionCorrector:
         correctors = [RegressionCorrector(lc) for lc in lightcurves]
         dmc = RegressionCorrector._as_collection(design_matrix_collection)
         dmc.validate()
-        X = np.ascontiguousarray(dmc.X, dtype=np.float64)
+        X = RegressionCorrector._dense_X(dmc)
         n = X.shape[0]
         Y = np.stack([np.asarray(lc.flux.value, dtype=np.float64) for lc in lightcurves])
         if Y.shape[1] != n:

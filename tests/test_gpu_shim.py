@@ -485,3 +485,45 @@ def test_overfit_metric_lombscargle():
     lc_flat.flux_err += 0.5
     lc_sine.flux_err += 0.5
     assert overfit_metric_lombscargle(lc_flat, lc_sine) > 0.5
+
+
+# ------------------------------------------------------------------ sparse design matrices / splines
+def test_sparse_designmatrix_through_gpu():
+    """/root/reference/tests/correctors/test_regressioncorrector.py:13-83 loops every case over
+    ``[design_matrix, design_matrix.to_sparse()]``: the sparse twin must give the same coefficients."""
+    from lightkurve_b200.correctors import SparseDesignMatrix, create_sparse_spline_matrix
+    lc = LightCurve(flux=[5, 10], flux_err=[1, 1])
+    dm = DesignMatrix(np.array([[1, 1], [1, 2]]).astype(float)).to_sparse()
+    assert isinstance(dm, SparseDesignMatrix)
+    rc = RegressionCorrector(lc)
+    rc.correct(dm)
+    assert_almost_equal(rc.coefficients, [0, 5])
+    dm.prior_mu = [99, 99]
+    dm.prior_sigma = [1e-6, 1e-6]
+    rc.correct(dm)
+    assert_almost_equal(rc.coefficients, [99, 99])
+
+    size = 100
+    time = np.linspace(1, 100, size)
+    noise = np.sin(time / 5)
+    noisy_lc = LightCurve(time=time, flux=1 + noise, flux_err=0.1 * np.ones(size))
+    dm = DesignMatrix({"noise": noise, "offset": np.ones(size)}, name="noise_model").to_sparse()
+    rc = RegressionCorrector(noisy_lc)
+    corrected = rc.correct(dm)
+    assert_almost_equal(corrected.normalize().flux.value, np.ones(size))
+    assert set(rc.diagnostic_lightcurves) == {"noise_model"}
+    assert_almost_equal(rc.diagnostic_lightcurves["noise_model"].flux.value, rc.model_lc.flux.value)
+
+    # a spline design matrix removes a smooth trend: same answer as the numpy oracle on the dense matrix
+    rng = np.random.default_rng(11)
+    t = np.linspace(0, 30, 1500)
+    flux = 1 + 0.02 * np.sin(t / 3.0) + 0.01 * (t / 30) ** 2 + 1e-3 * rng.normal(size=len(t))
+    lc = LightCurve(time=t, flux=flux, flux_err=np.full(len(t), 1e-3))
+    spline = create_sparse_spline_matrix(t, n_knots=15)
+    rc = RegressionCorrector(lc)
+    rc.correct(spline, sigma=5, niters=3)
+    ref = odet.regress(spline.values, flux, np.full(len(t), 1e-3), None, np.zeros(spline.shape[1]),
+                       np.full(spline.shape[1], np.inf), sigma=5, niters=3)
+    np.testing.assert_allclose(rc.coefficients, ref["coefficients"], rtol=1e-7, atol=1e-10)
+    assert np.array_equal(rc.outlier_mask, ref["outlier_mask"])
+    assert np.std(rc.corrected_lc.flux.value) < 1.3e-3

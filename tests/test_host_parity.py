@@ -2,7 +2,10 @@
 /root/reference/tests/test_periodogram.py:364-431 (error messages),
 /root/reference/tests/correctors/test_designmatrix.py:12-141 (DesignMatrix / DesignMatrixCollection),
 /root/reference/tests/correctors/test_regressioncorrector.py:86-118 (input validation of RegressionCorrector),
-/root/reference/tests/test_lightcurve.py:242-392 (fold, cycle numbering, odd/even masks)."""
+/root/reference/tests/test_lightcurve.py:242-392 (fold, cycle numbering, odd/even masks),
+/root/reference/tests/correctors/test_sparsedesignmatrix.py:22-186 (SparseDesignMatrix, collections, splines;
+the B-spline basis also against outputs of the reference's own recursion, tests/golden/spline_basis.npz)."""
+import os
 import warnings
 
 import numpy as np
@@ -12,7 +15,11 @@ from numpy.testing import assert_array_equal
 
 import lightkurve_b200 as lk
 from lightkurve_b200 import units as u
-from lightkurve_b200.correctors import DesignMatrix, DesignMatrixCollection, RegressionCorrector
+from scipy import sparse
+
+from lightkurve_b200.correctors import (DesignMatrix, DesignMatrixCollection, RegressionCorrector,
+                                        SparseDesignMatrix, SparseDesignMatrixCollection,
+                                        create_sparse_spline_matrix, create_spline_matrix)
 from lightkurve_b200.periodogram import Periodogram
 from lightkurve_b200.utils import LightkurveWarning
 
@@ -193,3 +200,139 @@ def test_lightcurve_fold_odd_even_masks(normalize_phase):
     expected_cycle = np.where(t < 1, 0, np.where(t < 5, 1, np.where(t < 9, 2, 3)))
     assert_array_equal(fold.cycle, expected_cycle)
     assert_array_equal(even, (t < 1) | ((t >= 5) & (t < 9)))
+
+
+# ---- sparse design matrices (reference: tests/correctors/test_sparsedesignmatrix.py) ----------------
+def test_sparse_designmatrix_basics():
+    size, name = 10, "testmatrix"
+    X = sparse.csr_matrix(np.vstack([np.ones(size), np.arange(size), np.arange(size) ** 2]).T)
+    cols = ["vector1", "vector2", "vector3"]
+    dm = SparseDesignMatrix(X, name=name, columns=cols)
+    assert dm.columns == cols and dm.name == name and dm.shape == (size, 3)
+    assert dm.append_constant().shape == (size, 4)
+    assert dm.pca(nterms=2).shape == (size, 2)
+    assert isinstance(dm.pca(nterms=2), SparseDesignMatrix)
+    assert dm.split([5]).shape == (size, 6)
+    assert "SparseDesignMatrix" in repr(dm)
+    dm.append_constant(inplace=True)
+    assert dm.shape == (size, 4)
+    dm = SparseDesignMatrix(X, name=name, columns=cols)
+    dm.split([5], inplace=True)
+    assert dm.shape == (size, 6)
+    with pytest.raises(ValueError, match="scipy.sparse"):
+        SparseDesignMatrix(np.ones((3, 2)))
+    with pytest.raises(ValueError, match="No such column"):
+        dm["nope"]
+
+
+def test_sparse_split():
+    X = sparse.csr_matrix(np.vstack([np.linspace(0, 9, 10), np.linspace(100, 109, 10)]).T)
+    dm = SparseDesignMatrix(X, columns=["a", "b"])
+    assert dm.shape == (10, 2)
+    assert dm.split(2).shape == (10, 4)
+    assert dm.split([2, 8]).shape == (10, 6)
+    assert (dm.split([2, 8]).values[2:, 0:2] == 0).all()
+    assert (dm.split([2, 8]).values[:8, 4:] == 0).all()
+    assert len(set(dm.split(4).columns)) == 4
+    # same values as the dense split (dense keeps the all-zero copy of column "a" in block 0, sparse drops it)
+    dense = DesignMatrix({"a": np.linspace(1, 10, 10), "b": np.linspace(100, 109, 10)})
+    assert_array_equal(dense.to_sparse().split([2, 8]).values, dense.split([2, 8]).values)
+    assert dm.split([0]) is dm and dm.split([10]) is dm                 # nothing to split at the ends
+    sp = dm.split([2, 8])
+    assert len(sp.prior_mu) == len(sp.prior_sigma) == sp.shape[1]
+
+
+def test_sparse_standardize():
+    dm = SparseDesignMatrix(sparse.csr_matrix(np.ones((10, 1))), columns=["const"])
+    assert (dm.standardize()["const"] == dm["const"]).all()             # zero spread: unchanged
+    rng = np.random.default_rng(5)
+    v = rng.normal(loc=5, scale=3, size=100)
+    dm = SparseDesignMatrix(sparse.csr_matrix(v[:, None]), columns=["normal"])
+    z = dm.standardize()["normal"].ravel()
+    np.testing.assert_allclose(z, (v - v.mean()) / v.std(ddof=1), rtol=1e-12)
+    # zeros are "not stored": they stay zero and do not enter the statistics
+    w = v.copy()
+    w[::4] = 0
+    z = SparseDesignMatrix(sparse.csr_matrix(w[:, None]), columns=["x"]).standardize()["x"].ravel()
+    nz = w != 0
+    assert (z[~nz] == 0).all()
+    np.testing.assert_allclose(z[nz], (w[nz] - w[nz].mean()) / w[nz].std(ddof=1), rtol=1e-12)
+    dm.standardize(inplace=True)
+
+
+def test_sparse_collection_basics():
+    size = 5
+    dm1 = DesignMatrix(np.ones((size, 1)), columns=["col1"], name="matrix1").to_sparse()
+    dm2 = DesignMatrix(np.zeros((size, 2)), columns=["col2", "col3"], name="matrix2").to_sparse()
+    dmc = SparseDesignMatrixCollection([dm1, dm2])
+    assert_array_equal(dmc["matrix1"].values, dm1.values)
+    assert_array_equal(dmc["matrix2"].values, dm2.values)
+    assert_array_equal(dmc.values, np.hstack((dm1.values, dm2.values)))
+    assert sparse.issparse(dmc.X) and dmc.X.shape == (size, 3)
+    assert "SparseDesignMatrixCollection" in repr(dmc)
+    dmc = dm1.collect(dm2)
+    assert isinstance(dmc, SparseDesignMatrixCollection)
+    assert_array_equal(dmc.values, np.hstack((dm1.values, dm2.values)))
+    dm1d = DesignMatrix(np.ones((size, 1)), columns=["col1"], name="matrix1")
+    with pytest.warns(LightkurveWarning, match="Sparse matrices will be converted to dense matrices."):
+        dmc = DesignMatrixCollection([dm1d, dm2])
+    assert not np.any([sparse.issparse(d.X) for d in dmc])
+    with pytest.warns(LightkurveWarning, match="Dense matrices will be converted to sparse matrices."):
+        dmc = SparseDesignMatrixCollection([dm1d, dm2])
+    assert np.all([sparse.issparse(d.X) for d in dmc])
+    assert isinstance(dmc.to_designmatrix(), SparseDesignMatrix)
+
+
+def test_sparse_designmatrix_rank():
+    dm = DesignMatrix({"a": [1, 2, 3]}).to_sparse()
+    assert dm.rank == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        dm.validate(rank=True)
+    dm = DesignMatrix({"a": [1, 2, 3], "b": [1, 1, 1], "c": [1, 1, 1], "d": [1, 1, 1], "e": [3, 4, 5]}).to_sparse()
+    assert dm.rank == 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        dm.validate()                                                   # sparse: rank check off by default
+    with pytest.warns(LightkurveWarning, match="rank"):
+        dm.validate(rank=True)
+
+
+def test_splines_dense_equals_sparse():
+    x = np.linspace(0, 1, 100)
+    dense = create_spline_matrix(x, knots=[0.1, 0.3, 0.6, 0.9], degree=2)
+    sp = create_sparse_spline_matrix(x, knots=[0.1, 0.3, 0.6, 0.9], degree=2)
+    assert np.allclose(dense.values, sp.values)
+    assert isinstance(dense, DesignMatrix) and isinstance(sp, SparseDesignMatrix)
+    # defaults: 20 cubic basis functions that sum to one everywhere (partition of unity)
+    for m in (create_spline_matrix(x), create_sparse_spline_matrix(x)):
+        assert m.shape == (100, 20)
+        np.testing.assert_allclose(m.values.sum(axis=1), 1.0, atol=1e-14)
+    assert list(create_spline_matrix(x).columns) == ["knot%d" % (i + 1) for i in range(20)]
+    assert create_spline_matrix(x, n_knots=8, include_intercept=False).shape == (100, 8)
+    with pytest.raises(ValueError, match="integer"):
+        create_sparse_spline_matrix(x, n_knots=5.0)
+    with pytest.raises(ValueError, match="greater than degree"):
+        create_sparse_spline_matrix(x, n_knots=3, degree=3)
+
+
+def test_sparse_spline_matches_reference_recursion():
+    """Bit-exact against matrices produced by the reference's own `_spline_basis_vector` recursion
+    (tests/golden/make_spline_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spline_basis.npz"))
+    for i in range(int(g["ncases"])):
+        n_knots, degree = (int(v) for v in g["cfg%d" % i])
+        m = create_sparse_spline_matrix(g["x%d" % i], n_knots=n_knots, degree=degree)
+        assert_array_equal(m.values, g["m%d" % i])
+
+
+def test_regression_oracle_with_sparse_matrix_is_the_dense_problem():
+    """`RegressionCorrector` hands a sparse collection to the GPU as its dense equivalent: the host-side
+    conversion must reproduce the matrix exactly (the GPU parity tests then cover both)."""
+    x = np.linspace(0, 10, 200)
+    dmc = SparseDesignMatrixCollection([create_sparse_spline_matrix(x, n_knots=10),
+                                        DesignMatrix(np.ones((200, 1)), name="offset").to_sparse()])
+    X = RegressionCorrector._dense_X(dmc)
+    assert isinstance(X, np.ndarray) and X.flags.c_contiguous and X.dtype == np.float64
+    assert_array_equal(X, dmc.values)
+    assert isinstance(RegressionCorrector._as_collection(create_sparse_spline_matrix(x)), SparseDesignMatrixCollection)
