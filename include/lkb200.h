@@ -32,7 +32,8 @@ extern "C" {
 #define LKB_E_CUDA        -2   /* CUDA runtime error / no device */
 #define LKB_E_OOM         -3   /* device allocation failed */
 #define LKB_E_SINGULAR    -4   /* normal equations singular (numpy LinAlgError analogue) */
-#define LKB_E_UNSUPPORTED -5   /* shape outside what the kernels support */
+#define LKB_E_UNSUPPORTED -5   /* shape outside what the kernels support / optional component absent */
+#define LKB_E_NCCL        -6   /* NCCL call failed */
 
 #define LKB_MEM_HOST   0
 #define LKB_MEM_DEVICE 1
@@ -185,6 +186,27 @@ int lkb_nanmedian_std(const double* x, const int64_t* offsets, int B,
  * power/background [B, F] fp64 (host or device per `mem`).  Bins covered by no window get NaN (0/0). */
 int lkb_pg_logmedian(const double* power, int B, int64_t F, const int32_t* win_lo, const int32_t* win_hi, int W,
                      double corr_factor, double* background, int mem, void* stream);
+
+/* ---- multi-GPU: the one exchange step of the path ------------------ */
+/* A LightCurveCollection is sharded BY TARGET over one process per GPU; the only data exchange is the
+ * reassembly of the fp32 power array [B, F] from the per-rank blocks (the reference has no counterpart: it
+ * loops over light curves in one Python process, collections.py:145-276).  NCCL is bound at run time
+ * (dlopen), so single-GPU use needs no NCCL.  Bootstrap: rank 0 fills a 128-byte id with
+ * lkb_nccl_unique_id, the host program carries it to the other ranks (torch.distributed store, MPI, a
+ * pipe ...), then EVERY rank calls lkb_nccl_init(rank, world_size, id) after lkb_init(device) - collectively,
+ * like ncclCommInitRank.  lkb_allgather_f32 gathers `n_local` floats from every rank into
+ * global[world_size * n_local] (rank-major) - DEVICE pointers, asynchronous on `stream` (0 = default
+ * stream), one ncclAllGather over NVLink/NVSwitch.  Ragged shards are padded to a common n_local by the
+ * caller (lightkurve_b200/dist.py).  Errors: LKB_E_UNSUPPORTED if no NCCL library can be loaded,
+ * LKB_E_NCCL if an NCCL call fails, LKB_E_ARG without a communicator. */
+#define LKB_NCCL_ID_BYTES 128
+int lkb_nccl_version(void);            /* NCCL_VERSION_CODE of the bound library, 0 if none */
+int lkb_nccl_unique_id(void* id_out /* [LKB_NCCL_ID_BYTES] */);
+int lkb_nccl_init(int rank, int world_size, const void* id /* [LKB_NCCL_ID_BYTES] */);
+int lkb_nccl_shutdown(void);
+int lkb_nccl_rank(void);               /* -1 without a communicator */
+int lkb_nccl_world_size(void);         /* 0 without a communicator */
+int lkb_allgather_f32(const float* local, int64_t n_local, float* global, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblkb200.so")
 
-OK, E_ARG, E_CUDA, E_OOM, E_SINGULAR, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+OK, E_ARG, E_CUDA, E_OOM, E_SINGULAR, E_UNSUPPORTED, E_NCCL = 0, -1, -2, -3, -4, -5, -6
+NCCL_ID_BYTES = 128
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F32, DTYPE_F64 = 0, 1
 LS_NORM_PSD_RAW, LS_NORM_PSD_SCALE, LS_NORM_AMPLITUDE = 0, 1, 2
@@ -48,6 +49,13 @@ SIGNATURES = {
     "lkb_savgol_tables": (c_int, [c_int, c_int, c_vp, c_vp]),
     "lkb_nanmedian_std": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp]),
     "lkb_pg_logmedian": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_dbl, c_vp, c_int, c_vp]),
+    "lkb_nccl_version": (c_int, []),
+    "lkb_nccl_unique_id": (c_int, [c_vp]),
+    "lkb_nccl_init": (c_int, [c_int, c_int, c_vp]),
+    "lkb_nccl_shutdown": (c_int, []),
+    "lkb_nccl_rank": (c_int, []),
+    "lkb_nccl_world_size": (c_int, []),
+    "lkb_allgather_f32": (c_int, [c_vp, c_i64, c_vp, c_vp]),
 }
 
 _lib = None

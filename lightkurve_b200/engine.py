@@ -361,3 +361,54 @@ def pg_logmedian(frequency, power, filter_width):
         inv[order] = np.arange(F)
         out = out[:, inv]
     return out[0] if one else out
+
+
+# --------------------------------------------------------------------------------------
+# multi-GPU exchange step: NCCL all-gather through the C ABI
+# --------------------------------------------------------------------------------------
+def nccl_version():
+    """NCCL_VERSION_CODE of the library the C ABI bound at run time (0: none could be loaded)."""
+    return int(L.load().lkb_nccl_version())
+
+
+def nccl_unique_id():
+    """128-byte NCCL id (bytes).  Rank 0 creates it; the host program carries it to the other ranks."""
+    buf = np.zeros(L.NCCL_ID_BYTES, dtype=np.uint8)
+    L.check(L.load().lkb_nccl_unique_id(L.ptr(buf)))
+    return buf.tobytes()
+
+
+def nccl_init(rank, world_size, unique_id):
+    """Collective: every rank calls this with the SAME id after ``init(device)``."""
+    buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+    if buf.size != L.NCCL_ID_BYTES:
+        raise ValueError("an NCCL unique id has %d bytes, got %d" % (L.NCCL_ID_BYTES, buf.size))
+    L.check(L.load().lkb_nccl_init(int(rank), int(world_size), L.ptr(buf)))
+
+
+def nccl_shutdown():
+    L.check(L.load().lkb_nccl_shutdown())
+
+
+def nccl_rank_world():
+    lib = L.load()
+    return int(lib.lkb_nccl_rank()), int(lib.lkb_nccl_world_size())
+
+
+def allgather_f32(local, out=None):
+    """One ncclAllGather of a contiguous CUDA float32 torch tensor `local` ([n, ...], same shape on every
+    rank) into `out` ([world * n, ...], rank-major), asynchronous on the current torch stream."""
+    import torch
+    lib = L.load()
+    world = int(lib.lkb_nccl_world_size())
+    if world <= 0:
+        raise ValueError("allgather_f32: no communicator (call engine.nccl_init on every rank first)")
+    if not (_is_torch(local) and local.is_cuda and local.dtype == torch.float32 and local.is_contiguous()):
+        raise TypeError("allgather_f32 needs a contiguous CUDA float32 tensor")
+    shape = (world * local.shape[0],) + tuple(local.shape[1:])
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=local.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("allgather_f32: `out` must be a contiguous CUDA float32 tensor of shape %r" % (shape,))
+    L.check(lib.lkb_allgather_f32(L.ptr(local), int(local.numel()), L.ptr(out), _stream_ptr()))
+    return out

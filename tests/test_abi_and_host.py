@@ -266,3 +266,20 @@ def test_logmedian_windows_match_reference_loop():
                 x0 += 0.5 * fw
                 w += 1
             assert w == len(lo)
+
+
+def test_nccl_entry_points_without_a_communicator():
+    """The exchange step of the C ABI (include/lkb200.h, multi-GPU section): NCCL is bound at run time, ids are
+    128 bytes, and the collective refuses to run before lkb_nccl_init - all checkable without a GPU."""
+    from lightkurve_b200 import _lib as L, engine
+    assert engine.nccl_rank_world() == (-1, 0)
+    with pytest.raises(ValueError, match="no communicator"):
+        L.check(L.load().lkb_allgather_f32(None, 4, None, None))
+    with pytest.raises(ValueError, match="no communicator"):
+        engine.allgather_f32(None)
+    with pytest.raises(ValueError, match="128 bytes"):
+        engine.nccl_init(0, 1, b"short")
+    if engine.nccl_version() > 0:                                   # an NCCL library is present in this image
+        a, b = engine.nccl_unique_id(), engine.nccl_unique_id()
+        assert len(a) == len(b) == 128 and a != b
+    engine.nccl_shutdown()                                          # no communicator: a no-op
