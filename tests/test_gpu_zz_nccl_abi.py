@@ -13,6 +13,20 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _get(q, procs, timeout=240.0):
+    """q.get that gives up as soon as a worker has died (instead of sitting out the whole timeout)."""
+    import queue
+    import time
+    t0 = time.time()
+    while True:
+        try:
+            return q.get(timeout=1.0)
+        except queue.Empty:
+            dead = [p for p in procs if not p.is_alive() and p.exitcode not in (0, None)]
+            assert not dead, "worker exited with code %r" % [p.exitcode for p in dead]
+            assert time.time() - t0 < timeout, "timed out waiting for the workers"
+
+
 def _make(seed=9, n_lc=11):
     rng = np.random.default_rng(seed)
     times, fluxes = [], []
@@ -69,7 +83,7 @@ def test_abi_nccl_allgather_and_sharded_ls():
     results = {}
     try:
         for _ in range(world):
-            rank, plain_ok, arr = out_q.get(timeout=240)
+            rank, plain_ok, arr = _get(out_q, procs)
             assert plain_ok
             results[rank] = arr
         for p in procs:
@@ -85,3 +99,41 @@ def test_abi_nccl_allgather_and_sharded_ls():
         ref = np.sqrt(ols.ls_slow_psd(times[b], fluxes[b], freq)) * np.sqrt(4.0 / len(times[b]))
         got = results[0][b].astype(np.float64)
         assert np.all(np.abs(got - ref) <= 1e-5 * ref.max() + 1e-4 * ref)
+
+
+def _single_rank_worker(out_q):
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(0)
+    from lightkurve_b200 import engine
+    from lightkurve_b200.dist import init_abi_communicator, ls_power_sharded
+    engine.init(0)
+    init_abi_communicator(0, 1, lambda uid: uid)
+    ok = engine.nccl_rank_world() == (0, 1) and engine.nccl_version() > 0
+    loc = torch.arange(12, device="cuda", dtype=torch.float32).reshape(3, 4)
+    got = engine.allgather_f32(loc)
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(got, loc))
+    times, fluxes, freq = _make(n_lc=4)
+    out = ls_power_sharded(times, fluxes, freq, "amplitude", via="abi")
+    ref = engine.ls_power_ragged(times, fluxes, freq, "amplitude")
+    ok = ok and np.array_equal(out.cpu().numpy(), np.asarray(ref))
+    engine.nccl_shutdown()
+    ok = ok and engine.nccl_rank_world() == (-1, 0)
+    out_q.put(bool(ok))
+
+
+def test_abi_nccl_single_rank_communicator():
+    """World size 1 on one GPU: exercises the run-time NCCL binding, the id / init / all-gather / shutdown calls
+    and the sharded path on top of them (a child process, so that the communicator never outlives the test)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    p = ctx.Process(target=_single_rank_worker, args=(out_q,), daemon=True)
+    p.start()
+    try:
+        assert _get(out_q, [p]) is True
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    finally:
+        if p.is_alive():
+            p.kill()
