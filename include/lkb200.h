@@ -50,6 +50,8 @@ extern "C" {
 #define LKB_LS_ALGO_AUTO     0   /* tcgen05 when shapes allow, else SIMT */
 #define LKB_LS_ALGO_SIMT     1   /* fp32 CUDA-core tiled contraction */
 #define LKB_LS_ALGO_TCGEN05  2   /* split-fp16 tcgen05.mma, fp32 TMEM accumulators */
+#define LKB_LS_ALGO_NUFFT    3   /* type-1 NUFFT (spread + FFT), regular grids f_k = (k0 + k) df only; opt-in:
+                                    AUTO does not select it (round 1: CPU-verified, not yet measured on hardware) */
 
 /* BLS objective (astropy BoxLeastSquares.power objective=) */
 #define LKB_BLS_LIKELIHOOD 0

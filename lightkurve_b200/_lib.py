@@ -17,7 +17,7 @@ NCCL_ID_BYTES = 128
 MEM_HOST, MEM_DEVICE = 0, 1
 DTYPE_F32, DTYPE_F64 = 0, 1
 LS_NORM_PSD_RAW, LS_NORM_PSD_SCALE, LS_NORM_AMPLITUDE = 0, 1, 2
-LS_ALGO_AUTO, LS_ALGO_SIMT, LS_ALGO_TCGEN05 = 0, 1, 2
+LS_ALGO_AUTO, LS_ALGO_SIMT, LS_ALGO_TCGEN05, LS_ALGO_NUFFT = 0, 1, 2, 3
 BLS_LIKELIHOOD, BLS_SNR = 0, 1
 
 c_int, c_i64, c_dbl, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

@@ -846,6 +846,11 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
                  double norm_scale, float* d_pow, cudaStream_t st, cudaEvent_t rot_ready, int ws_alt = 0);   // ls_tc.cu
 bool ls_tc_window_in_kernel(int64_t Npad, bool regular);
 bool ls_tc_supported(int B, int64_t N, int64_t F);
+bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df, double t_last);              // ls_nufft.cu
+int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
+                    const float* d_absmax, int B,
+                    const double* d_freq, int64_t F, double grid_f0, double grid_df, float4* d_rot, float2* d_rot2,
+                    int64_t F_low, int normalization, double norm_scale, float* d_pow, cudaStream_t st);
 
 int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,
                     int normalization, const double* norm_scale, float* power, int mem, cudaStream_t st,
@@ -854,7 +859,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   LKB_REQUIRE(y_dtype == LKB_DTYPE_F32 || y_dtype == LKB_DTYPE_F64, "lkb_ls_power_shared: bad y_dtype");
   LKB_REQUIRE(normalization >= 0 && normalization <= 2, "lkb_ls_power_shared: bad normalization");
   LKB_REQUIRE(normalization != LKB_LS_NORM_PSD_SCALE || norm_scale, "lkb_ls_power_shared: norm_scale required");
-  LKB_REQUIRE(algo >= 0 && algo <= 2, "lkb_ls_power_shared: bad algo");
+  LKB_REQUIRE(algo >= 0 && algo <= 3, "lkb_ls_power_shared: bad algo");
   LKB_TRY(ensure_device());
   const int64_t Npad = ((N + 63) / 64) * 64;
   const size_t ysz = (y_dtype == LKB_DTYPE_F32) ? 4 : 8;
@@ -940,6 +945,13 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   }
   // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
   const double lowf_max = (h_meta[3] > 0.0) ? LS_LOWF_CYCLES / h_meta[3] : 0.0;
+  // NUFFT path (ls_nufft.cu): opt-in only - `auto` does not select it until it has been measured on hardware
+  const bool use_nufft = algo == LKB_LS_ALGO_NUFFT;
+  if (use_nufft && !ls_nufft_supported(F, regular, grid_f0, grid_df, h_meta[3])) {
+    set_error("lkb_ls_power_shared: the NUFFT path needs a regular grid f_k = (k0 + k) df with integer k0 and "
+              "df * baseline <= 1");
+    return LKB_E_UNSUPPORTED;
+  }
   bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
   if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
     set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
@@ -960,7 +972,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   // this kernel's full-fp64 path.
   const bool win_in_kernel = use_tc && ls_tc_window_in_kernel(Npad, regular);
   int64_t F_win = F;
-  if (win_in_kernel) {
+  if (win_in_kernel || use_nufft) {     // only the low rows need the fp64 window path; the rest comes from the kernels
     const double nlow = floor((lowf_max - grid_f0) / grid_df) + 2.0;
     F_win = (nlow < 0.0) ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
   }
@@ -1018,7 +1030,11 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     LKB_CUDA_CHECK(cudaStreamSynchronize(st));
     return LKB_OK;
   }
-  if (use_tc) {
+  if (use_nufft) {
+    LKB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+    LKB_TRY(ls_nufft_launch(d_t, N, d_yc, Npad, d_ysumf, d_absmax, B, d_freq, F, grid_f0, grid_df, d_rot, d_rot2, F_win,
+                            normalization, ns, d_pow, st));
+  } else if (use_tc) {
     LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc, d_absmax, B, d_freq, F, d_rot, d_rot2, win_in_kernel, lowf_max, grid_f0, grid_df, normalization, ns, d_pow, st, ev_join));
   } else {
     static bool attr_set = false;

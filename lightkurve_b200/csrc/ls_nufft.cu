@@ -1,0 +1,309 @@
+// liblkb200 - shared-grid Lomb-Scargle by a type-1 NUFFT (LKB_LS_ALGO_NUFFT; OPT-IN in round 1: written and
+// verified on the CPU through tests/native/nufft_host_harness.cpp after the round's GPU budget was spent -
+// `auto` never selects it until it has been measured on hardware).
+//
+// Why: the contraction kernels (ls_tc.cu, ls.cu) do 4 N F flops per light curve; on a REGULAR frequency grid
+// the same trig sums are the Fourier coefficients of the (non-uniformly sampled) light curve, which a
+// spreading step + one FFT give in N w + 2.5 M log2 M flops (config 2: 5e7 instead of 2.6e10 per light curve),
+// within 0.02-0.16 of the parity tolerance in fp32 (tools/nufft_ls_model.py) - more accurate than the
+// split-fp16 tensor path (0.47).  The whole batch becomes an HBM sweep: fine grids [B/2, M] complex64.
+// This is the algorithm behind the reference's optional ls_method="fastnifty" (nifty-ls / finufft,
+// /root/reference/pyproject.toml:48, src/lightkurve/periodogram.py:917-946).
+//
+// Kernels (all "one thread = one function of nufft_core.h"):
+//   nufft_cad_kernel        per cadence: leftmost cell + offset of its kernel support on the M-cell grid
+//   nufft_first_ge_kernel   per cell: first cadence whose support starts at or after it (binary search)
+//   nufft_spread_kernel     per (cell, pair of light curves): gather of the cadences reaching the cell
+//   nufft_fft_pass_kernel   per butterfly: out-of-place Stockham pass of radix 16/8/4/2
+//   nufft_deconv_kernel     per mode: 1 / phihat and the grid-shift phase
+//   nufft_rot_kernel        per frequency: window terms (tau rotation, 1/CC', 1/SS') from the transform of
+//                           a_n = 1 on a grid twice as fine (modes kk and 2 kk)
+//   nufft_lowrows_kernel    per (low frequency, light curve): direct fp32/fp64 sums with the cos-1 design matrix
+//                           for f * baseline <= LS_LOWF_CYCLES (the rows whose sums cancel)
+//   nufft_finish_kernel     per (frequency, pair): unpack the two light curves, deconvolve, epilogue -> power
+// HBM traffic at config 2 (B = 1024, M = 2^19): spread 2.1 GB written, 5 passes x 4.3 GB, finish ~1 GB read +
+// 0.4 GB written  ~ 25 GB  ~ 4 ms at the measured 6.6 TB/s.  Next steps once measured: fuse the spreading into
+// the first pass (80 % of its input is zero for oversample 5), shared-memory passes (2 instead of 5 sweeps).
+#include "common.cuh"
+#include "ls_common.cuh"
+#include "nufft_core.h"
+
+namespace lkb {
+
+using nufft::Cad;
+
+namespace {
+
+struct GlNodes {
+  double x[32], w[32];
+};
+
+__global__ void nufft_cad_kernel(const double* __restrict__ t, int64_t N, double df, int64_t M, int w,
+                                 Cad* __restrict__ cad, int* __restrict__ unsorted) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  cad[n] = nufft::cad_entry(t[n], df, M, w);
+  if (n > 0 && t[n] < t[n - 1]) *unsorted = 1;
+  if (t[n] < 0.0) *unsorted = 1;
+}
+
+__global__ void nufft_first_ge_kernel(const Cad* __restrict__ cad, int64_t N, int64_t L, int32_t* __restrict__ first_ge) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < L) first_ge[c] = nufft::first_ge_entry(c, cad, N);
+}
+
+// Z[pair][m] = sum over cadences of phi * (y[2 pair][n] + i y[2 pair + 1][n])
+__global__ void __launch_bounds__(256)
+nufft_spread_kernel(const int32_t* __restrict__ first_ge, const Cad* __restrict__ cad, const float* __restrict__ y,
+                    int64_t ystride, const float* __restrict__ absmax, int B, int npairs, int w, float beta, int log2M,
+                    float2* __restrict__ Z) {
+  const int64_t M = (int64_t)1 << log2M;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)npairs << log2M) return;
+  const int64_t pair = gid >> log2M, m = gid & (M - 1);
+  const float* y0 = y + (2 * pair) * ystride;
+  const float* y1 = (2 * pair + 1 < B) ? y0 + ystride : nullptr;
+  const float s0 = absmax ? nufft::pow2_scale(absmax[2 * pair]) : 1.0f;
+  const float s1 = (absmax && y1) ? nufft::pow2_scale(absmax[2 * pair + 1]) : 1.0f;
+  Z[gid] = nufft::spread_cell(m, first_ge, cad, y0, y1, s0, s1, w, beta, M);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+nufft_fft_pass_kernel(const float2* __restrict__ x, float2* __restrict__ y, int64_t Ns, int log2M, int64_t total) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int64_t M = (int64_t)1 << log2M, per = M / R;
+  const int64_t pair = gid / per, i = gid - pair * per;
+  nufft::fft_pass_butterfly<R>(x + pair * M, y + pair * M, i, Ns, M);
+}
+
+__global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
+                                    float2* __restrict__ dec) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double re, im;
+  nufft::deconv_factor(k_first + k, M, w, beta, gl.x, gl.w, 32, &re, &im);
+  dec[k] = make_float2((float)re, (float)im);
+}
+
+// window terms of the rows k >= k_lo from the transform Zw (length M2) of unit strengths: mode kk gives
+// (C, S) = sum (cos, sin)(2 pi f t), mode 2 kk gives (C2, S2) = sum (cos, sin)(4 pi f t).
+// dec2[j] is the deconvolution factor of mode j (j = 0 .. 2 (k0 + F) - 1).
+__global__ void nufft_rot_kernel(const float2* __restrict__ Zw, int64_t M2, const float2* __restrict__ dec2, int64_t k0,
+                                 int64_t F, int64_t k_lo, double Nd, float4* __restrict__ rot, float2* __restrict__ rot2) {
+  const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= F) return;
+  const int64_t kk = k0 + k;
+  float2 a, unused;
+  nufft::unpack_pair(Zw, kk, M2, dec2[kk], 1.0f, 1.0f, &a, &unused);
+  float2 a2;
+  nufft::unpack_pair(Zw, 2 * kk, M2, dec2[2 * kk], 1.0f, 1.0f, &a2, &unused);
+  LsSums<double> d;
+  d.zero();
+  d.c = (double)a.x;
+  d.s = (double)a.y;
+  d.cc = 0.5 * (Nd + (double)a2.x);       // sum cos^2 = (N + sum cos 2wt) / 2
+  d.sc = 0.5 * (double)a2.y;              // sum sin cos = sum sin 2wt / 2
+  double ct, st, cc, ss;
+  ls_rotation(d, Nd, ct, st, cc, ss);
+  const double kf = 1.0 / (2.0 * Nd);
+  rot[k] = make_float4((float)ct, (float)st, (float)(kf / cc), (float)(kf / ss));
+  rot2[k] = make_float2((float)((d.c * ct + d.s * st) / Nd), (float)((d.s * ct - d.c * st) / Nd));
+}
+
+// rows with f * baseline <= LS_LOWF_CYCLES: direct sums, one warp per (row, light curve); the design matrix
+// holds cos - 1 (ls_common.cuh) and rot / rot2 of these rows come from the fp64 path of ls_window_kernel.
+__global__ void __launch_bounds__(128)
+nufft_lowrows_kernel(const double* __restrict__ t, int64_t N, const float* __restrict__ yc, int64_t ystride, int B,
+                     const double* __restrict__ freq, int64_t F_low, int64_t F, const float4* __restrict__ rot,
+                     const float2* __restrict__ rot2, const float* __restrict__ ysum, int normalization, float scale,
+                     float* __restrict__ power) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (job >= F_low * B) return;
+  const int64_t b = job / F_low, k = job - b * F_low;
+  const double fr = freq[k];
+  const float* y = yc + b * ystride;
+  double ch = 0.0, sh = 0.0;
+  for (int64_t c0 = 0; c0 < N; c0 += 32 * 64) {
+    float pc = 0.f, ps = 0.f;
+    const int64_t c1 = min(N, c0 + (int64_t)32 * 64);
+    for (int64_t i = c0 + lane; i < c1; i += 32) {
+      float s, cm1;
+      ls_sincos_cycles_low(fr * t[i], s, cm1);
+      const float v = y[i];
+      pc = fmaf(v, cm1, pc);
+      ps = fmaf(v, s, ps);
+    }
+    ch += (double)pc;
+    sh += (double)ps;
+  }
+  ch = warp_sum(ch);
+  sh = warp_sum(sh);
+  if (lane == 0)
+    power[b * F + k] = ls_epilogue_shared((float)ch, (float)sh, rot[k], rot2[k], ysum[b], (float)N, normalization,
+                                          scale, true);
+}
+
+__global__ void __launch_bounds__(256)
+nufft_finish_kernel(const float2* __restrict__ Z, int log2M, const float2* __restrict__ dec, int64_t k0, int64_t F,
+                    int64_t k_lo, const float4* __restrict__ rot, const float2* __restrict__ rot2,
+                    const float* __restrict__ ysum, const float* __restrict__ absmax, float Nf, int normalization,
+                    float scale, int B, int npairs, float* __restrict__ power) {
+  const int64_t nk = F - k_lo;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= nk * npairs) return;
+  const int64_t pair = gid / nk, k = k_lo + (gid - pair * nk);
+  const int64_t M = (int64_t)1 << log2M;
+  const int64_t b0 = 2 * pair;
+  const float inv0 = 1.0f / nufft::pow2_scale(absmax[b0]);
+  const float inv1 = (b0 + 1 < B) ? 1.0f / nufft::pow2_scale(absmax[b0 + 1]) : 1.0f;
+  float2 a, b;
+  nufft::unpack_pair(Z + pair * M, k0 + k, M, dec[k], inv0, inv1, &a, &b);
+  const float4 r = rot[k];
+  const float2 r2 = rot2[k];
+  power[b0 * F + k] = ls_epilogue_shared(a.x, a.y, r, r2, ysum[b0], Nf, normalization, scale);
+  if (b0 + 1 < B) power[(b0 + 1) * F + k] = ls_epilogue_shared(b.x, b.y, r, r2, ysum[b0 + 1], Nf, normalization, scale);
+}
+
+__global__ void nufft_fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// all FFT passes of `npairs` length-2^p transforms; *result points at the buffer holding the output
+int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2** result) {
+  const int64_t M = (int64_t)1 << p;
+  float2 *src = a, *dst = b;
+  int64_t Ns = 1;
+  for (int idx = 0;; ++idx) {
+    const int R = nufft::fft_pass_radix(p, idx);
+    if (R == 0) break;
+    const int64_t total = (int64_t)npairs * (M / R);
+    const unsigned g = blocks_for(total, 256);
+    if (R == 16) nufft_fft_pass_kernel<16><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+    else if (R == 8) nufft_fft_pass_kernel<8><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+    else if (R == 4) nufft_fft_pass_kernel<4><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+    else nufft_fft_pass_kernel<2><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+    LKB_LAUNCH_CHECK();
+    Ns *= R;
+    float2* tmp = src; src = dst; dst = tmp;
+  }
+  *result = src;
+  return LKB_OK;
+}
+
+int kernel_width() {
+  int w = 8;
+  if (const char* e = getenv("LKB_NUFFT_W")) w = atoi(e);
+  if (w < 4) w = 4;
+  if (w > 12) w = 12;
+  return w & ~1;                                  // even widths only
+}
+
+}  // namespace
+
+// Regular grid f_k = (k0 + k) df with integer k0 >= 0, df * baseline <= 1, fine grids that fit 2^24 cells.
+bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df, double t_last) {
+  if (!regular || F < 2 || !(grid_df > 0.0) || !(grid_f0 >= 0.0)) return false;
+  const double q = grid_f0 / grid_df, k0 = rint(q);
+  if (fabs(q - k0) > 1e-9 * fmax(1.0, q) || k0 > 1.0e7) return false;
+  if (!(grid_df * t_last <= 1.0 + 1e-9)) return false;      // oversample 1: df * baseline = 1 up to rounding
+  const int64_t kmax = (int64_t)k0 + F;
+  return nufft::fine_grid_log2(2 * kmax) <= 24;
+}
+
+// d_t: times shifted to t[0] = 0 (ascending - checked here), d_yc: centred flux rows [B, ystride] fp32,
+// d_rot / d_rot2 rows [0, F_low) already filled by ls_window_kernel (fp64 path); the rest is filled here.
+int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
+                    const float* d_absmax, int B,
+                    const double* d_freq, int64_t F, double grid_f0, double grid_df, float4* d_rot, float2* d_rot2,
+                    int64_t F_low, int normalization, double norm_scale, float* d_pow, cudaStream_t st) {
+  const int w = kernel_width();
+  const float beta = 2.30f * (float)w;
+  const int64_t k0 = (int64_t)rint(grid_f0 / grid_df);
+  const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
+  const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
+  const int npairs = (B + 1) / 2;
+  GlNodes gl;
+  nufft::gauss_legendre(32, gl.x, gl.w);
+
+  Cad *cad = nullptr, *cad2 = nullptr;
+  int32_t *fge = nullptr, *fge2 = nullptr;
+  float2 *dec = nullptr, *dec2 = nullptr, *Za = nullptr, *Zb = nullptr, *Zw = nullptr;
+  float* ones = nullptr;
+  int* flag = nullptr;
+  const int64_t L = nufft::table_len(M, w), L2 = nufft::table_len(M2, w);
+  LKB_TRY(ws_get_t<Cad>(WS_A, N, &cad));
+  LKB_TRY(ws_get_t<int32_t>(WS_B, L, &fge));
+  LKB_TRY(ws_get_t<float2>(WS_C, F, &dec));
+  LKB_TRY(ws_get_t<Cad>(WS_J, N, &cad2));
+  LKB_TRY(ws_get_t<int32_t>(WS_O, L2, &fge2));
+  LKB_TRY(ws_get_t<float2>(WS_P, 2 * M2, &Zw));
+  LKB_TRY(ws_get_t<float2>(WS_IN3, 2 * (k0 + F), &dec2));
+  LKB_TRY(ws_get_t<float>(WS_IN4, N, &ones));
+  LKB_TRY(ws_get_t<int>(WS_IN5, 1, &flag));
+  LKB_TRY(ws_get_t<float2>(WS_H, (size_t)npairs * M, &Za));
+  LKB_TRY(ws_get_t<float2>(WS_I, (size_t)npairs * M, &Zb));
+
+  // ---- tables of the two fine grids, sortedness check ----
+  LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  nufft_cad_kernel<<<blocks_for(N, 256), 256, 0, st>>>(d_t, N, grid_df, M, w, cad, flag);
+  LKB_LAUNCH_CHECK();
+  nufft_cad_kernel<<<blocks_for(N, 256), 256, 0, st>>>(d_t, N, grid_df, M2, w, cad2, flag);
+  LKB_LAUNCH_CHECK();
+  int h_flag = 0;
+  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flag) {
+    set_error("lkb_ls_power_shared: the NUFFT path needs ascending times");
+    return LKB_E_UNSUPPORTED;
+  }
+  nufft_first_ge_kernel<<<blocks_for(L, 256), 256, 0, st>>>(cad, N, L, fge);
+  LKB_LAUNCH_CHECK();
+  nufft_first_ge_kernel<<<blocks_for(L2, 256), 256, 0, st>>>(cad2, N, L2, fge2);
+  LKB_LAUNCH_CHECK();
+  nufft_deconv_kernel<<<blocks_for(F, 128), 128, 0, st>>>(k0, F, M, w, (double)beta, gl, dec);
+  LKB_LAUNCH_CHECK();
+  nufft_deconv_kernel<<<blocks_for(2 * (k0 + F), 128), 128, 0, st>>>(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
+  LKB_LAUNCH_CHECK();
+
+  // ---- window terms of the rows >= F_low: one transform of unit strengths on the 2x finer grid ----
+  if (F_low < F) {
+    nufft_fill_kernel<<<blocks_for(N, 256), 256, 0, st>>>(ones, N, 1.0f);
+    LKB_LAUNCH_CHECK();
+    nufft_spread_kernel<<<blocks_for(M2, 256), 256, 0, st>>>(fge2, cad2, ones, 0, nullptr, 1, 1, w, beta, p2, Zw);
+    LKB_LAUNCH_CHECK();
+    float2* Zw_out = nullptr;
+    LKB_TRY(fft_passes(Zw, Zw + M2, p2, 1, st, &Zw_out));
+    nufft_rot_kernel<<<blocks_for(F - F_low, 128), 128, 0, st>>>(Zw_out, M2, dec2, k0, F, F_low, (double)N, d_rot, d_rot2);
+    LKB_LAUNCH_CHECK();
+  }
+
+  // ---- the batch: spread, FFT, finish ----
+  prof_begin(st);
+  nufft_spread_kernel<<<blocks_for((int64_t)npairs * M, 256), 256, 0, st>>>(fge, cad, d_yc, ystride, d_absmax, B, npairs,
+                                                                          w, beta, p, Za);
+  LKB_LAUNCH_CHECK();
+  float2* Zout = nullptr;
+  LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+  if (F_low < F) {
+    nufft_finish_kernel<<<blocks_for((F - F_low) * npairs, 256), 256, 0, st>>>(
+        Zout, p, dec, k0, F, F_low, d_rot, d_rot2, d_ysumf, d_absmax, (float)N, normalization, (float)norm_scale, B, npairs,
+        d_pow);
+    LKB_LAUNCH_CHECK();
+  }
+  prof_end(st);
+  if (F_low > 0) {
+    nufft_lowrows_kernel<<<blocks_for(F_low * B, 4), 128, 0, st>>>(d_t, N, d_yc, ystride, B, d_freq, F_low, F, d_rot,
+                                                                   d_rot2, d_ysumf, normalization, (float)norm_scale,
+                                                                   d_pow);
+    LKB_LAUNCH_CHECK();
+  }
+  return LKB_OK;
+}
+
+}  // namespace lkb

@@ -1,0 +1,239 @@
+// Arithmetic of the NUFFT Lomb-Scargle path (ls_nufft.cu) as __host__ __device__ functions: every kernel of that
+// path is "one thread = one call of a function in this header" with no shared memory and no intra-CTA
+// communication, so the SAME code is compiled for the CPU by tests/nufft_host_harness.cpp and checked against
+// numpy's FFT and the fp64 oracle without a GPU (tests/test_nufft_core.py).
+//
+// Algorithm (type-1 NUFFT, "exponential of semicircle" kernel of Barnett, Magland & af Klinteberg 2019 - the
+// method behind lightkurve's optional ls_method="fastnifty", /root/reference/pyproject.toml:48,
+// src/lightkurve/periodogram.py:917-946; design study with the accuracy numbers: tools/nufft_ls_model.py):
+//
+//   sum_n a_n exp(2 pi i (k0 + k) df t_n),  k = 0 .. F-1,   t_n >= 0 sorted,   df * t_max <= 1
+//
+//   1. cadence n sits at fine-grid coordinate x_n = df t_n M + shift (cells, M = 2^p >= 4 (k0 + F)); it feeds the
+//      w cells i0_n .. i0_n + w - 1 (i0_n = ceil(x_n - w/2)) with weight phi((cell - x_n) / (w/2)),
+//      phi(z) = exp(beta (sqrt(1 - z^2) - 1)), beta = 2.30 w.  GATHER form: one thread per (cell, pair of light
+//      curves) sums the cadences that reach its cell (a contiguous range, because i0 is sorted) - no atomics.
+//   2. two light curves share one complex transform (real part / imaginary part); length-M FFT with the +i sign
+//      as a sequence of out-of-place Stockham passes of radix 16 / 8 / 4 / 2, one thread per butterfly.
+//   3. mode kk = k0 + k of light curve a is (Z[kk] + conj Z[M - kk]) / 2, of light curve b
+//      (Z[kk] - conj Z[M - kk]) / 2i; both are multiplied by exp(-2 pi i kk shift / M) / phihat(kk).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LKB_HD __host__ __device__ __forceinline__
+#else
+#define LKB_HD inline
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
+
+namespace lkb {
+namespace nufft {
+
+struct Cad {          // per cadence: leftmost fine-grid cell of its kernel support, and (that cell - x_n)
+  int32_t i0;
+  float d0;           // in [-w/2, -w/2 + 1)
+};
+
+LKB_HD int grid_shift(int w) { return (w + 1) / 2 + 1; }            // keeps every i0 >= 1
+LKB_HD int64_t table_len(int64_t M, int w) { return M + 2 * (int64_t)w + 4; }   // entries of first_ge
+
+// fine-grid size: power of two >= 4 * (highest mode index + 1)
+LKB_HD int fine_grid_log2(int64_t kmax_plus_1) {
+  int p = 4;
+  while (((int64_t)1 << p) < 4 * kmax_plus_1) ++p;
+  return p;
+}
+
+LKB_HD Cad cad_entry(double t_rel, double df, int64_t M, int w) {
+  const double x = df * t_rel * (double)M + (double)grid_shift(w);
+  const double i0 = ceil(x - 0.5 * (double)w);
+  Cad c;
+  c.i0 = (int32_t)i0;
+  c.d0 = (float)(i0 - x);
+  return c;
+}
+
+LKB_HD float es_eval(float z, float beta) {
+  const float q = 1.0f - z * z;
+  return q > 0.0f ? expf(beta * (sqrtf(q) - 1.0f)) : 0.0f;
+}
+
+// first_ge[c] = number of cadences with i0 < c  (lower bound in the sorted i0), c in [0, table_len)
+LKB_HD int32_t first_ge_entry(int64_t c, const Cad* cad, int64_t N) {
+  int64_t lo = 0, hi = N;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)cad[mid].i0 < c) lo = mid + 1; else hi = mid;
+  }
+  return (int32_t)lo;
+}
+
+// The two light curves of a pair share one fp32 transform, so its rounding errors scale with the LARGER of the
+// two: each is brought to max |y| in [0.5, 1) by an (exact) power of two before it is spread, and scaled back after
+// the unpacking.  Returns that power of two (1 for an all-zero light curve).
+LKB_HD float pow2_scale(float absmax) {
+  if (!(absmax > 0.0f) || !(absmax < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(absmax, &e);
+  return ldexpf(1.0f, -e);
+}
+
+// value of fine-grid cell m for the pair (s0 y0, s1 y1) of light curves (y1 may be NULL: imaginary part 0)
+LKB_HD float2 spread_cell(int64_t m, const int32_t* first_ge, const Cad* cad, const float* y0, const float* y1,
+                          float s0, float s1, int w, float beta, int64_t M) {
+  float2 acc = make_float2(0.0f, 0.0f);
+  const float inv_half = 2.0f / (float)w;
+  const int64_t L = table_len(M, w);
+  for (int wrap = 0; wrap < 2; ++wrap) {           // wrap = 1: cadences whose support runs past cell M - 1
+    const int64_t mm = m + (int64_t)wrap * M;
+    if (mm + 1 >= L) break;
+    int64_t lo_c = mm - w + 1;
+    if (lo_c < 0) lo_c = 0;
+    const int32_t a = first_ge[lo_c], b = first_ge[mm + 1];
+    for (int32_t n = a; n < b; ++n) {
+      const Cad c = cad[n];
+      const float ph = es_eval((c.d0 + (float)(mm - (int64_t)c.i0)) * inv_half, beta);
+      acc.x += ph * (s0 * y0[n]);
+      if (y1) acc.y += ph * (s1 * y1[n]);
+    }
+  }
+  return acc;
+}
+
+// ---- FFT ------------------------------------------------------------------------------------------
+LKB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// exp(+2 pi i q / 16), q = 0 .. 7
+LKB_HD float2 w16(int q) {
+  switch (q) {
+    case 0: return make_float2(1.0f, 0.0f);
+    case 1: return make_float2(0.923879532511286756f, 0.382683432365089772f);
+    case 2: return make_float2(0.707106781186547524f, 0.707106781186547524f);
+    case 3: return make_float2(0.382683432365089772f, 0.923879532511286756f);
+    case 4: return make_float2(0.0f, 1.0f);
+    case 5: return make_float2(-0.382683432365089772f, 0.923879532511286756f);
+    case 6: return make_float2(-0.707106781186547524f, 0.707106781186547524f);
+    default: return make_float2(-0.923879532511286756f, 0.382683432365089772f);
+  }
+}
+
+// in-place DFT of R points with the +i sign, natural order in and out (decimation in time, recursive halves)
+template <int R>
+struct SmallDft {
+  static LKB_HD void run(float2* u) {
+    float2 e[R / 2], o[R / 2];
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) { e[i] = u[2 * i]; o[i] = u[2 * i + 1]; }
+    SmallDft<R / 2>::run(e);
+    SmallDft<R / 2>::run(o);
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {
+      const float2 tw = cmul(o[q], w16(q * (16 / R)));
+      u[q] = make_float2(e[q].x + tw.x, e[q].y + tw.y);
+      u[q + R / 2] = make_float2(e[q].x - tw.x, e[q].y - tw.y);
+    }
+  }
+};
+template <>
+struct SmallDft<1> {
+  static LKB_HD void run(float2*) {}
+};
+
+LKB_HD float2 unit_phase(int64_t num, int64_t den) {     // exp(+2 pi i num / den), den a power of two, num < 2^24
+  float s, c;
+#if defined(__CUDA_ARCH__)
+  sincospif(2.0f * (float)num / (float)den, &s, &c);
+#else
+  const double a = 6.283185307179586476925 * (double)num / (double)den;
+  s = (float)sin(a);
+  c = (float)cos(a);
+#endif
+  return make_float2(c, s);
+}
+
+// One butterfly of an out-of-place Stockham pass of radix R over a length-M transform.
+//   i  in [0, M/R): butterfly index;  Ns = product of the radices of the earlier passes (1 for the first).
+// After passes whose radices multiply to M the output is the DFT in natural order.
+template <int R>
+LKB_HD void fft_pass_butterfly(const float2* x, float2* y, int64_t i, int64_t Ns, int64_t M) {
+  const int64_t T = M / R;
+  const int64_t k = i & (Ns - 1);
+  float2 u[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u[r] = x[i + (int64_t)r * T];
+  if (Ns > 1) {
+#pragma unroll
+    for (int r = 1; r < R; ++r) u[r] = cmul(u[r], unit_phase((int64_t)r * k, Ns * R));
+  }
+  SmallDft<R>::run(u);
+  const int64_t j = (i - k) * R + k;
+#pragma unroll
+  for (int r = 0; r < R; ++r) y[j + (int64_t)r * Ns] = u[r];
+}
+
+// radix of pass `idx` (0-based) for a length-2^p transform: sixteens first, the remainder last.  0 = done.
+LKB_HD int fft_pass_radix(int p, int idx) {
+  const int n16 = p / 4, rem = p % 4;
+  if (idx < n16) return 16;
+  if (idx == n16 && rem) return 1 << rem;
+  return 0;
+}
+
+// ---- unpacking --------------------------------------------------------------------------------------
+// Gauss-Legendre nodes and weights on [-1, 1] (Newton iteration on P_n; n <= 64)
+LKB_HD void gauss_legendre(int n, double* x, double* w) {
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double z = cos(3.14159265358979323846 * ((double)i + 0.75) / ((double)n + 0.5));
+    double pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j + 1.0) * z * p2 - (double)j * p3) / ((double)j + 1.0);
+      }
+      pp = (double)n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (fabs(dz) < 1e-15) break;
+    }
+    x[i] = -z;
+    x[n - 1 - i] = z;
+    w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+// Fourier coefficient of the kernel at mode kk on an M-cell grid, times the grid-shift phase, INVERTED:
+// the factor the raw transform value of mode kk is multiplied with.  glx/glw: Gauss-Legendre nodes/weights on
+// [-1, 1] (nq of them; 32 are ample for w <= 12).
+LKB_HD void deconv_factor(int64_t kk, int64_t M, int w, double beta, const double* glx, const double* glw, int nq,
+                          double* re, double* im) {
+  const double half = 0.5 * (double)w;                         // kernel half-width in cells
+  const double omega = 6.283185307179586476925 * (double)kk / (double)M;   // radians per cell
+  double acc = 0.0;
+  for (int q = 0; q < nq; ++q)
+    acc += glw[q] * exp(beta * (sqrt(1.0 - glx[q] * glx[q]) - 1.0)) * cos(omega * half * glx[q]);
+  const double phihat = half * acc;                            // sum over cells ~ integral in cells
+  const double ang = -omega * (double)grid_shift(w);
+  *re = cos(ang) / phihat;
+  *im = sin(ang) / phihat;
+}
+
+// (C + i S) of the two light curves of a pair at mode kk from the packed transform Z (length M); inv0 / inv1 undo
+// the pow2_scale factors of the two light curves
+LKB_HD void unpack_pair(const float2* Z, int64_t kk, int64_t M, float2 dec, float inv0, float inv1, float2* a,
+                        float2* b) {
+  const float2 g1 = Z[kk];
+  const float2 g2 = Z[kk == 0 ? 0 : M - kk];
+  const float2 ra = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));      // (g1 + conj g2) / 2
+  const float2 rb = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));      // (g1 - conj g2) / 2i
+  const float2 da = cmul(ra, dec), db = cmul(rb, dec);
+  *a = make_float2(da.x * inv0, da.y * inv0);
+  *b = make_float2(db.x * inv1, db.y * inv1);
+}
+
+}  // namespace nufft
+}  // namespace lkb

@@ -1,0 +1,100 @@
+"""GPU test of the opt-in NUFFT Lomb-Scargle path (algo="nufft", lightkurve_b200/csrc/ls_nufft.cu).
+
+Status: the arithmetic of every kernel is verified on the CPU (tests/test_nufft_core.py runs the same
+`__host__ __device__` functions through a g++ harness); the CUDA glue (launch shapes, workspace, epilogue, low
+rows) was written after round 1's GPU budget was spent and HAS NOT RUN ON HARDWARE YET - hence xfail(strict=False):
+a failure here is reported as xfailed, a pass as xpassed, and neither hides the verified tests.  The work runs
+in a child process so that a device fault cannot poison the CUDA context of the rest of the suite.  The file
+name sorts last on purpose."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _excess(got, ref):
+    return float(np.max(np.abs(got - ref) / (1e-5 * ref.max() + 1e-4 * ref)))
+
+
+def _worker(out_q):
+    sys.path.insert(0, ROOT)
+    from lightkurve_b200 import engine
+    from oracle import ls as ols
+    engine.init(0)
+    rng = np.random.default_rng(21)
+    res = {}
+    # (1) default lightkurve grid (f0 = df = 1 / (5 T)), odd batch, amplitudes spanning 3 decades
+    idx = np.flatnonzero(rng.uniform(size=4000) > 0.1)[:3000]
+    t = 131.5 + idx * 0.0204336
+    N = len(t)
+    df = 1.0 / (5.0 * (t[-1] - t[0]))
+    freq = df * (1 + np.arange(2000))
+    Y = np.stack([1 + a * np.sin(2 * np.pi * f * t) + s * rng.normal(size=N)
+                  for a, f, s in [(1e-2, 3.1, 1e-4), (0, 1, 5e-5), (1e-4, 7.7, 3e-4), (3e-3, 0.9, 1e-3), (0, 1, 1e-3)]])
+    got = np.asarray(engine.ls_power_shared(t, Y.astype(np.float32), freq, "amplitude", algo="nufft"), dtype=np.float64)
+    worst = 0.0
+    for b in range(len(Y)):
+        y = Y[b].astype(np.float32).astype(np.float64)
+        ref = np.sqrt(ols.ls_slow_psd(t, y, freq)) * np.sqrt(4.0 / N)
+        worst = max(worst, _excess(got[b], ref))
+    res["default grid, amplitude"] = worst
+    # (2) psd normalisation, oversample 1 (df * baseline = 1: the last cadence wraps around the fine grid), f64 flux
+    df1 = 1.0 / (t[-1] - t[0])
+    freq1 = df1 * (1 + np.arange(700))
+    scale = 2.0 / (N * 1.0 * df1)
+    got = np.asarray(engine.ls_power_shared(t, Y[:2], freq1, "psd", norm_scale=scale, algo="nufft"), dtype=np.float64)
+    worst = 0.0
+    for b in range(2):
+        ref = ols.ls_slow_psd(t, Y[b], freq1) * scale
+        worst = max(worst, float(np.max(np.abs(got[b] - ref) / (2e-5 * ref.max() + 2e-4 * ref))))
+    res["oversample 1, psd"] = worst
+    # (3) against the CUDA-core contraction kernel on a larger batch (sizes the oracle does not reach)
+    B, N3, F3 = 64, 20000, 30000
+    t3 = np.sort(rng.uniform(0, 90.0, N3))
+    df3 = 1.0 / (5.0 * (t3[-1] - t3[0]))
+    f3 = df3 * (1 + np.arange(F3))
+    Y3 = (1 + 1e-3 * np.sin(2 * np.pi * 2.2 * t3)[None, :] + 3e-4 * rng.normal(size=(B, N3))).astype(np.float32)
+    a = np.asarray(engine.ls_power_shared(t3, Y3, f3, "amplitude", algo="nufft"), dtype=np.float64)
+    s = np.asarray(engine.ls_power_shared(t3, Y3, f3, "amplitude", algo="simt"), dtype=np.float64)
+    res["vs simt kernel"] = max(_excess(a[b], s[b]) for b in range(B))
+    # (4) shapes the path must refuse
+    try:
+        engine.ls_power_shared(t, Y[:2].astype(np.float32), np.sort(rng.uniform(0.1, 5, 100)), "amplitude", algo="nufft")
+        res["irregular grid refused"] = False
+    except Exception:
+        res["irregular grid refused"] = True
+    out_q.put(res)
+
+
+@pytest.mark.xfail(strict=False, reason="CUDA glue of the NUFFT path not validated on hardware yet (round 1)")
+def test_nufft_path_matches_oracle_and_simt_kernel():
+    import queue
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    p = ctx.Process(target=_worker, args=(out_q,), daemon=True)
+    p.start()
+    res, t0 = None, time.time()
+    try:
+        while res is None:
+            try:
+                res = out_q.get(timeout=1.0)
+            except queue.Empty:
+                assert p.is_alive() or p.exitcode == 0, "worker died with exit code %r" % p.exitcode
+                assert time.time() - t0 < 300, "timed out"
+    finally:
+        if p.is_alive():
+            p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    print("NUFFT path, worst tolerance excess per case:", res)
+    assert res["irregular grid refused"] is True
+    assert res["default grid, amplitude"] < 1.0
+    assert res["oversample 1, psd"] < 1.0
+    assert res["vs simt kernel"] < 1.0
