@@ -333,7 +333,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tcgen05", "nufft"],
+                    help="nufft: the opt-in spread+FFT path (ls_nufft.cu); its roofline is the HBM one")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the BLS (configs[2]) leg")
@@ -459,6 +460,20 @@ def main():
                     "frac": achieved / peak_tf, "traffic": traffic, "kernel": "ls_tcg_kernel" if args.algo != "simt"
                     else "ls_shared_simt_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
                     "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
+        if args.algo == "nufft":
+            # HBM sweep: fine grids [B/2, M] complex64 written once by the spreading, read + written by every Stockham
+            # pass, two modes per output read by the finish kernel; flux read once, power written once
+            # (DESIGN.md K2n).  k0 = 1 on the bench grid (f0 = df).
+            pfine = int(np.ceil(np.log2(4.0 * (1 + F))))
+            npass = (pfine + 3) // 4
+            npairs = (B + 1) // 2
+            nbytes = npairs * (2 ** pfine) * 8.0 * (1 + 2 * npass) + npairs * 16.0 * F + 4.0 * B * N + 4.0 * B * F
+            hbm = float(peaks.get("hbm_gbs", 6589.3))
+            roofline = {"bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                        "kernel": "nufft_spread + %d nufft_fft_pass + nufft_finish" % npass, "kernel_ms": k_ms,
+                        "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                        "note": "algorithmic bytes = fine grids (1 + 2 passes) + unpack reads + flux + power"}
         cpu = None
         if not args.no_cpu_baseline:
             ts, Ys, fs = t, Y[:8], freq
@@ -469,7 +484,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16x2-split in / f32 accumulate (tcgen05), f64 phase",
+            "vs_baseline": None, "dtype": "f32 spreading + FFT, f64 phase (nufft)" if args.algo == "nufft" else
+                     "f16x2-split in / f32 accumulate (tcgen05), f64 phase",
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_per_gpu": B, "cadences": N,
                        "frequencies": F, "normalization": "amplitude", "algo": args.algo,
