@@ -12,6 +12,8 @@ from .lightcurve import LightCurve, FoldedLightCurve  # noqa: F401
 from .collections import LightCurveCollection  # noqa: F401
 from .periodogram import Periodogram, LombScarglePeriodogram, BoxLeastSquaresPeriodogram  # noqa: F401
 from . import correctors  # noqa: F401
+from . import seismology  # noqa: F401
+from .seismology import Seismology  # noqa: F401
 from .correctors import DesignMatrix, DesignMatrixCollection, RegressionCorrector  # noqa: F401
 
 __version__ = "0.1.0"

@@ -316,6 +316,62 @@ class LightCurve:
         from .periodogram import LombScarglePeriodogram
         return LombScarglePeriodogram.from_lightcurve(lc=self, **kwargs)
 
+    def to_seismology(self, **kwargs):
+        """`Seismology` object for estimating numax, deltanu, radius, mass, logg (lightcurve.py:2537-2550);
+        `kwargs` go to `to_periodogram`."""
+        from .seismology import Seismology
+        return Seismology.from_lightcurve(self, **kwargs)
+
+    def fill_gaps(self, method="gaussian_noise"):
+        """Fill gaps in time with white Gaussian noise N(mean flux, CDPP) (lightcurve.py:1329-1427; the variant for
+        light curves without a cadence-number column): cadences are inserted every median time step wherever two
+        consecutive times are more than 1.2 steps apart; their flux_err is interpolated.  The noise comes from
+        numpy's global RNG, as in the reference."""
+        lc = self.copy().remove_nans()
+        tval = np.asarray(lc.time.value, dtype=np.float64)
+        if len(tval) < 2:
+            return lc
+        dt = np.nanmedian(tval[1:] - tval[:-1])
+        ntime = [tval[0]]
+        for t in tval[1:]:
+            prevtime = ntime[-1]
+            while (t - prevtime) > 1.2 * dt:
+                ntime.append(prevtime + dt)
+                prevtime = ntime[-1]
+            ntime.append(t)
+        ntime = np.asarray(ntime, float)
+        in_original = np.isin(ntime, tval)
+        f = np.zeros(len(ntime))
+        f[in_original] = np.asarray(lc.flux.value, dtype=np.float64)
+        fe = np.zeros(len(ntime))
+        fe[in_original] = np.asarray(lc.flux_err.value, dtype=np.float64)
+        fe[~in_original] = np.interp(ntime[~in_original], tval, np.asarray(lc.flux_err.value, dtype=np.float64))
+        if method == "gaussian_noise":
+            try:
+                std = float(lc.estimate_cdpp().to(lc.flux.unit).value)
+            except Exception:
+                std = np.nanstd(lc.flux.value)
+            f[~in_original] = np.random.normal(np.nanmean(lc.flux.value), std, (~in_original).sum())
+        else:
+            raise NotImplementedError("No such method as {}".format(method))
+        return LightCurve(time=Time(ntime, lc.time.format, lc.time.scale), flux=Quantity(f, lc.flux.unit),
+                          flux_err=Quantity(fe, lc.flux_err.unit), meta=self.meta)
+
+    def append(self, others, inplace=False):
+        """Concatenate light curves in the order given (lightcurve.py:915-941)."""
+        if inplace:
+            raise ValueError("the `inplace` parameter is no longer supported "
+                             "as of Lightkurve v2.0")
+        if not hasattr(others, "__iter__"):
+            others = (others,)
+        lcs = [self] + list(others)
+        new = self.copy()
+        new.time = Time(np.concatenate([np.asarray(lc.time.value) for lc in lcs]), self.time.format, self.time.scale)
+        new.flux = Quantity(np.concatenate([np.asarray(lc.flux.to(self.flux.unit).value) for lc in lcs]), self.flux.unit)
+        new.flux_err = Quantity(np.concatenate([np.asarray(lc.flux_err.to(self.flux.unit).value) for lc in lcs]),
+                                self.flux.unit)
+        return new
+
     def to_corrector(self, method="regression", **kwargs):
         """Returns a corrector object (lightcurve.py:2732); only 'regression' is in scope."""
         method = validate_method(method, ["regression"])

@@ -190,6 +190,12 @@ class Periodogram(object):
             return snr, bkg
         return snr
 
+    def to_seismology(self, **kwargs):
+        """`Seismology` object of this periodogram (periodogram.py:576-587); background-correct it first
+        (`flatten()`), otherwise a LightkurveWarning is raised."""
+        from .seismology import Seismology
+        return Seismology(self)
+
     def plot(self, *args, **kwargs):
         raise NotImplementedError("plotting is outside the hot-path scope of lightkurve_b200")
 

@@ -8,7 +8,8 @@ from a real astropy installation are accepted by duck typing (``.value`` / ``.un
 """
 import numpy as np
 
-__all__ = ["Unit", "Quantity", "Time", "UnitConversionError", "day", "d", "hour", "minute", "second", "s",
+__all__ = ["Unit", "Quantity", "Time", "UnitConversionError", "Kelvin", "cm", "solRad", "solMass", "dex",
+           "day", "d", "hour", "minute", "second", "s",
            "Hz", "hertz", "microhertz", "uHz", "electron", "dimensionless_unscaled", "percent", "ppt", "ppm",
            "K"]
 
@@ -124,7 +125,11 @@ day = d = Unit({"s": 1}, 86400.0, "d")
 Hz = hertz = Unit({"s": -1}, 1.0, "Hz")
 microhertz = uHz = Unit({"s": -1}, 1e-6, "uHz")
 electron = Unit({"electron": 1}, 1.0, "electron")
-K = Unit({"K": 1}, 1.0, "K")
+K = Kelvin = Unit({"K": 1}, 1.0, "K")
+cm = Unit({"m": 1}, 1e-2, "cm")
+solRad = Unit({"m": 1}, 6.957e8, "solRad")           # IAU 2015 nominal solar radius
+solMass = Unit({"kg": 1}, 1.988409870698051e30, "solMass")
+dex = Unit({"dex": 1}, 1.0, "dex")
 dimensionless_unscaled = Unit({}, 1.0, "")
 percent = Unit({}, 1e-2, "%")
 ppt = Unit({}, 1e-3, "ppt")
@@ -134,7 +139,7 @@ _BY_NAME = {"s": second, "second": second, "min": minute, "minute": minute, "h":
             "d": day, "day": day, "Hz": Hz, "hertz": Hz, "uHz": microhertz, "microhertz": microhertz,
             "electron": electron, "e": electron, "": dimensionless_unscaled,
             "dimensionless": dimensionless_unscaled, "percent": percent, "%": percent, "ppt": ppt, "ppm": ppm,
-            "K": K, "electron/s": electron / second, "electron/second": electron / second,
+            "K": K, "Kelvin": K, "cm": cm, "solRad": solRad, "solMass": solMass, "dex": dex, "electron/s": electron / second, "electron/second": electron / second,
             "electron / s": electron / second, "e/s": electron / second, "1/d": 1 / day, "1 / d": 1 / day}
 
 

@@ -528,3 +528,32 @@ def test_sparse_designmatrix_through_gpu():
     np.testing.assert_allclose(rc.coefficients, ref["coefficients"], rtol=1e-6, atol=1e-9)
     assert np.array_equal(rc.outlier_mask, ref["outlier_mask"])
     assert np.std(rc.corrected_lc.flux.value) < 1.3e-3
+
+
+def test_seismology_from_lightcurve():
+    """lc.normalize().remove_nans().fill_gaps().to_periodogram().flatten() -> Seismology
+    (/root/reference/src/lightkurve/seismology/core.py:97-110; tests/seismology/test_butler.py:13-25 is the remote-data
+    original).  A synthetic red giant (numax 150 uHz, deltanu 14.07 uHz) sampled at the Kepler long cadence with a
+    gap: the oracle chain (oracle.ls + oracle.pg) recovers 149.5 / 14.07 uHz on the same construction."""
+    rng = np.random.default_rng(5)
+    N, dt = 12000, 1765.5 / 86400.0
+    t = np.arange(N) * dt
+    numax_true = 150.0
+    dnu = 0.294 * numax_true ** 0.772
+    modes = numax_true + dnu * np.arange(-5, 6)
+    modes = np.concatenate([modes, modes + 0.5 * dnu - 1.2])
+    amp = 3e-5 * np.exp(-0.5 * ((modes - numax_true) / (0.66 * numax_true ** 0.88 / 2.355)) ** 2)
+    y = 1 + sum(a * np.sin(2 * np.pi * (m * 1e-6 * 86400) * t + rng.uniform(0, 2 * np.pi)) for a, m in zip(amp, modes))
+    y = y + 2e-5 * rng.normal(size=N)
+    keep = np.ones(N, bool)
+    keep[5000:5200] = False
+    lc = LightCurve(time=t[keep], flux=y[keep], flux_err=np.full(keep.sum(), 2e-5))
+    np.random.seed(11)
+    seis = lc.to_seismology(normalization="psd")
+    assert isinstance(seis.periodogram, lk.periodogram.SNRPeriodogram)
+    assert seis.periodogram.frequency.unit == u.microhertz
+    numax = seis.estimate_numax()
+    deltanu = seis.estimate_deltanu()
+    assert np.isclose(numax.value, numax_true, atol=0.1 * numax_true)
+    assert np.isclose(deltanu.value, dnu, atol=0.25 * dnu)
+    assert seis.estimate_radius(teff=4800).unit == u.solRad
