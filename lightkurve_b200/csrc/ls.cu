@@ -18,10 +18,18 @@
 #include "ptx.cuh"
 #include "ls_common.cuh"
 #include <stdlib.h>
+#include <stdint.h>
 #include <type_traits>
 #include <vector>
 
 namespace lkb {
+
+// ls_nufft.cu: the opt-in NUFFT path for ragged batches (LKB_LS_RAGGED_NUFFT=1)
+bool ls_nufft_ragged_enabled();
+int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po, int B,
+                           int64_t ptotal, int64_t nmax, const double* d_span, const double* h_span,
+                           const double* d_ysum, int64_t F, double f0, double df, int normalization,
+                           const double* d_ns, float* d_pow, cudaStream_t st);
 
 // Per-cadence entry of a regular-grid light curve (ragged path): fixed-point phases of the grid origin and of one
 // grid step, plus the fp32 rotation by one step - the bins after a warp's first are obtained by rotating (cos, sin)
@@ -748,6 +756,29 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 
   dim3 grid((unsigned)((Fmax + LS_FPB - 1) / LS_FPB), (unsigned)B);
   LKB_REQUIRE(B <= 65535, "lkb_ls_power: B > 65535 per call (split the batch)");
+  // Opt-in (LKB_LS_RAGGED_NUFFT=1): the NUFFT path of ls_nufft.cu for one shared regular grid; light curves that
+  // do not qualify (empty / tiny, unsorted times, df * baseline > 1) send the whole call to the direct kernel.
+  if (ls_nufft_ragged_enabled() && regular && !h_freq_offsets) {
+    int64_t nmax = 0, nmin = INT64_MAX;
+    for (int b = 0; b < B; ++b) {
+      const int64_t n = h_offsets[b + 1] - h_offsets[b];
+      nmax = n > nmax ? n : nmax;
+      nmin = n < nmin ? n : nmin;
+    }
+    if (nmin >= 8) {
+      std::vector<double> h_span(B);
+      LKB_CUDA_CHECK(cudaMemcpyAsync(h_span.data(), d_span, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+      LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+      const int rc = ls_nufft_ragged_launch(d_t, d_y, d_off, d_po, B, ptotal, nmax, d_span, h_span.data(), d_ysum, F,
+                                            h_f0[0], h_df[0], normalization, d_ns, d_pow, st);
+      if (rc == LKB_OK) {
+        LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
+        if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+        return LKB_OK;
+      }
+      if (rc != LKB_E_UNSUPPORTED) return rc;
+    }
+  }
   prof_begin(st);
   if (regular)
     ls_direct_kernel<true><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_tab, d_y, d_off, d_po, d_freq, d_fo, F, d_span,

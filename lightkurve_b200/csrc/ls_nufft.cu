@@ -24,6 +24,8 @@
 // HBM traffic at config 2 (B = 1024, M = 2^19): spread 2.1 GB written, 5 passes x 4.3 GB, finish ~1 GB read +
 // 0.4 GB written  ~ 25 GB  ~ 4 ms at the measured 6.6 TB/s.  Next steps once measured: fuse the spreading into
 // the first pass (80 % of its input is zero for oversample 5), shared-memory passes (2 instead of 5 sweeps).
+#include <algorithm>
+
 #include "common.cuh"
 #include "ls_common.cuh"
 #include "nufft_core.h"
@@ -301,6 +303,247 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
     nufft_lowrows_kernel<<<blocks_for(F_low * B, 4), 128, 0, st>>>(d_t, N, d_yc, ystride, B, d_freq, F_low, F, d_rot,
                                                                    d_rot2, d_ysumf, normalization, (float)norm_scale,
                                                                    d_pow);
+    LKB_LAUNCH_CHECK();
+  }
+  return LKB_OK;
+}
+
+
+// =====================================================================================================
+// Ragged batches (K1 shapes: every light curve has its own times; one shared regular frequency grid).
+// Opt-in through LKB_LS_RAGGED_NUFFT=1 (round 1: CPU-verified arithmetic, CUDA glue not yet run on hardware).
+// Same pipeline, with per-light-curve cadence tables in the padded CSR layout of the K1 prologue, cell ranges by
+// binary search (nufft::spread_cell_search), and the window terms of each light curve taken from a second
+// transform of unit strengths (pairs packed the same way) inside the finish kernel - no rot arrays.
+// =====================================================================================================
+namespace {
+
+__global__ void nufft_cad_ragged_kernel(const double* __restrict__ t, const int64_t* __restrict__ off,
+                                        const int64_t* __restrict__ poff, const double* __restrict__ span, double df,
+                                        int64_t M, int64_t M2, int w, Cad* __restrict__ cad, Cad* __restrict__ cad2,
+                                        int* __restrict__ bad) {
+  const int b = blockIdx.y;
+  const int64_t n = off[b + 1] - off[b], po = poff[b];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !(df * span[b] <= 1.0 + 1e-9)) *bad = 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ti = t[po + i];
+    cad[po + i] = nufft::cad_entry(ti, df, M, w);
+    cad2[po + i] = nufft::cad_entry(ti, df, M2, w);
+    if (ti < 0.0 || (i > 0 && ti < t[po + i - 1])) *bad = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nufft_absmax_ragged_kernel(const float* __restrict__ y, const int64_t* __restrict__ off, const int64_t* __restrict__ poff,
+                           float* __restrict__ absmax) {
+  __shared__ float s_max[8];
+  const int b = blockIdx.x;
+  const int64_t n = off[b + 1] - off[b], po = poff[b];
+  float mx = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(y[po + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) m = fmaxf(m, s_max[wv]);
+    absmax[b] = m;
+  }
+}
+
+// Z[pair][m] for the flux (y != NULL, scaled) or for unit strengths (y == NULL)
+__global__ void __launch_bounds__(256)
+nufft_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict__ y, const int64_t* __restrict__ off,
+                           const int64_t* __restrict__ poff, const float* __restrict__ absmax, int B, int npairs, int w,
+                           float beta, int log2M, float2* __restrict__ Z) {
+  const int64_t M = (int64_t)1 << log2M;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (int64_t)npairs << log2M) return;
+  const int64_t pair = gid >> log2M, m = gid & (M - 1);
+  const int64_t b0 = 2 * pair, b1 = b0 + 1;
+  float2 v = make_float2(0.f, 0.f);
+  {
+    const int64_t po = poff[b0], n = off[b0 + 1] - off[b0];
+    v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b0]) : 1.0f, w,
+                                    beta, M);
+  }
+  if (b1 < B) {
+    const int64_t po = poff[b1], n = off[b1 + 1] - off[b1];
+    v.y = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b1]) : 1.0f, w,
+                                    beta, M);
+  }
+  Z[gid] = v;
+}
+
+__device__ __forceinline__ float ragged_power(float2 hs, float2 win1, float2 win2, double Nd, double ysum,
+                                              int normalization, double scale) {
+  LsSums<double> d;
+  d.zero();
+  d.ch = (double)hs.x;
+  d.sh = (double)hs.y;
+  d.c = (double)win1.x;
+  d.s = (double)win1.y;
+  d.cc = 0.5 * (Nd + (double)win2.x);
+  d.sc = 0.5 * (double)win2.y;
+  return ls_normalize(ls_power_from_sums(d, Nd, ysum), Nd, normalization, scale);
+}
+
+// power[b, k] for the rows that are not "low" for light curve b
+__global__ void __launch_bounds__(256)
+nufft_finish_ragged_kernel(const float2* __restrict__ Z, int log2M, const float2* __restrict__ Zw, int log2M2,
+                           const float2* __restrict__ dec, const float2* __restrict__ dec2, int64_t k0, int64_t F,
+                           double f0, double df, const int64_t* __restrict__ off, const double* __restrict__ span,
+                           const double* __restrict__ ysum, const float* __restrict__ absmax, int normalization,
+                           const double* __restrict__ norm_scale, int B, int npairs, float* __restrict__ power) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= F * npairs) return;
+  const int64_t pair = gid / F, k = gid - pair * F;
+  const int64_t M = (int64_t)1 << log2M, M2 = (int64_t)1 << log2M2, kk = k0 + k;
+  const int64_t b0 = 2 * pair, b1 = b0 + 1;
+  const bool has1 = b1 < B;
+  const float inv0 = 1.0f / nufft::pow2_scale(absmax[b0]);
+  const float inv1 = has1 ? 1.0f / nufft::pow2_scale(absmax[b1]) : 1.0f;
+  float2 ha, hb, w1a, w1b, w2a, w2b;
+  nufft::unpack_pair(Z + pair * M, kk, M, dec[k], inv0, inv1, &ha, &hb);
+  nufft::unpack_pair(Zw + pair * M2, kk, M2, dec2[kk], 1.0f, 1.0f, &w1a, &w1b);
+  nufft::unpack_pair(Zw + pair * M2, 2 * kk, M2, dec2[2 * kk], 1.0f, 1.0f, &w2a, &w2b);
+  const double fr = f0 + (double)k * df;
+  if (fr * span[b0] > LS_LOWF_CYCLES) {
+    const double Nd = (double)(off[b0 + 1] - off[b0]);
+    power[b0 * F + k] = ragged_power(ha, w1a, w2a, Nd, ysum[b0], normalization, norm_scale ? norm_scale[b0] : 1.0);
+  }
+  if (has1 && fr * span[b1] > LS_LOWF_CYCLES) {
+    const double Nd = (double)(off[b1 + 1] - off[b1]);
+    power[b1 * F + k] = ragged_power(hb, w1b, w2b, Nd, ysum[b1], normalization, norm_scale ? norm_scale[b1] : 1.0);
+  }
+}
+
+// rows with f * baseline_b <= LS_LOWF_CYCLES: direct fp64 sums, one warp per (row, light curve)
+__global__ void __launch_bounds__(128)
+nufft_lowrows_ragged_kernel(const double* __restrict__ t, const float* __restrict__ y, const int64_t* __restrict__ off,
+                            const int64_t* __restrict__ poff, const double* __restrict__ span,
+                            const double* __restrict__ ysum, double f0, double df, int64_t F_low_max, int64_t F,
+                            int normalization, const double* __restrict__ norm_scale, int B, float* __restrict__ power) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t job = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (job >= F_low_max * B) return;
+  const int64_t b = job / F_low_max, k = job - b * F_low_max;
+  const double fr = f0 + (double)k * df;
+  if (k >= F || fr * span[b] > LS_LOWF_CYCLES) return;
+  const int64_t n = off[b + 1] - off[b], po = poff[b];
+  if (n <= 0) return;
+  LsSums<double> d;
+  d.zero();
+  for (int64_t i = lane; i < n; i += 32) {
+    double s, c;
+    ls_sincos_cycles_f64(fr * t[po + i], s, c);
+    d.add((double)y[po + i], s, c);
+  }
+  d.warp_reduce();
+  if (lane == 0)
+    power[b * F + k] = ls_normalize(ls_power_from_sums(d, (double)n, ysum[b]), (double)n, normalization,
+                                    norm_scale ? norm_scale[b] : 1.0);
+}
+
+}  // namespace
+
+bool ls_nufft_ragged_enabled() {
+  const char* e = getenv("LKB_LS_RAGGED_NUFFT");
+  return e && atoi(e) != 0;
+}
+
+// One shared regular grid f_k = f0 + k df (k0 = f0 / df integer), light curves in the K1 prologue's layout
+// (d_t / d_y padded CSR with offsets d_po; d_off the unpadded offsets; d_span, d_ysum per light curve).
+// h_span: host copy of d_span.  Returns LKB_E_UNSUPPORTED when a light curve is not eligible (unsorted times,
+// df * baseline > 1): the caller then runs the direct kernel.
+int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po, int B,
+                           int64_t ptotal, int64_t nmax, const double* d_span, const double* h_span,
+                           const double* d_ysum, int64_t F, double f0, double df, int normalization,
+                           const double* d_ns, float* d_pow, cudaStream_t st) {
+  const double q = f0 / df, k0d = rint(q);
+  if (!(df > 0.0) || !(f0 >= 0.0) || fabs(q - k0d) > 1e-9 * fmax(1.0, q) || k0d > 1.0e7) {
+    set_error("NUFFT (ragged): the grid is not f_k = (k0 + k) df with integer k0");
+    return LKB_E_UNSUPPORTED;
+  }
+  const int64_t k0 = (int64_t)k0d;
+  const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
+  if (p2 > 24) { set_error("NUFFT (ragged): fine grid larger than 2^24 cells"); return LKB_E_UNSUPPORTED; }
+  double span_min = 1e300;
+  for (int b = 0; b < B; ++b) {
+    if (!(h_span[b] > 0.0) || !(df * h_span[b] <= 1.0 + 1e-9)) {
+      set_error("NUFFT (ragged): a light curve has zero baseline or df * baseline > 1");
+      return LKB_E_UNSUPPORTED;
+    }
+    if (h_span[b] > 0.0 && h_span[b] < span_min) span_min = h_span[b];
+  }
+  // rows k with (f0 + k df) * span_b <= LS_LOWF_CYCLES for at least one light curve
+  int64_t F_low_max = 0;
+  if (span_min < 1e300) {
+    const double nlow = floor((LS_LOWF_CYCLES / span_min - f0) / df) + 2.0;
+    F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
+  }
+  const int w = kernel_width();
+  const float beta = 2.30f * (float)w;
+  const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
+  const int npairs = (B + 1) / 2;
+  GlNodes gl;
+  nufft::gauss_legendre(32, gl.x, gl.w);
+
+  Cad *cad = nullptr, *cad2 = nullptr;
+  float2 *dec = nullptr, *dec2 = nullptr, *Za = nullptr, *Zb = nullptr, *Zw = nullptr;
+  float* absmax = nullptr;
+  int* flag = nullptr;
+  LKB_TRY(ws_get_t<Cad>(WS_K, ptotal + 4, &cad));
+  LKB_TRY(ws_get_t<Cad>(WS_L, ptotal + 4, &cad2));
+  LKB_TRY(ws_get_t<float>(WS_M, B, &absmax));
+  LKB_TRY(ws_get_t<float2>(WS_N, (size_t)npairs * M, &Za));
+  LKB_TRY(ws_get_t<float2>(WS_O, (size_t)npairs * M, &Zb));
+  LKB_TRY(ws_get_t<float2>(WS_P, (size_t)2 * npairs * M2, &Zw));
+  LKB_TRY(ws_get_t<float2>(WS_IN4, F, &dec));
+  LKB_TRY(ws_get_t<float2>(WS_IN5, 2 * (k0 + F), &dec2));
+  LKB_TRY(ws_get_t<int>(WS_IN6, 1, &flag));
+
+  LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  {
+    const unsigned gx = (unsigned)std::min<int64_t>(64, (nmax + 255) / 256);
+    nufft_cad_ragged_kernel<<<dim3(gx ? gx : 1, (unsigned)B), 256, 0, st>>>(d_t, d_off, d_po, d_span, df, M, M2, w, cad,
+                                                                          cad2, flag);
+    LKB_LAUNCH_CHECK();
+  }
+  int h_flag = 0;
+  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flag) { set_error("NUFFT (ragged): a light curve has unsorted times"); return LKB_E_UNSUPPORTED; }
+  nufft_absmax_ragged_kernel<<<B, 256, 0, st>>>(d_y, d_off, d_po, absmax);
+  LKB_LAUNCH_CHECK();
+  nufft_deconv_kernel<<<blocks_for(F, 128), 128, 0, st>>>(k0, F, M, w, (double)beta, gl, dec);
+  LKB_LAUNCH_CHECK();
+  nufft_deconv_kernel<<<blocks_for(2 * (k0 + F), 128), 128, 0, st>>>(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
+  LKB_LAUNCH_CHECK();
+
+  prof_begin(st);
+  // window terms: unit strengths on the 2x finer grid
+  nufft_spread_ragged_kernel<<<blocks_for((int64_t)npairs * M2, 256), 256, 0, st>>>(cad2, nullptr, d_off, d_po, absmax, B,
+                                                                                  npairs, w, beta, p2, Zw);
+  LKB_LAUNCH_CHECK();
+  float2* Zw_out = nullptr;
+  LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
+  // flux
+  nufft_spread_ragged_kernel<<<blocks_for((int64_t)npairs * M, 256), 256, 0, st>>>(cad, d_y, d_off, d_po, absmax, B,
+                                                                                 npairs, w, beta, p, Za);
+  LKB_LAUNCH_CHECK();
+  float2* Zout = nullptr;
+  LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+  nufft_finish_ragged_kernel<<<blocks_for(F * npairs, 256), 256, 0, st>>>(Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df,
+                                                                        d_off, d_span, d_ysum, absmax, normalization,
+                                                                        d_ns, B, npairs, d_pow);
+  LKB_LAUNCH_CHECK();
+  prof_end(st);
+  if (F_low_max > 0) {
+    nufft_lowrows_ragged_kernel<<<blocks_for(F_low_max * B, 4), 128, 0, st>>>(d_t, d_y, d_off, d_po, d_span, d_ysum, f0,
+                                                                             df, F_low_max, F, normalization, d_ns, B,
+                                                                             d_pow);
     LKB_LAUNCH_CHECK();
   }
   return LKB_OK;

@@ -103,6 +103,30 @@ LKB_HD float2 spread_cell(int64_t m, const int32_t* first_ge, const Cad* cad, co
   return acc;
 }
 
+// Ragged batches have one cadence table per light curve and no per-cell lookup table: the cadence range that
+// reaches cell m is found by two binary searches in the light curve's own (sorted) table.  Returns the cell value
+// of ONE light curve (y == NULL: unit strengths, for the window terms).
+LKB_HD float spread_cell_search(int64_t m, const Cad* cad, int64_t n, const float* y, float scale, int w, float beta,
+                                int64_t M) {
+  float acc = 0.0f;
+  const float inv_half = 2.0f / (float)w;
+  const int64_t L = table_len(M, w);
+  for (int wrap = 0; wrap < 2; ++wrap) {
+    if (wrap && m > 2 * (int64_t)w + 2) break;
+    const int64_t mm = m + (int64_t)wrap * M;
+    if (mm + 1 >= L) break;
+    int64_t lo_c = mm - w + 1;
+    if (lo_c < 0) lo_c = 0;
+    const int32_t a = first_ge_entry(lo_c, cad, n), b = first_ge_entry(mm + 1, cad, n);
+    for (int32_t i = a; i < b; ++i) {
+      const Cad c = cad[i];
+      const float ph = es_eval((c.d0 + (float)(mm - (int64_t)c.i0)) * inv_half, beta);
+      acc += y ? ph * (scale * y[i]) : ph;
+    }
+  }
+  return acc;
+}
+
 // ---- FFT ------------------------------------------------------------------------------------------
 LKB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 

@@ -49,8 +49,20 @@ int harness_gauss_legendre(int n, double* x, double* w) {
 
 // trig sums of one pair of light curves:  C + i S = sum_n y[n] exp(2 pi i (k0 + k) df t_rel[n]),  k < F
 // out_* have F entries; y1 / C1 / S1 may be NULL.  Returns log2 of the fine-grid size.
+// `search` != 0: the ragged-batch variant (binary searches per cell instead of the first_ge table); then the two
+// light curves may have DIFFERENT cadence sets: (t_rel, N, y0) and (t1_rel, N1, y1).
+int harness_trig_sums_ex(const double* t_rel, int64_t N, const float* y0, const double* t1_rel, int64_t N1,
+                         const float* y1, double df, int64_t k0, int64_t F, int w, int search, float* C0, float* S0,
+                         float* C1, float* S1);
+
 int harness_trig_sums(const double* t_rel, int64_t N, const float* y0, const float* y1, double df, int64_t k0,
                       int64_t F, int w, float* C0, float* S0, float* C1, float* S1) {
+  return harness_trig_sums_ex(t_rel, N, y0, t_rel, N, y1, df, k0, F, w, 0, C0, S0, C1, S1);
+}
+
+int harness_trig_sums_ex(const double* t_rel, int64_t N, const float* y0, const double* t1_rel, int64_t N1,
+                         const float* y1, double df, int64_t k0, int64_t F, int w, int search, float* C0, float* S0,
+                         float* C1, float* S1) {
   const int p = fine_grid_log2(k0 + F);
   const int64_t M = (int64_t)1 << p;
   const float beta = 2.30f * (float)w;
@@ -60,13 +72,19 @@ int harness_trig_sums(const double* t_rel, int64_t N, const float* y0, const flo
   std::vector<int32_t> first_ge(L);
   for (int64_t c = 0; c < L; ++c) first_ge[c] = first_ge_entry(c, cad.data(), N);
   float mx0 = 0.f, mx1 = 0.f;
-  for (int64_t n = 0; n < N; ++n) {
-    mx0 = fmaxf(mx0, fabsf(y0[n]));
-    if (y1) mx1 = fmaxf(mx1, fabsf(y1[n]));
-  }
+  for (int64_t n = 0; n < N; ++n) mx0 = fmaxf(mx0, fabsf(y0[n]));
+  if (y1) for (int64_t n = 0; n < N1; ++n) mx1 = fmaxf(mx1, fabsf(y1[n]));
   const float s0 = pow2_scale(mx0), s1 = pow2_scale(mx1);
   std::vector<float2> grid(M), spec(M);
-  for (int64_t m = 0; m < M; ++m) grid[m] = spread_cell(m, first_ge.data(), cad.data(), y0, y1, s0, s1, w, beta, M);
+  if (search) {
+    std::vector<Cad> cad1(N1);
+    for (int64_t n = 0; n < N1; ++n) cad1[n] = cad_entry(t1_rel[n], df, M, w);
+    for (int64_t m = 0; m < M; ++m)
+      grid[m] = make_float2(spread_cell_search(m, cad.data(), N, y0, s0, w, beta, M),
+                            y1 ? spread_cell_search(m, cad1.data(), N1, y1, s1, w, beta, M) : 0.0f);
+  } else {
+    for (int64_t m = 0; m < M; ++m) grid[m] = spread_cell(m, first_ge.data(), cad.data(), y0, y1, s0, s1, w, beta, M);
+  }
   fft_full(grid.data(), spec.data(), p);
   double glx[32], glw[32];
   gauss_legendre(32, glx, glw);

@@ -71,6 +71,80 @@ def _worker(out_q):
     out_q.put(res)
 
 
+def _worker_ragged(out_q):
+    """Ragged batches: LKB_LS_RAGGED_NUFFT=1 routes lkb_ls_power (one shared regular grid) through the NUFFT kernels."""
+    sys.path.insert(0, ROOT)
+    from lightkurve_b200 import engine
+    from oracle import ls as ols
+    engine.init(0)
+    rng = np.random.default_rng(33)
+    times, fluxes = [], []
+    for i in range(7):                                           # odd count: the last pair is half empty
+        n = int(rng.integers(300, 4000))
+        t = 1325.0 + np.sort(rng.uniform(0, 27.4 * rng.uniform(0.5, 1.0), n))
+        times.append(t)
+        a = [1e-2, 0.0, 1e-4, 3e-3, 0.0, 1e-3, 2e-5][i]
+        fluxes.append((1 + a * np.sin(2 * np.pi * 2.2 * t) + 10 ** rng.uniform(-4.3, -3) * rng.normal(size=n)).astype(
+            np.float32 if i % 2 else np.float64))
+    F = 3000
+    freq = np.linspace(12.0 / F, 12.0, F)                        # f0 = df: k0 = 1; df * baseline <= 0.11
+    os.environ["LKB_LS_RAGGED_NUFFT"] = "1"
+    got = np.asarray(engine.ls_power_ragged(times, [f.astype(np.float64) for f in fluxes], freq, "amplitude"),
+                     dtype=np.float64)
+    os.environ["LKB_LS_RAGGED_NUFFT"] = "0"
+    direct = np.asarray(engine.ls_power_ragged(times, [f.astype(np.float64) for f in fluxes], freq, "amplitude"),
+                        dtype=np.float64)
+    res = {"vs direct kernel": max(_excess(got[b], direct[b]) for b in range(len(times)))}
+    worst = 0.0
+    for b in (0, 1, 6):
+        y = fluxes[b].astype(np.float64)
+        ref = np.sqrt(ols.ls_slow_psd(times[b], y, freq)) * np.sqrt(4.0 / len(y))
+        worst = max(worst, _excess(got[b], ref))
+    res["vs oracle"] = worst
+    res["differs from direct"] = bool(np.any(got != direct))    # proves the NUFFT kernels actually ran
+    # a batch with an unsorted light curve falls back to the direct kernel (same numbers as without the switch)
+    os.environ["LKB_LS_RAGGED_NUFFT"] = "1"
+    t_bad = times[0][::-1].copy()
+    fb = engine.ls_power_ragged([t_bad, times[1]], [fluxes[0][::-1].astype(np.float64), fluxes[1].astype(np.float64)],
+                                freq, "amplitude")
+    res["fallback ok"] = _excess(np.asarray(fb[0], dtype=np.float64), direct[0]) < 1.0
+    out_q.put(res)
+
+
+def _run_child(target):
+    import queue
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    p = ctx.Process(target=target, args=(out_q,), daemon=True)
+    p.start()
+    res, t0 = None, time.time()
+    try:
+        while res is None:
+            try:
+                res = out_q.get(timeout=1.0)
+            except queue.Empty:
+                assert p.is_alive() or p.exitcode == 0, "worker died with exit code %r" % p.exitcode
+                assert time.time() - t0 < 300, "timed out"
+    finally:
+        if p.is_alive():
+            p.join(timeout=30)
+        if p.is_alive():
+            p.kill()
+    return res
+
+
+@pytest.mark.xfail(strict=False, reason="CUDA glue of the ragged NUFFT path not validated on hardware yet (round 1)")
+def test_ragged_nufft_path_matches_direct_kernel_and_oracle():
+    res = _run_child(_worker_ragged)
+    print("ragged NUFFT path, worst tolerance excess per case:", res)
+    assert res["differs from direct"] is True
+    assert res["vs direct kernel"] < 1.0
+    assert res["vs oracle"] < 1.0
+    assert res["fallback ok"] is True
+
+
 @pytest.mark.xfail(strict=False, reason="CUDA glue of the NUFFT path not validated on hardware yet (round 1)")
 def test_nufft_path_matches_oracle_and_simt_kernel():
     import queue

@@ -30,6 +30,8 @@ def harness(tmp_path_factory):
     lib.harness_gauss_legendre.argtypes = [ctypes.c_int, c_vp, c_vp]
     lib.harness_trig_sums.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, c_i64, c_i64, ctypes.c_int,
                                       c_vp, c_vp, c_vp, c_vp]
+    lib.harness_trig_sums_ex.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, ctypes.c_double, c_i64, c_i64,
+                                         ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]
     return lib
 
 
@@ -151,3 +153,33 @@ def test_pair_members_of_very_different_amplitude(harness):
         yd = y.astype(np.float64)
         err = max(np.abs(C - np.cos(ph) @ yd).max(), np.abs(S - np.sin(ph) @ yd).max())
         assert err <= 2e-7 * np.abs(yd).sum()
+
+
+def test_ragged_pair_with_different_cadence_sets(harness):
+    """Ragged batches (K1): the two light curves of a pair have their own times; cell ranges come from binary
+    searches in each light curve's sorted cadence table (`spread_cell_search`)."""
+    rng = np.random.default_rng(12)
+    ta = np.sort(rng.uniform(0, 27.4, 2500))
+    ta -= ta[0]
+    tb = np.sort(rng.uniform(0, 20.0, 900))
+    tb -= tb[0]
+    F, k0, w = 1500, 1, 8
+    df = 1.0 / (5.0 * 27.4)
+    ya = rng.normal(size=len(ta)).astype(np.float32)
+    yb = (3e-3 * np.sin(2 * np.pi * 0.7 * tb)).astype(np.float32)
+    out = [np.zeros(F, np.float32) for _ in range(4)]
+    harness.harness_trig_sums_ex(ta.ctypes.data, len(ta), ya.ctypes.data, tb.ctypes.data, len(tb), yb.ctypes.data,
+                                 df, k0, F, w, 1, *[o.ctypes.data for o in out])
+    f = (k0 + np.arange(F)) * df
+    for t, y, C, S in ((ta, ya, out[0], out[1]), (tb, yb, out[2], out[3])):
+        ph = 2 * np.pi * np.outer(f, t)
+        yd = y.astype(np.float64)
+        err = max(np.abs(C - np.cos(ph) @ yd).max(), np.abs(S - np.sin(ph) @ yd).max())
+        assert err <= 2e-7 * np.abs(yd).sum()
+    # the search variant and the table variant are the same arithmetic
+    ref = trig_sums(harness, ta, ya, None, df, k0, F, w)
+    out2 = [np.zeros(F, np.float32) for _ in range(2)]
+    harness.harness_trig_sums_ex(ta.ctypes.data, len(ta), ya.ctypes.data, ta.ctypes.data, len(ta), None, df, k0, F, w,
+                                 1, out2[0].ctypes.data, out2[1].ctypes.data, None, None)
+    np.testing.assert_array_equal(out2[0], ref[0].astype(np.float32))
+    np.testing.assert_array_equal(out2[1], ref[1].astype(np.float32))
