@@ -68,4 +68,7 @@ def test_gpu_shim_test_body_on_the_oracle(fn, params, oracle_engine, caplog, mon
         kwargs["monkeypatch"] = monkeypatch
     if "engine" in sig:
         kwargs["engine"] = oracle_engine
+    import numpy as np
+    from conftest import seed_for
+    np.random.seed(seed_for(fn.__name__))            # the data the GPU run of this test will see
     fn(**kwargs)
