@@ -183,3 +183,24 @@ def test_ragged_pair_with_different_cadence_sets(harness):
                                  1, out2[0].ctypes.data, out2[1].ctypes.data, None, None)
     np.testing.assert_array_equal(out2[0], ref[0].astype(np.float32))
     np.testing.assert_array_equal(out2[1], ref[1].astype(np.float32))
+
+
+def test_tiny_and_degenerate_inputs(harness):
+    """1-40 cadences, duplicate times, k0 = 0 (mode 0), 2-17 bins, df * baseline = 1 and 1/3."""
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for N in (1, 2, 3, 5, 9, 40):
+        for F in (2, 3, 17):
+            for k0 in (0, 1, 5):
+                for oversample in (1.0, 3.0):
+                    t = np.sort(rng.uniform(0, 10, N))
+                    t -= t[0]
+                    if N > 2:
+                        t[1] = t[2]
+                    df = 1.0 / (oversample * max(t[-1], 1.0))
+                    y = rng.normal(size=N).astype(np.float32)
+                    C, S, _, _ = trig_sums(harness, t, y, None, df, k0, F)
+                    ph = 2 * np.pi * np.outer((k0 + np.arange(F)) * df, t)
+                    err = max(np.abs(C - np.cos(ph) @ y).max(), np.abs(S - np.sin(ph) @ y).max())
+                    worst = max(worst, err / np.abs(y).sum())
+    assert worst < 2e-6
