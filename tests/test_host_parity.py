@@ -336,3 +336,45 @@ def test_regression_oracle_with_sparse_matrix_is_the_dense_problem():
     assert isinstance(X, np.ndarray) and X.flags.c_contiguous and X.dtype == np.float64
     assert_array_equal(X, dmc.values)
     assert isinstance(RegressionCorrector._as_collection(create_sparse_spline_matrix(x)), SparseDesignMatrixCollection)
+
+
+# ---- LightCurve.bin (reference: tests/test_lightcurve.py:707-767, 1543-1549, 2272-2276) -------------------
+def test_bin():
+    lc = lk.LightCurve(time=np.arange(10), flux=2 * np.ones(10), flux_err=2 ** 0.5 * np.ones(10))
+    binned_lc = lc.bin(binsize=2)
+    np.testing.assert_allclose(binned_lc.flux.value, 2 * np.ones(5))
+    np.testing.assert_allclose(binned_lc.flux_err.value, np.sqrt(((2 ** 0.5) ** 2 + (2 ** 0.5) ** 2) / 2) * np.ones(5))
+    assert len(binned_lc.time) == 5
+    with pytest.raises(TypeError):
+        lc.bin(method="doesnotexist")
+    lc = lk.LightCurve(time=np.arange(10), flux=2 * np.ones(10))
+    np.testing.assert_allclose(lc.bin(binsize=2).flux_err.value, np.zeros(5))        # no errors: std of the bin
+    lc = lk.LightCurve(time=np.arange(2000), flux=np.random.normal(loc=42, scale=0.01, size=2000))
+    assert np.round(lc.bin(2000).flux_err.value[0], 2) == 0.01                       # regression test for #500
+    lk.LightCurve(flux=[0, 0, 0]).bin(bins=2)                                        # #1162
+    lk.LightCurve(time=np.arange(50), flux=np.ones(50)).bin(binsize=15)              # #705
+    with pytest.raises(ValueError, match="Only one of"):
+        lc.bin(bins=2, binsize=2)
+    with pytest.raises(ValueError, match="conflicts"):
+        lc.bin(bins=2, time_bin_size=1)
+    with pytest.raises(TypeError, match="integer"):
+        lc.bin(bins=2.5)
+
+
+def test_bin_semantics():
+    lc = lk.LightCurve(time=np.arange(10), flux=np.arange(10.0), flux_err=np.ones(10), label="x")
+    lc.meta["SECTOR"] = 99
+    b = lc.bin(time_bin_size=5)
+    assert b.meta == lc.meta                                                         # #1040
+    np.testing.assert_allclose(b.time.value, [2.5, 7.5])                             # bin centres
+    np.testing.assert_allclose(b.flux.value, [2.0, 7.0])                             # [0, 5) and [5, 10)
+    b = lc.bin(time_bin_size=3, n_bins=5)                                            # the fifth bin [12, 15) is empty
+    np.testing.assert_allclose(b.flux.value[:4], [1.0, 4.0, 7.0, 9.0])
+    assert np.isnan(b.flux.value[4]) and np.isnan(b.flux_err.value[4])
+    b = lc.bin(time_bin_size=u.Quantity(48, u.hour), time_bin_start=1.0, aggregate_func=np.nanmedian)
+    np.testing.assert_allclose(b.flux.value, [1.5, 3.5, 5.5, 8.0])                   # 4 bins; t = 9 closes the last one
+    shuffled = lc[np.array([3, 1, 2, 0, 9, 8, 7, 6, 5, 4])]
+    np.testing.assert_allclose(shuffled.bin(time_bin_size=5).flux.value, [2.0, 7.0])
+    np.testing.assert_allclose(lc.bin(bins=np.array([0, 4, 9])).flux.value, [1.5, 6.5])  # cadence-index edges
+    folded = lk.LightCurve(time=np.arange(2000), flux=np.random.normal(loc=42, scale=0.01, size=2000)).fold(period=100)
+    assert np.round(folded.bin(time_bin_size=100).flux_err.value[0], 2) == 0.01       # #927
