@@ -298,7 +298,11 @@ class LightCurve:
                     berr[j] = np.nanstd(v) if np.any(np.isfinite(v)) else np.nan
         new = self.__class__.__new__(self.__class__)
         new.meta = _copy.deepcopy(self.meta)
-        new.time = Time(starts + 0.5 * (ends - starts), self.time.format, self.time.scale)
+        centres = starts + 0.5 * (ends - starts)
+        if isinstance(self.time, Time):
+            new.time = Time(centres, self.time.format, self.time.scale)
+        else:                                                   # a folded light curve: "time" is the phase
+            new.time = Quantity(centres, self.time.unit)
         new.flux = Quantity(bflux, self.flux.unit)
         new.flux_err = Quantity(berr, self.flux_err.unit)
         return new
