@@ -58,12 +58,17 @@ class LightCurve:
             time, flux, data = data, args[0], None
             if len(args) == 2:
                 flux_err = args[1]
+        extra = {}
         if isinstance(data, dict):
             time = data.get("time", time)
             flux = data.get("flux", flux)
             flux_err = data.get("flux_err", flux_err)
+            extra.update({k: v for k, v in data.items() if k in self._extra_column_names})
         elif data is not None:
             raise TypeError("`data` must be a dict with 'time'/'flux'[/'flux_err'] in this build")
+        for name in self._extra_column_names:                  # optional per-cadence columns (cadenceno, quality, ...)
+            if name in kwargs:
+                extra[name] = kwargs.pop(name)
         flux_unit = kwargs.pop("flux_unit", None)
         time_format = kwargs.pop("time_format", self._default_time_format)
         time_scale = kwargs.pop("time_scale", self._default_time_scale)
@@ -95,6 +100,22 @@ class LightCurve:
         self.time = time
         self.flux = flux
         self.flux_err = flux_err
+        self._columns = {}
+        for name, col in extra.items():
+            col = np.asarray(getattr(col, "value", col))
+            if len(col) != len(time):
+                raise ValueError("column `{}` must have as many entries as `time`".format(name))
+            self._columns[name] = col
+
+    # per-cadence columns carried along besides time / flux / flux_err (the reference's LightCurve is a table with
+    # arbitrary columns, lightcurve.py:490-539; these are the ones the hot path's neighbours use)
+    _extra_column_names = ("cadenceno", "quality", "centroid_col", "centroid_row")
+
+    def __getattr__(self, name):
+        cols = self.__dict__.get("_columns")
+        if cols is not None and name in cols:
+            return cols[name]
+        raise AttributeError("{!r} object has no attribute {!r}".format(type(self).__name__, name))
 
     # ------------------------------------------------------------------ container protocol
     def __len__(self):
@@ -117,6 +138,7 @@ class LightCurve:
         new.time = self.time.copy() if copy_data else self.time
         new.flux = self.flux.copy() if copy_data else self.flux
         new.flux_err = self.flux_err.copy() if copy_data else self.flux_err
+        new._columns = {k: (v.copy() if copy_data else v) for k, v in self.__dict__.get("_columns", {}).items()}
         return new
 
     def __getitem__(self, key):
@@ -128,6 +150,7 @@ class LightCurve:
         new.time = Time(self.time.value[key], self.time.format, self.time.scale)
         new.flux = Quantity(self.flux.value[key], self.flux.unit, dtype=self.flux.dtype)
         new.flux_err = Quantity(self.flux_err.value[key], self.flux_err.unit, dtype=self.flux_err.dtype)
+        new._columns = {k: v[key] for k, v in self.__dict__.get("_columns", {}).items()}
         return new
 
     def __setitem__(self, key, value):
@@ -298,6 +321,7 @@ class LightCurve:
                     berr[j] = np.nanstd(v) if np.any(np.isfinite(v)) else np.nan
         new = self.__class__.__new__(self.__class__)
         new.meta = _copy.deepcopy(self.meta)
+        new._columns = {}
         centres = starts + 0.5 * (ends - starts)
         if isinstance(self.time, Time):
             new.time = Time(centres, self.time.format, self.time.scale)
@@ -452,6 +476,10 @@ class LightCurve:
         new.flux = Quantity(np.concatenate([np.asarray(lc.flux.to(self.flux.unit).value) for lc in lcs]), self.flux.unit)
         new.flux_err = Quantity(np.concatenate([np.asarray(lc.flux_err.to(self.flux.unit).value) for lc in lcs]),
                                 self.flux.unit)
+        shared = set(self.__dict__.get("_columns", {}))
+        for lc in lcs[1:]:
+            shared &= set(lc.__dict__.get("_columns", {}))
+        new._columns = {k: np.concatenate([lc._columns[k] for lc in lcs]) for k in shared}
         return new
 
     def to_corrector(self, method="regression", **kwargs):
@@ -503,6 +531,7 @@ class LightCurve:
         folded.flux = Quantity(np.asarray(self.flux.value)[order], self.flux.unit, dtype=self.flux.dtype)
         folded.flux_err = Quantity(np.asarray(self.flux_err.value)[order], self.flux_err.unit, dtype=self.flux_err.dtype)
         folded.time_original = Time(t[order], self.time.format, self.time.scale)
+        folded._columns = {k: v[order] for k, v in self.__dict__.get("_columns", {}).items()}
         folded.meta["PERIOD"] = Quantity(per, u.day)
         folded.meta["EPOCH_TIME"] = None if epoch_time is None else Time(t0, self.time.format, self.time.scale)
         folded.meta["EPOCH_PHASE"] = epoch_phase
