@@ -4,3 +4,4 @@ from .designmatrix import (DesignMatrix, DesignMatrixCollection, SparseDesignMat
                            SparseDesignMatrixCollection, create_spline_matrix, create_sparse_spline_matrix)
 from .regressioncorrector import RegressionCorrector  # noqa: F401
 from .metrics import overfit_metric_lombscargle  # noqa: F401
+from .cbvcorrector import CBVCorrector, CotrendingBasisVectors  # noqa: F401
