@@ -11,7 +11,6 @@ import warnings
 
 import numpy as np
 
-from .. import units as u
 from ..lightcurve import LightCurve
 from ..units import Quantity
 from .designmatrix import (DesignMatrix, DesignMatrixCollection, SparseDesignMatrix,
