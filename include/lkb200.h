@@ -71,6 +71,10 @@ int64_t lkb_launch_count(void);
  * lkb_profile_read synchronises, writes up to max_n durations [ms] in call order, resets the ring
  * and returns how many were written (< 0 on error). */
 int lkb_profile_enable(int on);
+/* Diagnostic (not part of the drop-in boundary): read back `bytes` bytes at `offset` of one of the library's
+ * internal workspace buffers (slot numbering: enum Slot in lightkurve_b200/csrc/common.cuh) after the last call -
+ * used by tools/nufft_gpu_check.py to compare intermediate results stage by stage with the CPU harness. */
+int lkb_ws_read(int slot, int64_t offset, int64_t bytes, void* out);
 int lkb_profile_read(double* ms_out, int max_n);
 
 /* ---- Lomb-Scargle ------------------------------------------------------- */

@@ -292,6 +292,19 @@ int lkb_profile_read(double* ms_out, int max_n) {
 }
 int64_t lkb_launch_count(void) { return g_launches; }
 
+// Diagnostic: copy `bytes` bytes at `offset` of workspace slot `slot` to the host buffer `out` (after a device
+// synchronise).  Lets a test or tools/nufft_gpu_check.py look at the intermediate buffers of the last call.
+int lkb_ws_read(int slot, int64_t offset, int64_t bytes, void* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  LKB_REQUIRE(g_ctx.inited, "lkb_ws_read: engine not initialised");
+  LKB_REQUIRE(slot >= 0 && slot < WS_NSLOTS && out != nullptr && offset >= 0 && bytes >= 0, "lkb_ws_read: bad argument");
+  LKB_REQUIRE(g_ctx.ptr[slot] != nullptr && (size_t)(offset + bytes) <= g_ctx.cap[slot],
+              "lkb_ws_read: range outside the slot's current buffer");
+  LKB_CUDA_CHECK(cudaDeviceSynchronize());
+  LKB_CUDA_CHECK(cudaMemcpy(out, (const char*)g_ctx.ptr[slot] + offset, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return LKB_OK;
+}
+
 int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B, const double* freq,
                  const int64_t* freq_offsets, int64_t F, int normalization, const double* norm_scale, float* power,
                  int mem, void* stream) {

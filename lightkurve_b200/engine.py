@@ -55,6 +55,20 @@ def profile_read(max_n=512):
     return buf[:n].copy()
 
 
+# workspace slot numbers (enum Slot in csrc/common.cuh) for the diagnostic read-back
+WS_SLOTS = {name: i for i, name in enumerate(
+    ["A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L", "M", "N", "O", "P"]
+    + ["IN%d" % i for i in range(8)] + ["OUT%d" % i for i in range(8)])}
+
+
+def ws_read(slot, count, dtype, offset_bytes=0):
+    """Diagnostic: `count` items of `dtype` from workspace slot `slot` ("A".."P", "IN0".., "OUT0"..) as left by
+    the last call (device synchronised first)."""
+    out = np.empty(count, dtype=dtype)
+    L.check(L.load().lkb_ws_read(WS_SLOTS[slot], int(offset_bytes), int(out.nbytes), L.ptr(out)))
+    return out
+
+
 def sm_count():
     return int(L.load().lkb_sm_count())
 
