@@ -99,4 +99,36 @@ int harness_trig_sums_ex(const double* t_rel, int64_t N, const float* y0, const 
   return p;
 }
 
+// Intermediate buffers of the table-based (shared-grid) pipeline in the layouts ls_nufft_launch keeps them in its
+// workspace: cad [N] {int32 i0, float d0}, first_ge [M + 2w + 4] int32, grid / spec [M] float2, dec [F] float2.
+int harness_stages(const double* t_rel, int64_t N, const float* y0, const float* y1, double df, int64_t k0, int64_t F,
+                   int w, int32_t* cad_out, int32_t* first_ge_out, float* spec_out, float* dec_out) {
+  const int p = fine_grid_log2(k0 + F);
+  const int64_t M = (int64_t)1 << p;
+  const float beta = 2.30f * (float)w;
+  std::vector<Cad> cad(N);
+  for (int64_t n = 0; n < N; ++n) cad[n] = cad_entry(t_rel[n], df, M, w);
+  memcpy(cad_out, cad.data(), sizeof(Cad) * N);
+  const int64_t L = table_len(M, w);
+  std::vector<int32_t> first_ge(L);
+  for (int64_t c = 0; c < L; ++c) first_ge[c] = first_ge_entry(c, cad.data(), N);
+  memcpy(first_ge_out, first_ge.data(), sizeof(int32_t) * L);
+  float mx0 = 0.f, mx1 = 0.f;
+  for (int64_t n = 0; n < N; ++n) { mx0 = fmaxf(mx0, fabsf(y0[n])); if (y1) mx1 = fmaxf(mx1, fabsf(y1[n])); }
+  std::vector<float2> grid(M), spec(M);
+  for (int64_t m = 0; m < M; ++m)
+    grid[m] = spread_cell(m, first_ge.data(), cad.data(), y0, y1, pow2_scale(mx0), pow2_scale(mx1), w, beta, M);
+  fft_full(grid.data(), spec.data(), p);
+  memcpy(spec_out, spec.data(), sizeof(float2) * M);
+  double glx[32], glw[32];
+  gauss_legendre(32, glx, glw);
+  for (int64_t k = 0; k < F; ++k) {
+    double re, im;
+    deconv_factor(k0 + k, M, w, (double)beta, glx, glw, 32, &re, &im);
+    dec_out[2 * k] = (float)re;
+    dec_out[2 * k + 1] = (float)im;
+  }
+  return p;
+}
+
 }  // extern "C"

@@ -30,6 +30,8 @@ def harness(tmp_path_factory):
     lib.harness_gauss_legendre.argtypes = [ctypes.c_int, c_vp, c_vp]
     lib.harness_trig_sums.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, c_i64, c_i64, ctypes.c_int,
                                       c_vp, c_vp, c_vp, c_vp]
+    lib.harness_stages.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, c_i64, c_i64, ctypes.c_int,
+                                   c_vp, c_vp, c_vp, c_vp]
     lib.harness_trig_sums_ex.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, ctypes.c_double, c_i64, c_i64,
                                          ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]
     return lib
@@ -204,3 +206,38 @@ def test_tiny_and_degenerate_inputs(harness):
                     err = max(np.abs(C - np.cos(ph) @ y).max(), np.abs(S - np.sin(ph) @ y).max())
                     worst = max(worst, err / np.abs(y).sum())
     assert worst < 2e-6
+
+
+def test_gpu_bringup_tool_accepts_the_harness_buffers(harness):
+    """tools/nufft_gpu_check.py compares the GPU's intermediate buffers with reference formulas written in numpy;
+    fed with the buffers of the CPU harness (same layouts) every stage must pass - and a corrupted buffer must not."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("nufft_gpu_check", os.path.join(os.path.dirname(HERE), "tools",
+                                                                               "nufft_gpu_check.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    rng = np.random.default_rng(2)
+    N, F, k0, w = 700, 400, 1, 8
+    t = np.sort(rng.uniform(0, 30, N))
+    t -= t[0]
+    df = 1.0 / (5.0 * t[-1])
+    y0 = (3e-3 * rng.normal(size=N)).astype(np.float32)
+    y1 = rng.normal(size=N).astype(np.float32)
+    p = 4
+    while (1 << p) < 4 * (k0 + F):
+        p += 1
+    M = 1 << p
+    cad = np.zeros(2 * N, np.int32)
+    fge = np.zeros(M + 2 * w + 4, np.int32)
+    spec_buf = np.zeros((M, 2), np.float32)
+    dec = np.zeros((F, 2), np.float32)
+    assert harness.harness_stages(t.ctypes.data, N, y0.ctypes.data, y1.ctypes.data, df, k0, F, w, cad.ctypes.data,
+                                  fge.ctypes.data, spec_buf.ctypes.data, dec.ctypes.data) == p
+    C0, S0, _, _ = trig_sums(harness, t, y0, y1, df, k0, F, w)
+    stages = tool.check_stages(cad, fge, dec, spec_buf, t, y0, df, k0, F, w, (C0, S0))
+    assert [ok for _, ok, _ in stages] == [True, True, True], stages
+    bad = spec_buf.copy()
+    bad[k0 + 5] *= 1.01
+    stages = tool.check_stages(cad, fge, dec, bad, t, y0, df, k0, F, w, (C0, S0))
+    assert [ok for _, ok, _ in stages] == [True, True, False]

@@ -32,6 +32,37 @@ def build_harness():
     return lib
 
 
+def check_stages(cad, fge, dec, Z0, trel, yc0, df, k0, F, w, sums0):
+    """Compare the intermediate buffers of one call (cad [2N] int32 view of {i0, d0}, first_ge, dec [F, 2],
+    Z0 [M, 2] = final transform of pair 0) with what they must be; `sums0` = (C, S) of light curve 0 from the CPU
+    harness.  Returns [(stage, ok, detail)]."""
+    N = len(trel)
+    p = 4
+    while (1 << p) < 4 * (k0 + F):
+        p += 1
+    M = 1 << p
+    shift = (w + 1) // 2 + 1
+    out = []
+    i0 = np.asarray(cad[0::2], dtype=np.int64)
+    d0 = np.asarray(cad[1::2]).view(np.float32)
+    x = df * trel * M + shift
+    i0_ref = np.ceil(x - 0.5 * w).astype(np.int64)
+    out.append(("cadence table", np.array_equal(i0, i0_ref) and np.allclose(d0, i0_ref - x, atol=1e-6),
+                "max |d0 err| %.2e" % np.abs(d0 - (i0_ref - x)).max()))
+    L = M + 2 * w + 4
+    out.append(("first_ge table", np.array_equal(fge[:L], np.searchsorted(i0_ref, np.arange(L), side="left")), ""))
+    z = Z0[:, 0].astype(np.float64) + 1j * Z0[:, 1].astype(np.float64)
+    kk = k0 + np.arange(F)
+    g1, g2 = z[kk], z[(M - kk) % M]
+    mx = float(np.abs(yc0).max())
+    s0 = 1.0 if mx == 0 else 2.0 ** -(np.frexp(np.float32(mx))[1])          # nufft::pow2_scale
+    a = 0.5 * (g1 + np.conj(g2)) * (dec[:, 0] + 1j * dec[:, 1]) / s0
+    ref = sums0[0] + 1j * sums0[1]
+    err = np.abs(a - ref).max() / max(np.abs(yc0).sum(), 1e-30)
+    out.append(("spread + FFT + deconvolution", err < 3e-6, "pair 0, LC 0: max err / |y|_1 = %.2e" % err))
+    return out
+
+
 def main():
     from lightkurve_b200 import engine
     from oracle import ls as ols
@@ -50,55 +81,28 @@ def main():
                   1 + 3e-4 * rng.normal(size=N), 1 + 1e-3 * rng.normal(size=N)]).astype(np.float32)
     B = len(Y)
     got = np.asarray(engine.ls_power_shared(t, Y, freq, "amplitude", algo="nufft"), dtype=np.float64)
-
     p = 4
     while (1 << p) < 4 * (k0 + F):
         p += 1
     M = 1 << p
-    shift = (w + 1) // 2 + 1
-    ok_all = True
-
-    def report(stage, ok, detail=""):
-        nonlocal ok_all
-        ok_all &= bool(ok)
-        print("%-28s %s  %s" % (stage, "ok  " if ok else "FAIL", detail))
-
-    # -- cadence table
-    cad = engine.ws_read("A", 2 * N, np.int32)                      # struct {int32 i0; float d0;}
-    i0 = cad[0::2]
-    d0 = cad[1::2].view(np.float32)
-    x = df * trel * M + shift
-    i0_ref = np.ceil(x - 0.5 * w).astype(np.int64)
-    report("cadence table", np.array_equal(i0, i0_ref) and np.allclose(d0, i0_ref - x, atol=1e-6),
-           "max |d0 err| %.2e" % np.abs(d0 - (i0_ref - x)).max())
-    # -- first_ge
-    L = M + 2 * w + 4
-    fge = engine.ws_read("B", L, np.int32)
-    report("first_ge table", np.array_equal(fge, np.searchsorted(i0_ref, np.arange(L), side="left")))
-    # -- transform output: the harness gives the final trig sums; compare through the power instead, and check the
-    #    raw FFT buffer against numpy for the first pair
     yc = (Y.astype(np.float64) - Y.astype(np.float64).mean(axis=1, keepdims=True)).astype(np.float32)
     C0, S0, C1, S1 = (np.zeros(F, np.float32) for _ in range(4))
     lib.harness_trig_sums(trel.ctypes.data, N, yc[0].ctypes.data, yc[1].ctypes.data, df, k0, F, w, C0.ctypes.data,
                           S0.ctypes.data, C1.ctypes.data, S1.ctypes.data)
-    dec = engine.ws_read("C", 2 * F, np.float32).reshape(F, 2)
     npass = (p + 3) // 4
+    cad = engine.ws_read("A", 2 * N, np.int32)
+    fge = engine.ws_read("B", M + 2 * w + 4, np.int32)
+    dec = engine.ws_read("C", 2 * F, np.float32).reshape(F, 2)
     Z = engine.ws_read("H" if npass % 2 == 0 else "I", 2 * M * ((B + 1) // 2), np.float32).reshape(-1, M, 2)
-    z = Z[0, :, 0] + 1j * Z[0, :, 1]
-    kk = k0 + np.arange(F)
-    g1, g2 = z[kk], z[(M - kk) % M]
-    s0 = 2.0 ** -np.ceil(np.log2(np.abs(yc[0]).max() * (1 + 1e-7)))   # pow2_scale (max |y| into [0.5, 1))
-    a = 0.5 * (g1 + np.conj(g2)) * (dec[:, 0] + 1j * dec[:, 1])
-    scale0 = np.abs(a).max() / max(np.abs(C0 + 1j * S0).max(), 1e-30)
-    report("spread + FFT + deconvolution", np.allclose(a / scale0, C0 + 1j * S0, atol=3e-6 * np.abs(yc[0]).sum()),
-           "pair 0, LC 0: max err / |y|_1 = %.2e (pre-scale seen %.4g, expected %.4g)"
-           % (np.abs(a / scale0 - (C0 + 1j * S0)).max() / np.abs(yc[0]).sum(), scale0, s0))
-    # -- power vs oracle
+    stages = check_stages(cad, fge, dec, Z[0], trel, yc[0], df, k0, F, w, (C0.astype(np.float64), S0.astype(np.float64)))
     worst = 0.0
     for b in range(B):
         ref = np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq)) * np.sqrt(4.0 / N)
         worst = max(worst, float(np.max(np.abs(got[b] - ref) / (1e-5 * ref.max() + 1e-4 * ref))))
-    report("power vs fp64 oracle", worst < 1.0, "worst tolerance excess %.3f" % worst)
+    stages.append(("power vs fp64 oracle", worst < 1.0, "worst tolerance excess %.3f" % worst))
+    for stage, ok, detail in stages:
+        print("%-30s %s  %s" % (stage, "ok  " if ok else "FAIL", detail))
+    ok_all = all(ok for _, ok, _ in stages)
     print("VERDICT:", "NUFFT path verified on this GPU" if ok_all else "see the first FAIL above")
     return 0 if ok_all else 1
 
