@@ -285,18 +285,35 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
     LKB_LAUNCH_CHECK();
   }
 
-  // ---- the batch: spread, FFT, finish ----
+  // ---- the batch: spread, FFT, finish - optionally in groups of light-curve pairs small enough for the fine grids
+  // of a group (two buffers) to stay in the 126 MB L2 across the passes (LKB_NUFFT_GROUP_MB, default 0 = one group;
+  // to be tuned on hardware: more launches against HBM sweeps turned into L2 sweeps) ----
+  int group = npairs;
+  if (const char* e = getenv("LKB_NUFFT_GROUP_MB")) {
+    const double mb = atof(e);
+    if (mb > 0.0) {
+      const double per_pair = 2.0 * (double)M * sizeof(float2) / 1048576.0;
+      group = (int)fmax(1.0, floor(mb / per_pair));
+      if (group > npairs) group = npairs;
+    }
+  }
   prof_begin(st);
-  nufft_spread_kernel<<<blocks_for((int64_t)npairs * M, 256), 256, 0, st>>>(fge, cad, d_yc, ystride, d_absmax, B, npairs,
-                                                                          w, beta, p, Za);
-  LKB_LAUNCH_CHECK();
-  float2* Zout = nullptr;
-  LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
-  if (F_low < F) {
-    nufft_finish_kernel<<<blocks_for((F - F_low) * npairs, 256), 256, 0, st>>>(
-        Zout, p, dec, k0, F, F_low, d_rot, d_rot2, d_ysumf, d_absmax, (float)N, normalization, (float)norm_scale, B, npairs,
-        d_pow);
+  for (int g0 = 0; g0 < npairs; g0 += group) {
+    const int np_g = std::min(group, npairs - g0);
+    const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
+    float2* Za_g = Za + (size_t)g0 * M;
+    float2* Zb_g = Zb + (size_t)g0 * M;
+    nufft_spread_kernel<<<blocks_for((int64_t)np_g * M, 256), 256, 0, st>>>(
+        fge, cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
     LKB_LAUNCH_CHECK();
+    float2* Zout = nullptr;
+    LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));
+    if (F_low < F) {
+      nufft_finish_kernel<<<blocks_for((F - F_low) * np_g, 256), 256, 0, st>>>(
+          Zout, p, dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
+          (float)norm_scale, B_g, np_g, d_pow + (size_t)2 * g0 * F);
+      LKB_LAUNCH_CHECK();
+    }
   }
   prof_end(st);
   if (F_low > 0) {
