@@ -70,14 +70,22 @@ nufft_spread_kernel(const int32_t* __restrict__ first_ge, const Cad* __restrict_
   Z[gid] = nufft::spread_cell(m, first_ge, cad, y0, y1, s0, s1, w, beta, M);
 }
 
-template <int R>
+template <int R, bool CHAIN>
 __global__ void __launch_bounds__(256)
 nufft_fft_pass_kernel(const float2* __restrict__ x, float2* __restrict__ y, int64_t Ns, int log2M, int64_t total) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int64_t M = (int64_t)1 << log2M, per = M / R;
   const int64_t pair = gid / per, i = gid - pair * per;
-  nufft::fft_pass_butterfly<R>(x + pair * M, y + pair * M, i, Ns, M);
+  nufft::fft_pass_butterfly<R, CHAIN>(x + pair * M, y + pair * M, i, Ns, M);
+}
+
+template <bool CHAIN>
+void launch_pass(int R, unsigned g, const float2* src, float2* dst, int64_t Ns, int p, int64_t total, cudaStream_t st) {
+  if (R == 16) nufft_fft_pass_kernel<16, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+  else if (R == 8) nufft_fft_pass_kernel<8, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+  else if (R == 4) nufft_fft_pass_kernel<4, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+  else nufft_fft_pass_kernel<2, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
 }
 
 __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
@@ -181,15 +189,17 @@ int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2*
   const int64_t M = (int64_t)1 << p;
   float2 *src = a, *dst = b;
   int64_t Ns = 1;
+  const char* ce = getenv("LKB_NUFFT_TWIDDLE_CHAIN");
+  const bool chain = ce && atoi(ce) != 0;
   for (int idx = 0;; ++idx) {
     const int R = nufft::fft_pass_radix(p, idx);
     if (R == 0) break;
     const int64_t total = (int64_t)npairs * (M / R);
     const unsigned g = blocks_for(total, 256);
-    if (R == 16) nufft_fft_pass_kernel<16><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-    else if (R == 8) nufft_fft_pass_kernel<8><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-    else if (R == 4) nufft_fft_pass_kernel<4><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-    else nufft_fft_pass_kernel<2><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+    // LKB_NUFFT_TWIDDLE_CHAIN=1: one sincospif per butterfly + product tree (fewer instructions, 2.5x the rounding
+    // error of the transform; off by default until the passes have been profiled)
+    if (chain) launch_pass<true>(R, g, src, dst, Ns, p, total, st);
+    else launch_pass<false>(R, g, src, dst, Ns, p, total, st);
     LKB_LAUNCH_CHECK();
     Ns *= R;
     float2* tmp = src; src = dst; dst = tmp;

@@ -11,9 +11,12 @@
 
 using namespace lkb::nufft;
 
+static bool g_chain = false;          // twiddles by product tree (harness_set_chain)
+
 template <int R>
 static void run_pass(const float2* x, float2* y, int64_t Ns, int64_t M) {
-  for (int64_t i = 0; i < M / R; ++i) fft_pass_butterfly<R>(x, y, i, Ns, M);
+  if (g_chain) for (int64_t i = 0; i < M / R; ++i) fft_pass_butterfly<R, true>(x, y, i, Ns, M);
+  else for (int64_t i = 0; i < M / R; ++i) fft_pass_butterfly<R, false>(x, y, i, Ns, M);
 }
 
 // length-2^p transform (+i sign) of `in` (interleaved re, im); result in `out`
@@ -36,6 +39,8 @@ static void fft_full(const float2* in, float2* out, int p) {
 }
 
 extern "C" {
+
+void harness_set_chain(int on) { g_chain = on != 0; }
 
 int harness_fft(const float* in, int p, float* out) {
   fft_full(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), p);

@@ -30,6 +30,7 @@ def harness(tmp_path_factory):
     lib.harness_gauss_legendre.argtypes = [ctypes.c_int, c_vp, c_vp]
     lib.harness_trig_sums.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, c_i64, c_i64, ctypes.c_int,
                                       c_vp, c_vp, c_vp, c_vp]
+    lib.harness_set_chain.argtypes = [ctypes.c_int]
     lib.harness_stages.argtypes = [c_vp, c_i64, c_vp, c_vp, ctypes.c_double, c_i64, c_i64, ctypes.c_int,
                                    c_vp, c_vp, c_vp, c_vp]
     lib.harness_trig_sums_ex.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, ctypes.c_double, c_i64, c_i64,
@@ -241,3 +242,30 @@ def test_gpu_bringup_tool_accepts_the_harness_buffers(harness):
     bad[k0 + 5] *= 1.01
     stages = tool.check_stages(cad, fge, dec, bad, t, y0, df, k0, F, w, (C0, S0))
     assert [ok for _, ok, _ in stages] == [True, True, False]
+
+
+def test_twiddle_product_tree_variant(harness):
+    """LKB_NUFFT_TWIDDLE_CHAIN=1 (one sincospif per butterfly, the other twiddles by a product tree): the transform
+    error grows ~2.5x and the whole pipeline stays far inside the parity tolerance."""
+    rng = np.random.default_rng(31)
+    try:
+        harness.harness_set_chain(1)
+        for p in (9, 14):
+            M = 1 << p
+            z = (rng.normal(size=M) + 1j * rng.normal(size=M)).astype(np.complex64)
+            out = np.zeros(M, np.complex64)
+            harness.harness_fft(z.ctypes.data, p, out.ctypes.data)
+            ref = np.fft.ifft(z.astype(np.complex128)) * M
+            assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+        N, F, k0 = 3000, 4000, 1
+        t = np.sort(rng.uniform(0, 60.0, N))
+        t -= t[0]
+        df = 1.0 / (5.0 * t[-1])
+        y = (3e-4 * rng.normal(size=N)).astype(np.float32)
+        C, S, _, _ = trig_sums(harness, t, y, None, df, k0, F)
+        ph = 2 * np.pi * np.outer((k0 + np.arange(F)) * df, t)
+        yd = y.astype(np.float64)
+        err = max(np.abs(C - np.cos(ph) @ yd).max(), np.abs(S - np.sin(ph) @ yd).max())
+        assert err <= 3e-7 * np.abs(yd).sum()
+    finally:
+        harness.harness_set_chain(0)
