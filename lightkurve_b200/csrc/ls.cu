@@ -878,6 +878,12 @@ int ls_tc_launch(const double* d_t, const ulonglong2* d_tab, int64_t N, int64_t 
 bool ls_tc_window_in_kernel(int64_t Npad, bool regular);
 bool ls_tc_supported(int B, int64_t N, int64_t F);
 bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df, double t_last);              // ls_nufft.cu
+int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, double grid_df, float4* d_rot,
+                     float2* d_rot2, int64_t F_low, cudaStream_t st);
+int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
+                 const float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
+                 cudaStream_t st, int ws_alt, bool prof);
 int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
                     const float* d_absmax, int B,
                     const double* d_freq, int64_t F, double grid_f0, double grid_df, float4* d_rot, float2* d_rot2,
@@ -904,7 +910,8 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   // they just overlap less.
   constexpr int PIPE_CHUNK = 256;                    // one light-curve tile of the tensor kernel
   const bool pipelined = mem == LKB_MEM_HOST && B > PIPE_CHUNK && !getenv("LKB_LS_NO_PIPELINE") &&
-                         (algo == LKB_LS_ALGO_TCGEN05 || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
+                         (algo == LKB_LS_ALGO_TCGEN05 || algo == LKB_LS_ALGO_NUFFT ||
+                          (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
   unsigned char* d_ystage = nullptr;
   if (pipelined) {
     LKB_TRY(ws_get_t<unsigned char>(WS_IN1, (size_t)B * N * ysz, &d_ystage));
@@ -1014,7 +1021,11 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   LKB_LAUNCH_CHECK();
   LKB_CUDA_CHECK(cudaEventRecord(ev_join, aux));
 
-  if (use_tc && pipelined) {
+  if ((use_tc || use_nufft) && pipelined) {
+    if (use_nufft) {       // tables and window terms once, on `st`, before the chunks fan out over the streams
+      LKB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+      LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_win, st));
+    }
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t* ev;
     int nev;
@@ -1048,6 +1059,11 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
         ls_prep_shared_kernel<double><<<nb, 256, 0, sc>>>((const double*)dy_in + (size_t)b_lo * N, N, Npad,
                                                           d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, d_ysumf + b_lo);
       LKB_LAUNCH_CHECK();
+      if (use_nufft)
+        LKB_TRY(ls_nufft_run(d_t, N, d_yc + (size_t)b_lo * Npad, Npad, d_ysumf + b_lo, d_absmax + b_lo, nb, d_freq, F,
+                             d_rot, d_rot2, F_win, normalization, ns, d_pow + (size_t)b_lo * F, sc, (sc != st) ? 1 : 0,
+                             true));
+      else
       LKB_TRY(ls_tc_launch(d_t, d_tab, N, Npad, d_yc + (size_t)b_lo * Npad, d_absmax + b_lo, nb, d_freq, F, d_rot, d_rot2,
                            false, lowf_max, grid_f0, grid_df, normalization, ns, d_pow + (size_t)b_lo * F, sc, ev_join,
                            (sc != st) ? 1 : 0));

@@ -228,24 +228,34 @@ bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df,
   return nufft::fine_grid_log2(2 * kmax) <= 24;
 }
 
-// d_t: times shifted to t[0] = 0 (ascending - checked here), d_yc: centred flux rows [B, ystride] fp32,
-// d_rot / d_rot2 rows [0, F_low) already filled by ls_window_kernel (fp64 path); the rest is filled here.
-int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
-                    const float* d_absmax, int B,
-                    const double* d_freq, int64_t F, double grid_f0, double grid_df, float4* d_rot, float2* d_rot2,
-                    int64_t F_low, int normalization, double norm_scale, float* d_pow, cudaStream_t st) {
+// ---- shared-grid path in two steps: ls_nufft_prepare (tables + window terms, once per call) and ls_nufft_run (spread
+// + FFT + finish for a block of light curves; callable per chunk of a pipelined host-mode call, `ws_alt` = 1 selects a
+// second set of fine-grid buffers so that two chunks can be in flight on two streams) ----
+struct NufftPlan {
+  int w, p;
+  float beta;
+  int64_t k0, M;
+  const Cad* cad;
+  const int32_t* fge;
+  const float2* dec;
+};
+static NufftPlan g_plan;
+
+// d_t: times shifted to t[0] = 0 (ascending - checked here).  d_rot / d_rot2 rows [0, F_low) are already filled by
+// ls_window_kernel (fp64 path); the rows >= F_low are filled here from one transform of unit strengths.
+int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, double grid_df, float4* d_rot,
+                     float2* d_rot2, int64_t F_low, cudaStream_t st) {
   const int w = kernel_width();
   const float beta = 2.30f * (float)w;
   const int64_t k0 = (int64_t)rint(grid_f0 / grid_df);
   const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
   const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
-  const int npairs = (B + 1) / 2;
   GlNodes gl;
   nufft::gauss_legendre(32, gl.x, gl.w);
 
   Cad *cad = nullptr, *cad2 = nullptr;
   int32_t *fge = nullptr, *fge2 = nullptr;
-  float2 *dec = nullptr, *dec2 = nullptr, *Za = nullptr, *Zb = nullptr, *Zw = nullptr;
+  float2 *dec = nullptr, *dec2 = nullptr, *Zw = nullptr;
   float* ones = nullptr;
   int* flag = nullptr;
   const int64_t L = nufft::table_len(M, w), L2 = nufft::table_len(M2, w);
@@ -258,8 +268,6 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
   LKB_TRY(ws_get_t<float2>(WS_IN3, 2 * (k0 + F), &dec2));
   LKB_TRY(ws_get_t<float>(WS_IN4, N, &ones));
   LKB_TRY(ws_get_t<int>(WS_IN5, 1, &flag));
-  LKB_TRY(ws_get_t<float2>(WS_H, (size_t)npairs * M, &Za));
-  LKB_TRY(ws_get_t<float2>(WS_I, (size_t)npairs * M, &Zb));
 
   // ---- tables of the two fine grids, sortedness check ----
   LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -294,6 +302,32 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
     nufft_rot_kernel<<<blocks_for(F - F_low, 128), 128, 0, st>>>(Zw_out, M2, dec2, k0, F, F_low, (double)N, d_rot, d_rot2);
     LKB_LAUNCH_CHECK();
   }
+  g_plan.w = w;
+  g_plan.p = p;
+  g_plan.beta = beta;
+  g_plan.k0 = k0;
+  g_plan.M = M;
+  g_plan.cad = cad;
+  g_plan.fge = fge;
+  g_plan.dec = dec;
+  return LKB_OK;
+}
+
+// d_yc: centred flux rows [B, ystride] fp32 of THIS block of light curves (with their d_ysumf / d_absmax / d_pow
+// rows); d_t / d_freq / d_rot / d_rot2 as in ls_nufft_prepare, which must have run on an earlier point of the stream
+// order.  prof: record the library's profiling events around the batch kernels.
+int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
+                 const float* d_absmax, int B, const double* d_freq, int64_t F, const float4* d_rot,
+                 const float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
+                 cudaStream_t st, int ws_alt, bool prof) {
+  const NufftPlan pl = g_plan;
+  const int w = pl.w, p = pl.p;
+  const float beta = pl.beta;
+  const int64_t k0 = pl.k0, M = pl.M;
+  const int npairs = (B + 1) / 2;
+  float2 *Za = nullptr, *Zb = nullptr;
+  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)npairs * M, &Za));
+  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, (size_t)npairs * M, &Zb));
 
   // ---- the batch: spread, FFT, finish - optionally in groups of light-curve pairs small enough for the fine grids
   // of a group (two buffers) to stay in the 126 MB L2 across the passes (LKB_NUFFT_GROUP_MB, default 0 = one group;
@@ -307,25 +341,25 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
       if (group > npairs) group = npairs;
     }
   }
-  prof_begin(st);
+  if (prof) prof_begin(st);
   for (int g0 = 0; g0 < npairs; g0 += group) {
     const int np_g = std::min(group, npairs - g0);
     const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
     float2* Za_g = Za + (size_t)g0 * M;
     float2* Zb_g = Zb + (size_t)g0 * M;
     nufft_spread_kernel<<<blocks_for((int64_t)np_g * M, 256), 256, 0, st>>>(
-        fge, cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
+        pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
     LKB_LAUNCH_CHECK();
     float2* Zout = nullptr;
     LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));
     if (F_low < F) {
       nufft_finish_kernel<<<blocks_for((F - F_low) * np_g, 256), 256, 0, st>>>(
-          Zout, p, dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
+          Zout, p, pl.dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
           (float)norm_scale, B_g, np_g, d_pow + (size_t)2 * g0 * F);
       LKB_LAUNCH_CHECK();
     }
   }
-  prof_end(st);
+  if (prof) prof_end(st);
   if (F_low > 0) {
     nufft_lowrows_kernel<<<blocks_for(F_low * B, 4), 128, 0, st>>>(d_t, N, d_yc, ystride, B, d_freq, F_low, F, d_rot,
                                                                    d_rot2, d_ysumf, normalization, (float)norm_scale,
@@ -335,6 +369,17 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
   return LKB_OK;
 }
 
+
+
+// one-shot form (the whole batch on one stream)
+int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t ystride, const float* d_ysumf,
+                    const float* d_absmax, int B, const double* d_freq, int64_t F, double grid_f0, double grid_df,
+                    float4* d_rot, float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
+                    cudaStream_t st) {
+  LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_low, st));
+  return ls_nufft_run(d_t, N, d_yc, ystride, d_ysumf, d_absmax, B, d_freq, F, d_rot, d_rot2, F_low, normalization,
+                      norm_scale, d_pow, st, 0, true);
+}
 
 // =====================================================================================================
 // Ragged batches (K1 shapes: every light curve has its own times; one shared regular frequency grid).

@@ -61,6 +61,15 @@ def _worker(out_q):
     a = np.asarray(engine.ls_power_shared(t3, Y3, f3, "amplitude", algo="nufft"), dtype=np.float64)
     s = np.asarray(engine.ls_power_shared(t3, Y3, f3, "amplitude", algo="simt"), dtype=np.float64)
     res["vs simt kernel"] = max(_excess(a[b], s[b]) for b in range(B))
+    # (5) host-mode call with more than 256 light curves: the chunk-pipelined loop (two streams, two buffer sets)
+    B5, N5, F5 = 300, 1500, 1000
+    t5 = np.sort(rng.uniform(0, 40.0, N5))
+    f5 = (1.0 / (5.0 * (t5[-1] - t5[0]))) * (1 + np.arange(F5))
+    Y5 = (1 + 2e-3 * np.sin(2 * np.pi * 1.3 * t5)[None, :] + 10 ** rng.uniform(-4, -3, (B5, 1)) *
+          rng.normal(size=(B5, N5))).astype(np.float32)
+    a5 = np.asarray(engine.ls_power_shared(t5, Y5, f5, "amplitude", algo="nufft"), dtype=np.float64)
+    s5 = np.asarray(engine.ls_power_shared(t5, Y5, f5, "amplitude", algo="simt"), dtype=np.float64)
+    res["pipelined vs simt kernel"] = max(_excess(a5[b], s5[b]) for b in range(B5))
     # (4) shapes the path must refuse
     try:
         engine.ls_power_shared(t, Y[:2].astype(np.float32), np.sort(rng.uniform(0.1, 5, 100)), "amplitude", algo="nufft")
@@ -171,3 +180,4 @@ def test_nufft_path_matches_oracle_and_simt_kernel():
     assert res["default grid, amplitude"] < 1.0
     assert res["oversample 1, psd"] < 1.0
     assert res["vs simt kernel"] < 1.0
+    assert res["pipelined vs simt kernel"] < 1.0
