@@ -74,6 +74,8 @@ class Unit:
         return all(abs(self.bases.get(k, 0) - other.bases.get(k, 0)) < 1e-12 for k in keys)
 
     def factor_to(self, other):
+        if other is self:
+            return 1.0
         if not self.is_equivalent(other):
             raise UnitConversionError("'%s' and '%s' are not convertible" % (self, other))
         return self.scale / other.scale
