@@ -42,6 +42,12 @@ extern int64_t g_launches;
     }                                                                               \
   } while (0)
 
+// Kernel launch.  tests/native/cuda_emu.h redefines this to run the grid on host threads, which is how the whole
+// translation unit ls_nufft.cu (kernels AND launch orchestration) is executed and checked on a machine without a GPU.
+#ifndef LKB_LAUNCH
+#define LKB_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>>
+#endif
+
 #define LKB_TRY(expr)                                                               \
   do {                                                                              \
     int _s = (expr);                                                                \

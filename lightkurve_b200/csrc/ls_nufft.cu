@@ -82,10 +82,10 @@ nufft_fft_pass_kernel(const float2* __restrict__ x, float2* __restrict__ y, int6
 
 template <bool CHAIN>
 void launch_pass(int R, unsigned g, const float2* src, float2* dst, int64_t Ns, int p, int64_t total, cudaStream_t st) {
-  if (R == 16) nufft_fft_pass_kernel<16, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-  else if (R == 8) nufft_fft_pass_kernel<8, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-  else if (R == 4) nufft_fft_pass_kernel<4, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
-  else nufft_fft_pass_kernel<2, CHAIN><<<g, 256, 0, st>>>(src, dst, Ns, p, total);
+  if (R == 16) LKB_LAUNCH(g, 256, st, nufft_fft_pass_kernel<16, CHAIN>)(src, dst, Ns, p, total);
+  else if (R == 8) LKB_LAUNCH(g, 256, st, nufft_fft_pass_kernel<8, CHAIN>)(src, dst, Ns, p, total);
+  else if (R == 4) LKB_LAUNCH(g, 256, st, nufft_fft_pass_kernel<4, CHAIN>)(src, dst, Ns, p, total);
+  else LKB_LAUNCH(g, 256, st, nufft_fft_pass_kernel<2, CHAIN>)(src, dst, Ns, p, total);
 }
 
 __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
@@ -271,9 +271,9 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
 
   // ---- tables of the two fine grids, sortedness check ----
   LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  nufft_cad_kernel<<<blocks_for(N, 256), 256, 0, st>>>(d_t, N, grid_df, M, w, cad, flag);
+  LKB_LAUNCH(blocks_for(N, 256), 256, st, nufft_cad_kernel)(d_t, N, grid_df, M, w, cad, flag);
   LKB_LAUNCH_CHECK();
-  nufft_cad_kernel<<<blocks_for(N, 256), 256, 0, st>>>(d_t, N, grid_df, M2, w, cad2, flag);
+  LKB_LAUNCH(blocks_for(N, 256), 256, st, nufft_cad_kernel)(d_t, N, grid_df, M2, w, cad2, flag);
   LKB_LAUNCH_CHECK();
   int h_flag = 0;
   LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -282,24 +282,24 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     set_error("lkb_ls_power_shared: the NUFFT path needs ascending times");
     return LKB_E_UNSUPPORTED;
   }
-  nufft_first_ge_kernel<<<blocks_for(L, 256), 256, 0, st>>>(cad, N, L, fge);
+  LKB_LAUNCH(blocks_for(L, 256), 256, st, nufft_first_ge_kernel)(cad, N, L, fge);
   LKB_LAUNCH_CHECK();
-  nufft_first_ge_kernel<<<blocks_for(L2, 256), 256, 0, st>>>(cad2, N, L2, fge2);
+  LKB_LAUNCH(blocks_for(L2, 256), 256, st, nufft_first_ge_kernel)(cad2, N, L2, fge2);
   LKB_LAUNCH_CHECK();
-  nufft_deconv_kernel<<<blocks_for(F, 128), 128, 0, st>>>(k0, F, M, w, (double)beta, gl, dec);
+  LKB_LAUNCH(blocks_for(F, 128), 128, st, nufft_deconv_kernel)(k0, F, M, w, (double)beta, gl, dec);
   LKB_LAUNCH_CHECK();
-  nufft_deconv_kernel<<<blocks_for(2 * (k0 + F), 128), 128, 0, st>>>(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
+  LKB_LAUNCH(blocks_for(2 * (k0 + F), 128), 128, st, nufft_deconv_kernel)(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
   LKB_LAUNCH_CHECK();
 
   // ---- window terms of the rows >= F_low: one transform of unit strengths on the 2x finer grid ----
   if (F_low < F) {
-    nufft_fill_kernel<<<blocks_for(N, 256), 256, 0, st>>>(ones, N, 1.0f);
+    LKB_LAUNCH(blocks_for(N, 256), 256, st, nufft_fill_kernel)(ones, N, 1.0f);
     LKB_LAUNCH_CHECK();
-    nufft_spread_kernel<<<blocks_for(M2, 256), 256, 0, st>>>(fge2, cad2, ones, 0, nullptr, 1, 1, w, beta, p2, Zw);
+    LKB_LAUNCH(blocks_for(M2, 256), 256, st, nufft_spread_kernel)(fge2, cad2, ones, 0, nullptr, 1, 1, w, beta, p2, Zw);
     LKB_LAUNCH_CHECK();
     float2* Zw_out = nullptr;
     LKB_TRY(fft_passes(Zw, Zw + M2, p2, 1, st, &Zw_out));
-    nufft_rot_kernel<<<blocks_for(F - F_low, 128), 128, 0, st>>>(Zw_out, M2, dec2, k0, F, F_low, (double)N, d_rot, d_rot2);
+    LKB_LAUNCH(blocks_for(F - F_low, 128), 128, st, nufft_rot_kernel)(Zw_out, M2, dec2, k0, F, F_low, (double)N, d_rot, d_rot2);
     LKB_LAUNCH_CHECK();
   }
   g_plan.w = w;
@@ -347,13 +347,13 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
     const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
     float2* Za_g = Za + (size_t)g0 * M;
     float2* Zb_g = Zb + (size_t)g0 * M;
-    nufft_spread_kernel<<<blocks_for((int64_t)np_g * M, 256), 256, 0, st>>>(
+    LKB_LAUNCH(blocks_for((int64_t)np_g * M, 256), 256, st, nufft_spread_kernel)(
         pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
     LKB_LAUNCH_CHECK();
     float2* Zout = nullptr;
     LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));
     if (F_low < F) {
-      nufft_finish_kernel<<<blocks_for((F - F_low) * np_g, 256), 256, 0, st>>>(
+      LKB_LAUNCH(blocks_for((F - F_low) * np_g, 256), 256, st, nufft_finish_kernel)(
           Zout, p, pl.dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
           (float)norm_scale, B_g, np_g, d_pow + (size_t)2 * g0 * F);
       LKB_LAUNCH_CHECK();
@@ -361,7 +361,7 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
   }
   if (prof) prof_end(st);
   if (F_low > 0) {
-    nufft_lowrows_kernel<<<blocks_for(F_low * B, 4), 128, 0, st>>>(d_t, N, d_yc, ystride, B, d_freq, F_low, F, d_rot,
+    LKB_LAUNCH(blocks_for(F_low * B, 4), 128, st, nufft_lowrows_kernel)(d_t, N, d_yc, ystride, B, d_freq, F_low, F, d_rot,
                                                                    d_rot2, d_ysumf, normalization, (float)norm_scale,
                                                                    d_pow);
     LKB_LAUNCH_CHECK();
@@ -579,7 +579,7 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
   {
     const unsigned gx = (unsigned)std::min<int64_t>(64, (nmax + 255) / 256);
-    nufft_cad_ragged_kernel<<<dim3(gx ? gx : 1, (unsigned)B), 256, 0, st>>>(d_t, d_off, d_po, d_span, df, M, M2, w, cad,
+    LKB_LAUNCH(dim3(gx ? gx : 1, (unsigned)B), 256, st, nufft_cad_ragged_kernel)(d_t, d_off, d_po, d_span, df, M, M2, w, cad,
                                                                           cad2, flag);
     LKB_LAUNCH_CHECK();
   }
@@ -587,33 +587,33 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   LKB_CUDA_CHECK(cudaStreamSynchronize(st));
   if (h_flag) { set_error("NUFFT (ragged): a light curve has unsorted times"); return LKB_E_UNSUPPORTED; }
-  nufft_absmax_ragged_kernel<<<B, 256, 0, st>>>(d_y, d_off, d_po, absmax);
+  LKB_LAUNCH(B, 256, st, nufft_absmax_ragged_kernel)(d_y, d_off, d_po, absmax);
   LKB_LAUNCH_CHECK();
-  nufft_deconv_kernel<<<blocks_for(F, 128), 128, 0, st>>>(k0, F, M, w, (double)beta, gl, dec);
+  LKB_LAUNCH(blocks_for(F, 128), 128, st, nufft_deconv_kernel)(k0, F, M, w, (double)beta, gl, dec);
   LKB_LAUNCH_CHECK();
-  nufft_deconv_kernel<<<blocks_for(2 * (k0 + F), 128), 128, 0, st>>>(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
+  LKB_LAUNCH(blocks_for(2 * (k0 + F), 128), 128, st, nufft_deconv_kernel)(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
   LKB_LAUNCH_CHECK();
 
   prof_begin(st);
   // window terms: unit strengths on the 2x finer grid
-  nufft_spread_ragged_kernel<<<blocks_for((int64_t)npairs * M2, 256), 256, 0, st>>>(cad2, nullptr, d_off, d_po, absmax, B,
+  LKB_LAUNCH(blocks_for((int64_t)npairs * M2, 256), 256, st, nufft_spread_ragged_kernel)(cad2, nullptr, d_off, d_po, absmax, B,
                                                                                   npairs, w, beta, p2, Zw);
   LKB_LAUNCH_CHECK();
   float2* Zw_out = nullptr;
   LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
   // flux
-  nufft_spread_ragged_kernel<<<blocks_for((int64_t)npairs * M, 256), 256, 0, st>>>(cad, d_y, d_off, d_po, absmax, B,
+  LKB_LAUNCH(blocks_for((int64_t)npairs * M, 256), 256, st, nufft_spread_ragged_kernel)(cad, d_y, d_off, d_po, absmax, B,
                                                                                  npairs, w, beta, p, Za);
   LKB_LAUNCH_CHECK();
   float2* Zout = nullptr;
   LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
-  nufft_finish_ragged_kernel<<<blocks_for(F * npairs, 256), 256, 0, st>>>(Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df,
+  LKB_LAUNCH(blocks_for(F * npairs, 256), 256, st, nufft_finish_ragged_kernel)(Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df,
                                                                         d_off, d_span, d_ysum, absmax, normalization,
                                                                         d_ns, B, npairs, d_pow);
   LKB_LAUNCH_CHECK();
   prof_end(st);
   if (F_low_max > 0) {
-    nufft_lowrows_ragged_kernel<<<blocks_for(F_low_max * B, 4), 128, 0, st>>>(d_t, d_y, d_off, d_po, d_span, d_ysum, f0,
+    LKB_LAUNCH(blocks_for(F_low_max * B, 4), 128, st, nufft_lowrows_ragged_kernel)(d_t, d_y, d_off, d_po, d_span, d_ysum, f0,
                                                                              df, F_low_max, F, normalization, d_ns, B,
                                                                              d_pow);
     LKB_LAUNCH_CHECK();

@@ -25,8 +25,10 @@
 #define LKB_HD __host__ __device__ __forceinline__
 #else
 #define LKB_HD inline
+#if !defined(LKB_CUDA_EMU)          // (tests/native/cuda_emu.h brings CUDA's own vector types)
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+#endif
 #endif
 
 namespace lkb {

@@ -1,8 +1,9 @@
 """GPU test of the opt-in NUFFT Lomb-Scargle path (algo="nufft", lightkurve_b200/csrc/ls_nufft.cu).
 
 Status: the arithmetic of every kernel is verified on the CPU (tests/test_nufft_core.py runs the same
-`__host__ __device__` functions through a g++ harness); the CUDA glue (launch shapes, workspace, epilogue, low
-rows) was written after round 1's GPU budget was spent and HAS NOT RUN ON HARDWARE YET - hence xfail(strict=False):
+`__host__ __device__` functions through a g++ harness) and the whole translation unit runs on a CUDA-on-CPU layer
+against the oracle (tests/test_nufft_emulated.py); it was written after round 1's GPU budget was spent and HAS NOT
+RUN ON HARDWARE YET - hence xfail(strict=False):
 a failure here is reported as xfailed, a pass as xpassed, and neither hides the verified tests.  The work runs
 in a child process so that a device fault cannot poison the CUDA context of the rest of the suite.  The file
 name sorts last on purpose."""

@@ -1,0 +1,166 @@
+"""The WHOLE translation unit lightkurve_b200/csrc/ls_nufft.cu - kernels, launch shapes, workspace plumbing, the
+prepare/run split, the ragged variant - executed on the CPU through a small CUDA-on-CPU layer
+(tests/native/cuda_emu.h: every thread of a block is a host thread, so __syncthreads and warp shuffles work) and
+compared with the fp64 oracle.  Together with tests/test_nufft_core.py this leaves only genuinely hardware-side
+behaviour (memory model, launch limits, speed) to the GPU run of tests/test_gpu_zz_nufft.py."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ls as ols
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+c_vp, c_i64, c_int, c_dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = str(tmp_path_factory.mktemp("emu") / "libnufft_emu.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC",
+                           "-o", out, os.path.join(HERE, "native", "nufft_emu_driver.cpp")])
+    lib = ctypes.CDLL(out)
+    shared = [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_int, c_dbl, c_vp]
+    lib.emu_nufft_shared.argtypes = shared
+    lib.emu_nufft_shared_chunked.argtypes = shared + [c_int]
+    lib.emu_nufft_ragged.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_int,
+                                     c_vp, c_vp]
+    lib.emu_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+def _excess(got, ref):
+    return np.abs(got - ref) / (1e-5 * ref.max() + 1e-4 * ref)
+
+
+def _window_rows(trel, freq, n_rows):
+    """rot / rot2 of the first `n_rows` frequencies the way ls_window_kernel's fp64 path computes them."""
+    N = len(trel)
+    rot = np.zeros((len(freq), 4), np.float32)
+    rot2 = np.zeros((len(freq), 2), np.float32)
+    for k in range(n_rows):
+        ph = 2 * np.pi * freq[k] * trel
+        s, c = np.sin(ph), np.cos(ph)
+        Sb, Cb, CCb, SCb = s.sum() / N, c.sum() / N, (c * c).sum() / N, (s * c).sum() / N
+        SSb = 1.0 - CCb
+        ta = 0.5 * np.arctan2(2 * SCb - 2 * Sb * Cb, (2 * CCb - 1) - (Cb * Cb - Sb * Sb))
+        ct, st = np.cos(ta), np.sin(ta)
+        ctau, stau = Cb * ct + Sb * st, Sb * ct - Cb * st
+        cc = CCb * ct * ct + 2 * SCb * ct * st + SSb * st * st - ctau * ctau
+        ss = SSb * ct * ct - 2 * SCb * ct * st + CCb * st * st - stau * stau
+        kf = 1.0 / (2.0 * N)
+        rot[k] = (ct, st, kf / cc, kf / ss)
+        rot2[k] = (ctau, stau)
+    return rot, rot2
+
+
+def _shared_inputs(seed, N, F, B, oversample=5.0, k0=1):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, 30.0, N))
+    trel = t - t[0]
+    df = 1.0 / (oversample * trel[-1])
+    f0 = k0 * df
+    freq = f0 + df * np.arange(F)
+    amp = 10 ** rng.uniform(-4, -2, B)
+    Y = np.stack([1 + a * np.sin(2 * np.pi * rng.uniform(0.2, 3) * t) + 10 ** rng.uniform(-4.3, -3) * rng.normal(size=N)
+                  for a in amp])
+    yc = (Y - Y.mean(axis=1, keepdims=True)).astype(np.float32)
+    Npad = ((N + 63) // 64) * 64
+    ycp = np.zeros((B, Npad), np.float32)
+    ycp[:, :N] = yc
+    ysum = ycp.astype(np.float64).sum(axis=1).astype(np.float32)
+    absmax = np.abs(ycp).max(axis=1).astype(np.float32)
+    return t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df
+
+
+@pytest.mark.parametrize("B,oversample,k0,normalization,chunk,env", [
+    (3, 5.0, 1, 2, 0, {}),                                   # amplitude, one-shot, odd batch
+    (4, 1.0, 1, 1, 0, {}),                                   # psd, df * baseline = 1 (wrap-around of the fine grid)
+    (5, 5.0, 3, 2, 2, {}),                                   # prepare + run in chunks of 2 (two buffer sets), k0 = 3
+    (6, 5.0, 1, 2, 0, {"LKB_NUFFT_GROUP_MB": "0.05", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "LKB_NUFFT_W": "10"}),
+])
+def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, oversample, k0, normalization, chunk, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    N, F = 500, 260
+    t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(B, N, F, B, oversample, k0)
+    low = freq * trel[-1] <= 2.0
+    F_low = int(low.sum()) + 1 if low.any() else 0            # rows handled by the direct low-row kernel
+    rot, rot2 = _window_rows(trel, freq, F_low)
+    power = np.zeros((B, F), np.float32)
+    scale = 2.0 / (N * oversample * df)
+    args = [trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B, freq.ctypes.data, F, f0,
+            df, rot.ctypes.data, rot2.ctypes.data, F_low, normalization, scale, power.ctypes.data]
+    rc = emu.emu_nufft_shared_chunked(*args, chunk) if chunk else emu.emu_nufft_shared(*args)
+    assert rc == 0, emu.emu_last_error()
+    for b in range(B):
+        p = ols.ls_slow_psd(t, Y[b], freq)
+        if normalization == 2:
+            ref = np.sqrt(p) * np.sqrt(4.0 / N)
+            ex = _excess(power[b].astype(np.float64), ref)
+        else:
+            ref = p * scale
+            ex = np.abs(power[b] - ref) / (2e-5 * ref.max() + 2e-4 * ref)
+        assert ex.max() < 0.5, (b, int(np.argmax(ex)), ex.max())
+
+
+def test_shared_grid_refuses_unsorted_times(emu):
+    N, F, B = 200, 100, 2
+    t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(9, N, F, B)
+    trel = trel.copy()
+    trel[[10, 11]] = trel[[11, 10]]
+    rot, rot2 = np.zeros((F, 4), np.float32), np.zeros((F, 2), np.float32)
+    power = np.zeros((B, F), np.float32)
+    rc = emu.emu_nufft_shared(trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B,
+                              freq.ctypes.data, F, f0, df, rot.ctypes.data, rot2.ctypes.data, 0, 2, 1.0, power.ctypes.data)
+    assert rc == -5 and b"ascending" in emu.emu_last_error()
+
+
+def test_ragged_translation_unit_on_the_emulator(emu):
+    """K1 layout: per-light-curve times, padded CSR, one shared regular grid; odd batch, mixed amplitudes, psd scale."""
+    rng = np.random.default_rng(21)
+    B, F = 5, 240
+    ns = [300, 77, 512, 150, 40]
+    off = np.zeros(B + 1, np.int64)
+    poff = np.zeros(B + 1, np.int64)
+    for b, n in enumerate(ns):
+        off[b + 1] = off[b] + n
+        poff[b + 1] = poff[b] + ((n + 3) // 4) * 4
+    ptotal = int(poff[-1])
+    tt, yy = np.zeros(ptotal + 4), np.zeros(ptotal + 4, np.float32)
+    times, fluxes, span, ysum = [], [], np.zeros(B), np.zeros(B)
+    for b, n in enumerate(ns):
+        t = np.sort(rng.uniform(0, 25.0 * rng.uniform(0.4, 1.0), n))
+        y = 1 + [1e-2, 0, 1e-3, 1e-4, 3e-3][b] * np.sin(2 * np.pi * 0.9 * t) + 10 ** rng.uniform(-4, -3) * rng.normal(size=n)
+        times.append(t)
+        fluxes.append(y)
+        tr = t - t[0]
+        yc = (y - y.mean()).astype(np.float32)
+        tt[poff[b]:poff[b] + n] = tr
+        yy[poff[b]:poff[b] + n] = yc
+        span[b] = tr.max()
+        ysum[b] = yc.astype(np.float64).sum()
+    df = 1.0 / (5.0 * 25.0)
+    f0 = df
+    freq = f0 + df * np.arange(F)
+    scale = rng.uniform(0.5, 2.0, B)
+    power = np.zeros((B, F), np.float32)
+    rc = emu.emu_nufft_ragged(tt.ctypes.data, yy.ctypes.data, off.ctypes.data, poff.ctypes.data, B, ptotal, max(ns),
+                              span.ctypes.data, ysum.ctypes.data, F, f0, df, 1, scale.ctypes.data, power.ctypes.data)
+    assert rc == 0, emu.emu_last_error()
+    for b in range(B):
+        ref = ols.ls_slow_psd(times[b], fluxes[b], freq) * scale[b]
+        ex = np.abs(power[b] - ref) / (2e-5 * ref.max() + 2e-4 * ref)
+        assert ex.max() < 0.5, (b, int(np.argmax(ex)), ex.max())
+    # an unsorted light curve makes the launch report "unsupported" (the caller then runs the direct kernel)
+    tt2 = tt.copy()
+    tt2[[poff[2] + 5, poff[2] + 6]] = tt2[[poff[2] + 6, poff[2] + 5]]
+    rc = emu.emu_nufft_ragged(tt2.ctypes.data, yy.ctypes.data, off.ctypes.data, poff.ctypes.data, B, ptotal, max(ns),
+                              span.ctypes.data, ysum.ctypes.data, F, f0, df, 1, scale.ctypes.data, power.ctypes.data)
+    assert rc == -5
