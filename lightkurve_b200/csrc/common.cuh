@@ -46,6 +46,11 @@ extern int64_t g_launches;
 // translation unit ls_nufft.cu (kernels AND launch orchestration) is executed and checked on a machine without a GPU.
 #ifndef LKB_LAUNCH
 #define LKB_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>>
+#define LKB_LAUNCH_SMEM(grid, block, smem_bytes, stream, ...) __VA_ARGS__<<<(grid), (block), (smem_bytes), (stream)>>>
+// the kernel's dynamic shared memory as `type* name`
+#define LKB_DYN_SMEM(type, name)                                   \
+  extern __shared__ __align__(16) unsigned char lkb_dyn_smem_raw[]; \
+  type* name = reinterpret_cast<type*>(lkb_dyn_smem_raw)
 #endif
 
 #define LKB_TRY(expr)                                                               \

@@ -88,6 +88,89 @@ void launch_pass(int R, unsigned g, const float2* src, float2* dst, int64_t Ns, 
   else LKB_LAUNCH(g, 256, st, nufft_fft_pass_kernel<2, CHAIN>)(src, dst, Ns, p, total);
 }
 
+// ---- four-step transform with shared-memory sub-transforms (LKB_NUFFT_FFT=smem): two in-place global sweeps ----
+// nufft_core.h "four-step transform".  One CTA = a tile of TC columns (step 1) or TR rows (step 2) of one transform
+// in two skewed shared-memory buffers; the radix passes are the same butterflies as the global version.
+constexpr int FS_THREADS = 256;
+// float2 elements per shared-memory buffer (before skew padding): 4096 -> 2 x 34 KB per CTA, 3 CTAs per SM;
+// LKB_NUFFT_TILE overrides (power of two, up to 8192)
+inline int64_t fs_tile() {
+  int64_t v = 4096;
+  if (const char* e = getenv("LKB_NUFFT_TILE")) v = atoll(e);
+  if (v < 256) v = 256;
+  if (v > 8192) v = 8192;
+  int64_t p2 = 256;
+  while (p2 * 2 <= v) p2 *= 2;
+  return p2;
+}
+
+template <bool CHAIN>
+__device__ __forceinline__ void smem_line_passes(float2*& src, float2*& dst, int lines, int64_t line_stride, int plog2) {
+  const int64_t n = (int64_t)1 << plog2;
+  int64_t Ns = 1;
+  for (int idx = 0;; ++idx) {
+    const int R = nufft::fft_pass_radix(plog2, idx);
+    if (R == 0) break;
+    const int64_t nb = n / R;
+    for (int64_t j = threadIdx.x; j < (int64_t)lines * nb; j += blockDim.x) {
+      const int64_t c = j / nb, i = j - c * nb;
+      const float2* x = src + c * line_stride;
+      float2* y = dst + c * line_stride;
+      if (R == 16) nufft::fft_pass_butterfly<16, CHAIN, true>(x, y, i, Ns, n);
+      else if (R == 8) nufft::fft_pass_butterfly<8, CHAIN, true>(x, y, i, Ns, n);
+      else if (R == 4) nufft::fft_pass_butterfly<4, CHAIN, true>(x, y, i, Ns, n);
+      else nufft::fft_pass_butterfly<2, CHAIN, true>(x, y, i, Ns, n);
+    }
+    __syncthreads();
+    Ns *= R;
+    float2* tmp = src; src = dst; dst = tmp;
+  }
+}
+
+// step 1: grid (Bc / TC, npairs)
+template <bool CHAIN>
+__global__ void __launch_bounds__(FS_THREADS)
+nufft_fft_cols_kernel(float2* __restrict__ Z, int p, int pa, int tc) {
+  LKB_DYN_SMEM(float2, smem);
+  const int64_t M = (int64_t)1 << p, A = (int64_t)1 << pa, Bc = M >> pa;
+  const int64_t stride = nufft::smem_line(A);
+  float2* Zp = Z + (int64_t)blockIdx.y * M;
+  const int64_t c0 = (int64_t)blockIdx.x * tc;
+  float2 *src = smem, *dst = smem + (int64_t)tc * stride;
+  for (int64_t idx = threadIdx.x; idx < (int64_t)tc * A; idx += blockDim.x) {
+    const int64_t c = idx % tc, n1 = idx / tc;
+    src[c * stride + nufft::skew(n1)] = Zp[n1 * Bc + c0 + c];
+  }
+  __syncthreads();
+  smem_line_passes<CHAIN>(src, dst, tc, stride, pa);
+  for (int64_t idx = threadIdx.x; idx < (int64_t)tc * A; idx += blockDim.x) {
+    const int64_t c = idx % tc, k1 = idx / tc, n2 = c0 + c;
+    Zp[k1 * Bc + n2] = nufft::cmul(src[c * stride + nufft::skew(k1)], nufft::unit_phase(n2 * k1, M));
+  }
+}
+
+// step 2: grid (A / TR, npairs)
+template <bool CHAIN>
+__global__ void __launch_bounds__(FS_THREADS)
+nufft_fft_rows_kernel(float2* __restrict__ Z, int p, int pa, int tr) {
+  LKB_DYN_SMEM(float2, smem);
+  const int64_t M = (int64_t)1 << p, Bc = M >> pa;
+  const int pb = p - pa;
+  const int64_t stride = nufft::smem_line(Bc);
+  float2* Zp = Z + (int64_t)blockIdx.y * M + (int64_t)blockIdx.x * tr * Bc;
+  float2 *src = smem, *dst = smem + (int64_t)tr * stride;
+  for (int64_t idx = threadIdx.x; idx < (int64_t)tr * Bc; idx += blockDim.x) {
+    const int64_t r = idx / Bc, n2 = idx - r * Bc;
+    src[r * stride + nufft::skew(n2)] = Zp[idx];
+  }
+  __syncthreads();
+  smem_line_passes<CHAIN>(src, dst, tr, stride, pb);
+  for (int64_t idx = threadIdx.x; idx < (int64_t)tr * Bc; idx += blockDim.x) {
+    const int64_t r = idx / Bc, k2 = idx - r * Bc;
+    Zp[idx] = src[r * stride + nufft::skew(k2)];
+  }
+}
+
 __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
                                     float2* __restrict__ dec) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,7 +243,7 @@ __global__ void __launch_bounds__(256)
 nufft_finish_kernel(const float2* __restrict__ Z, int log2M, const float2* __restrict__ dec, int64_t k0, int64_t F,
                     int64_t k_lo, const float4* __restrict__ rot, const float2* __restrict__ rot2,
                     const float* __restrict__ ysum, const float* __restrict__ absmax, float Nf, int normalization,
-                    float scale, int B, int npairs, float* __restrict__ power) {
+                    float scale, int B, int npairs, int pa, float* __restrict__ power) {
   const int64_t nk = F - k_lo;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= nk * npairs) return;
@@ -170,7 +253,7 @@ nufft_finish_kernel(const float2* __restrict__ Z, int log2M, const float2* __res
   const float inv0 = 1.0f / nufft::pow2_scale(absmax[b0]);
   const float inv1 = (b0 + 1 < B) ? 1.0f / nufft::pow2_scale(absmax[b0 + 1]) : 1.0f;
   float2 a, b;
-  nufft::unpack_pair(Z + pair * M, k0 + k, M, dec[k], inv0, inv1, &a, &b);
+  nufft::unpack_pair(Z + pair * M, k0 + k, M, dec[k], inv0, inv1, &a, &b, pa);
   const float4 r = rot[k];
   const float2 r2 = rot2[k];
   power[b0 * F + k] = ls_epilogue_shared(a.x, a.y, r, r2, ysum[b0], Nf, normalization, scale);
@@ -206,6 +289,34 @@ int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2*
   }
   *result = src;
   return LKB_OK;
+}
+
+bool fft_use_smem() {
+  const char* e = getenv("LKB_NUFFT_FFT");
+  return e && strcmp(e, "smem") == 0;
+}
+
+// in-place four-step transform of `npairs` length-2^p arrays; result in the [A][Bc] layout (pa returned)
+template <bool CHAIN>
+int fft_fourstep_t(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out) {
+  const int pa = nufft::fourstep_pa(p), pb = p - pa;
+  const int64_t A = (int64_t)1 << pa, Bc = (int64_t)1 << pb;
+  const int tc = (int)std::max<int64_t>(1, std::min<int64_t>(Bc, fs_tile() / A));
+  const int tr = (int)std::max<int64_t>(1, std::min<int64_t>(A, fs_tile() / Bc));
+  const size_t smem_c = 2 * (size_t)tc * nufft::smem_line(A) * sizeof(float2);
+  const size_t smem_r = 2 * (size_t)tr * nufft::smem_line(Bc) * sizeof(float2);
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_cols_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_rows_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+  LKB_LAUNCH_SMEM(dim3((unsigned)(Bc / tc), (unsigned)npairs), FS_THREADS, smem_c, st, nufft_fft_cols_kernel<CHAIN>)(Z, p, pa, tc);
+  LKB_LAUNCH_CHECK();
+  LKB_LAUNCH_SMEM(dim3((unsigned)(A / tr), (unsigned)npairs), FS_THREADS, smem_r, st, nufft_fft_rows_kernel<CHAIN>)(Z, p, pa, tr);
+  LKB_LAUNCH_CHECK();
+  *pa_out = pa;
+  return LKB_OK;
+}
+int fft_fourstep(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out) {
+  const char* ce = getenv("LKB_NUFFT_TWIDDLE_CHAIN");
+  return (ce && atoi(ce) != 0) ? fft_fourstep_t<true>(Z, p, npairs, st, pa_out) : fft_fourstep_t<false>(Z, p, npairs, st, pa_out);
 }
 
 int kernel_width() {
@@ -351,11 +462,17 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
         pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
     LKB_LAUNCH_CHECK();
     float2* Zout = nullptr;
-    LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));
+    int pa = 0;                                               // 0: natural order, else the four-step layout
+    if (fft_use_smem()) {
+      LKB_TRY(fft_fourstep(Za_g, p, np_g, st, &pa));
+      Zout = Za_g;
+    } else {
+      LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));
+    }
     if (F_low < F) {
       LKB_LAUNCH(blocks_for((F - F_low) * np_g, 256), 256, st, nufft_finish_kernel)(
           Zout, p, pl.dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
-          (float)norm_scale, B_g, np_g, d_pow + (size_t)2 * g0 * F);
+          (float)norm_scale, B_g, np_g, pa, d_pow + (size_t)2 * g0 * F);
       LKB_LAUNCH_CHECK();
     }
   }

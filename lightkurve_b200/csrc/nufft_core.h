@@ -198,13 +198,17 @@ LKB_HD void twiddle_powers(float2 w1, float2* tw) {
 // CHAIN = false: every twiddle exp(2 pi i r k / (Ns R)) by its own sincospif (most accurate);
 // CHAIN = true : one sincospif per butterfly + twiddle_powers (fewer instructions; measured on the CPU harness:
 //                rms transform error at M = 2^19: 1.7e-7 -> 4.3e-7 of the rms output).
-template <int R, bool CHAIN = false>
+// Shared-memory arrays are addressed through skew(): one float2 of padding per 16 keeps the stride-R stores of the
+// first passes off a single bank (without it thread i writes word 2 (R i + r): one bank for the whole warp).
+LKB_HD int64_t skew(int64_t a) { return a + (a >> 4); }
+
+template <int R, bool CHAIN = false, bool SKEW = false>
 LKB_HD void fft_pass_butterfly(const float2* x, float2* y, int64_t i, int64_t Ns, int64_t M) {
   const int64_t T = M / R;
   const int64_t k = i & (Ns - 1);
   float2 u[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) u[r] = x[i + (int64_t)r * T];
+  for (int r = 0; r < R; ++r) u[r] = x[SKEW ? skew(i + (int64_t)r * T) : i + (int64_t)r * T];
   if (Ns > 1) {
     if (CHAIN) {
       float2 tw[R];
@@ -219,8 +223,19 @@ LKB_HD void fft_pass_butterfly(const float2* x, float2* y, int64_t i, int64_t Ns
   SmallDft<R>::run(u);
   const int64_t j = (i - k) * R + k;
 #pragma unroll
-  for (int r = 0; r < R; ++r) y[j + (int64_t)r * Ns] = u[r];
+  for (int r = 0; r < R; ++r) y[SKEW ? skew(j + (int64_t)r * Ns) : j + (int64_t)r * Ns] = u[r];
 }
+
+// ---- four-step transform (two global sweeps instead of one per radix pass) ---------------------------------------
+// M = A * Bc, A = 2^pa.  Input index n = n1 Bc + n2, output index k = k1 + A k2:
+//   X[k1 + A k2] = sum_n2 W_Bc^(n2 k2) * W_M^(n2 k1) * [ sum_n1 x[n1 Bc + n2] W_A^(n1 k1) ]
+// step 1 ("columns"): length-A transforms over n1 for every n2, times W_M^(n2 k1), stored at [k1][n2];
+// step 2 ("rows"):    length-Bc transforms over n2 for every k1, stored at [k1][k2]  (in place).
+// Mode k therefore lives at address fourstep_index(k).
+LKB_HD int fourstep_pa(int p) { return (p + 1) / 2; }
+LKB_HD int64_t fourstep_index(int64_t k, int pa, int64_t Bc) { return (k & (((int64_t)1 << pa) - 1)) * Bc + (k >> pa); }
+// float2 elements of one skewed shared-memory line of n elements
+LKB_HD int64_t smem_line(int64_t n) { return skew(n) + 1; }
 
 // radix of pass `idx` (0-based) for a length-2^p transform: sixteens first, the remainder last.  0 = done.
 LKB_HD int fft_pass_radix(int p, int idx) {
@@ -272,10 +287,12 @@ LKB_HD void deconv_factor(int64_t kk, int64_t M, int w, double beta, const doubl
 
 // (C + i S) of the two light curves of a pair at mode kk from the packed transform Z (length M); inv0 / inv1 undo
 // the pow2_scale factors of the two light curves
+// pa > 0: Z is in the four-step layout (fourstep_index), pa = 0: natural order
 LKB_HD void unpack_pair(const float2* Z, int64_t kk, int64_t M, float2 dec, float inv0, float inv1, float2* a,
-                        float2* b) {
-  const float2 g1 = Z[kk];
-  const float2 g2 = Z[kk == 0 ? 0 : M - kk];
+                        float2* b, int pa = 0) {
+  const int64_t km = (kk == 0) ? 0 : M - kk;
+  const float2 g1 = Z[pa ? fourstep_index(kk, pa, M >> pa) : kk];
+  const float2 g2 = Z[pa ? fourstep_index(km, pa, M >> pa) : km];
   const float2 ra = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));      // (g1 + conj g2) / 2
   const float2 rb = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));      // (g1 - conj g2) / 2i
   const float2 da = cmul(ra, dec), db = cmul(rb, dec);

@@ -48,6 +48,7 @@ struct Block {
   std::vector<Barrier> warp;
   std::vector<unsigned long long> scratch;      // 32 slots per warp
   std::vector<unsigned char> alive;             // per thread
+  std::vector<unsigned long long> dyn;          // dynamic shared memory of the block
 };
 
 inline thread_local Block* t_block = nullptr;
@@ -57,12 +58,13 @@ inline std::mutex g_atomic_mu;
 template <typename F>
 struct Launcher {
   dim3 grid, block;
+  size_t smem_bytes;
   F body;
   template <typename... Args>
   void operator()(Args... args);
 };
 template <typename F>
-Launcher<F> make_launcher(dim3 grid, dim3 block, F body) { return Launcher<F>{grid, block, body}; }
+Launcher<F> make_launcher(dim3 grid, dim3 block, size_t smem, F body) { return Launcher<F>{grid, block, smem, body}; }
 
 }  // namespace lkb_emu
 
@@ -83,6 +85,7 @@ void lkb_emu::Launcher<F>::operator()(Args... args) {
         for (int w = 0; w < nwarps; ++w) blk.warp[w].reset(std::min(32, nthreads - 32 * w));
         blk.scratch.assign((size_t)nwarps * 32, 0ull);
         blk.alive.assign(nthreads, 1);
+        blk.dyn.assign(smem_bytes / 8 + 2, 0ull);
         std::vector<std::thread> th;
         th.reserve(nthreads);
         for (int t = 0; t < nthreads; ++t)
@@ -105,7 +108,10 @@ void lkb_emu::Launcher<F>::operator()(Args... args) {
 }
 
 #define LKB_LAUNCH(grid, block, stream, ...) \
-  lkb_emu::make_launcher(dim3(grid), dim3(block), [&](auto... emu_args) { __VA_ARGS__(emu_args...); })
+  lkb_emu::make_launcher(dim3(grid), dim3(block), 0, [&](auto... emu_args) { __VA_ARGS__(emu_args...); })
+#define LKB_LAUNCH_SMEM(grid, block, smem_bytes, stream, ...) \
+  lkb_emu::make_launcher(dim3(grid), dim3(block), (smem_bytes), [&](auto... emu_args) { __VA_ARGS__(emu_args...); })
+#define LKB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(lkb_emu::t_block->dyn.data())
 
 // ---- device built-ins ------------------------------------------------------------------------------------
 inline void __syncthreads() { lkb_emu::t_block->all.wait(); }
@@ -160,4 +166,9 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+}
+template <typename T>
+inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }   // kernel-pointer form
+extern "C" {
 }

@@ -84,11 +84,14 @@ def _shared_inputs(seed, N, F, B, oversample=5.0, k0=1):
     (4, 1.0, 1, 1, 0, {}),                                   # psd, df * baseline = 1 (wrap-around of the fine grid)
     (5, 5.0, 3, 2, 2, {}),                                   # prepare + run in chunks of 2 (two buffer sets), k0 = 3
     (6, 5.0, 1, 2, 0, {"LKB_NUFFT_GROUP_MB": "0.05", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "LKB_NUFFT_W": "10"}),
+    (3, 5.0, 1, 2, 0, {"LKB_NUFFT_FFT": "smem"}),            # four-step transform in shared memory, one tile
+    (3, 5.0, 2, 1, 2, {"LKB_NUFFT_FFT": "smem", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "F": "2100"}),   # several tiles
 ])
 def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, oversample, k0, normalization, chunk, env):
+    env = dict(env)
+    N, F = 500, int(env.pop("F", 260))
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    N, F = 500, 260
     t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(B, N, F, B, oversample, k0)
     low = freq * trel[-1] <= 2.0
     F_low = int(low.sum()) + 1 if low.any() else 0            # rows handled by the direct low-row kernel
