@@ -128,18 +128,42 @@ __device__ __forceinline__ void smem_line_passes(float2*& src, float2*& dst, int
 }
 
 // step 1: grid (Bc / TC, npairs)
-template <bool CHAIN>
+// what the column kernel needs to compute its input cells itself (FUSED: the spreading never touches global memory)
+struct SpreadArgs {
+  const int32_t* first_ge;
+  const Cad* cad;
+  const float* y;
+  int64_t ystride;
+  const float* absmax;
+  int B, w;
+  float beta;
+};
+
+template <bool CHAIN, bool FUSED>
 __global__ void __launch_bounds__(FS_THREADS)
-nufft_fft_cols_kernel(float2* __restrict__ Z, int p, int pa, int tc) {
+nufft_fft_cols_kernel(float2* __restrict__ Z, int p, int pa, int tc, SpreadArgs sp) {
   LKB_DYN_SMEM(float2, smem);
   const int64_t M = (int64_t)1 << p, A = (int64_t)1 << pa, Bc = M >> pa;
   const int64_t stride = nufft::smem_line(A);
-  float2* Zp = Z + (int64_t)blockIdx.y * M;
+  const int64_t pair = blockIdx.y;
+  float2* Zp = Z + pair * M;
   const int64_t c0 = (int64_t)blockIdx.x * tc;
   float2 *src = smem, *dst = smem + (int64_t)tc * stride;
-  for (int64_t idx = threadIdx.x; idx < (int64_t)tc * A; idx += blockDim.x) {
-    const int64_t c = idx % tc, n1 = idx / tc;
-    src[c * stride + nufft::skew(n1)] = Zp[n1 * Bc + c0 + c];
+  if (FUSED) {
+    const float* y0 = sp.y + (2 * pair) * sp.ystride;
+    const float* y1 = (2 * pair + 1 < sp.B) ? y0 + sp.ystride : nullptr;
+    const float s0 = nufft::pow2_scale(sp.absmax[2 * pair]);
+    const float s1 = y1 ? nufft::pow2_scale(sp.absmax[2 * pair + 1]) : 1.0f;
+    for (int64_t idx = threadIdx.x; idx < (int64_t)tc * A; idx += blockDim.x) {
+      const int64_t c = idx % tc, n1 = idx / tc;
+      src[c * stride + nufft::skew(n1)] =
+          nufft::spread_cell(n1 * Bc + c0 + c, sp.first_ge, sp.cad, y0, y1, s0, s1, sp.w, sp.beta, M);
+    }
+  } else {
+    for (int64_t idx = threadIdx.x; idx < (int64_t)tc * A; idx += blockDim.x) {
+      const int64_t c = idx % tc, n1 = idx / tc;
+      src[c * stride + nufft::skew(n1)] = Zp[n1 * Bc + c0 + c];
+    }
   }
   __syncthreads();
   smem_line_passes<CHAIN>(src, dst, tc, stride, pa);
@@ -291,32 +315,41 @@ int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2*
   return LKB_OK;
 }
 
-bool fft_use_smem() {
+// LKB_NUFFT_FFT: "smem" = four-step transform in shared memory, "fused" = the same with the spreading done inside
+// the column kernel's load phase (the fine grids are written once, already half transformed)
+int fft_mode() {
   const char* e = getenv("LKB_NUFFT_FFT");
-  return e && strcmp(e, "smem") == 0;
+  if (e && strcmp(e, "smem") == 0) return 1;
+  if (e && strcmp(e, "fused") == 0) return 2;
+  return 0;
 }
 
-// in-place four-step transform of `npairs` length-2^p arrays; result in the [A][Bc] layout (pa returned)
+// in-place four-step transform of `npairs` length-2^p arrays; result in the [A][Bc] layout (pa returned).
+// sp != NULL: the input is not read from Z but spread on the fly from the light curves described by *sp.
 template <bool CHAIN>
-int fft_fourstep_t(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out) {
+int fft_fourstep_t(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out, const SpreadArgs* sp) {
   const int pa = nufft::fourstep_pa(p), pb = p - pa;
   const int64_t A = (int64_t)1 << pa, Bc = (int64_t)1 << pb;
   const int tc = (int)std::max<int64_t>(1, std::min<int64_t>(Bc, fs_tile() / A));
   const int tr = (int)std::max<int64_t>(1, std::min<int64_t>(A, fs_tile() / Bc));
   const size_t smem_c = 2 * (size_t)tc * nufft::smem_line(A) * sizeof(float2);
   const size_t smem_r = 2 * (size_t)tr * nufft::smem_line(Bc) * sizeof(float2);
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_cols_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_cols_kernel<CHAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_cols_kernel<CHAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft_fft_rows_kernel<CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-  LKB_LAUNCH_SMEM(dim3((unsigned)(Bc / tc), (unsigned)npairs), FS_THREADS, smem_c, st, nufft_fft_cols_kernel<CHAIN>)(Z, p, pa, tc);
+  const dim3 gc((unsigned)(Bc / tc), (unsigned)npairs);
+  if (sp) LKB_LAUNCH_SMEM(gc, FS_THREADS, smem_c, st, nufft_fft_cols_kernel<CHAIN, true>)(Z, p, pa, tc, *sp);
+  else LKB_LAUNCH_SMEM(gc, FS_THREADS, smem_c, st, nufft_fft_cols_kernel<CHAIN, false>)(Z, p, pa, tc, SpreadArgs());
   LKB_LAUNCH_CHECK();
   LKB_LAUNCH_SMEM(dim3((unsigned)(A / tr), (unsigned)npairs), FS_THREADS, smem_r, st, nufft_fft_rows_kernel<CHAIN>)(Z, p, pa, tr);
   LKB_LAUNCH_CHECK();
   *pa_out = pa;
   return LKB_OK;
 }
-int fft_fourstep(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out) {
+int fft_fourstep(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out, const SpreadArgs* sp) {
   const char* ce = getenv("LKB_NUFFT_TWIDDLE_CHAIN");
-  return (ce && atoi(ce) != 0) ? fft_fourstep_t<true>(Z, p, npairs, st, pa_out) : fft_fourstep_t<false>(Z, p, npairs, st, pa_out);
+  return (ce && atoi(ce) != 0) ? fft_fourstep_t<true>(Z, p, npairs, st, pa_out, sp)
+                               : fft_fourstep_t<false>(Z, p, npairs, st, pa_out, sp);
 }
 
 int kernel_width() {
@@ -458,13 +491,28 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
     const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
     float2* Za_g = Za + (size_t)g0 * M;
     float2* Zb_g = Zb + (size_t)g0 * M;
-    LKB_LAUNCH(blocks_for((int64_t)np_g * M, 256), 256, st, nufft_spread_kernel)(
-        pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
-    LKB_LAUNCH_CHECK();
+    const int mode = fft_mode();
+    if (mode != 2) {
+      LKB_LAUNCH(blocks_for((int64_t)np_g * M, 256), 256, st, nufft_spread_kernel)(
+          pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
+      LKB_LAUNCH_CHECK();
+    }
     float2* Zout = nullptr;
     int pa = 0;                                               // 0: natural order, else the four-step layout
-    if (fft_use_smem()) {
-      LKB_TRY(fft_fourstep(Za_g, p, np_g, st, &pa));
+    if (mode == 2) {
+      SpreadArgs sp;
+      sp.first_ge = pl.fge;
+      sp.cad = pl.cad;
+      sp.y = d_yc + (size_t)2 * g0 * ystride;
+      sp.ystride = ystride;
+      sp.absmax = d_absmax + 2 * g0;
+      sp.B = B_g;
+      sp.w = w;
+      sp.beta = beta;
+      LKB_TRY(fft_fourstep(Za_g, p, np_g, st, &pa, &sp));
+      Zout = Za_g;
+    } else if (mode == 1) {
+      LKB_TRY(fft_fourstep(Za_g, p, np_g, st, &pa, nullptr));
       Zout = Za_g;
     } else {
       LKB_TRY(fft_passes(Za_g, Zb_g, p, np_g, st, &Zout));

@@ -16,7 +16,8 @@ timeout 600 python -m pytest tests/test_gpu_zz_nufft.py -m gpu -q -rxX -s 2>&1 |
 echo "=== 3. headline bench: tensor path (today's default) vs NUFFT path and its switches ==="
 for cfg in "auto" "nufft" "nufft LKB_NUFFT_TWIDDLE_CHAIN=1" "nufft LKB_NUFFT_TWIDDLE_CHAIN=1 LKB_NUFFT_GROUP_MB=96" \
            "nufft LKB_NUFFT_TWIDDLE_CHAIN=1 LKB_NUFFT_W=6" "nufft LKB_NUFFT_FFT=smem" \
-           "nufft LKB_NUFFT_FFT=smem LKB_NUFFT_TWIDDLE_CHAIN=1" "nufft LKB_NUFFT_FFT=smem LKB_NUFFT_TWIDDLE_CHAIN=1 LKB_NUFFT_TILE=8192"; do
+           "nufft LKB_NUFFT_FFT=smem LKB_NUFFT_TWIDDLE_CHAIN=1" "nufft LKB_NUFFT_FFT=smem LKB_NUFFT_TWIDDLE_CHAIN=1 LKB_NUFFT_TILE=8192" \
+           "nufft LKB_NUFFT_FFT=fused LKB_NUFFT_TWIDDLE_CHAIN=1"; do
   set -- $cfg
   algo=$1; shift
   tag=$(echo "$cfg" | tr ' =' '__')
