@@ -21,6 +21,9 @@ One JSON line on stdout (rank 0).  A "step" = one pass of lkb_ls_power_shared ov
   secondary.bls: the other half of BASELINE.json's metric ("BLS periods/s"): configs[2] (256 TESS light
             curves x 20 000 cadences x 50 000 periods x 10 durations per GPU) with its own value / e2e /
             roofline / cpu_baseline objects (``secondary_bls``); ``--no-secondary`` skips it.
+  secondary.ls_nufft (N = 1 only): the opt-in NUFFT Lomb-Scargle path (algo="nufft") on the same
+            workload - ms/step and bin*cadence/s of its variants plus a parity check against the default path, measured
+            in a CHILD PROCESS after the headline timing (a fault there cannot touch the reported numbers).
 """
 import argparse
 import json
@@ -326,6 +329,73 @@ def _bls_cpu_leg(t, fluxes, errs, period, duration, res, P, n_lc=4, budget_s=15.
         return {"cpu_baseline": {"error": repr(e)}}
 
 
+def nufft_leg_child(args):
+    """Child process of the `secondary.ls_nufft` leg: the opt-in NUFFT Lomb-Scargle path on the same
+    configs[1] workload, device-resident, CUDA-event timed, with a parity check against the default path on a sample
+    of light curves.  Runs in its own process so that a fault of the not-yet-hardware-validated path cannot touch
+    the headline measurement.  Prints one JSON line."""
+    import torch
+    from lightkurve_b200 import engine
+    torch.cuda.set_device(0)
+    engine.init(0)
+    w = WORKLOADS[args.workload]
+    B, N, F = w["B"], w["N"], w["F"]
+    t, Y, freq = make_workload(args.workload, args.seed)
+    dev = torch.device("cuda", 0)
+    d_t, d_f, d_Y = torch.tensor(t, device=dev), torch.tensor(freq, device=dev), torch.tensor(Y, device=dev)
+    d_ref = torch.empty((B, F), dtype=torch.float32, device=dev)
+    engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo="auto", out=d_ref)
+    torch.cuda.synchronize()
+    ref = d_ref[:: max(1, B // 16)].cpu().numpy().astype(np.float64)
+    out = {"workload": "%s: %s" % (args.workload, w["desc"]), "modes": {}}
+    modes = {"global passes": {}, "global passes, twiddle chain": {"LKB_NUFFT_TWIDDLE_CHAIN": "1"},
+             "four-step smem, chain": {"LKB_NUFFT_TWIDDLE_CHAIN": "1", "LKB_NUFFT_FFT": "smem"},
+             "four-step fused spread, chain": {"LKB_NUFFT_TWIDDLE_CHAIN": "1", "LKB_NUFFT_FFT": "fused"}}
+    d_P = torch.empty((B, F), dtype=torch.float32, device=dev)
+    for name, env in modes.items():
+        for k in ("LKB_NUFFT_TWIDDLE_CHAIN", "LKB_NUFFT_FFT"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            for _ in range(2):
+                engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo="nufft", out=d_P)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(args.steps):
+                engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo="nufft", out=d_P)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / args.steps
+            got = d_P[:: max(1, B // 16)].cpu().numpy().astype(np.float64)
+            excess = float(np.max(np.abs(got - ref) / (1e-5 * ref.max(axis=1, keepdims=True) + 1e-4 * ref)))
+            out["modes"][name] = {"ms_per_step": ms, "value": float(F) * N * B / (ms * 1e-3), "unit": UNIT,
+                                  "worst_tolerance_excess_vs_default_path": excess, "parity": bool(excess < 1.5)}
+        except Exception as e:
+            out["modes"][name] = {"error": repr(e)}
+    print(json.dumps(out), flush=True)
+
+
+def nufft_leg(args):
+    """Parent side: run `nufft_leg_child` in a subprocess with a timeout; never raises."""
+    import subprocess
+    try:
+        cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--nufft-leg", "--steps", str(max(2, args.steps)),
+                             "--workload", args.workload, "--seed", str(args.seed)], capture_output=True, text=True,
+                            timeout=300, env={k: v for k, v in os.environ.items()
+                                              if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")})
+        lines = [ln for ln in cp.stdout.strip().splitlines() if ln.startswith("{")]
+        if cp.returncode != 0 or not lines:
+            return {"error": "child exit code %d: %s" % (cp.returncode, (cp.stderr or "")[-400:])}
+        res = json.loads(lines[-1])
+        res["note"] = ("opt-in path (algo='nufft'), not the reported metric: measured in a child process after the "
+                       "headline timing; parity = against the default path on 16 light curves (two fp32 paths, "
+                       "so up to 1.5x the single-path tolerance)")
+        return res
+    except Exception as e:                                        # timeout, JSON error, ...
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +408,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the BLS (configs[2]) leg")
+    ap.add_argument("--nufft-leg", action="store_true", help=argparse.SUPPRESS)      # internal: child of secondary.ls_nufft
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -345,6 +416,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.nufft_leg:
+        nufft_leg_child(args)
         return
     if args.warmup < 3:
         args.warmup = 3
@@ -433,6 +507,8 @@ def main():
                                               cpu_baseline=not args.no_cpu_baseline)}
         except Exception as e:                                    # the headline line must survive this leg
             secondary = {"bls": {"error": repr(e)}}
+        if world == 1 and rank == 0 and args.algo != "nufft":
+            secondary["ls_nufft"] = nufft_leg(args)
 
     units_per_step = float(F) * N * B * world
     value = units_per_step * args.steps / (ms_res * 1e-3)
