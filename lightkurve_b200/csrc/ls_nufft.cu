@@ -632,7 +632,8 @@ nufft_finish_ragged_kernel(const float2* __restrict__ Z, int log2M, const float2
                            const float2* __restrict__ dec, const float2* __restrict__ dec2, int64_t k0, int64_t F,
                            double f0, double df, const int64_t* __restrict__ off, const double* __restrict__ span,
                            const double* __restrict__ ysum, const float* __restrict__ absmax, int normalization,
-                           const double* __restrict__ norm_scale, int B, int npairs, float* __restrict__ power) {
+                           const double* __restrict__ norm_scale, int B, int npairs, int pa, int pa2,
+                           float* __restrict__ power) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= F * npairs) return;
   const int64_t pair = gid / F, k = gid - pair * F;
@@ -642,9 +643,9 @@ nufft_finish_ragged_kernel(const float2* __restrict__ Z, int log2M, const float2
   const float inv0 = 1.0f / nufft::pow2_scale(absmax[b0]);
   const float inv1 = has1 ? 1.0f / nufft::pow2_scale(absmax[b1]) : 1.0f;
   float2 ha, hb, w1a, w1b, w2a, w2b;
-  nufft::unpack_pair(Z + pair * M, kk, M, dec[k], inv0, inv1, &ha, &hb);
-  nufft::unpack_pair(Zw + pair * M2, kk, M2, dec2[kk], 1.0f, 1.0f, &w1a, &w1b);
-  nufft::unpack_pair(Zw + pair * M2, 2 * kk, M2, dec2[2 * kk], 1.0f, 1.0f, &w2a, &w2b);
+  nufft::unpack_pair(Z + pair * M, kk, M, dec[k], inv0, inv1, &ha, &hb, pa);
+  nufft::unpack_pair(Zw + pair * M2, kk, M2, dec2[kk], 1.0f, 1.0f, &w1a, &w1b, pa2);
+  nufft::unpack_pair(Zw + pair * M2, 2 * kk, M2, dec2[2 * kk], 1.0f, 1.0f, &w2a, &w2b, pa2);
   const double fr = f0 + (double)k * df;
   if (fr * span[b0] > LS_LOWF_CYCLES) {
     const double Nd = (double)(off[b0 + 1] - off[b0]);
@@ -765,16 +766,27 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
                                                                                   npairs, w, beta, p2, Zw);
   LKB_LAUNCH_CHECK();
   float2* Zw_out = nullptr;
-  LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
+  int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
+  if (fft_mode() != 0) {
+    LKB_TRY(fft_fourstep(Zw, p2, npairs, st, &pa2, nullptr));
+    Zw_out = Zw;
+  } else {
+    LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
+  }
   // flux
   LKB_LAUNCH(blocks_for((int64_t)npairs * M, 256), 256, st, nufft_spread_ragged_kernel)(cad, d_y, d_off, d_po, absmax, B,
                                                                                  npairs, w, beta, p, Za);
   LKB_LAUNCH_CHECK();
   float2* Zout = nullptr;
-  LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+  if (fft_mode() != 0) {
+    LKB_TRY(fft_fourstep(Za, p, npairs, st, &pa, nullptr));
+    Zout = Za;
+  } else {
+    LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+  }
   LKB_LAUNCH(blocks_for(F * npairs, 256), 256, st, nufft_finish_ragged_kernel)(Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df,
                                                                         d_off, d_span, d_ysum, absmax, normalization,
-                                                                        d_ns, B, npairs, d_pow);
+                                                                        d_ns, B, npairs, pa, pa2, d_pow);
   LKB_LAUNCH_CHECK();
   prof_end(st);
   if (F_low_max > 0) {

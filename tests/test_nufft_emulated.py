@@ -126,8 +126,12 @@ def test_shared_grid_refuses_unsorted_times(emu):
     assert rc == -5 and b"ascending" in emu.emu_last_error()
 
 
-def test_ragged_translation_unit_on_the_emulator(emu):
-    """K1 layout: per-light-curve times, padded CSR, one shared regular grid; odd batch, mixed amplitudes, psd scale."""
+@pytest.mark.parametrize("fft", ["", "smem"])
+def test_ragged_translation_unit_on_the_emulator(emu, monkeypatch, fft):
+    """K1 layout: per-light-curve times, padded CSR, one shared regular grid; odd batch, mixed amplitudes, psd scale;
+    global radix passes and the four-step shared-memory transform."""
+    if fft:
+        monkeypatch.setenv("LKB_NUFFT_FFT", fft)
     rng = np.random.default_rng(21)
     B, F = 5, 240
     ns = [300, 77, 512, 150, 40]
