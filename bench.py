@@ -382,7 +382,7 @@ def nufft_leg(args):
     try:
         cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--nufft-leg", "--steps", str(max(2, args.steps)),
                              "--workload", args.workload, "--seed", str(args.seed)], capture_output=True, text=True,
-                            timeout=300, env={k: v for k, v in os.environ.items()
+                            timeout=180, env={k: v for k, v in os.environ.items()
                                               if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")})
         lines = [ln for ln in cp.stdout.strip().splitlines() if ln.startswith("{")]
         if cp.returncode != 0 or not lines:
