@@ -23,10 +23,10 @@ void set_error(const char* fmt, ...) {
 static std::map<int, std::pair<void*, size_t>> g_ws;
 int ws_get(int slot, size_t bytes, void** out) {
   auto& e = g_ws[slot];
-  if (e.second < bytes + 64) {
+  if (e.second != bytes) {             // exact size, no slack: an out-of-bounds access is visible to ASan
     free(e.first);
-    e.first = calloc(bytes + 64, 1);
-    e.second = bytes + 64;
+    e.first = calloc(bytes ? bytes : 1, 1);
+    e.second = bytes;
   }
   *out = e.first;
   return LKB_OK;
