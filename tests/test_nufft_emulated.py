@@ -172,3 +172,28 @@ def test_ragged_translation_unit_on_the_emulator(emu, monkeypatch, fft):
     rc = emu.emu_nufft_ragged(tt2.ctypes.data, yy.ctypes.data, off.ctypes.data, poff.ctypes.data, B, ptotal, max(ns),
                               span.ctypes.data, ysum.ctypes.data, F, f0, df, 1, scale.ctypes.data, power.ctypes.data)
     assert rc == -5
+
+
+@pytest.mark.parametrize("B,N,F,k0", [(1, 40, 16, 0), (2, 9, 5, 1), (1, 300, 700, 5)])
+def test_small_and_odd_shapes_on_the_emulator(emu, monkeypatch, B, N, F, k0):
+    """A single light curve (half-empty pair), fewer cadences than the kernel is wide, k0 = 0 (the f = 0 row is a
+    low row: the reference itself returns NaN there), more bins than cadences; both transform variants."""
+    for mode in ("", "fused"):
+        if mode:
+            monkeypatch.setenv("LKB_NUFFT_FFT", mode)
+        t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(100 + N, N, F, B, 5.0, k0)
+        low = freq * trel[-1] <= 2.0
+        F_low = min(F, int(low.sum()) + 1)
+        with np.errstate(all="ignore"):
+            rot, rot2 = _window_rows(trel, freq, F_low)
+        power = np.zeros((B, F), np.float32)
+        rc = emu.emu_nufft_shared(trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B,
+                                  freq.ctypes.data, F, f0, df, rot.ctypes.data, rot2.ctypes.data, F_low, 2, 1.0,
+                                  power.ctypes.data)
+        assert rc == 0, emu.emu_last_error()
+        for b in range(B):
+            with np.errstate(all="ignore"):
+                ref = np.sqrt(ols.ls_slow_psd(t, Y[b], freq)) * np.sqrt(4.0 / N)
+            ok = np.isfinite(ref) & (freq > 0)
+            ex = _excess(power[b].astype(np.float64)[ok], ref[ok])
+            assert ex.max() < 0.5, (mode, b, ex.max())
