@@ -85,8 +85,8 @@ def _shared_inputs(seed, N, F, B, oversample=5.0, k0=1):
     (5, 5.0, 3, 2, 2, {}),                                   # prepare + run in chunks of 2 (two buffer sets), k0 = 3
     (6, 5.0, 1, 2, 0, {"LKB_NUFFT_GROUP_MB": "0.05", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "LKB_NUFFT_W": "10"}),
     (3, 5.0, 1, 2, 0, {"LKB_NUFFT_FFT": "smem"}),            # four-step transform in shared memory, one tile
-    (3, 5.0, 2, 1, 2, {"LKB_NUFFT_FFT": "smem", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "F": "2100"}),   # several tiles
-    (5, 1.0, 1, 2, 0, {"LKB_NUFFT_FFT": "fused", "F": "2100", "LKB_NUFFT_TILE": "2048"}),        # spreading fused in
+    (3, 5.0, 2, 1, 2, {"LKB_NUFFT_FFT": "smem", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "F": "1100", "LKB_NUFFT_TILE": "1024"}),  # 8 tiles
+    (5, 1.0, 1, 2, 0, {"LKB_NUFFT_FFT": "fused", "F": "1100", "LKB_NUFFT_TILE": "1024"}),        # spreading fused in
 ])
 def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, oversample, k0, normalization, chunk, env):
     env = dict(env)
