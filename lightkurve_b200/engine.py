@@ -164,7 +164,10 @@ def ls_power_chi2(times, fluxes, frequency, nterms=1, normalization="amplitude",
 
 def ls_power_shared(t, Y, frequency, normalization="amplitude", norm_scale=None, algo="auto", out=None):
     """K2.  One cadence grid `t` [N] shared by the batch `Y` [B, N]; `frequency` [F].
-    numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode)."""
+    numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode).
+    `algo`: "auto" (tcgen05 tensor path when the shape allows, else the CUDA-core contraction), "simt", "tcgen05",
+    or "nufft" - the opt-in spread + FFT path for regular frequency grids (raises for grids / times it
+    does not support)."""
     lib = L.load()
     if _is_torch(Y):
         import torch
