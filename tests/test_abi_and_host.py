@@ -283,3 +283,13 @@ def test_nccl_entry_points_without_a_communicator():
         a, b = engine.nccl_unique_id(), engine.nccl_unique_id()
         assert len(a) == len(b) == 128 and a != b
     engine.nccl_shutdown()                                          # no communicator: a no-op
+
+
+def test_diagnostic_workspace_readback_needs_an_initialised_engine():
+    """lkb_ws_read (diagnostic entry used by tools/nufft_gpu_check.py) refuses to run without a bound device and
+    validates its arguments; the slot names of the Python wrapper follow enum Slot of csrc/common.cuh."""
+    from lightkurve_b200 import engine
+    assert engine.WS_SLOTS["A"] == 0 and engine.WS_SLOTS["P"] == 15 and engine.WS_SLOTS["IN0"] == 16
+    assert engine.WS_SLOTS["OUT0"] == 24 and len(engine.WS_SLOTS) == 32
+    with pytest.raises(ValueError, match="not initialised"):
+        engine.ws_read("A", 4, np.float32)
