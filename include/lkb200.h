@@ -34,6 +34,7 @@ extern "C" {
 #define LKB_E_SINGULAR    -4   /* normal equations singular (numpy LinAlgError analogue) */
 #define LKB_E_UNSUPPORTED -5   /* shape outside what the kernels support / optional component absent */
 #define LKB_E_NCCL        -6   /* NCCL call failed */
+#define LKB_E_VERIFY      -7   /* a kernel's built-in self-check (LKB_NUFFT_VERIFY=1) found a wrong result */
 
 #define LKB_MEM_HOST   0
 #define LKB_MEM_DEVICE 1

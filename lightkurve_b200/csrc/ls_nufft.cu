@@ -284,6 +284,48 @@ nufft_finish_kernel(const float2* __restrict__ Z, int log2M, const float2* __res
   if (b0 + 1 < B) power[(b0 + 1) * F + k] = ls_epilogue_shared(b.x, b.y, r, r2, ysum[b0 + 1], Nf, normalization, scale);
 }
 
+// Self-check (LKB_NUFFT_VERIFY=1): 64 warps each pick one (light curve, frequency row >= k_lo) by a hash, recompute
+// the two trig sums directly in fp64 and compare them with what the transform delivered; the largest deviation in
+// units of 1e-7 * sum |y| goes to *worst (a correct transform stays below ~5, a defect gives >> 100).
+__global__ void __launch_bounds__(128)
+nufft_verify_kernel(const float2* __restrict__ Z, int log2M, int pa, const float2* __restrict__ dec, int64_t k0, int64_t F,
+                    int64_t k_lo, const double* __restrict__ t, int64_t N, const float* __restrict__ yc, int64_t ystride,
+                    const float* __restrict__ absmax, const double* __restrict__ freq, int B, float fault,
+                    unsigned* __restrict__ worst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned job = blockIdx.x * (blockDim.x >> 5) + warp;
+  unsigned h = job * 2654435761u + 12345u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const int64_t b = h % (unsigned)B;
+  const int64_t k = k_lo + (int64_t)((h >> 8) % (unsigned)(F - k_lo));
+  const float* y = yc + b * ystride;
+  const double fr = freq[k];
+  double c = 0.0, s = 0.0, l1 = 0.0;
+  for (int64_t i = lane; i < N; i += 32) {
+    double sn, cs;
+    ls_sincos_cycles_f64(fr * t[i], sn, cs);
+    const double v = (double)y[i];
+    c += v * cs;
+    s += v * sn;
+    l1 += fabs(v);
+  }
+  c = warp_sum(c);
+  s = warp_sum(s);
+  l1 = warp_sum(l1);
+  if (lane == 0) {
+    const int64_t M = (int64_t)1 << log2M, pair = b >> 1;
+    const int64_t b0 = 2 * pair;
+    const float inv0 = 1.0f / nufft::pow2_scale(absmax[b0]);
+    const float inv1 = (b0 + 1 < B) ? 1.0f / nufft::pow2_scale(absmax[b0 + 1]) : 1.0f;
+    float2 ha, hb;
+    nufft::unpack_pair(Z + pair * M, k0 + k, M, dec[k], inv0, inv1, &ha, &hb, pa);
+    const float2 got = (b & 1) ? hb : ha;
+    const double dev = fmax(fabs((double)got.x * (double)fault - c), fabs((double)got.y * (double)fault - s));
+    const double units = dev / (1e-7 * fmax(l1, 1e-300));
+    atomicMax(worst, (unsigned)fmin(units, 4.0e9));
+  }
+}
+
 __global__ void nufft_fill_kernel(float* __restrict__ p, int64_t n, float v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -472,6 +514,10 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
   float2 *Za = nullptr, *Zb = nullptr;
   LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)npairs * M, &Za));
   LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, (size_t)npairs * M, &Zb));
+  const char* ve = getenv("LKB_NUFFT_VERIFY");
+  const bool verify = ve && atoi(ve) != 0 && F_low < F;
+  unsigned* d_worst = nullptr;
+  if (verify) LKB_TRY(ws_get_t<unsigned>(ws_alt ? WS_OUT7 : WS_OUT6, 1, &d_worst));
 
   // ---- the batch: spread, FFT, finish - optionally in groups of light-curve pairs small enough for the fine grids
   // of a group (two buffers) to stay in the 126 MB L2 across the passes (LKB_NUFFT_GROUP_MB, default 0 = one group;
@@ -522,6 +568,20 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
           Zout, p, pl.dec, k0, F, F_low, d_rot, d_rot2, d_ysumf + 2 * g0, d_absmax + 2 * g0, (float)N, normalization,
           (float)norm_scale, B_g, np_g, pa, d_pow + (size_t)2 * g0 * F);
       LKB_LAUNCH_CHECK();
+      if (verify && g0 == 0) {            // self-check on the first group (one small kernel + one read-back)
+        const char* fe = getenv("LKB_NUFFT_INJECT_FAULT");       // test hook: pretend the transform is off by x
+        LKB_CUDA_CHECK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned), st));
+        LKB_LAUNCH(16, 128, st, nufft_verify_kernel)(Zout, p, pa, pl.dec, k0, F, F_low, d_t, N, d_yc, ystride, d_absmax,
+                                                   d_freq, B_g, fe ? (float)atof(fe) : 1.0f, d_worst);
+        LKB_LAUNCH_CHECK();
+        unsigned h_worst = 0;
+        LKB_CUDA_CHECK(cudaMemcpyAsync(&h_worst, d_worst, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h_worst > 100u) {
+          set_error("NUFFT self-check failed: transform deviates from the direct sums by %u x 1e-7 sum|y|", h_worst);
+          return LKB_E_VERIFY;
+        }
+      }
     }
   }
   if (prof) prof_end(st);

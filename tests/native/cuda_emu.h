@@ -135,6 +135,12 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 
+inline unsigned atomicMax(unsigned* addr, unsigned v) {
+  std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
+  const unsigned old = *addr;
+  if (v > old) *addr = v;
+  return old;
+}
 inline int atomicMax(int* addr, int v) {
   std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
   const int old = *addr;

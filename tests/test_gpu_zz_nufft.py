@@ -26,6 +26,7 @@ def _worker(out_q):
     from lightkurve_b200 import engine
     from oracle import ls as ols
     engine.init(0)
+    os.environ["LKB_NUFFT_VERIFY"] = "1"           # the path's built-in self-check (direct fp64 spot sums) stays on
     rng = np.random.default_rng(21)
     res = {}
     # (1) default lightkurve grid (f0 = df = 1 / (5 T)), odd batch, amplitudes spanning 3 decades

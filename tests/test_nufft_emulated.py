@@ -197,3 +197,22 @@ def test_small_and_odd_shapes_on_the_emulator(emu, monkeypatch, B, N, F, k0):
             ok = np.isfinite(ref) & (freq > 0)
             ex = _excess(power[b].astype(np.float64)[ok], ref[ok])
             assert ex.max() < 0.5, (mode, b, ex.max())
+
+
+def test_built_in_self_check(emu, monkeypatch):
+    """LKB_NUFFT_VERIFY=1: after the finish kernel 64 (light curve, row) samples are recomputed directly in fp64 and
+    compared with the transform; a healthy run passes, an injected 1 % fault is reported as LKB_E_VERIFY (-7)."""
+    monkeypatch.setenv("LKB_NUFFT_VERIFY", "1")
+    N, F, B = 400, 300, 3
+    t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(77, N, F, B)
+    F_low = int((freq * trel[-1] <= 2.0).sum()) + 1
+    rot, rot2 = _window_rows(trel, freq, F_low)
+    power = np.zeros((B, F), np.float32)
+    args = [trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B, freq.ctypes.data, F, f0,
+            df, rot.ctypes.data, rot2.ctypes.data, F_low, 2, 1.0, power.ctypes.data]
+    for mode in ("", "fused"):
+        if mode:
+            monkeypatch.setenv("LKB_NUFFT_FFT", mode)
+        assert emu.emu_nufft_shared(*args) == 0, emu.emu_last_error()
+    monkeypatch.setenv("LKB_NUFFT_INJECT_FAULT", "1.01")
+    assert emu.emu_nufft_shared(*args) == -7 and b"self-check failed" in emu.emu_last_error()
