@@ -36,6 +36,11 @@ except Exception as e:
 PY
 done
 
+echo "=== 3b. ragged batches (config-5 share): direct kernel vs NUFFT path ==="
+timeout 400 python tools/probe_others.py 0.125 k1
+LKB_LS_RAGGED_NUFFT=1 timeout 400 python tools/probe_others.py 0.125 k1
+LKB_LS_RAGGED_NUFFT=1 LKB_NUFFT_FFT=smem LKB_NUFFT_TWIDDLE_CHAIN=1 timeout 400 python tools/probe_others.py 0.125 k1
+
 echo "=== 4. launch list and one full ncu capture of the NUFFT passes (only if step 3 produced numbers) ==="
 if command -v ncu > /dev/null; then
   LKB_NUFFT_TWIDDLE_CHAIN=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
