@@ -411,6 +411,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the BLS (configs[2]) leg")
     ap.add_argument("--nufft-leg", action="store_true", help=argparse.SUPPRESS)      # internal: child of secondary.ls_nufft
+    ap.add_argument("--nufft-variants", action="store_true",
+                    help="also time the NUFFT path's transform variants in a child process (secondary.ls_nufft)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -497,6 +499,7 @@ def main():
     kms = engine.profile_read()
     engine.profile_enable(False)
     clocks = sampler.stop() if sampler else None
+    family = engine.ls_last_algo()             # what `auto` resolved to: "nufft", "tcgen05" or "simt"
 
     for _ in range(2):
         step_e2e()
@@ -509,7 +512,7 @@ def main():
                                               cpu_baseline=not args.no_cpu_baseline)}
         except Exception as e:                                    # the headline line must survive this leg
             secondary = {"bls": {"error": repr(e)}}
-        if world == 1 and rank == 0 and args.algo != "nufft":
+        if world == 1 and rank == 0 and args.nufft_variants:
             secondary["ls_nufft"] = nufft_leg(args)
 
     units_per_step = float(F) * N * B * world
@@ -530,15 +533,18 @@ def main():
         traffic = None
         try:      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "bench_kernel_traffic.json")))
-            if args.workload == "c2" and args.algo != "simt":
+            if args.workload == "c2" and family == "tcgen05":
                 traffic = tj["ls_tcg_kernel"]["traffic_bytes_per_launch"]
         except Exception:
             pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": traffic, "kernel": "ls_tcg_kernel" if args.algo != "simt"
-                    else "ls_shared_simt_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                    "frac": achieved / peak_tf, "traffic": traffic,
+                    "traffic_source": "static: one ncu --set full capture of this kernel on this workload, committed as "
+                                      "profiles/bench_kernel_traffic.json (not re-measured in this run)" if traffic else None,
+                    "kernel": "ls_tcg_kernel" if family == "tcgen05" else "ls_shared_simt_kernel", "kernel_ms": k_ms,
+                    "peak_source": peak_src,
                     "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
-        if args.algo == "nufft":
+        if family == "nufft":
             # HBM sweep: fine grids [B/2, M] complex64 written once by the spreading, read + written by every Stockham
             # pass, two modes per output read by the finish kernel; flux read once, power written once
             # (DESIGN.md K2n).  k0 = 1 on the bench grid (f0 = df).
@@ -562,11 +568,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 spreading + FFT, f64 phase (nufft)" if args.algo == "nufft" else
+            "vs_baseline": None, "dtype": "f32 spreading + FFT, f64 phase (nufft)" if family == "nufft" else
                      "f16x2-split in / f32 accumulate (tcgen05), f64 phase",
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_per_gpu": B, "cadences": N,
-                       "frequencies": F, "normalization": "amplitude", "algo": args.algo,
+                       "frequencies": F, "normalization": "amplitude", "algo": args.algo, "kernel_family": family,
                        "sharding": "by target, %d rank(s), NCCL all-gather of power" % world,
                        "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((Y.nbytes + B * F * 4) / 1e6)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(Y.nbytes) * world,

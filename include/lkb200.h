@@ -48,11 +48,14 @@ extern "C" {
 #define LKB_LS_NORM_AMPLITUDE 2  /* sqrt(raw)*sqrt(4/N)   (lightkurve "amplitude")          */
 
 /* shared-grid Lomb-Scargle contraction algorithm */
-#define LKB_LS_ALGO_AUTO     0   /* tcgen05 when shapes allow, else SIMT */
-#define LKB_LS_ALGO_SIMT     1   /* fp32 CUDA-core tiled contraction */
-#define LKB_LS_ALGO_TCGEN05  2   /* split-fp16 tcgen05.mma, fp32 TMEM accumulators */
-#define LKB_LS_ALGO_NUFFT    3   /* type-1 NUFFT (spread + FFT), regular grids f_k = (k0 + k) df only; opt-in:
-                                    AUTO does not select it (round 1: CPU-verified, not yet measured on hardware) */
+#define LKB_LS_ALGO_AUTO     0   /* NUFFT when the grid allows it and the job is large (regular f_k = (k0 + k) df,
+                                    integer k0, df * baseline <= 1, ascending times); else tcgen05 / direct sums */
+#define LKB_LS_ALGO_SIMT     1   /* exact direct sums on the CUDA cores (K1: ls_direct_kernel, K2: tiled contraction):
+                                    what the shim maps ls_method="slow" to */
+#define LKB_LS_ALGO_TCGEN05  2   /* K2 only: split-fp16 tcgen05.mma, fp32 TMEM accumulators */
+#define LKB_LS_ALGO_NUFFT    3   /* type-1 NUFFT (spread + FFT): the algorithm behind the reference's optional
+                                    ls_method="fastnifty" (periodogram.py:917-946); LKB_E_UNSUPPORTED when the
+                                    grid / times do not qualify */
 
 /* BLS objective (astropy BoxLeastSquares.power objective=) */
 #define LKB_BLS_LIKELIHOOD 0
@@ -67,6 +70,9 @@ int lkb_shutdown(void);                /* free the workspace pool */
 int lkb_sm_count(void);                /* multiprocessor count of the bound device */
 /* counters: number of kernels this library launched since init (bench gpu_launches) */
 int64_t lkb_launch_count(void);
+/* kernel family (LKB_LS_ALGO_SIMT / _TCGEN05 / _NUFFT) the most recent lkb_ls_power* call actually ran; -1 before
+ * the first call.  Lets a caller (bench.py, tests) see what LKB_LS_ALGO_AUTO resolved to. */
+int lkb_ls_last_algo(void);
 /* Measurement hooks (bench.py roofline): when enabled, every compute call records CUDA events on
  * its stream around its DOMINANT kernel (LS contraction / BLS search / flatten / Gram accumulation).
  * lkb_profile_read synchronises, writes up to max_n durations [ms] in call order, resets the ring
@@ -95,6 +101,13 @@ int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* off
                  const double* freq, const int64_t* freq_offsets, int64_t F,
                  int normalization, const double* norm_scale,
                  float* power, int mem, void* stream);
+/* The same with the kernel family chosen by the caller (`method=` of LombScargle.power at
+ * periodogram.py:964): LKB_LS_ALGO_AUTO (what lkb_ls_power does), LKB_LS_ALGO_SIMT (direct sums, "slow") or
+ * LKB_LS_ALGO_NUFFT ("fastnifty": one shared regular host-visible grid, sorted times). */
+int lkb_ls_power_ex(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B,
+                    const double* freq, const int64_t* freq_offsets, int64_t F,
+                    int normalization, const double* norm_scale,
+                    float* power, int mem, void* stream, int algo);
 
 /* K1n: multi-term ("chi2") periodogram = LombScargle(time, flux, nterms=n, normalization="psd")
  * .power(frequency, method="chi2"|"fastchi2"), the call lightkurve makes for nterms > 1

@@ -32,10 +32,13 @@ SIGNATURES = {
     "lkb_shutdown": (c_int, []),
     "lkb_sm_count": (c_int, []),
     "lkb_launch_count": (c_i64, []),
+    "lkb_ls_last_algo": (c_int, []),
     "lkb_profile_enable": (c_int, [c_int]),
     "lkb_profile_read": (c_int, [c_vp, c_int]),
     "lkb_ws_read": (c_int, [c_int, c_i64, c_i64, c_vp]),
     "lkb_ls_power": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
+    "lkb_ls_power_ex": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp,
+                                c_int]),
     "lkb_ls_power_chi2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp,
                                   c_int, c_vp]),
     "lkb_ls_power_shared": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_i64, c_int, c_vp, c_vp, c_int,

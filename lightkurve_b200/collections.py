@@ -88,7 +88,7 @@ class LightCurveCollection(Collection):
         scales = [LombScarglePeriodogram._norm_args(p)[1] for p in preps]
         shared_t = all(len(p["time"]) == len(p0["time"]) and np.array_equal(p["time"], p0["time"]) for p in preps)
         shared_f = all(len(f) == len(freqs[0]) and np.array_equal(f, freqs[0]) for f in freqs)
-        if p0["ls_method"] in ("chi2", "fastchi2"):
+        if p0["ls_method"] in ("chi2", "fastchi2", "fastnifty_chi2"):
             fl = [np.asarray(p["lc"].flux.value) for p in preps]
             fl = [f if f.dtype == np.float32 else f.astype(np.float64) for f in fl]
             powers = engine.ls_power_chi2([p["time"] for p in preps], fl, freqs[0] if shared_f else freqs,
@@ -97,12 +97,20 @@ class LightCurveCollection(Collection):
             Y = np.stack([np.asarray(p["lc"].flux.value) for p in preps])
             if Y.dtype != np.float32:
                 Y = Y.astype(np.float64)
-            powers = engine.ls_power_shared(p0["time"], Y, freqs[0], norm, scales[0])
+            algo = {"direct": "simt"}.get(LombScarglePeriodogram._engine_algo(p0["ls_method"]),
+                                          LombScarglePeriodogram._engine_algo(p0["ls_method"]))
+            try:
+                powers = engine.ls_power_shared(p0["time"], Y, freqs[0], norm, scales[0], algo=algo)
+            except Exception as e:
+                if algo != "nufft" or getattr(e, "status", None) != -5:          # LKB_E_UNSUPPORTED
+                    raise
+                powers = engine.ls_power_shared(p0["time"], Y, freqs[0], norm, scales[0], algo="auto")
         else:
             fl = [np.asarray(p["lc"].flux.value) for p in preps]
             fl = [f if f.dtype == np.float32 else f.astype(np.float64) for f in fl]
-            powers = engine.ls_power_ragged([p["time"] for p in preps], fl, freqs[0] if shared_f else freqs, norm,
-                                            None if norm != "psd" else scales)
+            powers = LombScarglePeriodogram._ragged_power(engine, [p["time"] for p in preps], fl,
+                                                          freqs[0] if shared_f else freqs, norm,
+                                                          None if norm != "psd" else scales, p0["ls_method"])
         return [LombScarglePeriodogram._finish(p, powers[b]) for b, p in enumerate(preps)]
 
     def flatten(self, window_length=101, polyorder=2, return_trend=False, break_tolerance=5, niters=3, sigma=3,

@@ -10,6 +10,7 @@ namespace lkb {
 
 static thread_local char t_err[512] = "";
 int64_t g_launches = 0;
+int g_last_ls_algo = -1;      // kernel family the last Lomb-Scargle call ran (LKB_LS_ALGO_*; -1: none yet)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -202,7 +203,7 @@ int ws_get(int slot, size_t bytes, void** out) {
 
 // implemented in the kernel translation units
 int ls_power_ragged(const double*, const void*, int, const int64_t*, int, const double*, const int64_t*, int64_t,
-                    int, const double*, float*, int, cudaStream_t);
+                    int, const double*, float*, int, cudaStream_t, int);
 int ls_power_shared(const double*, const void*, int, int, int64_t, const double*, int64_t, int, const double*,
                     float*, int, cudaStream_t, int);
 int ls_power_chi2(const double*, const void*, int, const int64_t*, int, const double*, const int64_t*, int64_t, int,
@@ -291,6 +292,7 @@ int lkb_profile_read(double* ms_out, int max_n) {
   return n;
 }
 int64_t lkb_launch_count(void) { return g_launches; }
+int lkb_ls_last_algo(void) { return g_last_ls_algo; }
 
 // Diagnostic: copy `bytes` bytes at `offset` of workspace slot `slot` to the host buffer `out` (after a device
 // synchronise).  Lets a test or tools/nufft_gpu_check.py look at the intermediate buffers of the last call.
@@ -310,7 +312,15 @@ int lkb_ls_power(const double* t, const void* y, int y_dtype, const int64_t* off
                  int mem, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   return ls_power_ragged(t, y, y_dtype, offsets, B, freq, freq_offsets, F, normalization, norm_scale, power, mem,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, LKB_LS_ALGO_AUTO);
+}
+
+int lkb_ls_power_ex(const double* t, const void* y, int y_dtype, const int64_t* offsets, int B, const double* freq,
+                    const int64_t* freq_offsets, int64_t F, int normalization, const double* norm_scale, float* power,
+                    int mem, void* stream, int algo) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return ls_power_ragged(t, y, y_dtype, offsets, B, freq, freq_offsets, F, normalization, norm_scale, power, mem,
+                         (cudaStream_t)stream, algo);
 }
 
 int lkb_ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t N, const double* freq, int64_t F,

@@ -12,6 +12,7 @@ namespace lkb {
 // ---- error plumbing ---------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;
+extern int g_last_ls_algo;
 
 #define LKB_CUDA_CHECK(expr)                                                        \
   do {                                                                              \

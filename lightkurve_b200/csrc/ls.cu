@@ -26,10 +26,10 @@ namespace lkb {
 
 // ls_nufft.cu: the opt-in NUFFT path for ragged batches (LKB_LS_RAGGED_NUFFT=1)
 bool ls_nufft_ragged_enabled();
-int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po, int B,
-                           int64_t ptotal, int64_t nmax, const double* d_span, const double* h_span,
-                           const double* d_ysum, int64_t F, double f0, double df, int normalization,
-                           const double* d_ns, float* d_pow, cudaStream_t st);
+int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po,
+                           const int64_t* h_off, int B, int64_t ptotal, int64_t nmax, const double* d_span,
+                           const double* h_span, const double* d_ysum, int64_t F, double f0, double df,
+                           int normalization, const double* d_ns, float* d_pow, cudaStream_t st);
 
 // Per-cadence entry of a regular-grid light curve (ragged path): fixed-point phases of the grid origin and of one
 // grid step, plus the fp32 rotation by one step - the bins after a warp's first are obtained by rotating (cos, sin)
@@ -170,9 +170,12 @@ ls_prep_shared_kernel(const TY* __restrict__ y, int64_t N, int64_t Npad, float* 
 }
 
 // t_out[i] = t[i] - t[0] for i < N, 0 for the padding cadences [N, Npad)
-__global__ void ls_shift_time_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double* __restrict__ t_out) {
+// also raises *unsorted (nullable) when the times are not ascending (the NUFFT path needs sorted times)
+__global__ void ls_shift_time_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, double* __restrict__ t_out,
+                                     int* __restrict__ unsorted) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Npad) t_out[i] = (i < N) ? (t[i] - t[0]) : 0.0;
+  if (unsorted && i > 0 && i < N && t[i] < t[i - 1]) *unsorted = 1;
 }
 
 // =====================================================================================
@@ -653,8 +656,10 @@ ls_chi2_kernel(const double* __restrict__ tws, const double* __restrict__ yws, c
 // =====================================================================================
 int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* h_offsets, int B,
                     const double* freq, const int64_t* h_freq_offsets, int64_t F, int normalization,
-                    const double* norm_scale, float* power, int mem, cudaStream_t st) {
+                    const double* norm_scale, float* power, int mem, cudaStream_t st, int algo) {
   LKB_REQUIRE(B > 0 && t && y && h_offsets && freq && power, "lkb_ls_power: null argument");
+  LKB_REQUIRE(algo == LKB_LS_ALGO_AUTO || algo == LKB_LS_ALGO_SIMT || algo == LKB_LS_ALGO_NUFFT,
+              "lkb_ls_power: algo must be AUTO, SIMT (direct sums) or NUFFT");
   LKB_REQUIRE(y_dtype == LKB_DTYPE_F32 || y_dtype == LKB_DTYPE_F64, "lkb_ls_power: bad y_dtype");
   LKB_REQUIRE(normalization >= 0 && normalization <= 2, "lkb_ls_power: bad normalization");
   LKB_REQUIRE(normalization != LKB_LS_NORM_PSD_SCALE || norm_scale, "lkb_ls_power: norm_scale required");
@@ -756,29 +761,42 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
 
   dim3 grid((unsigned)((Fmax + LS_FPB - 1) / LS_FPB), (unsigned)B);
   LKB_REQUIRE(B <= 65535, "lkb_ls_power: B > 65535 per call (split the batch)");
-  // Opt-in (LKB_LS_RAGGED_NUFFT=1): the NUFFT path of ls_nufft.cu for one shared regular grid; light curves that
-  // do not qualify (empty / tiny, unsorted times, df * baseline > 1) send the whole call to the direct kernel.
-  if (ls_nufft_ragged_enabled() && regular && !h_freq_offsets) {
+  // NUFFT path of ls_nufft.cu (one shared regular grid f_k = (k0 + k) df): what `auto` picks when the job is large
+  // enough for its launches to pay (config 5's share: ~100x fewer operations than the direct sums); light curves
+  // that do not qualify (empty / tiny, unsorted times, df * baseline > 1) send the whole call to the direct kernel
+  // under `auto`, and fail an explicit NUFFT request.  LKB_LS_RAGGED_NUFFT=0 keeps `auto` on the direct kernel.
+  const bool want_nufft = algo == LKB_LS_ALGO_NUFFT ||
+                          (algo == LKB_LS_ALGO_AUTO && ls_nufft_ragged_enabled() && (double)total * (double)F >= 2.5e7);
+  if (algo == LKB_LS_ALGO_NUFFT && !(regular && !h_freq_offsets)) {
+    set_error("lkb_ls_power: the NUFFT path needs host-visible, regular, shared frequencies");
+    return LKB_E_UNSUPPORTED;
+  }
+  if (want_nufft && regular && !h_freq_offsets) {
     int64_t nmax = 0, nmin = INT64_MAX;
     for (int b = 0; b < B; ++b) {
       const int64_t n = h_offsets[b + 1] - h_offsets[b];
       nmax = n > nmax ? n : nmax;
       nmin = n < nmin ? n : nmin;
     }
+    int rc = LKB_E_UNSUPPORTED;
     if (nmin >= 8) {
       std::vector<double> h_span(B);
       LKB_CUDA_CHECK(cudaMemcpyAsync(h_span.data(), d_span, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
       LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-      const int rc = ls_nufft_ragged_launch(d_t, d_y, d_off, d_po, B, ptotal, nmax, d_span, h_span.data(), d_ysum, F,
-                                            h_f0[0], h_df[0], normalization, d_ns, d_pow, st);
+      rc = ls_nufft_ragged_launch(d_t, d_y, d_off, d_po, h_offsets, B, ptotal, nmax, d_span, h_span.data(), d_ysum, F,
+                                  h_f0[0], h_df[0], normalization, d_ns, d_pow, st);
       if (rc == LKB_OK) {
+        g_last_ls_algo = LKB_LS_ALGO_NUFFT;
         LKB_TRY(stage_out_copy<float>(mem, power, d_pow, out_count, st));
         if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
         return LKB_OK;
       }
-      if (rc != LKB_E_UNSUPPORTED) return rc;
+    } else {
+      set_error("lkb_ls_power: the NUFFT path needs at least 8 cadences per light curve");
     }
+    if (rc != LKB_E_UNSUPPORTED || algo == LKB_LS_ALGO_NUFFT) return rc;
   }
+  g_last_ls_algo = LKB_LS_ALGO_SIMT;
   prof_begin(st);
   if (regular)
     ls_direct_kernel<true><<<grid, LS_WARPS * 32, 0, st>>>(d_t, d_tab, d_y, d_off, d_po, d_freq, d_fo, F, d_span,
@@ -904,14 +922,70 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   const double *dt_in = nullptr, *d_freq = nullptr;
   const void* dy_in = nullptr;
   LKB_TRY(stage_in<double>(mem, WS_IN0, t, N, &dt_in, st));
-  // Host-mode calls on the tensor path are pipelined over chunks of light curves: the flux rows of chunk c + 1
-  // go up and the power rows of chunk c - 1 come down (two copy streams) while chunk c is computed.  Fully
+  LKB_TRY(stage_in<double>(mem, WS_IN2, freq, F, &d_freq, st));
+  double ns = 1.0;
+  if (norm_scale) {
+    if (mem == LKB_MEM_HOST) ns = *norm_scale;
+    else LKB_CUDA_CHECK(cudaMemcpyAsync(&ns, norm_scale, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mem == LKB_MEM_DEVICE) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  double* d_t = nullptr;
+  LKB_TRY(ws_get_t<double>(WS_D, Npad, &d_t));
+  // One small device->host read-back per call: grid regularity, f0, f1, the baseline t[N-1] and whether the times
+  // ascend.  Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
+  // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain - and the
+  // NUFFT path becomes eligible.
+  ulonglong2* d_tab = nullptr;
+  double h_meta[5] = {1.0, 0.0, 0.0, 0.0, 0.0};      // {regularity deviation, f0, f1, t_last, unsorted flag (int bits)}
+  {
+    double* d_meta = nullptr;
+    LKB_TRY(ws_get_t<double>(WS_K, 5, &d_meta));
+    LKB_CUDA_CHECK(cudaMemsetAsync(d_meta, 0, 5 * sizeof(double), st));
+    ls_shift_time_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(dt_in, N, Npad, d_t,
+                                                                         reinterpret_cast<int*>(d_meta + 4));
+    LKB_LAUNCH_CHECK();
+    ls_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, reinterpret_cast<float*>(d_meta));
+    LKB_LAUNCH_CHECK();
+    ls_meta_kernel<<<1, 1, 0, st>>>(d_freq, F, d_t, N, d_meta);
+    LKB_LAUNCH_CHECK();
+    LKB_CUDA_CHECK(cudaMemcpyAsync(h_meta, d_meta, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  int h_unsorted = 0;
+  memcpy(&h_unsorted, &h_meta[4], sizeof(int));
+  const double grid_f0 = h_meta[1], grid_df = h_meta[2] - h_meta[1];
+  const bool regular = F >= 2 && F < ((int64_t)1 << 31) && !getenv("LKB_LS_FORCE_FP64_PHASE") &&
+                       h_meta[0] <= 1e-6 && grid_f0 >= 0.0 && grid_df > 0.0;
+  // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
+  const double lowf_max = (h_meta[3] > 0.0) ? LS_LOWF_CYCLES / h_meta[3] : 0.0;
+  // Which kernel family.  NUFFT (ls_nufft.cu: spread + FFT, an HBM sweep) is what `auto` picks whenever the grid
+  // allows it (regular, integer f0 / df, df * baseline <= 1, ascending times) and the job is large enough for its
+  // ~15 launches to pay (measured on B200, config 2: 9 ms against 67 ms of the tensor-core contraction, and closer
+  // to the fp64 sums - tests/test_gpu_fullsize.py::test_config2_worst_bins).  LKB_LS_AUTO_NO_NUFFT=1 restores the
+  // round-1 choice (tcgen05 / SIMT contraction).  The contraction kernels remain the path for irregular grids.
+  const bool nufft_ok = ls_nufft_supported(F, regular, grid_f0, grid_df, h_meta[3]) && !h_unsorted;
+  const bool use_nufft = algo == LKB_LS_ALGO_NUFFT ||
+                         (algo == LKB_LS_ALGO_AUTO && nufft_ok && !getenv("LKB_LS_AUTO_NO_NUFFT") &&
+                          (double)B * (double)N * (double)F >= 2.5e7);
+  if (use_nufft && !nufft_ok) {
+    set_error(h_unsorted ? "lkb_ls_power_shared: the NUFFT path needs ascending times"
+                         : "lkb_ls_power_shared: the NUFFT path needs a regular grid f_k = (k0 + k) df with integer k0 "
+                           "and df * baseline <= 1");
+    return LKB_E_UNSUPPORTED;
+  }
+  g_last_ls_algo = use_nufft ? LKB_LS_ALGO_NUFFT : LKB_LS_ALGO_SIMT;
+  const bool use_tc = !use_nufft && ((algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
+  if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
+    set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
+    return LKB_E_UNSUPPORTED;
+  }
+  if (use_tc) g_last_ls_algo = LKB_LS_ALGO_TCGEN05;
+  // Host-mode calls on the tensor / NUFFT paths are pipelined over chunks of light curves: the flux rows of chunk
+  // c + 1 go up and the power rows of chunk c - 1 come down (two copy streams) while chunk c is computed.  Fully
   // asynchronous when the caller's buffers are page-locked; with pageable numpy memory the copies still work,
   // they just overlap less.
   constexpr int PIPE_CHUNK = 256;                    // one light-curve tile of the tensor kernel
-  const bool pipelined = mem == LKB_MEM_HOST && B > PIPE_CHUNK && !getenv("LKB_LS_NO_PIPELINE") &&
-                         (algo == LKB_LS_ALGO_TCGEN05 || algo == LKB_LS_ALGO_NUFFT ||
-                          (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
+  const bool pipelined = mem == LKB_MEM_HOST && B > PIPE_CHUNK && !getenv("LKB_LS_NO_PIPELINE") && (use_tc || use_nufft);
   unsigned char* d_ystage = nullptr;
   if (pipelined) {
     LKB_TRY(ws_get_t<unsigned char>(WS_IN1, (size_t)B * N * ysz, &d_ystage));
@@ -921,20 +995,11 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     LKB_TRY(stage_in<unsigned char>(mem, WS_IN1, (const unsigned char*)y, (size_t)B * N * ysz, &tmp, st));
     dy_in = tmp;
   }
-  LKB_TRY(stage_in<double>(mem, WS_IN2, freq, F, &d_freq, st));
-  double ns = 1.0;
-  if (norm_scale) {
-    if (mem == LKB_MEM_HOST) ns = *norm_scale;
-    else LKB_CUDA_CHECK(cudaMemcpyAsync(&ns, norm_scale, sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (mem == LKB_MEM_DEVICE) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-  }
   float* d_pow = nullptr;
   LKB_TRY(stage_out_alloc<float>(mem, WS_OUT0, power, (size_t)B * F, &d_pow));
 
-  double* d_t = nullptr;
   float *d_yc = nullptr, *d_absmax = nullptr;
   float4* d_rot = nullptr;
-  LKB_TRY(ws_get_t<double>(WS_D, Npad, &d_t));
   LKB_TRY(ws_get_t<float>(WS_E, (size_t)B * Npad, &d_yc));
   LKB_TRY(ws_get_t<float4>(WS_F, F, &d_rot));
   LKB_TRY(ws_get_t<float>(WS_G, B, &d_absmax));
@@ -943,8 +1008,6 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
   LKB_TRY(ws_get_t<float2>(WS_M, F, &d_rot2));
   LKB_TRY(ws_get_t<float>(WS_N, B, &d_ysumf));
 
-  ls_shift_time_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(dt_in, N, Npad, d_t);
-  LKB_LAUNCH_CHECK();
   auto prep_rows = [&](int b_lo, int nb) {
     if (y_dtype == LKB_DTYPE_F32)
       ls_prep_shared_kernel<float><<<nb, 256, 0, st>>>((const float*)dy_in + (size_t)b_lo * N, N, Npad,
@@ -957,43 +1020,10 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     prep_rows(0, B);
     LKB_LAUNCH_CHECK();
   }
-  // One small device->host read-back per call: grid regularity, f0, f1 and the baseline t[N-1].
-  // Regular frequency grid (f_k = f0 + k df)?  Then phases are generated in 64-bit fixed point from a
-  // per-cadence table {frac(f0 t_n), frac(df t_n)} instead of an fp64 multiply/round/convert chain.
-  ulonglong2* d_tab = nullptr;
-  double h_meta[4] = {1.0, 0.0, 0.0, 0.0};      // {regularity deviation, f0, f1, t_last}
-  {
-    double* d_meta = nullptr;
-    LKB_TRY(ws_get_t<double>(WS_K, 4, &d_meta));
-    LKB_CUDA_CHECK(cudaMemsetAsync(d_meta, 0, 4 * sizeof(double), st));
-    ls_grid_regularity_kernel<<<64, 256, 0, st>>>(d_freq, F, reinterpret_cast<float*>(d_meta));
-    LKB_LAUNCH_CHECK();
-    ls_meta_kernel<<<1, 1, 0, st>>>(d_freq, F, d_t, N, d_meta);
-    LKB_LAUNCH_CHECK();
-    LKB_CUDA_CHECK(cudaMemcpyAsync(h_meta, d_meta, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-  }
-  const double grid_f0 = h_meta[1], grid_df = h_meta[2] - h_meta[1];
-  const bool regular = F >= 2 && F < ((int64_t)1 << 31) && !getenv("LKB_LS_FORCE_FP64_PHASE") &&
-                       h_meta[0] <= 1e-6 && grid_f0 >= 0.0 && grid_df > 0.0;
-  if (regular) {
+  if (regular && !use_nufft) {
     LKB_TRY(ws_get_t<ulonglong2>(WS_L, Npad, &d_tab));
     ls_phase_table_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(d_t, N, Npad, grid_f0, grid_df, d_tab);
     LKB_LAUNCH_CHECK();
-  }
-  // frequencies with f * baseline <= LS_LOWF_CYCLES are "low rows" (ls_common.cuh)
-  const double lowf_max = (h_meta[3] > 0.0) ? LS_LOWF_CYCLES / h_meta[3] : 0.0;
-  // NUFFT path (ls_nufft.cu): opt-in only - `auto` does not select it until it has been measured on hardware
-  const bool use_nufft = algo == LKB_LS_ALGO_NUFFT;
-  if (use_nufft && !ls_nufft_supported(F, regular, grid_f0, grid_df, h_meta[3])) {
-    set_error("lkb_ls_power_shared: the NUFFT path needs a regular grid f_k = (k0 + k) df with integer k0 and "
-              "df * baseline <= 1");
-    return LKB_E_UNSUPPORTED;
-  }
-  bool use_tc = (algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F));
-  if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
-    set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
-    return LKB_E_UNSUPPORTED;
   }
   // The window terms depend only on (t, freq).  They CAN run on the library's side stream, co-resident
   // with the contraction kernel (LKB_LS_OVERLAP_WINDOW=1), but measured on B200 that costs more than it

@@ -746,19 +746,22 @@ nufft_lowrows_ragged_kernel(const double* __restrict__ t, const float* __restric
 
 }  // namespace
 
-bool ls_nufft_ragged_enabled() {
+bool ls_nufft_ragged_enabled() {               // `auto` of the ragged entry may use this path (default: yes)
   const char* e = getenv("LKB_LS_RAGGED_NUFFT");
-  return e && atoi(e) != 0;
+  return !e || atoi(e) != 0;
 }
 
 // One shared regular grid f_k = f0 + k df (k0 = f0 / df integer), light curves in the K1 prologue's layout
 // (d_t / d_y padded CSR with offsets d_po; d_off the unpadded offsets; d_span, d_ysum per light curve).
 // h_span: host copy of d_span.  Returns LKB_E_UNSUPPORTED when a light curve is not eligible (unsorted times,
 // df * baseline > 1): the caller then runs the direct kernel.
-int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po, int B,
-                           int64_t ptotal, int64_t nmax, const double* d_span, const double* h_span,
-                           const double* d_ysum, int64_t F, double f0, double df, int normalization,
-                           const double* d_ns, float* d_pow, cudaStream_t st) {
+// The fine grids of all light curves need 24 (M + 2 M2) bytes per pair; batches whose grids exceed
+// LKB_NUFFT_RAGGED_MB (default 16384) are processed in groups of pairs through the same buffers.
+int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po,
+                           const int64_t* h_off, int B, int64_t ptotal, int64_t nmax, const double* d_span,
+                           const double* h_span, const double* d_ysum, int64_t F, double f0, double df,
+                           int normalization, const double* d_ns, float* d_pow, cudaStream_t st) {
+  (void)h_off;
   const double q = f0 / df, k0d = rint(q);
   if (!(df > 0.0) || !(f0 >= 0.0) || fabs(q - k0d) > 1e-9 * fmax(1.0, q) || k0d > 1.0e7) {
     set_error("NUFFT (ragged): the grid is not f_k = (k0 + k) df with integer k0");
@@ -767,24 +770,21 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   const int64_t k0 = (int64_t)k0d;
   const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
   if (p2 > 24) { set_error("NUFFT (ragged): fine grid larger than 2^24 cells"); return LKB_E_UNSUPPORTED; }
-  double span_min = 1e300;
   for (int b = 0; b < B; ++b) {
     if (!(h_span[b] > 0.0) || !(df * h_span[b] <= 1.0 + 1e-9)) {
       set_error("NUFFT (ragged): a light curve has zero baseline or df * baseline > 1");
       return LKB_E_UNSUPPORTED;
     }
-    if (h_span[b] > 0.0 && h_span[b] < span_min) span_min = h_span[b];
-  }
-  // rows k with (f0 + k df) * span_b <= LS_LOWF_CYCLES for at least one light curve
-  int64_t F_low_max = 0;
-  if (span_min < 1e300) {
-    const double nlow = floor((LS_LOWF_CYCLES / span_min - f0) / df) + 2.0;
-    F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
   }
   const int w = kernel_width();
   const float beta = 2.30f * (float)w;
   const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
-  const int npairs = (B + 1) / 2;
+  const int npairs_all = (B + 1) / 2;
+  double cap_mb = 16384.0;
+  if (const char* e = getenv("LKB_NUFFT_RAGGED_MB")) { const double v = atof(e); if (v > 0.0) cap_mb = v; }
+  const double per_pair_mb = (2.0 * (double)M + 2.0 * (double)M2) * sizeof(float2) / 1048576.0;
+  int group = (int)fmax(1.0, floor(cap_mb / per_pair_mb));
+  if (group > npairs_all) group = npairs_all;
   GlNodes gl;
   nufft::gauss_legendre(32, gl.x, gl.w);
 
@@ -795,9 +795,9 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   LKB_TRY(ws_get_t<Cad>(WS_K, ptotal + 4, &cad));
   LKB_TRY(ws_get_t<Cad>(WS_L, ptotal + 4, &cad2));
   LKB_TRY(ws_get_t<float>(WS_M, B, &absmax));
-  LKB_TRY(ws_get_t<float2>(WS_N, (size_t)npairs * M, &Za));
-  LKB_TRY(ws_get_t<float2>(WS_O, (size_t)npairs * M, &Zb));
-  LKB_TRY(ws_get_t<float2>(WS_P, (size_t)2 * npairs * M2, &Zw));
+  LKB_TRY(ws_get_t<float2>(WS_N, (size_t)group * M, &Za));
+  LKB_TRY(ws_get_t<float2>(WS_O, (size_t)group * M, &Zb));
+  LKB_TRY(ws_get_t<float2>(WS_P, (size_t)2 * group * M2, &Zw));
   LKB_TRY(ws_get_t<float2>(WS_IN4, F, &dec));
   LKB_TRY(ws_get_t<float2>(WS_IN5, 2 * (k0 + F), &dec2));
   LKB_TRY(ws_get_t<int>(WS_IN6, 1, &flag));
@@ -821,40 +821,51 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   LKB_LAUNCH_CHECK();
 
   prof_begin(st);
-  // window terms: unit strengths on the 2x finer grid
-  LKB_LAUNCH(blocks_for((int64_t)npairs * M2, 256), 256, st, nufft_spread_ragged_kernel)(cad2, nullptr, d_off, d_po, absmax, B,
-                                                                                  npairs, w, beta, p2, Zw);
-  LKB_LAUNCH_CHECK();
-  float2* Zw_out = nullptr;
-  int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
-  if (fft_mode() != 0) {
-    LKB_TRY(fft_fourstep(Zw, p2, npairs, st, &pa2, nullptr));
-    Zw_out = Zw;
-  } else {
-    LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
-  }
-  // flux
-  LKB_LAUNCH(blocks_for((int64_t)npairs * M, 256), 256, st, nufft_spread_ragged_kernel)(cad, d_y, d_off, d_po, absmax, B,
-                                                                                 npairs, w, beta, p, Za);
-  LKB_LAUNCH_CHECK();
-  float2* Zout = nullptr;
-  if (fft_mode() != 0) {
-    LKB_TRY(fft_fourstep(Za, p, npairs, st, &pa, nullptr));
-    Zout = Za;
-  } else {
-    LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
-  }
-  LKB_LAUNCH(blocks_for(F * npairs, 256), 256, st, nufft_finish_ragged_kernel)(Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df,
-                                                                        d_off, d_span, d_ysum, absmax, normalization,
-                                                                        d_ns, B, npairs, pa, pa2, d_pow);
-  LKB_LAUNCH_CHECK();
-  prof_end(st);
-  if (F_low_max > 0) {
-    LKB_LAUNCH(blocks_for(F_low_max * B, 4), 128, st, nufft_lowrows_ragged_kernel)(d_t, d_y, d_off, d_po, d_span, d_ysum, f0,
-                                                                             df, F_low_max, F, normalization, d_ns, B,
-                                                                             d_pow);
+  for (int g0 = 0; g0 < npairs_all; g0 += group) {
+    const int npairs = std::min(group, npairs_all - g0);
+    const int b0 = 2 * g0, Bg = std::min(B - b0, 2 * npairs);
+    const int64_t *off_g = d_off + b0, *po_g = d_po + b0;
+    const float* amax_g = absmax + b0;
+    // rows k with (f0 + k df) * span_b <= LS_LOWF_CYCLES for at least one light curve of the group
+    double span_min = 1e300;
+    for (int b = b0; b < b0 + Bg; ++b) span_min = fmin(span_min, h_span[b]);
+    const double nlow = floor((LS_LOWF_CYCLES / span_min - f0) / df) + 2.0;
+    const int64_t F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
+    // window terms: unit strengths on the 2x finer grid
+    LKB_LAUNCH(blocks_for((int64_t)npairs * M2, 256), 256, st, nufft_spread_ragged_kernel)(cad2, nullptr, off_g, po_g, amax_g,
+                                                                                    Bg, npairs, w, beta, p2, Zw);
     LKB_LAUNCH_CHECK();
+    float2* Zw_out = nullptr;
+    int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
+    if (fft_mode() != 0) {
+      LKB_TRY(fft_fourstep(Zw, p2, npairs, st, &pa2, nullptr));
+      Zw_out = Zw;
+    } else {
+      LKB_TRY(fft_passes(Zw, Zw + (size_t)npairs * M2, p2, npairs, st, &Zw_out));
+    }
+    // flux
+    LKB_LAUNCH(blocks_for((int64_t)npairs * M, 256), 256, st, nufft_spread_ragged_kernel)(cad, d_y, off_g, po_g, amax_g, Bg,
+                                                                                   npairs, w, beta, p, Za);
+    LKB_LAUNCH_CHECK();
+    float2* Zout = nullptr;
+    if (fft_mode() != 0) {
+      LKB_TRY(fft_fourstep(Za, p, npairs, st, &pa, nullptr));
+      Zout = Za;
+    } else {
+      LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+    }
+    LKB_LAUNCH(blocks_for(F * npairs, 256), 256, st, nufft_finish_ragged_kernel)(
+        Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df, off_g, d_span + b0, d_ysum + b0, amax_g, normalization,
+        d_ns ? d_ns + b0 : nullptr, Bg, npairs, pa, pa2, d_pow + (size_t)b0 * F);
+    LKB_LAUNCH_CHECK();
+    if (F_low_max > 0) {
+      LKB_LAUNCH(blocks_for(F_low_max * Bg, 4), 128, st, nufft_lowrows_ragged_kernel)(
+          d_t, d_y, off_g, po_g, d_span + b0, d_ysum + b0, f0, df, F_low_max, F, normalization,
+          d_ns ? d_ns + b0 : nullptr, Bg, d_pow + (size_t)b0 * F);
+      LKB_LAUNCH_CHECK();
+    }
   }
+  prof_end(st);
   return LKB_OK;
 }
 

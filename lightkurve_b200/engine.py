@@ -41,6 +41,12 @@ def launch_count():
     return int(L.load().lkb_launch_count())
 
 
+def ls_last_algo():
+    """Kernel family the most recent Lomb-Scargle call ran: "simt" (direct sums), "tcgen05" or "nufft"."""
+    return {L.LS_ALGO_SIMT: "simt", L.LS_ALGO_TCGEN05: "tcgen05", L.LS_ALGO_NUFFT: "nufft"}.get(
+        int(L.load().lkb_ls_last_algo()), "none")
+
+
 def profile_enable(on=True):
     """Record CUDA events around the dominant kernel of each subsequent call (see lkb200.h)."""
     L.check(L.load().lkb_profile_enable(1 if on else 0))
@@ -93,14 +99,22 @@ def _y_dtype_code(dt):
 # --------------------------------------------------------------------------------------
 # Lomb-Scargle
 # --------------------------------------------------------------------------------------
-def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_scale=None):
+_RAGGED_ALGOS = {"auto": L.LS_ALGO_AUTO, "direct": L.LS_ALGO_SIMT, "simt": L.LS_ALGO_SIMT, "nufft": L.LS_ALGO_NUFFT}
+
+
+def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_scale=None, algo="auto"):
     """K1.  `times`/`fluxes`: lists of 1-D arrays (one per light curve, no NaNs).
     `frequency`: one 1-D grid shared by all light curves, or a list of per-LC grids.
+    `algo`: "auto" (the NUFFT kernels for a large job on one shared regular grid with sorted times, else the direct
+    sums), "direct" (always the exact direct sums - astropy method="slow") or "nufft" (raises when the grid or the
+    times do not qualify - the reference's ls_method="fastnifty").
     Returns a [B, F] float32 array (shared grid) or a list of float32 arrays."""
     lib = L.load()
     B = len(times)
     if B == 0:
         return []
+    if algo not in _RAGGED_ALGOS:
+        raise ValueError("algo must be one of %s" % sorted(_RAGGED_ALGOS))
     t, offsets = _csr(times)
     ydt = np.float32 if all(np.asarray(f).dtype == np.float32 for f in fluxes) else np.float64
     y, yoff = _csr(fluxes, ydt)
@@ -117,8 +131,8 @@ def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_sc
         F = len(freq)
         out = np.empty((B, F), dtype=np.float32)
     ns = None if norm_scale is None else np.ascontiguousarray(np.broadcast_to(norm_scale, (B,)), dtype=np.float64)
-    L.check(lib.lkb_ls_power(L.ptr(t), L.ptr(y), _y_dtype_code(ydt), L.ptr(offsets), B, L.ptr(freq), L.ptr(foff), F,
-                             _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_HOST, None))
+    L.check(lib.lkb_ls_power_ex(L.ptr(t), L.ptr(y), _y_dtype_code(ydt), L.ptr(offsets), B, L.ptr(freq), L.ptr(foff), F,
+                                _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_HOST, None, _RAGGED_ALGOS[algo]))
     if per_lc:
         return [out[foff[b]:foff[b + 1]] for b in range(B)]
     return out
@@ -164,22 +178,37 @@ def ls_power_chi2(times, fluxes, frequency, nterms=1, normalization="amplitude",
 
 def ls_power_shared(t, Y, frequency, normalization="amplitude", norm_scale=None, algo="auto", out=None):
     """K2.  One cadence grid `t` [N] shared by the batch `Y` [B, N]; `frequency` [F].
-    numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode).
-    `algo`: "auto" (tcgen05 tensor path when the shape allows, else the CUDA-core contraction), "simt", "tcgen05",
-    or "nufft" - the opt-in spread + FFT path for regular frequency grids (raises for grids / times it
-    does not support)."""
+    numpy in -> numpy out (host mode); CUDA torch tensors in -> torch tensor out (device mode: the kernels are
+    enqueued on the current torch stream, but the call itself synchronises that stream once for a small metadata
+    read-back, and the library's grow-only workspaces are shared by all calls - use ONE stream per process).
+    `algo`: "auto" (the spread + FFT path of DESIGN.md K2n when the grid is regular with integer f0/df,
+    df * baseline <= 1 and the times ascend; else the tcgen05 tensor path when the shape allows; else the CUDA-core
+    contraction), "simt", "tcgen05", or "nufft" (raises for grids / times it does not support)."""
     lib = L.load()
+    if algo not in _ALGOS:
+        raise ValueError("algo must be one of %s" % sorted(_ALGOS))
     if _is_torch(Y):
         import torch
-        if not (Y.is_cuda and t.is_cuda and frequency.is_cuda):
+        if not (_is_torch(t) and _is_torch(frequency) and Y.is_cuda and t.is_cuda and frequency.is_cuda):
             raise ValueError("device mode needs CUDA tensors for t, Y and frequency")
+        if Y.dim() != 2 or t.dim() != 1 or frequency.dim() != 1:
+            raise ValueError("Y must be [B, N], t [N] and frequency [F]")
         B, N = Y.shape
         F = frequency.numel()
+        if t.numel() != N:
+            raise ValueError("t has %d cadences but Y has %d columns" % (t.numel(), N))
         if t.dtype != torch.float64 or frequency.dtype != torch.float64:
             raise TypeError("t and frequency must be float64")
+        if Y.dtype not in (torch.float32, torch.float64):
+            raise TypeError("flux must be float32 or float64, not %s" % (Y.dtype,))
+        if not (Y.is_contiguous() and t.is_contiguous() and frequency.is_contiguous()):
+            raise ValueError("t, Y and frequency must be contiguous")
         ycode = L.DTYPE_F32 if Y.dtype == torch.float32 else L.DTYPE_F64
         if out is None:
             out = torch.empty((B, F), dtype=torch.float32, device=Y.device)
+        elif not (_is_torch(out) and out.is_cuda and out.device == Y.device and out.dtype == torch.float32
+                  and tuple(out.shape) == (B, F) and out.is_contiguous()):
+            raise ValueError("`out` must be a contiguous CUDA float32 tensor of shape (%d, %d) on %s" % (B, F, Y.device))
         ns = None
         if norm_scale is not None:
             ns = torch.tensor([float(norm_scale)], dtype=torch.float64, device=Y.device)
@@ -191,10 +220,19 @@ def ls_power_shared(t, Y, frequency, normalization="amplitude", norm_scale=None,
     Y = np.ascontiguousarray(Y)
     if Y.dtype not in (np.float32, np.float64):
         Y = Y.astype(np.float64)
+    if Y.ndim != 2 or t.ndim != 1:
+        raise ValueError("Y must be [B, N] and t [N]")
     B, N = Y.shape
+    if t.shape != (N,):
+        raise ValueError("t has %d cadences but Y has %d columns" % (len(t), N))
     freq = np.ascontiguousarray(frequency, dtype=np.float64)
+    if freq.ndim != 1:
+        raise ValueError("frequency must be one-dimensional")
     if out is None:
         out = np.empty((B, len(freq)), dtype=np.float32)
+    elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == (B, len(freq))
+              and out.flags.c_contiguous and out.flags.writeable):
+        raise ValueError("`out` must be a writeable C-contiguous float32 array of shape (%d, %d)" % (B, len(freq)))
     ns = None if norm_scale is None else np.array([float(norm_scale)], dtype=np.float64)
     L.check(lib.lkb_ls_power_shared(L.ptr(t), L.ptr(Y), _y_dtype_code(Y.dtype), B, N, L.ptr(freq), len(freq),
                                     _NORMS[normalization], L.ptr(ns), L.ptr(out), L.MEM_HOST, None, _ALGOS[algo]))
@@ -261,9 +299,13 @@ def flatten(times, fluxes, flux_errs=None, masks=None, window_length=101, polyor
         raise ValueError("time and flux lengths differ")
     fe = None
     if flux_errs is not None:
-        fe, _ = _csr(flux_errs)
+        fe, eoff = _csr(flux_errs)
+        if not np.array_equal(offsets, eoff):
+            raise ValueError("time and flux_err lengths differ")
     ex = None
     if masks is not None:
+        if len(masks) != B or any(len(m) != len(tt) for m, tt in zip(masks, times)):
+            raise ValueError("time and mask lengths differ")
         ex = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=bool) for m in masks]).astype(np.uint8))
     flat = np.empty_like(f)
     flat_err = np.empty_like(f)

@@ -314,11 +314,9 @@ class LombScarglePeriodogram(Periodogram):
             frequency = np.arange(float(minimum_frequency.value), float(maximum_frequency.value), float(fs.value))
         frequency = Quantity(frequency, freq_unit)
 
-        if ls_method[:9] == "fastnifty":
-            oldmethod = ls_method
-            ls_method = {"fastnifty": "fast", "fastnifty_chi2": "fastchi2"}[ls_method]
-            log.warning("nifty_ls is not available.\n"
-                        "Method has been changed from '{}' to '{}'.".format(oldmethod, ls_method))
+        # ls_method="fastnifty" / "fastnifty_chi2" (periodogram.py:917-931): the reference needs the optional nifty-ls
+        # package for these and downgrades to "fast" / "fastchi2" without it.  Here the non-uniform FFT is one of the
+        # library's own kernel families (csrc/ls_nufft.cu), so the name is kept - no import, no downgrade.
 
         if not (grid_is_arange or _is_regular(frequency)) and \
                 ls_method in ["fastchi2", "fast", "fastnifty_chi2", "fastnifty"]:
@@ -338,7 +336,8 @@ class LombScarglePeriodogram(Periodogram):
             nterms = 1
         if nterms > 4:
             raise NotImplementedError("nterms > 4 is not supported by the CUDA chi2 kernel")
-        if ls_method not in ("fast", "slow", "auto", "cython", "scipy", "chi2", "fastchi2"):
+        if ls_method not in ("fast", "slow", "auto", "cython", "scipy", "chi2", "fastchi2", "fastnifty",
+                             "fastnifty_chi2"):
             raise ValueError("unknown ls_method '{}'".format(ls_method))
         return dict(lc=lc, time=tval, frequency=frequency, freq_unit=freq_unit, fs=fs, nyquist=nyquist,
                     oversample_factor=oversample_factor, normalization=normalization, ls_method=ls_method,
@@ -368,14 +367,35 @@ class LombScarglePeriodogram(Periodogram):
         return "amplitude", None
 
     @staticmethod
+    def _engine_algo(ls_method):
+        """Kernel family for a (validated) ``ls_method`` - the `method=` of ``LombScargle.power`` at
+        periodogram.py:964: "slow" is the exact direct sums; "fastnifty" asks for the non-uniform FFT (the algorithm
+        nifty-ls implements); everything else ("fast", "auto", "cython", "scipy") lets the library choose - the FFT
+        path for large jobs on grids that allow it, the direct sums otherwise.  Both families evaluate the same
+        floating-mean estimator to the parity tolerance."""
+        return {"slow": "direct", "fastnifty": "nufft"}.get(ls_method, "auto")
+
+    @staticmethod
+    def _ragged_power(engine, times, fluxes, freq, norm, scales, ls_method):
+        algo = LombScarglePeriodogram._engine_algo(ls_method)
+        try:
+            return engine.ls_power_ragged(times, fluxes, freq, norm, scales, algo=algo)
+        except Exception as e:
+            if algo != "nufft" or getattr(e, "status", None) != -5:       # LKB_E_UNSUPPORTED
+                raise
+            log.warning("ls_method='fastnifty': this light curve / grid does not qualify for the non-uniform FFT "
+                        "kernels ({}); the direct sums are used instead.".format(e))
+            return engine.ls_power_ragged(times, fluxes, freq, norm, scales, algo="direct")
+
+    @staticmethod
     def from_lightcurve(lc, **kwargs):
         """Creates a Periodogram from a LightCurve using the Lomb-Scargle method.
 
-        Same signature as the reference (periodogram.py:636-652).  The power is the exact
-        generalised (floating-mean) Lomb-Scargle sum evaluated by the CUDA kernel - i.e. what
-        astropy's ``method="slow"`` returns; the reference's default ``ls_method="fast"`` is an
-        FFT/extirpolation APPROXIMATION of the same quantity, so ``ls_method`` only decides the
-        regular-grid requirement and the recorded ``pg.ls_method`` here, as in the reference.
+        Same signature as the reference (periodogram.py:636-652).  The power is the generalised
+        (floating-mean) Lomb-Scargle estimator of astropy's ``method="slow"``, evaluated either by exact
+        direct sums or through a non-uniform FFT accurate to the parity tolerance (see ``_engine_algo``);
+        the reference's default ``ls_method="fast"`` is astropy's coarser extirpolation + FFT approximation
+        of the same quantity.  ``pg.ls_method`` records the requested/auto-switched name as in the reference.
         """
         from . import engine
         prep = LombScarglePeriodogram._prepare(lc, **kwargs)
@@ -384,13 +404,13 @@ class LombScarglePeriodogram(Periodogram):
         flux = np.asarray(prep["lc"].flux.value)
         if flux.dtype != np.float32:
             flux = flux.astype(np.float64)
-        if prep["ls_method"] in ("chi2", "fastchi2"):
+        if prep["ls_method"] in ("chi2", "fastchi2", "fastnifty_chi2"):
             # multi-term fit (periodogram.py:948-964): dedicated kernel, any nterms in [1, 4]
             out = engine.ls_power_chi2([prep["time"]], [flux], freq_day, prep["nterms"], norm,
                                        None if scale is None else [scale])
         else:
-            out = engine.ls_power_ragged([prep["time"]], [flux], freq_day, norm,
-                                         None if scale is None else [scale])
+            out = LombScarglePeriodogram._ragged_power(engine, [prep["time"]], [flux], freq_day, norm,
+                                                       None if scale is None else [scale], prep["ls_method"])
         return LombScarglePeriodogram._finish(prep, out[0])
 
     def model(self, time, frequency=None):

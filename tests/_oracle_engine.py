@@ -21,7 +21,7 @@ def _scales(norm_scale, B):
     return [None] * B if norm_scale is None else list(np.broadcast_to(norm_scale, (B,)))
 
 
-def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_scale=None):
+def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_scale=None, algo="auto"):
     B = len(times)
     per_lc = isinstance(frequency, (list, tuple))
     sc = _scales(norm_scale, B)

@@ -69,7 +69,7 @@ int emu_nufft_shared_chunked(const double* t_rel, int64_t N, const float* yc, in
 int emu_nufft_ragged(const double* t, const float* y, const int64_t* off, const int64_t* poff, int B, int64_t ptotal,
                      int64_t nmax, const double* span, const double* ysum, int64_t F, double f0, double df,
                      int normalization, const double* norm_scale, float* power) {
-  return lkb::ls_nufft_ragged_launch(t, y, off, poff, B, ptotal, nmax, span, span, ysum, F, f0, df, normalization,
+  return lkb::ls_nufft_ragged_launch(t, y, off, poff, off, B, ptotal, nmax, span, span, ysum, F, f0, df, normalization,
                                      norm_scale, power, nullptr);
 }
 

@@ -23,27 +23,51 @@ def engine():
     return eng
 
 
+_C2 = {}
+
+
+def _c2_workload():
+    if not _C2:
+        from bench import make_workload
+        _C2["w"] = make_workload("c2", 1002)
+    return _C2["w"]
+
+
+def _oracle_amplitude(t, y32, freq_bins):
+    """lightkurve's amplitude spectrum from the exact fp64 floating-mean sums (oracle) at the given bins."""
+    return np.sqrt(ols.ls_slow_psd(t, y32.astype(np.float64), freq_bins)) * np.sqrt(4.0 / len(t))
+
+
 def test_config2_full_size_lombscargle(engine):
-    """1024 light curves x 65 000 cadences x 1e5 frequencies (bench.py workload): the whole tensor-core call."""
-    from bench import make_workload
-    t, Y, freq = make_workload("c2", 1002)
+    """1024 light curves x 65 000 cadences x 1e5 frequencies (bench.py workload) through the default (`auto`) path."""
+    t, Y, freq = _c2_workload()
     B, N = Y.shape
     F = len(freq)
     assert (B, N, F) == (1024, 65000, 100000)
     out = engine.ls_power_shared(t, Y, freq, "amplitude")
     assert out.shape == (B, F) and np.isfinite(out).all()
     rng = np.random.default_rng(7)
-    # (a) spot check against the exact fp64 sums: 4 light curves x 150 random bins (+ the lowest and highest bins)
+    # (a) spot check against the exact fp64 sums: 4 light curves x 150 random bins (+ the lowest and highest bins),
+    # at the stated tolerance (DESIGN.md section 2) - 1x, no slack
     for b in rng.choice(B, 4, replace=False):
         bins = np.unique(np.concatenate([rng.choice(F, 150, replace=False), [0, 1, 2, F - 1]]))
-        ref = np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq[bins])) * np.sqrt(4.0 / N)
+        ref = _oracle_amplitude(t, Y[b], freq[bins])
         pmax = float(out[b].max())
         tol = 1e-5 * max(pmax, ref.max()) + 1e-4 * ref                     # amplitude spectrum: same form as the psd bound
-        assert np.all(np.abs(out[b][bins] - ref) <= 2 * tol), (b, np.max(np.abs(out[b][bins] - ref) / tol))
-    # (c) batch-permutation invariance: every light curve's spectrum is independent of its neighbours (bitwise)
-    perm = rng.permutation(B)
+        assert np.all(np.abs(out[b][bins] - ref) <= tol), (b, np.max(np.abs(out[b][bins] - ref) / tol))
+    # (c) batch-permutation invariance.  The default path packs light curves (2j, 2j+1) into one complex transform,
+    # so a light curve's rounding depends on its pair partner: permuting PAIRS as blocks must be bitwise neutral,
+    # an arbitrary permutation neutral to a fraction of the tolerance.
+    pair_perm = rng.permutation(B // 2)
+    perm = np.stack([2 * pair_perm, 2 * pair_perm + 1], axis=1).ravel()
     out_p = engine.ls_power_shared(t, np.ascontiguousarray(Y[perm]), freq, "amplitude")
     assert np.array_equal(out_p, out[perm])
+    perm = rng.permutation(B)
+    out_p = engine.ls_power_shared(t, np.ascontiguousarray(Y[perm]), freq, "amplitude")
+    ref_p = out[perm]
+    tol_p = 1e-5 * ref_p.max(axis=1, keepdims=True) + 1e-4 * ref_p
+    assert np.all(np.abs(out_p - ref_p) <= 0.5 * tol_p)
+    del out_p, ref_p, tol_p
     # (d) the amplitude spectrum is linear in the flux about its mean: y -> 1 + 4 (y - 1) is EXACT in fp32 for these
     # fluxes (|y - 1| << 1), so every bin must scale by 4 up to the kernel's own tolerance
     sub = rng.choice(B, 256, replace=False)
@@ -53,6 +77,61 @@ def test_config2_full_size_lombscargle(engine):
     o4 = engine.ls_power_shared(t, Y4, freq[:20000], "amplitude")
     big = o1 > 2e-2 * o1.max(axis=1, keepdims=True)
     np.testing.assert_allclose(o4[big], 4.0 * o1[big], rtol=5e-3)
+
+
+def worst_bin_excess(engine, t, Y, freq, algos, n_worst=2000, n_random=1000, seed=11, env=None):
+    """Runs every kernel family of `algos` on the whole workload, takes the `n_worst` (light curve, bin) pairs where
+    the families disagree most (in units of the tolerance) plus `n_random` random pairs, evaluates the fp64 oracle on
+    exactly those pairs and returns {algo: worst |P - oracle| / tol over the pairs}, the pairs, and the per-pair
+    excesses.  (tools/worst_bins.py prints the same for kernel variants.)"""
+    import os
+    outs = {}
+    for a in algos:
+        saved = {}
+        for k, v in (env or {}).get(a, {}).items():
+            saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        try:
+            outs[a] = engine.ls_power_shared(t, Y, freq, "amplitude", algo=a.split(":")[0])
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    B, F = outs[algos[0]].shape
+    base = outs[algos[0]]
+    tol = 1e-5 * base.max(axis=1, keepdims=True) + 1e-4 * base
+    picks = []
+    for a in algos[1:]:
+        d = np.abs(outs[a] - base) / tol
+        flat = np.argpartition(d.ravel(), -n_worst)[-n_worst:]
+        picks.append(flat)
+        del d
+    rng = np.random.default_rng(seed)
+    picks.append(rng.choice(B * F, n_random, replace=False))
+    flat = np.unique(np.concatenate(picks))
+    bb, kk = np.unravel_index(flat, (B, F))
+    ref = np.empty(len(flat))
+    for b in np.unique(bb):
+        sel = bb == b
+        ref[sel] = _oracle_amplitude(t, Y[b], freq[kk[sel]])
+    pmax = base.max(axis=1)[bb]
+    tol_ref = 1e-5 * np.maximum(pmax, ref) + 1e-4 * ref
+    excess = {a: np.abs(outs[a][bb, kk] - ref) / tol_ref for a in algos}
+    return {a: float(e.max()) for a, e in excess.items()}, (bb, kk), excess
+
+
+def test_config2_worst_bins(engine):
+    """The judge's round-1 finding: at the full config-2 size the NUFFT and tcgen05 families disagreed by 2.7x the
+    tolerance somewhere in the 1e8 bins while both passed random spot checks.  Here every family runs the whole
+    workload, the worst-disagreeing (light curve, bin) pairs are taken to the fp64 oracle, and EACH family must
+    be within 1x the stated tolerance there."""
+    t, Y, freq = _c2_workload()
+    worst, (bb, kk), _ = worst_bin_excess(engine, t, Y, freq, ["nufft", "tcgen05", "simt"])
+    print("config-2 worst-bin excess over the tolerance:", worst, "pairs checked:", len(bb))
+    for a, e in worst.items():
+        assert e <= 1.0, (a, e)
 
 
 def test_config3_shape_bls(engine):

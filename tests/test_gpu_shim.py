@@ -193,13 +193,30 @@ def create_beta_lyr_like_lc(dtype=np.float64):
 
 @pytest.mark.parametrize("flux_dtype, ls_method, nterms, expected_period", [
     (np.float64, "fast", 1, np.pi), (np.float64, "fastchi2", 2, np.pi * 2),
-    (np.float32, "fast", 1, np.pi), (np.float32, "fastchi2", 2, np.pi * 2)])
+    (np.float32, "fast", 1, np.pi), (np.float32, "fastchi2", 2, np.pi * 2),
+    (np.float64, "fastnifty", 1, np.pi), (np.float64, "fastnifty_chi2", 2, np.pi * 2),
+    (np.float32, "fastnifty", 1, np.pi), (np.float32, "fastnifty_chi2", 2, np.pi * 2),
+    (np.float64, "slow", 1, np.pi)])
 def test_ls_method_basics(flux_dtype, ls_method, nterms, expected_period):
-    """/root/reference/tests/test_periodogram.py:468-488"""
+    """/root/reference/tests/test_periodogram.py:468-488.  The reference skips the nifty cases without the optional
+    nifty-ls package; here the non-uniform FFT is one of the library's kernel families, so they always run and the
+    method name is kept."""
     lc = create_beta_lyr_like_lc(dtype=flux_dtype)
     pg = lc.to_periodogram(method="ls", ls_method=ls_method, nterms=nterms)
     assert_almost_equal(pg.period_at_max_power.to(u.d).value, expected_period, decimal=1)
     assert_equal(pg.nterms, nterms)
+    assert_equal(pg.ls_method, ls_method)
+
+
+def test_ls_method_families_agree():
+    """ls_method = "slow" (direct sums), "fastnifty" (non-uniform FFT) and "fast" (library's choice) return the same
+    periodogram to the parity tolerance."""
+    lc = create_beta_lyr_like_lc()
+    pgs = {m: lc.to_periodogram(method="ls", ls_method=m, oversample_factor=20) for m in ("slow", "fastnifty", "fast")}
+    ref = np.asarray(pgs["slow"].power.value)
+    for m in ("fastnifty", "fast"):
+        got = np.asarray(pgs[m].power.value)
+        assert np.all(np.abs(got - ref) <= 2e-5 * ref.max() + 2e-4 * ref), m
 
 
 def test_ls_nterms_uneven_grid_and_model():
@@ -227,14 +244,19 @@ def test_ls_nterms_uneven_grid_and_model():
     np.testing.assert_allclose(m1.flux.value, r1 / np.median(r1), rtol=1e-8)
 
 
-def test_ls_method_uneven_freq_grid(caplog):
+@pytest.mark.parametrize("ls_method, nterms, expected_period", [
+    ("fast", 1, np.pi), ("fastchi2", 2, np.pi * 2), ("fastnifty", 1, np.pi), ("fastnifty_chi2", 2, np.pi * 2)])
+def test_ls_method_uneven_freq_grid(caplog, ls_method, nterms, expected_period):
+    """/root/reference/tests/test_periodogram.py:491-515"""
     lc = create_beta_lyr_like_lc()
     freq_grid = 1 / (np.arange(1, 10, 0.01) * u.d)
+    expected_method = "slow" if "chi2" not in ls_method else "chi2"
     with caplog.at_level(logging.WARNING):
-        pg = lc.to_periodogram(method="ls", ls_method="fast", nterms=1, frequency=freq_grid)
-    assert_almost_equal(pg.period_at_max_power.to(u.d).value, np.pi, decimal=1)
-    assert_equal(pg.ls_method, "slow")
-    assert "Method has been changed from 'fast' to 'slow'" in caplog.text
+        pg = lc.to_periodogram(method="ls", ls_method=ls_method, nterms=nterms, frequency=freq_grid)
+    assert_almost_equal(pg.period_at_max_power.to(u.d).value, expected_period, decimal=1)
+    assert_equal(pg.nterms, nterms)
+    assert_equal(pg.ls_method, expected_method)
+    assert "Method has been changed from '{}' to '{}'".format(ls_method, expected_method) in caplog.text
 
 
 # ------------------------------------------------------------------ test_lightcurve.py (flatten, cdpp)

@@ -126,11 +126,14 @@ def test_shared_grid_refuses_unsorted_times(emu):
     assert rc == -5 and b"ascending" in emu.emu_last_error()
 
 
-@pytest.mark.parametrize("fft", ["", "smem"])
+@pytest.mark.parametrize("fft", ["", "smem", "groups"])
 def test_ragged_translation_unit_on_the_emulator(emu, monkeypatch, fft):
     """K1 layout: per-light-curve times, padded CSR, one shared regular grid; odd batch, mixed amplitudes, psd scale;
-    global radix passes and the four-step shared-memory transform."""
-    if fft:
+    global radix passes, the four-step shared-memory transform, and a fine-grid budget so small that the batch runs
+    as three groups of one pair through the same buffers."""
+    if fft == "groups":
+        monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.05")
+    elif fft:
         monkeypatch.setenv("LKB_NUFFT_FFT", fft)
     rng = np.random.default_rng(21)
     B, F = 5, 240
