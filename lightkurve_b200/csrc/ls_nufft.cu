@@ -195,6 +195,241 @@ nufft_fft_rows_kernel(float2* __restrict__ Z, int p, int pa, int tr) {
   }
 }
 
+// ---- "v2" transform (nufft_core.h): pruned spreading in the column kernel's layout, tiled column transforms with
+// table twiddles, row transforms fused with the finish.  Global traffic per pair of light curves at config 2
+// (M = 2^19): 0.5 MB flux + 0.84 MB G written + read, 4.2 MB T written + read, 0.8 MB power  = 11.4 MB
+// (the five global radix passes: 4.2 MB spread + 5 x 8.4 MB + 1.6 MB unpack reads + 0.8 MB = 48.6 MB).
+using nufft::V2_PB;
+using nufft::V2_THREADS;
+using nufft::V2_TILE;
+constexpr int V2_LOG_TILE = 13;
+static_assert((1 << V2_LOG_TILE) == V2_TILE, "tile size");
+
+__global__ void nufft2_tables_kernel(int pa, int pb, int p, float2* __restrict__ tw_a, float2* __restrict__ tw_b,
+                                     float2* __restrict__ t_hi, float2* __restrict__ t_lo) {
+  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(pb), pl = nufft::v2_log2_lo(p);
+  const int nlo = 1 << pl, nhi = 1 << (p - pl);
+  int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  int64_t num = 0, den = 1;
+  float2* dst = nullptr;
+  if (e < la) { nufft::v2_pass_table_entry(pa, e, &num, &den); dst = tw_a + e; }
+  else if ((e -= la) < lb) { nufft::v2_pass_table_entry(pb, e, &num, &den); dst = tw_b + e; }
+  else if ((e -= lb) < nhi) { num = e; den = nhi; dst = t_hi + e; }
+  else if ((e -= nhi) < nlo) { num = e; den = (int64_t)1 << p; dst = t_lo + e; }
+  else return;
+  double sn, cs;
+  sincospi(2.0 * (double)num / (double)den, &sn, &cs);
+  *dst = make_float2((float)cs, (float)sn);
+}
+
+// fine-grid cell m of position e of the G layout [c][n1][j]
+__device__ __forceinline__ int64_t v2_cell_of(int64_t e, int ptc, int n1max) {
+  const int64_t j = e & (((int64_t)1 << ptc) - 1), rest = e >> ptc;
+  const int64_t n1 = rest % n1max, c = rest / n1max;
+  return (n1 << V2_PB) + (c << ptc) + j;
+}
+
+// G[pair][e] for PP pairs of light curves per thread (the kernel weight of a (cell, cadence) is computed once and
+// applied to 2 PP light curves)
+template <int PP>
+__global__ void __launch_bounds__(256)
+nufft2_spread_kernel(const int32_t* __restrict__ first_ge, const Cad* __restrict__ cad, const float* __restrict__ y,
+                     int64_t ystride, const float* __restrict__ absmax, int B, int npairs, int w, float beta, int p,
+                     int ptc, int n1max, float2* __restrict__ G) {
+  const int64_t cells = (int64_t)n1max << V2_PB;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cells) return;
+  const int64_t M = (int64_t)1 << p, m = v2_cell_of(e, ptc, n1max);
+  const int pair0 = (int)blockIdx.y * PP;
+  const float* yr[2 * PP];
+#pragma unroll
+  for (int q = 0; q < 2 * PP; ++q) {
+    int b = 2 * pair0 + q;
+    if (b > B - 1) b = B - 1;                      // clamped rows are computed and dropped
+    yr[q] = y + (int64_t)b * ystride;
+  }
+  float acc[2 * PP];
+#pragma unroll
+  for (int q = 0; q < 2 * PP; ++q) acc[q] = 0.0f;
+  const float inv_half = 2.0f / (float)w;
+  const int64_t L = nufft::table_len(M, w);
+  for (int wrap = 0; wrap < 2; ++wrap) {           // wrap = 1: cadences whose support runs past cell M - 1
+    const int64_t mm = m + (int64_t)wrap * M;
+    if (mm + 1 >= L) break;
+    int64_t lo_c = mm - w + 1;
+    if (lo_c < 0) lo_c = 0;
+    const int32_t a = first_ge[lo_c], b = first_ge[mm + 1];
+    for (int32_t n = a; n < b; ++n) {
+      const Cad cd = cad[n];
+      const float ph = nufft::es_eval((cd.d0 + (float)(mm - (int64_t)cd.i0)) * inv_half, beta);
+#pragma unroll
+      for (int q = 0; q < 2 * PP; ++q) acc[q] = fmaf(ph, yr[q][n], acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PP; ++q) {
+    const int pair = pair0 + q;
+    if (pair >= npairs) break;
+    const int b0 = 2 * pair;
+    const float s0 = nufft::pow2_scale(absmax[b0]);
+    const float s1 = (b0 + 1 < B) ? nufft::pow2_scale(absmax[b0 + 1]) : 0.0f;
+    G[(int64_t)pair * cells + e] = make_float2(acc[2 * q] * s0, acc[2 * q + 1] * s1);
+  }
+}
+
+// one in-place pass of radix R over the lines of a tile (16 points per thread)
+template <int R>
+__device__ __forceinline__ void v2_pass(float2* buf, int plog, int lstride, int Ns, const float2* __restrict__ tw) {
+  constexpr int NB = 16 / R;
+  constexpr int LR = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
+  const int pnb = plog - LR, nb = 1 << pnb;            // butterflies per line
+  float2 u[NB][R];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int b = (int)threadIdx.x + V2_THREADS * q;
+    const int line = b >> pnb, i = b & (nb - 1);
+    const float2* x = buf + line * lstride;
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[q][r] = x[nufft::skew(i + r * nb)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int b = (int)threadIdx.x + V2_THREADS * q;
+    const int line = b >> pnb, i = b & (nb - 1), k = i & (Ns - 1);
+    float2* x = buf + line * lstride;
+    if (Ns > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) u[q][r] = nufft::cmul(u[q][r], tw[r * Ns + k]);
+    }
+    nufft::SmallDft<R>::run(u[q]);
+    const int j = ((i - k) << LR) + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[nufft::skew(j + r * Ns)] = u[q][r];
+  }
+  __syncthreads();
+}
+
+// all passes of the length-2^plog transforms of the tile's V2_TILE >> plog lines; tw: nufft::v2_pass_table_*
+__device__ __forceinline__ void v2_fft_lines(float2* buf, int plog, int lstride, const float2* __restrict__ tw) {
+  int Ns = 1;
+  for (int idx = 0;; ++idx) {
+    const int R = nufft::fft_pass_radix(plog, idx);
+    if (R == 0) break;
+    if (R == 16) v2_pass<16>(buf, plog, lstride, Ns, tw);
+    else if (R == 8) v2_pass<8>(buf, plog, lstride, Ns, tw);
+    else if (R == 4) v2_pass<4>(buf, plog, lstride, Ns, tw);
+    else v2_pass<2>(buf, plog, lstride, Ns, tw);
+    if (idx > 0) tw += R * Ns;
+    Ns *= R;
+  }
+}
+
+// step 1: grid (Bc / tc, npairs): tc columns n2 = c tc + j of one pair, length-A transforms over n1
+__global__ void __launch_bounds__(V2_THREADS, 2)
+nufft2_cols_kernel(const float2* __restrict__ G, float2* __restrict__ T, int p, int n1max,
+                   const float2* __restrict__ tw_a, const float2* __restrict__ t_hi, const float2* __restrict__ t_lo) {
+  LKB_DYN_SMEM(float2, buf);
+  const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa, tc = 1 << ptc, A = 1 << pa;
+  const int lstride = (int)nufft::smem_line(A);
+  const int c = (int)blockIdx.x, C = (1 << V2_PB) >> ptc;
+  const int64_t pair = blockIdx.y;
+  const int nvalid = n1max << ptc;
+  const float2* Gp = G + (pair * C + c) * (int64_t)nvalid;
+  for (int idx = (int)threadIdx.x; idx < V2_TILE; idx += V2_THREADS) {
+    const int n1 = idx >> ptc, j = idx & (tc - 1);
+    buf[j * lstride + (int)nufft::skew(n1)] = (idx < nvalid) ? Gp[idx] : make_float2(0.0f, 0.0f);
+  }
+  __syncthreads();
+  v2_fft_lines(buf, pa, lstride, tw_a);
+  float2* Tp = T + (pair * C + c) * (int64_t)V2_TILE;
+  const int pl = nufft::v2_log2_lo(p);
+  const int64_t Mmask = ((int64_t)1 << p) - 1;
+  for (int idx = (int)threadIdx.x; idx < V2_TILE; idx += V2_THREADS) {
+    const int k1 = idx >> ptc, j = idx & (tc - 1);
+    const int64_t q = ((int64_t)((c << ptc) + j) * k1) & Mmask;
+    const float2 wq = nufft::cmul(t_hi[q >> pl], t_lo[q & (((int64_t)1 << pl) - 1)]);
+    Tp[idx] = nufft::cmul(buf[j * lstride + (int)nufft::skew(k1)], wq);
+  }
+}
+
+struct V2Finish {
+  const float2* dec;
+  int64_t k0, F, k_lo;
+  const float4* rot;
+  const float2* rot2;
+  const float* ysum;
+  const float* absmax;
+  float Nf;
+  int normalization;
+  float scale;
+  int B;
+  float* power;
+};
+
+// step 2: grid (A / (2 R), npairs): rows k1 = 1 + g R .. (g + 1) R and their mirror rows, length-Bc transforms over n2;
+// FINISH: unpack / deconvolve / epilogue -> power; else the transform goes to Zout in the [k1][k2] layout
+// (nufft::fourstep_index).
+template <bool FINISH>
+__global__ void __launch_bounds__(V2_THREADS, 2)
+nufft2_rows_kernel(const float2* __restrict__ T, int p, const float2* __restrict__ tw_b, V2Finish fa,
+                   float2* __restrict__ Zout) {
+  LKB_DYN_SMEM(float2, buf);
+  constexpr int pb = V2_PB, Bc = 1 << pb, pR = V2_LOG_TILE - 1 - pb, R = 1 << pR;
+  const int pa = p - pb, A = 1 << pa, ptc = V2_LOG_TILE - pa, tc = 1 << ptc;
+  const int lstride = (int)nufft::smem_line(Bc);
+  const int g = (int)blockIdx.x;
+  const bool last = g == (A >> (pR + 1)) - 1;
+  const int64_t pair = blockIdx.y, M = (int64_t)1 << p;
+  auto slot_k1 = [&](int s) -> int {
+    const int h = s >> pR, r = s & (R - 1);
+    if (h == 0) return 1 + g * R + r;
+    if (last && r == 0) return 0;                    // instead of a second copy of row A / 2
+    return A - (g + 1) * R + r;
+  };
+  const float2* Tp = T + pair * M;
+  for (int e = (int)threadIdx.x; e < V2_TILE; e += V2_THREADS) {
+    const int j = e & (tc - 1), r = (e >> ptc) & (R - 1), h = (e >> (ptc + pR)) & 1, c = e >> (ptc + pR + 1);
+    const int s = h * R + r;
+    buf[s * lstride + (int)nufft::skew((c << ptc) + j)] = Tp[((((int64_t)c << pa) + slot_k1(s)) << ptc) + j];
+  }
+  __syncthreads();
+  v2_fft_lines(buf, pb, lstride, tw_b);
+  if (!FINISH) {
+    for (int e = (int)threadIdx.x; e < V2_TILE; e += V2_THREADS) {
+      const int s = e >> pb, k2 = e & (Bc - 1);
+      Zout[pair * M + ((int64_t)slot_k1(s) << pb) + k2] = buf[s * lstride + (int)nufft::skew(k2)];
+    }
+    return;
+  }
+  int64_t nK2 = ((fa.k0 + fa.F - 1) >> pa) + 1;
+  if (nK2 > Bc) nK2 = Bc;
+  const int64_t b0 = 2 * pair;
+  const bool has1 = b0 + 1 < fa.B;
+  const float inv0 = 1.0f / nufft::pow2_scale(fa.absmax[b0]);
+  const float inv1 = has1 ? 1.0f / nufft::pow2_scale(fa.absmax[b0 + 1]) : 1.0f;
+  const float ys0 = fa.ysum[b0], ys1 = has1 ? fa.ysum[b0 + 1] : 0.0f;
+  for (int item = (int)threadIdx.x; item < (int)nK2 * 2 * R; item += V2_THREADS) {
+    const int s = item & (2 * R - 1), k2 = item >> (pR + 1);
+    const int64_t jj = (int64_t)slot_k1(s) + ((int64_t)k2 << pa) - fa.k0;
+    if (jj < fa.k_lo || jj >= fa.F) continue;
+    const int h = s >> pR, r = s & (R - 1);
+    int ps = (1 - h) * R + (R - 1 - r), pi = Bc - 1 - k2;      // mode M - k: row A - k1, column Bc - 1 - k2
+    if (last && h == 0 && r == R - 1) ps = s;                  // row A / 2 mirrors onto itself
+    if (last && h == 1 && r == 0) { ps = s; pi = (Bc - k2) & (Bc - 1); }   // row 0: column Bc - k2
+    const float2 g1 = buf[s * lstride + (int)nufft::skew(k2)], g2 = buf[ps * lstride + (int)nufft::skew(pi)];
+    const float2 ra = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));      // (g1 + conj g2) / 2
+    const float2 rb = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));      // (g1 - conj g2) / 2i
+    const float2 dc = fa.dec[jj];
+    const float2 da = nufft::cmul(ra, dc), db = nufft::cmul(rb, dc);
+    const float4 rt = fa.rot[jj];
+    const float2 r2 = fa.rot2[jj];
+    fa.power[b0 * fa.F + jj] = ls_epilogue_shared(da.x * inv0, da.y * inv0, rt, r2, ys0, fa.Nf, fa.normalization, fa.scale);
+    if (has1)
+      fa.power[(b0 + 1) * fa.F + jj] = ls_epilogue_shared(db.x * inv1, db.y * inv1, rt, r2, ys1, fa.Nf, fa.normalization, fa.scale);
+  }
+}
+
 __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
                                     float2* __restrict__ dec) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,11 +594,66 @@ int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2*
 
 // LKB_NUFFT_FFT: "smem" = four-step transform in shared memory, "fused" = the same with the spreading done inside
 // the column kernel's load phase (the fine grids are written once, already half transformed)
-int fft_mode() {
+// "v2" (default where the fine grid allows it, 2^13 .. 2^22 cells) = the pruned, tiled transform with table twiddles
+// and the finish fused into the row kernel; "global" = one global sweep per radix pass.
+int fft_mode(int p = 0) {
   const char* e = getenv("LKB_NUFFT_FFT");
   if (e && strcmp(e, "smem") == 0) return 1;
   if (e && strcmp(e, "fused") == 0) return 2;
-  return 0;
+  if (e && strcmp(e, "global") == 0) return 0;
+  return (p >= nufft::V2_P_MIN && p <= nufft::V2_P_MAX) ? 3 : 0;
+}
+
+// twiddle tables of the v2 transform of 2^p cells in workspace slot `slot`
+struct V2Tables {
+  const float2 *tw_a, *tw_b, *t_hi, *t_lo;
+};
+int v2_tables(int p, int slot, cudaStream_t st, V2Tables* out) {
+  const int pa = p - V2_PB, pl = nufft::v2_log2_lo(p);
+  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(V2_PB), nhi = 1 << (p - pl), nlo = 1 << pl;
+  float2* base = nullptr;
+  LKB_TRY(ws_get_t<float2>(slot, (size_t)(la + lb + nhi + nlo + 4), &base));
+  float2 *tw_a = base, *tw_b = base + la, *t_hi = tw_b + lb, *t_lo = t_hi + nhi;
+  LKB_LAUNCH(blocks_for(la + lb + nhi + nlo, 256), 256, st, nufft2_tables_kernel)(pa, V2_PB, p, tw_a, tw_b, t_hi, t_lo);
+  LKB_LAUNCH_CHECK();
+  out->tw_a = tw_a; out->tw_b = tw_b; out->t_hi = t_hi; out->t_lo = t_lo;
+  return LKB_OK;
+}
+// rows of the [A][Bc] fine grid that cadences can reach when the last one's support starts at cell i0_last
+int v2_n1max(int p, int64_t i0_last, int w) {
+  const int64_t M = (int64_t)1 << p, A = M >> V2_PB;
+  const int64_t reach = i0_last + w + 1;                   // cells [0, reach) (a support running past M wraps to cell 0)
+  if (reach >= M) return (int)A;
+  const int64_t n = (reach + ((int64_t)1 << V2_PB) - 1) >> V2_PB;
+  return (int)(n < 1 ? 1 : (n > A ? A : n));
+}
+size_t v2_cols_smem(int p) {
+  const int pa = p - V2_PB;
+  return (size_t)(V2_TILE >> pa) * nufft::smem_line((int64_t)1 << pa) * sizeof(float2);
+}
+size_t v2_rows_smem() { return (size_t)(V2_TILE >> V2_PB) * nufft::smem_line((int64_t)1 << V2_PB) * sizeof(float2); }
+
+// G (pruned fine grids in the column layout) -> T (column transforms) for `npairs` transforms of 2^p cells
+int v2_cols(const float2* G, float2* T, int p, int n1max, int npairs, const V2Tables& tb, cudaStream_t st) {
+  const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa;
+  const size_t smem = v2_cols_smem(p);
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_LAUNCH_SMEM(dim3((unsigned)((1 << V2_PB) >> ptc), (unsigned)npairs), V2_THREADS, smem, st, nufft2_cols_kernel)(
+      G, T, p, n1max, tb.tw_a, tb.t_hi, tb.t_lo);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
+}
+// T -> power (fa != NULL) or -> Zout in the [k1][k2] layout
+int v2_rows(const float2* T, int p, int npairs, const V2Tables& tb, const V2Finish* fa, float2* Zout, cudaStream_t st) {
+  const int pa = p - V2_PB, groups = (1 << pa) >> (V2_LOG_TILE - V2_PB);          // A / (2 R)
+  const size_t smem = v2_rows_smem();
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((unsigned)groups, (unsigned)npairs);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<true>)(T, p, tb.tw_b, *fa, nullptr);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<false>)(T, p, tb.tw_b, V2Finish(), Zout);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
 }
 
 // in-place four-step transform of `npairs` length-2^p arrays; result in the [A][Bc] layout (pa returned).
@@ -424,6 +714,8 @@ struct NufftPlan {
   const Cad* cad;
   const int32_t* fge;
   const float2* dec;
+  int n1max;            // v2: rows of the [A][Bc] fine grid the cadences reach
+  V2Tables tb;          // v2: twiddle tables (valid when fft_mode(p) == 3)
 };
 static NufftPlan g_plan;
 
@@ -462,11 +754,18 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
   LKB_LAUNCH(blocks_for(N, 256), 256, st, nufft_cad_kernel)(d_t, N, grid_df, M2, w, cad2, flag);
   LKB_LAUNCH_CHECK();
   int h_flag = 0;
+  Cad h_last;
   LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_last, cad + (N - 1), sizeof(Cad), cudaMemcpyDeviceToHost, st));
   LKB_CUDA_CHECK(cudaStreamSynchronize(st));
   if (h_flag) {
     set_error("lkb_ls_power_shared: the NUFFT path needs ascending times");
     return LKB_E_UNSUPPORTED;
+  }
+  g_plan.n1max = 0;
+  if (fft_mode(p) == 3) {
+    g_plan.n1max = v2_n1max(p, (int64_t)h_last.i0, w);
+    LKB_TRY(v2_tables(p, WS_IN6, st, &g_plan.tb));
   }
   LKB_LAUNCH(blocks_for(L, 256), 256, st, nufft_first_ge_kernel)(cad, N, L, fge);
   LKB_LAUNCH_CHECK();
@@ -511,11 +810,16 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
   const float beta = pl.beta;
   const int64_t k0 = pl.k0, M = pl.M;
   const int npairs = (B + 1) / 2;
-  float2 *Za = nullptr, *Zb = nullptr;
-  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)npairs * M, &Za));
-  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, (size_t)npairs * M, &Zb));
+  const int mode = fft_mode(p);
   const char* ve = getenv("LKB_NUFFT_VERIFY");
   const bool verify = ve && atoi(ve) != 0 && F_low < F;
+  float2 *Za = nullptr, *Zb = nullptr;
+  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)npairs * M, &Za));
+  // second buffer: v2 keeps the pruned grids G there (n1max rows of Bc cells per pair; the self-check additionally
+  // needs room for a few whole transforms), the other variants a whole second set of fine grids
+  const size_t zb_count = (mode == 3) ? std::max((size_t)npairs * ((size_t)pl.n1max << V2_PB), verify ? (size_t)4 * M : (size_t)0)
+                                      : (size_t)npairs * M;
+  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, zb_count, &Zb));
   unsigned* d_worst = nullptr;
   if (verify) LKB_TRY(ws_get_t<unsigned>(ws_alt ? WS_OUT7 : WS_OUT6, 1, &d_worst));
 
@@ -537,7 +841,43 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
     const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
     float2* Za_g = Za + (size_t)g0 * M;
     float2* Zb_g = Zb + (size_t)g0 * M;
-    const int mode = fft_mode();
+    if (mode == 3) {
+      // spread (pruned, column layout) -> column transforms -> row transforms + finish
+      const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa;
+      const size_t cells = (size_t)pl.n1max << V2_PB;
+      // with L2-sized groups (LKB_NUFFT_GROUP_MB) every group goes through the SAME buffers, so that they stay in L2
+      float2* G_g = (group < npairs) ? Zb : Zb + (size_t)g0 * cells;
+      if (group < npairs) Za_g = Za;
+      const float* y_g = d_yc + (size_t)2 * g0 * ystride;
+      LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)((np_g + 3) / 4)), 256, st, nufft2_spread_kernel<4>)(
+          pl.fge, pl.cad, y_g, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, ptc, pl.n1max, G_g);
+      LKB_LAUNCH_CHECK();
+      LKB_TRY(v2_cols(G_g, Za_g, p, pl.n1max, np_g, pl.tb, st));
+      if (F_low < F) {
+        V2Finish fa;
+        fa.dec = pl.dec; fa.k0 = k0; fa.F = F; fa.k_lo = F_low; fa.rot = d_rot; fa.rot2 = d_rot2;
+        fa.ysum = d_ysumf + 2 * g0; fa.absmax = d_absmax + 2 * g0; fa.Nf = (float)N; fa.normalization = normalization;
+        fa.scale = (float)norm_scale; fa.B = B_g; fa.power = d_pow + (size_t)2 * g0 * F;
+        LKB_TRY(v2_rows(Za_g, p, np_g, pl.tb, &fa, nullptr, st));
+        if (verify && g0 == 0) {          // self-check: the first pairs' transforms once more, written out this time
+          const int np_v = std::min(np_g, 4), B_v = std::min(B_g, 2 * np_v);
+          LKB_TRY(v2_rows(Za_g, p, np_v, pl.tb, nullptr, Zb, st));     // G is no longer needed
+          const char* fe = getenv("LKB_NUFFT_INJECT_FAULT");
+          LKB_CUDA_CHECK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned), st));
+          LKB_LAUNCH(16, 128, st, nufft_verify_kernel)(Zb, p, pa, pl.dec, k0, F, F_low, d_t, N, d_yc, ystride, d_absmax,
+                                                     d_freq, B_v, fe ? (float)atof(fe) : 1.0f, d_worst);
+          LKB_LAUNCH_CHECK();
+          unsigned h_worst = 0;
+          LKB_CUDA_CHECK(cudaMemcpyAsync(&h_worst, d_worst, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+          LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+          if (h_worst > 100u) {
+            set_error("NUFFT self-check failed: transform deviates from the direct sums by %u x 1e-7 sum|y|", h_worst);
+            return LKB_E_VERIFY;
+          }
+        }
+      }
+      continue;
+    }
     if (mode != 2) {
       LKB_LAUNCH(blocks_for((int64_t)np_g * M, 256), 256, st, nufft_spread_kernel)(
           pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);

@@ -245,6 +245,54 @@ LKB_HD int fft_pass_radix(int p, int idx) {
   return 0;
 }
 
+// ---- "v2" four-step transform: pruned, tiled, table twiddles (ls_nufft.cu nufft2_* kernels) ---------------------
+// M = A * Bc with Bc = 2^V2_PB fixed and A = 2^pa, n = n1 Bc + n2, k = k1 + A k2 as above.  One CTA = V2_THREADS
+// threads working in place on V2_TILE = 16 * V2_THREADS points of shared memory: every radix-16 pass is exactly one
+// butterfly per thread (read 16 points, barrier, twiddle + DFT + write, barrier).
+//   * the spreading writes only the rows n1 < n1max that cadences can reach (df * baseline of the fine grid:
+//     20 % at lightkurve's default oversampling), in the layout the column kernel reads contiguously:
+//     G[pair][c][n1][j], c = n2 / tc, j = n2 % tc, tc = V2_TILE / A columns per CTA;
+//   * the column kernel (length-A transforms) writes T[pair][c][k1][j] - again one contiguous block per CTA;
+//   * the row kernel takes R = V2_TILE / (2 Bc) rows k1 = 1 + g R .. (g + 1) R together with their mirror rows
+//     A - k1 (mode k pairs with mode M - k when two real series share one complex transform), transforms them
+//     (length Bc) and finishes: unpack, deconvolve, epilogue -> power.  R consecutive k1 at one k2 are R consecutive
+//     frequency bins, so the power rows are written in R * 4-byte runs.  The transform itself never goes back to
+//     global memory.  The CTA that would hold row A / 2 twice takes row 0 (which pairs with itself) instead.
+// Twiddles come from tables built once per call in fp64 (no sincospif in the butterflies): per pass a table
+// [r][k] = exp(2 pi i r k / (Ns R)) (k fastest: consecutive lanes read consecutive entries), and for the inter-step
+// factor exp(2 pi i n2 k1 / M) a two-level table (hi * lo).
+constexpr int V2_THREADS = 512;
+constexpr int V2_TILE = 16 * V2_THREADS;        // 8192 points = 64 KB of float2
+constexpr int V2_PB = 9;                        // Bc = 512
+constexpr int V2_P_MIN = V2_PB + 4, V2_P_MAX = V2_PB + 13;      // 16 <= A <= 8192
+
+// entries of the pass tables of a length-2^q transform (the first pass has no twiddles and no table)
+LKB_HD int v2_pass_table_len(int q) {
+  int len = 0, Ns = 1;
+  for (int idx = 0;; ++idx) {
+    const int R = fft_pass_radix(q, idx);
+    if (R == 0) break;
+    if (idx > 0) len += R * Ns;
+    Ns *= R;
+  }
+  return len;
+}
+// entry e of those tables (e in [0, v2_pass_table_len(q))): exp(2 pi i r k / (Ns R)) as (num, den)
+LKB_HD void v2_pass_table_entry(int q, int e, int64_t* num, int64_t* den) {
+  int Ns = 1;
+  for (int idx = 0;; ++idx) {
+    const int R = fft_pass_radix(q, idx);
+    if (R == 0) break;
+    if (idx > 0) {
+      if (e < R * Ns) { *num = (int64_t)(e / Ns) * (e % Ns); *den = (int64_t)Ns * R; return; }
+      e -= R * Ns;
+    }
+    Ns *= R;
+  }
+  *num = 0; *den = 1;
+}
+LKB_HD int v2_log2_lo(int p) { return (p + 1) / 2; }          // the inter-step table splits q = hi 2^pl + lo
+
 // ---- unpacking --------------------------------------------------------------------------------------
 // Gauss-Legendre nodes and weights on [-1, 1] (Newton iteration on P_n; n <= 64)
 LKB_HD void gauss_legendre(int n, double* x, double* w) {

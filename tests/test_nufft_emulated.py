@@ -87,6 +87,11 @@ def _shared_inputs(seed, N, F, B, oversample=5.0, k0=1):
     (3, 5.0, 1, 2, 0, {"LKB_NUFFT_FFT": "smem"}),            # four-step transform in shared memory, one tile
     (3, 5.0, 2, 1, 2, {"LKB_NUFFT_FFT": "smem", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "F": "1100", "LKB_NUFFT_TILE": "1024"}),  # 8 tiles
     (5, 1.0, 1, 2, 0, {"LKB_NUFFT_FFT": "fused", "F": "1100", "LKB_NUFFT_TILE": "1024"}),        # spreading fused in
+    # the v2 transform (default from 2^13 fine-grid cells): pruned column layout, table twiddles, finish in the row kernel
+    (3, 5.0, 1, 2, 0, {"F": "1500"}),                        # 2^13 cells: A = 16, one column CTA, one row CTA (the "last")
+    (5, 5.0, 2, 1, 2, {"F": "3500"}),                        # 2^14: A = 32, two row CTAs; psd; chunks of 2; k0 = 2
+    (4, 1.0, 1, 2, 0, {"F": "6000", "LKB_NUFFT_VERIFY": "1"}),      # 2^15, oversample 1: no pruning, wrap-around; self-check
+    (3, 5.0, 1, 2, 0, {"F": "3500", "LKB_NUFFT_GROUP_MB": "0.2"}),  # groups of one pair through the same buffers
 ])
 def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, oversample, k0, normalization, chunk, env):
     env = dict(env)
@@ -112,6 +117,15 @@ def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, overs
             ref = p * scale
             ex = np.abs(power[b] - ref) / (2e-5 * ref.max() + 2e-4 * ref)
         assert ex.max() < 0.5, (b, int(np.argmax(ex)), ex.max())
+    if F >= 1500 and "LKB_NUFFT_FFT" not in env:      # the v2 transform really ran: the global passes round differently
+        monkeypatch.setenv("LKB_NUFFT_FFT", "global")
+        monkeypatch.delenv("LKB_NUFFT_VERIFY", raising=False)
+        power_g = np.zeros((B, F), np.float32)
+        args[-1] = power_g.ctypes.data
+        rc = emu.emu_nufft_shared_chunked(*args, chunk) if chunk else emu.emu_nufft_shared(*args)
+        assert rc == 0, emu.emu_last_error()
+        assert np.any(power_g != power)
+        np.testing.assert_allclose(power_g, power, rtol=3e-4, atol=1e-5 * float(power.max()))
 
 
 def test_shared_grid_refuses_unsorted_times(emu):
