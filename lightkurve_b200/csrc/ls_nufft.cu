@@ -368,12 +368,13 @@ struct V2Finish {
 };
 
 // step 2: grid (A / (2 R), npairs): rows k1 = 1 + g R .. (g + 1) R and their mirror rows, length-Bc transforms over n2;
-// FINISH: unpack / deconvolve / epilogue -> power; else the transform goes to Zout in the [k1][k2] layout
-// (nufft::fourstep_index).
-template <bool FINISH>
+// MODE 1: unpack / deconvolve / epilogue -> power;  MODE 0: the whole transform goes to Zout in the [k1][k2] layout
+// (nufft::fourstep_index);  MODE 2: the modes k < nk2_keep * A and their mirrors M - k go to Zout in NATURAL order
+// (what the ragged finish kernel reads; R consecutive k1 are R consecutive modes: 64-byte runs).
+template <int MODE>
 __global__ void __launch_bounds__(V2_THREADS, 2)
 nufft2_rows_kernel(const float2* __restrict__ T, int p, const float2* __restrict__ tw_b, V2Finish fa,
-                   float2* __restrict__ Zout) {
+                   float2* __restrict__ Zout, int nk2_keep) {
   LKB_DYN_SMEM(float2, buf);
   constexpr int pb = V2_PB, Bc = 1 << pb, pR = V2_LOG_TILE - 1 - pb, R = 1 << pR;
   const int pa = p - pb, A = 1 << pa, ptc = V2_LOG_TILE - pa, tc = 1 << ptc;
@@ -395,10 +396,19 @@ nufft2_rows_kernel(const float2* __restrict__ T, int p, const float2* __restrict
   }
   __syncthreads();
   v2_fft_lines(buf, pb, lstride, tw_b);
-  if (!FINISH) {
+  if (MODE == 0) {
     for (int e = (int)threadIdx.x; e < V2_TILE; e += V2_THREADS) {
       const int s = e >> pb, k2 = e & (Bc - 1);
       Zout[pair * M + ((int64_t)slot_k1(s) << pb) + k2] = buf[s * lstride + (int)nufft::skew(k2)];
+    }
+    return;
+  }
+  if (MODE == 2) {
+    const int keep = nk2_keep < Bc / 2 ? nk2_keep : Bc / 2;
+    for (int item = (int)threadIdx.x; item < 2 * keep * 2 * R; item += V2_THREADS) {
+      const int s = item & (2 * R - 1), q = item >> (pR + 1);
+      const int k2 = q < keep ? q : Bc - 2 * keep + q;          // [0, keep) and [Bc - keep, Bc)
+      Zout[pair * M + (int64_t)slot_k1(s) + ((int64_t)k2 << pa)] = buf[s * lstride + (int)nufft::skew(k2)];
     }
     return;
   }
@@ -643,15 +653,19 @@ int v2_cols(const float2* G, float2* T, int p, int n1max, int npairs, const V2Ta
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
-// T -> power (fa != NULL) or -> Zout in the [k1][k2] layout
-int v2_rows(const float2* T, int p, int npairs, const V2Tables& tb, const V2Finish* fa, float2* Zout, cudaStream_t st) {
+// T -> power (fa != NULL), -> Zout in the [k1][k2] layout (nk2_keep = 0), or -> Zout in natural order, modes
+// k < nk2_keep * A and their mirrors only (nk2_keep > 0)
+int v2_rows(const float2* T, int p, int npairs, const V2Tables& tb, const V2Finish* fa, float2* Zout, cudaStream_t st,
+            int nk2_keep = 0) {
   const int pa = p - V2_PB, groups = (1 << pa) >> (V2_LOG_TILE - V2_PB);          // A / (2 R)
   const size_t smem = v2_rows_smem();
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((unsigned)groups, (unsigned)npairs);
-  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<true>)(T, p, tb.tw_b, *fa, nullptr);
-  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<false>)(T, p, tb.tw_b, V2Finish(), Zout);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<1>)(T, p, tb.tw_b, *fa, nullptr, 0);
+  else if (nk2_keep > 0) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<2>)(T, p, tb.tw_b, V2Finish(), Zout, nk2_keep);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<0>)(T, p, tb.tw_b, V2Finish(), Zout, 0);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
@@ -1013,6 +1027,30 @@ nufft_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict_
   Z[gid] = v;
 }
 
+// v2: the same cell values in the column kernel's layout G[pair][c][n1][j], rows n1 < n1max only
+__global__ void __launch_bounds__(256)
+nufft2_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict__ y, const int64_t* __restrict__ off,
+                            const int64_t* __restrict__ poff, const float* __restrict__ absmax, int B, int npairs, int w,
+                            float beta, int p, int ptc, int n1max, float2* __restrict__ G) {
+  const int64_t cells = (int64_t)n1max << V2_PB;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cells) return;
+  const int64_t M = (int64_t)1 << p, m = v2_cell_of(e, ptc, n1max);
+  const int64_t pair = blockIdx.y, b0 = 2 * pair, b1 = b0 + 1;
+  float2 v = make_float2(0.f, 0.f);
+  {
+    const int64_t po = poff[b0], n = off[b0 + 1] - off[b0];
+    v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b0]) : 1.0f, w,
+                                    beta, M);
+  }
+  if (b1 < B) {
+    const int64_t po = poff[b1], n = off[b1 + 1] - off[b1];
+    v.y = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b1]) : 1.0f, w,
+                                    beta, M);
+  }
+  G[pair * cells + e] = v;
+}
+
 __device__ __forceinline__ float ragged_power(float2 hs, float2 win1, float2 win2, double Nd, double ysum,
                                               int normalization, double scale) {
   LsSums<double> d;
@@ -1128,6 +1166,21 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   GlNodes gl;
   nufft::gauss_legendre(32, gl.x, gl.w);
 
+  // v2 transform for both fine grids when they are in range: pruned to the rows the longest light curve reaches
+  const bool v2 = fft_mode(p) == 3 && fft_mode(p2) == 3;
+  int n1max = 0, n1max2 = 0;
+  V2Tables tb, tb2;
+  float2* Gbuf = nullptr;
+  if (v2) {
+    double span_max = 0.0;
+    for (int b = 0; b < B; ++b) span_max = fmax(span_max, h_span[b]);
+    n1max = v2_n1max(p, (int64_t)nufft::cad_entry(span_max, df, M, w).i0, w);
+    n1max2 = v2_n1max(p2, (int64_t)nufft::cad_entry(span_max, df, M2, w).i0, w);
+    LKB_TRY(v2_tables(p, WS_IN7, st, &tb));
+    LKB_TRY(v2_tables(p2, WS_OUT1, st, &tb2));
+    LKB_TRY(ws_get_t<float2>(WS_OUT2, (size_t)group * ((size_t)std::max(n1max, n1max2) << V2_PB), &Gbuf));
+  }
+
   Cad *cad = nullptr, *cad2 = nullptr;
   float2 *dec = nullptr, *dec2 = nullptr, *Za = nullptr, *Zb = nullptr, *Zw = nullptr;
   float* absmax = nullptr;
@@ -1171,12 +1224,31 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
     for (int b = b0; b < b0 + Bg; ++b) span_min = fmin(span_min, h_span[b]);
     const double nlow = floor((LS_LOWF_CYCLES / span_min - f0) / df) + 2.0;
     const int64_t F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
+    float2* Zw_out = nullptr;
+    float2* Zout = nullptr;
+    int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
+    if (v2) {
+      // window terms (unit strengths, 2x finer grid: modes kk and 2 kk), then the flux; the row kernels write the
+      // needed modes and their mirrors in natural order
+      const int nk2w = (int)((2 * (k0 + F)) >> (p2 - V2_PB)) + 1, nk2 = (int)((k0 + F) >> (p - V2_PB)) + 1;
+      const size_t cells2 = (size_t)n1max2 << V2_PB, cells = (size_t)n1max << V2_PB;
+      LKB_LAUNCH(dim3(blocks_for((int64_t)cells2, 256), (unsigned)npairs), 256, st, nufft2_spread_ragged_kernel)(
+          cad2, nullptr, off_g, po_g, amax_g, Bg, npairs, w, beta, p2, V2_LOG_TILE - (p2 - V2_PB), n1max2, Gbuf);
+      LKB_LAUNCH_CHECK();
+      LKB_TRY(v2_cols(Gbuf, Zw, p2, n1max2, npairs, tb2, st));
+      Zw_out = Zw + (size_t)npairs * M2;
+      LKB_TRY(v2_rows(Zw, p2, npairs, tb2, nullptr, Zw_out, st, nk2w));
+      LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)npairs), 256, st, nufft2_spread_ragged_kernel)(
+          cad, d_y, off_g, po_g, amax_g, Bg, npairs, w, beta, p, V2_LOG_TILE - (p - V2_PB), n1max, Gbuf);
+      LKB_LAUNCH_CHECK();
+      LKB_TRY(v2_cols(Gbuf, Za, p, n1max, npairs, tb, st));
+      Zout = Zb;
+      LKB_TRY(v2_rows(Za, p, npairs, tb, nullptr, Zout, st, nk2));
+    } else {
     // window terms: unit strengths on the 2x finer grid
     LKB_LAUNCH(blocks_for((int64_t)npairs * M2, 256), 256, st, nufft_spread_ragged_kernel)(cad2, nullptr, off_g, po_g, amax_g,
                                                                                     Bg, npairs, w, beta, p2, Zw);
     LKB_LAUNCH_CHECK();
-    float2* Zw_out = nullptr;
-    int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
     if (fft_mode() != 0) {
       LKB_TRY(fft_fourstep(Zw, p2, npairs, st, &pa2, nullptr));
       Zw_out = Zw;
@@ -1187,12 +1259,12 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
     LKB_LAUNCH(blocks_for((int64_t)npairs * M, 256), 256, st, nufft_spread_ragged_kernel)(cad, d_y, off_g, po_g, amax_g, Bg,
                                                                                    npairs, w, beta, p, Za);
     LKB_LAUNCH_CHECK();
-    float2* Zout = nullptr;
     if (fft_mode() != 0) {
       LKB_TRY(fft_fourstep(Za, p, npairs, st, &pa, nullptr));
       Zout = Za;
     } else {
       LKB_TRY(fft_passes(Za, Zb, p, npairs, st, &Zout));
+    }
     }
     LKB_LAUNCH(blocks_for(F * npairs, 256), 256, st, nufft_finish_ragged_kernel)(
         Zout, p, Zw_out, p2, dec, dec2, k0, F, f0, df, off_g, d_span + b0, d_ysum + b0, amax_g, normalization,

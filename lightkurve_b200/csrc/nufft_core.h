@@ -201,6 +201,7 @@ LKB_HD void twiddle_powers(float2 w1, float2* tw) {
 // Shared-memory arrays are addressed through skew(): one float2 of padding per 16 keeps the stride-R stores of the
 // first passes off a single bank (without it thread i writes word 2 (R i + r): one bank for the whole warp).
 LKB_HD int64_t skew(int64_t a) { return a + (a >> 4); }
+LKB_HD int skew(int a) { return a + (a >> 4); }             // (32-bit index math inside the shared-memory tiles)
 
 template <int R, bool CHAIN = false, bool SKEW = false>
 LKB_HD void fft_pass_butterfly(const float2* x, float2* y, int64_t i, int64_t Ns, int64_t M) {

@@ -140,17 +140,19 @@ def test_shared_grid_refuses_unsorted_times(emu):
     assert rc == -5 and b"ascending" in emu.emu_last_error()
 
 
-@pytest.mark.parametrize("fft", ["", "smem", "groups"])
+@pytest.mark.parametrize("fft", ["", "smem", "groups", "v2", "v2groups"])
 def test_ragged_translation_unit_on_the_emulator(emu, monkeypatch, fft):
     """K1 layout: per-light-curve times, padded CSR, one shared regular grid; odd batch, mixed amplitudes, psd scale;
     global radix passes, the four-step shared-memory transform, and a fine-grid budget so small that the batch runs
     as three groups of one pair through the same buffers."""
     if fft == "groups":
         monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.05")
-    elif fft:
+    elif fft == "v2groups":
+        monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.7")       # 2^13 + 2^14 cells: 0.375 MB per pair -> one pair per group
+    elif fft and fft != "v2":
         monkeypatch.setenv("LKB_NUFFT_FFT", fft)
     rng = np.random.default_rng(21)
-    B, F = 5, 240
+    B, F = 5, (1500 if fft.startswith("v2") else 240)        # 1500 bins: fine grids of 2^13 / 2^14 cells -> the v2 transform
     ns = [300, 77, 512, 150, 40]
     off = np.zeros(B + 1, np.int64)
     poff = np.zeros(B + 1, np.int64)
