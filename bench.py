@@ -43,8 +43,12 @@ UNIT = "bin*cadence/s"
 WORKLOADS = {
     # BASELINE.json configs[1]
     "c2": dict(B=1024, N=65000, F=100000, desc="1024 Kepler LC (65000 cadences, shared grid) x 1e5 frequencies"),
+    # BASELINE.json configs[4]: ragged collection sharded by target over the ranks (strong scaling), all-gather of power
+    "c5": dict(B=16384, F=20000, desc="16384 irregularly sampled LC (2000..20000 cadences) x 20000 frequencies, sharded by "
+                                      "target over the ranks, all-gather of the power rows"),
     # reduced shapes for debugging only (never the reported number)
     "c2_small": dict(B=256, N=8192, F=4096, desc="DEBUG 256 x 8192 x 4096"),
+    "c5_small": dict(B=512, F=20000, desc="DEBUG 512 ragged LC x 20000 frequencies"),
 }
 
 
@@ -329,6 +333,339 @@ def _bls_cpu_leg(t, fluxes, errs, period, duration, res, P, n_lc=4, budget_s=15.
         return {"cpu_baseline": {"error": repr(e)}}
 
 
+
+def make_c5_workload(seed, B=16384, F=20000, only=None):
+    """SURVEY.md 8(d) config C5 (BASELINE.json configs[4]): per light curve N_b ~ round(LogU(2000, 20000)) cadences of a
+    TESS-like 2-min grid over 27.8 d after a seeded random deletion, U(-20 s, 20 s) jitter (irregular: no shared grid);
+    flux = 1 + sinusoid + noise, fp32; one common regular frequency grid of F bins up to 50 / d (f0 = df).
+    `only` (index array): generate the flux of these light curves only (the others keep their times - the sharding
+    needs every length - and get a zero-length placeholder flux)."""
+    rng = np.random.default_rng(seed)
+    grid = 1325 + np.arange(int(27.8 * 720)) / 720.0
+    ns = np.minimum(len(grid), np.round(10 ** rng.uniform(np.log10(2000), np.log10(20000), B)).astype(int))
+    want = np.ones(B, bool) if only is None else np.isin(np.arange(B), only)
+    times, fluxes = [], []
+    for b in range(B):
+        r = np.random.default_rng([seed, b])
+        if not want[b]:
+            times.append(np.empty(int(ns[b]), dtype=np.float64))       # length only
+            fluxes.append(np.empty(0, dtype=np.float32))
+            continue
+        keep = np.sort(r.choice(len(grid), int(ns[b]), replace=False))
+        t = grid[keep] + r.uniform(-20, 20, int(ns[b])) / 86400.0
+        times.append(t)
+        fluxes.append((1 + 10 ** r.uniform(-4, -2) * np.sin(2 * np.pi * r.uniform(0.05, 20) * t + r.uniform(0, 6.28))
+                       + 10 ** r.uniform(np.log10(5e-5), -3) * r.standard_normal(int(ns[b]))).astype(np.float32))
+    freq = np.linspace(50.0 / F, 50.0, F)
+    return times, fluxes, freq
+
+
+def make_c4_workload(seed, B, N=65000, K=151):
+    """SURVEY.md 8(d) config C4 (BASELINE.json configs[3]): Kepler-like shared grid of N cadences; X = K - 1 orthonormalised
+    seeded random-walk "CBVs" + a constant column; flux = 1 + X w_b + slow trend + N(0, sigma) + 0.3 % outliers at
+    8 sigma; flux_err ~ sigma U(0.8, 1.2)."""
+    rng = np.random.default_rng(seed)
+    keep = np.sort(rng.choice(71500, N, replace=False))
+    tt = 131.5 + keep * 0.0204336
+    X = np.cumsum(rng.normal(size=(N, K - 1)), axis=0)
+    X, _ = np.linalg.qr(X - X.mean(0))
+    X = np.hstack([X * np.sqrt(N), np.ones((N, 1))])
+    W = rng.normal(size=(B, K)) * 1e-3
+    slow = np.cumsum(rng.normal(size=N)) * 1e-5
+    Y = np.empty((B, N))
+    FE = np.empty((B, N))
+    for b0 in range(0, B, 256):
+        nb = min(256, B - b0)
+        Y[b0:b0 + nb] = 1 + W[b0:b0 + nb] @ X.T + slow[None, :] + 3e-4 * rng.standard_normal((nb, N))
+        FE[b0:b0 + nb] = 3e-4 * rng.uniform(0.8, 1.2, (nb, N))
+    out = rng.integers(0, N, (B, N // 300))
+    Y[np.arange(B)[:, None], out] += 8 * 3e-4
+    return tt, X, Y, FE
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _max_over_ranks(torch, dist, world, dev, vals):
+    tm = torch.tensor([float(v) for v in vals], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    return [float(x) for x in tm.tolist()]
+
+
+def c5_step_stats(engine, torch, dist, rank, world, dev, times, fluxes, freq, steps, warmup, chunks=4):
+    """Device-resident sharded ragged Lomb-Scargle (lightkurve_b200.dist.ShardedLombScargle): per step compute of this
+    rank's shard + the pipelined all-gathers + restoring the target order.  Returns ms (device events, max over
+    ranks) for the resident step and for the end-to-end step (pinned H2D of the shard, the step, D2H of the whole
+    gathered power array on every rank)."""
+    from lightkurve_b200.dist import ShardedLombScargle
+    job = ShardedLombScargle(times, fluxes, freq, "amplitude", chunks=chunks, device=dev)
+    job.upload()
+    h_out = torch.empty((job.n_total, job.F), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(n):
+            fn()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1) / n
+
+    def step_e2e():
+        job.upload()
+        out = job.run()
+        h_out.copy_(out, non_blocking=True)
+
+    for _ in range(warmup):
+        job.run()
+    engine.profile_enable(True)
+    l0 = engine.launch_count()
+    ms_res = timed(job.run, steps)
+    launches = (engine.launch_count() - l0) // max(1, steps)
+    kms = engine.profile_read()
+    engine.profile_enable(False)
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(2, steps // 2))
+    k_ms = float(np.sum(kms)) / max(1, steps) if len(kms) else float("nan")      # all pieces of one step
+    ms_res, ms_e2e, k_ms = _max_over_ranks(torch, dist, world, dev, [ms_res, ms_e2e, k_ms])
+    mine = job.shards[rank]
+    return dict(ms=ms_res, ms_e2e=ms_e2e, kernel_ms=k_ms, launches=int(launches), family=engine.ls_last_algo(),
+                h2d=job.h2d_bytes, d2h=int(job.n_total) * job.F * 4, n_local=len(mine), job=job)
+
+
+def _ragged_cpu_leg(times, fluxes, freq, n_lc=48, budget_s=12.0):
+    """Reference default (astropy 'fast' restated in oracle/ls.py) on a sample of the ragged light curves, 1 core."""
+    from oracle import ls as ols
+    f0, df, nf = float(freq[0]), float(freq[1] - freq[0]), len(freq)
+    idx = [i for i in range(len(times)) if len(fluxes[i]) == len(times[i])][:n_lc]
+    t0 = time.perf_counter()
+    units = 0
+    done = 0
+    for i in idx:
+        ols.ls_fast_psd(times[i], fluxes[i].astype(np.float64), f0, df, nf)
+        units += nf * len(times[i])
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    secs = time.perf_counter() - t0
+    return {"value": units / secs, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d of the light curves (%.1f s), astropy method='fast' (lightkurve default) restated in oracle/ls.py, "
+                      "1 process; equivalent bin*cadence/s = F*sum(N)/time" % (done, secs)}
+
+
+def _ragged_roofline(F, units, k_ms, family, n_local, clocks_mhz=None):
+    """K1's bounds: the direct kernel is issue/MUFU-bound (2.3e12 units/s at 1965 MHz); the
+    NUFFT family is an HBM/L2 sweep of the fine grids."""
+    pk = _peaks()
+    hbm = float(pk.get("hbm_gbs", 6589.3))
+    if family == "nufft":
+        p = int(np.ceil(np.log2(4.0 * (1 + F))))
+        M, M2 = 2 ** p, 2 ** (p + 1)
+        npairs = (n_local + 1) // 2
+        # per pair: flux grid T written + read, pruned modes written + read (<= M / 2), the same on the 2x finer grid
+        nbytes = npairs * 8.0 * (2.5 * M + 2.5 * M2) + 4.0 * n_local * F
+        return {"bound": "hbm", "unit": "GB/s", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm,
+                "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel_ms": k_ms,
+                "kernel": "nufft2_spread_ragged + cols + rows (flux and window grids) + nufft_finish_ragged",
+                "note": "algorithmic bytes per pair of light curves: column transforms written + read and the kept modes "
+                        "written + read on the flux grid (2^%d cells) and the window grid (2^%d), + power; spread reads "
+                        "(cadence tables, flux) not counted" % (p, p + 1)}
+    ceil_units = 2.3e12
+    return {"bound": "issue", "unit": "bin*cadence/s", "achieved": units / (k_ms * 1e-3), "peak": ceil_units,
+            "frac": units / (k_ms * 1e-3) / ceil_units, "traffic": None, "kernel_ms": k_ms, "kernel": "ls_direct_kernel",
+            "note": "SURVEY 8(d) K1 ceiling: 2 MUFU + ~12 FMA-pipe slots per bin x cadence at 1965 MHz"}
+
+
+def secondary_ls_ragged(engine, torch, dist, rank, world, dev, steps=3, cpu_baseline=True):
+    """BASELINE.json configs[4] share: every rank takes 2048 of the ragged light curves (16384 / 8; at --gpus 8 this IS
+    config 5 with the all-gathers inside the step), F = 20000."""
+    B = 2048 * world
+    times, fluxes, freq = make_c5_workload(1005, B=B)
+    st = c5_step_stats(engine, torch, dist, rank, world, dev, times, fluxes, freq, steps, warmup=2)
+    units = float(len(freq)) * float(sum(len(t) for t in times))
+    mine = st["job"].shards[rank]
+    units_local = float(len(freq)) * float(sum(len(times[i]) for i in mine))
+    out = {"metric": METRIC, "unit": UNIT, "value": units / (st["ms"] * 1e-3), "ms_per_step": st["ms"], "steps": steps,
+           "n_gpus": world, "scaling": "weak", "dtype": "f32 spreading + FFT, f64 tables" if st["family"] == "nufft"
+           else "f32 sums flushed to f64, fixed-point phases",
+           "config": {"workload": "c5 share: %d ragged LC per GPU (2000..20000 cadences) x %d frequencies, sharded by "
+                                  "target, %d pipelined all-gather(s) of the power rows per step" %
+                                  (2048, len(freq), st["job"].chunks if world > 1 else 0), "kernel_family": st["family"]},
+           "e2e": {"value": units / (st["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": st["ms_e2e"],
+                   "h2d_bytes_per_step": st["h2d"] * world, "d2h_bytes_per_step": st["d2h"] * world},
+           "gpu_launches": st["launches"],
+           "roofline": _ragged_roofline(len(freq), units_local, st["kernel_ms"], st["family"], st["n_local"])}
+    if rank == 0 and cpu_baseline:
+        out["cpu_baseline"] = _ragged_cpu_leg(times, fluxes, freq)
+    return out
+
+
+def secondary_flatten(engine, torch, dist, rank, world, dev, cpu_baseline=True, B=4096):
+    """BASELINE.json configs[3], first half: LightCurve.flatten(window_length=401) of 4096 Kepler-length light curves
+    per GPU (weak scaling by target; no collective).  value = light curves / s from the library's CUDA events around
+    the flatten kernel; e2e = the host-buffer C-ABI call (page-locked in/out arrays: 6.4 GB up, 6.4 GB down)."""
+    N = 65000
+    tt, _, Y, FE = make_c4_workload(1004 + rank, B, N, K=3)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    t_cat = pin(np.tile(tt, B))
+    f_cat = pin(Y.reshape(-1))
+    fe_cat = pin(FE.reshape(-1))
+    offsets = np.arange(B + 1, dtype=np.int64) * N
+    outs = [pin(np.empty(B * N)) for _ in range(3)]
+    call = lambda: engine.flatten_csr(t_cat, f_cat, fe_cat, None, offsets, window_length=401, flat=outs[0],
+                                      flat_err=outs[1], trend=outs[2])
+    call()                                                                       # warm-up (workspace growth)
+    engine.profile_enable(True)
+    l0 = engine.launch_count()
+    t0 = time.perf_counter()
+    call()
+    wall = time.perf_counter() - t0
+    launches = engine.launch_count() - l0
+    kms = engine.profile_read()
+    engine.profile_enable(False)
+    k_ms, e2e_ms = _max_over_ranks(torch, dist, world, dev, [float(np.sum(kms)), 1e3 * wall])
+    hbm = float(_peaks().get("hbm_gbs", 6589.3))
+    nbytes = 63.0 * N * B
+    out = {"metric": "flatten_light_curves_per_s", "unit": "LC/s", "value": B * world / (k_ms * 1e-3), "ms_per_step": k_ms,
+           "steps": 1, "n_gpus": world, "scaling": "weak", "dtype": "f64",
+           "config": {"workload": "c4a: flatten(window_length=401, polyorder=2, niters=3, sigma=3) of %d LC x %d cadences "
+                                  "per GPU" % (B, N)},
+           "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "LC/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(3 * 8 * B * N) * world, "d2h_bytes_per_step": int(3 * 8 * B * N) * world},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm,
+                        "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None, "kernel_ms": k_ms,
+                        "note": "SURVEY 8(d) algorithmic bytes 63*N per light curve"}}
+    if rank == 0 and cpu_baseline:
+        from oracle import detrend as odet
+        n_lc, t0 = 0, time.perf_counter()
+        ok = True
+        while n_lc < 16 and time.perf_counter() - t0 < 12.0:
+            rf, _, rt = odet.flatten(tt, Y[n_lc], FE[n_lc], window_length=401)
+            ok = ok and bool(np.allclose(outs[2][n_lc * N:(n_lc + 1) * N], rt, rtol=1e-5, atol=0))
+            n_lc += 1
+        secs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_lc / secs, "unit": "LC/s", "cores": 1, "kind": "reference",
+                               "sample": "%d of the %d light curves (%.1f s): the reference's own flatten body on the real "
+                                         "scipy.signal.savgol_filter / scipy.interpolate.interp1d (oracle/detrend.py), "
+                                         "1 core" % (n_lc, B, secs)}
+        out["parity_on_sample"] = ok
+    return out
+
+
+def secondary_regress(engine, torch, dist, rank, world, dev, cpu_baseline=True, B=4096):
+    """BASELINE.json configs[3], second half: RegressionCorrector.correct (sigma = 5, niters = 5) of 4096 light curves
+    against one shared design matrix of 150 CBV-like regressors + constant (K = 151)."""
+    N, K = 65000, 151
+    tt, X, Y, FE = make_c4_workload(1004 + rank, B, N, K)
+    call = lambda: engine.regress(X, Y, FE, None, np.zeros(K), np.full(K, np.inf), sigma=5, niters=5)
+    engine.regress(X, Y[:64], FE[:64], None, np.zeros(K), np.full(K, np.inf), sigma=5, niters=5)      # warm-up
+    engine.profile_enable(True)
+    l0 = engine.launch_count()
+    t0 = time.perf_counter()
+    res = call()
+    wall = time.perf_counter() - t0
+    launches = engine.launch_count() - l0
+    kms = engine.profile_read()
+    engine.profile_enable(False)
+    k_ms, e2e_ms = _max_over_ranks(torch, dist, world, dev, [float(np.sum(kms)), 1e3 * wall])
+    pk = _peaks()
+    flops = float(B) * N * K * K                      # symmetric half of X^T W X, once (later iterations downdate)
+    out = {"metric": "regression_light_curves_per_s", "unit": "LC/s", "value": B * world / (e2e_ms * 1e-3),
+           "ms_per_step": e2e_ms, "steps": 1, "n_gpus": world, "scaling": "weak", "dtype": "f64 (DMMA Gram, LU)",
+           "config": {"workload": "c4b: RegressionCorrector.correct(sigma=5, niters=5), %d LC x %d cadences, shared "
+                                  "design matrix K = %d, per-cadence flux_err" % (B, N, K)},
+           "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "LC/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(8 * (2 * B * N + N * K)) * world,
+                   "d2h_bytes_per_step": int(8 * B * (N + K) + B * N) * world},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / (k_ms * 1e-3) / 1e12,
+                        "peak": 37.1, "frac": flops / (k_ms * 1e-3) / 1e12 / 37.1, "traffic": None, "kernel_ms": k_ms,
+                        "kernel": "rg_gram_mma (Gram matrices on the FP64 tensor cores)",
+                        "peak_source": "FP64 DMMA peak measured on this pool with tools/fp64_peak.cu (37.1 TFLOP/s); the "
+                                       "bf16 figure of MEASURED_PEAKS.json (%.0f) is SURVEY 8(d)'s bound for a "
+                                       "reduced-precision Gram" % float(pk.get("bf16_tflops_sustained", 1370.0)),
+                        "note": "algorithmic flops N*K^2 per light curve (first iteration; later ones downdate)"}}
+    if rank == 0 and cpu_baseline:
+        from oracle import detrend as odet
+        n_lc, t0 = 0, time.perf_counter()
+        ok = True
+        while n_lc < 8 and time.perf_counter() - t0 < 15.0:
+            ref = odet.regress(X, Y[n_lc], FE[n_lc], None, np.zeros(K), np.full(K, np.inf), sigma=5, niters=5)
+            ok = ok and bool(np.array_equal(res["outlier_mask"][n_lc], ref["outlier_mask"])) and \
+                bool(np.allclose(res["coefficients"][n_lc], ref["coefficients"], rtol=1e-6, atol=1e-9))
+            n_lc += 1
+        secs = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_lc / secs, "unit": "LC/s", "cores": _cores(), "kind": "reference",
+                               "sample": "%d of the %d light curves (%.1f s): the reference's correct() loop on the real "
+                                         "numpy.linalg.solve / BLAS (oracle/detrend.py), BLAS threads = all cores"
+                                         % (n_lc, B, secs)}
+        out["parity_on_sample"] = ok
+    return out
+
+
+def run_c5(args, engine, torch, dist, rank, world, local_rank, dev):
+    """--workload c5: BASELINE.json configs[4] as a STRONG-scaling job - the same 16384 light curves whatever the
+    number of ranks; every rank computes its shard and pipelined all-gathers reassemble [16384, 20000] everywhere."""
+    w = WORKLOADS[args.workload]
+    B, F = w["B"], w["F"]
+    lens_only = make_c5_workload(args.seed + 3, B=B, F=F, only=np.zeros(0, int))[0]
+    from lightkurve_b200.dist import shard_by_length
+    mine = shard_by_length([len(t) for t in lens_only], world)[rank]
+    times, fluxes, freq = make_c5_workload(args.seed + 3, B=B, F=F, only=mine)
+    for i in range(B):                       # the other ranks' light curves: lengths only (never uploaded here)
+        if len(fluxes[i]) != len(times[i]):
+            fluxes[i] = np.empty(len(times[i]), dtype=np.float32)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    st = c5_step_stats(engine, torch, dist, rank, world, dev, times, fluxes, freq, args.steps, args.warmup,
+                       chunks=args.chunks)
+    clocks = sampler.stop() if sampler else None
+    units = float(F) * float(sum(len(t) for t in times))
+    if rank != 0:
+        return
+    units_local = float(F) * float(sum(len(times[i]) for i in mine))
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = _ragged_cpu_leg([times[i] for i in mine], [fluxes[i] for i in mine], freq)
+    line = {"metric": METRIC, "value": units / (st["ms"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": st["ms"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 spreading + FFT, f64 tables" if st["family"] == "nufft" else "f32/f64 direct sums",
+            "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "light_curves": B, "frequencies": F,
+                       "cadences_total": int(sum(len(t) for t in times)), "normalization": "amplitude",
+                       "kernel_family": st["family"], "pieces": st["job"].chunks,
+                       "sharding": "by target (sorted by length, round-robin), %d rank(s); per step %d asynchronous "
+                                   "all-gather(s) of [%d x %d] fp32 blocks overlapped with the next piece's kernels" %
+                                   (world, st["job"].chunks if world > 1 else 0, world * (st["job"].bounds[0][1]), F),
+                       "l2": "the fine grids of one piece exceed the 126 MB L2"},
+            "e2e": {"value": units / (st["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": st["ms_e2e"],
+                    "h2d_bytes_per_step": st["h2d"] * world, "d2h_bytes_per_step": st["d2h"] * world,
+                    "note": "pinned H2D of every rank's shard, the step, D2H of the whole [B, F] power array on every rank"},
+            "gpu_launches": st["launches"],
+            "roofline": _ragged_roofline(F, units_local, st["kernel_ms"], st["family"], st["n_local"]),
+            "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
 def nufft_leg_child(args):
     """Child process of the `secondary.ls_nufft` leg: the opt-in NUFFT Lomb-Scargle path on the same
     configs[1] workload, device-resident, CUDA-event timed, with a parity check against the default path on a sample
@@ -409,7 +746,9 @@ def main():
                     help="nufft: the opt-in spread+FFT path (ls_nufft.cu); its roofline is the HBM one")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the BLS (configs[2]) leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary legs (BLS, flatten, regression, ragged LS)")
+    ap.add_argument("--legs", default="bls,flatten,regress,ls_ragged", help="comma list of secondary legs to run")
+    ap.add_argument("--chunks", type=int, default=4, help="c5: pieces per rank (one asynchronous all-gather each)")
     ap.add_argument("--nufft-leg", action="store_true", help=argparse.SUPPRESS)      # internal: child of secondary.ls_nufft
     ap.add_argument("--nufft-variants", action="store_true",
                     help="also time the NUFFT path's transform variants in a child process (secondary.ls_nufft)")
@@ -437,10 +776,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    dev = torch.device("cuda", local_rank)
+    if args.workload.startswith("c5"):
+        run_c5(args, engine, torch, dist, rank, world, local_rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     w = WORKLOADS[args.workload]
     B, N, F = w["B"], w["N"], w["F"]
     t, Y, freq = make_workload(args.workload, args.seed + rank)      # every rank: its own 1024 targets
-    dev = torch.device("cuda", local_rank)
     d_t = torch.tensor(t, device=dev)
     d_f = torch.tensor(freq, device=dev)
     d_Y = torch.tensor(Y, device=dev)
@@ -507,11 +851,16 @@ def main():
 
     secondary = None
     if not args.no_secondary and args.workload == "c2":
-        try:
-            secondary = {"bls": secondary_bls(engine, torch, dist, rank, world, dev,
-                                              cpu_baseline=not args.no_cpu_baseline)}
-        except Exception as e:                                    # the headline line must survive this leg
-            secondary = {"bls": {"error": repr(e)}}
+        secondary = {}
+        del d_Y, d_P, d_all, h_Y, h_P, h_Y_np, h_P_np               # the legs bring their own buffers
+        torch.cuda.empty_cache()
+        legs = {"bls": secondary_bls, "flatten": secondary_flatten, "regress": secondary_regress,
+                "ls_ragged": secondary_ls_ragged}
+        for name in [x for x in args.legs.split(",") if x]:
+            try:
+                secondary[name] = legs[name](engine, torch, dist, rank, world, dev, cpu_baseline=not args.no_cpu_baseline)
+            except Exception as e:                                # the headline line must survive every leg
+                secondary[name] = {"error": repr(e)}
         if world == 1 and rank == 0 and args.nufft_variants:
             secondary["ls_nufft"] = nufft_leg(args)
 

@@ -696,15 +696,23 @@ int ls_power_ragged(const double* t, const void* y, int y_dtype, const int64_t* 
   double *d_span = nullptr, *d_ysum = nullptr;
   if (s == LKB_OK) s = ws_get_t<double>(WS_F, B, &d_span);
   if (s == LKB_OK) s = ws_get_t<double>(WS_J, B, &d_ysum);
-  // Regular frequency grids?  Host-mode calls can tell from the host copy of `freq`
-  // (device-mode callers of the ragged entry keep the fp64 phase path).
-  bool regular = (mem == LKB_MEM_HOST) && !getenv("LKB_LS_FORCE_FP64_PHASE");
-  std::vector<double> h_f0(B, 0.0), h_df(B, 0.0);
+  // Regular frequency grids?  Decided on the host from `freq` (device-mode callers: one small read-back of the
+  // grid - it is what makes the fixed-point phases and the NUFFT path available to device-resident batches).
+  bool regular = !getenv("LKB_LS_FORCE_FP64_PHASE");
+  std::vector<double> h_f0(B, 0.0), h_df(B, 0.0), h_freq_copy;
+  const double* freq_h = freq;
+  if (regular && mem == LKB_MEM_DEVICE) {
+    h_freq_copy.resize((size_t)Ftot);
+    cudaError_t ce = cudaMemcpyAsync(h_freq_copy.data(), freq, sizeof(double) * (size_t)Ftot, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { free(h_po); set_error("frequency read-back failed: %s", cudaGetErrorString(ce)); return LKB_E_CUDA; }
+    freq_h = h_freq_copy.data();
+  }
   if (regular) {
     for (int b = 0; b < B && regular; ++b) {
       const int64_t fo = h_freq_offsets ? h_freq_offsets[b] : 0;
       const int64_t Fb = h_freq_offsets ? h_freq_offsets[b + 1] - fo : F;
-      const double* fq = freq + fo;
+      const double* fq = freq_h + fo;
       if (Fb < 2 || Fb >= ((int64_t)1 << 31)) { regular = false; break; }
       const double f0 = fq[0], df = fq[1] - fq[0];
       if (!(f0 >= 0.0) || !(df > 0.0)) { regular = false; break; }

@@ -9,7 +9,7 @@ inputs (frequency / period grids, a shared design matrix) are replicated.
 """
 import numpy as np
 
-__all__ = ["shard_by_length", "allgather_rows", "ls_power_sharded", "init_abi_communicator"]
+__all__ = ["shard_by_length", "allgather_rows", "ls_power_sharded", "init_abi_communicator", "ShardedLombScargle"]
 
 
 def shard_by_length(lengths, world_size):
@@ -92,3 +92,112 @@ def ls_power_sharded(times, fluxes, frequency, normalization="amplitude", norm_s
         device = torch.device("cuda", torch.cuda.current_device()) if via == "abi" or dist.get_backend(group) == "nccl" \
             else torch.device("cpu")
     return allgather_rows(torch.as_tensor(local, device=device), shards, len(times), group, via=via)
+
+
+class ShardedLombScargle:
+    """Device-resident, chunk-pipelined form of ``ls_power_sharded`` (BASELINE config 5: a ragged collection sharded
+    by target over the GPUs of one box, the power rows reassembled on every rank by all-gathers over NVLink).
+
+    ``ShardedLombScargle(times, fluxes, frequency, ...)`` deals the targets (sorted by length, round-robin), uploads
+    THIS rank's shard once (`upload()`; call it again to time the host->device copy) and splits it into `chunks`
+    pieces.  ``run()`` computes piece c on the current stream and hands its power block to an asynchronous
+    ``all_gather_into_tensor`` while piece c + 1 is being computed - the collective of all but the last piece is
+    hidden behind the kernels (gather per tile, overlapped).  Returns the [B, F] float32 CUDA
+    tensor in the ORIGINAL target order on every rank.  Nothing goes through the host inside ``run()``.
+
+    `compute(t_cat, y_cat, offsets, frequency, normalization, norm_scale, out)` can be injected (the gloo CPU test
+    uses the oracle on CPU tensors); the product default is ``engine.ls_power_ragged_device``."""
+
+    def __init__(self, times, fluxes, frequency, normalization="amplitude", norm_scale=None, chunks=4, device=None,
+                 group=None, compute=None, algo="auto"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        if device is None:
+            nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+            device = torch.device("cuda", torch.cuda.current_device()) if (nccl or torch.cuda.is_available()) \
+                else torch.device("cpu")
+        self.device = device
+        self.normalization, self.algo = normalization, algo
+        self.n_total = len(times)
+        self.F = len(frequency)
+        self.shards = shard_by_length([len(t) for t in times], self.world)
+        n_max = max(len(s) for s in self.shards)
+        self.chunks = max(1, min(int(chunks), n_max))
+        # piece c of every rank holds rows [lo_c, hi_c) of its (length-sorted) shard; pieces have the same row count
+        # on every rank (the last rows of a short shard are padding: zero power rows that are dropped again)
+        bounds = np.linspace(0, n_max, self.chunks + 1).round().astype(int)
+        self.bounds = [(int(bounds[c]), int(bounds[c + 1])) for c in range(self.chunks)]
+        mine = self.shards[self.rank]
+        self._host = []
+        for lo, hi in self.bounds:
+            ids = mine[lo:min(hi, len(mine))]
+            ts = [np.asarray(times[i], dtype=np.float64) for i in ids]
+            ydt = np.float32 if all(np.asarray(fluxes[i]).dtype == np.float32 for i in ids) else np.float64
+            ys = [np.asarray(fluxes[i], dtype=ydt) for i in ids]
+            off = np.zeros(len(ids) + 1, dtype=np.int64)
+            np.cumsum([len(t) for t in ts], out=off[1:])
+            ns = None if norm_scale is None else np.asarray([norm_scale[i] for i in ids], dtype=np.float64)
+            self._host.append(dict(t=np.concatenate(ts) if ts else np.zeros(0), y=np.concatenate(ys) if ys else
+                                   np.zeros(0, ydt), off=off, ns=ns, n=len(ids)))
+        self._freq_host = np.ascontiguousarray(frequency, dtype=np.float64)
+        if compute is None:
+            from . import engine
+            compute = lambda t, y, off, f, norm, ns, out: engine.ls_power_ragged_device(t, y, off, f, norm, ns,
+                                                                                        algo=self.algo, out=out)
+        self._compute = compute
+        self._pinned = None
+        self._dev = None
+        self._blocks = [torch.zeros((hi - lo, self.F), dtype=torch.float32, device=device) for lo, hi in self.bounds]
+        self._gathered = [torch.empty((self.world * (hi - lo), self.F), dtype=torch.float32, device=device)
+                          for lo, hi in self.bounds]
+        self._out = torch.empty((self.n_total, self.F), dtype=torch.float32, device=device)
+        # where the rows of every gathered piece go in the original order
+        self._dst = []
+        for lo, hi in self.bounds:
+            idx = np.full(self.world * (hi - lo), -1, dtype=np.int64)
+            for r, s in enumerate(self.shards):
+                ids = s[lo:min(hi, len(s))]
+                idx[r * (hi - lo): r * (hi - lo) + len(ids)] = ids
+            keep = np.flatnonzero(idx >= 0)
+            self._dst.append((torch.as_tensor(keep, device=device), torch.as_tensor(idx[keep], device=device)))
+
+    @property
+    def h2d_bytes(self):
+        return int(sum(h["t"].nbytes + h["y"].nbytes for h in self._host) + self._freq_host.nbytes)
+
+    def upload(self):
+        """Host -> device copy of this rank's shard (pinned staging on CUDA)."""
+        torch = self.torch
+        cuda = self.device.type == "cuda"
+        if self._pinned is None:
+            pin = (lambda a: torch.from_numpy(a).pin_memory()) if cuda else torch.from_numpy
+            self._pinned = [dict(t=pin(h["t"]), y=pin(h["y"]), ns=None if h["ns"] is None else pin(h["ns"]))
+                            for h in self._host]
+            self._pinned_f = pin(self._freq_host)
+        self._dev = [dict(t=p["t"].to(self.device, non_blocking=True), y=p["y"].to(self.device, non_blocking=True),
+                          ns=None if p["ns"] is None else p["ns"].to(self.device, non_blocking=True))
+                     for p in self._pinned]
+        self._dev_f = self._pinned_f.to(self.device, non_blocking=True)
+
+    def run(self):
+        if self._dev is None:
+            self.upload()
+        works = []
+        for c, (h, d) in enumerate(zip(self._host, self._dev)):
+            blk = self._blocks[c]
+            if h["n"]:
+                self._compute(d["t"], d["y"], h["off"], self._dev_f, self.normalization, d["ns"], blk[: h["n"]])
+            if self.world > 1:
+                works.append(self.dist.all_gather_into_tensor(self._gathered[c], blk, group=self.group, async_op=True))
+            else:
+                self._gathered[c] = blk
+        for w in works:
+            w.wait()
+        for c, (src, dst) in enumerate(self._dst):
+            self._out.index_copy_(0, dst, self._gathered[c].index_select(0, src))
+        return self._out

@@ -138,6 +138,46 @@ def ls_power_ragged(times, fluxes, frequency, normalization="amplitude", norm_sc
     return out
 
 
+def ls_power_ragged_device(t_cat, y_cat, offsets, frequency, normalization="amplitude", norm_scale=None, algo="auto",
+                           out=None):
+    """K1 with DEVICE-resident inputs: `t_cat` (float64) and `y_cat` (float32 / float64) are CUDA torch tensors
+    holding the light curves back to back, `offsets` the int64 [B + 1] CSR boundaries (host metadata, numpy),
+    `frequency` a CUDA float64 tensor [F] shared by all light curves, `norm_scale` None or a CUDA float64 [B].
+    Returns a CUDA float32 [B, F] tensor (`out` if given).  The kernels run on the current torch stream; the call
+    synchronises that stream for its metadata read-backs."""
+    import torch
+    lib = L.load()
+    if algo not in _RAGGED_ALGOS:
+        raise ValueError("algo must be one of %s" % sorted(_RAGGED_ALGOS))
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    B = len(offsets) - 1
+    if B <= 0:
+        raise ValueError("empty batch")
+    for name, x in (("t_cat", t_cat), ("y_cat", y_cat), ("frequency", frequency)):
+        if not (_is_torch(x) and x.is_cuda and x.is_contiguous() and x.dim() == 1):
+            raise ValueError("%s must be a contiguous one-dimensional CUDA tensor" % name)
+    if t_cat.dtype != torch.float64 or frequency.dtype != torch.float64:
+        raise TypeError("t_cat and frequency must be float64")
+    if y_cat.dtype not in (torch.float32, torch.float64):
+        raise TypeError("flux must be float32 or float64, not %s" % (y_cat.dtype,))
+    if offsets[0] != 0 or np.any(np.diff(offsets) < 0) or t_cat.numel() != offsets[-1] or y_cat.numel() != offsets[-1]:
+        raise ValueError("offsets do not describe t_cat / y_cat")
+    F = frequency.numel()
+    if out is None:
+        out = torch.empty((B, F), dtype=torch.float32, device=y_cat.device)
+    elif not (_is_torch(out) and out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (B, F)
+              and out.is_contiguous()):
+        raise ValueError("`out` must be a contiguous CUDA float32 tensor of shape (%d, %d)" % (B, F))
+    if norm_scale is not None and not (_is_torch(norm_scale) and norm_scale.is_cuda and
+                                       norm_scale.dtype == torch.float64 and norm_scale.numel() == B):
+        raise ValueError("norm_scale must be a CUDA float64 tensor with one entry per light curve")
+    ycode = L.DTYPE_F32 if y_cat.dtype == torch.float32 else L.DTYPE_F64
+    L.check(lib.lkb_ls_power_ex(L.ptr(t_cat), L.ptr(y_cat), ycode, L.ptr(offsets), B, L.ptr(frequency), None, F,
+                                _NORMS[normalization], L.ptr(norm_scale), L.ptr(out), L.MEM_DEVICE, _stream_ptr(),
+                                _RAGGED_ALGOS[algo]))
+    return out
+
+
 def ls_power_chi2(times, fluxes, frequency, nterms=1, normalization="amplitude", norm_scale=None,
                   return_theta=False):
     """K1n.  Multi-term periodogram (astropy method="chi2"/"fastchi2", nterms in [1, 4]); same
@@ -287,11 +327,42 @@ def bls_bin_index(t_rel, min_t, period, bin_duration):
 # --------------------------------------------------------------------------------------
 # flatten
 # --------------------------------------------------------------------------------------
+def flatten_csr(t, f, fe, exclude, offsets, window_length=101, polyorder=2, break_tolerance=5, niters=3, sigma=3,
+                flat=None, flat_err=None, trend=None):
+    """K4 on already concatenated host arrays (CSR `offsets` [B + 1]): `t`, `f`, `fe` (or None) float64 [total],
+    `exclude` uint8 [total] or None (1 = leave the cadence out of the fit).  Output arrays may be passed in (e.g.
+    page-locked buffers).  Returns (flat, flat_err, trend) float64 [total]."""
+    lib = L.load()
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    B = len(offsets) - 1
+    total = int(offsets[-1])
+    for name, a in (("t", t), ("f", f), ("fe", fe)):
+        if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == (total,)
+                                  and a.flags.c_contiguous):
+            raise ValueError("%s must be a C-contiguous float64 array of %d cadences" % (name, total))
+    if exclude is not None and not (isinstance(exclude, np.ndarray) and exclude.dtype == np.uint8
+                                    and exclude.shape == (total,) and exclude.flags.c_contiguous):
+        raise ValueError("exclude must be a C-contiguous uint8 array of %d cadences" % total)
+    outs = []
+    for name, a in (("flat", flat), ("flat_err", flat_err), ("trend", trend)):
+        if a is None:
+            a = np.empty(total, dtype=np.float64)
+        elif not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.shape == (total,) and a.flags.c_contiguous
+                  and a.flags.writeable):
+            raise ValueError("%s must be a writeable C-contiguous float64 array of %d cadences" % (name, total))
+        outs.append(a)
+    flat, flat_err, trend = outs
+    bt = np.nan if break_tolerance is None else float(break_tolerance)
+    L.check(lib.lkb_flatten(L.ptr(t), L.ptr(f), L.ptr(fe), L.ptr(exclude), L.ptr(offsets), B, int(window_length),
+                            int(polyorder), bt, int(niters), float(sigma), L.ptr(flat), L.ptr(flat_err),
+                            L.ptr(trend), L.MEM_HOST, None))
+    return flat, flat_err, trend
+
+
 def flatten(times, fluxes, flux_errs=None, masks=None, window_length=101, polyorder=2, break_tolerance=5,
             niters=3, sigma=3):
     """K4.  Lists of per-LC arrays.  `masks`: list of bool arrays, True = exclude (lightkurve
     semantics) or None.  Returns (flat, flat_err, trend) as lists of float64 arrays."""
-    lib = L.load()
     B = len(times)
     t, offsets = _csr(times)
     f, foff = _csr(fluxes)
@@ -307,13 +378,7 @@ def flatten(times, fluxes, flux_errs=None, masks=None, window_length=101, polyor
         if len(masks) != B or any(len(m) != len(tt) for m, tt in zip(masks, times)):
             raise ValueError("time and mask lengths differ")
         ex = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=bool) for m in masks]).astype(np.uint8))
-    flat = np.empty_like(f)
-    flat_err = np.empty_like(f)
-    trend = np.empty_like(f)
-    bt = np.nan if break_tolerance is None else float(break_tolerance)
-    L.check(lib.lkb_flatten(L.ptr(t), L.ptr(f), L.ptr(fe), L.ptr(ex), L.ptr(offsets), B, int(window_length),
-                            int(polyorder), bt, int(niters), float(sigma), L.ptr(flat), L.ptr(flat_err),
-                            L.ptr(trend), L.MEM_HOST, None))
+    flat, flat_err, trend = flatten_csr(t, f, fe, ex, offsets, window_length, polyorder, break_tolerance, niters, sigma)
     sp = lambda a: [a[offsets[b]:offsets[b + 1]] for b in range(B)]
     return sp(flat), sp(flat_err), sp(trend)
 
