@@ -793,10 +793,26 @@ def main():
     h_Y = torch.from_numpy(Y).pin_memory()
     h_P = torch.empty((B, F), dtype=torch.float32).pin_memory()
 
+    # N > 1: the rank's batch goes through the library in `pieces` calls on the same grid (the y-independent tables are
+    # built once and found cached by the later calls) and every piece's power rows are handed to an ASYNCHRONOUS
+    # all-gather while the next piece is computed; the gathered array is piece-major: [piece][rank][B / pieces, F]
+    pieces = max(1, min(args.chunks, B // 64)) if world > 1 else 1
+    pb_rows = B // pieces
+    assert pb_rows * pieces == B
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+
     def step_resident():
-        engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo=args.algo, out=d_P)
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_P)
+        if world == 1:
+            engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo=args.algo, out=d_P)
+            return
+        works = []
+        for c in range(pieces):
+            rows = slice(c * pb_rows, (c + 1) * pb_rows)
+            engine.ls_power_shared(d_t, d_Y[rows], d_f, "amplitude", algo=args.algo, out=d_P[rows])
+            works.append(dist.all_gather_into_tensor(d_all[c * world * pb_rows:(c + 1) * world * pb_rows], d_P[rows],
+                                                     async_op=True))
+        for wk in works:
+            wk.wait()
 
     h_Y_np, h_P_np = h_Y.numpy(), h_P.numpy()                 # numpy views of the page-locked buffers
 
@@ -806,10 +822,29 @@ def main():
             # down itself (chunk-pipelined over light-curve tiles, two copy streams) and returns synchronised
             engine.ls_power_shared(t, h_Y_np, freq, "amplitude", algo=args.algo, out=h_P_np)
             return
-        d_Y.copy_(h_Y, non_blocking=True)                     # H2D of this step's inputs (pinned)
-        engine.ls_power_shared(d_t, d_Y, d_f, "amplitude", algo=args.algo, out=d_P)
-        dist.all_gather_into_tensor(d_all, d_P)
-        h_P.copy_(d_P, non_blocking=True)                     # D2H of this step's result (pinned)
+        cur = torch.cuda.current_stream()
+        ev_in = []
+        s_h2d.wait_stream(cur)
+        with torch.cuda.stream(s_h2d):                        # H2D of this step's inputs (pinned), piece by piece
+            for c in range(pieces):
+                rows = slice(c * pb_rows, (c + 1) * pb_rows)
+                d_Y[rows].copy_(h_Y[rows], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_h2d)
+                ev_in.append(e)
+        works = []
+        for c in range(pieces):
+            rows = slice(c * pb_rows, (c + 1) * pb_rows)
+            cur.wait_event(ev_in[c])
+            engine.ls_power_shared(d_t, d_Y[rows], d_f, "amplitude", algo=args.algo, out=d_P[rows])
+            works.append(dist.all_gather_into_tensor(d_all[c * world * pb_rows:(c + 1) * world * pb_rows], d_P[rows],
+                                                     async_op=True))
+            s_d2h.wait_stream(cur)
+            with torch.cuda.stream(s_d2h):                    # D2H of this rank's result rows (pinned)
+                h_P[rows].copy_(d_P[rows], non_blocking=True)
+        for wk in works:
+            wk.wait()
+        cur.wait_stream(s_d2h)
 
     def barrier():
         if world > 1:
@@ -893,7 +928,24 @@ def main():
                     "kernel": "ls_tcg_kernel" if family == "tcgen05" else "ls_shared_simt_kernel", "kernel_ms": k_ms,
                     "peak_source": peak_src,
                     "note": "algorithmic flops 4*F*N*B; the split-fp16 scheme issues 3x that on the tensor pipe"}
-        if family == "nufft":
+        if family == "nufft" and not os.environ.get("LKB_NUFFT_FFT"):
+            # v2 transform (nufft_v2.cuh): per light curve the centred flux is read by the spreading, the pruned fine
+            # grid G (n1max rows of 512 complex cells) and the column transforms T (M / 2 complex points) are written
+            # once and read once, the power row is written once (DESIGN.md K2n byte model; tables are L2-resident)
+            pfine = int(np.ceil(np.log2(4.0 * (1 + F))))
+            Mh = 2 ** (pfine - 1)
+            reach = freq[0] * (t[-1] - t[0]) * 2 ** pfine + 16
+            n1max = int(np.ceil(np.ceil(reach / 2) / 512))
+            nbytes = B * (4.0 * N + 2 * 8.0 * n1max * 512 + 2 * 8.0 * Mh + 4.0 * F)
+            hbm = float(peaks.get("hbm_gbs", 6589.3))
+            roofline = {"bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                        "kernel": "nufft2_spread + nufft2_cols + nufft2_rows(finish) + nufft2_lowrows", "kernel_ms": k_ms,
+                        "bytes_per_launch": nbytes,
+                        "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                        "note": "algorithmic bytes per light curve = 4 N (flux) + 2 x 8 x %d (pruned grid, written + read) + "
+                                "2 x 8 x %d (column transforms, written + read) + 4 F (power)" % (n1max * 512, Mh)}
+        elif family == "nufft":
             # HBM sweep: fine grids [B/2, M] complex64 written once by the spreading, read + written by every Stockham
             # pass, two modes per output read by the finish kernel; flux read once, power written once
             # (DESIGN.md K2n).  k0 = 1 on the bench grid (f0 = df).
@@ -922,7 +974,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_per_gpu": B, "cadences": N,
                        "frequencies": F, "normalization": "amplitude", "algo": args.algo, "kernel_family": family,
-                       "sharding": "by target, %d rank(s), NCCL all-gather of power" % world,
+                       "sharding": "by target, %d rank(s), %s" % (world, "no collective" if world == 1 else
+                                   "%d asynchronous NCCL all-gathers of [%d x %d] power blocks per step, overlapped with the "
+                                   "next piece's kernels" % (pieces, world * pb_rows, F)),
                        "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % ((Y.nbytes + B * F * 4) / 1e6)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(Y.nbytes) * world,
                     "d2h_bytes_per_step": int(B * F * 4) * world, "ms_per_step": ms_e2e / args.steps},

@@ -29,7 +29,11 @@ struct Ctx {
 static Ctx g_ctx;
 static std::mutex g_mu;
 
+// every compute entry point passes through ensure_device() exactly once: the epoch tells a cached plan (the shared-grid
+// Lomb-Scargle keeps its y-independent tables in workspace slots) whether another entry point ran in between
+int64_t g_epoch = 0;
 int ensure_device() {
+  g_epoch++;
   if (g_ctx.inited) {
     cudaError_t e = cudaSetDevice(g_ctx.device);
     if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", g_ctx.device, cudaGetErrorString(e)); return LKB_E_CUDA; }
@@ -267,6 +271,7 @@ int lkb_shutdown(void) {
   for (int i = 0; i < 2; ++i)
     if (g_bounce[i]) { cudaFreeHost(g_bounce[i]); cudaEventDestroy(g_bounce_ev[i]); g_bounce[i] = nullptr; }
   g_ctx.inited = false;
+  g_epoch += 2;              // (nothing cached survives a shutdown)
   return LKB_OK;
 }
 

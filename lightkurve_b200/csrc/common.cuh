@@ -13,6 +13,7 @@ namespace lkb {
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;
 extern int g_last_ls_algo;
+extern int64_t g_epoch;
 
 #define LKB_CUDA_CHECK(expr)                                                        \
   do {                                                                              \
@@ -67,6 +68,7 @@ enum Slot {
   WS_A = 0, WS_B, WS_C, WS_D, WS_E, WS_F, WS_G, WS_H, WS_I, WS_J, WS_K, WS_L, WS_M, WS_N, WS_O, WS_P,
   WS_IN0, WS_IN1, WS_IN2, WS_IN3, WS_IN4, WS_IN5, WS_IN6, WS_IN7,
   WS_OUT0, WS_OUT1, WS_OUT2, WS_OUT3, WS_OUT4, WS_OUT5, WS_OUT6, WS_OUT7,
+  WS_X0, WS_X1, WS_X2, WS_X3, WS_X4, WS_X5, WS_X6, WS_X7,
   WS_NSLOTS
 };
 int ws_get(int slot, size_t bytes, void** out);

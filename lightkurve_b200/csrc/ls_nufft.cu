@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "ls_common.cuh"
 #include "nufft_core.h"
+#include "nufft_v2.cuh"
 
 namespace lkb {
 
@@ -195,251 +196,6 @@ nufft_fft_rows_kernel(float2* __restrict__ Z, int p, int pa, int tr) {
   }
 }
 
-// ---- "v2" transform (nufft_core.h): pruned spreading in the column kernel's layout, tiled column transforms with
-// table twiddles, row transforms fused with the finish.  Global traffic per pair of light curves at config 2
-// (M = 2^19): 0.5 MB flux + 0.84 MB G written + read, 4.2 MB T written + read, 0.8 MB power  = 11.4 MB
-// (the five global radix passes: 4.2 MB spread + 5 x 8.4 MB + 1.6 MB unpack reads + 0.8 MB = 48.6 MB).
-using nufft::V2_PB;
-using nufft::V2_THREADS;
-using nufft::V2_TILE;
-constexpr int V2_LOG_TILE = 13;
-static_assert((1 << V2_LOG_TILE) == V2_TILE, "tile size");
-
-__global__ void nufft2_tables_kernel(int pa, int pb, int p, float2* __restrict__ tw_a, float2* __restrict__ tw_b,
-                                     float2* __restrict__ t_hi, float2* __restrict__ t_lo) {
-  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(pb), pl = nufft::v2_log2_lo(p);
-  const int nlo = 1 << pl, nhi = 1 << (p - pl);
-  int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  int64_t num = 0, den = 1;
-  float2* dst = nullptr;
-  if (e < la) { nufft::v2_pass_table_entry(pa, e, &num, &den); dst = tw_a + e; }
-  else if ((e -= la) < lb) { nufft::v2_pass_table_entry(pb, e, &num, &den); dst = tw_b + e; }
-  else if ((e -= lb) < nhi) { num = e; den = nhi; dst = t_hi + e; }
-  else if ((e -= nhi) < nlo) { num = e; den = (int64_t)1 << p; dst = t_lo + e; }
-  else return;
-  double sn, cs;
-  sincospi(2.0 * (double)num / (double)den, &sn, &cs);
-  *dst = make_float2((float)cs, (float)sn);
-}
-
-// fine-grid cell m of position e of the G layout [c][n1][j]
-__device__ __forceinline__ int64_t v2_cell_of(int64_t e, int ptc, int n1max) {
-  const int64_t j = e & (((int64_t)1 << ptc) - 1), rest = e >> ptc;
-  const int64_t n1 = rest % n1max, c = rest / n1max;
-  return (n1 << V2_PB) + (c << ptc) + j;
-}
-
-// G[pair][e] for PP pairs of light curves per thread (the kernel weight of a (cell, cadence) is computed once and
-// applied to 2 PP light curves)
-template <int PP>
-__global__ void __launch_bounds__(256)
-nufft2_spread_kernel(const int32_t* __restrict__ first_ge, const Cad* __restrict__ cad, const float* __restrict__ y,
-                     int64_t ystride, const float* __restrict__ absmax, int B, int npairs, int w, float beta, int p,
-                     int ptc, int n1max, float2* __restrict__ G) {
-  const int64_t cells = (int64_t)n1max << V2_PB;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= cells) return;
-  const int64_t M = (int64_t)1 << p, m = v2_cell_of(e, ptc, n1max);
-  const int pair0 = (int)blockIdx.y * PP;
-  const float* yr[2 * PP];
-#pragma unroll
-  for (int q = 0; q < 2 * PP; ++q) {
-    int b = 2 * pair0 + q;
-    if (b > B - 1) b = B - 1;                      // clamped rows are computed and dropped
-    yr[q] = y + (int64_t)b * ystride;
-  }
-  float acc[2 * PP];
-#pragma unroll
-  for (int q = 0; q < 2 * PP; ++q) acc[q] = 0.0f;
-  const float inv_half = 2.0f / (float)w;
-  const int64_t L = nufft::table_len(M, w);
-  for (int wrap = 0; wrap < 2; ++wrap) {           // wrap = 1: cadences whose support runs past cell M - 1
-    const int64_t mm = m + (int64_t)wrap * M;
-    if (mm + 1 >= L) break;
-    int64_t lo_c = mm - w + 1;
-    if (lo_c < 0) lo_c = 0;
-    const int32_t a = first_ge[lo_c], b = first_ge[mm + 1];
-    for (int32_t n = a; n < b; ++n) {
-      const Cad cd = cad[n];
-      const float ph = nufft::es_eval((cd.d0 + (float)(mm - (int64_t)cd.i0)) * inv_half, beta);
-#pragma unroll
-      for (int q = 0; q < 2 * PP; ++q) acc[q] = fmaf(ph, yr[q][n], acc[q]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < PP; ++q) {
-    const int pair = pair0 + q;
-    if (pair >= npairs) break;
-    const int b0 = 2 * pair;
-    const float s0 = nufft::pow2_scale(absmax[b0]);
-    const float s1 = (b0 + 1 < B) ? nufft::pow2_scale(absmax[b0 + 1]) : 0.0f;
-    G[(int64_t)pair * cells + e] = make_float2(acc[2 * q] * s0, acc[2 * q + 1] * s1);
-  }
-}
-
-// one in-place pass of radix R over the lines of a tile (16 points per thread)
-template <int R>
-__device__ __forceinline__ void v2_pass(float2* buf, int plog, int lstride, int Ns, const float2* __restrict__ tw) {
-  constexpr int NB = 16 / R;
-  constexpr int LR = (R == 16) ? 4 : (R == 8) ? 3 : (R == 4) ? 2 : 1;
-  const int pnb = plog - LR, nb = 1 << pnb;            // butterflies per line
-  float2 u[NB][R];
-#pragma unroll
-  for (int q = 0; q < NB; ++q) {
-    const int b = (int)threadIdx.x + V2_THREADS * q;
-    const int line = b >> pnb, i = b & (nb - 1);
-    const float2* x = buf + line * lstride;
-#pragma unroll
-    for (int r = 0; r < R; ++r) u[q][r] = x[nufft::skew(i + r * nb)];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < NB; ++q) {
-    const int b = (int)threadIdx.x + V2_THREADS * q;
-    const int line = b >> pnb, i = b & (nb - 1), k = i & (Ns - 1);
-    float2* x = buf + line * lstride;
-    if (Ns > 1) {
-#pragma unroll
-      for (int r = 1; r < R; ++r) u[q][r] = nufft::cmul(u[q][r], tw[r * Ns + k]);
-    }
-    nufft::SmallDft<R>::run(u[q]);
-    const int j = ((i - k) << LR) + k;
-#pragma unroll
-    for (int r = 0; r < R; ++r) x[nufft::skew(j + r * Ns)] = u[q][r];
-  }
-  __syncthreads();
-}
-
-// all passes of the length-2^plog transforms of the tile's V2_TILE >> plog lines; tw: nufft::v2_pass_table_*
-__device__ __forceinline__ void v2_fft_lines(float2* buf, int plog, int lstride, const float2* __restrict__ tw) {
-  int Ns = 1;
-  for (int idx = 0;; ++idx) {
-    const int R = nufft::fft_pass_radix(plog, idx);
-    if (R == 0) break;
-    if (R == 16) v2_pass<16>(buf, plog, lstride, Ns, tw);
-    else if (R == 8) v2_pass<8>(buf, plog, lstride, Ns, tw);
-    else if (R == 4) v2_pass<4>(buf, plog, lstride, Ns, tw);
-    else v2_pass<2>(buf, plog, lstride, Ns, tw);
-    if (idx > 0) tw += R * Ns;
-    Ns *= R;
-  }
-}
-
-// step 1: grid (Bc / tc, npairs): tc columns n2 = c tc + j of one pair, length-A transforms over n1
-__global__ void __launch_bounds__(V2_THREADS, 2)
-nufft2_cols_kernel(const float2* __restrict__ G, float2* __restrict__ T, int p, int n1max,
-                   const float2* __restrict__ tw_a, const float2* __restrict__ t_hi, const float2* __restrict__ t_lo) {
-  LKB_DYN_SMEM(float2, buf);
-  const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa, tc = 1 << ptc, A = 1 << pa;
-  const int lstride = (int)nufft::smem_line(A);
-  const int c = (int)blockIdx.x, C = (1 << V2_PB) >> ptc;
-  const int64_t pair = blockIdx.y;
-  const int nvalid = n1max << ptc;
-  const float2* Gp = G + (pair * C + c) * (int64_t)nvalid;
-  for (int idx = (int)threadIdx.x; idx < V2_TILE; idx += V2_THREADS) {
-    const int n1 = idx >> ptc, j = idx & (tc - 1);
-    buf[j * lstride + (int)nufft::skew(n1)] = (idx < nvalid) ? Gp[idx] : make_float2(0.0f, 0.0f);
-  }
-  __syncthreads();
-  v2_fft_lines(buf, pa, lstride, tw_a);
-  float2* Tp = T + (pair * C + c) * (int64_t)V2_TILE;
-  const int pl = nufft::v2_log2_lo(p);
-  const int64_t Mmask = ((int64_t)1 << p) - 1;
-  for (int idx = (int)threadIdx.x; idx < V2_TILE; idx += V2_THREADS) {
-    const int k1 = idx >> ptc, j = idx & (tc - 1);
-    const int64_t q = ((int64_t)((c << ptc) + j) * k1) & Mmask;
-    const float2 wq = nufft::cmul(t_hi[q >> pl], t_lo[q & (((int64_t)1 << pl) - 1)]);
-    Tp[idx] = nufft::cmul(buf[j * lstride + (int)nufft::skew(k1)], wq);
-  }
-}
-
-struct V2Finish {
-  const float2* dec;
-  int64_t k0, F, k_lo;
-  const float4* rot;
-  const float2* rot2;
-  const float* ysum;
-  const float* absmax;
-  float Nf;
-  int normalization;
-  float scale;
-  int B;
-  float* power;
-};
-
-// step 2: grid (A / (2 R), npairs): rows k1 = 1 + g R .. (g + 1) R and their mirror rows, length-Bc transforms over n2;
-// MODE 1: unpack / deconvolve / epilogue -> power;  MODE 0: the whole transform goes to Zout in the [k1][k2] layout
-// (nufft::fourstep_index);  MODE 2: the modes k < nk2_keep * A and their mirrors M - k go to Zout in NATURAL order
-// (what the ragged finish kernel reads; R consecutive k1 are R consecutive modes: 64-byte runs).
-template <int MODE>
-__global__ void __launch_bounds__(V2_THREADS, 2)
-nufft2_rows_kernel(const float2* __restrict__ T, int p, const float2* __restrict__ tw_b, V2Finish fa,
-                   float2* __restrict__ Zout, int nk2_keep) {
-  LKB_DYN_SMEM(float2, buf);
-  constexpr int pb = V2_PB, Bc = 1 << pb, pR = V2_LOG_TILE - 1 - pb, R = 1 << pR;
-  const int pa = p - pb, A = 1 << pa, ptc = V2_LOG_TILE - pa, tc = 1 << ptc;
-  const int lstride = (int)nufft::smem_line(Bc);
-  const int g = (int)blockIdx.x;
-  const bool last = g == (A >> (pR + 1)) - 1;
-  const int64_t pair = blockIdx.y, M = (int64_t)1 << p;
-  auto slot_k1 = [&](int s) -> int {
-    const int h = s >> pR, r = s & (R - 1);
-    if (h == 0) return 1 + g * R + r;
-    if (last && r == 0) return 0;                    // instead of a second copy of row A / 2
-    return A - (g + 1) * R + r;
-  };
-  const float2* Tp = T + pair * M;
-  for (int e = (int)threadIdx.x; e < V2_TILE; e += V2_THREADS) {
-    const int j = e & (tc - 1), r = (e >> ptc) & (R - 1), h = (e >> (ptc + pR)) & 1, c = e >> (ptc + pR + 1);
-    const int s = h * R + r;
-    buf[s * lstride + (int)nufft::skew((c << ptc) + j)] = Tp[((((int64_t)c << pa) + slot_k1(s)) << ptc) + j];
-  }
-  __syncthreads();
-  v2_fft_lines(buf, pb, lstride, tw_b);
-  if (MODE == 0) {
-    for (int e = (int)threadIdx.x; e < V2_TILE; e += V2_THREADS) {
-      const int s = e >> pb, k2 = e & (Bc - 1);
-      Zout[pair * M + ((int64_t)slot_k1(s) << pb) + k2] = buf[s * lstride + (int)nufft::skew(k2)];
-    }
-    return;
-  }
-  if (MODE == 2) {
-    const int keep = nk2_keep < Bc / 2 ? nk2_keep : Bc / 2;
-    for (int item = (int)threadIdx.x; item < 2 * keep * 2 * R; item += V2_THREADS) {
-      const int s = item & (2 * R - 1), q = item >> (pR + 1);
-      const int k2 = q < keep ? q : Bc - 2 * keep + q;          // [0, keep) and [Bc - keep, Bc)
-      Zout[pair * M + (int64_t)slot_k1(s) + ((int64_t)k2 << pa)] = buf[s * lstride + (int)nufft::skew(k2)];
-    }
-    return;
-  }
-  int64_t nK2 = ((fa.k0 + fa.F - 1) >> pa) + 1;
-  if (nK2 > Bc) nK2 = Bc;
-  const int64_t b0 = 2 * pair;
-  const bool has1 = b0 + 1 < fa.B;
-  const float inv0 = 1.0f / nufft::pow2_scale(fa.absmax[b0]);
-  const float inv1 = has1 ? 1.0f / nufft::pow2_scale(fa.absmax[b0 + 1]) : 1.0f;
-  const float ys0 = fa.ysum[b0], ys1 = has1 ? fa.ysum[b0 + 1] : 0.0f;
-  for (int item = (int)threadIdx.x; item < (int)nK2 * 2 * R; item += V2_THREADS) {
-    const int s = item & (2 * R - 1), k2 = item >> (pR + 1);
-    const int64_t jj = (int64_t)slot_k1(s) + ((int64_t)k2 << pa) - fa.k0;
-    if (jj < fa.k_lo || jj >= fa.F) continue;
-    const int h = s >> pR, r = s & (R - 1);
-    int ps = (1 - h) * R + (R - 1 - r), pi = Bc - 1 - k2;      // mode M - k: row A - k1, column Bc - 1 - k2
-    if (last && h == 0 && r == R - 1) ps = s;                  // row A / 2 mirrors onto itself
-    if (last && h == 1 && r == 0) { ps = s; pi = (Bc - k2) & (Bc - 1); }   // row 0: column Bc - k2
-    const float2 g1 = buf[s * lstride + (int)nufft::skew(k2)], g2 = buf[ps * lstride + (int)nufft::skew(pi)];
-    const float2 ra = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));      // (g1 + conj g2) / 2
-    const float2 rb = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));      // (g1 - conj g2) / 2i
-    const float2 dc = fa.dec[jj];
-    const float2 da = nufft::cmul(ra, dc), db = nufft::cmul(rb, dc);
-    const float4 rt = fa.rot[jj];
-    const float2 r2 = fa.rot2[jj];
-    fa.power[b0 * fa.F + jj] = ls_epilogue_shared(da.x * inv0, da.y * inv0, rt, r2, ys0, fa.Nf, fa.normalization, fa.scale);
-    if (has1)
-      fa.power[(b0 + 1) * fa.F + jj] = ls_epilogue_shared(db.x * inv1, db.y * inv1, rt, r2, ys1, fa.Nf, fa.normalization, fa.scale);
-  }
-}
-
 __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, int w, double beta, GlNodes gl,
                                     float2* __restrict__ dec) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,6 +327,147 @@ nufft_verify_kernel(const float2* __restrict__ Z, int log2M, int pa, const float
   }
 }
 
+// ---- y-independent tables of the v2 path (built in ls_nufft_prepare) ----------------------------------------------
+// folded finish table of the rows k >= k_lo (nufft_v2.cuh V2FTab): deconvolution factor x tau rotation, the same
+// times exp(2 pi i kk / M), (Ctau, Stau), 1 / (2 N CC'), 1 / (2 N SS')
+__global__ void nufft2_ftab_kernel(const float4* __restrict__ rot, const float2* __restrict__ rot2, int64_t k0, int64_t F,
+                                   int64_t k_lo, int64_t M, int w, double beta, GlNodes gl, V2FTab* __restrict__ ftab) {
+  const int64_t k = k_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= F) return;
+  const int64_t kk = k0 + k;
+  double dre, dim;
+  nufft::deconv_factor(kk, M, w, beta, gl.x, gl.w, 32, &dre, &dim);
+  const float4 r = rot[k];
+  const float2 r2 = rot2[k];
+  const double ct = (double)r.x, st = (double)r.y;
+  const double d1x = dre * ct + dim * st, d1y = dim * ct - dre * st;            // dec * (ct - i st)
+  double ws, wc;
+  sincospi(2.0 * (double)kk / (double)M, &ws, &wc);
+  V2FTab o;
+  o.d = make_float4((float)d1x, (float)d1y, (float)(d1x * wc - d1y * ws), (float)(d1x * ws + d1y * wc));
+  o.c = make_float4(r2.x, r2.y, r.z, r.w);
+  ftab[k] = o;
+}
+
+// design matrix of the low rows (f * baseline <= LS_LOWF_CYCLES): D[r][n] = (cos - 1, sin)(2 pi f_r t_n), zero padding
+__global__ void nufft2_lowtab_kernel(const double* __restrict__ t, int64_t N, int64_t Npad, const double* __restrict__ freq,
+                                     int F_low, float2* __restrict__ D) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)F_low * Npad) return;
+  const int r = (int)(e / Npad);
+  const int64_t n = e - (int64_t)r * Npad;
+  float sn = 0.f, cm1 = 0.f;
+  if (n < N) ls_sincos_cycles_low(freq[r] * t[n], sn, cm1);
+  D[e] = make_float2(cm1, sn);
+}
+
+// power of the low rows: out[b][r] from sum_n y_b[n] D[r][n]; one warp = 2 light curves, one CTA = 16 light curves
+// sharing every 256-cadence slice of D through shared memory; rows in groups of LOWR.
+constexpr int LOWR = 12;
+__global__ void __launch_bounds__(256)
+nufft2_lowrows_kernel(const float2* __restrict__ D, int64_t N, int64_t Npad, const float* __restrict__ yc,
+                      int64_t ystride, int B, int F_low, int64_t F, const float4* __restrict__ rot,
+                      const float2* __restrict__ rot2, const float* __restrict__ ysum, int normalization, float scale,
+                      float* __restrict__ power) {
+  __shared__ float2 sD[LOWR][256];
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  const int b0 = (int)blockIdx.x * 16 + 2 * warp, b1 = b0 + 1;
+  const float* y0 = yc + (int64_t)(b0 < B ? b0 : B - 1) * ystride;
+  const float* y1 = yc + (int64_t)(b1 < B ? b1 : B - 1) * ystride;
+  for (int r0 = 0; r0 < F_low; r0 += LOWR) {
+    const int nr = (F_low - r0 < LOWR) ? F_low - r0 : LOWR;
+    double dc0[LOWR], ds0[LOWR], dc1[LOWR], ds1[LOWR];
+#pragma unroll
+    for (int r = 0; r < LOWR; ++r) { dc0[r] = ds0[r] = dc1[r] = ds1[r] = 0.0; }
+    for (int64_t c0 = 0; c0 < N; c0 += 256 * 8) {                 // fp32 partial sums over 2048 cadences, then fp64
+      float ac0[LOWR], as0[LOWR], ac1[LOWR], as1[LOWR];
+#pragma unroll
+      for (int r = 0; r < LOWR; ++r) { ac0[r] = as0[r] = ac1[r] = as1[r] = 0.0f; }
+      for (int64_t s0 = c0; s0 < c0 + 256 * 8 && s0 < N; s0 += 256) {
+        __syncthreads();
+        for (int r = 0; r < nr; ++r) {
+          const int64_t n = s0 + threadIdx.x;
+          sD[r][threadIdx.x] = (n < Npad) ? D[(int64_t)(r0 + r) * Npad + n] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int64_t n = s0 + lane + 32 * q;
+          const float v0 = (n < N) ? y0[n] : 0.0f, v1 = (n < N) ? y1[n] : 0.0f;
+#pragma unroll
+          for (int r = 0; r < LOWR; ++r) {
+            if (r < nr) {
+              const float2 d = sD[r][lane + 32 * q];
+              ac0[r] = fmaf(v0, d.x, ac0[r]); as0[r] = fmaf(v0, d.y, as0[r]);
+              ac1[r] = fmaf(v1, d.x, ac1[r]); as1[r] = fmaf(v1, d.y, as1[r]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < LOWR; ++r) {
+        dc0[r] += (double)ac0[r]; ds0[r] += (double)as0[r]; dc1[r] += (double)ac1[r]; ds1[r] += (double)as1[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < LOWR; ++r) {
+      if (r < nr) {
+        const double c0v = warp_sum(dc0[r]), s0v = warp_sum(ds0[r]), c1v = warp_sum(dc1[r]), s1v = warp_sum(ds1[r]);
+        if (lane == 0) {
+          const int k = r0 + r;
+          if (b0 < B)
+            power[(int64_t)b0 * F + k] = ls_epilogue_shared((float)c0v, (float)s0v, rot[k], rot2[k], ysum[b0], (float)N,
+                                                           normalization, scale, true);
+          if (b1 < B)
+            power[(int64_t)b1 * F + k] = ls_epilogue_shared((float)c1v, (float)s1v, rot[k], rot2[k], ysum[b1], (float)N,
+                                                           normalization, scale, true);
+        }
+      }
+    }
+  }
+}
+
+// Self-check of the v2 path: Zn [nv][Mh] holds the transforms of the first nv light curves in natural order (modes
+// below nk2_keep * A and their mirrors); same sampling and units as nufft_verify_kernel.
+__global__ void __launch_bounds__(128)
+nufft2_verify_kernel(const float2* __restrict__ Zn, int p, const float2* __restrict__ dec, int64_t k0, int64_t F,
+                     int64_t k_lo, const double* __restrict__ t, int64_t N, const float* __restrict__ yc, int64_t ystride,
+                     const double* __restrict__ freq, int nv, float fault, unsigned* __restrict__ worst) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned job = blockIdx.x * (blockDim.x >> 5) + warp;
+  unsigned h = job * 2654435761u + 12345u;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  const int64_t b = h % (unsigned)nv;
+  const int64_t k = k_lo + (int64_t)((h >> 8) % (unsigned)(F - k_lo));
+  const float* y = yc + b * ystride;
+  const double fr = freq[k];
+  double c = 0.0, s = 0.0, l1 = 0.0;
+  for (int64_t i = lane; i < N; i += 32) {
+    double sn, cs;
+    ls_sincos_cycles_f64(fr * t[i], sn, cs);
+    const double v = (double)y[i];
+    c += v * cs;
+    s += v * sn;
+    l1 += fabs(v);
+  }
+  c = warp_sum(c);
+  s = warp_sum(s);
+  l1 = warp_sum(l1);
+  if (lane == 0) {
+    const int64_t M = (int64_t)1 << p, Mh = M >> 1, kk = k0 + k;
+    const float2 g1 = Zn[b * Mh + kk], g2 = Zn[b * Mh + ((Mh - kk) & (Mh - 1))];
+    const float2 E = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));
+    const float2 O = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));
+    double wsn, wcs;
+    sincospi(2.0 * (double)kk / (double)M, &wsn, &wcs);
+    const float2 G = make_float2(E.x + (float)wcs * O.x - (float)wsn * O.y, E.y + (float)wcs * O.y + (float)wsn * O.x);
+    const float2 got = nufft::cmul(G, dec[k]);
+    const double dev = fmax(fabs((double)got.x * (double)fault - c), fabs((double)got.y * (double)fault - s));
+    const double units = dev / (1e-7 * fmax(l1, 1e-300));
+    atomicMax(worst, (unsigned)fmin(units, 4.0e9));
+  }
+}
+
 __global__ void nufft_fill_kernel(float* __restrict__ p, int64_t n, float v) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -604,70 +501,15 @@ int fft_passes(float2* a, float2* b, int p, int npairs, cudaStream_t st, float2*
 
 // LKB_NUFFT_FFT: "smem" = four-step transform in shared memory, "fused" = the same with the spreading done inside
 // the column kernel's load phase (the fine grids are written once, already half transformed)
-// "v2" (default where the fine grid allows it, 2^13 .. 2^22 cells) = the pruned, tiled transform with table twiddles
-// and the finish fused into the row kernel; "global" = one global sweep per radix pass.
+// "v2" (nufft_v2.cuh; default where the fine grid allows it, 2^14 .. 2^23 cells) = one real transform per light
+// curve, pruned + tiled, table twiddles, finish fused into the row kernel; "global" = the pair-packed round-1 form
+// with one global sweep per radix pass (also what tiny and huge grids use).
 int fft_mode(int p = 0) {
   const char* e = getenv("LKB_NUFFT_FFT");
   if (e && strcmp(e, "smem") == 0) return 1;
   if (e && strcmp(e, "fused") == 0) return 2;
   if (e && strcmp(e, "global") == 0) return 0;
-  return (p >= nufft::V2_P_MIN && p <= nufft::V2_P_MAX) ? 3 : 0;
-}
-
-// twiddle tables of the v2 transform of 2^p cells in workspace slot `slot`
-struct V2Tables {
-  const float2 *tw_a, *tw_b, *t_hi, *t_lo;
-};
-int v2_tables(int p, int slot, cudaStream_t st, V2Tables* out) {
-  const int pa = p - V2_PB, pl = nufft::v2_log2_lo(p);
-  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(V2_PB), nhi = 1 << (p - pl), nlo = 1 << pl;
-  float2* base = nullptr;
-  LKB_TRY(ws_get_t<float2>(slot, (size_t)(la + lb + nhi + nlo + 4), &base));
-  float2 *tw_a = base, *tw_b = base + la, *t_hi = tw_b + lb, *t_lo = t_hi + nhi;
-  LKB_LAUNCH(blocks_for(la + lb + nhi + nlo, 256), 256, st, nufft2_tables_kernel)(pa, V2_PB, p, tw_a, tw_b, t_hi, t_lo);
-  LKB_LAUNCH_CHECK();
-  out->tw_a = tw_a; out->tw_b = tw_b; out->t_hi = t_hi; out->t_lo = t_lo;
-  return LKB_OK;
-}
-// rows of the [A][Bc] fine grid that cadences can reach when the last one's support starts at cell i0_last
-int v2_n1max(int p, int64_t i0_last, int w) {
-  const int64_t M = (int64_t)1 << p, A = M >> V2_PB;
-  const int64_t reach = i0_last + w + 1;                   // cells [0, reach) (a support running past M wraps to cell 0)
-  if (reach >= M) return (int)A;
-  const int64_t n = (reach + ((int64_t)1 << V2_PB) - 1) >> V2_PB;
-  return (int)(n < 1 ? 1 : (n > A ? A : n));
-}
-size_t v2_cols_smem(int p) {
-  const int pa = p - V2_PB;
-  return (size_t)(V2_TILE >> pa) * nufft::smem_line((int64_t)1 << pa) * sizeof(float2);
-}
-size_t v2_rows_smem() { return (size_t)(V2_TILE >> V2_PB) * nufft::smem_line((int64_t)1 << V2_PB) * sizeof(float2); }
-
-// G (pruned fine grids in the column layout) -> T (column transforms) for `npairs` transforms of 2^p cells
-int v2_cols(const float2* G, float2* T, int p, int n1max, int npairs, const V2Tables& tb, cudaStream_t st) {
-  const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa;
-  const size_t smem = v2_cols_smem(p);
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LKB_LAUNCH_SMEM(dim3((unsigned)((1 << V2_PB) >> ptc), (unsigned)npairs), V2_THREADS, smem, st, nufft2_cols_kernel)(
-      G, T, p, n1max, tb.tw_a, tb.t_hi, tb.t_lo);
-  LKB_LAUNCH_CHECK();
-  return LKB_OK;
-}
-// T -> power (fa != NULL), -> Zout in the [k1][k2] layout (nk2_keep = 0), or -> Zout in natural order, modes
-// k < nk2_keep * A and their mirrors only (nk2_keep > 0)
-int v2_rows(const float2* T, int p, int npairs, const V2Tables& tb, const V2Finish* fa, float2* Zout, cudaStream_t st,
-            int nk2_keep = 0) {
-  const int pa = p - V2_PB, groups = (1 << pa) >> (V2_LOG_TILE - V2_PB);          // A / (2 R)
-  const size_t smem = v2_rows_smem();
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const dim3 grid((unsigned)groups, (unsigned)npairs);
-  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<1>)(T, p, tb.tw_b, *fa, nullptr, 0);
-  else if (nk2_keep > 0) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<2>)(T, p, tb.tw_b, V2Finish(), Zout, nk2_keep);
-  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<0>)(T, p, tb.tw_b, V2Finish(), Zout, 0);
-  LKB_LAUNCH_CHECK();
-  return LKB_OK;
+  return v2_supported(p) ? 3 : 0;
 }
 
 // in-place four-step transform of `npairs` length-2^p arrays; result in the [A][Bc] layout (pa returned).
@@ -728,15 +570,19 @@ struct NufftPlan {
   const Cad* cad;
   const int32_t* fge;
   const float2* dec;
-  int n1max;            // v2: rows of the [A][Bc] fine grid the cadences reach
+  int n1max;            // v2: rows of the [A][Bc] grid of z cells the cadences reach
   V2Tables tb;          // v2: twiddle tables (valid when fft_mode(p) == 3)
+  const float* Wt;      // v2: kernel weights [N, w]
+  const V2FTab* ftab;   // v2: folded finish table [F] (rows >= F_low)
+  const float2* lowD;   // v2: design matrix of the low rows [F_low, Npad]
+  int64_t Npad;
 };
 static NufftPlan g_plan;
 
 // d_t: times shifted to t[0] = 0 (ascending - checked here).  d_rot / d_rot2 rows [0, F_low) are already filled by
 // ls_window_kernel (fp64 path); the rows >= F_low are filled here from one transform of unit strengths.
 int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, double grid_df, float4* d_rot,
-                     float2* d_rot2, int64_t F_low, cudaStream_t st) {
+                     float2* d_rot2, int64_t F_low, cudaStream_t st, const double* d_freq, int64_t Npad) {
   const int w = kernel_width();
   const float beta = 2.30f * (float)w;
   const int64_t k0 = (int64_t)rint(grid_f0 / grid_df);
@@ -777,9 +623,26 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     return LKB_E_UNSUPPORTED;
   }
   g_plan.n1max = 0;
-  if (fft_mode(p) == 3) {
+  g_plan.Wt = nullptr;
+  g_plan.ftab = nullptr;
+  g_plan.lowD = nullptr;
+  g_plan.Npad = Npad;
+  const bool v2 = fft_mode(p) == 3 && d_freq != nullptr;
+  if (v2) {
     g_plan.n1max = v2_n1max(p, (int64_t)h_last.i0, w);
     LKB_TRY(v2_tables(p, WS_IN6, st, &g_plan.tb));
+    float* Wt = nullptr;
+    LKB_TRY(ws_get_t<float>(WS_X0, (size_t)N * w, &Wt));
+    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel)(cad, N, w, beta, Wt);
+    LKB_LAUNCH_CHECK();
+    g_plan.Wt = Wt;
+    if (F_low > 0) {
+      float2* lowD = nullptr;
+      LKB_TRY(ws_get_t<float2>(WS_X2, (size_t)F_low * Npad, &lowD));
+      LKB_LAUNCH(blocks_for(F_low * Npad, 256), 256, st, nufft2_lowtab_kernel)(d_t, N, Npad, d_freq, (int)F_low, lowD);
+      LKB_LAUNCH_CHECK();
+      g_plan.lowD = lowD;
+    }
   }
   LKB_LAUNCH(blocks_for(L, 256), 256, st, nufft_first_ge_kernel)(cad, N, L, fge);
   LKB_LAUNCH_CHECK();
@@ -800,6 +663,14 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     LKB_TRY(fft_passes(Zw, Zw + M2, p2, 1, st, &Zw_out));
     LKB_LAUNCH(blocks_for(F - F_low, 128), 128, st, nufft_rot_kernel)(Zw_out, M2, dec2, k0, F, F_low, (double)N, d_rot, d_rot2);
     LKB_LAUNCH_CHECK();
+    if (v2) {
+      V2FTab* ftab = nullptr;
+      LKB_TRY(ws_get_t<V2FTab>(WS_X1, (size_t)F, &ftab));
+      LKB_LAUNCH(blocks_for(F - F_low, 128), 128, st, nufft2_ftab_kernel)(d_rot, d_rot2, k0, F, F_low, M, w, (double)beta, gl,
+                                                                       ftab);
+      LKB_LAUNCH_CHECK();
+      g_plan.ftab = ftab;
+    }
   }
   g_plan.w = w;
   g_plan.p = p;
@@ -824,16 +695,59 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
   const float beta = pl.beta;
   const int64_t k0 = pl.k0, M = pl.M;
   const int npairs = (B + 1) / 2;
-  const int mode = fft_mode(p);
+  const int mode = (pl.Wt != nullptr) ? 3 : fft_mode(p) == 3 ? 0 : fft_mode(p);
   const char* ve = getenv("LKB_NUFFT_VERIFY");
   const bool verify = ve && atoi(ve) != 0 && F_low < F;
+  if (mode == 3) {
+    // ---- v2: one real transform per light curve (nufft_v2.cuh): spread -> column transforms -> row transforms + finish
+    const int64_t Mh = M >> 1;
+    const size_t cells = (size_t)pl.n1max << V2_PB;
+    float2 *T = nullptr, *G = nullptr;
+    LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)B * Mh, &T));
+    LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, std::max((size_t)B * cells, verify ? (size_t)4 * Mh : (size_t)0), &G));
+    unsigned* d_worst = nullptr;
+    if (verify) LKB_TRY(ws_get_t<unsigned>(ws_alt ? WS_OUT7 : WS_OUT6, 1, &d_worst));
+    const int ptc = V2_LOG_TILE - (p - 1 - V2_PB);
+    if (prof) prof_begin(st);
+    constexpr int LCS = 8;
+    LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)((B + LCS - 1) / LCS)), 256, st, nufft2_spread_kernel<LCS>)(
+        pl.fge, pl.cad, pl.Wt, d_yc, ystride, B, w, p, ptc, pl.n1max, G);
+    LKB_LAUNCH_CHECK();
+    LKB_TRY(v2_cols(G, T, p, pl.n1max, B, pl.tb, st));
+    if (F_low < F) {
+      V2Finish fa;
+      fa.ftab = pl.ftab; fa.k0 = k0; fa.F = F; fa.k_lo = F_low; fa.ysum = d_ysumf; fa.Nf = (float)N;
+      fa.normalization = normalization; fa.scale = (float)norm_scale; fa.power = d_pow;
+      LKB_TRY(v2_rows(T, p, B, pl.tb, &fa, nullptr, 0, st));
+    }
+    if (F_low > 0) {
+      LKB_LAUNCH(blocks_for(B, 16), 256, st, nufft2_lowrows_kernel)(pl.lowD, N, pl.Npad, d_yc, ystride, B, (int)F_low, F, d_rot,
+                                                               d_rot2, d_ysumf, normalization, (float)norm_scale, d_pow);
+      LKB_LAUNCH_CHECK();
+    }
+    if (prof) prof_end(st);
+    if (verify) {            // the first light curves' transforms once more, written out this time (G is free again)
+      const int nv = std::min(B, 4);
+      const int nk2 = (int)((k0 + F) >> (p - 1 - V2_PB)) + 1;
+      LKB_TRY(v2_rows(T, p, nv, pl.tb, nullptr, G, nk2, st));
+      const char* fe = getenv("LKB_NUFFT_INJECT_FAULT");
+      LKB_CUDA_CHECK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned), st));
+      LKB_LAUNCH(16, 128, st, nufft2_verify_kernel)(G, p, pl.dec, k0, F, F_low, d_t, N, d_yc, ystride, d_freq, nv,
+                                                  fe ? (float)atof(fe) : 1.0f, d_worst);
+      LKB_LAUNCH_CHECK();
+      unsigned h_worst = 0;
+      LKB_CUDA_CHECK(cudaMemcpyAsync(&h_worst, d_worst, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (h_worst > 100u) {
+        set_error("NUFFT self-check failed: transform deviates from the direct sums by %u x 1e-7 sum|y|", h_worst);
+        return LKB_E_VERIFY;
+      }
+    }
+    return LKB_OK;
+  }
   float2 *Za = nullptr, *Zb = nullptr;
   LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT4 : WS_H, (size_t)npairs * M, &Za));
-  // second buffer: v2 keeps the pruned grids G there (n1max rows of Bc cells per pair; the self-check additionally
-  // needs room for a few whole transforms), the other variants a whole second set of fine grids
-  const size_t zb_count = (mode == 3) ? std::max((size_t)npairs * ((size_t)pl.n1max << V2_PB), verify ? (size_t)4 * M : (size_t)0)
-                                      : (size_t)npairs * M;
-  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, zb_count, &Zb));
+  LKB_TRY(ws_get_t<float2>(ws_alt ? WS_OUT5 : WS_I, (size_t)npairs * M, &Zb));
   unsigned* d_worst = nullptr;
   if (verify) LKB_TRY(ws_get_t<unsigned>(ws_alt ? WS_OUT7 : WS_OUT6, 1, &d_worst));
 
@@ -855,43 +769,6 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
     const int B_g = std::min(B - 2 * g0, 2 * np_g);              // light curves in this group
     float2* Za_g = Za + (size_t)g0 * M;
     float2* Zb_g = Zb + (size_t)g0 * M;
-    if (mode == 3) {
-      // spread (pruned, column layout) -> column transforms -> row transforms + finish
-      const int pa = p - V2_PB, ptc = V2_LOG_TILE - pa;
-      const size_t cells = (size_t)pl.n1max << V2_PB;
-      // with L2-sized groups (LKB_NUFFT_GROUP_MB) every group goes through the SAME buffers, so that they stay in L2
-      float2* G_g = (group < npairs) ? Zb : Zb + (size_t)g0 * cells;
-      if (group < npairs) Za_g = Za;
-      const float* y_g = d_yc + (size_t)2 * g0 * ystride;
-      LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)((np_g + 3) / 4)), 256, st, nufft2_spread_kernel<4>)(
-          pl.fge, pl.cad, y_g, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, ptc, pl.n1max, G_g);
-      LKB_LAUNCH_CHECK();
-      LKB_TRY(v2_cols(G_g, Za_g, p, pl.n1max, np_g, pl.tb, st));
-      if (F_low < F) {
-        V2Finish fa;
-        fa.dec = pl.dec; fa.k0 = k0; fa.F = F; fa.k_lo = F_low; fa.rot = d_rot; fa.rot2 = d_rot2;
-        fa.ysum = d_ysumf + 2 * g0; fa.absmax = d_absmax + 2 * g0; fa.Nf = (float)N; fa.normalization = normalization;
-        fa.scale = (float)norm_scale; fa.B = B_g; fa.power = d_pow + (size_t)2 * g0 * F;
-        LKB_TRY(v2_rows(Za_g, p, np_g, pl.tb, &fa, nullptr, st));
-        if (verify && g0 == 0) {          // self-check: the first pairs' transforms once more, written out this time
-          const int np_v = std::min(np_g, 4), B_v = std::min(B_g, 2 * np_v);
-          LKB_TRY(v2_rows(Za_g, p, np_v, pl.tb, nullptr, Zb, st));     // G is no longer needed
-          const char* fe = getenv("LKB_NUFFT_INJECT_FAULT");
-          LKB_CUDA_CHECK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned), st));
-          LKB_LAUNCH(16, 128, st, nufft_verify_kernel)(Zb, p, pa, pl.dec, k0, F, F_low, d_t, N, d_yc, ystride, d_absmax,
-                                                     d_freq, B_v, fe ? (float)atof(fe) : 1.0f, d_worst);
-          LKB_LAUNCH_CHECK();
-          unsigned h_worst = 0;
-          LKB_CUDA_CHECK(cudaMemcpyAsync(&h_worst, d_worst, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-          LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-          if (h_worst > 100u) {
-            set_error("NUFFT self-check failed: transform deviates from the direct sums by %u x 1e-7 sum|y|", h_worst);
-            return LKB_E_VERIFY;
-          }
-        }
-      }
-      continue;
-    }
     if (mode != 2) {
       LKB_LAUNCH(blocks_for((int64_t)np_g * M, 256), 256, st, nufft_spread_kernel)(
           pl.fge, pl.cad, d_yc + (size_t)2 * g0 * ystride, ystride, d_absmax + 2 * g0, B_g, np_g, w, beta, p, Za_g);
@@ -955,7 +832,7 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
                     const float* d_absmax, int B, const double* d_freq, int64_t F, double grid_f0, double grid_df,
                     float4* d_rot, float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
                     cudaStream_t st) {
-  LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_low, st));
+  LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_low, st, d_freq, ystride));
   return ls_nufft_run(d_t, N, d_yc, ystride, d_ysumf, d_absmax, B, d_freq, F, d_rot, d_rot2, F_low, normalization,
                       norm_scale, d_pow, st, 0, true);
 }
@@ -1027,28 +904,33 @@ nufft_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict_
   Z[gid] = v;
 }
 
-// v2: the same cell values in the column kernel's layout G[pair][c][n1][j], rows n1 < n1max only
+// v2 (one real transform per light curve): G[lc][e] = (cell 2n, cell 2n + 1) in the column kernel's layout, rows
+// n1 < n1max only; y == NULL: unit strengths (window terms)
 __global__ void __launch_bounds__(256)
 nufft2_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict__ y, const int64_t* __restrict__ off,
-                            const int64_t* __restrict__ poff, const float* __restrict__ absmax, int B, int npairs, int w,
-                            float beta, int p, int ptc, int n1max, float2* __restrict__ G) {
+                            const int64_t* __restrict__ poff, int w, float beta, int p, int ptc, int n1max,
+                            float2* __restrict__ G) {
   const int64_t cells = (int64_t)n1max << V2_PB;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cells) return;
-  const int64_t M = (int64_t)1 << p, m = v2_cell_of(e, ptc, n1max);
-  const int64_t pair = blockIdx.y, b0 = 2 * pair, b1 = b0 + 1;
-  float2 v = make_float2(0.f, 0.f);
-  {
-    const int64_t po = poff[b0], n = off[b0 + 1] - off[b0];
-    v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b0]) : 1.0f, w,
-                                    beta, M);
-  }
-  if (b1 < B) {
-    const int64_t po = poff[b1], n = off[b1 + 1] - off[b1];
-    v.y = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, y ? nufft::pow2_scale(absmax[b1]) : 1.0f, w,
-                                    beta, M);
-  }
-  G[pair * cells + e] = v;
+  const int64_t M = (int64_t)1 << p, m = 2 * v2_zcell_of(e, ptc, n1max);
+  const int64_t lc = blockIdx.y, po = poff[lc], n = off[lc + 1] - off[lc];
+  float2 v;
+  v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
+  v.y = nufft::spread_cell_search(m + 1, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
+  G[lc * cells + e] = v;
+}
+
+// mode kk of ONE real series from its half-length transform Zn (natural order, length Mh = M / 2)
+__device__ __forceinline__ float2 v2_unpack_real(const float2* __restrict__ Zn, int64_t kk, int64_t M) {
+  const int64_t Mh = M >> 1;
+  const float2 g1 = Zn[kk], g2 = Zn[(Mh - kk) & (Mh - 1)];
+  const float2 E = make_float2(0.5f * (g1.x + g2.x), 0.5f * (g1.y - g2.y));
+  const float2 O = make_float2(0.5f * (g1.y + g2.y), 0.5f * (g2.x - g1.x));
+  double wsn, wcs;
+  sincospi(2.0 * (double)kk / (double)M, &wsn, &wcs);
+  const float wc = (float)wcs, ws = (float)wsn;
+  return make_float2(E.x + wc * O.x - ws * O.y, E.y + wc * O.y + ws * O.x);
 }
 
 __device__ __forceinline__ float ragged_power(float2 hs, float2 win1, float2 win2, double Nd, double ysum,
@@ -1095,6 +977,27 @@ nufft_finish_ragged_kernel(const float2* __restrict__ Z, int log2M, const float2
   }
 }
 
+// v2: power[b, k] from the per-light-curve transforms Zn [B][M / 2] (flux) and Zwn [B][M2 / 2] (unit strengths on the
+// 2x finer grid), both in natural order
+__global__ void __launch_bounds__(256)
+nufft2_finish_ragged_kernel(const float2* __restrict__ Zn, int p, const float2* __restrict__ Zwn, int p2,
+                            const float2* __restrict__ dec, const float2* __restrict__ dec2, int64_t k0, int64_t F,
+                            double f0, double df, const int64_t* __restrict__ off, const double* __restrict__ span,
+                            const double* __restrict__ ysum, int normalization, const double* __restrict__ norm_scale,
+                            int B, float* __restrict__ power) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= F * B) return;
+  const int64_t b = gid / F, k = gid - b * F;
+  const double fr = f0 + (double)k * df;
+  if (!(fr * span[b] > LS_LOWF_CYCLES)) return;
+  const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2, kk = k0 + k;
+  const float2 hs = nufft::cmul(v2_unpack_real(Zn + b * (M >> 1), kk, M), dec[k]);
+  const float2 w1 = nufft::cmul(v2_unpack_real(Zwn + b * (M2 >> 1), kk, M2), dec2[kk]);
+  const float2 w2 = nufft::cmul(v2_unpack_real(Zwn + b * (M2 >> 1), 2 * kk, M2), dec2[2 * kk]);
+  const double Nd = (double)(off[b + 1] - off[b]);
+  power[b * F + k] = ragged_power(hs, w1, w2, Nd, ysum[b], normalization, norm_scale ? norm_scale[b] : 1.0);
+}
+
 // rows with f * baseline_b <= LS_LOWF_CYCLES: direct fp64 sums, one warp per (row, light curve)
 __global__ void __launch_bounds__(128)
 nufft_lowrows_ragged_kernel(const double* __restrict__ t, const float* __restrict__ y, const int64_t* __restrict__ off,
@@ -1122,6 +1025,95 @@ nufft_lowrows_ragged_kernel(const double* __restrict__ t, const float* __restric
                                     norm_scale ? norm_scale[b] : 1.0);
 }
 
+}  // namespace
+
+namespace {
+// Ragged batch through the v2 transform: every light curve is one real series on the flux grid (2^p cells) and one on
+// the window grid (2^p2 cells, unit strengths); groups of light curves share the buffers when the fine grids of the
+// whole batch exceed cap_mb.
+int ls_nufft_ragged_v2(const double* d_t, const float* d_y, const int64_t* d_off, const int64_t* d_po, int B,
+                       int64_t ptotal, int64_t nmax, const double* d_span, const double* h_span, const double* d_ysum,
+                       int64_t F, double f0, double df, int64_t k0, int p, int p2, int w, float beta, double cap_mb,
+                       int normalization, const double* d_ns, float* d_pow, cudaStream_t st) {
+  const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2, Mh = M >> 1, Mh2 = M2 >> 1;
+  double span_max = 0.0;
+  for (int b = 0; b < B; ++b) span_max = fmax(span_max, h_span[b]);
+  const int n1max = v2_n1max(p, (int64_t)nufft::cad_entry(span_max, df, M, w).i0, w);
+  const int n1max2 = v2_n1max(p2, (int64_t)nufft::cad_entry(span_max, df, M2, w).i0, w);
+  const size_t cells = (size_t)n1max << V2_PB, cells2 = (size_t)n1max2 << V2_PB;
+  const double per_lc_mb = (2.0 * (double)Mh + 2.0 * (double)Mh2 + (double)std::max(cells, cells2)) * sizeof(float2) / 1048576.0;
+  int group = (int)fmax(1.0, floor(cap_mb / per_lc_mb));
+  if (group > B) group = B;
+  GlNodes gl;
+  nufft::gauss_legendre(32, gl.x, gl.w);
+  V2Tables tb, tb2;
+  LKB_TRY(v2_tables(p, WS_IN7, st, &tb));
+  LKB_TRY(v2_tables(p2, WS_OUT1, st, &tb2));
+  Cad *cad = nullptr, *cad2 = nullptr;
+  float2 *dec = nullptr, *dec2 = nullptr, *T = nullptr, *Zn = nullptr, *Tw = nullptr, *Zwn = nullptr, *G = nullptr;
+  int* flag = nullptr;
+  LKB_TRY(ws_get_t<Cad>(WS_K, ptotal + 4, &cad));
+  LKB_TRY(ws_get_t<Cad>(WS_L, ptotal + 4, &cad2));
+  LKB_TRY(ws_get_t<float2>(WS_N, (size_t)group * Mh, &T));
+  LKB_TRY(ws_get_t<float2>(WS_O, (size_t)group * Mh, &Zn));
+  LKB_TRY(ws_get_t<float2>(WS_P, (size_t)group * Mh2, &Tw));
+  LKB_TRY(ws_get_t<float2>(WS_OUT3, (size_t)group * Mh2, &Zwn));
+  LKB_TRY(ws_get_t<float2>(WS_OUT2, (size_t)group * std::max(cells, cells2), &G));
+  LKB_TRY(ws_get_t<float2>(WS_IN4, F, &dec));
+  LKB_TRY(ws_get_t<float2>(WS_IN5, 2 * (k0 + F), &dec2));
+  LKB_TRY(ws_get_t<int>(WS_IN6, 1, &flag));
+
+  LKB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  {
+    const unsigned gx = (unsigned)std::min<int64_t>(64, (nmax + 255) / 256);
+    LKB_LAUNCH(dim3(gx ? gx : 1, (unsigned)B), 256, st, nufft_cad_ragged_kernel)(d_t, d_off, d_po, d_span, df, M, M2, w, cad,
+                                                                          cad2, flag);
+    LKB_LAUNCH_CHECK();
+  }
+  int h_flag = 0;
+  LKB_CUDA_CHECK(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flag) { set_error("NUFFT (ragged): a light curve has unsorted times"); return LKB_E_UNSUPPORTED; }
+  LKB_LAUNCH(blocks_for(F, 128), 128, st, nufft_deconv_kernel)(k0, F, M, w, (double)beta, gl, dec);
+  LKB_LAUNCH_CHECK();
+  LKB_LAUNCH(blocks_for(2 * (k0 + F), 128), 128, st, nufft_deconv_kernel)(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
+  LKB_LAUNCH_CHECK();
+
+  const int ptc = V2_LOG_TILE - (p - 1 - V2_PB), ptc2 = V2_LOG_TILE - (p2 - 1 - V2_PB);
+  const int nk2 = (int)((k0 + F) >> (p - 1 - V2_PB)) + 1, nk2w = (int)((2 * (k0 + F)) >> (p2 - 1 - V2_PB)) + 1;
+  prof_begin(st);
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int Bg = std::min(group, B - b0);
+    const int64_t *off_g = d_off + b0, *po_g = d_po + b0;
+    double span_min = 1e300;
+    for (int b = b0; b < b0 + Bg; ++b) span_min = fmin(span_min, h_span[b]);
+    const double nlow = floor((LS_LOWF_CYCLES / span_min - f0) / df) + 2.0;
+    const int64_t F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
+    // window terms: unit strengths on the 2x finer grid (modes kk and 2 kk), then the flux
+    LKB_LAUNCH(dim3(blocks_for((int64_t)cells2, 256), (unsigned)Bg), 256, st, nufft2_spread_ragged_kernel)(
+        cad2, nullptr, off_g, po_g, w, beta, p2, ptc2, n1max2, G);
+    LKB_LAUNCH_CHECK();
+    LKB_TRY(v2_cols(G, Tw, p2, n1max2, Bg, tb2, st));
+    LKB_TRY(v2_rows(Tw, p2, Bg, tb2, nullptr, Zwn, nk2w, st));
+    LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)Bg), 256, st, nufft2_spread_ragged_kernel)(
+        cad, d_y, off_g, po_g, w, beta, p, ptc, n1max, G);
+    LKB_LAUNCH_CHECK();
+    LKB_TRY(v2_cols(G, T, p, n1max, Bg, tb, st));
+    LKB_TRY(v2_rows(T, p, Bg, tb, nullptr, Zn, nk2, st));
+    LKB_LAUNCH(blocks_for(F * Bg, 256), 256, st, nufft2_finish_ragged_kernel)(
+        Zn, p, Zwn, p2, dec, dec2, k0, F, f0, df, off_g, d_span + b0, d_ysum + b0, normalization,
+        d_ns ? d_ns + b0 : nullptr, Bg, d_pow + (size_t)b0 * F);
+    LKB_LAUNCH_CHECK();
+    if (F_low_max > 0) {
+      LKB_LAUNCH(blocks_for(F_low_max * Bg, 4), 128, st, nufft_lowrows_ragged_kernel)(
+          d_t, d_y, off_g, po_g, d_span + b0, d_ysum + b0, f0, df, F_low_max, F, normalization,
+          d_ns ? d_ns + b0 : nullptr, Bg, d_pow + (size_t)b0 * F);
+      LKB_LAUNCH_CHECK();
+    }
+  }
+  prof_end(st);
+  return LKB_OK;
+}
 }  // namespace
 
 bool ls_nufft_ragged_enabled() {               // `auto` of the ragged entry may use this path (default: yes)
@@ -1166,20 +1158,10 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   GlNodes gl;
   nufft::gauss_legendre(32, gl.x, gl.w);
 
-  // v2 transform for both fine grids when they are in range: pruned to the rows the longest light curve reaches
-  const bool v2 = fft_mode(p) == 3 && fft_mode(p2) == 3;
-  int n1max = 0, n1max2 = 0;
-  V2Tables tb, tb2;
-  float2* Gbuf = nullptr;
-  if (v2) {
-    double span_max = 0.0;
-    for (int b = 0; b < B; ++b) span_max = fmax(span_max, h_span[b]);
-    n1max = v2_n1max(p, (int64_t)nufft::cad_entry(span_max, df, M, w).i0, w);
-    n1max2 = v2_n1max(p2, (int64_t)nufft::cad_entry(span_max, df, M2, w).i0, w);
-    LKB_TRY(v2_tables(p, WS_IN7, st, &tb));
-    LKB_TRY(v2_tables(p2, WS_OUT1, st, &tb2));
-    LKB_TRY(ws_get_t<float2>(WS_OUT2, (size_t)group * ((size_t)std::max(n1max, n1max2) << V2_PB), &Gbuf));
-  }
+  // v2 (one real transform per light curve, nufft_v2.cuh) when both fine grids are in range
+  if (fft_mode(p) == 3 && fft_mode(p2) == 3)
+    return ls_nufft_ragged_v2(d_t, d_y, d_off, d_po, B, ptotal, nmax, d_span, h_span, d_ysum, F, f0, df, k0, p, p2, w, beta,
+                              cap_mb, normalization, d_ns, d_pow, st);
 
   Cad *cad = nullptr, *cad2 = nullptr;
   float2 *dec = nullptr, *dec2 = nullptr, *Za = nullptr, *Zb = nullptr, *Zw = nullptr;
@@ -1227,24 +1209,7 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
     float2* Zw_out = nullptr;
     float2* Zout = nullptr;
     int pa = 0, pa2 = 0;                       // LKB_NUFFT_FFT=smem|fused: four-step transforms (in place)
-    if (v2) {
-      // window terms (unit strengths, 2x finer grid: modes kk and 2 kk), then the flux; the row kernels write the
-      // needed modes and their mirrors in natural order
-      const int nk2w = (int)((2 * (k0 + F)) >> (p2 - V2_PB)) + 1, nk2 = (int)((k0 + F) >> (p - V2_PB)) + 1;
-      const size_t cells2 = (size_t)n1max2 << V2_PB, cells = (size_t)n1max << V2_PB;
-      LKB_LAUNCH(dim3(blocks_for((int64_t)cells2, 256), (unsigned)npairs), 256, st, nufft2_spread_ragged_kernel)(
-          cad2, nullptr, off_g, po_g, amax_g, Bg, npairs, w, beta, p2, V2_LOG_TILE - (p2 - V2_PB), n1max2, Gbuf);
-      LKB_LAUNCH_CHECK();
-      LKB_TRY(v2_cols(Gbuf, Zw, p2, n1max2, npairs, tb2, st));
-      Zw_out = Zw + (size_t)npairs * M2;
-      LKB_TRY(v2_rows(Zw, p2, npairs, tb2, nullptr, Zw_out, st, nk2w));
-      LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)npairs), 256, st, nufft2_spread_ragged_kernel)(
-          cad, d_y, off_g, po_g, amax_g, Bg, npairs, w, beta, p, V2_LOG_TILE - (p - V2_PB), n1max, Gbuf);
-      LKB_LAUNCH_CHECK();
-      LKB_TRY(v2_cols(Gbuf, Za, p, n1max, npairs, tb, st));
-      Zout = Zb;
-      LKB_TRY(v2_rows(Za, p, npairs, tb, nullptr, Zout, st, nk2));
-    } else {
+    {
     // window terms: unit strengths on the 2x finer grid
     LKB_LAUNCH(blocks_for((int64_t)npairs * M2, 256), 256, st, nufft_spread_ragged_kernel)(cad2, nullptr, off_g, po_g, amax_g,
                                                                                     Bg, npairs, w, beta, p2, Zw);

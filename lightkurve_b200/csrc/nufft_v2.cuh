@@ -1,0 +1,380 @@
+// "v2" transform of the NUFFT Lomb-Scargle path (included by ls_nufft.cu; also compiled for the CPU through
+// tests/native/cuda_emu.h).  Every light curve is ONE REAL series on the fine grid of M = 2^p cells, transformed as a
+// complex series of Mh = M / 2 points  z[n] = g[2n] + i g[2n + 1]:
+//     G[k] = E[k] + exp(2 pi i k / M) O[k],   E = (Z[k] + conj Z[Mh - k]) / 2,   O = (Z[k] - conj Z[Mh - k]) / 2i.
+// (Round 2, hardware finding: packing TWO light curves into one complex transform leaks the partner's spectral peak
+// into a quiet light curve with relative weight ~1e-7 - fp32 rounding of Z at the partner's peak bin - which is
+// 2-3x the parity tolerance when the partner is >~ 300x louder; tools/worst_bins_detail.py.  A light curve's own
+// transform has no such cross-talk, batches of odd size need no padding, and the result of a light curve no longer
+// depends on its neighbour.)
+//
+// Mh = A * Bc, Bc = 2^V2_PB = 512 fixed, A = 2^pa;  n = n1 Bc + n2,  k = k1 + A k2  (four-step transform):
+//   spread : G[lc][c][n1][j]   (c = n2 / TC, j = n2 % TC, TC = 8192 / A columns per CTA), rows n1 < n1max only -
+//            the cadences reach just the first df * baseline (20 % at lightkurve's default oversampling) of the grid;
+//            kernel weights come from a per-cadence table (built once per call), one thread = one z cell = two fine
+//            grid cells of LCS light curves;
+//   cols   : one CTA = TC columns of one light curve: length-A transforms over n1 in shared memory (in place, one
+//            radix-16 butterfly per thread and pass, twiddles from tables), times exp(2 pi i n2 k1 / Mh), written as
+//            T[lc][c][k1][j] - one contiguous 64 KB block per CTA;
+//   rows   : one CTA = rows k1 = 1 + 8 g .. 8 (g + 1) and their mirror rows A - k1 of one light curve: length-Bc
+//            transforms over n2, then the finish (unpack E / O, deconvolve + tau rotation through one folded table,
+//            epilogue) -> power, written in 32-byte runs (8 consecutive k1 at one k2 are 8 consecutive frequency
+//            bins); the transform itself never goes back to global memory.  The CTA that would hold row A / 2 twice
+//            takes row 0 (which mirrors onto itself) instead.
+// All tile geometry is compile-time (template parameter PA): every shared-memory offset inside the passes is
+// `runtime base + constant`.
+#pragma once
+#include "nufft_core.h"
+
+namespace lkb {
+namespace {
+
+using nufft::V2_PB;
+using nufft::V2_THREADS;
+using nufft::V2_TILE;
+constexpr int V2_LOG_TILE = 13;
+static_assert((1 << V2_LOG_TILE) == V2_TILE, "tile size");
+constexpr int V2_BC = 1 << V2_PB;
+constexpr int V2_R = V2_TILE / (2 * V2_BC);                     // rows per block of the row kernel (8)
+constexpr int V2_LSB = V2_BC + V2_BC / 16 + 1;                  // skewed line of Bc points
+// real-mode limits: Mh = 2^(p - 1) = A * Bc with 16 <= A <= 8192
+constexpr int V2R_P_MIN = V2_PB + 4 + 1, V2R_P_MAX = V2_PB + 13 + 1;
+
+__host__ __device__ constexpr int v2_radix(int plog, int idx) {
+  return (idx < plog / 4) ? 16 : ((idx == plog / 4 && (plog % 4)) ? (1 << (plog % 4)) : 0);
+}
+__host__ __device__ constexpr int v2_log2i(int r) { return r == 16 ? 4 : r == 8 ? 3 : r == 4 ? 2 : r == 2 ? 1 : 0; }
+__device__ __forceinline__ int v2_skew(int a) { return a + (a >> 4); }
+// offset of input r of a butterfly (r * nb points further) in a skewed line; exact because the butterfly index is
+// either a multiple-of-16 aligned case (nb % 16 == 0) or smaller than nb <= 8
+template <int nb>
+__host__ __device__ constexpr int v2_in_off(int r) {
+  return (nb % 16 == 0) ? r * (nb + nb / 16) : r * nb + ((r * nb) >> 4);
+}
+
+// ---- tables -------------------------------------------------------------------------------------------------------
+// pass tables of the length-A and the length-Bc transforms, the two-level inter-step table of exp(2 pi i q / Mh)
+__global__ void nufft2_tables_kernel(int pa, int pb, int ph, float2* __restrict__ tw_a, float2* __restrict__ tw_b,
+                                     float2* __restrict__ t_hi, float2* __restrict__ t_lo) {
+  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(pb), pl = nufft::v2_log2_lo(ph);
+  const int nlo = 1 << pl, nhi = 1 << (ph - pl);
+  int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  int64_t num = 0, den = 1;
+  float2* dst = nullptr;
+  if (e < la) { nufft::v2_pass_table_entry(pa, e, &num, &den); dst = tw_a + e; }
+  else if ((e -= la) < lb) { nufft::v2_pass_table_entry(pb, e, &num, &den); dst = tw_b + e; }
+  else if ((e -= lb) < nhi) { num = e; den = nhi; dst = t_hi + e; }
+  else if ((e -= nhi) < nlo) { num = e; den = (int64_t)1 << ph; dst = t_lo + e; }
+  else return;
+  double sn, cs;
+  sincospi(2.0 * (double)num / (double)den, &sn, &cs);
+  *dst = make_float2((float)cs, (float)sn);
+}
+
+// kernel weights of every cadence: Wt[n w + q] = phi((d0_n + q) / (w / 2)), q = 0 .. w - 1
+__global__ void nufft2_weights_kernel(const nufft::Cad* __restrict__ cad, int64_t N, int w, float beta,
+                                      float* __restrict__ Wt) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * w) return;
+  const int64_t n = e / w;
+  const int q = (int)(e - n * w);
+  Wt[e] = nufft::es_eval((cad[n].d0 + (float)q) * (2.0f / (float)w), beta);
+}
+
+// z index (n = n1 Bc + n2) of position e of the G layout [c][n1][j]
+__device__ __forceinline__ int64_t v2_zcell_of(int64_t e, int ptc, int n1max) {
+  const int64_t j = e & (((int64_t)1 << ptc) - 1), rest = e >> ptc;
+  const int64_t n1 = rest % n1max, c = rest / n1max;
+  return (n1 << V2_PB) + (c << ptc) + j;
+}
+
+// ---- spread -------------------------------------------------------------------------------------------------------
+// G[lc][e] = (cell 2n, cell 2n + 1) of light curves lc0 .. lc0 + LCS - 1; grid (ceil(cells / 256), ceil(B / LCS)).
+// y rows [B, ystride] (centred flux); no scaling: a light curve's transform is its own.
+template <int LCS>
+__global__ void __launch_bounds__(256)
+nufft2_spread_kernel(const int32_t* __restrict__ first_ge, const nufft::Cad* __restrict__ cad,
+                     const float* __restrict__ Wt, const float* __restrict__ y, int64_t ystride, int B, int w, int p,
+                     int ptc, int n1max, float2* __restrict__ G) {
+  const int64_t cells = (int64_t)n1max << V2_PB;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cells) return;
+  const int64_t M = (int64_t)1 << p, m = 2 * v2_zcell_of(e, ptc, n1max);
+  const int lc0 = (int)blockIdx.y * LCS;
+  const float* yr[LCS];
+#pragma unroll
+  for (int q = 0; q < LCS; ++q) {
+    int b = lc0 + q;
+    if (b > B - 1) b = B - 1;                      // clamped rows are computed and dropped
+    yr[q] = y + (int64_t)b * ystride;
+  }
+  float a0[LCS], a1[LCS];
+#pragma unroll
+  for (int q = 0; q < LCS; ++q) { a0[q] = 0.0f; a1[q] = 0.0f; }
+  const int64_t L = nufft::table_len(M, w);
+  for (int wrap = 0; wrap < 2; ++wrap) {           // wrap = 1: cadences whose support runs past cell M - 1
+    const int64_t mm = m + (int64_t)wrap * M;
+    if (mm + 1 >= L) break;
+    int64_t lo_c = mm - w + 1, hi_c = mm + 2;
+    if (lo_c < 0) lo_c = 0;
+    if (hi_c > L - 1) hi_c = L - 1;
+    const int32_t na = first_ge[lo_c], nb = first_ge[hi_c];          // cadences with mm - w + 1 <= i0 <= mm + 1
+    for (int32_t n = na; n < nb; ++n) {
+      const int tap = (int)(mm - (int64_t)cad[n].i0);                // in [-1, w - 1]
+      const float* wr = Wt + (int64_t)n * w;
+      const float w0 = (tap >= 0) ? wr[tap] : 0.0f;                  // weight on cell mm
+      const float w1 = (tap + 1 < w) ? wr[tap + 1] : 0.0f;           // weight on cell mm + 1
+#pragma unroll
+      for (int q = 0; q < LCS; ++q) {
+        const float v = yr[q][n];
+        a0[q] = fmaf(w0, v, a0[q]);
+        a1[q] = fmaf(w1, v, a1[q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < LCS; ++q)
+    if (lc0 + q < B) G[(int64_t)(lc0 + q) * cells + e] = make_float2(a0[q], a1[q]);
+}
+
+// ---- in-place passes over the lines of a tile (compile-time geometry) ---------------------------------------------
+// PLOG: log2 of the line length, LS: skewed line stride, IDX / NS: pass number and the product of earlier radices.
+template <int PLOG, int LS, int IDX, int NS>
+__device__ __forceinline__ void v2_pass_t(float2* buf, const float2* __restrict__ tw) {
+  constexpr int R = v2_radix(PLOG, IDX);
+  if constexpr (R != 0) {
+    constexpr int LR = v2_log2i(R), NB = 16 / R, PNB = PLOG - LR, nb = 1 << PNB;      // nb butterflies per line
+    constexpr bool WIDE = nb > V2_THREADS;           // one line, several butterflies of it per thread
+    static_assert(WIDE || (V2_THREADS % nb) == 0, "geometry");
+    // per-input offset r * nb in the skewed line: v2_in_off<nb>(r)
+    const int t = (int)threadIdx.x;
+    float2 u[NB][R];
+    int base_in[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      int line, i;
+      if constexpr (WIDE) { line = 0; i = t + V2_THREADS * q; }
+      else { line = (t >> PNB) + ((V2_THREADS * q) >> PNB); i = t & (nb - 1); }
+      base_in[q] = line * LS + ((nb % 16 == 0) ? v2_skew(i) : i);
+#pragma unroll
+      for (int r = 0; r < R; ++r) u[q][r] = buf[base_in[q] + v2_in_off<nb>(r)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      int line, i;
+      if constexpr (WIDE) { line = 0; i = t + V2_THREADS * q; }
+      else { line = (t >> PNB) + ((V2_THREADS * q) >> PNB); i = t & (nb - 1); }
+      const int k = i & (NS - 1);
+      if constexpr (NS > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) u[q][r] = nufft::cmul(u[q][r], tw[r * NS + k]);
+      }
+      nufft::SmallDft<R>::run(u[q]);
+      const int j = ((i - k) << LR) + k;
+      // NS = 1 (then R = 16): skew(16 i + r) = 17 i + r;  NS >= 16: skew(j + r NS) = skew(j) + r NS 17 / 16
+      const int base_out = line * LS + ((NS == 1) ? (j + i) : v2_skew(j));
+#pragma unroll
+      for (int r = 0; r < R; ++r) buf[base_out + ((NS == 1) ? r : r * (NS + NS / 16))] = u[q][r];
+    }
+    __syncthreads();
+    v2_pass_t<PLOG, LS, IDX + 1, NS * R>(buf, tw + ((IDX > 0) ? R * NS : 0));
+  }
+}
+
+// ---- cols ---------------------------------------------------------------------------------------------------------
+// grid (Bc / TC, B).  G: pruned fine grids [B][c][n1 < n1max][j]; T: [B][c][k1][j]
+template <int PA>
+__global__ void __launch_bounds__(V2_THREADS, 2)
+nufft2_cols_kernel(const float2* __restrict__ G, float2* __restrict__ T, int n1max, const float2* __restrict__ tw_a,
+                   const float2* __restrict__ t_hi, const float2* __restrict__ t_lo) {
+  LKB_DYN_SMEM(float2, buf);
+  constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, LS = A + A / 16 + 1, C = V2_BC / TC;
+  // one sweep of the 512 threads covers JW columns x RW rows (RW is a multiple of 16: constant skew increments)
+  constexpr int JW = TC < 32 ? TC : 32, RW = V2_THREADS / JW, CG = TC / JW;
+  constexpr int LJW = JW == 32 ? 5 : JW == 16 ? 4 : JW == 8 ? 3 : JW == 4 ? 2 : JW == 2 ? 1 : 0;
+  static_assert((1 << LJW) == JW && RW % 16 == 0, "geometry");
+  const int t = (int)threadIdx.x, c = (int)blockIdx.x;
+  const int64_t lc = blockIdx.y;
+  const int jl = t & (JW - 1), nl = t >> LJW;
+  const int nvalid = n1max << PTC;
+  const float2* Gp = G + (lc * C + c) * (int64_t)nvalid;
+  const int s_base = jl * LS + v2_skew(nl), g_base = nl * TC + jl;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int cg = u % CG, nbk = u / CG;                           // column group, row block of this sweep
+    const int idx = g_base + nbk * RW * TC + cg * JW;
+    buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)] = (idx < nvalid) ? Gp[idx] : make_float2(0.0f, 0.0f);
+  }
+  __syncthreads();
+  v2_pass_t<PA, LS, 0, 1>(buf, tw_a);
+  float2* Tp = T + (lc * C + c) * (int64_t)V2_TILE;
+  const int ph = PA + V2_PB, pl = nufft::v2_log2_lo(ph);
+  const unsigned Mmask = (1u << ph) - 1u, lmask = (1u << pl) - 1u;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int cg = u % CG, nbk = u / CG;
+    const int k1 = nl + nbk * RW, n2 = c * TC + jl + cg * JW;
+    const unsigned q = ((unsigned)n2 * (unsigned)k1) & Mmask;       // n2 k1 < 2^22
+    const float2 wq = nufft::cmul(t_hi[q >> pl], t_lo[q & lmask]);
+    Tp[g_base + nbk * RW * TC + cg * JW] = nufft::cmul(buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)], wq);
+  }
+}
+
+// ---- rows + finish -----------------------------------------------------------------------------------------------
+// Folded per-frequency table (built once per call, y-independent): with G d = (C + i S) of a light curve at bin j,
+//   yc + i ys = E d1 + O d2 - ysum c2,   power = yc^2 wz + ys^2 ww
+//   d1 = dec conj(tau),  d2 = exp(2 pi i kk / M) d1,  c2 = (Ctau, Stau),  (wz, ww) = 1 / (2 N CC'), 1 / (2 N SS')
+struct V2FTab {
+  float4 d;       // d1.x, d1.y, d2.x, d2.y
+  float4 c;       // c2.x, c2.y, wz, ww
+};
+struct V2Finish {
+  const V2FTab* ftab;      // [F]
+  int64_t k0, F, k_lo;
+  const float* ysum;       // [B]
+  float Nf;
+  int normalization;
+  float scale;
+  float* power;            // [B, F]
+};
+
+__device__ __forceinline__ float v2_finish_power(float2 g1, float2 g2, const V2FTab tb, float ysum, float Nf,
+                                                 int normalization, float scale) {
+  const float ex = 0.5f * (g1.x + g2.x), ey = 0.5f * (g1.y - g2.y);        // E = (g1 + conj g2) / 2
+  const float ox = 0.5f * (g1.y + g2.y), oy = 0.5f * (g2.x - g1.x);        // O = (g1 - conj g2) / 2i
+  const float yc = ex * tb.d.x - ey * tb.d.y + ox * tb.d.z - oy * tb.d.w - ysum * tb.c.x;
+  const float ys = ex * tb.d.y + ey * tb.d.x + ox * tb.d.w + oy * tb.d.z - ysum * tb.c.y;
+  const float pw = yc * yc * tb.c.z + ys * ys * tb.c.w;
+  if (normalization == LKB_LS_NORM_PSD_SCALE) return pw * scale;
+  if (normalization == LKB_LS_NORM_AMPLITUDE) return sqrtf(pw * (4.0f / Nf));
+  return pw;
+}
+
+// MODE 1: finish -> power.  MODE 2: the modes k < nk2_keep * A and their mirrors Mh - k go to Zout [B][Mh] in natural
+// order (the ragged finish kernel reads them there).  grid (A / 16, B)
+template <int PA, int MODE>
+__global__ void __launch_bounds__(V2_THREADS, 2)
+nufft2_rows_kernel(const float2* __restrict__ T, const float2* __restrict__ tw_b, V2Finish fa, float2* __restrict__ Zout,
+                   int nk2_keep) {
+  LKB_DYN_SMEM(float2, buf);
+  constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, R = V2_R, LS = V2_LSB, Bc = V2_BC;
+  const int t = (int)threadIdx.x, g = (int)blockIdx.x;
+  const bool last = g == (A / (2 * R)) - 1;
+  const int64_t lc = blockIdx.y, Mh = (int64_t)1 << (PA + V2_PB);
+  auto slot_k1 = [&](int s) -> int {
+    const int h = s >> 3, r = s & (R - 1);
+    if (h == 0) return 1 + g * R + r;
+    if (last && r == 0) return 0;                    // instead of a second copy of row A / 2
+    return A - (g + 1) * R + r;
+  };
+  const float2* Tp = T + lc * Mh;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int e = t + V2_THREADS * u;
+    const int j = e & (TC - 1), r = (e >> PTC) & (R - 1), h = (e >> (PTC + 3)) & 1, c = e >> (PTC + 4);
+    const int s = h * R + r;
+    buf[s * LS + v2_skew((c << PTC) + j)] = Tp[(((c << PA) + slot_k1(s)) << PTC) + j];
+  }
+  __syncthreads();
+  v2_pass_t<V2_PB, LS, 0, 1>(buf, tw_b);
+  // one slot per thread for all its items: s = t % 16, k2 = t / 16 + 32 u
+  const int s = t & (2 * R - 1), h = s >> 3, r = s & (R - 1), k1 = slot_k1(s);
+  if (MODE == 2) {
+    const int keep = nk2_keep < Bc / 2 ? nk2_keep : Bc / 2;
+    for (int q = t >> 4; q < 2 * keep; q += V2_THREADS / 16) {
+      const int k2 = q < keep ? q : Bc - 2 * keep + q;          // [0, keep) and [Bc - keep, Bc)
+      Zout[lc * Mh + k1 + ((int64_t)k2 << PA)] = buf[s * LS + v2_skew(k2)];
+    }
+    return;
+  }
+  int ps = (1 - h) * R + (R - 1 - r);                              // mode Mh - k: row A - k1, column Bc - 1 - k2
+  bool row0 = false;
+  if (last && h == 0 && r == R - 1) ps = s;                        // row A / 2 mirrors onto itself
+  if (last && h == 1 && r == 0) { ps = s; row0 = true; }           // row 0: column (Bc - k2) mod Bc
+  int64_t nK2 = ((fa.k0 + fa.F - 1) >> PA) + 1;
+  if (nK2 > Bc) nK2 = Bc;
+  const float ys0 = fa.ysum[lc];
+  float* prow = fa.power + lc * fa.F;
+  const int64_t jbase = (int64_t)k1 - fa.k0;
+  for (int k2 = t >> 4; k2 < (int)nK2; k2 += V2_THREADS / 16) {
+    const int64_t jj = jbase + ((int64_t)k2 << PA);
+    if (jj < fa.k_lo || jj >= fa.F) continue;
+    const int pi = row0 ? ((Bc - k2) & (Bc - 1)) : (Bc - 1 - k2);
+    const float2 g1 = buf[s * LS + v2_skew(k2)], g2 = buf[ps * LS + v2_skew(pi)];
+    prow[jj] = v2_finish_power(g1, g2, fa.ftab[jj], ys0, fa.Nf, fa.normalization, fa.scale);
+  }
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------------------------
+inline unsigned v2_blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+struct V2Tables {
+  const float2 *tw_a, *tw_b, *t_hi, *t_lo;
+};
+// twiddle tables of the transform of 2^p real cells in workspace slot `slot`
+inline int v2_tables(int p, int slot, cudaStream_t st, V2Tables* out) {
+  const int ph = p - 1, pa = ph - V2_PB, pl = nufft::v2_log2_lo(ph);
+  const int la = nufft::v2_pass_table_len(pa), lb = nufft::v2_pass_table_len(V2_PB), nhi = 1 << (ph - pl), nlo = 1 << pl;
+  float2* base = nullptr;
+  LKB_TRY(ws_get_t<float2>(slot, (size_t)(la + lb + nhi + nlo + 4), &base));
+  float2 *tw_a = base, *tw_b = base + la, *t_hi = tw_b + lb, *t_lo = t_hi + nhi;
+  LKB_LAUNCH(v2_blocks_for(la + lb + nhi + nlo, 256), 256, st, nufft2_tables_kernel)(pa, V2_PB, ph, tw_a, tw_b, t_hi, t_lo);
+  LKB_LAUNCH_CHECK();
+  out->tw_a = tw_a; out->tw_b = tw_b; out->t_hi = t_hi; out->t_lo = t_lo;
+  return LKB_OK;
+}
+// rows n1 of the [A][Bc] grid of z cells that cadences can reach when the last one's support starts at cell i0_last
+inline int v2_n1max(int p, int64_t i0_last, int w) {
+  const int64_t M = (int64_t)1 << p, A = (M / 2) >> V2_PB;
+  const int64_t reach = i0_last + w + 1;                   // fine-grid cells [0, reach) (a support past M wraps to 0)
+  if (reach >= M) return (int)A;
+  const int64_t n = ((reach + 1) / 2 + V2_BC - 1) >> V2_PB;
+  return (int)(n < 1 ? 1 : (n > A ? A : n));
+}
+inline bool v2_supported(int p) { return p >= V2R_P_MIN && p <= V2R_P_MAX; }
+
+template <int PA>
+int v2_cols_pa(const float2* G, float2* T, int n1max, int B, const V2Tables& tb, cudaStream_t st) {
+  constexpr int A = 1 << PA, TC = V2_TILE / A;
+  const size_t smem = (size_t)TC * (A + A / 16 + 1) * sizeof(float2);
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_LAUNCH_SMEM(dim3((unsigned)(V2_BC / TC), (unsigned)B), V2_THREADS, smem, st, nufft2_cols_kernel<PA>)(
+      G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
+}
+template <int PA>
+int v2_rows_pa(const float2* T, int B, const V2Tables& tb, const V2Finish* fa, float2* Zout, int nk2_keep, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * V2_R) * V2_LSB * sizeof(float2);
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1>)(T, tb.tw_b, *fa, nullptr, 0);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
+}
+#define V2_DISPATCH_PA(pa, CALL)                                                                       \
+  switch (pa) {                                                                                         \
+    case 4: return CALL(4); case 5: return CALL(5); case 6: return CALL(6); case 7: return CALL(7);      \
+    case 8: return CALL(8); case 9: return CALL(9); case 10: return CALL(10); case 11: return CALL(11);  \
+    case 12: return CALL(12); case 13: return CALL(13);                                                  \
+    default: set_error("NUFFT v2: fine grid of 2^%d cells out of range", (pa) + V2_PB + 1); return LKB_E_UNSUPPORTED; \
+  }
+// G -> T for B transforms of 2^p real cells
+inline int v2_cols(const float2* G, float2* T, int p, int n1max, int B, const V2Tables& tb, cudaStream_t st) {
+#define V2_CALL(PA) v2_cols_pa<PA>(G, T, n1max, B, tb, st)
+  V2_DISPATCH_PA(p - 1 - V2_PB, V2_CALL)
+#undef V2_CALL
+}
+// T -> power (fa != NULL) or -> Zout in natural order, modes k < nk2_keep * A and their mirrors
+inline int v2_rows(const float2* T, int p, int B, const V2Tables& tb, const V2Finish* fa, float2* Zout, int nk2_keep,
+                   cudaStream_t st) {
+#define V2_CALL(PA) v2_rows_pa<PA>(T, B, tb, fa, Zout, nk2_keep, st)
+  V2_DISPATCH_PA(p - 1 - V2_PB, V2_CALL)
+#undef V2_CALL
+}
+
+}  // namespace
+}  // namespace lkb

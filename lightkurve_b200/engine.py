@@ -64,7 +64,7 @@ def profile_read(max_n=512):
 # workspace slot numbers (enum Slot in csrc/common.cuh) for the diagnostic read-back
 WS_SLOTS = {name: i for i, name in enumerate(
     ["A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L", "M", "N", "O", "P"]
-    + ["IN%d" % i for i in range(8)] + ["OUT%d" % i for i in range(8)])}
+    + ["IN%d" % i for i in range(8)] + ["OUT%d" % i for i in range(8)] + ["X%d" % i for i in range(8)])}
 
 
 def ws_read(slot, count, dtype, offset_bytes=0):

@@ -55,7 +55,7 @@ int emu_nufft_shared_chunked(const double* t_rel, int64_t N, const float* yc, in
                              float* rot, float* rot2, int64_t F_low, int normalization, double norm_scale,
                              float* power, int chunk) {
   int rc = lkb::ls_nufft_prepare(t_rel, N, F, f0, df, reinterpret_cast<float4*>(rot), reinterpret_cast<float2*>(rot2),
-                                 F_low, nullptr);
+                                 F_low, nullptr, freq, ystride);
   for (int b0 = 0, c = 0; rc == LKB_OK && b0 < B; b0 += chunk, ++c) {
     const int nb = std::min(chunk, B - b0);
     rc = lkb::ls_nufft_run(t_rel, N, yc + (size_t)b0 * ystride, ystride, ysum + b0, absmax + b0, nb, freq, F,

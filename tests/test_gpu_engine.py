@@ -216,6 +216,36 @@ def test_ls_shared_host_pipeline_matches_single_shot(engine, monkeypatch):
         assert_ls_close(piped[b], np.sqrt(ols.ls_slow_psd(t, Y[b].astype(np.float64), freq)) * np.sqrt(4.0 / N))
 
 
+@pytest.mark.parametrize("algo", ["auto", "simt"])
+def test_ls_shared_plan_cache(engine, algo):
+    """The y-independent tables of the shared-grid call are cached between calls on the same (times, regular grid,
+    family): a second call must return bitwise the same powers, a call with other time stamps of the same count, or
+    another grid, must not see stale tables, and an unrelated entry point in between invalidates the cache."""
+    rng = np.random.default_rng(5)
+    N, B, F = 3000, 9, 20000
+    t = 100.0 + np.sort(rng.uniform(0, 80.0, N))
+    df = 1.0 / (5.0 * (t[-1] - t[0]))
+    freq = df * (1 + np.arange(F))
+    Y = (1 + 1e-3 * np.sin(2 * np.pi * 1.7 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
+    a = engine.ls_power_shared(t, Y, freq, "amplitude", algo=algo)
+    b = engine.ls_power_shared(t, Y, freq, "amplitude", algo=algo)              # plan found cached
+    assert np.array_equal(a, b)
+    c = engine.ls_power_shared(t, Y[:4], freq, "amplitude", algo=algo)          # another batch on the cached plan
+    assert np.array_equal(c, a[:4])
+    t2 = t.copy()
+    t2[1000:2000] += 1e-3                                                       # same count, same ends, other stamps
+    d = engine.ls_power_shared(t2, Y, freq, "amplitude", algo=algo)
+    ref = np.sqrt(ols.ls_slow_psd(t2, Y[2].astype(np.float64), freq[:3000])) * np.sqrt(4.0 / N)
+    assert_ls_close(d[2][:3000], ref)
+    assert not np.array_equal(d, a)
+    engine.nanmedian_std([Y[0].astype(np.float64)])                             # unrelated entry point (re-uses workspace)
+    e = engine.ls_power_shared(t2, Y, freq, "amplitude", algo=algo)
+    assert np.array_equal(e, d)
+    f = engine.ls_power_shared(t2, Y, 2 * freq, "amplitude", algo=algo)         # other grid
+    ref = np.sqrt(ols.ls_slow_psd(t2, Y[5].astype(np.float64), 2 * freq[:3000])) * np.sqrt(4.0 / N)
+    assert_ls_close(f[5][:3000], ref)
+
+
 def test_ls_shared_equals_ragged(engine):
     rng = np.random.default_rng(22)
     N, B, F = 1500, 9, 200

@@ -87,11 +87,12 @@ def _shared_inputs(seed, N, F, B, oversample=5.0, k0=1):
     (3, 5.0, 1, 2, 0, {"LKB_NUFFT_FFT": "smem"}),            # four-step transform in shared memory, one tile
     (3, 5.0, 2, 1, 2, {"LKB_NUFFT_FFT": "smem", "LKB_NUFFT_TWIDDLE_CHAIN": "1", "F": "1100", "LKB_NUFFT_TILE": "1024"}),  # 8 tiles
     (5, 1.0, 1, 2, 0, {"LKB_NUFFT_FFT": "fused", "F": "1100", "LKB_NUFFT_TILE": "1024"}),        # spreading fused in
-    # the v2 transform (default from 2^13 fine-grid cells): pruned column layout, table twiddles, finish in the row kernel
-    (3, 5.0, 1, 2, 0, {"F": "1500"}),                        # 2^13 cells: A = 16, one column CTA, one row CTA (the "last")
-    (5, 5.0, 2, 1, 2, {"F": "3500"}),                        # 2^14: A = 32, two row CTAs; psd; chunks of 2; k0 = 2
-    (4, 1.0, 1, 2, 0, {"F": "6000", "LKB_NUFFT_VERIFY": "1"}),      # 2^15, oversample 1: no pruning, wrap-around; self-check
-    (3, 5.0, 1, 2, 0, {"F": "3500", "LKB_NUFFT_GROUP_MB": "0.2"}),  # groups of one pair through the same buffers
+    # the v2 transform (default from 2^14 fine-grid cells): one real transform per light curve, pruned column layout,
+    # table twiddles, finish in the row kernel, low rows through the design-matrix table
+    (3, 5.0, 1, 2, 0, {"F": "3500"}),                        # 2^14 cells: A = 16, one column CTA, one row CTA (the "last")
+    (5, 5.0, 2, 1, 2, {"F": "7000"}),                        # 2^15: A = 32, two row CTAs; psd; chunks of 2; k0 = 2
+    (4, 1.0, 1, 2, 0, {"F": "14000", "LKB_NUFFT_VERIFY": "1"}),     # 2^16, oversample 1: no pruning, wrap-around; self-check
+    (17, 5.0, 1, 2, 0, {"F": "3500"}),                       # 17 light curves: two spread groups of 8 + 1, two low-row CTAs
 ])
 def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, oversample, k0, normalization, chunk, env):
     env = dict(env)
@@ -117,7 +118,7 @@ def test_shared_grid_translation_unit_on_the_emulator(emu, monkeypatch, B, overs
             ref = p * scale
             ex = np.abs(power[b] - ref) / (2e-5 * ref.max() + 2e-4 * ref)
         assert ex.max() < 0.5, (b, int(np.argmax(ex)), ex.max())
-    if F >= 1500 and "LKB_NUFFT_FFT" not in env:      # the v2 transform really ran: the global passes round differently
+    if F >= 3500 and "LKB_NUFFT_FFT" not in env:      # the v2 transform really ran: the global passes round differently
         monkeypatch.setenv("LKB_NUFFT_FFT", "global")
         monkeypatch.delenv("LKB_NUFFT_VERIFY", raising=False)
         power_g = np.zeros((B, F), np.float32)
@@ -148,11 +149,11 @@ def test_ragged_translation_unit_on_the_emulator(emu, monkeypatch, fft):
     if fft == "groups":
         monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.05")
     elif fft == "v2groups":
-        monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.7")       # 2^13 + 2^14 cells: 0.375 MB per pair -> one pair per group
+        monkeypatch.setenv("LKB_NUFFT_RAGGED_MB", "0.9")       # 2^14 + 2^15 cells: ~0.4 MB per light curve -> groups of two
     elif fft and fft != "v2":
         monkeypatch.setenv("LKB_NUFFT_FFT", fft)
     rng = np.random.default_rng(21)
-    B, F = 5, (1500 if fft.startswith("v2") else 240)        # 1500 bins: fine grids of 2^13 / 2^14 cells -> the v2 transform
+    B, F = 5, (3500 if fft.startswith("v2") else 240)        # 3500 bins: fine grids of 2^14 / 2^15 cells -> the v2 transform
     ns = [300, 77, 512, 150, 40]
     off = np.zeros(B + 1, np.int64)
     poff = np.zeros(B + 1, np.int64)

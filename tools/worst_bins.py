@@ -29,6 +29,7 @@ def main():
     t0 = time.time()
     worst, (bb, kk), excess = tf.worst_bin_excess(engine, t, Y, freq, algos, env=env)
     out = {"worst_excess": worst, "pairs": int(len(bb)), "seconds": time.time() - t0,
+           "note": "tol = stated tolerance 1e-5 max(P) + 1e-4 P; tol_data = floor relative to sqrt(2) std(y) as well",
            "p99_excess": {a: float(np.quantile(e, 0.99)) for a, e in excess.items()},
            "median_excess": {a: float(np.median(e)) for a, e in excess.items()}}
     print(json.dumps(out, indent=1))
