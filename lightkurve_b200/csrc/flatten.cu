@@ -10,6 +10,7 @@
 // K6 entry lkb_nanmedian_std is here too.
 #include "common.cuh"
 #include "select.cuh"
+#include "flatten_v2.cuh"
 #include <vector>
 
 namespace lkb {
@@ -360,6 +361,33 @@ static bool savgol_tables(int w, int p, std::vector<double>& coeffs, std::vector
   return true;
 }
 
+// Inverse normal matrix of the degree-p fit on the scaled abscissae u_k = (k - c) / c, c = (w - 1) / 2 (flatten_v2.cuh:
+// centre taps c_j = sum_s Ginv[0][s] (j / c)^s, edge polynomials beta = Ginv m).
+static bool savgol_ginv(int w, int p, F2Coef& cf) {
+  const int q = p + 1;
+  if (q > F2_MAXQ) return false;
+  const double c = 0.5 * (w - 1), sc = c > 0 ? c : 1.0;
+  std::vector<double> G((size_t)q * q, 0.0), I((size_t)q * q, 0.0);
+  for (int k = 0; k < w; ++k) {
+    const double u = (k - c) / sc;
+    double pr = 1.0;
+    std::vector<double> pw(q);
+    for (int r = 0; r < q; ++r) { pw[r] = pr; pr *= u; }
+    for (int r = 0; r < q; ++r)
+      for (int s2 = 0; s2 < q; ++s2) G[r * q + s2] += pw[r] * pw[s2];
+  }
+  for (int r = 0; r < q; ++r) I[r * q + r] = 1.0;
+  if (!solve_dense(G, I, q, q)) return false;
+  cf.q = q;
+  for (int i = 0; i < F2_MAXQ * F2_MAXQ; ++i) cf.Ginv[i] = 0.0;
+  for (int r = 0; r < q; ++r)
+    for (int s2 = 0; s2 < q; ++s2) cf.Ginv[r * q + s2] = I[r * q + s2];
+  cf.A[0] = I[0];
+  cf.A[1] = q > 2 ? I[2] / (sc * sc) : 0.0;
+  cf.A[2] = q > 4 ? I[4] / (sc * sc * sc * sc) : 0.0;
+  return true;
+}
+
 int savgol_tables_host(int w, int p, double* coeffs, double* edge) {
   LKB_REQUIRE(w >= 1 && (w & 1), "window_length must be a positive odd integer");
   LKB_REQUIRE(p >= 0 && p < w && p <= 12, "polyorder must be in [0, min(window_length-1, 12)]");
@@ -408,6 +436,63 @@ int flatten(const double* time, const double* flux, const double* flux_err, cons
   LKB_CUDA_CHECK(cudaStreamSynchronize(st));   // tables are locals
   (void)half;
 
+  double *o_flat = nullptr, *o_fe = nullptr, *o_tr = nullptr;
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT0, flat, total, &o_flat));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, flat_err, total, &o_fe));
+  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT2, trend, total, &o_tr));
+
+  // ---- v2 kernel (flatten_v2.cuh: bitmask bookkeeping, sliding-moment Savitzky-Golay) whenever the shapes allow ----
+  {
+    int64_t nmax = 0;
+    for (int b = 0; b < B; ++b) nmax = std::max(nmax, h_offsets[b + 1] - h_offsets[b]);
+    const int NM = polyorder <= 1 ? 1 : polyorder <= 3 ? 3 : 5;
+    int tile_out = std::min(2048, std::min(65536 / (8 * NM) - 2 * half - 1, 4094 - 2 * half));
+    // fourth-order power sums lose (tile half-length / half-window)^4 in the difference of prefix sums: short tiles
+    if (NM == 5) tile_out = std::min(tile_out, std::max(128, 10 * half));
+    F2Coef cf;
+    if (!getenv("LKB_FLATTEN_V1") && polyorder <= 5 && nmax <= F2_MAXN && tile_out >= 128 &&
+        savgol_ginv(window_length, polyorder, cf)) {
+      double* tro = nullptr;
+      int* d_status = nullptr;
+      LKB_TRY(ws_get_t<double>(WS_H, total, &tro));
+      LKB_TRY(ws_get_t<int>(WS_N, B, &d_status));
+      const size_t smem2 = ((sizeof(F2Smem) + 15) & ~(size_t)15) + sizeof(double) * (size_t)NM * (tile_out + 2 * half + 1);
+      static size_t attr2[3] = {0, 0, 0};
+      const int slot = NM == 1 ? 0 : NM == 3 ? 1 : 2;
+      if (smem2 > attr2[slot]) {
+        if (NM == 1) LKB_CUDA_CHECK(cudaFuncSetAttribute(flatten2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        else if (NM == 3) LKB_CUDA_CHECK(cudaFuncSetAttribute(flatten2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        else LKB_CUDA_CHECK(cudaFuncSetAttribute(flatten2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr2[slot] = smem2;
+      }
+      prof_begin(st);
+      if (NM == 1)
+        flatten2_kernel<1><<<B, F2_THREADS, smem2, st>>>(d_t, d_f, d_fe, d_ex, d_off, tro, window_length, break_tolerance,
+                                                      niters, sigma, cf, tile_out, o_flat, o_fe, o_tr, d_status);
+      else if (NM == 3)
+        flatten2_kernel<3><<<B, F2_THREADS, smem2, st>>>(d_t, d_f, d_fe, d_ex, d_off, tro, window_length, break_tolerance,
+                                                      niters, sigma, cf, tile_out, o_flat, o_fe, o_tr, d_status);
+      else
+        flatten2_kernel<5><<<B, F2_THREADS, smem2, st>>>(d_t, d_f, d_fe, d_ex, d_off, tro, window_length, break_tolerance,
+                                                      niters, sigma, cf, tile_out, o_flat, o_fe, o_tr, d_status);
+      prof_end(st);
+      LKB_LAUNCH_CHECK();
+      std::vector<int> h_status(B, 0);
+      LKB_CUDA_CHECK(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+      LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+      bool overflow = false;
+      for (int b = 0; b < B; ++b) overflow = overflow || h_status[b] == 2;
+      if (!overflow) {
+        LKB_TRY(stage_out_copy<double>(mem, flat, o_flat, total, st));
+        LKB_TRY(stage_out_copy<double>(mem, flat_err, o_fe, total, st));
+        LKB_TRY(stage_out_copy<double>(mem, trend, o_tr, total, st));
+        if (mem == LKB_MEM_HOST) LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+        return LKB_OK;
+      }
+      // a light curve with more gap segments than the v2 kernel's shared-memory list: the whole call re-runs below
+    }
+  }
+
   FlWs ws;
   LKB_TRY(ws_get_t<uint8_t>(WS_D, total, &ws.mask));
   LKB_TRY(ws_get_t<int32_t>(WS_E, total, &ws.cidx));
@@ -419,11 +504,6 @@ int flatten(const double* time, const double* flux, const double* flux_err, cons
   LKB_TRY(ws_get_t<int32_t>(WS_K, total + B, &ws.cuts));
   LKB_TRY(ws_get_t<double>(WS_L, total, &ws.xs));
   LKB_TRY(ws_get_t<double>(WS_M, total, &ws.ys));
-
-  double *o_flat = nullptr, *o_fe = nullptr, *o_tr = nullptr;
-  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT0, flat, total, &o_flat));
-  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT1, flat_err, total, &o_fe));
-  LKB_TRY(stage_out_alloc<double>(mem, WS_OUT2, trend, total, &o_tr));
 
   const size_t smem = sizeof(double) * (((window_length + 3) & ~3) + (size_t)(FL_TI + window_length) * 17 / 16 + 8);
   static size_t attr_smem = 0;

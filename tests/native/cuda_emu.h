@@ -135,6 +135,69 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int delta) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  lkb_emu::Block* b = lkb_emu::t_block;
+  const int t = lkb_emu::t_tid, w = t / 32, lane = t % 32, other = lane - delta;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  b->scratch[(size_t)w * 32 + lane] = bits;
+  b->warp[w].wait();
+  T out = v;
+  if (other >= 0 && b->alive[w * 32 + other]) {
+    const unsigned long long ob = b->scratch[(size_t)w * 32 + other];
+    memcpy(&out, &ob, sizeof(T));
+  }
+  b->warp[w].wait();
+  return out;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  lkb_emu::Block* b = lkb_emu::t_block;
+  const int t = lkb_emu::t_tid, w = t / 32, lane = t % 32;
+  b->scratch[(size_t)w * 32 + lane] = pred ? 1ull : 0ull;
+  b->warp[w].wait();
+  unsigned out = 0;
+  for (int l = 0; l < 32; ++l) {
+    const int ot = w * 32 + l;
+    if (ot < (int)b->alive.size() && b->alive[ot] && b->scratch[(size_t)w * 32 + l]) out |= 1u << l;
+  }
+  b->warp[w].wait();
+  return out;
+}
+inline unsigned __match_any_sync(unsigned, int value) {
+  lkb_emu::Block* b = lkb_emu::t_block;
+  const int t = lkb_emu::t_tid, w = t / 32, lane = t % 32;
+  b->scratch[(size_t)w * 32 + lane] = (unsigned long long)(long long)value;
+  b->warp[w].wait();
+  unsigned out = 0;
+  for (int l = 0; l < 32; ++l) {
+    const int ot = w * 32 + l;
+    if (ot < (int)b->alive.size() && b->alive[ot] && b->scratch[(size_t)w * 32 + l] == (unsigned long long)(long long)value)
+      out |= 1u << l;
+  }
+  b->warp[w].wait();
+  return out;
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { lkb_emu::t_block->warp[lkb_emu::t_tid / 32].wait(); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline unsigned __fns(unsigned mask, unsigned base, int offset) {      // offset-th set bit at or above `base` (offset > 0)
+  if (offset <= 0) return 0xffffffffu;
+  for (unsigned bpos = base; bpos < 32; ++bpos)
+    if ((mask >> bpos) & 1u) { if (--offset == 0) return bpos; }
+  return 0xffffffffu;
+}
+inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
+inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+inline int atomicAdd(int* addr, int v) {
+  std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
+  const int old = *addr;
+  *addr = old + v;
+  return old;
+}
+
 inline unsigned atomicMax(unsigned* addr, unsigned v) {
   std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
   const unsigned old = *addr;
