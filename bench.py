@@ -179,41 +179,88 @@ def cpu_reference_rate(t, Y, freq, n_lc, procs, pool=None):
     return len(freq) * len(t) * n_lc / dt, dt
 
 
+_REF = {}           # workload of the reference arm: set before the worker pool forks, so jobs carry only an index
+
+
+def _ref_index_worker(i):
+    t, Y, f0, df, nf, real = _REF["t"], _REF["Y"], _REF["f0"], _REF["df"], _REF["nf"], _REF["real"]
+    y = Y[i % len(Y)]
+    return _real_reference_worker((t, y, f0, f0 + df * nf)) if real else _cpu_ls_worker((t, y, f0, df, nf))
+
+
+def _real_reference_worker(args):
+    """One light curve through the REAL reference (lightkurve + astropy), if they are importable on this box."""
+    import lightkurve as lk
+    t, y, fmin, fmax = args
+    lc = lk.LightCurve(time=t, flux=y)
+    pg = lc.to_periodogram("lombscargle", minimum_frequency=fmin, maximum_frequency=fmax, oversample_factor=5,
+                           normalization="amplitude", ls_method="fast")
+    return float(pg.power.value[-1])
+
+
+def _have_real_reference():
+    try:
+        import astropy  # noqa: F401
+        import lightkurve  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU algorithm on the box's host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU algorithm on the box's host cores (rank 0 only).  The REAL lightkurve +
+    astropy call chain when importable (kind "reference"); else the oracle's restatement of astropy's default method
+    "fast" (kind "port" - astropy is in neither this image nor its wheelhouse).  Every step takes the next `n_lc`
+    DISTINCT light curves of the full 1024-curve workload; value = the median step; 1-core and all-core rates."""
     if rank != 0:
         return
-    name = args.workload
+    name = args.workload if args.workload in ("c2", "c2_small") else "c2"
     w = WORKLOADS[name]
     from multiprocessing import get_context
-    t, Y, freq = make_workload_sample(name, args.seed)
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count() or 1
-    n_lc = max(2 * cores, 8)
+    t, Y, freq = make_workload(name, args.seed)
+    cores = _cores()
+    real = _have_real_reference()
+    n_lc = min(w["B"], max(cores, 8))
+    f0, df, nf = float(freq[0]), float(freq[1] - freq[0]), len(freq)
+    _REF.update(t=t, Y=Y, f0=f0, df=df, nf=nf, real=real)
+    fn, job = _ref_index_worker, (lambda i: i)
     pool = get_context("fork").Pool(cores, initializer=_cpu_worker_init) if cores > 1 else None
-    for _ in range(args.warmup):
-        cpu_reference_rate(t, Y, freq, cores, cores, pool)
+
+    def step(k, n):
+        jobs = [job(k * n + i) for i in range(n)]
+        t0 = time.perf_counter()
+        if pool is None:
+            for j in jobs:
+                fn(j)
+        else:
+            pool.map(fn, jobs, chunksize=1)
+        return time.perf_counter() - t0
+
+    for k in range(args.warmup):
+        step(k, min(n_lc, cores))
+    secs = [step(args.warmup + k, n_lc) for k in range(args.steps)]
     t0 = time.perf_counter()
-    rates = []
-    for _ in range(args.steps):
-        r, _ = cpu_reference_rate(t, Y, freq, n_lc, cores, pool)
-        rates.append(r)
-    wall = time.perf_counter() - t0
+    for i in range(2):
+        fn(job(i))
+    one_core = 2 * nf * len(t) / (time.perf_counter() - t0)
     if pool is not None:
         pool.close()
         pool.join()
-    val = float(np.mean(rates))
+    med = float(np.median(secs))
+    val = nf * len(t) * n_lc / med
+    how = ("lightkurve.LightCurve.to_periodogram(ls_method='fast') on astropy" if real else
+           "astropy 'fast' (extirpolation + FFT) restated in oracle/ls.py")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s; CPU sample = %d light curves per step" % (name, w["desc"], n_lc)},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d light curves of the %d-LC workload per step, astropy 'fast' (extirpolation+FFT) "
-                                   "restated in oracle/ls.py, pool of %d single-threaded processes; "
-                                   "value = F*N*n/time" % (n_lc, w["B"], cores)},
+        "config": {"workload": "%s: %s; CPU sample = %d distinct light curves per step" % (name, w["desc"], n_lc)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference" if real else "port",
+                         "value_1core": one_core,
+                         "sample": "%d distinct light curves of the %d-LC workload per step (median of %d steps; "
+                                   "min %.0f / max %.0f ms), %s, pool of %d single-threaded processes; "
+                                   "value = F*N*n/time (the FFT method does far less than F*N work)" %
+                                   (n_lc, w["B"], args.steps, 1e3 * min(secs), 1e3 * max(secs), how, cores)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

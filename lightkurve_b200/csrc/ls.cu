@@ -1150,8 +1150,21 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
                            false, lowf_max, grid_f0, grid_df, normalization, ns, d_pow + (size_t)b_lo * F, sc, ev_join,
                            (sc != st) ? 1 : 0));
       LKB_CUDA_CHECK(cudaEventRecord(e_out, sc));
+      // The power rows of chunk c - 1 go down only now, AFTER chunk c has been enqueued (s_d2h has waited for chunk
+      // c - 1 only): into pageable memory (a plain numpy array) cudaMemcpyAsync blocks the host until the copy is
+      // done, and issued right after its own chunk it would keep chunk c + 1 from being enqueued - no overlap at all
+      // (ADVICE.md, round 1).  One chunk late, the blocking copy runs while the next chunk computes; page-locked
+      // destinations are asynchronous either way.
+      if (c > 0) {
+        const int p_lo = (c - 1) * PIPE_CHUNK, p_nb = min(PIPE_CHUNK, B - p_lo);
+        LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)p_lo * F, d_pow + (size_t)p_lo * F, (size_t)p_nb * F * sizeof(float),
+                                       cudaMemcpyDeviceToHost, s_d2h));
+      }
       LKB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, e_out, 0));
-      LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)b_lo * F, d_pow + (size_t)b_lo * F, (size_t)nb * F * sizeof(float),
+    }
+    {
+      const int p_lo = (nchunk - 1) * PIPE_CHUNK, p_nb = min(PIPE_CHUNK, B - p_lo);
+      LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)p_lo * F, d_pow + (size_t)p_lo * F, (size_t)p_nb * F * sizeof(float),
                                      cudaMemcpyDeviceToHost, s_d2h));
     }
     if (cs[1] != st) LKB_CUDA_CHECK(cudaStreamSynchronize(cs[1]));

@@ -361,70 +361,69 @@ __global__ void nufft2_lowtab_kernel(const double* __restrict__ t, int64_t N, in
   D[e] = make_float2(cm1, sn);
 }
 
-// power of the low rows: out[b][r] from sum_n y_b[n] D[r][n]; one warp = 2 light curves, one CTA = 16 light curves
-// sharing every 256-cadence slice of D through shared memory; rows in groups of LOWR.
+// sums of the low rows: acc[b][r] += sum over this CTA's cadence slice of y_b[n] D[r][n] (fp64 atomics; acc zeroed by
+// the caller).  grid (ceil(B / 16), S): one warp = 2 light curves, one CTA = 16 light curves sharing every 256-cadence
+// slice of D through shared memory, the cadence range split S ways so that a small batch still fills the SMs (the
+// first version walked all cadences in 64 CTAs: 1.9 ms for 11 rows, latency-bound).  Rows in groups of LOWR.
 constexpr int LOWR = 12;
 __global__ void __launch_bounds__(256)
 nufft2_lowrows_kernel(const float2* __restrict__ D, int64_t N, int64_t Npad, const float* __restrict__ yc,
-                      int64_t ystride, int B, int F_low, int64_t F, const float4* __restrict__ rot,
-                      const float2* __restrict__ rot2, const float* __restrict__ ysum, int normalization, float scale,
-                      float* __restrict__ power) {
+                      int64_t ystride, int B, int F_low, int64_t slice, double* __restrict__ acc) {
   __shared__ float2 sD[LOWR][256];
   const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
   const int b0 = (int)blockIdx.x * 16 + 2 * warp, b1 = b0 + 1;
   const float* y0 = yc + (int64_t)(b0 < B ? b0 : B - 1) * ystride;
   const float* y1 = yc + (int64_t)(b1 < B ? b1 : B - 1) * ystride;
+  const int64_t n_lo = (int64_t)blockIdx.y * slice, n_hi = (n_lo + slice < N) ? n_lo + slice : N;
   for (int r0 = 0; r0 < F_low; r0 += LOWR) {
     const int nr = (F_low - r0 < LOWR) ? F_low - r0 : LOWR;
-    double dc0[LOWR], ds0[LOWR], dc1[LOWR], ds1[LOWR];
+    float ac0[LOWR], as0[LOWR], ac1[LOWR], as1[LOWR];
 #pragma unroll
-    for (int r = 0; r < LOWR; ++r) { dc0[r] = ds0[r] = dc1[r] = ds1[r] = 0.0; }
-    for (int64_t c0 = 0; c0 < N; c0 += 256 * 8) {                 // fp32 partial sums over 2048 cadences, then fp64
-      float ac0[LOWR], as0[LOWR], ac1[LOWR], as1[LOWR];
+    for (int r = 0; r < LOWR; ++r) { ac0[r] = as0[r] = ac1[r] = as1[r] = 0.0f; }
+    for (int64_t s0 = n_lo; s0 < n_hi; s0 += 256) {               // <= slice / 32 terms per lane in fp32
+      __syncthreads();
+      for (int r = 0; r < nr; ++r) {
+        const int64_t n = s0 + threadIdx.x;
+        sD[r][threadIdx.x] = (n < n_hi) ? D[(int64_t)(r0 + r) * Npad + n] : make_float2(0.f, 0.f);
+      }
+      __syncthreads();
 #pragma unroll
-      for (int r = 0; r < LOWR; ++r) { ac0[r] = as0[r] = ac1[r] = as1[r] = 0.0f; }
-      for (int64_t s0 = c0; s0 < c0 + 256 * 8 && s0 < N; s0 += 256) {
-        __syncthreads();
-        for (int r = 0; r < nr; ++r) {
-          const int64_t n = s0 + threadIdx.x;
-          sD[r][threadIdx.x] = (n < Npad) ? D[(int64_t)(r0 + r) * Npad + n] : make_float2(0.f, 0.f);
-        }
-        __syncthreads();
+      for (int q = 0; q < 8; ++q) {
+        const int64_t n = s0 + lane + 32 * q;
+        const float v0 = (n < n_hi) ? y0[n] : 0.0f, v1 = (n < n_hi) ? y1[n] : 0.0f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int64_t n = s0 + lane + 32 * q;
-          const float v0 = (n < N) ? y0[n] : 0.0f, v1 = (n < N) ? y1[n] : 0.0f;
-#pragma unroll
-          for (int r = 0; r < LOWR; ++r) {
-            if (r < nr) {
-              const float2 d = sD[r][lane + 32 * q];
-              ac0[r] = fmaf(v0, d.x, ac0[r]); as0[r] = fmaf(v0, d.y, as0[r]);
-              ac1[r] = fmaf(v1, d.x, ac1[r]); as1[r] = fmaf(v1, d.y, as1[r]);
-            }
+        for (int r = 0; r < LOWR; ++r) {
+          if (r < nr) {
+            const float2 d = sD[r][lane + 32 * q];
+            ac0[r] = fmaf(v0, d.x, ac0[r]); as0[r] = fmaf(v0, d.y, as0[r]);
+            ac1[r] = fmaf(v1, d.x, ac1[r]); as1[r] = fmaf(v1, d.y, as1[r]);
           }
         }
-      }
-#pragma unroll
-      for (int r = 0; r < LOWR; ++r) {
-        dc0[r] += (double)ac0[r]; ds0[r] += (double)as0[r]; dc1[r] += (double)ac1[r]; ds1[r] += (double)as1[r];
       }
     }
 #pragma unroll
     for (int r = 0; r < LOWR; ++r) {
       if (r < nr) {
-        const double c0v = warp_sum(dc0[r]), s0v = warp_sum(ds0[r]), c1v = warp_sum(dc1[r]), s1v = warp_sum(ds1[r]);
+        const double c0v = warp_sum((double)ac0[r]), s0v = warp_sum((double)as0[r]);
+        const double c1v = warp_sum((double)ac1[r]), s1v = warp_sum((double)as1[r]);
         if (lane == 0) {
-          const int k = r0 + r;
-          if (b0 < B)
-            power[(int64_t)b0 * F + k] = ls_epilogue_shared((float)c0v, (float)s0v, rot[k], rot2[k], ysum[b0], (float)N,
-                                                           normalization, scale, true);
-          if (b1 < B)
-            power[(int64_t)b1 * F + k] = ls_epilogue_shared((float)c1v, (float)s1v, rot[k], rot2[k], ysum[b1], (float)N,
-                                                           normalization, scale, true);
+          if (b0 < B) { atomicAdd(acc + ((int64_t)b0 * F_low + r0 + r) * 2, c0v); atomicAdd(acc + ((int64_t)b0 * F_low + r0 + r) * 2 + 1, s0v); }
+          if (b1 < B) { atomicAdd(acc + ((int64_t)b1 * F_low + r0 + r) * 2, c1v); atomicAdd(acc + ((int64_t)b1 * F_low + r0 + r) * 2 + 1, s1v); }
         }
       }
     }
   }
+}
+// epilogue of the low rows
+__global__ void nufft2_lowfinish_kernel(const double* __restrict__ acc, int B, int F_low, int64_t F, int64_t N,
+                                        const float4* __restrict__ rot, const float2* __restrict__ rot2,
+                                        const float* __restrict__ ysum, int normalization, float scale,
+                                        float* __restrict__ power) {
+  const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (e >= B * F_low) return;
+  const int b = e / F_low, k = e - b * F_low;
+  power[(int64_t)b * F + k] = ls_epilogue_shared((float)acc[2 * (int64_t)e], (float)acc[2 * (int64_t)e + 1], rot[k], rot2[k],
+                                                 ysum[b], (float)N, normalization, scale, true);
 }
 
 // Self-check of the v2 path: Zn [nv][Mh] holds the transforms of the first nv light curves in natural order (modes
@@ -721,8 +720,18 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
       LKB_TRY(v2_rows(T, p, B, pl.tb, &fa, nullptr, 0, st));
     }
     if (F_low > 0) {
-      LKB_LAUNCH(blocks_for(B, 16), 256, st, nufft2_lowrows_kernel)(pl.lowD, N, pl.Npad, d_yc, ystride, B, (int)F_low, F, d_rot,
-                                                               d_rot2, d_ysumf, normalization, (float)norm_scale, d_pow);
+      double* acc = nullptr;
+      LKB_TRY(ws_get_t<double>(ws_alt ? WS_X4 : WS_X3, (size_t)B * F_low * 2, &acc));
+      LKB_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)B * F_low * 2, st));
+      const int groups = (B + 15) / 16;
+      int S = (600 + groups - 1) / groups;                     // ~2 waves of CTAs whatever the batch size
+      S = S < 1 ? 1 : (S > 64 ? 64 : S);
+      const int64_t slice = (((N + S - 1) / S + 255) / 256) * 256;
+      LKB_LAUNCH(dim3((unsigned)groups, (unsigned)((N + slice - 1) / slice)), 256, st, nufft2_lowrows_kernel)(
+          pl.lowD, N, pl.Npad, d_yc, ystride, B, (int)F_low, slice, acc);
+      LKB_LAUNCH_CHECK();
+      LKB_LAUNCH(blocks_for((int64_t)B * F_low, 256), 256, st, nufft2_lowfinish_kernel)(
+          acc, B, (int)F_low, F, N, d_rot, d_rot2, d_ysumf, normalization, (float)norm_scale, d_pow);
       LKB_LAUNCH_CHECK();
     }
     if (prof) prof_end(st);

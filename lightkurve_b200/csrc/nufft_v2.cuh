@@ -139,8 +139,9 @@ nufft2_spread_kernel(const int32_t* __restrict__ first_ge, const nufft::Cad* __r
 
 // ---- in-place passes over the lines of a tile (compile-time geometry) ---------------------------------------------
 // PLOG: log2 of the line length, LS: skewed line stride, IDX / NS: pass number and the product of earlier radices.
+// nz (first pass only): line positions >= nz hold zeros that were never stored - they are not read either
 template <int PLOG, int LS, int IDX, int NS>
-__device__ __forceinline__ void v2_pass_t(float2* buf, const float2* __restrict__ tw) {
+__device__ __forceinline__ void v2_pass_t(float2* buf, const float2* __restrict__ tw, int nz = 1 << 30) {
   constexpr int R = v2_radix(PLOG, IDX);
   if constexpr (R != 0) {
     constexpr int LR = v2_log2i(R), NB = 16 / R, PNB = PLOG - LR, nb = 1 << PNB;      // nb butterflies per line
@@ -157,7 +158,8 @@ __device__ __forceinline__ void v2_pass_t(float2* buf, const float2* __restrict_
       else { line = (t >> PNB) + ((V2_THREADS * q) >> PNB); i = t & (nb - 1); }
       base_in[q] = line * LS + ((nb % 16 == 0) ? v2_skew(i) : i);
 #pragma unroll
-      for (int r = 0; r < R; ++r) u[q][r] = buf[base_in[q] + v2_in_off<nb>(r)];
+      for (int r = 0; r < R; ++r)
+        u[q][r] = (IDX > 0 || r * nb < nz) ? buf[base_in[q] + v2_in_off<nb>(r)] : make_float2(0.0f, 0.0f);
     }
     __syncthreads();
 #pragma unroll
@@ -200,14 +202,19 @@ nufft2_cols_kernel(const float2* __restrict__ G, float2* __restrict__ T, int n1m
   const int nvalid = n1max << PTC;
   const float2* Gp = G + (lc * C + c) * (int64_t)nvalid;
   const int s_base = jl * LS + v2_skew(nl), g_base = nl * TC + jl;
+  // rows the first pass reads: whole input blocks (of A / R1 rows) that contain a row < n1max
+  constexpr int NB1 = A / v2_radix(PA, 0);
+  const int nz = ((n1max + NB1 - 1) / NB1) * NB1;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int cg = u % CG, nbk = u / CG;                           // column group, row block of this sweep
-    const int idx = g_base + nbk * RW * TC + cg * JW;
-    buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)] = (idx < nvalid) ? Gp[idx] : make_float2(0.0f, 0.0f);
+    if (nbk * RW < nz) {
+      const int idx = g_base + nbk * RW * TC + cg * JW;
+      buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)] = (idx < nvalid) ? Gp[idx] : make_float2(0.0f, 0.0f);
+    }
   }
   __syncthreads();
-  v2_pass_t<PA, LS, 0, 1>(buf, tw_a);
+  v2_pass_t<PA, LS, 0, 1>(buf, tw_a, nz);
   float2* Tp = T + (lc * C + c) * (int64_t)V2_TILE;
   const int ph = PA + V2_PB, pl = nufft::v2_log2_lo(ph);
   const unsigned Mmask = (1u << ph) - 1u, lmask = (1u << pl) - 1u;
@@ -297,12 +304,26 @@ nufft2_rows_kernel(const float2* __restrict__ T, const float2* __restrict__ tw_b
   const float ys0 = fa.ysum[lc];
   float* prow = fa.power + lc * fa.F;
   const int64_t jbase = (int64_t)k1 - fa.k0;
-  for (int k2 = t >> 4; k2 < (int)nK2; k2 += V2_THREADS / 16) {
-    const int64_t jj = jbase + ((int64_t)k2 << PA);
-    if (jj < fa.k_lo || jj >= fa.F) continue;
-    const int pi = row0 ? ((Bc - k2) & (Bc - 1)) : (Bc - 1 - k2);
-    const float2 g1 = buf[s * LS + v2_skew(k2)], g2 = buf[ps * LS + v2_skew(pi)];
-    prow[jj] = v2_finish_power(g1, g2, fa.ftab[jj], ys0, fa.Nf, fa.normalization, fa.scale);
+  constexpr int KSTEP = V2_THREADS / 16, UB = 4;                   // items of a thread: k2 = t / 16 + 32 u
+  for (int k2b = t >> 4; k2b < (int)nK2; k2b += KSTEP * UB) {
+    V2FTab tb[UB];
+    int64_t jj[UB];
+    bool valid[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {                                 // all table loads of the batch in flight together
+      const int k2 = k2b + KSTEP * u;
+      jj[u] = jbase + ((int64_t)k2 << PA);
+      valid[u] = k2 < (int)nK2 && jj[u] >= fa.k_lo && jj[u] < fa.F;
+      if (valid[u]) tb[u] = fa.ftab[jj[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (!valid[u]) continue;
+      const int k2 = k2b + KSTEP * u;
+      const int pi = row0 ? ((Bc - k2) & (Bc - 1)) : (Bc - 1 - k2);
+      const float2 g1 = buf[s * LS + v2_skew(k2)], g2 = buf[ps * LS + v2_skew(pi)];
+      prow[jj[u]] = v2_finish_power(g1, g2, tb[u], ys0, fa.Nf, fa.normalization, fa.scale);
+    }
   }
 }
 

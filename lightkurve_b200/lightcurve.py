@@ -331,14 +331,22 @@ class LightCurve:
         new.flux_err = Quantity(berr, self.flux_err.unit)
         return new
 
-    def remove_outliers(self, sigma=5.0, sigma_lower=None, sigma_upper=None, return_mask=False, **kwargs):
-        """Sigma-clip outliers (lightcurve.py:1429-1549; astropy sigma_clip defaults:
-        maxiters=5, median centre, std).  Centre/spread come from the GPU select kernel."""
+    def remove_outliers(self, sigma=5.0, sigma_lower=None, sigma_upper=None, return_mask=False, column="flux", **kwargs):
+        """Sigma-clip outliers of `column` (lightcurve.py:1429-1549; astropy sigma_clip defaults:
+        maxiters=5, median centre, std).  Centre/spread come from the GPU select kernel; of astropy's further
+        ``sigma_clip`` keywords only ``maxiters`` and the defaults ``cenfunc="median"`` / ``stdfunc="std"`` are
+        implemented - anything else raises instead of being silently ignored."""
         from . import engine
         maxiters = kwargs.pop("maxiters", 5)
+        if kwargs.pop("cenfunc", "median") not in ("median", np.median, np.nanmedian) or \
+                kwargs.pop("stdfunc", "std") not in ("std", np.std, np.nanstd):
+            raise NotImplementedError("remove_outliers(): only cenfunc='median' and stdfunc='std' run on the GPU kernel")
+        if kwargs:
+            raise TypeError("remove_outliers(): unsupported sigma_clip keyword(s) %s" % sorted(kwargs))
         lo_s = sigma if sigma_lower is None else sigma_lower
         hi_s = sigma if sigma_upper is None else sigma_upper
-        data = np.array(self.flux.value, dtype=np.float64)
+        col = getattr(self, column)
+        data = np.array(getattr(col, "value", col), dtype=np.float64)
         mask = ~np.isfinite(data)
         it = 0
         while maxiters is None or it < maxiters:

@@ -191,6 +191,12 @@ inline unsigned __fns(unsigned mask, unsigned base, int offset) {      // offset
 }
 inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+inline double atomicAdd(double* addr, double v) {
+  std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
+  const double old = *addr;
+  *addr = old + v;
+  return old;
+}
 inline int atomicAdd(int* addr, int v) {
   std::lock_guard<std::mutex> lk(lkb_emu::g_atomic_mu);
   const int old = *addr;

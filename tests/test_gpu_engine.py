@@ -450,6 +450,35 @@ def test_flatten_vs_oracle(engine, window_length, polyorder, niters):
         np.testing.assert_allclose(flat_err[b], rfe, rtol=1e-9, equal_nan=True)
 
 
+def test_flatten_kernel_generations_agree(engine, monkeypatch):
+    """The streaming kernel (flatten_v2.cuh, default) and the round-1 FIR kernel (LKB_FLATTEN_V1=1) on the same light
+    curves; a light curve with more gap segments than the streaming kernel's shared-memory list (status 2) makes the
+    whole call re-run on the first kernel - the result is the oracle's either way; polyorder 6 is first-kernel only."""
+    rng = np.random.default_rng(77)
+    lcs = [make_trend_lc(rng, n) for n in (5000, 2500)]
+    args = dict(window_length=101, polyorder=2, niters=3)
+    a = engine.flatten([l[0] for l in lcs], [l[1] for l in lcs], [l[2] for l in lcs], None, **args)
+    monkeypatch.setenv("LKB_FLATTEN_V1", "1")
+    b = engine.flatten([l[0] for l in lcs], [l[1] for l in lcs], [l[2] for l in lcs], None, **args)
+    monkeypatch.delenv("LKB_FLATTEN_V1")
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            np.testing.assert_allclose(u, v, rtol=1e-9, equal_nan=True)
+    # 1500 gaps of 10 cadence steps each, segments of 8 cadences: all median fallbacks, more than 1023 segments
+    n_seg, seg_len = 1500, 8
+    idx = (np.arange(n_seg)[:, None] * (seg_len + 10) + np.arange(seg_len)[None, :]).ravel()
+    t = 100.0 + idx * 0.02
+    f = 1 + 1e-3 * np.sin(t) + 1e-4 * rng.normal(size=len(t))
+    fe = np.full(len(t), 1e-4)
+    flat, _, trend = engine.flatten([t, lcs[0][0]], [f, lcs[0][1]], [fe, lcs[0][2]], None, window_length=5, polyorder=2)
+    rf, _, rt = odet.flatten(t, f, fe, window_length=5, polyorder=2)
+    np.testing.assert_allclose(trend[0], rt, rtol=1e-9)
+    np.testing.assert_allclose(flat[0], rf, rtol=1e-9)
+    flat6, _, trend6 = engine.flatten([lcs[1][0]], [lcs[1][1]], [lcs[1][2]], None, window_length=51, polyorder=6)
+    np.testing.assert_allclose(trend6[0], odet.flatten(lcs[1][0], lcs[1][1], lcs[1][2], window_length=51, polyorder=6)[2],
+                               rtol=1e-8)
+
+
 def test_flatten_reference_known_answers(engine):
     """reference tests/test_lightcurve.py:1297-1317."""
     t = np.arange(6.0)

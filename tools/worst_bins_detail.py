@@ -32,6 +32,25 @@ def main():
         ref[sel] = tf._oracle_amplitude(t, Y[b], freq[kk[sel]])
     tol_ref = 1e-5 * np.maximum(pmax[bb], ref) + 1e-4 * ref
     ex = {a: np.abs(outs[a][bb, kk] - ref) / tol_ref for a in algos}
+    # candidates for NUFFT misses as well: where it differs most from tcgen05, and the bins just above the low rows
+    d2 = np.abs(outs["tcgen05"] - outs["nufft"]) / tol
+    flat2 = np.argpartition(d2.ravel(), -1500)[-1500:]
+    b2, k2 = np.unravel_index(flat2, (B, F))
+    lowb = np.repeat(np.arange(B), 8)
+    lowk = np.tile(np.arange(8, 16), B)
+    bb2, kk2 = np.concatenate([b2, lowb]), np.concatenate([k2, lowk])
+    ref2 = np.empty(len(bb2))
+    for b in np.unique(bb2):
+        sel = bb2 == b
+        ref2[sel] = tf._oracle_amplitude(t, Y[b], freq[kk2[sel]])
+    tol2 = 1e-5 * np.maximum(pmax[bb2], ref2) + 1e-4 * ref2
+    exn = np.abs(outs["nufft"][bb2, kk2] - ref2) / tol2
+    print("NUFFT: its 25 worst pairs among %d candidates (b, k, f*T, oracle, nufft, pmax_b, excess, |k - k_peak|, std(y))" % len(bb2))
+    kpk0 = outs["nufft"].argmax(axis=1)
+    for i in np.argsort(-exn)[:25]:
+        b, k = int(bb2[i]), int(kk2[i])
+        print("%5d %7d %9.2f %12.5e %12.5e %10.3e %6.2f %7d %10.3e" % (b, k, freq[k] * T, ref2[i], outs["nufft"][b, k], pmax[b],
+                                                                  exn[i], abs(k - int(kpk0[b])), Y[b].astype(np.float64).std()))
     order = np.argsort(-np.maximum(ex["nufft"], ex["simt"]))[:40]
     print("baseline T = %.3f d, df*T = %.3f; rows with f*T <= 2 are 'low rows'" % (T, freq[0] * T))
     print("%5s %7s %8s %12s %12s %12s %12s %10s %10s | excess nufft simt tc | partner pmax" %
