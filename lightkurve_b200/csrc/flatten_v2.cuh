@@ -39,6 +39,7 @@ struct F2Coef {
 };
 
 struct F2Smem {
+  FastSelSmem fs;                               // sampling select (median in two passes)
   unsigned keep[F2_MAXWORDS];                   // bit i: cadence i is used for the fit
   int wpre[F2_MAXWORDS + 1];                    // kept cadences before word w
   int cuts[F2_MAXSEG + 1];                      // segment starts (positions in the kept sequence), cuts[nseg] = m
@@ -154,6 +155,8 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
   LKB_DYN_SMEM(unsigned char, f2_dyn);
   F2Smem& sm = *reinterpret_cast<F2Smem*>(f2_dyn);
   double* P = reinterpret_cast<double*>(f2_dyn + ((sizeof(F2Smem) + 15) & ~(size_t)15));     // NM arrays of plen doubles
+  if (threadIdx.x == 0) sm.fs.cand = P;        // the select's candidate buffer aliases the (then idle) prefix arrays
+  __syncthreads();
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int64_t o = offsets[b];
   const int n = (int)(offsets[b + 1] - o);
@@ -167,7 +170,8 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
   const double sc = half > 0 ? (double)half : 1.0;
 
   // ---- initial mask (:996-1010): finite, not excluded, within sigma * nanstd of the nanmedian ----
-  const double med0 = block_nanmedian([&](int64_t i) { const double v = f[i]; return isfinite(v) ? v : qnan; }, n, sm.sel);
+  const double med0 = block_nanmedian_fast([&](int64_t i) { const double v = f[i]; return isfinite(v) ? v : qnan; }, n,
+                                           sm.sel, sm.fs);
   const double std0 = block_nanstd([&](int64_t i) { return f[i]; }, n, sm.sel);
   {
     const double thr = std0 * sigma;
@@ -193,11 +197,11 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
     m = f2_prefix(sm, nw);
     if (m < 2) { ok = false; break; }
     // ---- gap segmentation (:1022-1027): cut where dt > break_tolerance * nanmedian(dt) over the kept cadences ----
-    const double med_dt = block_nanmedian([&](int64_t i) {
+    const double med_dt = block_nanmedian_fast([&](int64_t i) {
       if (!f2_kept(sm, (int)i)) return qnan;
       const int pv = f2_prev(sm, (int)i);
       return pv < 0 ? qnan : tt[i] - tt[pv];
-    }, n, sm.sel);
+    }, n, sm.sel, sm.fs, (long long)m - 1);
     const double thr_dt = break_tolerance * med_dt;
     if (t == 0) { sm.misc[0] = 1; sm.cuts[0] = 0; }         // misc[0] = number of segment starts so far
     __syncthreads();

@@ -632,6 +632,10 @@ __global__ void rg_zero_kernel(double* p, int64_t n, uint8_t* q, int64_t nq) {
   if (q && i < nq) q[i] = 0;
 }
 
+bool regress_tc_supported(int B, int64_t N, int K);                                              // regress_tc.cu
+int regress_tc_gram(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used, int B, int64_t N,
+                    int K, double* d_gram, cudaStream_t st);
+
 int regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
             const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma, int niters,
             double* coeff, double* model, uint8_t* outlier_mask, int32_t* status_out, double* coeff_cov, int mem,
@@ -699,6 +703,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
   const int nb5 = (ntile + tb - 1) / tb;
   static const bool force_simt = getenv("LKB_REGRESS_SIMT") != nullptr;
   const bool use_mma = !force_simt && Ka <= RGM_LD && nb5 <= 5;
+  const bool use_tc = !force_simt && !x_batched && regress_tc_supported(B, N, K);
   static bool mma_attr = false;
   if (!mma_attr) {
     const int sm2 = (int)(2 * sizeof(RgmStage));
@@ -728,7 +733,10 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, d_fe, N, it == 0 ? 1 : 0, ws);
     LKB_LAUNCH_CHECK();
     if (it == 0) prof_begin(st);
-    if (use_mma) {
+    if (it == 0 && use_tc) {
+      // first fit of a large shared-design-matrix batch: the Gram matrices as one tcgen05 GEMM (regress_tc.cu)
+      LKB_TRY(regress_tc_gram(d_X, d_y, d_fe, ws.used, B, N, K, ws.gram, st));
+    } else if (use_mma) {
       const double sgn = it == 0 ? 1.0 : -1.0;
       const size_t sm2 = 2 * sizeof(RgmStage);
       // first pass of a small batch: two CTAs per light curve to fill the SMs (wave quantisation)

@@ -129,6 +129,107 @@ __device__ double block_nanmedian(Get get, int64_t n, SelSmem& sm, long long* co
   return (vlo + vhi) / 2.0;
 }
 
+// ---- exact median in TWO passes over the data (Floyd-Rivest style) -----------------------------------------------
+// The radix select above reads the data once per key byte (8 passes + count + tie pass).  Here a strided sample of
+// FS_SAMPLE values brackets the wanted order statistics [lo, hi] (sample ranks +- FS_GAP around the target), ONE
+// pass over the data counts the values below lo / equal lo / equal hi and collects those strictly between into a
+// shared-memory buffer, and the order statistics are selected inside that buffer (radix select over shared memory).
+// Exact; if the bracket misses (probability ~1e-3 per call for random data) or more than FS_CAP values fall between
+// (heavily skewed duplicates), the caller's answer comes from block_nanmedian above - same result, just slower.
+constexpr int FS_SAMPLE = 1024, FS_GAP = 56, FS_CAP = 6144;
+struct FastSelSmem {
+  double* cand;                 // FS_CAP doubles of shared memory provided by the caller (may alias idle scratch)
+  double sample[FS_SAMPLE];
+  int n_cand, c_lt, c_eqlo, c_eqhi, ok;
+};
+
+// value of rank r (0-based) among {lt block | eq-lo block | cand (sorted logically) | eq-hi block}; valid iff inside
+template <class GetC>
+__device__ inline double fs_rank_value(long long r, long long c_lt, long long c_eqlo, long long n_cand, long long c_eqhi,
+                                       double lo, double hi, GetC getc, SelSmem& sm, bool* valid) {
+  *valid = true;
+  if (r < c_lt) { *valid = false; return 0.0; }
+  r -= c_lt;
+  if (r < c_eqlo) return lo;
+  r -= c_eqlo;
+  if (r < n_cand) return f64_unkey(block_select_key(getc, n_cand, r, sm));
+  r -= n_cand;
+  if (r < c_eqhi) return hi;
+  *valid = false;
+  return 0.0;
+}
+
+// np.nanmedian over get(0..n-1); m = number of non-NaN values if known (>= 0), else -1 (counted in the sample pass).
+template <class Get>
+__device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelSmem& fs, long long m_known = -1) {
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (n < 4 * FS_SAMPLE) return block_nanmedian(get, n, sm);
+  // ---- sample (every stride-th element; NaNs are dropped from the sample) + count ----
+  long long m = m_known;
+  if (m < 0) {
+    long long cnt = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double v = get(i); cnt += (v == v) ? 1 : 0; }
+    m = block_sum_ll(cnt, sm.redll);
+  }
+  if (m == 0) return qnan;
+  const int64_t stride = n / FS_SAMPLE;
+  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) fs.sample[sidx] = get((int64_t)sidx * stride);
+  __syncthreads();
+  long long scnt = 0;
+  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) scnt += (fs.sample[sidx] == fs.sample[sidx]) ? 1 : 0;
+  const long long ns = block_sum_ll(scnt, sm.redll);
+  if (ns < 4 * FS_GAP) return block_nanmedian(get, n, sm);
+  auto gets = [&](int64_t i) { return fs.sample[i]; };
+  long long rlo = ns / 2 - FS_GAP, rhi = ns / 2 + FS_GAP;
+  if (rlo < 0) rlo = 0;
+  if (rhi > ns - 1) rhi = ns - 1;
+  const double lo = f64_unkey(block_select_key(gets, FS_SAMPLE, rlo, sm));
+  const double hi = f64_unkey(block_select_key(gets, FS_SAMPLE, rhi, sm));
+  // ---- the one pass: partition counts + candidates strictly between lo and hi ----
+  if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; }
+  __syncthreads();
+  int c_lt = 0, c_eqlo = 0, c_eqhi = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    bool between = false;
+    double v = 0.0;
+    if (i < n) {
+      v = get(i);
+      if (v == v) {
+        if (v < lo) c_lt++;
+        else if (v == lo) c_eqlo++;
+        else if (v < hi) between = true;
+        else if (v == hi) c_eqhi++;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, between);
+    if (bal) {
+      int base = 0;
+      if ((threadIdx.x & 31) == 0) base = atomicAdd(&fs.n_cand, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (between) {
+        const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+        if (pos < FS_CAP) fs.cand[pos] = v;
+      }
+    }
+  }
+  if (lo == hi) c_eqhi = 0;                                     // (one value: counted once, as eq-lo)
+  c_lt = warp_sum(c_lt); c_eqlo = warp_sum(c_eqlo); c_eqhi = warp_sum(c_eqhi);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&fs.c_lt, c_lt); atomicAdd(&fs.c_eqlo, c_eqlo); atomicAdd(&fs.c_eqhi, c_eqhi); }
+  __syncthreads();
+  const long long n_cand = fs.n_cand, t_lt = fs.c_lt, t_eqlo = fs.c_eqlo, t_eqhi = fs.c_eqhi;
+  __syncthreads();
+  if (n_cand > FS_CAP) return block_nanmedian(get, n, sm);
+  auto getc = [&](int64_t i) { return fs.cand[i]; };
+  const long long klo = (m - 1) / 2, khi = m / 2;
+  bool v1, v2;
+  const double a = fs_rank_value(klo, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v1);
+  const double b = (khi == klo) ? a : fs_rank_value(khi, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v2);
+  if (khi == klo) v2 = v1;
+  if (!(v1 && v2)) return block_nanmedian(get, n, sm);           // the bracket missed: full radix select
+  return (a + b) / 2.0;
+}
+
 // np.nanstd (ddof = 0): two-pass (mean, then squared deviations), NaN ignored.
 template <class Get>
 __device__ double block_nanstd(Get get, int64_t n, SelSmem& sm, double* mean_out = nullptr) {

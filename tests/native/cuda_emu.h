@@ -152,6 +152,21 @@ inline T __shfl_up_sync(unsigned, T v, int delta) {
   b->warp[w].wait();
   return out;
 }
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  lkb_emu::Block* b = lkb_emu::t_block;
+  const int t = lkb_emu::t_tid, w = t / 32, lane = t % 32;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  b->scratch[(size_t)w * 32 + lane] = bits;
+  b->warp[w].wait();
+  T out = v;
+  const unsigned long long ob = b->scratch[(size_t)w * 32 + (src_lane & 31)];
+  memcpy(&out, &ob, sizeof(T));
+  b->warp[w].wait();
+  return out;
+}
 inline unsigned __ballot_sync(unsigned, int pred) {
   lkb_emu::Block* b = lkb_emu::t_block;
   const int t = lkb_emu::t_tid, w = t / 32, lane = t % 32;

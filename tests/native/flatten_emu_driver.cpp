@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../lightkurve_b200/csrc/flatten_v2.cuh"
@@ -28,7 +29,8 @@ int emu_flatten2(const double* t, const double* f, const double* fe, const unsig
   for (int i = 0; i < cf.q * cf.q; ++i) cf.Ginv[i] = Ginv[i];
   const int NM = polyorder <= 1 ? 1 : polyorder <= 3 ? 3 : 5;
   const int half = window / 2;
-  const size_t smem = ((sizeof(lkb::F2Smem) + 15) & ~(size_t)15) + sizeof(double) * (size_t)NM * (tile_out + 2 * half + 1);
+  const size_t smem = ((sizeof(lkb::F2Smem) + 15) & ~(size_t)15) +
+                      sizeof(double) * std::max((size_t)NM * (tile_out + 2 * half + 1), (size_t)lkb::FS_CAP);
   std::vector<double> tro((size_t)off[B] + 1, 0.0);
   if (NM == 1)
     LKB_LAUNCH_SMEM(B, lkb::F2_THREADS, smem, 0, lkb::flatten2_kernel<1>)(t, f, fe, ex, off, tro.data(), window, break_tol,

@@ -115,6 +115,22 @@ def test_flatten_v2_kernel_on_the_emulator(emu, w, p, bt, niters, sigma, nans, t
         np.testing.assert_allclose(flat_err[b], re_, rtol=1e-9, equal_nan=True)
 
 
+def test_flatten_v2_sampling_select_on_the_emulator(emu):
+    """Light curves long enough (>= 4096 cadences) for the two-pass sampling median (select.cuh block_nanmedian_fast):
+    regular cadence (every dt within rounding of one value: the equal-to-pivot branches) and jittered cadence (many
+    distinct dt: the candidate buffer)."""
+    rng = np.random.default_rng(31)
+    t1, f1, fe1 = _lc(rng, 9000, gaps=3, outliers=40)
+    t2, f2, fe2 = _lc(rng, 7000, gaps=2, outliers=30)
+    t2 = np.sort(t2 + rng.uniform(-2e-3, 2e-3, len(t2)))
+    flat, flat_err, trend, status = _run(emu, [t1, t2], [f1, f2], [fe1, fe2], None, 201, 2, 5, 3, 3)
+    assert (status == 0).all(), status
+    for b, (t, f, fe) in enumerate(((t1, f1, fe1), (t2, f2, fe2))):
+        rf, _, rt = odet.flatten(t, f, fe, window_length=201)
+        np.testing.assert_allclose(trend[b], rt, rtol=1e-9)
+        np.testing.assert_allclose(flat[b], rf, rtol=1e-9)
+
+
 def test_flatten_v2_mask_and_failure_on_the_emulator(emu):
     """An exclude mask (lightkurve's mask=True cadences), and a light curve with fewer than two usable cadences (NaN
     trend, status 1) next to a healthy one."""

@@ -476,7 +476,7 @@ def test_flatten_kernel_generations_agree(engine, monkeypatch):
     np.testing.assert_allclose(flat[0], rf, rtol=1e-9)
     flat6, _, trend6 = engine.flatten([lcs[1][0]], [lcs[1][1]], [lcs[1][2]], None, window_length=51, polyorder=6)
     np.testing.assert_allclose(trend6[0], odet.flatten(lcs[1][0], lcs[1][1], lcs[1][2], window_length=51, polyorder=6)[2],
-                               rtol=1e-8)
+                               rtol=2e-7)      # (first kernel: degree-6 edge tables)
 
 
 def test_flatten_reference_known_answers(engine):
@@ -545,6 +545,37 @@ def test_regress_vs_oracle(engine, K, N, B):
         assert np.array_equal(r["outlier_mask"][b], ref["outlier_mask"])
         np.testing.assert_allclose(r["coefficients"][b], ref["coefficients"], rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(r["model"][b], ref["model"], rtol=1e-7, atol=1e-10)
+
+
+def test_regress_tcgen05_gram_vs_fp64(engine, monkeypatch):
+    """The first fit's Gram matrices as one tcgen05 GEMM (regress_tc.cu) against the fp64 DMMA kernel on the same
+    batch: K = 37 (three column blocks, the last one partly empty), 70 light curves (a partly filled light-curve
+    tile), per-cadence errors, a cadence mask and outliers that later iterations downdate.  Identical outlier masks,
+    coefficients to SURVEY 8c's 1e-4."""
+    rng = np.random.default_rng(202)
+    N, K, B = 6000, 37, 70
+    X = np.cumsum(rng.normal(size=(N, K - 1)), axis=0)
+    X, _ = np.linalg.qr(X - X.mean(0))
+    X = np.hstack([X * np.sqrt(N) * 10 ** rng.uniform(-2, 2, K - 1), np.ones((N, 1))])     # columns of very different scale
+    Wt = rng.normal(size=(B, K)) * 1e-3 / np.abs(X).max(axis=0)
+    Wt[:, -1] = 0
+    Y = 1 + Wt @ X.T + 3e-4 * rng.normal(size=(B, N))
+    for b in range(B):
+        Y[b, rng.choice(N, 20, replace=False)] += 8 * 3e-4
+    fe = 3e-4 * rng.uniform(0.7, 1.4, (B, N))
+    cm = rng.uniform(size=(B, N)) > 0.03
+    monkeypatch.setenv("LKB_REGRESS_TC", "1")
+    a = engine.regress(X, Y, fe, cm, None, None, sigma=5, niters=4)
+    monkeypatch.setenv("LKB_REGRESS_TC", "0")
+    b_ = engine.regress(X, Y, fe, cm, None, None, sigma=5, niters=4)
+    assert (a["status"] == 0).all() and (b_["status"] == 0).all()
+    assert np.array_equal(a["outlier_mask"], b_["outlier_mask"])
+    scale = np.abs(b_["coefficients"] * np.abs(X).max(axis=0)).max(axis=1, keepdims=True) / np.abs(X).max(axis=0)
+    assert np.all(np.abs(a["coefficients"] - b_["coefficients"]) <= 1e-4 * np.abs(b_["coefficients"]) + 1e-5 * scale)
+    np.testing.assert_allclose(a["model"], b_["model"], atol=2e-7)
+    ref = odet.regress(X, Y[3], fe[3], cm[3], None, None, sigma=5, niters=4)
+    assert np.array_equal(a["outlier_mask"][3], ref["outlier_mask"])
+    np.testing.assert_allclose(a["model"][3], ref["model"], atol=2e-7)
 
 
 def test_regress_singular_reports_status(engine):

@@ -189,14 +189,23 @@ def test_config4_shape_flatten_and_regression(engine):
     for b in range(B):
         Y[b, out_idx[b]] += 8 * 3e-4
     fe = 3e-4 * rng.uniform(0.8, 1.2, (B, N))
-    r = engine.regress(X, Y, fe, None, None, None, sigma=5, niters=5)
-    assert (r["status"] == 0).all()
-    for b in (0, B - 1):
-        ref = odet.regress(X, Y[b], fe[b], None, None, None, sigma=5, niters=5)
-        assert np.array_equal(r["outlier_mask"][b], ref["outlier_mask"])
-        np.testing.assert_allclose(r["coefficients"][b], ref["coefficients"], rtol=1e-6, atol=1e-9)
-        np.testing.assert_allclose(r["model"][b], ref["model"], rtol=1e-6, atol=1e-9)
-    np.testing.assert_allclose(r["coefficients"][:, :-1], W[:, :-1], atol=2e-5)   # the injected coefficients come back
+    import os
+    # This shape (B >= 64 light curves on one design matrix, N >= 4096) takes the tcgen05 Gram kernel (regress_tc.cu):
+    # 22-bit operands, so the coefficient tolerance is SURVEY.md 8c's rtol 1e-4 (floor: 1e-7); the outlier masks must
+    # be identical.  The same call on the fp64 DMMA path (LKB_REGRESS_TC=0) keeps the tight tolerance.
+    for tc, rtol, atol_c, atol_m in (("1", 1e-4, 1e-7, 1e-7), ("0", 1e-6, 1e-9, 1e-9)):
+        os.environ["LKB_REGRESS_TC"] = tc
+        try:
+            r = engine.regress(X, Y, fe, None, None, None, sigma=5, niters=5)
+        finally:
+            os.environ.pop("LKB_REGRESS_TC", None)
+        assert (r["status"] == 0).all()
+        for b in (0, B - 1):
+            ref = odet.regress(X, Y[b], fe[b], None, None, None, sigma=5, niters=5)
+            assert np.array_equal(r["outlier_mask"][b], ref["outlier_mask"]), tc
+            np.testing.assert_allclose(r["coefficients"][b], ref["coefficients"], rtol=rtol, atol=atol_c, err_msg=tc)
+            np.testing.assert_allclose(r["model"][b], ref["model"], rtol=rtol, atol=atol_m, err_msg=tc)
+        np.testing.assert_allclose(r["coefficients"][:, :-1], W[:, :-1], atol=2e-5)   # the injected coefficients come back
     # flatten of the corrected light curves, window_length = 401
     corrected = [Y[b] - r["model"][b] + 1e-3 * np.sin(2 * np.pi * (t - t[0]) / 7.0) for b in range(8)]
     flat, flat_err, trend = engine.flatten([t] * 8, corrected, [fe[b] for b in range(8)], None, window_length=401,
