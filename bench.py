@@ -37,6 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+BLS_WARP_INSTR_PER_PAIR = 33450.0      # ncu smsp__inst_executed.sum / (light curves x periods), config-3 grid (run 4)
 METRIC = "lombscargle_freqbins_x_cadences_per_s"
 UNIT = "bin*cadence/s"
 
@@ -334,17 +335,21 @@ def secondary_bls(engine, torch, dist, rank, world, dev, steps=2, cpu_baseline=T
            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "(LC,period)/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": int(3 * 8 * B * N) * world, "d2h_bytes_per_step": int(7 * 8 * B * P) * world},
            "gpu_launches": int(launches),
-           "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": B * P * (24.0 * N + 56) / (k_ms * 1e-3) / 1e9,
-                        "note": "SURVEY 8(d) algorithmic bytes (24*N+56) per (LC, period); the kernel keeps the light "
-                                "curve in L1/L2, so this effective figure may exceed the HBM peak"}}
+           # K3 keeps the light curve on chip (DRAM 0.01 %, profiles/r01_bls_kernel_v2_boundary.md): the bound is
+           # instruction issue.  33 450 warp instructions per (light curve, period), measured with ncu over ALL period
+           # chunks of this workload's grid (profiles/r02_bls_instructions.csv); peak = SMs x 4 schedulers x max clock.
+           "roofline": {"bound": "issue", "unit": "warp-instructions/s",
+                        "achieved": BLS_WARP_INSTR_PER_PAIR * B * P / (k_ms * 1e-3),
+                        "warp_instructions_per_pair": BLS_WARP_INSTR_PER_PAIR,
+                        "compulsory_bytes_per_step": int(3 * 8 * B * N + 7 * 8 * B * P),
+                        "effective_gbs_of_24N_plus_56": B * P * (24.0 * N + 56) / (k_ms * 1e-3) / 1e9,
+                        "note": "issue-slot roofline (the SURVEY 8(d) streaming figure (24 N + 56) B per pair is kept as "
+                                "effective_gbs...: the kernel never streams the light curve from HBM)"}}
     if rank == 0:
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            pk = float(peaks.get("hbm_gbs", 6589.3))
-        except Exception:
-            pk = 6589.3
+        pk = float(engine.sm_count()) * 4.0 * float(_peaks().get("sm_max_mhz", 1965.0)) * 1e6
         out["roofline"]["peak"] = pk
         out["roofline"]["frac"] = out["roofline"]["achieved"] / pk
+        out["roofline"]["peak_source"] = "SM count x 4 warp schedulers x sm_max_mhz of MEASURED_PEAKS.json"
         if cpu_baseline:
             out.update(_bls_cpu_leg(t, fluxes, errs, period, duration, res, P))
     return out

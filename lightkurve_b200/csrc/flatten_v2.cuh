@@ -43,6 +43,7 @@ struct F2Smem {
   unsigned keep[F2_MAXWORDS];                   // bit i: cadence i is used for the fit
   int wpre[F2_MAXWORDS + 1];                    // kept cadences before word w
   int cuts[F2_MAXSEG + 1];                      // segment starts (positions in the kept sequence), cuts[nseg] = m
+  int ucuts[F2_MAXSEG];                         // the same, unordered (as found)
   SelSmem sel;
   double red[F2_MAXQ][17];
   double beta[F2_MAXQ];
@@ -203,9 +204,10 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       return pv < 0 ? qnan : tt[i] - tt[pv];
     }, n, sm.sel, sm.fs, (long long)m - 1);
     const double thr_dt = break_tolerance * med_dt;
-    if (t == 0) { sm.misc[0] = 1; sm.cuts[0] = 0; }         // misc[0] = number of segment starts so far
+    // cuts are rare: unordered append (one atomic per warp that found any), then a rank sort of the short list
+    if (t == 0) { sm.misc[0] = 0; }                          // misc[0] = number of cuts found
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += F2_THREADS) {            // cuts are rare: ordered append by one lane per warp
+    for (int i0 = 0; i0 < n; i0 += F2_THREADS) {
       const int i = i0 + t;
       bool cut = false;
       if (i < n && f2_kept(sm, i)) {
@@ -213,27 +215,30 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
         cut = pv >= 0 && (tt[i] - tt[pv]) > thr_dt;
       }
       const unsigned bal = __ballot_sync(0xffffffffu, cut);
-      if (lane == 0) sm.scan_tmp[warp] = __popc(bal);
-      __syncthreads();
-      int base = sm.misc[0];
-      for (int ww = 0; ww < warp; ++ww) base += sm.scan_tmp[ww];
-      if (cut) {
-        const int pos = base + __popc(bal & ((1u << lane) - 1u));
-        if (pos <= F2_MAXSEG - 1) sm.cuts[pos] = f2_rank(sm, i);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cut) {
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (pos < F2_MAXSEG - 1) sm.ucuts[pos] = f2_rank(sm, i);
+        }
       }
-      __syncthreads();
-      if (t == 0) {
-        int tot = 0;
-        for (int ww = 0; ww < F2_THREADS / 32; ++ww) tot += sm.scan_tmp[ww];
-        sm.misc[0] += tot;
-      }
-      __syncthreads();
     }
-    const int nseg = sm.misc[0];
-    if (nseg > F2_MAXSEG - 1) {                             // too many segments for the shared-memory list
+    __syncthreads();
+    const int ncut = sm.misc[0];
+    if (ncut > F2_MAXSEG - 2) {                              // too many segments for the shared-memory list
       if (t == 0) status[b] = 2;
       return;
     }
+    for (int e = t; e < ncut; e += F2_THREADS) {             // distinct values: rank = number of smaller entries
+      const int v = sm.ucuts[e];
+      int r = 0;
+      for (int q = 0; q < ncut; ++q) r += (sm.ucuts[q] < v) ? 1 : 0;
+      sm.cuts[1 + r] = v;
+    }
+    if (t == 0) sm.cuts[0] = 0;
+    const int nseg = ncut + 1;
     if (t == 0) sm.cuts[nseg] = m;
     __syncthreads();
 
@@ -302,10 +307,12 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       __syncthreads();
       // outputs of the tile that are interior points of a filtered segment
       const int o_lo = f2_select(sm, nw, k0), o_hi = f2_select(sm, nw, kout1 - 1) + 1;
+      int l = 0, h = -1;                                   // this thread's last segment (positions only grow)
       for (int i = o_lo + t; i < o_hi; i += F2_THREADS) {
         if (!f2_kept(sm, i)) continue;
         const int k = f2_rank(sm, i);
-        const int s = f2_segment(sm, nseg, k), l = sm.cuts[s], h = sm.cuts[s + 1], len = h - l;
+        if (k >= h) { const int s = f2_segment(sm, nseg, k); l = sm.cuts[s]; h = sm.cuts[s + 1]; }
+        const int len = h - l;
         if ((w > len) || ((double)len < break_tolerance)) continue;          // median fallback (below)
         if (k - l < half || h - k <= half) continue;                           // edge (below)
         const int a = k - half - kin0, e = k + half - kin0 + 1;                // window [a, e) in tile coordinates

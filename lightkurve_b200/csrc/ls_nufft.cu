@@ -632,7 +632,7 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     LKB_TRY(v2_tables(p, WS_IN6, st, &g_plan.tb));
     float* Wt = nullptr;
     LKB_TRY(ws_get_t<float>(WS_X0, (size_t)N * w, &Wt));
-    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel)(cad, N, w, beta, Wt);
+    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel)(d_t, N, grid_df, M, w, (double)beta, Wt);
     LKB_LAUNCH_CHECK();
     g_plan.Wt = Wt;
     if (F_low > 0) {

@@ -71,14 +71,22 @@ __global__ void nufft2_tables_kernel(int pa, int pb, int ph, float2* __restrict_
   *dst = make_float2((float)cs, (float)sn);
 }
 
-// kernel weights of every cadence: Wt[n w + q] = phi((d0_n + q) / (w / 2)), q = 0 .. w - 1
-__global__ void nufft2_weights_kernel(const nufft::Cad* __restrict__ cad, int64_t N, int w, float beta,
+// kernel weights of every cadence: Wt[n w + q] = phi((i0_n + q - x_n) / (w / 2)), q = 0 .. w - 1, evaluated in FP64
+// from the time stamp itself and rounded once.  (Round 2, hardware finding: with fp32 offsets and expf the weights
+// carry ~1e-6 relative errors - a perturbation of the kernel SHAPE that the deconvolution does not undo; it leaked
+// strong lines from above the frequency band into the band at 2e-8 of their amplitude, 1.5x the tolerance on light
+// curves whose in-band spectrum is 1000x below their variability, and a WIDER kernel made it worse, not better.)
+__global__ void nufft2_weights_kernel(const double* __restrict__ t, int64_t N, double df, int64_t M, int w, double beta,
                                       float* __restrict__ Wt) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * w) return;
   const int64_t n = e / w;
   const int q = (int)(e - n * w);
-  Wt[e] = nufft::es_eval((cad[n].d0 + (float)q) * (2.0f / (float)w), beta);
+  const double x = df * t[n] * (double)M + (double)nufft::grid_shift(w);       // as nufft::cad_entry
+  const double i0 = ceil(x - 0.5 * (double)w);
+  const double z = (i0 + (double)q - x) * (2.0 / (double)w);
+  const double s2 = 1.0 - z * z;
+  Wt[e] = (s2 > 0.0) ? (float)exp(beta * (sqrt(s2) - 1.0)) : 0.0f;
 }
 
 // z index (n = n1 Bc + n2) of position e of the G layout [c][n1][j]

@@ -316,9 +316,11 @@ rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __
 }
 
 // ---- solve ------------------------------------------------------------------------------------------
+// grad != NULL: iterative-refinement step - solve (A + prior) d = grad - prior (w - mu) for the current w = coeff and
+// write w + d (the matrix may be approximate, e.g. the tcgen05 Gram; grad is the exact fp64 gradient of the fit)
 __global__ void __launch_bounds__(256)
 rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __restrict__ prior_sigma, RgWs ws,
-                double* __restrict__ coeff, int32_t* __restrict__ status) {
+                double* __restrict__ coeff, int32_t* __restrict__ status, const double* __restrict__ grad) {
   extern __shared__ __align__(16) double s_m[];        // [K][K+1] augmented
   __shared__ double s_red[8];
   __shared__ int s_redi[8];
@@ -331,10 +333,11 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
   for (int e = threadIdx.x; e < K * Ka; e += blockDim.x) {
     const int i = e / Ka, j = e % Ka;
     double v = (j >= i) ? G[(int64_t)i * Ka + j] : G[(int64_t)j * Ka + i];
+    if (grad && j == K) v = grad[(int64_t)b * K + i];
     if (prior_sigma) {
       const double ps = prior_sigma[i];
       if (j == i) v += 1.0 / (ps * ps);
-      if (j == K) v += prior_mu[i] / (ps * ps);
+      if (j == K) v += (grad ? (prior_mu[i] - coeff[(int64_t)b * K + i]) : prior_mu[i]) / (ps * ps);
     }
     s_m[e] = v;
   }
@@ -401,7 +404,8 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) coeff[(int64_t)b * K + k] = s_m[k * Ka + K];
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    coeff[(int64_t)b * K + k] = grad ? coeff[(int64_t)b * K + k] + s_m[k * Ka + K] : s_m[k * Ka + K];
   if (threadIdx.x == 0 && status) status[b] = LKB_OK;
 }
 
@@ -635,6 +639,8 @@ __global__ void rg_zero_kernel(double* p, int64_t n, uint8_t* q, int64_t nq) {
 bool regress_tc_supported(int B, int64_t N, int K);                                              // regress_tc.cu
 int regress_tc_gram(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used, int B, int64_t N,
                     int K, double* d_gram, cudaStream_t st);
+int regress_tc_gradient(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used,
+                        const double* d_model, int B, int64_t N, int K, double* d_grad, cudaStream_t st);
 
 int regress(const double* X, int x_batched, const double* y, const double* flux_err, const uint8_t* cadence_mask,
             const double* prior_mu, const double* prior_sigma, int B, int64_t N, int K, double clip_sigma, int niters,
@@ -755,9 +761,22 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
                                                                            it == 0 ? 1.0 : -1.0, ws);
     if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
-    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status);
+    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, nullptr);
     LKB_LAUNCH_CHECK();
     if (gemm_model) {
+      rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
+      LKB_LAUNCH_CHECK();
+    }
+    if (use_tc && gemm_model) {
+      // The tcgen05 Gram matrices carry ~1e-6 relative errors, which a coefficient of order one (the offset of a
+      // normalised light curve) turns into ~1e-6 ABSOLUTE errors of the small coefficients.  One step of iterative
+      // refinement with the EXACT fp64 gradient X^T W (y - X w) of the cadences in use removes them (the error
+      // contracts by ~1e-6 per step): w <- w + (A~ + prior)^-1 [X^T W (y - X w) - prior (w - mu)], then the model again.
+      double* d_grad = nullptr;
+      LKB_TRY(ws_get_t<double>(WS_X6, (size_t)B * K, &d_grad));
+      LKB_TRY(regress_tc_gradient(d_X, d_y, d_fe, ws.used, ws.resid, B, N, K, d_grad, st));
+      rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, d_grad);
+      LKB_LAUNCH_CHECK();
       rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
       LKB_LAUNCH_CHECK();
     }

@@ -320,11 +320,14 @@ rt_finish_kernel(const float* __restrict__ part, int nseg, int B, int P, const i
 }
 
 // exact right-hand sides: G[b][i][K] = sum_n w y X[n,i] (i < K), G[b][K][K] = sum_n w y^2; one CTA = 8 light curves
-// sharing every 32-cadence slice of X through shared memory, thread k = column k
+// sharing every 32-cadence slice of X through shared memory, thread k = column k.
+// With `model` (the current fit X w) the same sums are taken of the residual y - model and go to grad[b][k] (k < K):
+// the exact gradient X^T W (y - X w) of the iterative-refinement step in regress.cu.
 constexpr int RH_LC = 8;
 __global__ void __launch_bounds__(256)
 rt_rhs_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ flux_err,
-              const uint8_t* __restrict__ used, int64_t N, int K, int B, double* __restrict__ gram) {
+              const uint8_t* __restrict__ used, int64_t N, int K, int B, double* __restrict__ gram,
+              const double* __restrict__ model, double* __restrict__ grad) {
   __shared__ double sX[32][168];
   __shared__ double sWY[RH_LC][32];
   __shared__ double sY[RH_LC][32];
@@ -345,6 +348,7 @@ rt_rhs_kernel(const double* __restrict__ X, const double* __restrict__ y, const 
       if (b < B && n0 + nn < N && used[(int64_t)b * N + n0 + nn]) {
         const double f = flux_err ? flux_err[(int64_t)b * N + n0 + nn] : 1.0;
         yy = y[(int64_t)b * N + n0 + nn];
+        if (model) yy -= model[(int64_t)b * N + n0 + nn];
         v = yy / (f * f);
       }
       sWY[l][nn] = v;
@@ -365,9 +369,23 @@ rt_rhs_kernel(const double* __restrict__ X, const double* __restrict__ y, const 
     }
   }
   const int Ka = K + 1;
+  if (model) {
+    if (k < K)
+      for (int l = 0; l < RH_LC; ++l)
+        if (b0 + l < B) grad[(int64_t)(b0 + l) * K + k] = acc[l];
+    return;
+  }
   if (k <= K)
     for (int l = 0; l < RH_LC; ++l)
       if (b0 + l < B) gram[(int64_t)(b0 + l) * Ka * Ka + (int64_t)k * Ka + K] = acc[l];
+}
+
+// exact gradient X^T W (y - model) over the cadences in use -> grad [B, K]
+int regress_tc_gradient(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used,
+                        const double* d_model, int B, int64_t N, int K, double* d_grad, cudaStream_t st) {
+  rt_rhs_kernel<<<(unsigned)((B + RH_LC - 1) / RH_LC), 256, 0, st>>>(d_X, d_y, d_fe, d_used, N, K, B, nullptr, d_model, d_grad);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -465,7 +483,7 @@ int regress_tc_gram(const double* d_X, const double* d_y, const double* d_fe, co
   rt_finish_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)B), 256, 0, st>>>(part, nseg, B, P, d_tiles, K, colmax, inv,
                                                                                 d_gram);
   LKB_LAUNCH_CHECK();
-  rt_rhs_kernel<<<(unsigned)((B + RH_LC - 1) / RH_LC), 256, 0, st>>>(d_X, d_y, d_fe, d_used, N, K, B, d_gram);
+  rt_rhs_kernel<<<(unsigned)((B + RH_LC - 1) / RH_LC), 256, 0, st>>>(d_X, d_y, d_fe, d_used, N, K, B, d_gram, nullptr, nullptr);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
