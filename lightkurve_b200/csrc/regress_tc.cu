@@ -319,73 +319,98 @@ rt_finish_kernel(const float* __restrict__ part, int nseg, int B, int P, const i
   gram[(int64_t)b * Ka * Ka + (int64_t)i * Ka + j] = acc * un;
 }
 
-// exact right-hand sides: G[b][i][K] = sum_n w y X[n,i] (i < K), G[b][K][K] = sum_n w y^2; one CTA = 8 light curves
-// sharing every 32-cadence slice of X through shared memory, thread k = column k.
-// With `model` (the current fit X w) the same sums are taken of the residual y - model and go to grad[b][k] (k < K):
+// exact right-hand sides: G[b][i][K] = sum_n w y X[n,i] (i < K), G[b][K][K] = sum_n w y^2.  grid (ceil(B / 16), S):
+// one CTA = 16 light curves x one slice of the cadences (split S ways, fp64 atomics into a zeroed accumulator), every
+// 32-cadence chunk of X copied LINEARLY into shared memory (X is row-major: a chunk is one contiguous run of 32 K
+// doubles), thread k = column k.  With `model` (the current fit X w) the same sums are taken of the residual y - model:
 // the exact gradient X^T W (y - X w) of the iterative-refinement step in regress.cu.
-constexpr int RH_LC = 8;
+// (First version: 8 light curves per CTA walking ALL cadences, chunk loads through a div/mod index loop: 23 ms per
+// call for 512 light curves - 64 CTAs on 148 SMs, latency-bound.)
+constexpr int RH_LC = 16;
 __global__ void __launch_bounds__(256)
 rt_rhs_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ flux_err,
-              const uint8_t* __restrict__ used, int64_t N, int K, int B, double* __restrict__ gram,
-              const double* __restrict__ model, double* __restrict__ grad) {
-  __shared__ double sX[32][168];
-  __shared__ double sWY[RH_LC][32];
-  __shared__ double sY[RH_LC][32];
+              const uint8_t* __restrict__ used, int64_t N, int K, int B, int64_t slice, const double* __restrict__ model,
+              double* __restrict__ acc_out /*[B][K + 1]*/) {
+  extern __shared__ __align__(16) double rh_smem[];
+  double* sX = rh_smem;                              // [32 * K]
+  double* sWY = sX + 32 * K;                         // [RH_LC][32]
+  double* sY = sWY + RH_LC * 32;                     // [RH_LC][32]
   const int k = threadIdx.x, b0 = blockIdx.x * RH_LC;
+  const int64_t n_lo = (int64_t)blockIdx.y * slice, n_hi = (n_lo + slice < N) ? n_lo + slice : N;
   double acc[RH_LC];
 #pragma unroll
   for (int l = 0; l < RH_LC; ++l) acc[l] = 0.0;
-  for (int64_t n0 = 0; n0 < N; n0 += 32) {
+  for (int64_t n0 = n_lo; n0 < n_hi; n0 += 32) {
+    const int rows = (int)((n_hi - n0 < 32) ? n_hi - n0 : 32);
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * K; e += blockDim.x) {
-      const int nn = e / K, c = e - nn * K;
-      sX[nn][c] = (n0 + nn < N) ? X[(n0 + nn) * K + c] : 0.0;
-    }
-    {
-      const int l = threadIdx.x >> 5, nn = threadIdx.x & 31;           // 8 warps = 8 light curves
+    const double* xs = X + n0 * K;
+    for (int e = threadIdx.x; e < 32 * K; e += blockDim.x) sX[e] = (e < rows * K) ? xs[e] : 0.0;
+    for (int e = threadIdx.x; e < RH_LC * 32; e += blockDim.x) {
+      const int l = e >> 5, nn = e & 31, b = b0 + l;
       double v = 0.0, yy = 0.0;
-      const int b = b0 + l;
-      if (b < B && n0 + nn < N && used[(int64_t)b * N + n0 + nn]) {
+      if (b < B && nn < rows && used[(int64_t)b * N + n0 + nn]) {
         const double f = flux_err ? flux_err[(int64_t)b * N + n0 + nn] : 1.0;
         yy = y[(int64_t)b * N + n0 + nn];
         if (model) yy -= model[(int64_t)b * N + n0 + nn];
         v = yy / (f * f);
       }
-      sWY[l][nn] = v;
-      sY[l][nn] = yy;
+      sWY[e] = v;
+      sY[e] = yy;
     }
     __syncthreads();
     if (k < K) {
 #pragma unroll 4
       for (int nn = 0; nn < 32; ++nn) {
-        const double x = sX[nn][k];
+        const double x = sX[nn * K + k];
 #pragma unroll
-        for (int l = 0; l < RH_LC; ++l) acc[l] = fma(sWY[l][nn], x, acc[l]);
+        for (int l = 0; l < RH_LC; ++l) acc[l] = fma(sWY[l * 32 + nn], x, acc[l]);
       }
     } else if (k == K) {                                               // y^T W y: w y^2 = (w y) y
 #pragma unroll
       for (int l = 0; l < RH_LC; ++l)
-        for (int nn = 0; nn < 32; ++nn) acc[l] = fma(sWY[l][nn], sY[l][nn], acc[l]);
+        for (int nn = 0; nn < 32; ++nn) acc[l] = fma(sWY[l * 32 + nn], sY[l * 32 + nn], acc[l]);
     }
-  }
-  const int Ka = K + 1;
-  if (model) {
-    if (k < K)
-      for (int l = 0; l < RH_LC; ++l)
-        if (b0 + l < B) grad[(int64_t)(b0 + l) * K + k] = acc[l];
-    return;
   }
   if (k <= K)
     for (int l = 0; l < RH_LC; ++l)
-      if (b0 + l < B) gram[(int64_t)(b0 + l) * Ka * Ka + (int64_t)k * Ka + K] = acc[l];
+      if (b0 + l < B) atomicAdd(acc_out + (int64_t)(b0 + l) * (K + 1) + k, acc[l]);
+}
+// accumulator [B][K + 1] -> column K of the Gram matrices (gram != NULL) or the gradient array grad [B][K]
+__global__ void rt_rhs_store_kernel(const double* __restrict__ acc, int B, int K, double* __restrict__ gram,
+                                    double* __restrict__ grad) {
+  const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (e >= B * (K + 1)) return;
+  const int b = e / (K + 1), k = e - b * (K + 1);
+  if (gram) gram[(int64_t)b * (K + 1) * (K + 1) + (int64_t)k * (K + 1) + K] = acc[e];
+  else if (k < K) grad[(int64_t)b * K + k] = acc[e];
+}
+static int rt_rhs_launch(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used,
+                         const double* d_model, int B, int64_t N, int K, double* d_gram, double* d_grad, cudaStream_t st) {
+  double* acc = nullptr;
+  LKB_TRY(ws_get_t<double>(WS_X7, (size_t)B * (K + 1), &acc));
+  LKB_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)B * (K + 1), st));
+  const int groups = (B + RH_LC - 1) / RH_LC;
+  int S = (4 * 148 + groups - 1) / groups;
+  S = S < 1 ? 1 : (S > 64 ? 64 : S);
+  const int64_t slice = (((N + S - 1) / S + 31) / 32) * 32;
+  const size_t smem = sizeof(double) * ((size_t)32 * K + 2 * RH_LC * 32);
+  static size_t attr = 0;
+  if (smem > attr) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rt_rhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  rt_rhs_kernel<<<dim3((unsigned)groups, (unsigned)((N + slice - 1) / slice)), 256, smem, st>>>(d_X, d_y, d_fe, d_used, N, K, B,
+                                                                                        slice, d_model, acc);
+  LKB_LAUNCH_CHECK();
+  rt_rhs_store_kernel<<<(unsigned)((B * (K + 1) + 255) / 256), 256, 0, st>>>(acc, B, K, d_gram, d_grad);
+  LKB_LAUNCH_CHECK();
+  return LKB_OK;
 }
 
 // exact gradient X^T W (y - model) over the cadences in use -> grad [B, K]
 int regress_tc_gradient(const double* d_X, const double* d_y, const double* d_fe, const uint8_t* d_used,
                         const double* d_model, int B, int64_t N, int K, double* d_grad, cudaStream_t st) {
-  rt_rhs_kernel<<<(unsigned)((B + RH_LC - 1) / RH_LC), 256, 0, st>>>(d_X, d_y, d_fe, d_used, N, K, B, nullptr, d_model, d_grad);
-  LKB_LAUNCH_CHECK();
-  return LKB_OK;
+  return rt_rhs_launch(d_X, d_y, d_fe, d_used, d_model, B, N, K, nullptr, d_grad, st);
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -483,9 +508,7 @@ int regress_tc_gram(const double* d_X, const double* d_y, const double* d_fe, co
   rt_finish_kernel<<<dim3((unsigned)((P + 255) / 256), (unsigned)B), 256, 0, st>>>(part, nseg, B, P, d_tiles, K, colmax, inv,
                                                                                 d_gram);
   LKB_LAUNCH_CHECK();
-  rt_rhs_kernel<<<(unsigned)((B + RH_LC - 1) / RH_LC), 256, 0, st>>>(d_X, d_y, d_fe, d_used, N, K, B, d_gram, nullptr, nullptr);
-  LKB_LAUNCH_CHECK();
-  return LKB_OK;
+  return rt_rhs_launch(d_X, d_y, d_fe, d_used, nullptr, B, N, K, d_gram, nullptr, st);
 }
 
 }  // namespace lkb

@@ -1,0 +1,36 @@
+#!/usr/bin/env bash
+# Device sanitizers on the GPU box: memcheck over smoke() (every kernel family once) and
+# racecheck over the shared-memory-heavy kernels (NUFFT v2 tiles, flatten v2).  Summaries -> gpurun_out/sanitize/.
+set -u
+O=gpurun_out/sanitize
+mkdir -p $O
+CS=/usr/local/cuda/bin/compute-sanitizer
+export PYTHONUNBUFFERED=1
+echo "=== memcheck: smoke() ==="
+timeout 1500 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/memcheck_smoke.log 2>&1; echo "rc=$?"
+grep -E "ERROR SUMMARY|smoke ok|Invalid|========= Error" $O/memcheck_smoke.log | head -10
+cat > $O/_small.py <<'PY'
+import numpy as np, sys
+sys.path.insert(0, ".")
+from lightkurve_b200 import engine
+engine.init(0)
+rng = np.random.default_rng(3)
+N, B, F = 3000, 9, 3600
+t = 100.0 + np.sort(rng.uniform(0, 60.0, N))
+freq = (1 + np.arange(F)) / (5.0 * (t[-1] - t[0]))
+Y = (1 + 1e-3 * np.sin(2 * np.pi * 1.1 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
+engine.ls_power_shared(t, Y, freq, "amplitude")
+assert engine.ls_last_algo() == "nufft"
+engine.ls_power_ragged([t[:2000], t[:2500], t], [Y[0, :2000], Y[1, :2500], Y[2]], freq, "amplitude", algo="nufft")
+tt = np.arange(0, 120, 0.02)
+f = 1 + 0.01 * np.sin(tt / 3.0) + 1e-3 * rng.normal(size=len(tt))
+engine.flatten([tt, tt[:3000]], [f, f[:3000]], None, None, window_length=101)
+print("small ok")
+PY
+echo "=== racecheck: NUFFT v2 + flatten v2 ==="
+timeout 1500 $CS --tool racecheck --error-exitcode 9 --print-limit 20 python $O/_small.py > $O/racecheck_small.log 2>&1; echo "rc=$?"
+grep -E "RACECHECK SUMMARY|small ok|hazard|========= Error" $O/racecheck_small.log | head -10
+echo "=== memcheck: NUFFT v2 + flatten v2 ==="
+timeout 1500 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python $O/_small.py > $O/memcheck_small.log 2>&1; echo "rc=$?"
+grep -E "ERROR SUMMARY|small ok|Invalid|========= Error" $O/memcheck_small.log | head -10
+echo "=== done ==="
