@@ -457,7 +457,7 @@ int flatten(const double* time, const double* flux, const double* flux_err, cons
       LKB_TRY(ws_get_t<double>(WS_H, total, &tro));
       LKB_TRY(ws_get_t<int>(WS_N, B, &d_status));
       const size_t smem2 = ((sizeof(F2Smem) + 15) & ~(size_t)15) +
-                           sizeof(double) * std::max((size_t)NM * (tile_out + 2 * half + 1), (size_t)FS_CAP);
+                           sizeof(double) * std::max((size_t)NM * (tile_out + 2 * half + 1), (size_t)(FS_CAP + FS_SAMPLE));
       static size_t attr2[3] = {0, 0, 0};
       const int slot = NM == 1 ? 0 : NM == 3 ? 1 : 2;
       if (smem2 > attr2[slot]) {

@@ -100,6 +100,19 @@ __device__ __forceinline__ int f2_select(const F2Smem& sm, int nw, int k) {   //
   }
   return lo * 32 + (int)__fns(sm.keep[lo], 0, k - sm.wpre[lo] + 1);
 }
+// f2_select for up to four ranks at once: threads 0..3 search, everyone reads the answers.  (Every thread running its
+// own binary search over wpre was 25 % of the kernel's instructions - per-line profile of r02_flatten2_c.ncu-rep.)
+// All threads call; two barriers.
+__device__ inline void f2_select4(F2Smem& sm, int nw, int ka, int kb, int kc, int kd, int* out) {
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int k = threadIdx.x == 0 ? ka : threadIdx.x == 1 ? kb : threadIdx.x == 2 ? kc : kd;
+    sm.misc[4 + threadIdx.x] = k >= 0 ? f2_select(sm, nw, k) : -1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = sm.misc[4 + j];
+}
 __device__ __forceinline__ int f2_prev(const F2Smem& sm, int i) {            // last kept cadence before i, or -1
   int w = i >> 5;
   unsigned bits = sm.keep[w] & ((1u << (i & 31)) - 1u);
@@ -207,21 +220,30 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
     // cuts are rare: unordered append (one atomic per warp that found any), then a rank sort of the short list
     if (t == 0) { sm.misc[0] = 0; }                          // misc[0] = number of cuts found
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += F2_THREADS) {
-      const int i = i0 + t;
-      bool cut = false;
-      if (i < n && f2_kept(sm, i)) {
-        const int pv = f2_prev(sm, i);
-        cut = pv >= 0 && (tt[i] - tt[pv]) > thr_dt;
+    for (int i0 = 0; i0 < n; i0 += 4 * F2_THREADS) {          // 4 independent (t[i], t[prev]) load pairs in flight
+      double dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * F2_THREADS + t;
+        dd[u] = qnan;                                         // no predecessor: never a cut
+        if (i < n && f2_kept(sm, i)) {
+          const int pv = f2_prev(sm, i);
+          if (pv >= 0) dd[u] = tt[i] - tt[pv];
+        }
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, cut);
-      if (bal) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (cut) {
-          const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (pos < F2_MAXSEG - 1) sm.ucuts[pos] = f2_rank(sm, i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * F2_THREADS + t;
+        const bool cut = dd[u] > thr_dt;                      // (NaN threshold: no cuts, as in numpy)
+        const unsigned bal = __ballot_sync(0xffffffffu, cut);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (cut) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (pos < F2_MAXSEG - 1) sm.ucuts[pos] = f2_rank(sm, i);
+          }
         }
       }
     }
@@ -247,9 +269,10 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       const int kin0 = max(0, k0 - half), kin1 = min(m, k0 + tile_out + half);      // inputs [kin0, kin1)
       const int kout1 = min(m, k0 + tile_out);
       const int nin = kin1 - kin0;
-      const int i_lo = f2_select(sm, nw, kin0), i_hi = f2_select(sm, nw, kin1 - 1) + 1;
+      int sel4[4];
+      f2_select4(sm, nw, kin0, kin1 - 1, k0, kout1 - 1, sel4);
+      const int i_lo = sel4[0], i_hi = sel4[1] + 1;
       const double qc = 0.5 * (double)nin;
-      __syncthreads();
       // stage x_q in P[0][q + 1]
       for (int i = i_lo + t; i < i_hi; i += F2_THREADS)
         if (f2_kept(sm, i)) P[f2_rank(sm, i) - kin0 + 1] = f[i];
@@ -306,7 +329,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       }
       __syncthreads();
       // outputs of the tile that are interior points of a filtered segment
-      const int o_lo = f2_select(sm, nw, k0), o_hi = f2_select(sm, nw, kout1 - 1) + 1;
+      const int o_lo = sel4[2], o_hi = sel4[3] + 1;
       int l = 0, h = -1;                                   // this thread's last segment (positions only grow)
       for (int i = o_lo + t; i < o_hi; i += F2_THREADS) {
         if (!f2_kept(sm, i)) continue;
@@ -340,7 +363,9 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       if (len <= 0) continue;
       const bool fallback = (w > len) || ((double)len < break_tolerance);
       if (fallback) {
-        const int i_lo = f2_select(sm, nw, l), i_hi = f2_select(sm, nw, h - 1) + 1;
+        int sel4[4];
+        f2_select4(sm, nw, l, h - 1, -1, -1, sel4);
+        const int i_lo = sel4[0], i_hi = sel4[1] + 1;
         const double md = block_nanmedian([&](int64_t j) { return f2_kept(sm, i_lo + (int)j) ? f[i_lo + j] : qnan; },
                                           i_hi - i_lo, sm.sel);
         for (int i = i_lo + t; i < i_hi; i += F2_THREADS)
@@ -350,7 +375,10 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       if (half == 0) continue;
       for (int side = 0; side < 2; ++side) {
         const int kw0 = side == 0 ? l : h - w;                    // first kept position of the w-sample fit window
-        const int i_lo = f2_select(sm, nw, kw0), i_hi = f2_select(sm, nw, kw0 + w - 1) + 1;
+        const int kq0 = side == 0 ? l : h - half;                 // outputs: the first / last `half` positions of the window
+        int sel4[4];
+        f2_select4(sm, nw, kw0, kw0 + w - 1, kq0, kq0 + half - 1, sel4);
+        const int i_lo = sel4[0], i_hi = sel4[1] + 1;
         double mom[F2_MAXQ];
 #pragma unroll
         for (int r = 0; r < F2_MAXQ; ++r) mom[r] = 0.0;
@@ -373,8 +401,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
           bet[r] = acc;
         }
         // outputs: the first (side 0) / last (side 1) `half` positions of the window
-        const int kq0 = side == 0 ? l : h - half;
-        const int j_lo = f2_select(sm, nw, kq0), j_hi = f2_select(sm, nw, kq0 + half - 1) + 1;
+        const int j_lo = sel4[2], j_hi = sel4[3] + 1;
         for (int i = j_lo + t; i < j_hi; i += F2_THREADS) {
           if (!f2_kept(sm, i)) continue;
           const double u = ((double)(f2_rank(sm, i) - kw0) - (double)half) / sc;
@@ -423,8 +450,9 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
     if (t == 0) status[b] = 1;
     return;
   }
-  const int s_first = f2_select(sm, nw, 0), s_second = f2_select(sm, nw, 1);
-  const int s_last = f2_select(sm, nw, ms - 1), s_prelast = f2_select(sm, nw, ms - 2);
+  int selE[4];
+  f2_select4(sm, nw, 0, 1, ms - 1, ms - 2, selE);
+  const int s_first = selE[0], s_second = selE[1], s_last = selE[2], s_prelast = selE[3];
   for (int g = t; g < n; g += F2_THREADS) {
     const int j = f2_rank(sm, g);                          // survivors before g = np.searchsorted(xs, t[g], "left")
     int il, ih;

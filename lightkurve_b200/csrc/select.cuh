@@ -136,10 +136,15 @@ __device__ double block_nanmedian(Get get, int64_t n, SelSmem& sm, long long* co
 // shared-memory buffer, and the order statistics are selected inside that buffer (radix select over shared memory).
 // Exact; if the bracket misses (probability ~1e-3 per call for random data) or more than FS_CAP values fall between
 // (heavily skewed duplicates), the caller's answer comes from block_nanmedian above - same result, just slower.
-constexpr int FS_SAMPLE = 1024, FS_GAP = 56, FS_CAP = 6144;
+// Sizing: the bracket spans 2 FS_GAP of the FS_SAMPLE sample ranks, i.e. a fraction 2 FS_GAP / FS_SAMPLE = 1/16 of the data
+// (65 000 cadences: 4060 +- 350 candidates, FS_CAP is 4.5 sigma above); the median's rank in the sample has standard
+// deviation sqrt(FS_SAMPLE) / 2 = 22.6, so the bracket misses it with probability 0.5 %.  (Round 2's first version used
+// 1024 / 56 / 6144: 7100 +- 630 expected candidates for 65 000 cadences - it overflowed the buffer and fell back to the
+// 8-pass select 93 % of the time; found in the per-line ncu profile, profiles/r02_flatten2_v2_fastselect.md.)
+constexpr int FS_SAMPLE = 2048, FS_GAP = 64, FS_CAP = 5632;
 struct FastSelSmem {
-  double* cand;                 // FS_CAP doubles of shared memory provided by the caller (may alias idle scratch)
-  double sample[FS_SAMPLE];
+  double* cand;                 // FS_CAP + FS_SAMPLE doubles of shared memory provided by the caller (may alias idle
+                                // scratch): candidates first, then the sample
   int n_cand, c_lt, c_eqlo, c_eqhi, ok;
 };
 
@@ -168,18 +173,22 @@ __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelS
   long long m = m_known;
   if (m < 0) {
     long long cnt = 0;
+#pragma unroll 4
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double v = get(i); cnt += (v == v) ? 1 : 0; }
     m = block_sum_ll(cnt, sm.redll);
   }
   if (m == 0) return qnan;
   const int64_t stride = n / FS_SAMPLE;
-  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) fs.sample[sidx] = get((int64_t)sidx * stride);
-  __syncthreads();
+  double* const sample = fs.cand + FS_CAP;
   long long scnt = 0;
-  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) scnt += (fs.sample[sidx] == fs.sample[sidx]) ? 1 : 0;
-  const long long ns = block_sum_ll(scnt, sm.redll);
+  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) {
+    const double v = get((int64_t)sidx * stride);
+    sample[sidx] = v;
+    scnt += (v == v) ? 1 : 0;
+  }
+  const long long ns = block_sum_ll(scnt, sm.redll);             // (its barriers also publish the sample)
   if (ns < 4 * FS_GAP) return block_nanmedian(get, n, sm);
-  auto gets = [&](int64_t i) { return fs.sample[i]; };
+  auto gets = [&](int64_t i) { return sample[i]; };
   long long rlo = ns / 2 - FS_GAP, rhi = ns / 2 + FS_GAP;
   if (rlo < 0) rlo = 0;
   if (rhi > ns - 1) rhi = ns - 1;
@@ -189,27 +198,32 @@ __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelS
   if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; }
   __syncthreads();
   int c_lt = 0, c_eqlo = 0, c_eqhi = 0;
-  for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {
-    const int64_t i = i0 + threadIdx.x;
-    bool between = false;
-    double v = 0.0;
-    if (i < n) {
-      v = get(i);
+  for (int64_t i0 = 0; i0 < n; i0 += 4 * (int64_t)blockDim.x) {   // warp-uniform trip count; 4 loads in flight per thread
+    double vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+      vv[u] = (i < n) ? get(i) : qnan;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double v = vv[u];
+      bool between = false;
       if (v == v) {
         if (v < lo) c_lt++;
         else if (v == lo) c_eqlo++;
         else if (v < hi) between = true;
         else if (v == hi) c_eqhi++;
       }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, between);
-    if (bal) {
-      int base = 0;
-      if ((threadIdx.x & 31) == 0) base = atomicAdd(&fs.n_cand, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (between) {
-        const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-        if (pos < FS_CAP) fs.cand[pos] = v;
+      const unsigned bal = __ballot_sync(0xffffffffu, between);
+      if (bal) {
+        int base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(&fs.n_cand, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (between) {
+          const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+          if (pos < FS_CAP) fs.cand[pos] = v;
+        }
       }
     }
   }
@@ -235,6 +249,7 @@ template <class Get>
 __device__ double block_nanstd(Get get, int64_t n, SelSmem& sm, double* mean_out = nullptr) {
   double s = 0.0;
   long long c = 0;
+#pragma unroll 4
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double v = get(i);
     if (v == v) { s += v; c++; }
@@ -245,6 +260,7 @@ __device__ double block_nanstd(Get get, int64_t n, SelSmem& sm, double* mean_out
   const double mean = tot / (double)m;
   if (mean_out) *mean_out = mean;
   double q = 0.0;
+#pragma unroll 4
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double v = get(i);
     if (v == v) { const double d = v - mean; q += d * d; }

@@ -30,7 +30,7 @@ int emu_flatten2(const double* t, const double* f, const double* fe, const unsig
   const int NM = polyorder <= 1 ? 1 : polyorder <= 3 ? 3 : 5;
   const int half = window / 2;
   const size_t smem = ((sizeof(lkb::F2Smem) + 15) & ~(size_t)15) +
-                      sizeof(double) * std::max((size_t)NM * (tile_out + 2 * half + 1), (size_t)lkb::FS_CAP);
+                      sizeof(double) * std::max((size_t)NM * (tile_out + 2 * half + 1), (size_t)(lkb::FS_CAP + lkb::FS_SAMPLE));
   std::vector<double> tro((size_t)off[B] + 1, 0.0);
   if (NM == 1)
     LKB_LAUNCH_SMEM(B, lkb::F2_THREADS, smem, 0, lkb::flatten2_kernel<1>)(t, f, fe, ex, off, tro.data(), window, break_tol,

@@ -5,6 +5,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <map>
 
@@ -39,6 +40,14 @@ void prof_end(cudaStream_t) {}
 extern "C" {
 
 const char* emu_last_error() { return lkb::g_err; }
+
+// diagnostic: copy of a workspace slot as the last call left it (returns the slot's size in bytes)
+int64_t emu_ws_read(int slot, void* dst, int64_t bytes) {
+  auto it = lkb::g_ws.find(slot);
+  if (it == lkb::g_ws.end()) return -1;
+  if (dst && bytes > 0) memcpy(dst, it->second.first, (size_t)std::min<int64_t>(bytes, (int64_t)it->second.second));
+  return (int64_t)it->second.second;
+}
 
 // shared cadence grid: t_rel [N] (ascending, t_rel[0] = 0), yc [B, ystride] centred fp32, ysum/absmax [B],
 // rot/rot2 [F] (rows < F_low pre-filled by the caller), power [B, F] out
