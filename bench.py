@@ -931,6 +931,7 @@ def main():
     engine.profile_enable(False)
     clocks = sampler.stop() if sampler else None
     family = engine.ls_last_algo()             # what `auto` resolved to: "nufft", "tcgen05" or "simt"
+    escalated = engine.ls_last_escalated()     # light curves of the last step that took the double-precision pass
 
     for _ in range(2):
         step_e2e()
@@ -1026,6 +1027,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "batch_per_gpu": B, "cadences": N,
                        "frequencies": F, "normalization": "amplitude", "algo": args.algo, "kernel_family": family,
+                       "escalated_per_step": escalated,
                        "sharding": "by target, %d rank(s), %s" % (world, "no collective" if world == 1 else
                                    "%d asynchronous NCCL all-gathers of [%d x %d] power blocks per step, overlapped with the "
                                    "next piece's kernels" % (pieces, world * pb_rows, F)),

@@ -73,6 +73,9 @@ int64_t lkb_launch_count(void);
 /* kernel family (LKB_LS_ALGO_SIMT / _TCGEN05 / _NUFFT) the most recent lkb_ls_power* call actually ran; -1 before
  * the first call.  Lets a caller (bench.py, tests) see what LKB_LS_ALGO_AUTO resolved to. */
 int lkb_ls_last_algo(void);
+/* light curves of the most recent shared-grid NUFFT call that were transformed a second time in double precision
+ * (precision escalation: flux excursion > LKB_NUFFT_ESCALATE [250] x the in-band peak amplitude) */
+int lkb_ls_last_escalated(void);
 /* Measurement hooks (bench.py roofline): when enabled, every compute call records CUDA events on
  * its stream around its DOMINANT kernel (LS contraction / BLS search / flatten / Gram accumulation).
  * lkb_profile_read synchronises, writes up to max_n durations [ms] in call order, resets the ring

@@ -13,6 +13,7 @@ namespace lkb {
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;
 extern int g_last_ls_algo;
+extern int g_last_escalated;     // ls_nufft.cu: light curves of the last call that took the double-precision pass
 extern int64_t g_epoch;
 
 #define LKB_CUDA_CHECK(expr)                                                        \
@@ -69,6 +70,7 @@ enum Slot {
   WS_IN0, WS_IN1, WS_IN2, WS_IN3, WS_IN4, WS_IN5, WS_IN6, WS_IN7,
   WS_OUT0, WS_OUT1, WS_OUT2, WS_OUT3, WS_OUT4, WS_OUT5, WS_OUT6, WS_OUT7,
   WS_X0, WS_X1, WS_X2, WS_X3, WS_X4, WS_X5, WS_X6, WS_X7,
+  WS_Y0, WS_Y1, WS_Y2, WS_Y3, WS_Y4, WS_Y5, WS_Y6, WS_Y7,
   WS_NSLOTS
 };
 int ws_get(int slot, size_t bytes, void** out);

@@ -996,6 +996,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     return LKB_E_UNSUPPORTED;
   }
   g_last_ls_algo = use_nufft ? LKB_LS_ALGO_NUFFT : LKB_LS_ALGO_SIMT;
+  g_last_escalated = 0;
   const bool use_tc = !use_nufft && ((algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
   if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
     set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");

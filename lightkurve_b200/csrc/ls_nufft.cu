@@ -418,12 +418,53 @@ nufft2_lowrows_kernel(const float2* __restrict__ D, int64_t N, int64_t Npad, con
 __global__ void nufft2_lowfinish_kernel(const double* __restrict__ acc, int B, int F_low, int64_t F, int64_t N,
                                         const float4* __restrict__ rot, const float2* __restrict__ rot2,
                                         const float* __restrict__ ysum, int normalization, float scale,
-                                        float* __restrict__ power) {
+                                        float* __restrict__ power, unsigned* __restrict__ peak) {
   const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (e >= B * F_low) return;
   const int b = e / F_low, k = e - b * F_low;
-  power[(int64_t)b * F + k] = ls_epilogue_shared((float)acc[2 * (int64_t)e], (float)acc[2 * (int64_t)e + 1], rot[k], rot2[k],
-                                                 ysum[b], (float)N, normalization, scale, true);
+  const float pw = ls_epilogue_shared((float)acc[2 * (int64_t)e], (float)acc[2 * (int64_t)e + 1], rot[k], rot2[k], ysum[b],
+                                      (float)N, LKB_LS_NORM_PSD_RAW, 1.0f, true);
+  power[(int64_t)b * F + k] = v2_normalise(pw, (float)N, normalization, scale);
+  if (peak && pw > 0.0f) atomicMax(peak + b, __float_as_uint(pw));     // (a handful of rows per light curve)
+}
+
+// Escalation pass, low rows: the listed light curves' rows k < F_low once more from direct FP64 sums and the FP64
+// floating-mean formula (ls_common.cuh: ls_power_from_sums).  grid (F_low, n), 256 threads.
+__global__ void __launch_bounds__(256)
+nufft2_lowrows_exact_kernel(const int* __restrict__ list, const double* __restrict__ t, int64_t N,
+                            const float* __restrict__ yc, int64_t ystride, const double* __restrict__ freq, int64_t F,
+                            int normalization, float scale, float* __restrict__ power) {
+  __shared__ double red[7][8];
+  const int k = (int)blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = list[blockIdx.y];
+  const float* y = yc + b * ystride;
+  const double fr = freq[k];
+  LsSums<double> d;
+  d.zero();
+  double ysum = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    double sn, cs;
+    ls_sincos_cycles_f64(fr * t[i], sn, cs);
+    const double v = (double)y[i];
+    d.add(v, sn, cs);
+    ysum += v;
+  }
+  d.warp_reduce();
+  ysum = warp_sum(ysum);
+  if (lane == 0) {
+    red[0][warp] = d.sh; red[1][warp] = d.ch; red[2][warp] = d.s; red[3][warp] = d.c; red[4][warp] = d.cc;
+    red[5][warp] = d.sc; red[6][warp] = ysum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[7];
+    for (int q = 0; q < 7; ++q) {
+      a[q] = 0.0;
+      for (int w2 = 0; w2 < 8; ++w2) a[q] += red[q][w2];
+    }
+    d.sh = a[0]; d.ch = a[1]; d.s = a[2]; d.c = a[3]; d.cc = a[4]; d.sc = a[5];
+    power[b * F + k] = ls_normalize(ls_power_from_sums(d, (double)N, a[6]), (double)N, normalization, (double)scale);
+  }
 }
 
 // Self-check of the v2 path: Zn [nv][Mh] holds the transforms of the first nv light curves in natural order (modes
@@ -539,15 +580,27 @@ int fft_fourstep(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out, con
                                : fft_fourstep_t<false>(Z, p, npairs, st, pa_out, sp);
 }
 
+// 10 cells: with 8 the aliasing images of a strong line ABOVE the frequency grid (a near-regular cadence repeats the
+// spectrum every 1 / dt) came back into the band at 2.5e-8 of its amplitude - 1.5x the tolerance on light curves whose
+// in-band spectrum is 1000x below their variability; 10 cells put it at 3e-10 and cost nothing measurable (the spread
+// kernel is 15 % of the step).  tools/worst_bins.py, DESIGN.md section 2.
 int kernel_width() {
-  int w = 8;
+  int w = 10;
   if (const char* e = getenv("LKB_NUFFT_W")) w = atoi(e);
   if (w < 4) w = 4;
   if (w > 12) w = 12;
   return w & ~1;                                  // even widths only
 }
 
+// precision escalation threshold (nufft_v2.cuh): max |y - mean| over the in-band peak amplitude; <= 0 turns it off
+float escalate_ratio() {
+  if (const char* e = getenv("LKB_NUFFT_ESCALATE")) return (float)atof(e);
+  return 250.0f;
+}
+
 }  // namespace
+
+int g_last_escalated = 0;      // light curves of the last ls_nufft_run that took the double-precision pass
 
 // Regular grid f_k = (k0 + k) df with integer k0 >= 0, df * baseline <= 1, fine grids that fit 2^24 cells.
 bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df, double t_last) {
@@ -572,6 +625,8 @@ struct NufftPlan {
   int n1max;            // v2: rows of the [A][Bc] grid of z cells the cadences reach
   V2Tables tb;          // v2: twiddle tables (valid when fft_mode(p) == 3)
   const float* Wt;      // v2: kernel weights [N, w]
+  const double* Wtd;    // v2: the same in double precision (escalation pass)
+  V2TablesD tbd;        // v2: double-precision twiddle tables (escalation pass)
   const V2FTab* ftab;   // v2: folded finish table [F] (rows >= F_low)
   const float2* lowD;   // v2: design matrix of the low rows [F_low, Npad]
   int64_t Npad;
@@ -623,6 +678,7 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
   }
   g_plan.n1max = 0;
   g_plan.Wt = nullptr;
+  g_plan.Wtd = nullptr;
   g_plan.ftab = nullptr;
   g_plan.lowD = nullptr;
   g_plan.Npad = Npad;
@@ -632,9 +688,15 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     LKB_TRY(v2_tables(p, WS_IN6, st, &g_plan.tb));
     float* Wt = nullptr;
     LKB_TRY(ws_get_t<float>(WS_X0, (size_t)N * w, &Wt));
-    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel)(d_t, N, grid_df, M, w, (double)beta, Wt);
+    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel<float>)(d_t, N, grid_df, M, w, (double)beta, Wt);
     LKB_LAUNCH_CHECK();
     g_plan.Wt = Wt;
+    double* Wtd = nullptr;
+    LKB_TRY(ws_get_t<double>(WS_Y0, (size_t)N * w, &Wtd));
+    LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel<double>)(d_t, N, grid_df, M, w, (double)beta, Wtd);
+    LKB_LAUNCH_CHECK();
+    g_plan.Wtd = Wtd;
+    LKB_TRY(v2_tables(p, WS_Y1, st, &g_plan.tbd));
     if (F_low > 0) {
       float2* lowD = nullptr;
       LKB_TRY(ws_get_t<float2>(WS_X2, (size_t)F_low * Npad, &lowD));
@@ -713,12 +775,20 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
         pl.fge, pl.cad, pl.Wt, d_yc, ystride, B, w, p, ptc, pl.n1max, G);
     LKB_LAUNCH_CHECK();
     LKB_TRY(v2_cols(G, T, p, pl.n1max, B, pl.tb, st));
-    if (F_low < F) {
-      V2Finish fa;
-      fa.ftab = pl.ftab; fa.k0 = k0; fa.F = F; fa.k_lo = F_low; fa.ysum = d_ysumf; fa.Nf = (float)N;
-      fa.normalization = normalization; fa.scale = (float)norm_scale; fa.power = d_pow;
-      LKB_TRY(v2_rows(T, p, B, pl.tb, &fa, nullptr, 0, st));
+    // in-band peak of every light curve (psd-scaled power, float bits), filled by the two finish kernels
+    const float esc_ratio = escalate_ratio();
+    unsigned* d_peak = nullptr;
+    int* d_list = nullptr;                                       // [0] = count, [1 ..] = listed light curves
+    if (esc_ratio > 0.0f && F_low < F) {
+      LKB_TRY(ws_get_t<unsigned>(ws_alt ? WS_Y3 : WS_Y2, (size_t)2 * B + 1, &d_peak));      // peak [B] | count | list [B]
+      d_list = reinterpret_cast<int*>(d_peak + B);
+      LKB_CUDA_CHECK(cudaMemsetAsync(d_peak, 0, sizeof(unsigned) * ((size_t)B + 1), st));
     }
+    V2Finish fa;
+    fa.ftab = pl.ftab; fa.k0 = k0; fa.F = F; fa.k_lo = F_low; fa.ysum = d_ysumf; fa.Nf = (float)N;
+    fa.normalization = normalization; fa.scale = (float)norm_scale; fa.power = d_pow;
+    fa.peak = d_peak; fa.lcmap = nullptr; fa.log2M = p;
+    if (F_low < F) LKB_TRY(v2_rows(T, p, B, pl.tb, &fa, (float2*)nullptr, 0, st));
     if (F_low > 0) {
       double* acc = nullptr;
       LKB_TRY(ws_get_t<double>(ws_alt ? WS_X4 : WS_X3, (size_t)B * F_low * 2, &acc));
@@ -731,14 +801,45 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
           pl.lowD, N, pl.Npad, d_yc, ystride, B, (int)F_low, slice, acc);
       LKB_LAUNCH_CHECK();
       LKB_LAUNCH(blocks_for((int64_t)B * F_low, 256), 256, st, nufft2_lowfinish_kernel)(
-          acc, B, (int)F_low, F, N, d_rot, d_rot2, d_ysumf, normalization, (float)norm_scale, d_pow);
+          acc, B, (int)F_low, F, N, d_rot, d_rot2, d_ysumf, normalization, (float)norm_scale, d_pow, d_peak);
       LKB_LAUNCH_CHECK();
+    }
+    // ---- precision escalation (nufft_v2.cuh): light curves whose flux excursion dwarfs their in-band peak are
+    // transformed again in double precision; the count comes back to the host (one 4-byte copy and a stream sync)
+    if (d_peak) {
+      LKB_LAUNCH(blocks_for(B, 256), 256, st, nufft2_flag_kernel)(d_peak, d_absmax, B, (float)N, esc_ratio, d_list, d_list + 1);
+      LKB_LAUNCH_CHECK();
+      int h_cnt = 0;
+      LKB_CUDA_CHECK(cudaMemcpyAsync(&h_cnt, d_list, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LKB_CUDA_CHECK(cudaStreamSynchronize(st));
+      g_last_escalated += h_cnt;
+      const int cap = 64;
+      for (int i0 = 0; i0 < h_cnt; i0 += cap) {
+        const int n = std::min(cap, h_cnt - i0);
+        double2 *Gd = nullptr, *Td = nullptr;
+        LKB_TRY(ws_get_t<double2>(ws_alt ? WS_Y6 : WS_Y4, (size_t)n * cells, &Gd));
+        LKB_TRY(ws_get_t<double2>(ws_alt ? WS_Y7 : WS_Y5, (size_t)n * Mh, &Td));
+        const int* lst = d_list + 1 + i0;
+        LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)n), 256, st, nufft2_spread_list_kernel)(
+            pl.fge, pl.cad, pl.Wtd, d_yc, ystride, lst, w, p, ptc, pl.n1max, Gd);
+        LKB_LAUNCH_CHECK();
+        LKB_TRY(v2_cols(Gd, Td, p, pl.n1max, n, pl.tbd, st));
+        V2Finish fd = fa;
+        fd.peak = nullptr;
+        fd.lcmap = lst;
+        LKB_TRY(v2_rows(Td, p, n, pl.tbd, &fd, (double2*)nullptr, 0, st));
+        if (F_low > 0) {
+          LKB_LAUNCH(dim3((unsigned)F_low, (unsigned)n), 256, st, nufft2_lowrows_exact_kernel)(
+              lst, d_t, N, d_yc, ystride, d_freq, F, normalization, (float)norm_scale, d_pow);
+          LKB_LAUNCH_CHECK();
+        }
+      }
     }
     if (prof) prof_end(st);
     if (verify) {            // the first light curves' transforms once more, written out this time (G is free again)
       const int nv = std::min(B, 4);
       const int nk2 = (int)((k0 + F) >> (p - 1 - V2_PB)) + 1;
-      LKB_TRY(v2_rows(T, p, nv, pl.tb, nullptr, G, nk2, st));
+      LKB_TRY(v2_rows(T, p, nv, pl.tb, (const V2Finish*)nullptr, G, nk2, st));
       const char* fe = getenv("LKB_NUFFT_INJECT_FAULT");
       LKB_CUDA_CHECK(cudaMemsetAsync(d_worst, 0, sizeof(unsigned), st));
       LKB_LAUNCH(16, 128, st, nufft2_verify_kernel)(G, p, pl.dec, k0, F, F_low, d_t, N, d_yc, ystride, d_freq, nv,
@@ -841,6 +942,7 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
                     const float* d_absmax, int B, const double* d_freq, int64_t F, double grid_f0, double grid_df,
                     float4* d_rot, float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
                     cudaStream_t st) {
+  g_last_escalated = 0;
   LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_low, st, d_freq, ystride));
   return ls_nufft_run(d_t, N, d_yc, ystride, d_ysumf, d_absmax, B, d_freq, F, d_rot, d_rot2, F_low, normalization,
                       norm_scale, d_pow, st, 0, true);

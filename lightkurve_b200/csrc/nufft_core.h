@@ -28,6 +28,8 @@
 #if !defined(LKB_CUDA_EMU)          // (tests/native/cuda_emu.h brings CUDA's own vector types)
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
+struct double2 { double x, y; };
+static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 #endif
 #endif
 
@@ -132,40 +134,56 @@ LKB_HD float spread_cell_search(int64_t m, const Cad* cad, int64_t n, const floa
 // ---- FFT ------------------------------------------------------------------------------------------
 LKB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
+LKB_HD double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// complex value type of a transform: float2 (the batch path) or double2 (the escalation pass of nufft_v2.cuh)
+template <class CT> struct CplxOf;
+template <> struct CplxOf<float2> {
+  typedef float real;
+  static LKB_HD float2 mk(float a, float b) { return make_float2(a, b); }
+};
+template <> struct CplxOf<double2> {
+  typedef double real;
+  static LKB_HD double2 mk(double a, double b) { return make_double2(a, b); }
+};
+
 // exp(+2 pi i q / 16), q = 0 .. 7
-LKB_HD float2 w16(int q) {
+template <class CT>
+LKB_HD CT w16_t(int q) {
+  typedef typename CplxOf<CT>::real RT;
   switch (q) {
-    case 0: return make_float2(1.0f, 0.0f);
-    case 1: return make_float2(0.923879532511286756f, 0.382683432365089772f);
-    case 2: return make_float2(0.707106781186547524f, 0.707106781186547524f);
-    case 3: return make_float2(0.382683432365089772f, 0.923879532511286756f);
-    case 4: return make_float2(0.0f, 1.0f);
-    case 5: return make_float2(-0.382683432365089772f, 0.923879532511286756f);
-    case 6: return make_float2(-0.707106781186547524f, 0.707106781186547524f);
-    default: return make_float2(-0.923879532511286756f, 0.382683432365089772f);
+    case 0: return CplxOf<CT>::mk((RT)1.0, (RT)0.0);
+    case 1: return CplxOf<CT>::mk((RT)0.923879532511286756128183189397, (RT)0.382683432365089771728459984030);
+    case 2: return CplxOf<CT>::mk((RT)0.707106781186547524400844362105, (RT)0.707106781186547524400844362105);
+    case 3: return CplxOf<CT>::mk((RT)0.382683432365089771728459984030, (RT)0.923879532511286756128183189397);
+    case 4: return CplxOf<CT>::mk((RT)0.0, (RT)1.0);
+    case 5: return CplxOf<CT>::mk((RT)-0.382683432365089771728459984030, (RT)0.923879532511286756128183189397);
+    case 6: return CplxOf<CT>::mk((RT)-0.707106781186547524400844362105, (RT)0.707106781186547524400844362105);
+    default: return CplxOf<CT>::mk((RT)-0.923879532511286756128183189397, (RT)0.382683432365089771728459984030);
   }
 }
+LKB_HD float2 w16(int q) { return w16_t<float2>(q); }
 
 // in-place DFT of R points with the +i sign, natural order in and out (decimation in time, recursive halves)
-template <int R>
+template <int R, class CT = float2>
 struct SmallDft {
-  static LKB_HD void run(float2* u) {
-    float2 e[R / 2], o[R / 2];
+  static LKB_HD void run(CT* u) {
+    CT e[R / 2], o[R / 2];
 #pragma unroll
     for (int i = 0; i < R / 2; ++i) { e[i] = u[2 * i]; o[i] = u[2 * i + 1]; }
-    SmallDft<R / 2>::run(e);
-    SmallDft<R / 2>::run(o);
+    SmallDft<R / 2, CT>::run(e);
+    SmallDft<R / 2, CT>::run(o);
 #pragma unroll
     for (int q = 0; q < R / 2; ++q) {
-      const float2 tw = cmul(o[q], w16(q * (16 / R)));
-      u[q] = make_float2(e[q].x + tw.x, e[q].y + tw.y);
-      u[q + R / 2] = make_float2(e[q].x - tw.x, e[q].y - tw.y);
+      const CT tw = cmul(o[q], w16_t<CT>(q * (16 / R)));
+      u[q] = CplxOf<CT>::mk(e[q].x + tw.x, e[q].y + tw.y);
+      u[q + R / 2] = CplxOf<CT>::mk(e[q].x - tw.x, e[q].y - tw.y);
     }
   }
 };
-template <>
-struct SmallDft<1> {
-  static LKB_HD void run(float2*) {}
+template <class CT>
+struct SmallDft<1, CT> {
+  static LKB_HD void run(CT*) {}
 };
 
 LKB_HD float2 unit_phase(int64_t num, int64_t den) {     // exp(+2 pi i num / den), den a power of two, num < 2^24

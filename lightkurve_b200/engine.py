@@ -47,6 +47,11 @@ def ls_last_algo():
         int(L.load().lkb_ls_last_algo()), "none")
 
 
+def ls_last_escalated():
+    """Light curves of the most recent shared-grid NUFFT call that took the double-precision pass (lkb200.h)."""
+    return int(L.load().lkb_ls_last_escalated())
+
+
 def profile_enable(on=True):
     """Record CUDA events around the dominant kernel of each subsequent call (see lkb200.h)."""
     L.check(L.load().lkb_profile_enable(1 if on else 0))
@@ -64,7 +69,7 @@ def profile_read(max_n=512):
 # workspace slot numbers (enum Slot in csrc/common.cuh) for the diagnostic read-back
 WS_SLOTS = {name: i for i, name in enumerate(
     ["A", "B", "C", "D", "E", "F", "G", "H", "I", "J", "K", "L", "M", "N", "O", "P"]
-    + ["IN%d" % i for i in range(8)] + ["OUT%d" % i for i in range(8)] + ["X%d" % i for i in range(8)])}
+    + ["IN%d" % i for i in range(8)] + ["OUT%d" % i for i in range(8)] + ["X%d" % i for i in range(8)] + ["Y%d" % i for i in range(8)])}
 
 
 def ws_read(slot, count, dtype, offset_bytes=0):

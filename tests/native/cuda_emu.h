@@ -242,6 +242,7 @@ inline double __dsub_rn(double a, double b) { volatile double r = a - b; return 
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline unsigned long long __double2ull_rd(double x) { return (unsigned long long)floor(x); }
 template <typename A, typename B>
 inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }

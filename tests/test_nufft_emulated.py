@@ -32,6 +32,7 @@ def emu(tmp_path_factory):
     lib.emu_nufft_ragged.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_int,
                                      c_vp, c_vp]
     lib.emu_last_error.restype = ctypes.c_char_p
+    lib.emu_last_escalated.restype = ctypes.c_int
     return lib
 
 
@@ -236,3 +237,52 @@ def test_built_in_self_check(emu, monkeypatch):
         assert emu.emu_nufft_shared(*args) == 0, emu.emu_last_error()
     monkeypatch.setenv("LKB_NUFFT_INJECT_FAULT", "1.01")
     assert emu.emu_nufft_shared(*args) == -7 and b"self-check failed" in emu.emu_last_error()
+
+
+def test_precision_escalation_on_the_emulator(emu, monkeypatch):
+    """A light curve whose variability sits ABOVE the frequency grid (a strong line at ~0.7 Nyquist) while its in-band
+    spectrum is only noise: the fp32 transform's rounding noise scales with the loud line, the tolerance with the
+    in-band peak (config C2's worst bins, tools/worst_bins.py).  The finish flags it (flux excursion > 250 x in-band
+    peak amplitude) and the double-precision instantiation of the same kernels replaces its row; a light curve with a
+    visible in-band line is left alone.  Checked over EVERY bin against the fp64 oracle."""
+    rng = np.random.default_rng(5)
+    n0, dt = 9900, 0.02
+    keep = np.ones(n0, bool)
+    for c in rng.choice(n0 - 60, 6, replace=False):
+        keep[c:c + 50] = False                                       # a near-regular cadence with gaps
+    t = 131.5 + np.flatnonzero(keep) * dt
+    trel = t - t[0]
+    N, F, B, oversample = len(t), 14000, 2, 5.0
+    df = 1.0 / (oversample * trel[-1])
+    freq = df * (1 + np.arange(F))
+    nyq = 0.5 / dt
+    f_loud = rng.uniform(freq[-1] * 1.02, 0.82 * nyq, B)
+    inband = [0.0, 2e-4]                                             # light curve 1 has a visible in-band line
+    Y = np.stack([1 + 8e-3 * np.sin(2 * np.pi * f_loud[b] * t + b) + inband[b] * np.sin(2 * np.pi * 3.1 * t)
+                  + 5e-5 * rng.normal(size=N) for b in range(B)]).astype(np.float32).astype(np.float64)
+    yc = (Y - Y.mean(axis=1, keepdims=True)).astype(np.float32)
+    Npad = ((N + 63) // 64) * 64
+    ycp = np.zeros((B, Npad), np.float32)
+    ycp[:, :N] = yc
+    ysum = ycp.astype(np.float64).sum(axis=1).astype(np.float32)
+    absmax = np.abs(ycp).max(axis=1).astype(np.float32)
+    F_low = int((freq * trel[-1] <= 2.0).sum()) + 1
+    rot, rot2 = _window_rows(trel, freq, F_low)
+    ref = [np.sqrt(ols.ls_slow_psd(t, Y[b], freq)) * np.sqrt(4.0 / N) for b in range(B)]
+
+    def run(ratio):
+        monkeypatch.setenv("LKB_NUFFT_ESCALATE", ratio)
+        power = np.zeros((B, F), np.float32)
+        rc = emu.emu_nufft_shared(trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B,
+                                  freq.ctypes.data, F, df, df, rot.ctypes.data, rot2.ctypes.data, F_low, 2,
+                                  2.0 / (N * oversample * df), power.ctypes.data)
+        assert rc == 0, emu.emu_last_error()
+        return [float(_excess(power[b].astype(np.float64), ref[b]).max()) for b in range(B)], emu.emu_last_escalated()
+
+    ex_on, n_on = run("250")
+    ex_off, n_off = run("0")
+    print("worst tolerance excess, escalation on / off:", ex_on, ex_off)
+    assert n_on == 1 and n_off == 0
+    assert ex_on[0] < 0.3 and ex_on[1] < 0.3
+    assert ex_on[0] < 0.6 * ex_off[0]                                # the double-precision pass is what lowered it
+    assert ex_on[1] == ex_off[1]                                     # the other light curve's row is untouched
