@@ -298,7 +298,7 @@ int lkb_profile_read(double* ms_out, int max_n) {
 }
 int64_t lkb_launch_count(void) { return g_launches; }
 int lkb_ls_last_algo(void) { return g_last_ls_algo; }
-int lkb_ls_last_escalated(void) { return g_last_escalated; }
+int lkb_ls_last_escalated(void) { return g_last_ls_algo == LKB_LS_ALGO_NUFFT ? ls_nufft_last_escalated() : 0; }
 
 // Diagnostic: copy `bytes` bytes at `offset` of workspace slot `slot` to the host buffer `out` (after a device
 // synchronise).  Lets a test or tools/nufft_gpu_check.py look at the intermediate buffers of the last call.

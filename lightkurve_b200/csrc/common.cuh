@@ -13,7 +13,9 @@ namespace lkb {
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;
 extern int g_last_ls_algo;
-extern int g_last_escalated;     // ls_nufft.cu: light curves of the last call that took the double-precision pass
+// ls_nufft.cu: light curves of the current / last shared-grid NUFFT call that took the double-precision pass
+void ls_nufft_begin_call(cudaStream_t st);
+int ls_nufft_last_escalated();
 extern int64_t g_epoch;
 
 #define LKB_CUDA_CHECK(expr)                                                        \

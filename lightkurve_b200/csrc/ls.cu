@@ -996,7 +996,6 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     return LKB_E_UNSUPPORTED;
   }
   g_last_ls_algo = use_nufft ? LKB_LS_ALGO_NUFFT : LKB_LS_ALGO_SIMT;
-  g_last_escalated = 0;
   const bool use_tc = !use_nufft && ((algo == LKB_LS_ALGO_TCGEN05) || (algo == LKB_LS_ALGO_AUTO && ls_tc_supported(B, N, F)));
   if (algo == LKB_LS_ALGO_TCGEN05 && !ls_tc_supported(B, N, F)) {
     set_error("lkb_ls_power_shared: tcgen05 path unsupported for this shape");
@@ -1101,6 +1100,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     LKB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
     LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_win, st, d_freq, Npad));
   }
+  if (use_nufft) ls_nufft_begin_call(st);
   if (!plan_hit) {
     g_key.valid = true;
     g_key.N = N; g_key.F = F; g_key.F_win = F_win; g_key.f0 = h_meta[1]; g_key.f1 = h_meta[2]; g_key.t_last = h_meta[3];

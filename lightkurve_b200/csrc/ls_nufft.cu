@@ -429,42 +429,70 @@ __global__ void nufft2_lowfinish_kernel(const double* __restrict__ acc, int B, i
 }
 
 // Escalation pass, low rows: the listed light curves' rows k < F_low once more from direct FP64 sums and the FP64
-// floating-mean formula (ls_common.cuh: ls_power_from_sums).  grid (F_low, n), 256 threads.
+// floating-mean formula (ls_common.cuh: ls_power_from_sums).  The sines and cosines of a (row, cadence chunk) are
+// evaluated once and reused for every listed light curve.  grid (F_low, ceil(N / 2048)), 256 threads.
+//   accW [F_low][4]      : sum s, c, c^2, s c                 (y-independent)
+//   accY [cap][F_low][2] : sum y s, sum y c                   (slot i = light curve list[base + i])
+//   accS [cap]           : sum y
+constexpr int LOWX_PER = 8;                               // cadences per thread
 __global__ void __launch_bounds__(256)
-nufft2_lowrows_exact_kernel(const int* __restrict__ list, const double* __restrict__ t, int64_t N,
-                            const float* __restrict__ yc, int64_t ystride, const double* __restrict__ freq, int64_t F,
-                            int normalization, float scale, float* __restrict__ power) {
-  __shared__ double red[7][8];
-  const int k = (int)blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = list[blockIdx.y];
-  const float* y = yc + b * ystride;
+nufft2_lowacc_kernel(const int* __restrict__ list, V2Count nc, const double* __restrict__ t, int64_t N,
+                     const float* __restrict__ yc, int64_t ystride, const double* __restrict__ freq, int F_low,
+                     double* __restrict__ accW, double* __restrict__ accY, double* __restrict__ accS) {
+  const int ntr = v2_count(nc, 0);
+  if (ntr <= 0) return;
+  const int k = (int)blockIdx.x, lane = threadIdx.x & 31;
+  const int64_t n0 = (int64_t)blockIdx.y * (256 * LOWX_PER) + threadIdx.x;
   const double fr = freq[k];
-  LsSums<double> d;
-  d.zero();
-  double ysum = 0.0;
-  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
-    double sn, cs;
-    ls_sincos_cycles_f64(fr * t[i], sn, cs);
-    const double v = (double)y[i];
-    d.add(v, sn, cs);
-    ysum += v;
-  }
-  d.warp_reduce();
-  ysum = warp_sum(ysum);
-  if (lane == 0) {
-    red[0][warp] = d.sh; red[1][warp] = d.ch; red[2][warp] = d.s; red[3][warp] = d.c; red[4][warp] = d.cc;
-    red[5][warp] = d.sc; red[6][warp] = ysum;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a[7];
-    for (int q = 0; q < 7; ++q) {
-      a[q] = 0.0;
-      for (int w2 = 0; w2 < 8; ++w2) a[q] += red[q][w2];
+  double sn[LOWX_PER], cs[LOWX_PER];
+  double ws = 0.0, wc = 0.0, wcc = 0.0, wsc = 0.0;
+#pragma unroll
+  for (int q = 0; q < LOWX_PER; ++q) {
+    const int64_t n = n0 + (int64_t)q * 256;
+    sn[q] = 0.0; cs[q] = 0.0;
+    if (n < N) {
+      ls_sincos_cycles_f64(fr * t[n], sn[q], cs[q]);
+      ws += sn[q]; wc += cs[q]; wcc += cs[q] * cs[q]; wsc += sn[q] * cs[q];
     }
-    d.sh = a[0]; d.ch = a[1]; d.s = a[2]; d.c = a[3]; d.cc = a[4]; d.sc = a[5];
-    power[b * F + k] = ls_normalize(ls_power_from_sums(d, (double)N, a[6]), (double)N, normalization, (double)scale);
   }
+  ws = warp_sum(ws); wc = warp_sum(wc); wcc = warp_sum(wcc); wsc = warp_sum(wsc);
+  if (lane == 0) {
+    atomicAdd(accW + 4 * k + 0, ws); atomicAdd(accW + 4 * k + 1, wc);
+    atomicAdd(accW + 4 * k + 2, wcc); atomicAdd(accW + 4 * k + 3, wsc);
+  }
+  for (int i = 0; i < ntr; ++i) {
+    const float* y = yc + (int64_t)list[nc.base + i] * ystride;
+    double sh = 0.0, ch = 0.0, sy = 0.0;
+#pragma unroll
+    for (int q = 0; q < LOWX_PER; ++q) {
+      const int64_t n = n0 + (int64_t)q * 256;
+      const double v = (n < N) ? (double)y[n] : 0.0;
+      sh = fma(v, sn[q], sh);
+      ch = fma(v, cs[q], ch);
+      sy += v;
+    }
+    sh = warp_sum(sh); ch = warp_sum(ch);
+    if (k == 0) sy = warp_sum(sy);
+    if (lane == 0) {
+      atomicAdd(accY + ((int64_t)i * F_low + k) * 2 + 0, sh);
+      atomicAdd(accY + ((int64_t)i * F_low + k) * 2 + 1, ch);
+      if (k == 0) atomicAdd(accS + i, sy);
+    }
+  }
+}
+__global__ void nufft2_lowexact_finish_kernel(const int* __restrict__ list, V2Count nc, const double* __restrict__ accW,
+                                              const double* __restrict__ accY, const double* __restrict__ accS,
+                                              int F_low, int64_t F, int64_t N, int normalization, float scale,
+                                              float* __restrict__ power) {
+  const int ntr = v2_count(nc, 0);
+  const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (e >= ntr * F_low) return;
+  const int i = e / F_low, k = e - i * F_low;
+  LsSums<double> d;
+  d.sh = accY[2 * (int64_t)e]; d.ch = accY[2 * (int64_t)e + 1];
+  d.s = accW[4 * k]; d.c = accW[4 * k + 1]; d.cc = accW[4 * k + 2]; d.sc = accW[4 * k + 3];
+  power[(int64_t)list[nc.base + i] * F + k] =
+      ls_normalize(ls_power_from_sums(d, (double)N, accS[i]), (double)N, normalization, (double)scale);
 }
 
 // Self-check of the v2 path: Zn [nv][Mh] holds the transforms of the first nv light curves in natural order (modes
@@ -600,8 +628,6 @@ float escalate_ratio() {
 
 }  // namespace
 
-int g_last_escalated = 0;      // light curves of the last ls_nufft_run that took the double-precision pass
-
 // Regular grid f_k = (k0 + k) df with integer k0 >= 0, df * baseline <= 1, fine grids that fit 2^24 cells.
 bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df, double t_last) {
   if (!regular || F < 2 || !(grid_df > 0.0) || !(grid_f0 >= 0.0)) return false;
@@ -626,12 +652,26 @@ struct NufftPlan {
   V2Tables tb;          // v2: twiddle tables (valid when fft_mode(p) == 3)
   const float* Wt;      // v2: kernel weights [N, w]
   const double* Wtd;    // v2: the same in double precision (escalation pass)
+  int* esc_total;       // v2: device counter of escalated light curves since ls_nufft_begin_call
   V2TablesD tbd;        // v2: double-precision twiddle tables (escalation pass)
   const V2FTab* ftab;   // v2: folded finish table [F] (rows >= F_low)
   const float2* lowD;   // v2: design matrix of the low rows [F_low, Npad]
   int64_t Npad;
 };
 static NufftPlan g_plan;
+
+// light curves that took the double-precision pass since the last ls_nufft_begin_call (diagnostic; synchronises)
+void ls_nufft_begin_call(cudaStream_t st) {
+  if (g_plan.esc_total) cudaMemsetAsync(g_plan.esc_total, 0, sizeof(int), st);
+}
+int ls_nufft_last_escalated() {
+  if (!g_plan.esc_total) return 0;
+  int h = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&h, g_plan.esc_total, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return h;
+}
+
 
 // d_t: times shifted to t[0] = 0 (ascending - checked here).  d_rot / d_rot2 rows [0, F_low) are already filled by
 // ls_window_kernel (fp64 path); the rows >= F_low are filled here from one transform of unit strengths.
@@ -679,6 +719,7 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
   g_plan.n1max = 0;
   g_plan.Wt = nullptr;
   g_plan.Wtd = nullptr;
+  g_plan.esc_total = nullptr;
   g_plan.ftab = nullptr;
   g_plan.lowD = nullptr;
   g_plan.Npad = Npad;
@@ -692,7 +733,9 @@ int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, do
     LKB_LAUNCH_CHECK();
     g_plan.Wt = Wt;
     double* Wtd = nullptr;
-    LKB_TRY(ws_get_t<double>(WS_Y0, (size_t)N * w, &Wtd));
+    LKB_TRY(ws_get_t<double>(WS_Y0, (size_t)N * w + 2, &Wtd));
+    g_plan.esc_total = reinterpret_cast<int*>(Wtd + (size_t)N * w);
+    LKB_CUDA_CHECK(cudaMemsetAsync(g_plan.esc_total, 0, sizeof(int), st));
     LKB_LAUNCH(blocks_for(N * w, 256), 256, st, nufft2_weights_kernel<double>)(d_t, N, grid_df, M, w, (double)beta, Wtd);
     LKB_LAUNCH_CHECK();
     g_plan.Wtd = Wtd;
@@ -805,32 +848,40 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
       LKB_LAUNCH_CHECK();
     }
     // ---- precision escalation (nufft_v2.cuh): light curves whose flux excursion dwarfs their in-band peak are
-    // transformed again in double precision; the count comes back to the host (one 4-byte copy and a stream sync)
+    // transformed again in double precision.  No host round trip: the launches are sized for `cap` light curves per
+    // round and read the device-side count (blocks stride over the listed light curves; rounds past the count exit).
     if (d_peak) {
-      LKB_LAUNCH(blocks_for(B, 256), 256, st, nufft2_flag_kernel)(d_peak, d_absmax, B, (float)N, esc_ratio, d_list, d_list + 1);
+      LKB_LAUNCH(blocks_for(B, 256), 256, st, nufft2_flag_kernel)(d_peak, d_absmax, B, (float)N, esc_ratio, d_list, d_list + 1,
+                                                                pl.esc_total);
       LKB_LAUNCH_CHECK();
-      int h_cnt = 0;
-      LKB_CUDA_CHECK(cudaMemcpyAsync(&h_cnt, d_list, sizeof(int), cudaMemcpyDeviceToHost, st));
-      LKB_CUDA_CHECK(cudaStreamSynchronize(st));
-      g_last_escalated += h_cnt;
-      const int cap = 64;
-      for (int i0 = 0; i0 < h_cnt; i0 += cap) {
-        const int n = std::min(cap, h_cnt - i0);
-        double2 *Gd = nullptr, *Td = nullptr;
-        LKB_TRY(ws_get_t<double2>(ws_alt ? WS_Y6 : WS_Y4, (size_t)n * cells, &Gd));
-        LKB_TRY(ws_get_t<double2>(ws_alt ? WS_Y7 : WS_Y5, (size_t)n * Mh, &Td));
-        const int* lst = d_list + 1 + i0;
-        LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)n), 256, st, nufft2_spread_list_kernel)(
-            pl.fge, pl.cad, pl.Wtd, d_yc, ystride, lst, w, p, ptc, pl.n1max, Gd);
+      const int cap = std::min(B, 256), gy = std::min(cap, 32);
+      const size_t lowlen = F_low > 0 ? (size_t)F_low * 4 + (size_t)cap * F_low * 2 + cap : 0;
+      double *Gbuf = nullptr;
+      double2* Td = nullptr;
+      LKB_TRY(ws_get_t<double>(ws_alt ? WS_Y6 : WS_Y4, 2 * (size_t)cap * cells + lowlen, &Gbuf));
+      LKB_TRY(ws_get_t<double2>(ws_alt ? WS_Y7 : WS_Y5, (size_t)cap * Mh, &Td));
+      double2* Gd = reinterpret_cast<double2*>(Gbuf);
+      double* accW = Gbuf + 2 * (size_t)cap * cells;
+      double* accY = accW + (size_t)F_low * 4;
+      double* accS = accY + (size_t)cap * F_low * 2;
+      const int* lst = d_list + 1;
+      for (int base = 0; base < B; base += cap) {
+        const V2Count nc = {d_list, base, cap};
+        LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)gy), 256, st, nufft2_spread_list_kernel)(
+            pl.fge, pl.cad, pl.Wtd, d_yc, ystride, lst, w, p, ptc, pl.n1max, Gd, nc);
         LKB_LAUNCH_CHECK();
-        LKB_TRY(v2_cols(Gd, Td, p, pl.n1max, n, pl.tbd, st));
+        LKB_TRY(v2_cols(Gd, Td, p, pl.n1max, gy, pl.tbd, st, nc));
         V2Finish fd = fa;
         fd.peak = nullptr;
         fd.lcmap = lst;
-        LKB_TRY(v2_rows(Td, p, n, pl.tbd, &fd, (double2*)nullptr, 0, st));
+        LKB_TRY(v2_rows(Td, p, gy, pl.tbd, &fd, (double2*)nullptr, 0, st, nc));
         if (F_low > 0) {
-          LKB_LAUNCH(dim3((unsigned)F_low, (unsigned)n), 256, st, nufft2_lowrows_exact_kernel)(
-              lst, d_t, N, d_yc, ystride, d_freq, F, normalization, (float)norm_scale, d_pow);
+          LKB_CUDA_CHECK(cudaMemsetAsync(accW, 0, sizeof(double) * lowlen, st));
+          LKB_LAUNCH(dim3((unsigned)F_low, blocks_for(N, 256 * LOWX_PER)), 256, st, nufft2_lowacc_kernel)(
+              lst, nc, d_t, N, d_yc, ystride, d_freq, (int)F_low, accW, accY, accS);
+          LKB_LAUNCH_CHECK();
+          LKB_LAUNCH(blocks_for((int64_t)cap * F_low, 256), 256, st, nufft2_lowexact_finish_kernel)(
+              lst, nc, accW, accY, accS, (int)F_low, F, N, normalization, (float)norm_scale, d_pow);
           LKB_LAUNCH_CHECK();
         }
       }
@@ -942,7 +993,6 @@ int ls_nufft_launch(const double* d_t, int64_t N, const float* d_yc, int64_t yst
                     const float* d_absmax, int B, const double* d_freq, int64_t F, double grid_f0, double grid_df,
                     float4* d_rot, float2* d_rot2, int64_t F_low, int normalization, double norm_scale, float* d_pow,
                     cudaStream_t st) {
-  g_last_escalated = 0;
   LKB_TRY(ls_nufft_prepare(d_t, N, F, grid_f0, grid_df, d_rot, d_rot2, F_low, st, d_freq, ystride));
   return ls_nufft_run(d_t, N, d_yc, ystride, d_ysumf, d_absmax, B, d_freq, F, d_rot, d_rot2, F_low, normalization,
                       norm_scale, d_pow, st, 0, true);

@@ -195,12 +195,24 @@ __device__ __forceinline__ void v2_pass_t(CT* buf, const CT* __restrict__ tw, in
   }
 }
 
+// Number of transforms a launch works on: the grid's y extent, or (escalation pass, sized before the host knows how many
+// light curves were listed) the device-side count minus `base`, at most `cap`; blocks stride over them by gridDim.y.
+struct V2Count {
+  const int* count;     // NULL: gridDim.y transforms
+  int base, cap;
+};
+__device__ __forceinline__ int v2_count(const V2Count nc, int grid_y) {
+  if (!nc.count) return grid_y;
+  const int n = *nc.count - nc.base;
+  return n < 0 ? 0 : (n > nc.cap ? nc.cap : n);
+}
+
 // ---- cols ---------------------------------------------------------------------------------------------------------
 // grid (Bc / TC, B).  G: pruned fine grids [B][c][n1 < n1max][j]; T: [B][c][k1][j]
 template <int PA, class CT = float2>
 __global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
 nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, const CT* __restrict__ tw_a,
-                   const CT* __restrict__ t_hi, const CT* __restrict__ t_lo) {
+                   const CT* __restrict__ t_hi, const CT* __restrict__ t_lo, V2Count nc) {
   LKB_DYN_SMEM(CT, buf);
   constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, LS = A + A / 16 + 1, C = V2_BC / TC;
   // one sweep of the 512 threads covers JW columns x RW rows (RW is a multiple of 16: constant skew increments)
@@ -208,9 +220,11 @@ nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, cons
   constexpr int LJW = JW == 32 ? 5 : JW == 16 ? 4 : JW == 8 ? 3 : JW == 4 ? 2 : JW == 2 ? 1 : 0;
   static_assert((1 << LJW) == JW && RW % 16 == 0, "geometry");
   const int t = (int)threadIdx.x, c = (int)blockIdx.x;
-  const int64_t lc = blockIdx.y;
   const int jl = t & (JW - 1), nl = t >> LJW;
   const int nvalid = n1max << PTC;
+  const int64_t ntr = v2_count(nc, (int)gridDim.y);
+  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {       // (one trip except in the escalation pass)
+  __syncthreads();
   const CT* Gp = G + (lc * C + c) * (int64_t)nvalid;
   const int s_base = jl * LS + v2_skew(nl), g_base = nl * TC + jl;
   // rows the first pass reads: whole input blocks (of A / R1 rows) that contain a row < n1max
@@ -236,6 +250,7 @@ nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, cons
     const unsigned q = ((unsigned)n2 * (unsigned)k1) & Mmask;       // n2 k1 < 2^22
     const CT wq = nufft::cmul(t_hi[q >> pl], t_lo[q & lmask]);
     Tp[g_base + nbk * RW * TC + cg * JW] = nufft::cmul(buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)], wq);
+  }
   }
 }
 
@@ -291,18 +306,21 @@ __device__ __forceinline__ float v2_finish_pw(double2 g1, double2 g2, const V2FT
 template <int PA, int MODE, class CT = float2>
 __global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
 nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Finish fa, CT* __restrict__ Zout,
-                   int nk2_keep) {
+                   int nk2_keep, V2Count nc) {
   LKB_DYN_SMEM(CT, buf);
   constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, R = V2_R, LS = V2_LSB, Bc = V2_BC;
   const int t = (int)threadIdx.x, g = (int)blockIdx.x;
   const bool last = g == (A / (2 * R)) - 1;
-  const int64_t lc = blockIdx.y, Mh = (int64_t)1 << (PA + V2_PB);
+  const int64_t Mh = (int64_t)1 << (PA + V2_PB);
   auto slot_k1 = [&](int s) -> int {
     const int h = s >> 3, r = s & (R - 1);
     if (h == 0) return 1 + g * R + r;
     if (last && r == 0) return 0;                    // instead of a second copy of row A / 2
     return A - (g + 1) * R + r;
   };
+  const int64_t ntr = v2_count(nc, (int)gridDim.y);
+  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {       // (one trip except in the escalation pass)
+  __syncthreads();
   const CT* Tp = T + lc * Mh;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
@@ -321,7 +339,7 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
       const int k2 = q < keep ? q : Bc - 2 * keep + q;          // [0, keep) and [Bc - keep, Bc)
       Zout[lc * Mh + k1 + ((int64_t)k2 << PA)] = buf[s * LS + v2_skew(k2)];
     }
-    return;
+    continue;
   }
   int ps = (1 - h) * R + (R - 1 - r);                              // mode Mh - k: row A - k1, column Bc - 1 - k2
   bool row0 = false;
@@ -329,7 +347,7 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
   if (last && h == 1 && r == 0) { ps = s; row0 = true; }           // row 0: column (Bc - k2) mod Bc
   int64_t nK2 = ((fa.k0 + fa.F - 1) >> PA) + 1;
   if (nK2 > Bc) nK2 = Bc;
-  const int64_t lcd = fa.lcmap ? (int64_t)fa.lcmap[lc] : lc;       // the light curve whose flux this transform holds
+  const int64_t lcd = fa.lcmap ? (int64_t)fa.lcmap[nc.base + lc] : lc;   // the light curve whose flux this transform holds
   const float ys0 = fa.ysum[lcd];
   float* prow = fa.power + lcd * fa.F;
   const int64_t jbase = (int64_t)k1 - fa.k0;
@@ -362,6 +380,7 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
     for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
     if ((t & 31) == 0 && pmax > 0.0f) atomicMax(fa.peak + lcd, __float_as_uint(pmax));
   }
+  }
 }
 
 // ---- precision escalation -------------------------------------------------------------------------------------
@@ -373,7 +392,7 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
 //     max |y - mean| > ratio * (in-band peak amplitude)
 // are listed, and the listed ones are transformed again in double precision (same kernels, double2 instantiation).
 __global__ void nufft2_flag_kernel(const unsigned* __restrict__ peak, const float* __restrict__ absmax, int B, float Nf,
-                                   float ratio, int* __restrict__ count, int* __restrict__ list) {
+                                   float ratio, int* __restrict__ count, int* __restrict__ list, int* __restrict__ total) {
   const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   bool f = false;
   if (b < B) {
@@ -383,7 +402,10 @@ __global__ void nufft2_flag_kernel(const unsigned* __restrict__ peak, const floa
   const unsigned bal = __ballot_sync(0xffffffffu, f);
   if (bal) {
     int base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(count, __popc(bal));
+    if ((threadIdx.x & 31) == 0) {
+      base = atomicAdd(count, __popc(bal));
+      if (total) atomicAdd(total, __popc(bal));
+    }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (f) list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = b;
   }
@@ -393,12 +415,15 @@ __global__ void nufft2_flag_kernel(const unsigned* __restrict__ peak, const floa
 __global__ void __launch_bounds__(256)
 nufft2_spread_list_kernel(const int32_t* __restrict__ first_ge, const nufft::Cad* __restrict__ cad,
                           const double* __restrict__ Wt, const float* __restrict__ y, int64_t ystride,
-                          const int* __restrict__ list, int w, int p, int ptc, int n1max, double2* __restrict__ G) {
+                          const int* __restrict__ list, int w, int p, int ptc, int n1max, double2* __restrict__ G,
+                          V2Count nc) {
   const int64_t cells = (int64_t)n1max << V2_PB;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cells) return;
   const int64_t M = (int64_t)1 << p, m = 2 * v2_zcell_of(e, ptc, n1max);
-  const float* yr = y + (int64_t)list[blockIdx.y] * ystride;
+  const int ntr = v2_count(nc, (int)gridDim.y);
+  for (int i = (int)blockIdx.y; i < ntr; i += (int)gridDim.y) {
+  const float* yr = y + (int64_t)list[nc.base + i] * ystride;
   double a0 = 0.0, a1 = 0.0;
   const int64_t L = nufft::table_len(M, w);
   for (int wrap = 0; wrap < 2; ++wrap) {
@@ -417,7 +442,8 @@ nufft2_spread_list_kernel(const int32_t* __restrict__ first_ge, const nufft::Cad
       a1 = fma(w1, v, a1);
     }
   }
-  G[(int64_t)blockIdx.y * cells + e] = make_double2(a0, a1);
+  G[(int64_t)i * cells + e] = make_double2(a0, a1);
+  }
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------------------------
@@ -453,23 +479,24 @@ inline int v2_n1max(int p, int64_t i0_last, int w) {
 inline bool v2_supported(int p) { return p >= V2R_P_MIN && p <= V2R_P_MAX; }
 
 template <int PA, class CT>
-int v2_cols_pa(const CT* G, CT* T, int n1max, int B, const V2TablesT<CT>& tb, cudaStream_t st) {
+int v2_cols_pa(const CT* G, CT* T, int n1max, int B, const V2TablesT<CT>& tb, cudaStream_t st, V2Count nc) {
   constexpr int A = 1 << PA, TC = V2_TILE / A;
   const size_t smem = (size_t)TC * (A + A / 16 + 1) * sizeof(CT);
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_kernel<PA, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LKB_LAUNCH_SMEM(dim3((unsigned)(V2_BC / TC), (unsigned)B), V2_THREADS, smem, st, nufft2_cols_kernel<PA, CT>)(
-      G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo);
+      G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo, nc);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
 template <int PA, class CT>
-int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep, cudaStream_t st) {
+int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep, cudaStream_t st,
+               V2Count nc) {
   const size_t smem = (size_t)(2 * V2_R) * V2_LSB * sizeof(CT);
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 1, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 2, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
-  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
-  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0, nc);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep, nc);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
@@ -482,16 +509,17 @@ int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, 
   }
 // G -> T for B transforms of 2^p real cells
 template <class CT>
-inline int v2_cols(const CT* G, CT* T, int p, int n1max, int B, const V2TablesT<CT>& tb, cudaStream_t st) {
-#define V2_CALL(PA) v2_cols_pa<PA, CT>(G, T, n1max, B, tb, st)
+inline int v2_cols(const CT* G, CT* T, int p, int n1max, int B, const V2TablesT<CT>& tb, cudaStream_t st,
+                   V2Count nc = V2Count{nullptr, 0, 0}) {
+#define V2_CALL(PA) v2_cols_pa<PA, CT>(G, T, n1max, B, tb, st, nc)
   V2_DISPATCH_PA(p - 1 - V2_PB, V2_CALL)
 #undef V2_CALL
 }
 // T -> power (fa != NULL) or -> Zout in natural order, modes k < nk2_keep * A and their mirrors
 template <class CT>
 inline int v2_rows(const CT* T, int p, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep,
-                   cudaStream_t st) {
-#define V2_CALL(PA) v2_rows_pa<PA, CT>(T, B, tb, fa, Zout, nk2_keep, st)
+                   cudaStream_t st, V2Count nc = V2Count{nullptr, 0, 0}) {
+#define V2_CALL(PA) v2_rows_pa<PA, CT>(T, B, tb, fa, Zout, nk2_keep, st, nc)
   V2_DISPATCH_PA(p - 1 - V2_PB, V2_CALL)
 #undef V2_CALL
 }

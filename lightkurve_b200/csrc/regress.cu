@@ -320,7 +320,8 @@ rg_gram_mma_kernel(const double* __restrict__ X, int x_batched, const double* __
 // write w + d (the matrix may be approximate, e.g. the tcgen05 Gram; grad is the exact fp64 gradient of the fit)
 __global__ void __launch_bounds__(256)
 rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __restrict__ prior_sigma, RgWs ws,
-                double* __restrict__ coeff, int32_t* __restrict__ status, const double* __restrict__ grad) {
+                double* __restrict__ coeff, int32_t* __restrict__ status, const double* __restrict__ grad,
+                double* __restrict__ lu_out, int32_t* __restrict__ piv_out) {
   extern __shared__ __align__(16) double s_m[];        // [K][K+1] augmented
   __shared__ double s_red[8];
   __shared__ int s_redi[8];
@@ -370,6 +371,7 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
     __syncthreads();
     const int piv = s_piv;
     if (piv < 0) { singular = true; break; }
+    if (piv_out && threadIdx.x == 0) piv_out[(int64_t)b * K + c] = piv;
     if (piv != c) {
       for (int k = threadIdx.x; k < Ka; k += blockDim.x) {
         const double tmp = s_m[c * Ka + k];
@@ -384,7 +386,7 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
       __syncwarp();
       for (int k = c + 1 + lane; k < Ka; k += 32) s_m[r * Ka + k] = fma(-fct, s_m[c * Ka + k], s_m[r * Ka + k]);
       __syncwarp();
-      if (lane == 0) s_m[r * Ka + c] = 0.0;
+      if (lane == 0) s_m[r * Ka + c] = fct;          // the multiplier stays in place: s_m = [L \\ U | rhs]
     }
     __syncthreads();
   }
@@ -393,6 +395,8 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
     if (threadIdx.x == 0 && status) status[b] = LKB_E_SINGULAR;
     return;
   }
+  if (lu_out)                                          // factors for rg_resolve_kernel (same matrix, another rhs)
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) lu_out[(int64_t)b * K * K + e] = s_m[(e / K) * Ka + (e % K)];
   // back substitution (warp 0)
   if (warp == 0) {
     for (int c = K - 1; c >= 0; --c) {
@@ -407,6 +411,57 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
   for (int k = threadIdx.x; k < K; k += blockDim.x)
     coeff[(int64_t)b * K + k] = grad ? coeff[(int64_t)b * K + k] + s_m[k * Ka + K] : s_m[k * Ka + K];
   if (threadIdx.x == 0 && status) status[b] = LKB_OK;
+}
+
+// Iterative-refinement step with the factors rg_solve_kernel left behind (P (A + prior) = L U, pivots piv):
+// d = (A + prior)^-1 [grad - prior (w - mu)], w <- w + d.  Two triangular solves instead of a second elimination
+// (the elimination is ~150 dependent block steps per light curve; the substitutions are one warp's dot products).
+__global__ void __launch_bounds__(256)
+rg_resolve_kernel(int K, const double* __restrict__ prior_mu, const double* __restrict__ prior_sigma,
+                  const double* __restrict__ lu, const int32_t* __restrict__ piv, double* __restrict__ coeff,
+                  const int32_t* __restrict__ status, const double* __restrict__ grad) {
+  extern __shared__ __align__(16) double s_m[];        // [K][K] factors, then the right-hand side [K]
+  const int b = blockIdx.x;
+  if (status && status[b] != LKB_OK) return;           // singular system: the coefficients are already NaN
+  double* s_r = s_m + (size_t)K * K;
+  const double* LU = lu + (int64_t)b * K * K;
+  for (int e = threadIdx.x; e < K * K; e += blockDim.x) s_m[e] = LU[e];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    double v = grad[(int64_t)b * K + i];
+    if (prior_sigma) {
+      const double ps = prior_sigma[i];
+      v += (prior_mu[i] - coeff[(int64_t)b * K + i]) / (ps * ps);
+    }
+    s_r[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) {                                   // the row interchanges, in elimination order
+      const int32_t* pv = piv + (int64_t)b * K;
+      for (int c = 0; c < K; ++c) {
+        const int p = pv[c];
+        if (p != c) { const double tmp = s_r[c]; s_r[c] = s_r[p]; s_r[p] = tmp; }
+      }
+    }
+    __syncwarp();
+    for (int c = 1; c < K; ++c) {                      // L y = P rhs (unit diagonal)
+      double part = 0.0;
+      for (int k = lane; k < c; k += 32) part = fma(s_m[c * K + k], s_r[k], part);
+      part = warp_sum(part);
+      if (lane == 0) s_r[c] -= part;
+      __syncwarp();
+    }
+    for (int c = K - 1; c >= 0; --c) {                 // U d = y
+      double part = 0.0;
+      for (int k = c + 1 + lane; k < K; k += 32) part = fma(s_m[c * K + k], s_r[k], part);
+      part = warp_sum(part);
+      if (lane == 0) s_r[c] = (s_r[c] - part) / s_m[c * K + c];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) coeff[(int64_t)b * K + k] += s_r[k];
 }
 
 // ---- (A + prior)^-1 for propagate_errors (np.linalg.inv at regressioncorrector.py:185) -----------
@@ -695,6 +750,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
   static size_t solve_attr = 0;
   if (solve_smem > solve_attr) {
     LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     solve_attr = solve_smem;
   }
   static bool accum_attr = false;
@@ -761,7 +817,13 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
                                                                            it == 0 ? 1.0 : -1.0, ws);
     if (it == 0) prof_end(st);
     LKB_LAUNCH_CHECK();
-    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, nullptr);
+    double* d_lu = nullptr;
+    int32_t* d_piv = nullptr;
+    if (use_tc && gemm_model) {                        // the refinement step below reuses the factors
+      LKB_TRY(ws_get_t<double>(WS_Y0, (size_t)B * K * K, &d_lu));
+      LKB_TRY(ws_get_t<int32_t>(WS_Y1, (size_t)B * K, &d_piv));
+    }
+    rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, nullptr, d_lu, d_piv);
     LKB_LAUNCH_CHECK();
     if (gemm_model) {
       rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
@@ -775,7 +837,10 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
       double* d_grad = nullptr;
       LKB_TRY(ws_get_t<double>(WS_X6, (size_t)B * K, &d_grad));
       LKB_TRY(regress_tc_gradient(d_X, d_y, d_fe, ws.used, ws.resid, B, N, K, d_grad, st));
-      rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, d_grad);
+      if (getenv("LKB_REGRESS_REFACTOR"))            // (A/B: eliminate again instead of reusing the factors)
+        rg_solve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, ws, o_c, d_status, d_grad, nullptr, nullptr);
+      else
+        rg_resolve_kernel<<<B, 256, solve_smem, st>>>(K, d_pm, d_ps, d_lu, d_piv, o_c, d_status, d_grad);
       LKB_LAUNCH_CHECK();
       rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
       LKB_LAUNCH_CHECK();

