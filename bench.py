@@ -638,11 +638,14 @@ def secondary_regress(engine, torch, dist, rank, world, dev, cpu_baseline=True, 
     launches = engine.launch_count() - l0
     kms = engine.profile_read()
     engine.profile_enable(False)
-    k_ms, e2e_ms = _max_over_ranks(torch, dist, world, dev, [float(np.sum(kms)), 1e3 * wall])
+    # the library records two intervals per call: the first Gram pass (the roofline kernel) and everything after it
+    k_ms, dev_ms, e2e_ms = _max_over_ranks(torch, dist, world, dev, [float(kms[0]) if len(kms) else 0.0,
+                                                                     float(np.sum(kms)), 1e3 * wall])
     pk = _peaks()
     flops = float(B) * N * K * K                      # symmetric half of X^T W X, once (later iterations downdate)
-    out = {"metric": "regression_light_curves_per_s", "unit": "LC/s", "value": B * world / (e2e_ms * 1e-3),
-           "ms_per_step": e2e_ms, "steps": 1, "n_gpus": world, "scaling": "weak", "dtype": "f64 (DMMA Gram, LU)",
+    out = {"metric": "regression_light_curves_per_s", "unit": "LC/s", "value": B * world / (dev_ms * 1e-3),
+           "ms_per_step": dev_ms, "steps": 1, "n_gpus": world, "scaling": "weak",
+           "dtype": "split-f16 tcgen05 Gram + f64 refinement (DMMA right-hand sides, LU)",
            "config": {"workload": "c4b: RegressionCorrector.correct(sigma=5, niters=5), %d LC x %d cadences, shared "
                                   "design matrix K = %d, per-cadence flux_err" % (B, N, K)},
            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "LC/s", "ms_per_step": e2e_ms,
@@ -650,12 +653,17 @@ def secondary_regress(engine, torch, dist, rank, world, dev, cpu_baseline=True, 
                    "d2h_bytes_per_step": int(8 * B * (N + K) + B * N) * world},
            "gpu_launches": int(launches),
            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / (k_ms * 1e-3) / 1e12,
-                        "peak": 37.1, "frac": flops / (k_ms * 1e-3) / 1e12 / 37.1, "traffic": None, "kernel_ms": k_ms,
-                        "kernel": "rg_gram_mma (Gram matrices on the FP64 tensor cores)",
-                        "peak_source": "FP64 DMMA peak measured on this pool with tools/fp64_peak.cu (37.1 TFLOP/s); the "
-                                       "bf16 figure of MEASURED_PEAKS.json (%.0f) is SURVEY 8(d)'s bound for a "
-                                       "reduced-precision Gram" % float(pk.get("bf16_tflops_sustained", 1370.0)),
-                        "note": "algorithmic flops N*K^2 per light curve (first iteration; later ones downdate)"}}
+                        "peak": float(pk.get("bf16_tflops_sustained", 1370.0)),
+                        "frac": flops / (k_ms * 1e-3) / 1e12 / float(pk.get("bf16_tflops_sustained", 1370.0)),
+                        "traffic": None, "kernel_ms": k_ms,
+                        "kernel": "regress_tc_gram: rt_gram_kernel (tcgen05, split-f16 operands, f32 TMEM accumulators) + "
+                                  "operand preparation + the DMMA right-hand side",
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor-core rate; the "
+                                        "kernel issues 3 f16 MMAs per algorithmic product: hi*hi, hi*lo, lo*hi)")
+                                       if pk else "fallback 1370 TF/s (B200_PROFILING.md)",
+                        "note": "algorithmic flops N*K^2 per light curve (symmetric half of X^T W X, first iteration; "
+                                "later iterations downdate the clipped rows on the FP64 tensor cores); round 1's FP64 DMMA "
+                                "Gram ran at 16 TF/s of a measured 37.1 TF/s FP64 peak"}}
     if rank == 0 and cpu_baseline:
         from oracle import detrend as odet
         n_lc, t0 = 0, time.perf_counter()

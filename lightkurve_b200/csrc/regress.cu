@@ -815,7 +815,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     } else
       rg_accum_kernel<<<dim3(nupper, B), 128, 2 * sizeof(RgStage), st>>>(d_X, x_batched, d_y, d_fe, N, K, nblk,
                                                                            it == 0 ? 1.0 : -1.0, ws);
-    if (it == 0) prof_end(st);
+    if (it == 0) { prof_end(st); prof_begin(st); }     // second record: everything after the first Gram pass
     LKB_LAUNCH_CHECK();
     double* d_lu = nullptr;
     int32_t* d_piv = nullptr;
@@ -864,6 +864,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     LKB_LAUNCH_CHECK();
   }
 
+  if (niters > 0) prof_end(st);
   LKB_TRY(stage_out_copy<double>(mem, coeff, o_c, (size_t)B * K, st));
   LKB_TRY(stage_out_copy<double>(mem, model, o_m, BN, st));
   LKB_TRY(stage_out_copy<uint8_t>(mem, outlier_mask, o_om, BN, st));

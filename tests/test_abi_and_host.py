@@ -290,6 +290,7 @@ def test_diagnostic_workspace_readback_needs_an_initialised_engine():
     validates its arguments; the slot names of the Python wrapper follow enum Slot of csrc/common.cuh."""
     from lightkurve_b200 import engine
     assert engine.WS_SLOTS["A"] == 0 and engine.WS_SLOTS["P"] == 15 and engine.WS_SLOTS["IN0"] == 16
-    assert engine.WS_SLOTS["OUT0"] == 24 and len(engine.WS_SLOTS) == 32
+    assert engine.WS_SLOTS["OUT0"] == 24 and engine.WS_SLOTS["X0"] == 32 and engine.WS_SLOTS["Y7"] == 47
+    assert len(engine.WS_SLOTS) == 48
     with pytest.raises(ValueError, match="not initialised"):
         engine.ws_read("A", 4, np.float32)
