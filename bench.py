@@ -523,13 +523,20 @@ def _ragged_cpu_leg(times, fluxes, freq, n_lc=48, budget_s=12.0):
                       "1 process; equivalent bin*cadence/s = F*sum(N)/time" % (done, secs)}
 
 
+def _nufft_fine_log2(kmax_plus_1):
+    """log2 of the NUFFT fine grid (ls_nufft.cu: fine_log2): the smallest power of two with an upsampling factor of at
+    least LKB_NUFFT_SIGMA (default 2) over the highest mode."""
+    smin = min(2.0, max(1.25, float(os.environ.get("LKB_NUFFT_SIGMA", "2"))))
+    return max(4, int(np.ceil(np.log2(2.0 * smin * kmax_plus_1))))
+
+
 def _ragged_roofline(F, units, k_ms, family, n_local, clocks_mhz=None):
     """K1's bounds: the direct kernel is issue/MUFU-bound (2.3e12 units/s at 1965 MHz); the
     NUFFT family is an HBM/L2 sweep of the fine grids."""
     pk = _peaks()
     hbm = float(pk.get("hbm_gbs", 6589.3))
     if family == "nufft":
-        p = int(np.ceil(np.log2(4.0 * (1 + F))))
+        p = _nufft_fine_log2(1 + F)
         M, M2 = 2 ** p, 2 ** (p + 1)
         npairs = (n_local + 1) // 2
         # per pair: flux grid T written + read, pruned modes written + read (<= M / 2), the same on the 2x finer grid
@@ -698,7 +705,7 @@ def run_c5(args, engine, torch, dist, rank, world, local_rank, dev):
     if sampler:
         sampler.start()
     st = c5_step_stats(engine, torch, dist, rank, world, dev, times, fluxes, freq, args.steps, args.warmup,
-                       chunks=args.chunks)
+                       chunks=args.chunks if args.chunks > 0 else 4)
     clocks = sampler.stop() if sampler else None
     units = float(F) * float(sum(len(t) for t in times))
     if rank != 0:
@@ -808,7 +815,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary legs (BLS, flatten, regression, ragged LS)")
     ap.add_argument("--legs", default="bls,flatten,regress,ls_ragged", help="comma list of secondary legs to run")
-    ap.add_argument("--chunks", type=int, default=4, help="c5: pieces per rank (one asynchronous all-gather each)")
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="N > 1: pieces per rank, one asynchronous all-gather each (0 = by rank count: c2 1 / 2 / 4 pieces at "
+                         "<= 2 / <= 4 / more ranks, c5 4)")
     ap.add_argument("--nufft-leg", action="store_true", help=argparse.SUPPRESS)      # internal: child of secondary.ls_nufft
     ap.add_argument("--nufft-variants", action="store_true",
                     help="also time the NUFFT path's transform variants in a child process (secondary.ls_nufft)")
@@ -856,7 +865,8 @@ def main():
     # N > 1: the rank's batch goes through the library in `pieces` calls on the same grid (the y-independent tables are
     # built once and found cached by the later calls) and every piece's power rows are handed to an ASYNCHRONOUS
     # all-gather while the next piece is computed; the gathered array is piece-major: [piece][rank][B / pieces, F]
-    pieces = max(1, min(args.chunks, B // 64)) if world > 1 else 1
+    auto_pieces = 1 if world <= 2 else (2 if world <= 4 else 4)   # the all-gather volume per rank grows with world - 1
+    pieces = max(1, min(args.chunks if args.chunks > 0 else auto_pieces, B // 64)) if world > 1 else 1
     pb_rows = B // pieces
     assert pb_rows * pieces == B
     s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
@@ -993,7 +1003,7 @@ def main():
             # v2 transform (nufft_v2.cuh): per light curve the centred flux is read by the spreading, the pruned fine
             # grid G (n1max rows of 512 complex cells) and the column transforms T (M / 2 complex points) are written
             # once and read once, the power row is written once (DESIGN.md K2n byte model; tables are L2-resident)
-            pfine = int(np.ceil(np.log2(4.0 * (1 + F))))
+            pfine = _nufft_fine_log2(1 + F)
             Mh = 2 ** (pfine - 1)
             reach = freq[0] * (t[-1] - t[0]) * 2 ** pfine + 16
             n1max = int(np.ceil(np.ceil(reach / 2) / 512))
@@ -1010,7 +1020,7 @@ def main():
             # HBM sweep: fine grids [B/2, M] complex64 written once by the spreading, read + written by every Stockham
             # pass, two modes per output read by the finish kernel; flux read once, power written once
             # (DESIGN.md K2n).  k0 = 1 on the bench grid (f0 = df).
-            pfine = int(np.ceil(np.log2(4.0 * (1 + F))))
+            pfine = _nufft_fine_log2(1 + F)
             npass = (pfine + 3) // 4
             npairs = (B + 1) // 2
             nbytes = npairs * (2 ** pfine) * 8.0 * (1 + 2 * npass) + npairs * 16.0 * F + 4.0 * B * N + 4.0 * B * F

@@ -37,8 +37,9 @@ using nufft::Cad;
 
 namespace {
 
+constexpr int GL_NQ = 48;
 struct GlNodes {
-  double x[32], w[32];
+  double x[GL_NQ], w[GL_NQ];
 };
 
 __global__ void nufft_cad_kernel(const double* __restrict__ t, int64_t N, double df, int64_t M, int w,
@@ -201,7 +202,7 @@ __global__ void nufft_deconv_kernel(int64_t k_first, int64_t count, int64_t M, i
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
   double re, im;
-  nufft::deconv_factor(k_first + k, M, w, beta, gl.x, gl.w, 32, &re, &im);
+  nufft::deconv_factor(k_first + k, M, w, beta, gl.x, gl.w, GL_NQ, &re, &im);
   dec[k] = make_float2((float)re, (float)im);
 }
 
@@ -336,7 +337,7 @@ __global__ void nufft2_ftab_kernel(const float4* __restrict__ rot, const float2*
   if (k >= F) return;
   const int64_t kk = k0 + k;
   double dre, dim;
-  nufft::deconv_factor(kk, M, w, beta, gl.x, gl.w, 32, &dre, &dim);
+  nufft::deconv_factor(kk, M, w, beta, gl.x, gl.w, GL_NQ, &dre, &dim);
   const float4 r = rot[k];
   const float2 r2 = rot2[k];
   const double ct = (double)r.x, st = (double)r.y;
@@ -608,15 +609,27 @@ int fft_fourstep(float2* Z, int p, int npairs, cudaStream_t st, int* pa_out, con
                                : fft_fourstep_t<false>(Z, p, npairs, st, pa_out, sp);
 }
 
-// 10 cells: with 8 the aliasing images of a strong line ABOVE the frequency grid (a near-regular cadence repeats the
-// spectrum every 1 / dt) came back into the band at 2.5e-8 of its amplitude - 1.5x the tolerance on light curves whose
-// in-band spectrum is 1000x below their variability; 10 cells put it at 3e-10 and cost nothing measurable (the spread
-// kernel is 15 % of the step).  tools/worst_bins.py, DESIGN.md section 2.
-int kernel_width() {
-  int w = 10;
+// Fine-grid size and kernel: upsampling factor >= 2, "exponential of semicircle" kernel of 10 cells, beta = 2.30 w.
+//  * Width 8 (round 2's first half) let the aliasing images of a strong line ABOVE the frequency grid (a near-regular
+//    cadence repeats the spectrum every 1 / dt) back into the band at 2.5e-8 of its amplitude - 1.5x the tolerance on
+//    light curves whose in-band spectrum is 1000x below their variability; width 10 puts it at 3e-10
+//    (tools/worst_bins.py).
+//  * A smaller grid with a wider kernel (upsampling 1.25 .. 2: config 2 would transform 2^18 instead of 2^19 cells
+//    with a 14-cell kernel, FP64 model error 2e-12) was tried because the transform is 70 % of the step: in FP32 it is
+//    NOT usable here - the deconvolution 1 / phihat(k) grows steeply towards the band edge at low upsampling and
+//    amplifies the grid's rounding noise 10x (emulated config-2 light curve: rms error 0.14 of the tolerance instead
+//    of 0.015, worst bin 3.3x instead of 1.08x).  LKB_NUFFT_SIGMA=1.25 selects it for experiments; the default is 2.
+double upsampling_min() {
+  double s = 2.0;
+  if (const char* e = getenv("LKB_NUFFT_SIGMA")) s = atof(e);
+  return s < 1.25 ? 1.25 : (s > 2.0 ? 2.0 : s);
+}
+int fine_log2(int64_t kmax_plus_1) { return nufft::fine_grid_log2(kmax_plus_1, upsampling_min()); }
+int kernel_width(double sigma) {
+  int w = nufft::es_width(sigma);
   if (const char* e = getenv("LKB_NUFFT_W")) w = atoi(e);
   if (w < 4) w = 4;
-  if (w > 12) w = 12;
+  if (w > 16) w = 16;
   return w & ~1;                                  // even widths only
 }
 
@@ -635,7 +648,7 @@ bool ls_nufft_supported(int64_t F, bool regular, double grid_f0, double grid_df,
   if (fabs(q - k0) > 1e-9 * fmax(1.0, q) || k0 > 1.0e7) return false;
   if (!(grid_df * t_last <= 1.0 + 1e-9)) return false;      // oversample 1: df * baseline = 1 up to rounding
   const int64_t kmax = (int64_t)k0 + F;
-  return nufft::fine_grid_log2(2 * kmax) <= 24;
+  return fine_log2(2 * kmax) <= 24;
 }
 
 // ---- shared-grid path in two steps: ls_nufft_prepare (tables + window terms, once per call) and ls_nufft_run (spread
@@ -677,13 +690,14 @@ int ls_nufft_last_escalated() {
 // ls_window_kernel (fp64 path); the rows >= F_low are filled here from one transform of unit strengths.
 int ls_nufft_prepare(const double* d_t, int64_t N, int64_t F, double grid_f0, double grid_df, float4* d_rot,
                      float2* d_rot2, int64_t F_low, cudaStream_t st, const double* d_freq, int64_t Npad) {
-  const int w = kernel_width();
-  const float beta = 2.30f * (float)w;
   const int64_t k0 = (int64_t)rint(grid_f0 / grid_df);
-  const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
+  const int p = fine_log2(k0 + F), p2 = fine_log2(2 * (k0 + F));
+  const double sigma = fmin(2.0, nufft::grid_sigma(p, k0 + F));   // (the validated rule: beta = 2.30 w from sigma = 2 on)
+  const int w = kernel_width(sigma);
+  const float beta = (float)nufft::es_beta(w, sigma);
   const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
   GlNodes gl;
-  nufft::gauss_legendre(32, gl.x, gl.w);
+  nufft::gauss_legendre(GL_NQ, gl.x, gl.w);
 
   Cad *cad = nullptr, *cad2 = nullptr;
   int32_t *fge = nullptr, *fge2 = nullptr;
@@ -1206,7 +1220,7 @@ int ls_nufft_ragged_v2(const double* d_t, const float* d_y, const int64_t* d_off
   int group = (int)fmax(1.0, floor(cap_mb / per_lc_mb));
   if (group > B) group = B;
   GlNodes gl;
-  nufft::gauss_legendre(32, gl.x, gl.w);
+  nufft::gauss_legendre(GL_NQ, gl.x, gl.w);
   V2Tables tb, tb2;
   LKB_TRY(v2_tables(p, WS_IN7, st, &tb));
   LKB_TRY(v2_tables(p2, WS_OUT1, st, &tb2));
@@ -1299,7 +1313,7 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
     return LKB_E_UNSUPPORTED;
   }
   const int64_t k0 = (int64_t)k0d;
-  const int p = nufft::fine_grid_log2(k0 + F), p2 = nufft::fine_grid_log2(2 * (k0 + F));
+  const int p = fine_log2(k0 + F), p2 = fine_log2(2 * (k0 + F));
   if (p2 > 24) { set_error("NUFFT (ragged): fine grid larger than 2^24 cells"); return LKB_E_UNSUPPORTED; }
   for (int b = 0; b < B; ++b) {
     if (!(h_span[b] > 0.0) || !(df * h_span[b] <= 1.0 + 1e-9)) {
@@ -1307,8 +1321,9 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
       return LKB_E_UNSUPPORTED;
     }
   }
-  const int w = kernel_width();
-  const float beta = 2.30f * (float)w;
+  const double sigma = fmin(2.0, nufft::grid_sigma(p, k0 + F));   // (the validated rule: beta = 2.30 w from sigma = 2 on)
+  const int w = kernel_width(sigma);
+  const float beta = (float)nufft::es_beta(w, sigma);
   const int64_t M = (int64_t)1 << p, M2 = (int64_t)1 << p2;
   const int npairs_all = (B + 1) / 2;
   double cap_mb = 16384.0;
@@ -1317,7 +1332,7 @@ int ls_nufft_ragged_launch(const double* d_t, const float* d_y, const int64_t* d
   int group = (int)fmax(1.0, floor(cap_mb / per_pair_mb));
   if (group > npairs_all) group = npairs_all;
   GlNodes gl;
-  nufft::gauss_legendre(32, gl.x, gl.w);
+  nufft::gauss_legendre(GL_NQ, gl.x, gl.w);
 
   // v2 (one real transform per light curve, nufft_v2.cuh) when both fine grids are in range
   if (fft_mode(p) == 3 && fft_mode(p2) == 3)

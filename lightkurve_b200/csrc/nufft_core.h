@@ -44,11 +44,26 @@ struct Cad {          // per cadence: leftmost fine-grid cell of its kernel supp
 LKB_HD int grid_shift(int w) { return (w + 1) / 2 + 1; }            // keeps every i0 >= 1
 LKB_HD int64_t table_len(int64_t M, int w) { return M + 2 * (int64_t)w + 4; }   // entries of first_ge
 
-// fine-grid size: power of two >= 4 * (highest mode index + 1)
-LKB_HD int fine_grid_log2(int64_t kmax_plus_1) {
+// fine-grid size: power of two >= 2 sigma_min (highest mode index + 1); sigma_min = 2 is the classical upsampling
+// factor, 1.25 the low-upsampling choice (smaller transform, wider kernel - es_width / es_beta below)
+LKB_HD int fine_grid_log2(int64_t kmax_plus_1, double sigma_min = 2.0) {
   int p = 4;
-  while (((int64_t)1 << p) < 4 * kmax_plus_1) ++p;
+  while ((double)((int64_t)1 << p) < 2.0 * sigma_min * (double)kmax_plus_1) ++p;
   return p;
+}
+// upsampling factor a grid of 2^p cells actually gives for modes up to kmax (capped: nothing is gained past 4)
+LKB_HD double grid_sigma(int p, int64_t kmax_plus_1) {
+  const double s = (double)((int64_t)1 << p) / (2.0 * (double)kmax_plus_1);
+  return s > 4.0 ? 4.0 : s;
+}
+// "exponential of semicircle" kernel phi(z) = exp(beta (sqrt(1 - z^2) - 1)) at upsampling factor sigma (Barnett,
+// Magland & af Klinteberg 2019, the finufft parameter rule): beta = 0.976 pi (1 - 1 / (2 sigma)) w  (2.30 w at
+// sigma = 2), and the even width that puts the aliasing error near 1e-9 of sum |y|.
+LKB_HD double es_beta(int w, double sigma) { return 0.976 * 3.14159265358979323846 * (1.0 - 0.5 / sigma) * (double)w; }
+LKB_HD int es_width(double sigma) {
+  int w = (int)ceil(20.7 / (3.14159265358979323846 * sqrt(1.0 - 1.0 / sigma)));
+  w += w & 1;
+  return w < 10 ? 10 : (w > 16 ? 16 : w);
 }
 
 LKB_HD Cad cad_entry(double t_rel, double df, int64_t M, int w) {
@@ -338,7 +353,7 @@ LKB_HD void gauss_legendre(int n, double* x, double* w) {
 
 // Fourier coefficient of the kernel at mode kk on an M-cell grid, times the grid-shift phase, INVERTED:
 // the factor the raw transform value of mode kk is multiplied with.  glx/glw: Gauss-Legendre nodes/weights on
-// [-1, 1] (nq of them; 32 are ample for w <= 12).
+// [-1, 1] (nq of them; 48 are ample for w <= 16).
 LKB_HD void deconv_factor(int64_t kk, int64_t M, int w, double beta, const double* glx, const double* glw, int nq,
                           double* re, double* im) {
   const double half = 0.5 * (double)w;                         // kernel half-width in cells
