@@ -16,6 +16,20 @@ fi
 echo "=== c2, N = $N: weak scaling, pipelined all-gathers ==="
 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-secondary --no-cpu-baseline > $O/bench_c2_n$N.json 2> $O/bench_c2_n$N.err; echo "rc=$?"
 tail -c 1800 $O/bench_c2_n$N.json; tail -3 $O/bench_c2_n$N.err
+if [ "$MODE" = "pieces" ]; then
+for c in 1 2; do
+echo "=== c2, N = $N: --chunks $c ==="
+timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-secondary --no-cpu-baseline --chunks $c > $O/bench_c2_n${N}_chunks$c.json 2> $O/bench_c2_n${N}_chunks$c.err; echo "rc=$?"
+python - $O/bench_c2_n${N}_chunks$c.json <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open(sys.argv[1]).read().strip().splitlines() if l.startswith("{")][-1])
+    print("ms/step %.3f value %.4g e2e ms %.3f" % (d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"]))
+except Exception as e:
+    print("no line", e)
+PY
+done
+fi
 if [ "$MODE" = "full" ]; then
 echo "=== c2, N = $N: one monolithic all-gather after the kernels (--chunks 1) ==="
 timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-secondary --no-cpu-baseline --chunks 1 > $O/bench_c2_n${N}_mono.json 2> $O/bench_c2_n${N}_mono.err; echo "rc=$?"

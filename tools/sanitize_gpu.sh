@@ -16,7 +16,10 @@ from lightkurve_b200 import engine
 engine.init(0)
 rng = np.random.default_rng(3)
 N, B, F = 3000, 9, 3600
-t = 100.0 + 0.02 * np.sort(rng.choice(3300, N, replace=False))       # a regular cadence with 9 % of it missing
+keep = np.ones(3300, bool)
+for c in (200, 700, 1300, 1900, 2500, 3000):
+    keep[c:c + 50] = False                                   # a regular cadence with six gaps
+t = 100.0 + 0.02 * np.flatnonzero(keep)
 freq = (1 + np.arange(F)) / (5.0 * (t[-1] - t[0]))
 Y = (1 + 1e-3 * np.sin(2 * np.pi * 1.1 * t)[None, :] + 3e-4 * rng.normal(size=(B, N))).astype(np.float32)
 Y[0] = (1 + 1e-2 * np.sin(2 * np.pi * 18.3 * t) + 1e-5 * rng.normal(size=N)).astype(np.float32)   # loud line above the grid
