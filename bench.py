@@ -95,7 +95,7 @@ def make_workload(name, seed):
 class ClockSampler:
     """SM clock / throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, device_index, period_s=0.05):
+    def __init__(self, device_index, period_s=0.005):
         self.dev = device_index
         self.period = period_s
         self.sm, self.reasons, self.power = [], set(), []
@@ -805,7 +805,7 @@ def nufft_leg(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -1010,7 +1010,12 @@ def main():
             nbytes = B * (4.0 * N + 2 * 8.0 * n1max * 512 + 2 * 8.0 * Mh + 4.0 * F)
             hbm = float(peaks.get("hbm_gbs", 6589.3))
             roofline = {"bound": "hbm", "achieved": nbytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                        "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                        "frac": nbytes / (k_ms * 1e-3) / 1e9 / hbm,
+                        # DRAM bytes of the four batch kernels of one step at this exact shape, from the committed ncu
+                        # capture (spread 0.66 + cols 2.52 + rows 2.55 + low rows 0.28 GB): 1.03x the algorithmic bytes
+                        "traffic": 6.003e9 if (B, N, F) == (1024, 65000, 100000) else None,
+                        "traffic_source": "static: ncu --set full dram__bytes_read+write per launch, "
+                                          "profiles/r02_nufft_v2_realmode_b.json (not re-measured in this run)",
                         "kernel": "nufft2_spread + nufft2_cols + nufft2_rows(finish) + nufft2_lowrows", "kernel_ms": k_ms,
                         "bytes_per_launch": nbytes,
                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",

@@ -209,11 +209,11 @@ __device__ __forceinline__ int v2_count(const V2Count nc, int grid_y) {
 
 // ---- cols ---------------------------------------------------------------------------------------------------------
 // grid (Bc / TC, B).  G: pruned fine grids [B][c][n1 < n1max][j]; T: [B][c][k1][j]
-template <int PA, class CT = float2>
-__global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
-nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, const CT* __restrict__ tw_a,
-                   const CT* __restrict__ t_hi, const CT* __restrict__ t_lo, V2Count nc) {
-  LKB_DYN_SMEM(CT, buf);
+// one transform (light curve slot lc): all threads of the CTA
+template <int PA, class CT>
+__device__ __forceinline__ void v2_cols_one(CT* buf, const CT* __restrict__ G, CT* __restrict__ T, int n1max,
+                                            const CT* __restrict__ tw_a, const CT* __restrict__ t_hi,
+                                            const CT* __restrict__ t_lo, const int64_t lc) {
   constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, LS = A + A / 16 + 1, C = V2_BC / TC;
   // one sweep of the 512 threads covers JW columns x RW rows (RW is a multiple of 16: constant skew increments)
   constexpr int JW = TC < 32 ? TC : 32, RW = V2_THREADS / JW, CG = TC / JW;
@@ -222,9 +222,6 @@ nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, cons
   const int t = (int)threadIdx.x, c = (int)blockIdx.x;
   const int jl = t & (JW - 1), nl = t >> LJW;
   const int nvalid = n1max << PTC;
-  const int64_t ntr = v2_count(nc, (int)gridDim.y);
-  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {       // (one trip except in the escalation pass)
-  __syncthreads();
   const CT* Gp = G + (lc * C + c) * (int64_t)nvalid;
   const int s_base = jl * LS + v2_skew(nl), g_base = nl * TC + jl;
   // rows the first pass reads: whole input blocks (of A / R1 rows) that contain a row < n1max
@@ -251,6 +248,28 @@ nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, cons
     const CT wq = nufft::cmul(t_hi[q >> pl], t_lo[q & lmask]);
     Tp[g_base + nbk * RW * TC + cg * JW] = nufft::cmul(buf[s_base + cg * JW * LS + nbk * (RW + RW / 16)], wq);
   }
+}
+// grid (Bc / TC, B): one transform per CTA.  (Kept free of any extra kernel parameter: the float2 instantiation sits
+// exactly at the 64-register cap of 2 CTAs/SM, and a 16-byte parameter more made ptxas spill 184 bytes - the column
+// kernel went from 1.12 to 1.66 ms; profiles/launches_r02_c2_escalation_v2_spill.csv.)
+template <int PA, class CT = float2>
+__global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
+nufft2_cols_kernel(const CT* __restrict__ G, CT* __restrict__ T, int n1max, const CT* __restrict__ tw_a,
+                   const CT* __restrict__ t_hi, const CT* __restrict__ t_lo) {
+  LKB_DYN_SMEM(CT, buf);
+  v2_cols_one<PA, CT>(buf, G, T, n1max, tw_a, t_hi, t_lo, (int64_t)blockIdx.y);
+}
+// escalation pass (double precision): blocks stride over a device-side count of transforms
+template <int PA>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+nufft2_cols_list_kernel(const double2* __restrict__ G, double2* __restrict__ T, int n1max,
+                        const double2* __restrict__ tw_a, const double2* __restrict__ t_hi,
+                        const double2* __restrict__ t_lo, V2Count nc) {
+  LKB_DYN_SMEM(double2, buf);
+  const int64_t ntr = v2_count(nc, (int)gridDim.y);
+  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {
+    __syncthreads();
+    v2_cols_one<PA, double2>(buf, G, T, n1max, tw_a, t_hi, t_lo, lc);
   }
 }
 
@@ -302,12 +321,11 @@ __device__ __forceinline__ float v2_finish_pw(double2 g1, double2 g2, const V2FT
 }
 
 // MODE 1: finish -> power.  MODE 2: the modes k < nk2_keep * A and their mirrors Mh - k go to Zout [B][Mh] in natural
-// order (the ragged finish kernel reads them there).  grid (A / 16, B)
-template <int PA, int MODE, class CT = float2>
-__global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
-nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Finish fa, CT* __restrict__ Zout,
-                   int nk2_keep, V2Count nc) {
-  LKB_DYN_SMEM(CT, buf);
+// order (the ragged finish kernel reads them there).  One transform (slot lc; lc_base + lc indexes fa.lcmap).
+template <int PA, int MODE, class CT>
+__device__ __forceinline__ void v2_rows_one(CT* buf, const CT* __restrict__ T, const CT* __restrict__ tw_b,
+                                            const V2Finish& fa, CT* __restrict__ Zout, int nk2_keep, const int64_t lc,
+                                            const int lc_base) {
   constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, R = V2_R, LS = V2_LSB, Bc = V2_BC;
   const int t = (int)threadIdx.x, g = (int)blockIdx.x;
   const bool last = g == (A / (2 * R)) - 1;
@@ -318,9 +336,6 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
     if (last && r == 0) return 0;                    // instead of a second copy of row A / 2
     return A - (g + 1) * R + r;
   };
-  const int64_t ntr = v2_count(nc, (int)gridDim.y);
-  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {       // (one trip except in the escalation pass)
-  __syncthreads();
   const CT* Tp = T + lc * Mh;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
@@ -339,15 +354,14 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
       const int k2 = q < keep ? q : Bc - 2 * keep + q;          // [0, keep) and [Bc - keep, Bc)
       Zout[lc * Mh + k1 + ((int64_t)k2 << PA)] = buf[s * LS + v2_skew(k2)];
     }
-    continue;
-  }
+  } else {
   int ps = (1 - h) * R + (R - 1 - r);                              // mode Mh - k: row A - k1, column Bc - 1 - k2
   bool row0 = false;
   if (last && h == 0 && r == R - 1) ps = s;                        // row A / 2 mirrors onto itself
   if (last && h == 1 && r == 0) { ps = s; row0 = true; }           // row 0: column (Bc - k2) mod Bc
   int64_t nK2 = ((fa.k0 + fa.F - 1) >> PA) + 1;
   if (nK2 > Bc) nK2 = Bc;
-  const int64_t lcd = fa.lcmap ? (int64_t)fa.lcmap[nc.base + lc] : lc;   // the light curve whose flux this transform holds
+  const int64_t lcd = fa.lcmap ? (int64_t)fa.lcmap[lc_base + lc] : lc;   // the light curve whose flux this transform holds
   const float ys0 = fa.ysum[lcd];
   float* prow = fa.power + lcd * fa.F;
   const int64_t jbase = (int64_t)k1 - fa.k0;
@@ -380,6 +394,27 @@ nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Fini
     for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
     if ((t & 31) == 0 && pmax > 0.0f) atomicMax(fa.peak + lcd, __float_as_uint(pmax));
   }
+  }
+}
+
+// grid (A / 16, B): one transform per CTA (no extra parameters: see nufft2_cols_kernel)
+template <int PA, int MODE, class CT = float2>
+__global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
+nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Finish fa, CT* __restrict__ Zout,
+                   int nk2_keep) {
+  LKB_DYN_SMEM(CT, buf);
+  v2_rows_one<PA, MODE, CT>(buf, T, tw_b, fa, Zout, nk2_keep, (int64_t)blockIdx.y, 0);
+}
+// escalation pass (double precision, finish mode): blocks stride over a device-side count of transforms; transform
+// slot lc holds light curve fa.lcmap[nc.base + lc]
+template <int PA>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+nufft2_rows_list_kernel(const double2* __restrict__ T, const double2* __restrict__ tw_b, V2Finish fa, V2Count nc) {
+  LKB_DYN_SMEM(double2, buf);
+  const int64_t ntr = v2_count(nc, (int)gridDim.y);
+  for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {
+    __syncthreads();
+    v2_rows_one<PA, 1, double2>(buf, T, tw_b, fa, nullptr, 0, lc, nc.base);
   }
 }
 
@@ -482,9 +517,17 @@ template <int PA, class CT>
 int v2_cols_pa(const CT* G, CT* T, int n1max, int B, const V2TablesT<CT>& tb, cudaStream_t st, V2Count nc) {
   constexpr int A = 1 << PA, TC = V2_TILE / A;
   const size_t smem = (size_t)TC * (A + A / 16 + 1) * sizeof(CT);
+  const dim3 grid((unsigned)(V2_BC / TC), (unsigned)B);
+  if constexpr (sizeof(CT) == 16) {
+    if (nc.count) {
+      LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_list_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_cols_list_kernel<PA>)(G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo, nc);
+      LKB_LAUNCH_CHECK();
+      return LKB_OK;
+    }
+  }
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_cols_kernel<PA, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LKB_LAUNCH_SMEM(dim3((unsigned)(V2_BC / TC), (unsigned)B), V2_THREADS, smem, st, nufft2_cols_kernel<PA, CT>)(
-      G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo, nc);
+  LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_cols_kernel<PA, CT>)(G, T, n1max, tb.tw_a, tb.t_hi, tb.t_lo);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }
@@ -492,11 +535,19 @@ template <int PA, class CT>
 int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep, cudaStream_t st,
                V2Count nc) {
   const size_t smem = (size_t)(2 * V2_R) * V2_LSB * sizeof(CT);
+  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
+  if constexpr (sizeof(CT) == 16) {
+    if (nc.count && fa) {
+      LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_list_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_list_kernel<PA>)(T, tb.tw_b, *fa, nc);
+      LKB_LAUNCH_CHECK();
+      return LKB_OK;
+    }
+  }
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 1, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 2, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
-  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0, nc);
-  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep, nc);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }

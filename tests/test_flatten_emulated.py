@@ -21,7 +21,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
     out = str(tmp_path_factory.mktemp("emu") / "libflatten_emu.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC", "-Wl,-Bsymbolic",
                            "-o", out, os.path.join(HERE, "native", "flatten_emu_driver.cpp")])
     lib = ctypes.CDLL(out)
     lib.emu_flatten2.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_vp, c_vp, c_int,

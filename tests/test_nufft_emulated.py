@@ -23,7 +23,7 @@ def emu(tmp_path_factory):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
     out = str(tmp_path_factory.mktemp("emu") / "libnufft_emu.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC", "-Wl,-Bsymbolic",
                            "-o", out, os.path.join(HERE, "native", "nufft_emu_driver.cpp")])
     lib = ctypes.CDLL(out)
     shared = [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_i64, c_int, c_dbl, c_vp]
