@@ -325,9 +325,9 @@ __device__ __forceinline__ float v2_finish_pw(double2 g1, double2 g2, const V2FT
 template <int PA, int MODE, class CT>
 __device__ __forceinline__ void v2_rows_one(CT* buf, const CT* __restrict__ T, const CT* __restrict__ tw_b,
                                             const V2Finish& fa, CT* __restrict__ Zout, int nk2_keep, const int64_t lc,
-                                            const int lc_base) {
+                                            const int lc_base, const int g) {
   constexpr int A = 1 << PA, PTC = V2_LOG_TILE - PA, TC = 1 << PTC, R = V2_R, LS = V2_LSB, Bc = V2_BC;
-  const int t = (int)threadIdx.x, g = (int)blockIdx.x;
+  const int t = (int)threadIdx.x;
   const bool last = g == (A / (2 * R)) - 1;
   const int64_t Mh = (int64_t)1 << (PA + V2_PB);
   auto slot_k1 = [&](int s) -> int {
@@ -397,13 +397,15 @@ __device__ __forceinline__ void v2_rows_one(CT* buf, const CT* __restrict__ T, c
   }
 }
 
-// grid (A / 16, B): one transform per CTA (no extra parameters: see nufft2_cols_kernel)
+// grid (B, A / 16) - the LIGHT CURVE is the fast block index: the CTAs in flight at any moment then work on the same
+// group of rows, i.e. read the same 100 KB slice of the finish table, which stays in L1/L2 instead of being fetched
+// 32 table slices at a time.  One transform per CTA (no extra parameters: see nufft2_cols_kernel).
 template <int PA, int MODE, class CT = float2>
 __global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
 nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Finish fa, CT* __restrict__ Zout,
                    int nk2_keep) {
   LKB_DYN_SMEM(CT, buf);
-  v2_rows_one<PA, MODE, CT>(buf, T, tw_b, fa, Zout, nk2_keep, (int64_t)blockIdx.y, 0);
+  v2_rows_one<PA, MODE, CT>(buf, T, tw_b, fa, Zout, nk2_keep, (int64_t)blockIdx.x, 0, (int)blockIdx.y);
 }
 // escalation pass (double precision, finish mode): blocks stride over a device-side count of transforms; transform
 // slot lc holds light curve fa.lcmap[nc.base + lc]
@@ -414,7 +416,7 @@ nufft2_rows_list_kernel(const double2* __restrict__ T, const double2* __restrict
   const int64_t ntr = v2_count(nc, (int)gridDim.y);
   for (int64_t lc = blockIdx.y; lc < ntr; lc += gridDim.y) {
     __syncthreads();
-    v2_rows_one<PA, 1, double2>(buf, T, tw_b, fa, nullptr, 0, lc, nc.base);
+    v2_rows_one<PA, 1, double2>(buf, T, tw_b, fa, nullptr, 0, lc, nc.base, (int)blockIdx.x);
   }
 }
 
@@ -535,7 +537,7 @@ template <int PA, class CT>
 int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep, cudaStream_t st,
                V2Count nc) {
   const size_t smem = (size_t)(2 * V2_R) * V2_LSB * sizeof(CT);
-  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
+  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B), grid_t((unsigned)B, (unsigned)((1 << PA) / (2 * V2_R)));
   if constexpr (sizeof(CT) == 16) {
     if (nc.count && fa) {
       LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_list_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -546,8 +548,8 @@ int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, 
   }
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 1, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 2, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
-  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
+  if (fa) LKB_LAUNCH_SMEM(grid_t, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
+  else LKB_LAUNCH_SMEM(grid_t, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }

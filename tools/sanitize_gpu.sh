@@ -10,8 +10,9 @@ echo "=== memcheck: smoke() ==="
 timeout 1500 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/memcheck_smoke.log 2>&1; echo "rc=$?"
 grep -E "ERROR SUMMARY|smoke ok|Invalid|========= Error" $O/memcheck_smoke.log | head -10
 cat > $O/_small.py <<'PY'
-import numpy as np, sys
+import numpy as np, os, sys
 sys.path.insert(0, ".")
+os.environ["LKB_NUFFT_ESCALATE"] = "50"       # (the test light curve's flux excursion is 219 x its in-band peak)
 from lightkurve_b200 import engine
 engine.init(0)
 rng = np.random.default_rng(3)
