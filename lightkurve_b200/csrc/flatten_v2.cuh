@@ -184,9 +184,31 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
   const double sc = half > 0 ? (double)half : 1.0;
 
   // ---- initial mask (:996-1010): finite, not excluded, within sigma * nanstd of the nanmedian ----
+  // np.nanstd(flux) rides along in the median's partition pass: sums of d = flux - lo and d^2 (lo = the bracket's
+  // lower value, within a few percent of a standard deviation of the mean) over the non-NaN values
+  double is1 = 0.0, is2 = 0.0;
+  int isc = 0;
+  auto stats0 = [&](int64_t i, double, double lo, bool valid) {
+    if (valid) {
+      const double raw = f[i];                    // (infinities stay in, as in numpy: the result is then NaN)
+      if (raw == raw) { const double d = raw - lo; is1 += d; is2 = fma(d, d, is2); isc++; }
+    }
+  };
+  bool seen0 = false;
   const double med0 = block_nanmedian_fast([&](int64_t i) { const double v = f[i]; return isfinite(v) ? v : qnan; }, n,
-                                           sm.sel, sm.fs);
-  const double std0 = block_nanstd([&](int64_t i) { return f[i]; }, n, sm.sel);
+                                           sm.sel, sm.fs, -1, stats0, &seen0);
+  double std0;
+  if (seen0) {
+    const double t1 = block_sum(is1, sm.sel.red), t2 = block_sum(is2, sm.sel.red);
+    const long long tc = block_sum_ll((long long)isc, sm.sel.redll);
+    if (tc == 0) std0 = qnan;
+    else {
+      const double md = t1 / (double)tc, var = t2 / (double)tc - md * md;
+      std0 = (var == var) ? sqrt(var > 0.0 ? var : 0.0) : qnan;
+    }
+  } else {
+    std0 = block_nanstd([&](int64_t i) { return f[i]; }, n, sm.sel);
+  }
   {
     const double thr = std0 * sigma;
     for (int w0 = warp; w0 < nw; w0 += F2_THREADS / 32) {
@@ -211,15 +233,59 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
     m = f2_prefix(sm, nw);
     if (m < 2) { ok = false; break; }
     // ---- gap segmentation (:1022-1027): cut where dt > break_tolerance * nanmedian(dt) over the kept cadences ----
+    // The median's partition pass sees every dt once with a lower bound `lo` of the median: cadences with
+    // dt > break_tolerance * lo (a superset of the cuts - a handful) are noted on the way, so that no second pass over
+    // the time stamps is needed; they are filtered with the exact threshold afterwards.
+    if (t == 0) { sm.misc[0] = 0; sm.misc[1] = 0; }          // misc[0] = cuts found, misc[1] = cut candidates noted
+    __syncthreads();
+    const bool bt_ok = break_tolerance >= 0.0;
+    auto note = [&](int64_t i, double v, double lo, bool valid) {
+      const bool c = valid && bt_ok && v > break_tolerance * lo;      // (NaN dt / NaN lo: false)
+      const unsigned bal = __ballot_sync(0xffffffffu, c);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sm.misc[1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (c) {
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (pos < F2_MAXSEG) sm.cuts[pos] = (int)i;
+        }
+      }
+    };
+    bool observed = false;
     const double med_dt = block_nanmedian_fast([&](int64_t i) {
       if (!f2_kept(sm, (int)i)) return qnan;
       const int pv = f2_prev(sm, (int)i);
       return pv < 0 ? qnan : tt[i] - tt[pv];
-    }, n, sm.sel, sm.fs, (long long)m - 1);
+    }, n, sm.sel, sm.fs, (long long)m - 1, note, &observed);
     const double thr_dt = break_tolerance * med_dt;
-    // cuts are rare: unordered append (one atomic per warp that found any), then a rank sort of the short list
-    if (t == 0) { sm.misc[0] = 0; }                          // misc[0] = number of cuts found
     __syncthreads();
+    const int ncand = sm.misc[1];
+    if (observed && bt_ok && ncand <= F2_MAXSEG) {
+      // exact filter of the noted candidates (unordered append of the kept-sequence rank, as the full pass does)
+      for (int e0 = 0; e0 < ncand; e0 += F2_THREADS) {
+        const int e = e0 + t;
+        bool cut = false;
+        int i = 0;
+        if (e < ncand) {
+          i = sm.cuts[e];
+          const int pv = f2_prev(sm, i);
+          cut = pv >= 0 && (tt[i] - tt[pv]) > thr_dt;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cut);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sm.misc[0], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (cut) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (pos < F2_MAXSEG - 1) sm.ucuts[pos] = f2_rank(sm, i);
+          }
+        }
+      }
+    } else {
+    // (the median came from a fallback path, or too many candidates: one pass over the time stamps)
+    // cuts are rare: unordered append (one atomic per warp that found any), then a rank sort of the short list
     for (int i0 = 0; i0 < n; i0 += 4 * F2_THREADS) {          // 4 independent (t[i], t[prev]) load pairs in flight
       double dd[4];
 #pragma unroll
@@ -247,6 +313,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
         }
       }
     }
+    }
     __syncthreads();
     const int ncut = sm.misc[0];
     if (ncut > F2_MAXSEG - 2) {                              // too many segments for the shared-memory list
@@ -264,6 +331,14 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
     if (t == 0) sm.cuts[nseg] = m;
     __syncthreads();
 
+    // residual statistics of this iteration, gathered where the trend values are produced (no extra passes):
+    // sum r, sum r^2, count over the kept cadences (np.nanstd semantics: NaN residuals are left out)
+    double rs1 = 0.0, rs2 = 0.0;
+    int rsc = 0;
+    auto residual = [&](int i, double y) {
+      const double r = f[i] - y;
+      if (r == r) { rs1 += r; rs2 = fma(r, r, rs2); rsc++; }
+    };
     // ---- Savitzky-Golay interior by tiles of `tile_out` kept positions ----
     for (int k0 = 0; k0 < m; k0 += tile_out) {
       const int kin0 = max(0, k0 - half), kin1 = min(m, k0 + tile_out + half);      // inputs [kin0, kin1)
@@ -354,6 +429,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
           }
         }
         tro[i] = y;
+        residual(i, y);
       }
     }
     __syncthreads();
@@ -369,7 +445,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
         const double md = block_nanmedian([&](int64_t j) { return f2_kept(sm, i_lo + (int)j) ? f[i_lo + j] : qnan; },
                                           i_hi - i_lo, sm.sel);
         for (int i = i_lo + t; i < i_hi; i += F2_THREADS)
-          if (f2_kept(sm, i)) tro[i] = md;
+          if (f2_kept(sm, i)) { tro[i] = md; residual(i, md); }
         continue;
       }
       if (half == 0) continue;
@@ -410,13 +486,25 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
           for (int r = F2_MAXQ - 1; r >= 0; --r)
             if (r < cf.q) y = y * u + bet[r];
           tro[i] = y;
+          residual(i, y);
         }
         __syncthreads();
       }
     }
     __syncthreads();
     // ---- residual clip (:1049-1052, :1060-1063) ----
-    const double rstd = block_nanstd([&](int64_t i) { return f2_kept(sm, (int)i) ? f[i] - tro[i] : qnan; }, n, sm.sel);
+    // np.nanstd(flux - trend) from the running sums: var = <r^2> - <r>^2 (the residuals are centred on zero by
+    // construction - |<r>| << std - so the one-pass form loses nothing; numpy's two-pass value differs by ~1e-16)
+    double rstd;
+    {
+      const double t1 = block_sum(rs1, sm.sel.red), t2 = block_sum(rs2, sm.sel.red);
+      const long long tc = block_sum_ll((long long)rsc, sm.sel.redll);
+      if (tc == 0) rstd = qnan;
+      else {
+        const double mean = t1 / (double)tc, var = t2 / (double)tc - mean * mean;
+        rstd = sqrt(var > 0.0 ? var : 0.0);
+      }
+    }
     const double rthr = rstd * sigma + 1e-14;
     for (int w0 = warp; w0 < nw; w0 += F2_THREADS / 32) {
       const int i = w0 * 32 + lane;

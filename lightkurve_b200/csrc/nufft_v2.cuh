@@ -397,15 +397,16 @@ __device__ __forceinline__ void v2_rows_one(CT* buf, const CT* __restrict__ T, c
   }
 }
 
-// grid (B, A / 16) - the LIGHT CURVE is the fast block index: the CTAs in flight at any moment then work on the same
-// group of rows, i.e. read the same 100 KB slice of the finish table, which stays in L1/L2 instead of being fetched
-// 32 table slices at a time.  One transform per CTA (no extra parameters: see nufft2_cols_kernel).
+// grid (A / 16, B): one transform per CTA (no extra parameters: see nufft2_cols_kernel).  (Tried: the light curve as
+// the FAST block index, so that the CTAs in flight share one 100 KB slice of the finish table - 1.84 ms instead of
+// 1.76 ms: the tile reads of 296 different light curves scatter over DRAM pages, which costs more than the table
+// locality gains.)
 template <int PA, int MODE, class CT = float2>
 __global__ void __launch_bounds__(V2_THREADS, sizeof(CT) == 8 ? 2 : 1)
 nufft2_rows_kernel(const CT* __restrict__ T, const CT* __restrict__ tw_b, V2Finish fa, CT* __restrict__ Zout,
                    int nk2_keep) {
   LKB_DYN_SMEM(CT, buf);
-  v2_rows_one<PA, MODE, CT>(buf, T, tw_b, fa, Zout, nk2_keep, (int64_t)blockIdx.x, 0, (int)blockIdx.y);
+  v2_rows_one<PA, MODE, CT>(buf, T, tw_b, fa, Zout, nk2_keep, (int64_t)blockIdx.y, 0, (int)blockIdx.x);
 }
 // escalation pass (double precision, finish mode): blocks stride over a device-side count of transforms; transform
 // slot lc holds light curve fa.lcmap[nc.base + lc]
@@ -537,7 +538,7 @@ template <int PA, class CT>
 int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, CT* Zout, int nk2_keep, cudaStream_t st,
                V2Count nc) {
   const size_t smem = (size_t)(2 * V2_R) * V2_LSB * sizeof(CT);
-  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B), grid_t((unsigned)B, (unsigned)((1 << PA) / (2 * V2_R)));
+  const dim3 grid((unsigned)((1 << PA) / (2 * V2_R)), (unsigned)B);
   if constexpr (sizeof(CT) == 16) {
     if (nc.count && fa) {
       LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_list_kernel<PA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -548,8 +549,8 @@ int v2_rows_pa(const CT* T, int B, const V2TablesT<CT>& tb, const V2Finish* fa, 
   }
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 1, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LKB_CUDA_CHECK(cudaFuncSetAttribute(nufft2_rows_kernel<PA, 2, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (fa) LKB_LAUNCH_SMEM(grid_t, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
-  else LKB_LAUNCH_SMEM(grid_t, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
+  if (fa) LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 1, CT>)(T, tb.tw_b, *fa, nullptr, 0);
+  else LKB_LAUNCH_SMEM(grid, V2_THREADS, smem, st, nufft2_rows_kernel<PA, 2, CT>)(T, tb.tw_b, V2Finish(), Zout, nk2_keep);
   LKB_LAUNCH_CHECK();
   return LKB_OK;
 }

@@ -164,20 +164,23 @@ __device__ inline double fs_rank_value(long long r, long long c_lt, long long c_
   return 0.0;
 }
 
+struct FsNoObserver {
+  __device__ __forceinline__ void operator()(int64_t, double, double, bool) const {}
+};
 // np.nanmedian over get(0..n-1); m = number of non-NaN values if known (>= 0), else -1 (counted in the sample pass).
-template <class Get>
-__device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelSmem& fs, long long m_known = -1) {
+// obs(i, v, lo, valid): called convergently (all 32 lanes of a warp, `valid` false for lanes past the end) for every
+// element during the ONE partition pass, with the bracket's lower value `lo` <= median - a caller can piggy-back work
+// that only needs a bound of the median (flatten: the gap-cut candidates).  *observed tells whether that pass ran
+// (false on the small-n / fallback paths, where obs was never called or the pass was abandoned).
+template <class Get, class Obs = FsNoObserver>
+__device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelSmem& fs, long long m_known = -1,
+                                       Obs obs = Obs(), bool* observed = nullptr) {
+  if (observed) *observed = false;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
   if (n < 4 * FS_SAMPLE) return block_nanmedian(get, n, sm);
-  // ---- sample (every stride-th element; NaNs are dropped from the sample) + count ----
+  // ---- sample (every stride-th element; NaNs are dropped from the sample).  The number of non-NaN values is only
+  // needed for the final rank: when the caller does not know it, it is counted in the partition pass itself ----
   long long m = m_known;
-  if (m < 0) {
-    long long cnt = 0;
-#pragma unroll 4
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double v = get(i); cnt += (v == v) ? 1 : 0; }
-    m = block_sum_ll(cnt, sm.redll);
-  }
-  if (m == 0) return qnan;
   const int64_t stride = n / FS_SAMPLE;
   double* const sample = fs.cand + FS_CAP;
   long long scnt = 0;
@@ -195,9 +198,9 @@ __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelS
   const double lo = f64_unkey(block_select_key(gets, FS_SAMPLE, rlo, sm));
   const double hi = f64_unkey(block_select_key(gets, FS_SAMPLE, rhi, sm));
   // ---- the one pass: partition counts + candidates strictly between lo and hi ----
-  if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; }
+  if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; fs.ok = 0; }
   __syncthreads();
-  int c_lt = 0, c_eqlo = 0, c_eqhi = 0;
+  int c_lt = 0, c_eqlo = 0, c_eqhi = 0, c_ge = 0;                 // c_ge: values >= hi (only the total is needed)
   for (int64_t i0 = 0; i0 < n; i0 += 4 * (int64_t)blockDim.x) {   // warp-uniform trip count; 4 loads in flight per thread
     double vv[4];
 #pragma unroll
@@ -208,12 +211,13 @@ __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelS
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double v = vv[u];
+      obs(i0 + (int64_t)u * blockDim.x + threadIdx.x, v, lo, i0 + (int64_t)u * blockDim.x + threadIdx.x < n);
       bool between = false;
       if (v == v) {
         if (v < lo) c_lt++;
         else if (v == lo) c_eqlo++;
         else if (v < hi) between = true;
-        else if (v == hi) c_eqhi++;
+        else { c_ge++; if (v == hi) c_eqhi++; }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, between);
       if (bal) {
@@ -228,11 +232,15 @@ __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelS
     }
   }
   if (lo == hi) c_eqhi = 0;                                     // (one value: counted once, as eq-lo)
-  c_lt = warp_sum(c_lt); c_eqlo = warp_sum(c_eqlo); c_eqhi = warp_sum(c_eqhi);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&fs.c_lt, c_lt); atomicAdd(&fs.c_eqlo, c_eqlo); atomicAdd(&fs.c_eqhi, c_eqhi); }
+  c_lt = warp_sum(c_lt); c_eqlo = warp_sum(c_eqlo); c_eqhi = warp_sum(c_eqhi); c_ge = warp_sum(c_ge);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&fs.c_lt, c_lt); atomicAdd(&fs.c_eqlo, c_eqlo); atomicAdd(&fs.c_eqhi, c_eqhi); atomicAdd(&fs.ok, c_ge);
+  }
   __syncthreads();
   const long long n_cand = fs.n_cand, t_lt = fs.c_lt, t_eqlo = fs.c_eqlo, t_eqhi = fs.c_eqhi;
+  if (m < 0) m = t_lt + t_eqlo + n_cand + (long long)fs.ok;      // (lo == hi: the values equal to it were counted as eq-lo)
   __syncthreads();
+  if (observed) *observed = true;                                // every element went past obs exactly once
   if (n_cand > FS_CAP) return block_nanmedian(get, n, sm);
   auto getc = [&](int64_t i) { return fs.cand[i]; };
   const long long klo = (m - 1) / 2, khi = m / 2;
