@@ -49,6 +49,7 @@ struct F2Smem {
   double beta[F2_MAXQ];
   int scan_tmp[17];
   int misc[8];
+  FastBracket br_dt;                            // the dt median's bracket, carried from one iteration to the next
 };
 
 // exclusive prefix of popc(keep[w]) over nw words -> wpre[0 .. nw]; returns the total.  All threads call.
@@ -229,6 +230,7 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
 
   bool ok = true;
   int m = 0;
+  if (t == 0) sm.br_dt.valid = false;         // (the first f2_prefix's barriers publish it)
   for (int it = 0; it < niters && ok; ++it) {
     m = f2_prefix(sm, nw);
     if (m < 2) { ok = false; break; }
@@ -252,12 +254,16 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
         }
       }
     };
+#ifdef LKB_FS_TEST_BAD_BRACKET            // test hook (tests/test_flatten_emulated.py): a stale bracket that misses the median
+    if (t == 0 && it > 0) { sm.br_dt.lo = -2.0; sm.br_dt.hi = -1.0; sm.br_dt.valid = true; }
+    __syncthreads();
+#endif
     bool observed = false;
     const double med_dt = block_nanmedian_fast([&](int64_t i) {
       if (!f2_kept(sm, (int)i)) return qnan;
       const int pv = f2_prev(sm, (int)i);
       return pv < 0 ? qnan : tt[i] - tt[pv];
-    }, n, sm.sel, sm.fs, (long long)m - 1, note, &observed);
+    }, n, sm.sel, sm.fs, (long long)m - 1, note, &observed, &sm.br_dt, [&]() { if (t == 0) sm.misc[1] = 0; });
     const double thr_dt = break_tolerance * med_dt;
     __syncthreads();
     const int ncand = sm.misc[1];
@@ -349,8 +355,21 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       const int i_lo = sel4[0], i_hi = sel4[1] + 1;
       const double qc = 0.5 * (double)nin;
       // stage x_q in P[0][q + 1]
-      for (int i = i_lo + t; i < i_hi; i += F2_THREADS)
-        if (f2_kept(sm, i)) P[f2_rank(sm, i) - kin0 + 1] = f[i];
+      for (int i0 = i_lo; i0 < i_hi; i0 += 4 * F2_THREADS) {       // 4 loads in flight per thread
+        double xv[4];
+        bool kp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * F2_THREADS + t;
+          kp[u] = i < i_hi && f2_kept(sm, i);
+          xv[u] = kp[u] ? f[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * F2_THREADS + t;
+          if (kp[u]) P[f2_rank(sm, i) - kin0 + 1] = xv[u];
+        }
+      }
       __syncthreads();
       // prefix sums P[s][q + 1] = sum_{q' <= q} (q' - qc)^s x_q'   (each thread owns PER consecutive q)
       {
@@ -468,14 +487,18 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
           }
         }
         f2_block_sums(sm, mom, cf.q);                              // sm.beta = moments
+        // polynomial coefficients = Ginv * moments: q threads, one row each, then everyone reads them (all 512
+        // threads indexing the parameter struct dynamically was 2.8 % of the kernel's instructions)
+        __syncthreads();
+        if (t < cf.q) {
+          double acc = 0.0;
+          for (int c2 = 0; c2 < cf.q; ++c2) acc += cf.Ginv[t * cf.q + c2] * sm.beta[c2];
+          sm.red[0][t] = acc;
+        }
+        __syncthreads();
         double bet[F2_MAXQ];
 #pragma unroll
-        for (int r = 0; r < F2_MAXQ; ++r) {
-          double acc = 0.0;
-          if (r < cf.q)
-            for (int c2 = 0; c2 < cf.q; ++c2) acc += cf.Ginv[r * cf.q + c2] * sm.beta[c2];
-          bet[r] = acc;
-        }
+        for (int r = 0; r < F2_MAXQ; ++r) bet[r] = (r < cf.q) ? sm.red[0][r] : 0.0;
         // outputs: the first (side 0) / last (side 1) `half` positions of the window
         const int j_lo = sel4[2], j_hi = sel4[3] + 1;
         for (int i = j_lo + t; i < j_hi; i += F2_THREADS) {
@@ -506,17 +529,29 @@ flatten2_kernel(const double* __restrict__ time, const double* __restrict__ flux
       }
     }
     const double rthr = rstd * sigma + 1e-14;
-    for (int w0 = warp; w0 < nw; w0 += F2_THREADS / 32) {
-      const int i = w0 * 32 + lane;
-      bool keepit = false;
-      if (i < n && f2_kept(sm, i)) {
-        double a = fabs(f[i] - tro[i]);
-        if (a != a) a = 0.0;
-        keepit = a < rthr;
+    for (int wb = warp; wb < nw; wb += 4 * (F2_THREADS / 32)) {   // 4 words per warp and trip: 8 loads in flight per lane
+      double fv[4], tv4[4];
+      bool kp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w0 = wb + u * (F2_THREADS / 32), i = w0 * 32 + lane;
+        kp[u] = w0 < nw && i < n && f2_kept(sm, i);
+        fv[u] = kp[u] ? f[i] : 0.0;
+        tv4[u] = kp[u] ? tro[i] : 0.0;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, keepit);
-      __syncwarp();
-      if (lane == 0) sm.keep[w0] = bal;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w0 = wb + u * (F2_THREADS / 32);
+        bool keepit = false;
+        if (kp[u]) {
+          double a = fabs(fv[u] - tv4[u]);
+          if (a != a) a = 0.0;
+          keepit = a < rthr;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keepit);
+        __syncwarp();
+        if (lane == 0 && w0 < nw) sm.keep[w0] = bal;
+      }
     }
     __syncthreads();
   }

@@ -167,89 +167,127 @@ __device__ inline double fs_rank_value(long long r, long long c_lt, long long c_
 struct FsNoObserver {
   __device__ __forceinline__ void operator()(int64_t, double, double, bool) const {}
 };
+// A bracket [lo, hi] that held the median of an earlier, nearly identical data set (flatten: the time differences of
+// the kept cadences change by a few hundred entries per iteration).  When given and valid, the sampling stage and its
+// two selects are skipped; if the median turns out to lie outside, the call starts over with a fresh sample.
+struct FastBracket {
+  double lo, hi;
+  bool valid;
+};
 // np.nanmedian over get(0..n-1); m = number of non-NaN values if known (>= 0), else -1 (counted in the sample pass).
 // obs(i, v, lo, valid): called convergently (all 32 lanes of a warp, `valid` false for lanes past the end) for every
 // element during the ONE partition pass, with the bracket's lower value `lo` <= median - a caller can piggy-back work
 // that only needs a bound of the median (flatten: the gap-cut candidates).  *observed tells whether that pass ran
 // (false on the small-n / fallback paths, where obs was never called or the pass was abandoned).
-template <class Get, class Obs = FsNoObserver>
+struct FsNoReset {
+  __device__ __forceinline__ void operator()() const {}
+};
+// br (optional, in memory every thread of the block sees - shared memory): bracket to try first / to leave behind.  reset(): called (by all threads, followed by a barrier) before
+// the partition pass is REPEATED with a fresh bracket, so that obs can start over.
+template <class Get, class Obs = FsNoObserver, class Reset = FsNoReset>
 __device__ double block_nanmedian_fast(Get get, int64_t n, SelSmem& sm, FastSelSmem& fs, long long m_known = -1,
-                                       Obs obs = Obs(), bool* observed = nullptr) {
+                                       Obs obs = Obs(), bool* observed = nullptr, FastBracket* br = nullptr,
+                                       Reset reset = Reset()) {
   if (observed) *observed = false;
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-  if (n < 4 * FS_SAMPLE) return block_nanmedian(get, n, sm);
-  // ---- sample (every stride-th element; NaNs are dropped from the sample).  The number of non-NaN values is only
-  // needed for the final rank: when the caller does not know it, it is counted in the partition pass itself ----
-  long long m = m_known;
-  const int64_t stride = n / FS_SAMPLE;
-  double* const sample = fs.cand + FS_CAP;
-  long long scnt = 0;
-  for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) {
-    const double v = get((int64_t)sidx * stride);
-    sample[sidx] = v;
-    scnt += (v == v) ? 1 : 0;
-  }
-  const long long ns = block_sum_ll(scnt, sm.redll);             // (its barriers also publish the sample)
-  if (ns < 4 * FS_GAP) return block_nanmedian(get, n, sm);
-  auto gets = [&](int64_t i) { return sample[i]; };
-  long long rlo = ns / 2 - FS_GAP, rhi = ns / 2 + FS_GAP;
-  if (rlo < 0) rlo = 0;
-  if (rhi > ns - 1) rhi = ns - 1;
-  const double lo = f64_unkey(block_select_key(gets, FS_SAMPLE, rlo, sm));
-  const double hi = f64_unkey(block_select_key(gets, FS_SAMPLE, rhi, sm));
-  // ---- the one pass: partition counts + candidates strictly between lo and hi ----
-  if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; fs.ok = 0; }
-  __syncthreads();
-  int c_lt = 0, c_eqlo = 0, c_eqhi = 0, c_ge = 0;                 // c_ge: values >= hi (only the total is needed)
-  for (int64_t i0 = 0; i0 < n; i0 += 4 * (int64_t)blockDim.x) {   // warp-uniform trip count; 4 loads in flight per thread
-    double vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
-      vv[u] = (i < n) ? get(i) : qnan;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double v = vv[u];
-      obs(i0 + (int64_t)u * blockDim.x + threadIdx.x, v, lo, i0 + (int64_t)u * blockDim.x + threadIdx.x < n);
-      bool between = false;
-      if (v == v) {
-        if (v < lo) c_lt++;
-        else if (v == lo) c_eqlo++;
-        else if (v < hi) between = true;
-        else { c_ge++; if (v == hi) c_eqhi++; }
+  if (n < 4 * FS_SAMPLE) { if (br && threadIdx.x == 0) br->valid = false; return block_nanmedian(get, n, sm); }
+  bool reuse = br != nullptr && br->valid;                       // (block-uniform: every thread holds the same copy)
+  for (;;) {
+    // ---- bracket: the caller's, or from a sample (every stride-th element; NaNs are dropped from the sample).  The
+    // number of non-NaN values is only needed for the final rank: when the caller does not know it, it is counted
+    // in the partition pass itself ----
+    long long m = m_known;
+    double lo, hi;
+    if (reuse) {
+      lo = br->lo;
+      hi = br->hi;
+    } else {
+      const int64_t stride = n / FS_SAMPLE;
+      double* const sample = fs.cand + FS_CAP;
+      long long scnt = 0;
+      for (int sidx = threadIdx.x; sidx < FS_SAMPLE; sidx += blockDim.x) {
+        const double v = get((int64_t)sidx * stride);
+        sample[sidx] = v;
+        scnt += (v == v) ? 1 : 0;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, between);
-      if (bal) {
-        int base = 0;
-        if ((threadIdx.x & 31) == 0) base = atomicAdd(&fs.n_cand, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (between) {
-          const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-          if (pos < FS_CAP) fs.cand[pos] = v;
+      const long long ns = block_sum_ll(scnt, sm.redll);         // (its barriers also publish the sample)
+      if (ns < 4 * FS_GAP) { if (br && threadIdx.x == 0) br->valid = false; return block_nanmedian(get, n, sm); }
+      auto gets = [&](int64_t i) { return sample[i]; };
+      long long rlo = ns / 2 - FS_GAP, rhi = ns / 2 + FS_GAP;
+      if (rlo < 0) rlo = 0;
+      if (rhi > ns - 1) rhi = ns - 1;
+      lo = f64_unkey(block_select_key(gets, FS_SAMPLE, rlo, sm));
+      hi = f64_unkey(block_select_key(gets, FS_SAMPLE, rhi, sm));
+    }
+    // ---- the one pass: partition counts + candidates strictly between lo and hi ----
+    if (threadIdx.x == 0) { fs.n_cand = 0; fs.c_lt = 0; fs.c_eqlo = 0; fs.c_eqhi = 0; fs.ok = 0; }
+    __syncthreads();
+    int c_lt = 0, c_eqlo = 0, c_eqhi = 0, c_ge = 0;               // c_ge: values >= hi (only the total is needed)
+    for (int64_t i0 = 0; i0 < n; i0 += 4 * (int64_t)blockDim.x) { // warp-uniform trip count; 4 loads in flight per thread
+      double vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+        vv[u] = (i < n) ? get(i) : qnan;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double v = vv[u];
+        obs(i0 + (int64_t)u * blockDim.x + threadIdx.x, v, lo, i0 + (int64_t)u * blockDim.x + threadIdx.x < n);
+        bool between = false;
+        if (v == v) {
+          if (v < lo) c_lt++;
+          else if (v == lo) c_eqlo++;
+          else if (v < hi) between = true;
+          else { c_ge++; if (v == hi) c_eqhi++; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, between);
+        if (bal) {
+          int base = 0;
+          if ((threadIdx.x & 31) == 0) base = atomicAdd(&fs.n_cand, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (between) {
+            const int pos = base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+            if (pos < FS_CAP) fs.cand[pos] = v;
+          }
         }
       }
     }
+    if (lo == hi) c_eqhi = 0;                                     // (one value: counted once, as eq-lo)
+    c_lt = warp_sum(c_lt); c_eqlo = warp_sum(c_eqlo); c_eqhi = warp_sum(c_eqhi); c_ge = warp_sum(c_ge);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&fs.c_lt, c_lt); atomicAdd(&fs.c_eqlo, c_eqlo); atomicAdd(&fs.c_eqhi, c_eqhi); atomicAdd(&fs.ok, c_ge);
+    }
+    __syncthreads();
+    const long long n_cand = fs.n_cand, t_lt = fs.c_lt, t_eqlo = fs.c_eqlo, t_eqhi = fs.c_eqhi;
+    if (m < 0) m = t_lt + t_eqlo + n_cand + (long long)fs.ok;    // (lo == hi: the values equal to it were counted as eq-lo)
+    __syncthreads();
+    const long long klo = (m - 1) / 2, khi = m / 2;
+    if (reuse) {
+      // is the median still inside the old bracket, and the candidate buffer large enough?  If not: fresh sample
+      const bool inside = m > 0 && klo >= t_lt && khi < t_lt + t_eqlo + n_cand + t_eqhi && n_cand <= FS_CAP;
+      if (!inside) {
+        reuse = false;
+        if (threadIdx.x == 0) br->valid = false;
+        reset();
+        __syncthreads();
+        continue;
+      }
+    }
+    if (observed) *observed = true;                              // every element went past obs exactly once
+    if (br && threadIdx.x == 0) { br->lo = lo; br->hi = hi; br->valid = n_cand <= FS_CAP; }   // (barriers follow)
+    if (n_cand > FS_CAP) return block_nanmedian(get, n, sm);
+    auto getc = [&](int64_t i) { return fs.cand[i]; };
+    bool v1, v2;
+    const double a = fs_rank_value(klo, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v1);
+    const double b = (khi == klo) ? a : fs_rank_value(khi, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v2);
+    if (khi == klo) v2 = v1;
+    if (!(v1 && v2)) {                                           // the bracket missed: full radix select
+      if (br && threadIdx.x == 0) br->valid = false;
+      return block_nanmedian(get, n, sm);
+    }
+    return (a + b) / 2.0;
   }
-  if (lo == hi) c_eqhi = 0;                                     // (one value: counted once, as eq-lo)
-  c_lt = warp_sum(c_lt); c_eqlo = warp_sum(c_eqlo); c_eqhi = warp_sum(c_eqhi); c_ge = warp_sum(c_ge);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&fs.c_lt, c_lt); atomicAdd(&fs.c_eqlo, c_eqlo); atomicAdd(&fs.c_eqhi, c_eqhi); atomicAdd(&fs.ok, c_ge);
-  }
-  __syncthreads();
-  const long long n_cand = fs.n_cand, t_lt = fs.c_lt, t_eqlo = fs.c_eqlo, t_eqhi = fs.c_eqhi;
-  if (m < 0) m = t_lt + t_eqlo + n_cand + (long long)fs.ok;      // (lo == hi: the values equal to it were counted as eq-lo)
-  __syncthreads();
-  if (observed) *observed = true;                                // every element went past obs exactly once
-  if (n_cand > FS_CAP) return block_nanmedian(get, n, sm);
-  auto getc = [&](int64_t i) { return fs.cand[i]; };
-  const long long klo = (m - 1) / 2, khi = m / 2;
-  bool v1, v2;
-  const double a = fs_rank_value(klo, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v1);
-  const double b = (khi == klo) ? a : fs_rank_value(khi, t_lt, t_eqlo, n_cand, t_eqhi, lo, hi, getc, sm, &v2);
-  if (khi == klo) v2 = v1;
-  if (!(v1 && v2)) return block_nanmedian(get, n, sm);           // the bracket missed: full radix select
-  return (a + b) / 2.0;
 }
 
 // np.nanstd (ddof = 0): two-pass (mean, then squared deviations), NaN ignored.

@@ -23,7 +23,10 @@ def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libflatten_emu.so")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC", "-Wl,-Bsymbolic",
                            "-o", out, os.path.join(HERE, "native", "flatten_emu_driver.cpp")])
-    lib = ctypes.CDLL(out)
+    return _bind(ctypes.CDLL(out))
+
+
+def _bind(lib):
     lib.emu_flatten2.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_dbl, c_vp, c_vp, c_int,
                                  c_vp, c_vp, c_vp, c_vp]
     return lib
@@ -115,13 +118,36 @@ def test_flatten_v2_kernel_on_the_emulator(emu, w, p, bt, niters, sigma, nans, t
         np.testing.assert_allclose(flat_err[b], re_, rtol=1e-9, equal_nan=True)
 
 
+@pytest.fixture(scope="module")
+def emu_bad_bracket(tmp_path_factory):
+    """The same translation unit with the test hook that hands the dt median a STALE bracket from the second iteration
+    on: the restart path of block_nanmedian_fast (fresh sample, observer reset)."""
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = str(tmp_path_factory.mktemp("emu") / "libflatten_emu_bad.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + CUDA_INC, "-Wno-attributes", "-shared", "-fPIC",
+                           "-Wl,-Bsymbolic", "-DLKB_FS_TEST_BAD_BRACKET", "-o", out,
+                           os.path.join(HERE, "native", "flatten_emu_driver.cpp")])
+    return _bind(ctypes.CDLL(out))
+
+
+def test_flatten_v2_stale_bracket_restarts_on_the_emulator(emu_bad_bracket):
+    rng = np.random.default_rng(32)
+    t1, f1, fe1 = _lc(rng, 9000, gaps=3, outliers=40)
+    flat, flat_err, trend, status = _run(emu_bad_bracket, [t1], [f1], [fe1], None, 201, 2, 5, 3, 3)
+    assert (status == 0).all(), status
+    rf, _, rt = odet.flatten(t1, f1, fe1, window_length=201)
+    np.testing.assert_allclose(trend[0], rt, rtol=1e-9)
+    np.testing.assert_allclose(flat[0], rf, rtol=1e-9)
+
+
 def test_flatten_v2_sampling_select_on_the_emulator(emu):
-    """Light curves long enough (>= 4096 cadences) for the two-pass sampling median (select.cuh block_nanmedian_fast):
+    """Light curves long enough (>= 8192 cadences) for the two-pass sampling median (select.cuh block_nanmedian_fast):
     regular cadence (every dt within rounding of one value: the equal-to-pivot branches) and jittered cadence (many
-    distinct dt: the candidate buffer)."""
+    distinct dt: the candidate buffer); three iterations, so the dt median's bracket is carried over twice."""
     rng = np.random.default_rng(31)
     t1, f1, fe1 = _lc(rng, 9000, gaps=3, outliers=40)
-    t2, f2, fe2 = _lc(rng, 7000, gaps=2, outliers=30)
+    t2, f2, fe2 = _lc(rng, 9500, gaps=2, outliers=30)
     t2 = np.sort(t2 + rng.uniform(-2e-3, 2e-3, len(t2)))
     flat, flat_err, trend, status = _run(emu, [t1, t2], [f1, f2], [fe1, fe2], None, 201, 2, 5, 3, 3)
     assert (status == 0).all(), status
