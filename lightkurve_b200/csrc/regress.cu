@@ -381,12 +381,22 @@ rg_solve_kernel(int K, const double* __restrict__ prior_mu, const double* __rest
     }
     __syncthreads();
     const double pv = s_m[c * Ka + c];
-    for (int r = c + 1 + warp; r < K; r += nw) {
-      const double fct = s_m[r * Ka + c] / pv;
+    // two rows per warp and trip: their update chains (LDS, FMA, STS) are independent and interleave
+    for (int r = c + 1 + 2 * warp; r < K; r += 2 * nw) {
+      const bool two = r + 1 < K;
+      const double f0 = s_m[r * Ka + c] / pv, f1 = two ? s_m[(r + 1) * Ka + c] / pv : 0.0;
       __syncwarp();
-      for (int k = c + 1 + lane; k < Ka; k += 32) s_m[r * Ka + k] = fma(-fct, s_m[c * Ka + k], s_m[r * Ka + k]);
+      for (int k = c + 1 + lane; k < Ka; k += 32) {
+        const double p = s_m[c * Ka + k];
+        const double a0 = s_m[r * Ka + k], a1 = two ? s_m[(r + 1) * Ka + k] : 0.0;
+        s_m[r * Ka + k] = fma(-f0, p, a0);
+        if (two) s_m[(r + 1) * Ka + k] = fma(-f1, p, a1);
+      }
       __syncwarp();
-      if (lane == 0) s_m[r * Ka + c] = fct;          // the multiplier stays in place: s_m = [L \\ U | rhs]
+      if (lane == 0) {                               // the multipliers stay in place: s_m = [L \\ U | rhs]
+        s_m[r * Ka + c] = f0;
+        if (two) s_m[(r + 1) * Ka + c] = f1;
+      }
     }
     __syncthreads();
   }
@@ -632,8 +642,9 @@ __global__ void __launch_bounds__(512)
 rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __restrict__ y, int64_t N, int K,
                const double* __restrict__ coeff, double clip_sigma, RgWs ws, uint8_t* __restrict__ outlier,
                int model_ready) {
-  extern __shared__ __align__(16) double s_w[];
+  extern __shared__ __align__(16) double s_w[];       // [K] coefficients | FastSelSmem | FS_CAP + FS_SAMPLE candidates
   __shared__ SelSmem sm;
+  __shared__ FastBracket s_br;
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += blockDim.x) s_w[k] = coeff[(int64_t)b * K + k];
   __syncthreads();
@@ -646,21 +657,48 @@ rg_clip_kernel(const double* __restrict__ X, int x_batched, const double* __rest
   __syncthreads();
   for (int64_t i = threadIdx.x; i < N; i += blockDim.x) res[i] = used[i] ? (yb[i] - res[i]) : qnan;
   __syncthreads();
-  // astropy.stats.sigma_clip(residuals, sigma): maxiters=5, cenfunc=median, stdfunc=std
-  for (int it = 0; it < 5; ++it) {
-    long long cntv = 0;
-    const double med = block_nanmedian([&](int64_t i) { return res[i]; }, N, sm, &cntv);
-    if (cntv == 0) break;
-    const double sd = block_nanstd([&](int64_t i) { return res[i]; }, N, sm);
-    const double lo = med - sd * clip_sigma, hi = med + sd * clip_sigma;
+  // astropy.stats.sigma_clip(residuals, sigma): maxiters=5, cenfunc=median, stdfunc=std.  One pass over the residuals
+  // per round: the values outside the PREVIOUS round's bounds are struck out on the way into the median's partition
+  // pass (select.cuh: block_nanmedian_fast, bracket carried from round to round), whose observer also gathers the sums
+  // of the standard deviation.  (First version: 10-pass radix median + 2-pass std + clip pass per round, up to 65 sweeps
+  // of the light curve - a quarter of the device time of correct().)
+  FastSelSmem& fs = *reinterpret_cast<FastSelSmem*>(s_w + ((K + 1) & ~1));
+  double* cand = reinterpret_cast<double*>(&fs + 1);
+  if (threadIdx.x == 0) { fs.cand = cand; s_br.valid = false; }
+  __syncthreads();
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double lo_c = -inf, hi_c = inf;
+  for (int round = 0; round <= 5; ++round) {
     long long changed = 0;
-    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    long long sc = 0;
+    auto get = [&](int64_t i) {
       const double v = res[i];
-      if (v == v && (v < lo || v > hi)) { res[i] = qnan; changed++; }
-    }
+      if (v == v && (v < lo_c || v > hi_c)) { res[i] = qnan; changed++; return qnan; }   // (idempotent: counted once)
+      return v;
+    };
+    auto stats = [&](int64_t, double v, double lo, bool valid) {
+      if (valid && v == v) { const double d = v - lo; s1 += d; s2 = fma(d, d, s2); sc++; }
+    };
+    bool observed = false;
+    const double med = block_nanmedian_fast(get, N, sm, fs, -1, stats, &observed, &s_br,
+                                            [&]() { s1 = 0.0; s2 = 0.0; sc = 0; });
     const long long tot = block_sum_ll(changed, sm.redll);
-    if (tot == 0) break;
+    if (round > 0 && tot == 0) break;             // the last clip removed nothing: converged
+    if (round == 5 || !(med == med)) break;       // five clips done / nothing left
+    double sd;
+    if (observed) {
+      const double t1 = block_sum(s1, sm.red), t2 = block_sum(s2, sm.red);
+      const long long tc = block_sum_ll(sc, sm.redll);
+      const double md = t1 / (double)tc, var = t2 / (double)tc - md * md;
+      sd = (var == var) ? sqrt(var > 0.0 ? var : 0.0) : qnan;
+    } else {
+      sd = block_nanstd([&](int64_t i) { return res[i]; }, N, sm);
+    }
+    lo_c = med - sd * clip_sigma;
+    hi_c = med + sd * clip_sigma;
   }
+  __syncthreads();
   for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
     const double v = res[i];
     if (!(v == v)) om[i] = 1;          // .mask includes the cadences that were NaN on entry
@@ -791,6 +829,13 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
     int gx = (4 * sm_count() + (int)gemm_grid.y - 1) / (int)gemm_grid.y;
     gemm_grid.x = (unsigned)(gx < 1 ? 1 : (gx > nstage ? nstage : gx));
   }
+  const size_t clip_smem = sizeof(double) * (size_t)((K + 1) & ~1) + sizeof(FastSelSmem) +
+                           sizeof(double) * (size_t)(FS_CAP + FS_SAMPLE);
+  static size_t clip_attr = 0;
+  if (clip_smem > clip_attr) {
+    LKB_CUDA_CHECK(cudaFuncSetAttribute(rg_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clip_smem));
+    clip_attr = clip_smem;
+  }
   for (int it = 0; it < niters; ++it) {
     rg_rows_kernel<<<B, 256, 0, st>>>(d_cm, o_om, d_fe, N, it == 0 ? 1 : 0, ws);
     LKB_LAUNCH_CHECK();
@@ -845,8 +890,7 @@ int regress(const double* X, int x_batched, const double* y, const double* flux_
       rg_model_mma_kernel<<<gemm_grid, 256, sizeof(RgeSmem), st>>>(d_X, N, K, B, o_c, ws.resid);
       LKB_LAUNCH_CHECK();
     }
-    rg_clip_kernel<<<B, 512, K * sizeof(double), st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om,
-                                                       gemm_model ? 1 : 0);
+    rg_clip_kernel<<<B, 512, clip_smem, st>>>(d_X, x_batched, d_y, N, K, o_c, clip_sigma, ws, o_om, gemm_model ? 1 : 0);
     LKB_LAUNCH_CHECK();
   }
   if (gemm_model) {
