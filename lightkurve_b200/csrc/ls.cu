@@ -1113,7 +1113,21 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     cudaEvent_t* ev;
     int nev;
     LKB_TRY(pipe_streams_get(&s_h2d, &s_d2h, &ev, &nev));
-    const int nchunk = (B + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    // chunk boundaries: the tensor path in tiles of PIPE_CHUNK light curves; the NUFFT path ramps up (64, 64, 128, then
+    // PIPE_CHUNK) - its kernels are short, so the time before the first power rows can start down the link (upload of
+    // chunk 0 + its kernels) is what the end-to-end step adds to the 7.5 ms the download takes by itself
+    int c_lo[520];
+    int nchunk = 0;
+    {
+      static const int ramp[3] = {64, 64, 128};
+      int b0 = 0;
+      while (b0 < B && nchunk < 518) {
+        const int sz = (use_nufft && nchunk < 3 && !getenv("LKB_LS_NO_RAMP")) ? ramp[nchunk] : PIPE_CHUNK;
+        c_lo[nchunk++] = b0;
+        b0 += sz;
+      }
+      c_lo[nchunk] = B;
+    }
     // chunks alternate between two compute streams (and two workspace sets): the last, partly filled wave of one
     // chunk's tensor kernel (782 CTAs on 148 SMs) overlaps the first wave of the next chunk
     cudaStream_t cs[2] = {st, st};
@@ -1128,7 +1142,7 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
     LKB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, ev[0], 0));
     if (cs[1] != st) LKB_CUDA_CHECK(cudaStreamWaitEvent(cs[1], ev[0], 0));
     for (int c = 0; c < nchunk; ++c) {
-      const int b_lo = c * PIPE_CHUNK, nb = min(PIPE_CHUNK, B - b_lo);
+      const int b_lo = c_lo[c], nb = c_lo[c + 1] - b_lo;
       cudaStream_t sc = cs[c & 1];
       cudaEvent_t e_in = ev[1 + (2 * c) % (nev - 1)], e_out = ev[1 + (2 * c + 1) % (nev - 1)];
       LKB_CUDA_CHECK(cudaMemcpyAsync(d_ystage + (size_t)b_lo * N * ysz, (const unsigned char*)y + (size_t)b_lo * N * ysz,
@@ -1157,14 +1171,14 @@ int ls_power_shared(const double* t, const void* y, int y_dtype, int B, int64_t 
       // (ADVICE.md, round 1).  One chunk late, the blocking copy runs while the next chunk computes; page-locked
       // destinations are asynchronous either way.
       if (c > 0) {
-        const int p_lo = (c - 1) * PIPE_CHUNK, p_nb = min(PIPE_CHUNK, B - p_lo);
+        const int p_lo = c_lo[c - 1], p_nb = c_lo[c] - p_lo;
         LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)p_lo * F, d_pow + (size_t)p_lo * F, (size_t)p_nb * F * sizeof(float),
                                        cudaMemcpyDeviceToHost, s_d2h));
       }
       LKB_CUDA_CHECK(cudaStreamWaitEvent(s_d2h, e_out, 0));
     }
     {
-      const int p_lo = (nchunk - 1) * PIPE_CHUNK, p_nb = min(PIPE_CHUNK, B - p_lo);
+      const int p_lo = c_lo[nchunk - 1], p_nb = B - p_lo;
       LKB_CUDA_CHECK(cudaMemcpyAsync(power + (size_t)p_lo * F, d_pow + (size_t)p_lo * F, (size_t)p_nb * F * sizeof(float),
                                      cudaMemcpyDeviceToHost, s_d2h));
     }
