@@ -851,9 +851,10 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
       LKB_TRY(ws_get_t<double>(ws_alt ? WS_X4 : WS_X3, (size_t)B * F_low * 2, &acc));
       LKB_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (size_t)B * F_low * 2, st));
       const int groups = (B + 15) / 16;
-      int S = (600 + groups - 1) / groups;                     // ~2 waves of CTAs whatever the batch size
-      S = S < 1 ? 1 : (S > 64 ? 64 : S);
-      const int64_t slice = (((N + S - 1) / S + 255) / 256) * 256;
+      // cadence slices of a FIXED length: the partition of a light curve's sums must not depend on the batch size, or
+      // its low rows would change in the last bit with the chunk of the host-mode pipeline it happens to land in
+      // (bitwise permutation invariance is asserted at full size)
+      const int64_t slice = 2048;
       LKB_LAUNCH(dim3((unsigned)groups, (unsigned)((N + slice - 1) / slice)), 256, st, nufft2_lowrows_kernel)(
           pl.lowD, N, pl.Npad, d_yc, ystride, B, (int)F_low, slice, acc);
       LKB_LAUNCH_CHECK();
