@@ -2,11 +2,9 @@
 
 Status: the arithmetic of every kernel is verified on the CPU (tests/test_nufft_core.py runs the same
 `__host__ __device__` functions through a g++ harness) and the whole translation unit runs on a CUDA-on-CPU layer
-against the oracle (tests/test_nufft_emulated.py); it was written after round 1's GPU budget was spent and HAS NOT
-RUN ON HARDWARE YET - hence xfail(strict=False):
-a failure here is reported as xfailed, a pass as xpassed, and neither hides the verified tests.  The work runs
-in a child process so that a device fault cannot poison the CUDA context of the rest of the suite.  The file
-name sorts last on purpose."""
+against the oracle (tests/test_nufft_emulated.py).  Written after round 1's GPU budget was spent (then marked xfail);
+it has passed on hardware in every run of round 2, so the marks are gone.  The work runs in a child process so that a
+device fault cannot poison the CUDA context of the rest of the suite.  The file name sorts last on purpose."""
 import os
 import sys
 
@@ -145,7 +143,6 @@ def _run_child(target):
     return res
 
 
-@pytest.mark.xfail(strict=False, reason="CUDA glue of the ragged NUFFT path not validated on hardware yet (round 1)")
 def test_ragged_nufft_path_matches_direct_kernel_and_oracle():
     res = _run_child(_worker_ragged)
     print("ragged NUFFT path, worst tolerance excess per case:", res)
@@ -155,7 +152,6 @@ def test_ragged_nufft_path_matches_direct_kernel_and_oracle():
     assert res["fallback ok"] is True
 
 
-@pytest.mark.xfail(strict=False, reason="CUDA glue of the NUFFT path not validated on hardware yet (round 1)")
 def test_nufft_path_matches_oracle_and_simt_kernel():
     import queue
     import time
