@@ -869,7 +869,9 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
       LKB_LAUNCH(blocks_for(B, 256), 256, st, nufft2_flag_kernel)(d_peak, d_absmax, B, (float)N, esc_ratio, d_list, d_list + 1,
                                                                 pl.esc_total);
       LKB_LAUNCH_CHECK();
-      const int cap = std::min(B, 256), gy = std::min(cap, 32);
+      // one round for batches up to 1024 light curves (double-precision buffers for all of them: 5 GB at config 2,
+      // from the grow-only pool); larger batches go round by round
+      const int cap = std::min(B, 1024), gy = std::min(cap, 32);
       const size_t lowlen = F_low > 0 ? (size_t)F_low * 4 + (size_t)cap * F_low * 2 + cap : 0;
       double *Gbuf = nullptr;
       double2* Td = nullptr;
