@@ -1087,15 +1087,21 @@ nufft_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict_
 __global__ void __launch_bounds__(256)
 nufft2_spread_ragged_kernel(const Cad* __restrict__ cad, const float* __restrict__ y, const int64_t* __restrict__ off,
                             const int64_t* __restrict__ poff, int w, float beta, int p, int ptc, int n1max,
-                            float2* __restrict__ G) {
+                            float2* __restrict__ G, const double* __restrict__ t, double df) {
   const int64_t cells = (int64_t)n1max << V2_PB;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= cells) return;
   const int64_t M = (int64_t)1 << p, m = 2 * v2_zcell_of(e, ptc, n1max);
   const int64_t lc = blockIdx.y, po = poff[lc], n = off[lc + 1] - off[lc];
   float2 v;
-  v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
-  v.y = nufft::spread_cell_search(m + 1, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
+  if (t) {                       // kernel weights in FP64 from the time stamps (nufft_core.h: spread_cell_search_acc)
+    const double dfM = df * (double)M;
+    v.x = nufft::spread_cell_search_acc(m, cad + po, t + po, n, y ? y + po : nullptr, w, (double)beta, dfM, M);
+    v.y = nufft::spread_cell_search_acc(m + 1, cad + po, t + po, n, y ? y + po : nullptr, w, (double)beta, dfM, M);
+  } else {
+    v.x = nufft::spread_cell_search(m, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
+    v.y = nufft::spread_cell_search(m + 1, cad + po, n, y ? y + po : nullptr, 1.0f, w, beta, M);
+  }
   G[lc * cells + e] = v;
 }
 
@@ -1257,6 +1263,8 @@ int ls_nufft_ragged_v2(const double* d_t, const float* d_y, const int64_t* d_off
   LKB_LAUNCH(blocks_for(2 * (k0 + F), 128), 128, st, nufft_deconv_kernel)(0, 2 * (k0 + F), M2, w, (double)beta, gl, dec2);
   LKB_LAUNCH_CHECK();
 
+  // kernel weights in FP64 from the time stamps (default; LKB_NUFFT_RAGGED_W32=1: the fp32 form, for A/B timing)
+  const double* t_acc = getenv("LKB_NUFFT_RAGGED_W32") ? nullptr : d_t;
   const int ptc = V2_LOG_TILE - (p - 1 - V2_PB), ptc2 = V2_LOG_TILE - (p2 - 1 - V2_PB);
   const int nk2 = (int)((k0 + F) >> (p - 1 - V2_PB)) + 1, nk2w = (int)((2 * (k0 + F)) >> (p2 - 1 - V2_PB)) + 1;
   prof_begin(st);
@@ -1269,12 +1277,12 @@ int ls_nufft_ragged_v2(const double* d_t, const float* d_y, const int64_t* d_off
     const int64_t F_low_max = nlow < 0.0 ? 0 : (nlow > (double)F ? F : (int64_t)nlow);
     // window terms: unit strengths on the 2x finer grid (modes kk and 2 kk), then the flux
     LKB_LAUNCH(dim3(blocks_for((int64_t)cells2, 256), (unsigned)Bg), 256, st, nufft2_spread_ragged_kernel)(
-        cad2, nullptr, off_g, po_g, w, beta, p2, ptc2, n1max2, G);
+        cad2, nullptr, off_g, po_g, w, beta, p2, ptc2, n1max2, G, t_acc, df);
     LKB_LAUNCH_CHECK();
     LKB_TRY(v2_cols(G, Tw, p2, n1max2, Bg, tb2, st));
     LKB_TRY(v2_rows(Tw, p2, Bg, tb2, nullptr, Zwn, nk2w, st));
     LKB_LAUNCH(dim3(blocks_for((int64_t)cells, 256), (unsigned)Bg), 256, st, nufft2_spread_ragged_kernel)(
-        cad, d_y, off_g, po_g, w, beta, p, ptc, n1max, G);
+        cad, d_y, off_g, po_g, w, beta, p, ptc, n1max, G, t_acc, df);
     LKB_LAUNCH_CHECK();
     LKB_TRY(v2_cols(G, T, p, n1max, Bg, tb, st));
     LKB_TRY(v2_rows(T, p, Bg, tb, nullptr, Zn, nk2, st));

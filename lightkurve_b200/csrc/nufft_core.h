@@ -146,6 +146,36 @@ LKB_HD float spread_cell_search(int64_t m, const Cad* cad, int64_t n, const floa
   return acc;
 }
 
+// The same with the kernel weight evaluated in FP64 from the time stamp itself (x = dfM t + shift, exactly as cad_entry
+// places the cadence) and rounded once.  The fp32 form above carries ~1e-6 relative weight errors (fp32 offsets, expf):
+// a perturbation of the kernel SHAPE the deconvolution does not undo, which leaks a strong line from above the
+// frequency grid into the band at ~1e-8 of its amplitude - 7x the rounding noise of the transform itself (emulated
+// ragged light curve, flux excursion 600x its in-band peak: rms error 0.085 of the tolerance against 0.012).
+LKB_HD float es_eval_acc(double z, double beta) {
+  const double q = 1.0 - z * z;
+  return q > 0.0 ? (float)exp(beta * (sqrt(q) - 1.0)) : 0.0f;
+}
+LKB_HD float spread_cell_search_acc(int64_t m, const Cad* cad, const double* t, int64_t n, const float* y, int w,
+                                    double beta, double dfM, int64_t M) {
+  float acc = 0.0f;
+  const double inv_half = 2.0 / (double)w, shift = (double)grid_shift(w);
+  const int64_t L = table_len(M, w);
+  for (int wrap = 0; wrap < 2; ++wrap) {
+    if (wrap && m > 2 * (int64_t)w + 2) break;
+    const int64_t mm = m + (int64_t)wrap * M;
+    if (mm + 1 >= L) break;
+    int64_t lo_c = mm - w + 1;
+    if (lo_c < 0) lo_c = 0;
+    const int32_t a = first_ge_entry(lo_c, cad, n), b = first_ge_entry(mm + 1, cad, n);
+    for (int32_t i = a; i < b; ++i) {
+      const double x = dfM * t[i] + shift;
+      const float ph = es_eval_acc(((double)mm - x) * inv_half, beta);
+      acc += y ? ph * y[i] : ph;
+    }
+  }
+  return acc;
+}
+
 // ---- FFT ------------------------------------------------------------------------------------------
 LKB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
