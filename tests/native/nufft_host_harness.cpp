@@ -42,6 +42,12 @@ extern "C" {
 
 void harness_set_chain(int on) { g_chain = on != 0; }
 
+// grid-size and kernel rules of nufft_core.h (the library's fine_log2 / kernel_width / es_beta call these)
+int harness_fine_grid_log2(int64_t kmax_plus_1, double sigma_min) { return fine_grid_log2(kmax_plus_1, sigma_min); }
+double harness_grid_sigma(int p, int64_t kmax_plus_1) { return grid_sigma(p, kmax_plus_1); }
+int harness_es_width(double sigma) { return es_width(sigma); }
+double harness_es_beta(int w, double sigma) { return es_beta(w, sigma); }
+
 int harness_fft(const float* in, int p, float* out) {
   fft_full(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), p);
   return 0;

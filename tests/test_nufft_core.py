@@ -269,3 +269,31 @@ def test_twiddle_product_tree_variant(harness):
         assert err <= 3e-7 * np.abs(yd).sum()
     finally:
         harness.harness_set_chain(0)
+
+
+def test_grid_size_and_kernel_rules(harness):
+    """The fine-grid / kernel-parameter rules (nufft_core.h) the library uses, and the copy of the grid-size rule in
+    bench.py's byte model: smallest power of two with an upsampling factor >= sigma_min over the highest mode; width
+    10 and beta = 2.30 w at sigma = 2 (the validated setting), wider kernels below."""
+    import ctypes
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    harness.harness_fine_grid_log2.argtypes = [ctypes.c_int64, ctypes.c_double]
+    harness.harness_grid_sigma.argtypes = [ctypes.c_int, ctypes.c_int64]
+    harness.harness_grid_sigma.restype = ctypes.c_double
+    harness.harness_es_width.argtypes = [ctypes.c_double]
+    harness.harness_es_beta.argtypes = [ctypes.c_int, ctypes.c_double]
+    harness.harness_es_beta.restype = ctypes.c_double
+    os.environ.pop("LKB_NUFFT_SIGMA", None)
+    for kmax in (17, 261, 3501, 7002, 14001, 100001, 100002, 131072, 131073, 5000000):
+        p = harness.harness_fine_grid_log2(kmax, 2.0)
+        assert (1 << p) >= 4 * kmax and ((1 << (p - 1)) < 4 * kmax or p == 4)
+        assert p == bench._nufft_fine_log2(kmax)                       # the byte model sizes the same grid
+        assert 2.0 <= harness.harness_grid_sigma(p, kmax) <= 4.0
+        p_low = harness.harness_fine_grid_log2(kmax, 1.25)
+        assert p_low in (p, p - 1) and (1 << p_low) >= 2.5 * kmax
+    assert harness.harness_fine_grid_log2(100001, 2.0) == 19 and harness.harness_fine_grid_log2(100001, 1.25) == 18
+    assert harness.harness_es_width(2.0) == 10 and harness.harness_es_width(1.31) == 14 and harness.harness_es_width(1.25) == 16
+    assert abs(harness.harness_es_beta(10, 2.0) - 23.0) < 0.01        # 2.30 w
+    assert harness.harness_es_beta(14, 1.31) < harness.harness_es_beta(14, 2.0)
