@@ -871,7 +871,9 @@ int ls_nufft_run(const double* d_t, int64_t N, const float* d_yc, int64_t ystrid
       LKB_LAUNCH_CHECK();
       // one round for batches up to 1024 light curves (double-precision buffers for all of them: 5 GB at config 2,
       // from the grow-only pool); larger batches go round by round
-      const int cap = std::min(B, 1024), gy = std::min(cap, 32);
+      int cap_max = 1024;
+      if (const char* e = getenv("LKB_NUFFT_ESCALATE_CAP")) cap_max = std::max(1, atoi(e));     // (tests: several rounds)
+      const int cap = std::min(B, cap_max), gy = std::min(cap, 32);
       const size_t lowlen = F_low > 0 ? (size_t)F_low * 4 + (size_t)cap * F_low * 2 + cap : 0;
       double *Gbuf = nullptr;
       double2* Td = nullptr;

@@ -288,3 +288,31 @@ def test_precision_escalation_on_the_emulator(emu, monkeypatch):
     # the double-precision pass is what lowered it (what is left is the fp32 rounding of the centred flux itself)
     assert ex_on[0] < ex_off[0] and rms_on[0] < 0.6 * rms_off[0]
     assert ex_on[1] == ex_off[1] and rms_on[1] == rms_off[1]         # the other light curve's row is untouched
+
+
+@pytest.mark.parametrize("cap", [None, "16"])
+def test_escalation_pass_strides_over_more_light_curves_than_grid_rows(emu, monkeypatch, cap):
+    """40 light curves, ALL listed (threshold ~0): the double-precision list kernels are launched with 32 grid rows
+    and stride over the device-side count, so 8 of their blocks transform two light curves one after the other through
+    the same shared-memory tile.  Every row must match the oracle (it is the double-precision result that is kept).
+    cap = 16: three rounds of at most 16 listed light curves each (the path of batches above 1024 light curves)."""
+    monkeypatch.setenv("LKB_NUFFT_ESCALATE", "1e-6")
+    if cap:
+        monkeypatch.setenv("LKB_NUFFT_ESCALATE_CAP", cap)
+    B, N, F = 40, 500, 3500
+    t, trel, Y, ycp, Npad, ysum, absmax, freq, f0, df = _shared_inputs(77, N, F, B, 5.0, 1)
+    low = freq * trel[-1] <= 2.0
+    F_low = int(low.sum()) + 1
+    rot, rot2 = _window_rows(trel, freq, F_low)
+    power = np.zeros((B, F), np.float32)
+    rc = emu.emu_nufft_shared(trel.ctypes.data, N, ycp.ctypes.data, Npad, ysum.ctypes.data, absmax.ctypes.data, B,
+                              freq.ctypes.data, F, f0, df, rot.ctypes.data, rot2.ctypes.data, F_low, 2,
+                              2.0 / (N * 5.0 * df), power.ctypes.data)
+    assert rc == 0, emu.emu_last_error()
+    assert emu.emu_last_escalated() == B
+    worst = 0.0
+    for b in range(B):
+        ref = np.sqrt(ols.ls_slow_psd(t, Y[b], freq)) * np.sqrt(4.0 / N)
+        worst = max(worst, float(_excess(power[b].astype(np.float64), ref).max()))
+    print("worst tolerance excess over 40 escalated light curves:", worst)
+    assert worst < 0.1
